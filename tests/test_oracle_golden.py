@@ -1,0 +1,39 @@
+"""The oracle restatement (oracle/vlnce.py + oracle/hb017.py) must reproduce the
+golden vectors frozen from the unmodified reference (oracle/make_golden.py)."""
+import os
+import warnings
+
+import pytest
+import torch
+
+from oracle import cases, vlnce
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+warnings.filterwarnings("ignore")
+
+
+def load(name):
+    return torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_oracle_matches_reference_golden(name):
+    gold = load(name)
+    got = cases.run_case(vlnce, name, aux=vlnce.AuxLosses)
+    for k, v in got.items():
+        g = gold[k]
+        if v.dtype in (torch.int64, torch.uint8):
+            assert torch.equal(v, g), k
+        else:
+            # same torch ops on the same CPU image: tight; loosened only for other hosts' BLAS
+            torch.testing.assert_close(v, g, rtol=2e-4, atol=2e-5, msg=lambda m: f"{name}:{k}: {m}")
+    assert set(k for k in gold if not k.startswith("_")) == set(got)
+
+
+def test_seeded_inputs_checksum():
+    """Weights / inputs regenerate bit-identically from the seeds."""
+    from oracle.make_golden import checksum
+
+    for name in ("cma_act", "cma_train_features"):
+        gold = load(name)
+        assert torch.equal(checksum(cases.CASES[name]), gold["_checksum"]), name

@@ -1,0 +1,32 @@
+"""Pin the oracle against the UNMODIFIED reference files (build container only —
+/root/reference does not exist on the GPU box, where this module skips)."""
+import warnings
+
+import pytest
+import torch
+
+from oracle import cases, reference_import, vlnce
+
+pytestmark = pytest.mark.skipif(not reference_import.available(),
+                                reason="/root/reference not present")
+warnings.filterwarnings("ignore")
+
+
+@pytest.mark.parametrize("name", ["cma_act_bntrain", "cma_train_features", "seq2seq_act"])
+def test_oracle_equals_reference_live(name):
+    ref = reference_import.load()
+    a = cases.run_case(ref, name, aux=ref.AuxLosses)
+    b = cases.run_case(vlnce, name, aux=vlnce.AuxLosses)
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]) or torch.allclose(a[k], b[k], rtol=1e-6, atol=1e-7), k
+
+
+def test_state_dict_keys_match_reference():
+    ref = reference_import.load()
+    for name in ("cma_act", "seq2seq_act"):
+        case = cases.CASES[name]
+        r = cases.build_policy(ref, case).state_dict()
+        o = cases.build_policy(vlnce, case).state_dict()
+        assert list(r) == list(o)
+        assert all(r[k].shape == o[k].shape for k in r)

@@ -1,0 +1,142 @@
+"""Synthetic observation batches of the shapes BASELINE.json quotes the metric on
+(the simulator is stubbed: north_star).  Shapes/dtypes follow what the reference
+feeds ``policy.act`` / ``_update_agent``:
+
+* ``rgb``  uint8 ``(R,H,W,3)`` 0..255, ``depth`` f32 ``(R,H,W,1)`` 0..1 — sensor
+  layout, ``habitat_extensions/config/vlnce_task.yaml`` + ``resnet_encoders.py:198``;
+* ``instruction`` int64 ``(R,L)`` token ids, 0 = PAD (``instruction_encoder.py:70-78``);
+* time-major ``(T*N, ...)`` row layout, ``masks`` zero on the first row-block,
+  inflection weights — ``dagger_trainer.py:39-114,199-211``;
+* ``progress`` f32 ``(R,1)`` (``habitat_extensions/sensors.py:72,85-87``).
+
+Generated on the CPU with a seeded ``torch.Generator`` so the oracle and the CUDA
+path see bit-identical inputs.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+
+def make_instruction(gen, rows: int, length: int = 80, vocab: int = 2504,
+                     min_len: int = 40) -> torch.Tensor:
+    ids = torch.randint(1, vocab, (rows, length), generator=gen, dtype=torch.int64)
+    lens = torch.randint(min(min_len, length), length + 1, (rows,), generator=gen)
+    pos = torch.arange(length).unsqueeze(0)
+    return ids * (pos < lens.unsqueeze(1))
+
+
+def make_rxr_instruction(gen, rows: int, length: int = 512, dim: int = 768,
+                         min_len: int = 256) -> torch.Tensor:
+    x = torch.randn(rows, length, dim, generator=gen)
+    lens = torch.randint(min(min_len, length), length + 1, (rows,), generator=gen)
+    pos = torch.arange(length).view(1, length, 1)
+    return x * (pos < lens.view(rows, 1, 1))
+
+
+def make_act_batch(seed: int, n: int, hw: int = 256, rgb_hw: int | None = None,
+                   length: int = 80, hidden: int = 512, layers: int = 2,
+                   vocab: int = 2504, num_actions: int = 4,
+                   fresh: bool = False) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, torch.Tensor, torch.Tensor]:
+    """One ``policy.act`` call: (observations, rnn_states, prev_actions, masks)."""
+    gen = torch.Generator().manual_seed(seed)
+    rgb_hw = rgb_hw or hw
+    obs = {
+        "rgb": torch.randint(0, 256, (n, rgb_hw, rgb_hw, 3), generator=gen, dtype=torch.uint8),
+        "depth": torch.rand(n, hw, hw, 1, generator=gen),
+        "instruction": make_instruction(gen, n, length, vocab),
+    }
+    if fresh:
+        h = torch.zeros(n, layers, hidden)
+        prev = torch.zeros(n, 1, dtype=torch.int64)
+        masks = torch.zeros(n, 1, dtype=torch.uint8)
+    else:
+        h = torch.randn(n, layers, hidden, generator=gen) * 0.5
+        prev = torch.randint(0, num_actions, (n, 1), generator=gen, dtype=torch.int64)
+        masks = (torch.rand(n, 1, generator=gen) > 0.2).to(torch.uint8)
+    return obs, h, prev, masks
+
+
+def make_train_batch(seed: int, t: int, n: int, hw: int = 256, rgb_hw: int | None = None,
+                     length: int = 80, vocab: int = 2504, num_actions: int = 4,
+                     coef: float = 3.2, ragged: bool = True, features: bool = False):
+    """One ``_update_agent`` call in the collate_fn layout: returns
+    (observations, prev_actions (T*N,1), not_done_masks (T*N,1) u8,
+    corrected_actions (T,N) i64, weights (T,N) f32)."""
+    gen = torch.Generator().manual_seed(seed)
+    rgb_hw = rgb_hw or hw
+    r = t * n
+    # the same instruction for all T rows of a trajectory (dagger_trainer.py:342-362)
+    instr = make_instruction(gen, n, length, vocab).unsqueeze(0).expand(t, n, length).reshape(r, length)
+    obs: Dict[str, torch.Tensor] = {"instruction": instr.contiguous()}
+    if features:  # DAgger caches frozen-CNN features (dagger_trainer.py:300-314)
+        obs["rgb_features"] = torch.rand(r, 2048, 4, 4, generator=gen)
+        obs["depth_features"] = torch.rand(r, 128, 4, 4, generator=gen)
+    else:
+        obs["rgb"] = torch.randint(0, 256, (r, rgb_hw, rgb_hw, 3), generator=gen, dtype=torch.uint8)
+        obs["depth"] = torch.rand(r, hw, hw, 1, generator=gen)
+    obs["progress"] = torch.rand(r, 1, generator=gen)
+    actions = torch.randint(0, num_actions, (t, n), generator=gen, dtype=torch.int64)
+    lens = torch.randint(max(1, t // 2), t + 1, (n,), generator=gen) if ragged else torch.full((n,), t)
+    lens[0] = t
+    valid = torch.arange(t).unsqueeze(1) < lens.unsqueeze(0)  # (T,N)
+    infl = torch.ones(t, n, dtype=torch.bool)
+    infl[1:] = actions[1:] != actions[:-1]
+    weights = torch.where(infl, torch.tensor(coef), torch.tensor(1.0)) * valid
+    actions = actions * valid
+    prev = torch.zeros(t, n, dtype=torch.int64)
+    prev[1:] = actions[:-1]
+    prev = prev * valid
+    masks = torch.ones(t, n, dtype=torch.uint8)
+    masks[0] = 0
+    return obs, prev.view(-1, 1), masks.view(-1, 1), actions, weights.float()
+
+
+def seeded_state_dict(module: torch.nn.Module, seed: int) -> Dict[str, torch.Tensor]:
+    """Deterministic "trained-like" weights for any of the policies, a pure function
+    of (parameter names, shapes, seed): plain ``torch.randn`` / ``torch.rand`` on a
+    seeded CPU generator (no LAPACK-dependent initialisers), so the build container,
+    the GPU box and the golden fixtures all regenerate bit-identical tensors.
+
+    There is no network for checkpoints (``resnet_encoders.py:136`` pretrained
+    ImageNet weights, ``default.py:247-250`` DD-PPO depth weights), so every parity
+    test and the benchmark use these.  Scales keep activations O(1) through the
+    16 residual blocks (last norm of each block damped) and give the action head a
+    usable logit spread (SURVEY hard-part 2: orthogonal gain 0.01 leaves ~1e-2)."""
+    gen = torch.Generator().manual_seed(seed)
+    out: Dict[str, torch.Tensor] = {}
+    sd = module.state_dict()
+    for name, ref in sd.items():
+        shape = tuple(ref.shape)
+        leaf = name.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            out[name] = torch.zeros_like(ref)
+            continue
+        if name.endswith("_scale"):
+            out[name] = ref.clone()
+            continue
+        if leaf == "running_mean":
+            t = torch.randn(shape, generator=gen) * 0.1
+        elif leaf == "running_var":
+            t = torch.rand(shape, generator=gen) + 0.5
+        elif ref.dim() == 1 and leaf == "weight":  # norm scale
+            damp = (".bn3." in name or name.endswith("convs.7.weight")
+                    or ".downsample.1." in name or name.endswith("convs.4.weight"))
+            t = torch.rand(shape, generator=gen) * (0.2 if damp else 1.0) + (0.2 if damp else 0.5)
+        elif ref.dim() == 1 or "bias" in leaf:
+            t = torch.randn(shape, generator=gen) * 0.05
+        elif "embedding" in name:
+            t = torch.randn(shape, generator=gen) * 0.5
+            if name.endswith("embedding_layer.weight"):
+                t[0] = 0  # PAD row (instruction_encoder.py:41-45 padding_idx=0)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            gain = 2.0 if ref.dim() == 4 else 1.0
+            if "action_distribution" in name:
+                gain = 4.0
+            t = torch.randn(shape, generator=gen) * (gain / fan_in) ** 0.5
+        out[name] = t.to(ref.dtype)
+    return out
