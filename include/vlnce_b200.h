@@ -1,0 +1,162 @@
+/* vlnce_b200 — C ABI of the B200 (sm_100a) kernels behind the VLN-CE policy hot path.
+ *
+ * Drop-in boundary: these entry points are what the reference's Python policy classes
+ * (vlnce_baselines/models/{policy,cma_policy,seq2seq_policy}.py, encoders/*.py) and the
+ * per-step loss (common/base_il_trainer.py:134-180) bind through ctypes in place of their
+ * torch/cuDNN/cuBLAS calls (INTEGRATION.md shows the binding).  Each function cites the
+ * reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch types.  All pointers are DEVICE pointers unless noted.
+ *   - the caller owns every tensor and workspace; the library allocates no device memory
+ *     and keeps no reference after return (only cached function attributes).
+ *   - every call enqueues on `stream` and returns immediately; 0 = ok, <0 = bad argument,
+ *     >=1000 = 1000 + cudaError_t.  vlnce_last_error() gives the message (thread-local).
+ *   - activations are channels-last: images NHWC, sequences (rows, positions, channels).
+ *   - dtype codes: VLNCE_F32, VLNCE_BF16, VLNCE_U8, VLNCE_I64.
+ */
+#ifndef VLNCE_B200_H_
+#define VLNCE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define VLNCE_OK 0
+#define VLNCE_ERR_INVALID_ARGUMENT (-1)
+#define VLNCE_ERR_NO_DRIVER (-2)
+#define VLNCE_ERR_CUDA_BASE 1000
+
+#define VLNCE_F32 0
+#define VLNCE_BF16 1
+#define VLNCE_U8 2
+#define VLNCE_I64 3
+
+/* ---- library ---------------------------------------------------------------------- */
+const char* vlnce_version(void);
+const char* vlnce_last_error(void);
+/* number of kernel launches issued through this library since process start */
+long long vlnce_launch_count(void);
+
+/* ---- convolution trunks ------------------------------------------------------------ */
+/* Implicit-GEMM NHWC conv on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM):
+ *   y = act(scale[k] * conv(x, w) + shift[k] (+ residual)).
+ * x (N,H,W,C) bf16, w (K,R,S,C) bf16, y (N,P,Q,K) bf16|f32, residual like y in bf16 or NULL,
+ * scale/shift (K) f32 or both NULL (raw conv).  C % 32 == 0, K % 32 == 0.  block_n: 0 = auto.
+ * Replaces torch.nn.Conv2d + folded BatchNorm2d/ReLU/residual in torchvision ResNet
+ * (resnet_encoders.py:198-199) and the convs of the DD-PPO GroupNorm ResNet
+ * (resnet_encoders.py:95; habitat_baselines v0.1.7 rl/ddppo/policy/resnet.py). */
+int vlnce_conv2d_bf16(const void* x, const void* w, const float* scale, const float* shift,
+                      const void* residual, void* y, int y_dtype, int N, int H, int W, int C,
+                      int K, int R, int S, int stride, int pad, int relu, int block_n,
+                      cudaStream_t stream);
+
+/* Same contract on CUDA cores with fp32 accumulation and arbitrary C/K: the fp32-exact mode
+ * and the on-device cross-check of the tensor-core tiles.  dtypes per tensor. */
+int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w_dtype, const float* scale,
+                     const float* shift, const void* residual, int res_dtype, void* y,
+                     int y_dtype, int N, int H, int W, int C, int K, int R, int S, int stride,
+                     int pad, int relu, cudaStream_t stream);
+
+/* RGB stem operand: x (N,H,W,3) u8|f32 0..255 -> im2col rows (N*P*Q, 192) bf16 of the 7x7/2
+ * pad-3 window, K index (r*7+s)*3+c, zero padded 147..191 (resnet_encoders.py:182,198:
+ * permute + /255 + conv1; the /255 and optional mean/std live in the folded scale/shift). */
+int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int N, int H, int W,
+                          cudaStream_t stream);
+/* Depth stem operand: depth (N,H,W,1) f32 -> avg_pool2d(2) -> 7x7/2 pad-3 im2col rows
+ * (N*P*Q, 64) bf16, K index r*7+s, zero padded 49..63 (habitat_baselines v0.1.7
+ * ResNetEncoder.forward: permute, avg_pool2d(2), backbone.conv1). */
+int vlnce_im2col_depth_stem(const float* x, void* a, int N, int H, int W, cudaStream_t stream);
+/* avg_pool2d(2) on (N,H,W,C) f32 -> (N,H/2,W/2,C) f32 (fp32-exact mode of the depth stem) */
+int vlnce_avgpool2x2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);
+/* MaxPool2d(3, stride 2, pad 1) NHWC */
+int vlnce_maxpool3x3s2(const void* x, void* y, int dtype, int N, int H, int W, int C,
+                       cudaStream_t stream);
+/* GroupNorm statistics of raw conv output x (N, HW, C): writes per-(n,c) scale/shift with the
+ * affine folded: scale = rstd*gamma, shift = beta - mean*rstd*gamma (torch.nn.GroupNorm). */
+int vlnce_groupnorm_stats(const void* x, int dtype, const float* gamma, const float* beta,
+                          float* scale, float* shift, int N, int HW, int C, int groups, float eps,
+                          cudaStream_t stream);
+/* Train-mode BatchNorm2d statistics over all N*HW rows: per-channel scale/shift
+ * from batch mean / biased var; updates running_mean/var (momentum, unbiased var) in place. */
+int vlnce_batchnorm_train_stats(const void* x, int dtype, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, float momentum,
+                                float* scale, float* shift, double* workspace, long long rows,
+                                int C, float eps, cudaStream_t stream);
+/* y = act(x*scale[n or 0, c] + shift[..] (+ residual)); scale_stride_n = C (per sample) or 0. */
+int vlnce_affine_apply(const void* x, const float* scale, const float* shift, int scale_stride_n,
+                       const void* residual, void* y, int dtype, int N, int HW, int C, int relu,
+                       cudaStream_t stream);
+/* adaptive_avg_pool2d(x,(O,O)), O in {1,4}, on NHWC -> f32 (N,O*O,ldy) slice
+ * (resnet_encoders.py:154-162 4x4 pool; torchvision's global pool for the non-spatial
+ * encoder); with H=W=O it is a plain bf16->f32 layout copy. */
+int vlnce_adaptive_avgpool(const void* x, int dtype, float* y, int ldy, int N, int H, int W, int C,
+                           int O, cudaStream_t stream);
+/* (N,C,4,4) f32 cached features (rgb_features / depth_features, resnet_encoders.py:92-93,
+ * 194-195) -> (N,16,ldy) f32 channels-last slice */
+int vlnce_nchw_to_positions(const float* x, float* y, int ldy, int N, int C, int P,
+                            cudaStream_t stream);
+
+/* ---- trainable head: dense algebra --------------------------------------------------- */
+/* C[m,n] = act(sum_k A[m*lda_m + k*lda_k] * B[k*ldb_k + n*ldb_n] + bias[n] + beta*C[m,n]),
+ * fp32 on CUDA cores; act 0 none / 1 ReLU / 2 tanh.  One routine for every Linear / Conv1d(k=1) of
+ * the head forward and backward (cma_policy.py:101-184: rgb_linear, depth_linear, state_q,
+ * text_k, text_q, rgb_kv, depth_kv, second_state_compress, progress_monitor; policy.py:19-21
+ * CategoricalNet; GRU / LSTM input and hidden projections). */
+int vlnce_sgemm(const float* A, long long lda_m, long long lda_k, const float* B, long long ldb_k,
+                long long ldb_n, float* C, long long ldc, const float* bias, int M, int N, int K,
+                float beta, int act, cudaStream_t stream);
+/* out[n] (+)= sum_m A[m*lda + n]  — bias gradients */
+int vlnce_colsum(const float* A, long long lda, float* out, int M, int N, int accumulate,
+                 cudaStream_t stream);
+
+/* ---- trainable head: forward -------------------------------------------------------- */
+/* nn.Embedding gather (instruction_encoder.py:70-73): out[r, :dim] = table[ids[r]] */
+int vlnce_embedding_fwd(const long long* ids, const float* table, float* out, long long rows,
+                        int dim, int ldo, int vocab, cudaStream_t stream);
+/* prev-action embedding with index ((a+1)*mask) (cma_policy.py:233-235); writes the
+ * 32-d rows into two concat slices at once */
+int vlnce_prev_action_embed(const long long* prev_actions, const float* masks, const float* table,
+                            float* out, int ldo, float* out2, int ldo2, int rows, int dim,
+                            int table_rows, cudaStream_t stream);
+/* per-row instruction length (instruction_encoder.py:77-78), token ids / rxr features */
+int vlnce_token_lengths(const long long* ids, int* lengths, int rows, int L, cudaStream_t stream);
+int vlnce_feature_lengths(const float* x, int* lengths, int rows, int L, int D, cudaStream_t stream);
+/* persistent (bi)LSTM over packed rows (instruction_encoder.py:80-94): gx (dirs,R,L,4H) = input
+ * projection + b_ih (b_hh is added here); out (R,L,dirs*H) zero beyond each row's length; hn (dirs,R,H) final
+ * states; save_* optional residuals for the backward. */
+int vlnce_lstm_seq_fwd(const float* gx, const float* whh_f, const float* whh_b, const float* bhh_f,
+                       const float* bhh_b, const int* lengths, float* out, float* hn,
+                       float* save_gates, float* save_c, int R, int L, int H, int dirs,
+                       cudaStream_t stream);
+/* GRU cell pointwise part (habitat_baselines v0.1.7 rnn_state_encoder / torch.nn.GRU) */
+int vlnce_gru_pointwise_fwd(const float* gi, const float* gh, const float* h, long long ldh,
+                            float* hout, long long ldo, float* hout2, long long ldo2, float* save,
+                            int rows, int H, cudaStream_t stream);
+/* out = h * mask[row]  (hidden reset at episode starts) */
+int vlnce_mask_rows(const float* h, long long ldh, const float* mask, float* out, long long ldo,
+                    int rows, int H, cudaStream_t stream);
+/* single-query attention pooling (cma_policy.py:207-217, keys/values re-associated) */
+int vlnce_attn_pool_fwd(const float* q, long long ldq, const float* E, long long lde_r,
+                        long long lde_p, const int* lengths, float scale, float* probs, float* out,
+                        long long ldo, int R, int P, int D, cudaStream_t stream);
+int vlnce_mean_positions(const float* E, long long lde_r, long long lde_p, float* out, long long ldo,
+                         int R, int P, int D, cudaStream_t stream);
+int vlnce_spatial_embed_fill(const float* table, float* E, long long lde_r, long long lde_p,
+                             int c_off, int R, int P, int Cs, cudaStream_t stream);
+int vlnce_positions_to_nchw(const float* E, long long lde_r, long long lde_p, float* out,
+                            long long ldo, int R, int P, int C, cudaStream_t stream);
+int vlnce_log_softmax_rows(float* x, int rows, int A, cudaStream_t stream);
+int vlnce_argmax_rows(const float* x, long long* out, int rows, int A, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLNCE_B200_H_ */

@@ -1,0 +1,89 @@
+"""Conv kernels on the B200: the CUDA-core reference conv against torch (fp32), and the
+tcgen05 implicit-GEMM tiles against the reference conv on identical bf16 operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from vlnce_b200 import lib
+from vlnce_b200.lib import C, ptr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ref_conv(x, w, scale, shift, res, stride, pad, relu, y_dtype=torch.float32):
+    n, h, ww, c = x.shape
+    k, r, s, _ = w.shape
+    p, q = (h + 2 * pad - r) // stride + 1, (ww + 2 * pad - s) // stride + 1
+    y = torch.empty(n, p, q, k, device=DEV, dtype=y_dtype)
+    C.vlnce_conv2d_ref(ptr(x), lib.code(x), ptr(w), lib.code(w), ptr(scale), ptr(shift), ptr(res),
+                       lib.code(res) if res is not None else 0, ptr(y), lib.code(y), n, h, ww, c, k, r, s,
+                       stride, pad, int(relu), lib.stream())
+    return y
+
+
+@pytest.mark.parametrize("cin,k,r,stride,pad,hw", [(3, 16, 7, 2, 3, 20), (8, 24, 3, 1, 1, 9), (16, 8, 1, 2, 0, 10)])
+def test_conv_ref_matches_torch(cin, k, r, stride, pad, hw):
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = torch.randn(2, hw, hw, cin, generator=g).to(DEV)
+    w = torch.randn(k, r, r, cin, generator=g).to(DEV) * 0.2
+    scale = (torch.rand(k, generator=g) + 0.5).to(DEV)
+    shift = torch.randn(k, generator=g).to(DEV)
+    want = F.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), stride=stride, padding=pad)
+    want = want * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res = torch.randn_like(want.permute(0, 2, 3, 1).contiguous())
+    want = torch.relu(want + res.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        got = _ref_conv(x, w, scale, shift, res, stride, pad, True)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+CASES = [
+    # n, h, w, c, k, r, stride, pad, block_n, epilogue
+    (2, 16, 16, 64, 64, 1, 1, 0, 0, "affine_relu"),       # plain GEMM, one k-iter
+    (2, 16, 16, 128, 64, 1, 1, 0, 64, "raw"),             # two k-iters
+    (3, 12, 12, 64, 128, 3, 1, 1, 128, "affine_res_relu"),  # 3x3 pad, M=432 (ragged last tile)
+    (2, 16, 16, 64, 256, 3, 2, 1, 256, "affine_relu"),    # stride 2, widest tile
+    (2, 16, 16, 256, 512, 1, 2, 0, 0, "affine"),          # 1x1 stride 2 (downsample)
+    (4, 8, 8, 32, 32, 3, 1, 1, 32, "raw"),                # BLOCK_K = 32 (64B swizzle), N = 32
+    (4, 8, 8, 32, 128, 1, 1, 0, 0, "affine_relu"),        # BLOCK_K = 32
+    (1, 8, 8, 512, 512, 3, 1, 1, 128, "affine_res_relu"),  # long K loop (72 iters), ring wraps
+    (1, 1, 1, 192, 64, 1, 1, 0, 64, "affine_relu"),       # M = 1 row (stem-GEMM shape, tiny)
+    (5, 7, 7, 64, 64, 3, 1, 1, 64, "raw"),                # odd spatial size (224-input shapes)
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_umma_matches_reference(case):
+    n, h, w, c, k, r, stride, pad, bn, epi = case
+    g = torch.Generator(device="cpu").manual_seed(hash(case) % 1000)
+    x = torch.randn(n, h, w, c, generator=g).to(DEV).bfloat16()
+    wt = (torch.randn(k, r, r, c, generator=g) * (2.0 / (r * r * c)) ** 0.5).to(DEV).bfloat16()
+    p, q = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - r) // stride + 1
+    scale = shift = res = None
+    if "affine" in epi:
+        scale = (torch.rand(k, generator=g) + 0.5).to(DEV)
+        shift = torch.randn(k, generator=g).to(DEV) * 0.1
+    if "res" in epi:
+        res = torch.randn(n, p, q, k, generator=g).to(DEV).bfloat16()
+    relu = "relu" in epi
+    want = _ref_conv(x, wt, scale, shift, res, stride, pad, relu)  # fp32 out, same bf16 operands
+    for y_dtype in (torch.bfloat16, torch.float32):
+        y = torch.full((n, p, q, k), float("nan"), device=DEV, dtype=y_dtype)
+        C.vlnce_conv2d_bf16(ptr(x), ptr(wt), ptr(scale), ptr(shift), ptr(res), ptr(y), lib.code(y), n, h, w,
+                            c, k, r, r, stride, pad, int(relu), bn, lib.stream())
+        torch.cuda.synchronize()
+        tol = 2e-2 if y_dtype == torch.bfloat16 else 2e-3
+        err = (y.float() - want).abs().max().item()
+        ref = want.abs().max().item()
+        assert torch.isfinite(y.float()).all(), f"non-finite output ({y_dtype})"
+        assert err <= tol * max(ref, 1.0), f"{case} {y_dtype}: max err {err} vs ref max {ref}"
+
+
+def test_conv_umma_rejects_bad_shapes():
+    x = torch.zeros(1, 4, 4, 24, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(32, 1, 1, 24, device=DEV, dtype=torch.bfloat16)
+    y = torch.zeros(1, 4, 4, 32, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(lib.VlnceError, match="multiple of 32"):
+        C.vlnce_conv2d_bf16(ptr(x), ptr(w), None, None, None, ptr(y), lib.BF16, 1, 4, 4, 24, 32, 1, 1, 1, 0, 0,
+                            0, lib.stream())

@@ -1,0 +1,132 @@
+"""Head kernels on the B200 against plain torch fp32 (the per-op references)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from vlnce_b200 import lib
+from vlnce_b200.engine import linear, linear_dw, linear_dx
+from vlnce_b200.lib import C, ptr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _r(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("m,n,k", [(64, 256, 2112), (70, 33, 50), (1, 4, 512), (130, 1536, 416)])
+def test_sgemm_variants(m, n, k):
+    x, w, b = _r(m, k), _r(n, k, scale=0.1), _r(n)
+    out = torch.full((m, n + 3), float("nan"), device=DEV)
+    linear(ptr(x), k, ptr(w), ptr(out), n + 3, ptr(b), m, n, k, act=1)
+    torch.testing.assert_close(out[:, :n], torch.relu(x @ w.t() + b), rtol=1e-4, atol=1e-4)
+    dy = _r(m, n, seed=3)
+    dx = torch.empty(m, k, device=DEV)
+    linear_dx(ptr(dy), n, ptr(w), ptr(dx), k, m, n, k)
+    torch.testing.assert_close(dx, dy @ w, rtol=1e-4, atol=1e-4)
+    dw = torch.ones(n, k, device=DEV)
+    linear_dw(ptr(dy), n, ptr(x), k, ptr(dw), k, m, n, k, beta=1.0)
+    torch.testing.assert_close(dw, 1 + dy.t() @ x, rtol=1e-4, atol=2e-4)
+    cs = torch.empty(n, device=DEV)
+    C.vlnce_colsum(ptr(dy), n, ptr(cs), m, n, 0, lib.stream())
+    torch.testing.assert_close(cs, dy.sum(0), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("dirs", [1, 2])
+def test_lstm_matches_packed_torch(dirs):
+    R, L, E, H = 5, 11, 50, 128
+    torch.manual_seed(0)
+    rnn = nn.LSTM(E, H, bidirectional=dirs == 2).to(DEV)
+    x = _r(R, L, E)
+    lens = torch.tensor([11, 1, 7, 4, 9])
+    x = x * (torch.arange(L).view(1, L, 1) < lens.view(R, 1, 1)).to(DEV)
+    packed = nn.utils.rnn.pack_padded_sequence(x, lens, batch_first=True, enforce_sorted=False)
+    with torch.no_grad():
+        o, (hn, _) = rnn(packed)
+    want = nn.utils.rnn.pad_packed_sequence(o, batch_first=True, total_length=L)[0]
+    lengths = lens.to(DEV).int()
+    gx = torch.empty(dirs, R, L, 4 * H, device=DEV)
+    ws = [(rnn.weight_ih_l0, rnn.bias_ih_l0)] + ([(rnn.weight_ih_l0_reverse, rnn.bias_ih_l0_reverse)] if dirs == 2 else [])
+    for d, (w, b) in enumerate(ws):
+        linear(ptr(x), E, ptr(w), gx[d].data_ptr(), 4 * H, ptr(b), R * L, 4 * H, E)
+    out = torch.full((R, L, dirs * H), float("nan"), device=DEV)
+    hn_got = torch.empty(dirs, R, H, device=DEV)
+    C.vlnce_lstm_seq_fwd(ptr(gx), ptr(rnn.weight_hh_l0), ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None,
+                         ptr(rnn.bias_hh_l0), ptr(rnn.bias_hh_l0_reverse) if dirs == 2 else None, ptr(lengths),
+                         ptr(out), ptr(hn_got), None, None, R, L, H, dirs, lib.stream())
+    torch.testing.assert_close(out, want, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(hn_got, hn, rtol=1e-4, atol=2e-5)
+
+
+def test_gru_cell_matches_torch():
+    N, I, H = 7, 416, 512
+    torch.manual_seed(0)
+    rnn = nn.GRU(I, H).to(DEV)
+    x, h = _r(N, I), _r(N, H, seed=5)
+    with torch.no_grad():
+        _, want = rnn(x.unsqueeze(0), h.unsqueeze(0))
+    gi, gh = torch.empty(N, 3 * H, device=DEV), torch.empty(N, 3 * H, device=DEV)
+    linear(ptr(x), I, ptr(rnn.weight_ih_l0), ptr(gi), 3 * H, ptr(rnn.bias_ih_l0), N, 3 * H, I)
+    linear(ptr(h), H, ptr(rnn.weight_hh_l0), ptr(gh), 3 * H, ptr(rnn.bias_hh_l0), N, 3 * H, H)
+    out = torch.empty(N, H, device=DEV)
+    C.vlnce_gru_pointwise_fwd(ptr(gi), ptr(gh), ptr(h), H, ptr(out), H, None, 0, None, N, H, lib.stream())
+    torch.testing.assert_close(out, want[0], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("P,D,masked", [(80, 256, True), (16, 2112, False), (16, 192, False)])
+def test_attention_pool_matches_reference_attn(P, D, masked):
+    """cma_policy.py:207-217 with keys/values from a Conv1d, against the re-associated kernel."""
+    R, hk, dv = 6, 256, 128
+    E = _r(R, P, D, scale=0.5)
+    lens = torch.randint(1, P + 1, (R,), generator=torch.Generator().manual_seed(1)).to(DEV)
+    if masked:
+        E = E * (torch.arange(P, device=DEV).view(1, P, 1) < lens.view(R, 1, 1))
+    wk, bk, wv, bv = _r(hk, D, scale=D ** -0.5), _r(hk), _r(dv, D, scale=D ** -0.5), _r(dv)
+    q = _r(R, hk, seed=9)
+    scale = 1.0 / 16
+    En = E.permute(0, 2, 1)  # (R, D, P) reference layout
+    k = torch.einsum("od,rdp->rop", wk, En) + bk.view(1, -1, 1)
+    v = (torch.einsum("od,rdp->rop", wv, En) + bv.view(1, -1, 1)) if not masked else En
+    logits = torch.einsum("nc,nci->ni", q, k)
+    if masked:
+        logits = logits - (En == 0).all(1).float() * 1e8
+    want = torch.einsum("ni,nci->nc", F.softmax(logits * scale, 1), v)
+    qp = q @ wk
+    pooled = torch.empty(R, D, device=DEV)
+    probs = torch.empty(R, P, device=DEV)
+    C.vlnce_attn_pool_fwd(ptr(qp), D, ptr(E), P * D, D, ptr(lens.int()) if masked else None, scale, ptr(probs),
+                          ptr(pooled), D, R, P, D, lib.stream())
+    got = pooled if masked else pooled @ wv.t() + bv
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(probs.sum(1), torch.ones(R, device=DEV), rtol=1e-5, atol=1e-5)
+
+
+def test_small_layout_ops():
+    R, P, Cc = 3, 16, 192
+    E = _r(R, P, Cc)
+    out = torch.empty(R, Cc * P, device=DEV)
+    C.vlnce_positions_to_nchw(ptr(E), P * Cc, Cc, ptr(out), Cc * P, R, P, Cc, lib.stream())
+    torch.testing.assert_close(out, E.permute(0, 2, 1).reshape(R, -1))
+    f = _r(R, 128, 4, 4)
+    dst = torch.zeros(R, P, Cc, device=DEV)
+    C.vlnce_nchw_to_positions(ptr(f), ptr(dst), Cc, R, 128, 16, lib.stream())
+    torch.testing.assert_close(dst[:, :, :128], f.flatten(2).permute(0, 2, 1))
+    table = _r(16, 64)
+    C.vlnce_spatial_embed_fill(ptr(table), ptr(dst), P * Cc, Cc, 128, R, P, 64, lib.stream())
+    want = table.view(1, 64, 4, 4).expand(R, 64, 4, 4).flatten(2).permute(0, 2, 1)
+    torch.testing.assert_close(dst[:, :, 128:], want)
+    m = torch.empty(R, Cc, device=DEV)
+    C.vlnce_mean_positions(ptr(dst), P * Cc, Cc, ptr(m), Cc, R, P, Cc, lib.stream())
+    torch.testing.assert_close(m, dst.mean(1), rtol=1e-5, atol=1e-6)
+    x = _r(4, 9, 9, 40)
+    y = torch.empty(4, 16, 40, device=DEV)
+    C.vlnce_adaptive_avgpool(ptr(x), lib.F32, ptr(y), 40, 4, 9, 9, 40, 4, lib.stream())
+    want = F.adaptive_avg_pool2d(x.permute(0, 3, 1, 2), (4, 4)).flatten(2).permute(0, 2, 1)
+    torch.testing.assert_close(y, want, rtol=1e-5, atol=1e-6)
+    ids = torch.tensor([[3, 0, 5, 0], [0, 0, 0, 0], [1, 2, 3, 4]], device=DEV)
+    lens = torch.empty(3, dtype=torch.int32, device=DEV)
+    C.vlnce_token_lengths(ptr(ids), ptr(lens), 3, 4, lib.stream())
+    assert lens.tolist() == [2, 0, 4]

@@ -1,0 +1,86 @@
+"""End-to-end parity of the CUDA policy against the oracle and the golden vectors frozen
+from the unmodified reference.  Tolerances follow BASELINE.json north_star: 1e-3 relative
+for the fp32 path, 1e-2 for bf16 trunks, argmax actions bit-exact."""
+import os
+import warnings
+
+import pytest
+import torch
+
+import vlnce_b200
+from oracle import cases, vlnce as oracle_vlnce
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    return ((a.float().cpu() - b.float().cpu()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def to_dev(obs):
+    return {k: v.to(DEV) for k, v in obs.items()}
+
+
+def cuda_policy(case, precision):
+    pol = cases.build_policy(vlnce_b200, case).to(DEV)
+    pol.net.precision = precision
+    cases.set_mode(pol, case)
+    return pol
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_trunks_match_oracle(precision, tol):
+    case = cases.CASES["cma_act"]
+    opol = cases.build_policy(oracle_vlnce, case).eval()
+    cpol = cuda_policy(case, precision)
+    obs, _, _, _ = cases.inputs(case)
+    with torch.no_grad():
+        want_rgb = opol.net.rgb_encoder.cnn(obs["rgb"].permute(0, 3, 1, 2).float() / 255.0)
+        want_dep = opol.net.depth_encoder.visual_encoder(obs)
+    dobs = to_dev(obs)
+    n = obs["rgb"].shape[0]
+    out_rgb = torch.zeros(n, 16, 2112, device=DEV)
+    out_dep = torch.zeros(n, 16, 192, device=DEV)
+    cpol.net.rgb_encoder.features_into(dobs, out_rgb, 2112, precision)
+    cpol.net.depth_encoder.features_into(dobs, out_dep, 192, precision)
+    torch.cuda.synchronize()
+    got_rgb = out_rgb[:, :, :2048].permute(0, 2, 1).reshape(n, 2048, 4, 4)
+    got_dep = out_dep[:, :, :128].permute(0, 2, 1).reshape(n, 128, 4, 4)
+    e_rgb, e_dep = rel(got_rgb, want_rgb), rel(got_dep, want_dep)
+    print(f"trunk rel err [{precision}] rgb {e_rgb:.3e} depth {e_dep:.3e}")
+    assert e_rgb < tol and e_dep < tol
+
+
+@pytest.mark.parametrize("name", ["cma_act", "cma_act_rgb224", "cma_act_bntrain"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
+def test_cma_act_matches_golden(name, precision, tol):
+    case = cases.CASES[name]
+    gold = torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+    pol = cuda_policy(case, precision)
+    obs, h, prev, masks = cases.inputs(case)
+    obs, h, prev, masks = to_dev(obs), h.to(DEV), prev.to(DEV), masks.to(DEV)
+    with torch.no_grad():
+        dist = pol.build_distribution(obs, h, prev, masks)
+        if case["bn_train"]:  # running stats were updated by the first call; rebuild for act()
+            pol = cuda_policy(case, precision)
+        action, h_out = pol.act(obs, h, prev, masks, deterministic=True)
+    torch.cuda.synchronize()
+    e_logits = rel(dist.logits.exp(), gold["logits"].exp())
+    e_h = rel(h_out, gold["rnn_states_out"])
+    margin = gold["logits"].topk(2, dim=1).values
+    margin = (margin[:, 0] - margin[:, 1]).min().item()
+    print(f"{name}[{precision}] rel err probs {e_logits:.3e} hidden {e_h:.3e} (min logit margin {margin:.3f})")
+    assert e_logits < tol and e_h < tol
+    assert torch.equal(action.cpu(), gold["action"]), "argmax actions must be bit-exact"
+    assert h_out.shape == gold["rnn_states_out"].shape and action.dtype == torch.int64
+
+
+def test_no_cpu_fallback():
+    case = cases.CASES["cma_act"]
+    pol = cases.build_policy(vlnce_b200, case)  # parameters left on the CPU
+    obs, h, prev, masks = cases.inputs(case)
+    with pytest.raises(vlnce_b200.lib.VlnceError, match="CUDA only"):
+        pol.act(obs, h, prev, masks, deterministic=True)

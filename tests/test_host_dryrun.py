@@ -1,0 +1,39 @@
+"""Host logic without a GPU: walk the full launch sequence of the CUDA policy with every
+C-ABI call validated against the header prototypes (``vlnce_b200.lib.dry_run``)."""
+import warnings
+
+import pytest
+import torch
+
+import vlnce_b200
+from oracle import cases
+from vlnce_b200 import lib
+
+warnings.filterwarnings("ignore")
+
+
+@pytest.mark.parametrize("name,precision", [("cma_act", "bf16"), ("cma_act", "fp32"),
+                                            ("cma_act_bntrain", "bf16"), ("cma_act_rgb224", "bf16")])
+def test_act_launch_sequence(name, precision):
+    case = cases.CASES[name]
+    pol = cases.build_policy(vlnce_b200, case)
+    pol.net.precision = precision
+    cases.set_mode(pol, case)
+    obs, h, prev, masks = cases.inputs(case)
+    with lib.dry_run() as rec:
+        action, h_out = pol.act(obs, h, prev, masks, deterministic=True)
+    assert action.shape == (case["n"], 1) and action.dtype == torch.int64
+    assert h_out.shape == h.shape
+    n_conv = sum(c.startswith("vlnce_conv2d") for c in rec.calls)
+    assert n_conv == 53 + 54, n_conv  # torchvision ResNet-50 + DD-PPO ResNet-50 & compression
+    assert rec.calls.count("vlnce_attn_pool_fwd") == 3
+    assert rec.calls.count("vlnce_lstm_seq_fwd") == 1
+
+
+def test_header_and_library_agree():
+    """Every prototype in include/vlnce_b200.h is exported by the built library (loads on CPU)."""
+    import ctypes
+    dll = ctypes.CDLL(lib.LIB_PATH)
+    for name in lib.C.protos:
+        assert hasattr(dll, name), name
+    assert b"sm_100a" in lib.C.vlnce_version()

@@ -1,0 +1,379 @@
+// Implicit-GEMM (im2col-free) NHWC convolution on the 5th-gen tensor cores.
+//
+//   Y[m, k] = act( scale[k] * sum_{r,s,c} X[n, p*st+r-pad, q*st+s-pad, c] * W[k, r, s, c]
+//                  + shift[k] (+ residual[m, k]) ),   m = (n, p, q)
+//
+// Replaces the cuDNN convolutions behind torchvision ResNet-50 (`resnet_encoders.py:198-199`)
+// and the DD-PPO GroupNorm ResNet-50 (`resnet_encoders.py:95`, habitat_baselines v0.1.7
+// `ResNetEncoder`) on the policy hot path.  GEMM view: M = N*P*Q pixels, N = K filters,
+// K = R*S*C.  One CTA computes a 128 x BLOCK_N output tile:
+//
+//   warps 0-3  gather the A tile (128 pixels x BLOCK_K channels of one filter tap) straight
+//              from the NHWC activation with 16-byte cp.async into the 128B/64B-swizzled
+//              K-major layout the MMA expects (zero-fill = padding), then run the epilogue:
+//              tcgen05.ld the fp32 accumulator rows from TMEM, apply folded-norm scale/shift,
+//              residual, ReLU, store bf16 NHWC.
+//   warp 4     allocates TMEM and issues tcgen05.mma (one elected thread), committing each
+//              smem stage back to the producers through an mbarrier.
+//   warp 5     streams the weight tile (BLOCK_N x BLOCK_K of the [K, R*S*C] matrix) with TMA.
+//
+// A 4-stage mbarrier ring decouples the three roles.  Activations stay bf16 NHWC in HBM; the
+// accumulator never leaves TMEM until the fused epilogue.
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace vlnce {
+namespace {
+
+using namespace ptx;
+
+constexpr int BLOCK_M = 128;
+constexpr int kStages = 4;
+constexpr int kLag = 2;  // cp.async groups kept in flight before a stage is published
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 192;
+
+struct ConvParams {
+  const __nv_bfloat16* x;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  void* y;
+  int N, H, W, C, K, R, S, stride, pad, P, Q;
+  int M;            // N*P*Q
+  int c_chunks;     // C / BLOCK_K
+  int num_k_iters;  // R*S*c_chunks
+  int n_tiles;      // K / BLOCK_N
+  int relu;
+  int y_fp32;       // 1: store fp32 instead of bf16
+};
+
+template <int BLOCK_N, int BLOCK_K>
+struct Cfg {
+  static constexpr int ROW_BYTES = BLOCK_K * 2;
+  static constexpr int CPR = ROW_BYTES / 16;             // 16B chunks per operand row
+  static constexpr int ROWS_PER_PASS = kProducerThreads / CPR;
+  static constexpr int RPT = BLOCK_M / ROWS_PER_PASS;    // rows gathered per producer thread
+  static constexpr int A_BYTES = BLOCK_M * ROW_BYTES;
+  static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = kStages * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + align slack
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must stay 1024B aligned");
+};
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
+  using C = Cfg<BLOCK_N, BLOCK_K>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* accum_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_tile = blockIdx.x / p.n_tiles;
+  const int m0 = m_tile * BLOCK_M;
+  const int n0 = n_tile * BLOCK_N;
+
+  if (threadIdx.x == 5 * 32) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], kProducerThreads + 1);  // 128 gather threads + the TMA issuer
+      mbar_init(&empty_bar[s], 1);                    // one tcgen05.commit
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_a0 = smem_u32(smem);
+  const uint32_t smem_b0 = smem_a0 + kStages * C::A_BYTES;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ A gather (producers)
+    const int t = threadIdx.x;
+    const int chunk = t % C::CPR;
+    int ih0[C::RPT], iw0[C::RPT], img_off[C::RPT];
+    uint32_t dst_off[C::RPT];
+#pragma unroll
+    for (int i = 0; i < C::RPT; ++i) {
+      const int row = t / C::CPR + i * C::ROWS_PER_PASS;
+      const int m = m0 + row;
+      dst_off[i] = swizzled_offset(row, chunk, C::ROW_BYTES);
+      if (m < p.M) {
+        const int pq = p.P * p.Q;
+        const int n_img = m / pq;
+        const int rem = m - n_img * pq;
+        const int po = rem / p.Q;
+        const int qo = rem - po * p.Q;
+        ih0[i] = po * p.stride - p.pad;
+        iw0[i] = qo * p.stride - p.pad;
+        img_off[i] = n_img * p.H * p.W * p.C;
+      } else {
+        ih0[i] = -(1 << 20);  // always out of range -> zero rows
+        iw0[i] = 0;
+        img_off[i] = 0;
+      }
+    }
+    int rf = 0, sf = 0, cc = 0;
+    for (int it = 0; it < p.num_k_iters; ++it) {
+      const int stage = it % kStages;
+      const uint32_t phase = (it / kStages) & 1;
+      mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+      const uint32_t a_stage = smem_a0 + stage * C::A_BYTES;
+      const int c_off = cc * BLOCK_K + chunk * 8;
+#pragma unroll
+      for (int i = 0; i < C::RPT; ++i) {
+        const int ih = ih0[i] + rf, iw = iw0[i] + sf;
+        const bool ok = (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+        const __nv_bfloat16* src =
+            ok ? p.x + (size_t)img_off[i] + (size_t)(ih * p.W + iw) * p.C + c_off : p.x;
+        cp_async_16(a_stage + dst_off[i], src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (it >= kLag) {
+        cp_async_wait<kLag>();
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the MMA (async proxy)
+        mbar_arrive(&full_bar[(it - kLag) % kStages]);
+      }
+      if (++cc == p.c_chunks) {
+        cc = 0;
+        if (++sf == p.S) { sf = 0; ++rf; }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (int it = (p.num_k_iters > kLag ? p.num_k_iters - kLag : 0); it < p.num_k_iters; ++it)
+      mbar_arrive(&full_bar[it % kStages]);
+
+    // ------------------------------------------------------------ epilogue
+    mbar_wait(accum_bar, 0, 2);
+    tc_fence_after_sync();
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + cb * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        const int col0 = n0 + cb * 32;
+        const size_t off = (size_t)m * p.K + col0;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], __ldg(p.scale + col0 + j), __ldg(p.shift + col0 + j));
+        }
+        if (p.residual != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint4 rv = __ldg(rp + q4);
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[q4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
+              f[q4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.y_fp32) {
+          float4* yp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + off);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            yp[q4] = make_float4(f[q4 * 4], f[q4 * 4 + 1], f[q4 * 4 + 2], f[q4 * 4 + 3]);
+        } else {
+          uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q4 * 8 + e * 2], f[q4 * 8 + e * 2 + 1]);
+              w[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            yp[q4] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+    for (int it = 0; it < p.num_k_iters; ++it) {
+      const int stage = it % kStages;
+      const uint32_t phase = (it / kStages) & 1;
+      mbar_wait(&full_bar[stage], phase, 3);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint64_t adesc = make_smem_desc(smem_a0 + stage * C::A_BYTES, C::ROW_BYTES);
+        const uint64_t bdesc = make_smem_desc(smem_b0 + stage * C::B_BYTES, C::ROW_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // +32 bytes (two 16B units) per K=16 step inside the swizzled row
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((it | k) != 0));
+        }
+        umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(accum_bar);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ weight TMA (warp 5)
+    if (lane == 0) {
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        const int stage = it % kStages;
+        const uint32_t phase = (it / kStages) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1, 4);
+        mbar_arrive_expect_tx(&full_bar[stage], C::B_BYTES);
+        tma_load_2d(smem_b0 + stage * C::B_BYTES, &tmap_w, &full_bar[stage], it * BLOCK_K, n0);
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+template <int BLOCK_N, int BLOCK_K>
+int launch(const CUtensorMap& tmap, const ConvParams& p, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, BLOCK_K>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BLOCK_N, BLOCK_K>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(conv_umma)");
+    configured = true;
+  }
+  const long long tiles = (long long)cdiv(p.M, BLOCK_M) * p.n_tiles;
+  conv_umma_kernel<BLOCK_N, BLOCK_K><<<(unsigned)tiles, kThreads, C::SMEM_BYTES, stream>>>(tmap, p);
+  VLNCE_LAUNCH_CHECK("conv_umma_kernel");
+  return VLNCE_OK;
+}
+
+}  // namespace
+}  // namespace vlnce
+
+using namespace vlnce;
+
+extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, const float* scale,
+                                 const float* shift, const void* residual, void* y, int y_dtype,
+                                 int N, int H, int W, int C, int K, int R, int S, int stride,
+                                 int pad, int relu, int block_n, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && w && y, "conv2d_bf16: null tensor");
+  VLNCE_CHECK_ARG(N > 0 && H > 0 && W > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0,
+                  "conv2d_bf16: bad geometry");
+  VLNCE_CHECK_ARG(C % 32 == 0, "conv2d_bf16: C=%d must be a multiple of 32", C);
+  VLNCE_CHECK_ARG(K % 32 == 0, "conv2d_bf16: K=%d must be a multiple of 32", K);
+  VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv2d_bf16: scale/shift must come together");
+  VLNCE_CHECK_ARG(y_dtype == VLNCE_BF16 || y_dtype == VLNCE_F32, "conv2d_bf16: y dtype");
+  VLNCE_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+                  "conv2d_bf16: tensors must be 16-byte aligned");
+  const int P = (H + 2 * pad - R) / stride + 1;
+  const int Q = (W + 2 * pad - S) / stride + 1;
+  VLNCE_CHECK_ARG(P > 0 && Q > 0, "conv2d_bf16: empty output");
+  VLNCE_CHECK_ARG((long long)N * H * W * C < (1ll << 31) && (long long)N * P * Q < (1ll << 31) / 1,
+                  "conv2d_bf16: tensor too large for 32-bit offsets");
+  const int block_k = (C % 64 == 0) ? 64 : 32;
+  const int m_tiles = cdiv((long long)N * P * Q, BLOCK_M);
+  int bn = block_n;
+  if (bn == 0) {
+    // widest tile that still gives every SM (148) a CTA; otherwise the narrowest legal one >= 64
+    static const int cand[4] = {256, 128, 64, 32};
+    for (int i = 0; i < 4 && bn == 0; ++i)
+      if (K % cand[i] == 0 && (long long)m_tiles * (K / cand[i]) >= 148) bn = cand[i];
+    if (bn == 0) bn = (K % 64 == 0) ? 64 : 32;
+  }
+  VLNCE_CHECK_ARG((bn == 32 || bn == 64 || bn == 128 || bn == 256) && K % bn == 0,
+                  "conv2d_bf16: block_n=%d does not tile K=%d", bn, K);
+
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    set_error("conv2d_bf16: cuTensorMapEncodeTiled unavailable (no driver)");
+    return VLNCE_ERR_NO_DRIVER;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)R * S * C, (cuuint64_t)K};
+  const cuuint64_t gstride[1] = {(cuuint64_t)R * S * C * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)bn};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride,
+                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("conv2d_bf16: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return VLNCE_ERR_CUDA_BASE + 1;
+  }
+
+  ConvParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.scale = scale;
+  p.shift = shift;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.y = y;
+  p.N = N; p.H = H; p.W = W; p.C = C; p.K = K; p.R = R; p.S = S;
+  p.stride = stride; p.pad = pad; p.P = P; p.Q = Q;
+  p.M = N * P * Q;
+  p.c_chunks = C / block_k;
+  p.num_k_iters = R * S * p.c_chunks;
+  p.n_tiles = K / bn;
+  p.relu = relu;
+  p.y_fp32 = (y_dtype == VLNCE_F32);
+
+#define VLNCE_CONV_CASE(BN, BK) \
+  if (bn == BN && block_k == BK) return launch<BN, BK>(tmap, p, stream);
+  VLNCE_CONV_CASE(256, 64)
+  VLNCE_CONV_CASE(128, 64)
+  VLNCE_CONV_CASE(64, 64)
+  VLNCE_CONV_CASE(32, 64)
+  VLNCE_CONV_CASE(256, 32)
+  VLNCE_CONV_CASE(128, 32)
+  VLNCE_CONV_CASE(64, 32)
+  VLNCE_CONV_CASE(32, 32)
+#undef VLNCE_CONV_CASE
+  set_error("conv2d_bf16: no kernel for block_n=%d block_k=%d", bn, block_k);
+  return VLNCE_ERR_INVALID_ARGUMENT;
+}

@@ -1,0 +1,119 @@
+// fp32 strided GEMM on CUDA cores for the (small) trainable head:
+//   C[m,n] = act( sum_k A[m*lda_m + k*lda_k] * B[k*ldb_k + n*ldb_n] + bias[n] + beta*C[m,n] )
+// Arbitrary strides on both operands cover every forward/backward variant of the head's
+// Linear / Conv1d(k=1) layers (x W^T, dY W, dY^T X) without transposed copies.  64x64x16
+// tiles, 256 threads, 4x4 register micro-tiles, true fp32 (this is the 1e-3-parity path).
+#include "common.cuh"
+
+namespace vlnce {
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
+             const float* __restrict__ B, long long ldb_k, long long ldb_n, float* __restrict__ C,
+             long long ldc, const float* __restrict__ bias, int M, int N, int K, float beta, int act) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int tx = tid % 16, ty = tid / 16;  // micro-tile coords: rows ty*4.., cols tx*4..
+  float acc[4][4] = {};
+  // load mappings: favour the contiguous dimension of each operand
+  const bool a_kfast = (lda_k == 1);
+  const bool b_nfast = (ldb_n == 1);
+  for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;  // 1024 elements of the 64x16 A tile
+      int mm, kk;
+      if (a_kfast) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? __ldg(A + gm * lda_m + gk * lda_k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      int nn, kk;
+      if (b_nfast) { nn = e % TN; kk = e / TN; } else { kk = e % TK; nn = e / TK; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < K) ? __ldg(B + gk * ldb_k + gn * ldb_n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr) v += bias[gn];
+      float* cp = C + gm * ldc + gn;
+      if (beta != 0.f) v += beta * (*cp);
+      if (act == 1) v = fmaxf(v, 0.f);
+      else if (act == 2) v = tanhf(v);
+      *cp = v;
+    }
+  }
+}
+
+// out[n] = (accumulate ? out[n] : 0) + sum_m A[m*lda + n]   (bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ A, long long lda, float* __restrict__ out,
+                              int M, int N, int accumulate) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int slice = threadIdx.x >> 5, nslices = blockDim.x >> 5;
+  __shared__ float part[8][33];
+  float s = 0.f;
+  if (n < N)
+    for (int m = slice; m < M; m += nslices) s += A[m * lda + n];
+  part[slice][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (slice == 0 && n < N) {
+    float t = 0.f;
+    for (int i = 0; i < nslices; ++i) t += part[i][threadIdx.x & 31];
+    out[n] = accumulate ? out[n] + t : t;
+  }
+}
+
+}  // namespace
+}  // namespace vlnce
+
+using namespace vlnce;
+
+extern "C" int vlnce_sgemm(const float* A, long long lda_m, long long lda_k, const float* B,
+                           long long ldb_k, long long ldb_n, float* C, long long ldc,
+                           const float* bias, int M, int N, int K, float beta, int act,
+                           cudaStream_t stream) {
+  VLNCE_CHECK_ARG(A && B && C, "sgemm: null operand");
+  VLNCE_CHECK_ARG(M > 0 && N > 0 && K > 0, "sgemm: empty problem %dx%dx%d", M, N, K);
+  VLNCE_CHECK_ARG(act >= 0 && act <= 2, "sgemm: act must be 0 (none), 1 (relu) or 2 (tanh)");
+  dim3 grid(cdiv(N, TN), cdiv(M, TM));
+  sgemm_kernel<<<grid, 256, 0, stream>>>(A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta,
+                                         act);
+  VLNCE_LAUNCH_CHECK("sgemm_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_colsum(const float* A, long long lda, float* out, int M, int N, int accumulate,
+                            cudaStream_t stream) {
+  VLNCE_CHECK_ARG(A && out && M > 0 && N > 0, "colsum: bad arguments");
+  colsum_kernel<<<cdiv(N, 32), 256, 0, stream>>>(A, lda, out, M, N, accumulate);
+  VLNCE_LAUNCH_CHECK("colsum_kernel");
+  return VLNCE_OK;
+}

@@ -1,0 +1,457 @@
+// Forward kernels of the trainable CMA / Seq2Seq head (everything after the conv trunks):
+// token embedding + lengths, persistent (bi)LSTM instruction encoder, GRU state-encoder
+// cell, single-query attention pooling, spatial-embedding fill, small layout helpers.
+// All fp32, HBM/latency-bound: coalesced channel-fastest loads, weights of the recurrent
+// step held in registers across the whole sequence.
+#include "common.cuh"
+
+namespace vlnce {
+namespace {
+
+// ------------------------------------------------------------------------------------
+// instruction_encoder.py:70-78 — embedding gather and per-row length
+// ------------------------------------------------------------------------------------
+__global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                     float* __restrict__ out, long long rows, int dim, int ldo,
+                                     int vocab) {
+  const long long total = rows * dim;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / dim;
+    const int d = (int)(idx % dim);
+    long long id = ids[r];
+    if (id < 0 || id >= vocab) id = 0;
+    out[r * ldo + d] = __ldg(table + id * dim + d);
+  }
+}
+
+// prev-action index, Q6 (cma_policy.py:233-235): idx = ((a + 1) * mask), then gather 32-d rows
+__global__ void prev_action_embed_kernel(const long long* __restrict__ prev, const float* __restrict__ masks,
+                                         const float* __restrict__ table, float* __restrict__ out,
+                                         float* __restrict__ out2, int rows, int dim, int ldo, int ldo2,
+                                         int num_rows_table) {
+  const int total = rows * dim;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / dim, d = idx % dim;
+    long long id = (long long)(((float)prev[r] + 1.f) * masks[r]);
+    if (id < 0 || id >= num_rows_table) id = 0;
+    const float v = __ldg(table + id * dim + d);
+    out[(size_t)r * ldo + d] = v;
+    if (out2 != nullptr) out2[(size_t)r * ldo2 + d] = v;
+  }
+}
+
+__global__ void token_lengths_kernel(const long long* __restrict__ ids, int* __restrict__ lengths,
+                                     int rows, int L) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  int cnt = 0;
+  for (int t = threadIdx.x & 31; t < L; t += 32) cnt += ids[(size_t)r * L + t] != 0;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) lengths[r] = cnt;
+}
+
+// rxr features (R,L,D): a position counts if its row has any non-zero entry
+__global__ void feature_lengths_kernel(const float* __restrict__ x, int* __restrict__ lengths, int L,
+                                       int D) {
+  const int r = blockIdx.x;
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  int local = 0;
+  for (int t = warp; t < L; t += nw) {
+    const float* row = x + ((size_t)r * L + t) * D;
+    int any = 0;
+    for (int d = lane; d < D; d += 32) any |= (row[d] != 0.f);
+    any = __any_sync(0xffffffffu, any);
+    local += any;
+  }
+  if (lane == 0) atomicAdd(&cnt, local);
+  __syncthreads();
+  if (threadIdx.x == 0) lengths[r] = cnt;
+}
+
+// ------------------------------------------------------------------------------------
+// Persistent LSTM recurrence (instruction_encoder.py:80-84, torch.nn.LSTM on a packed
+// sequence): one CTA per (row, direction), 4H threads; thread j keeps row j of W_hh in
+// registers for all L steps.  gx = x W_ih^T + b_ih + b_hh is precomputed by one GEMM.
+// Gate order i, f, g, o (PyTorch).  Steps t >= len are skipped (outputs stay zero); the
+// reverse direction starts at each row's own last token.
+// ------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(4 * H, 1)
+lstm_seq_fwd_kernel(const float* __restrict__ gx,   // (dirs, R, L, 4H) = x W_ih^T + b_ih
+                    const float* __restrict__ whh_f, const float* __restrict__ whh_b,  // (4H, H) per direction
+                    const float* __restrict__ bhh_f, const float* __restrict__ bhh_b,  // (4H) per direction
+                    const int* __restrict__ lengths, float* __restrict__ out,  // (R, L, dirs*H)
+                    float* __restrict__ hn,          // (dirs, R, H) or null
+                    float* __restrict__ save_gates,  // (dirs, R, L, 4H) activated gates or null
+                    float* __restrict__ save_c,      // (dirs, R, L, H) or null
+                    int R, int L, int dirs) {
+  // Row j of W_hh: columns [0, KR) live in registers, [KR, H) in shared memory as float4
+  // groups laid out [k/4][j] (conflict-free 16B reads) — 4H threads cannot hold H registers each.
+  constexpr int KR = H / 2;
+  constexpr int KS4 = (H - KR) / 4;
+  extern __shared__ __align__(16) float lstm_smem[];
+  float4* w_s = reinterpret_cast<float4*>(lstm_smem);           // KS4 * 4H float4
+  float* h_s = lstm_smem + (size_t)KS4 * 4 * H * 4;              // H
+  float* g_s = h_s + H;                                          // 4H
+  const int r = blockIdx.x, dir = blockIdx.y;
+  const int j = threadIdx.x;  // gate row
+  float w[KR];
+  {
+    const float4* wp = reinterpret_cast<const float4*>((dir == 0 ? whh_f : whh_b) + (size_t)j * H);
+#pragma unroll
+    for (int k = 0; k < KR / 4; ++k) {
+      const float4 t4 = __ldg(wp + k);
+      w[4 * k] = t4.x; w[4 * k + 1] = t4.y; w[4 * k + 2] = t4.z; w[4 * k + 3] = t4.w;
+    }
+#pragma unroll
+    for (int k = 0; k < KS4; ++k) w_s[k * 4 * H + j] = __ldg(wp + KR / 4 + k);
+  }
+  const int len = min(lengths[r], L);
+  const float bh = __ldg((dir == 0 ? bhh_f : bhh_b) + j);
+  float c = 0.f;
+  if (j < H) h_s[j] = 0.f;
+  __syncthreads();
+  const size_t row_base = ((size_t)dir * R + r) * L;
+  for (int step = 0; step < len; ++step) {
+    const int t = dir == 0 ? step : len - 1 - step;
+    float a0 = __ldg(gx + (row_base + t) * 4 * H + j) + bh, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KR; k += 4) {
+      const float4 h4 = *reinterpret_cast<const float4*>(&h_s[k]);
+      a0 = fmaf(w[k], h4.x, a0);
+      a1 = fmaf(w[k + 1], h4.y, a1);
+      a2 = fmaf(w[k + 2], h4.z, a2);
+      a3 = fmaf(w[k + 3], h4.w, a3);
+    }
+#pragma unroll
+    for (int k = 0; k < KS4; ++k) {
+      const float4 w4 = w_s[k * 4 * H + j];
+      const float4 h4 = *reinterpret_cast<const float4*>(&h_s[KR + 4 * k]);
+      a0 = fmaf(w4.x, h4.x, a0);
+      a1 = fmaf(w4.y, h4.y, a1);
+      a2 = fmaf(w4.z, h4.z, a2);
+      a3 = fmaf(w4.w, h4.w, a3);
+    }
+    const float pre = (a0 + a1) + (a2 + a3);
+    const float act = (j >= 2 * H && j < 3 * H) ? tanhf(pre) : sigmoid_precise(pre);
+    g_s[j] = act;
+    if (save_gates != nullptr) save_gates[(row_base + t) * 4 * H + j] = act;
+    __syncthreads();
+    if (j < H) {
+      const float ig = g_s[j], fg = g_s[H + j], gg = g_s[2 * H + j], og = g_s[3 * H + j];
+      c = fmaf(fg, c, ig * gg);
+      const float h = og * tanhf(c);
+      h_s[j] = h;
+      out[((size_t)r * L + t) * (dirs * H) + dir * H + j] = h;
+      if (save_c != nullptr) save_c[(row_base + t) * H + j] = c;
+    }
+    __syncthreads();
+  }
+  if (hn != nullptr && j < H) hn[((size_t)dir * R + r) * H + j] = h_s[j];
+}
+
+// ------------------------------------------------------------------------------------
+// GRU cell pointwise (habitat_baselines v0.1.7 rnn_state_encoder single step; torch.nn.GRU):
+//   r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r * gh_n), h' = (1-z) n + z h
+// gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (both (rows, 3H)) come from the GEMM; h is the
+// already mask-reset hidden state.
+// ------------------------------------------------------------------------------------
+__global__ void gru_pointwise_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                         const float* __restrict__ h, long long ldh,
+                                         float* __restrict__ hout, long long ldo,
+                                         float* __restrict__ hout2, long long ldo2,
+                                         float* __restrict__ save,  // (rows, 4H): r, z, n, gh_n or null
+                                         int rows, int H) {
+  const int total = rows * H;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int b = idx / H, k = idx % H;
+    const float* gib = gi + (size_t)b * 3 * H;
+    const float* ghb = gh + (size_t)b * 3 * H;
+    const float rg = sigmoid_precise(gib[k] + ghb[k]);
+    const float zg = sigmoid_precise(gib[H + k] + ghb[H + k]);
+    const float ghn = ghb[2 * H + k];
+    const float ng = tanhf(fmaf(rg, ghn, gib[2 * H + k]));
+    const float hp = h[b * ldh + k];
+    const float hn = fmaf(zg, hp - ng, ng);  // (1-z) n + z h
+    hout[b * ldo + k] = hn;
+    if (hout2 != nullptr) hout2[b * ldo2 + k] = hn;
+    if (save != nullptr) {
+      float* s = save + (size_t)b * 4 * H;
+      s[k] = rg; s[H + k] = zg; s[2 * H + k] = ng; s[3 * H + k] = ghn;
+    }
+  }
+}
+
+// out[b, :] = h[b, :] * mask[b]   (hidden-state reset where an episode starts)
+__global__ void mask_rows_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ mask,
+                                 float* __restrict__ out, long long ldo, int rows, int H) {
+  const int total = rows * H;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int b = idx / H, k = idx % H;
+    out[b * ldo + k] = h[b * ldh + k] * mask[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Single-query attention pooling (cma_policy.py:207-217 `_attn`, re-associated):
+//   a = softmax(scale * (E q - 1e8 * [p >= len])),  out = sum_p a_p E_p
+// With keys k_p = W_k e_p + b_k the reference's logits q.k_p equal (W_k^T q).e_p + q.b_k; the
+// constant q.b_k cancels in the softmax, so the caller passes q' = W_k^T q and the raw
+// embedding E (read once per pass instead of materialising K and V).  One CTA per row.
+// ------------------------------------------------------------------------------------
+__global__ void attn_pool_fwd_kernel(const float* __restrict__ q, long long ldq,
+                                     const float* __restrict__ E, long long lde_r, long long lde_p,
+                                     const int* __restrict__ lengths, float scale,
+                                     float* __restrict__ probs,  // (R, P)
+                                     float* __restrict__ out, long long ldo, int P, int D) {
+  extern __shared__ float sm[];
+  float* logit = sm;           // P
+  float* red = sm + P;         // 32
+  const int r = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* qr = q + r * ldq;
+  const float* Er = E + r * lde_r;
+  const int len = lengths != nullptr ? lengths[r] : P;
+  for (int p = warp; p < P; p += nw) {
+    const float* e = Er + p * lde_p;
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s = fmaf(qr[d], e[d], s);
+    s = warp_sum(s);
+    if (lane == 0) logit[p] = (p < len ? s : s - 1e8f) * scale;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) mx = fmaxf(mx, logit[p]);
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const float ex = expf(logit[p] - mx);
+    logit[p] = ex;
+    sum += ex;
+  }
+  sum = block_sum(sum, red);
+  __syncthreads();
+  const float inv = 1.f / sum;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const float a = logit[p] * inv;
+    logit[p] = a;
+    if (probs != nullptr) probs[(size_t)r * P + p] = a;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int p = 0; p < P; ++p) acc = fmaf(logit[p], Er[p * lde_p + d], acc);
+    out[r * ldo + d] = acc;
+  }
+}
+
+// out[r, d] = mean_p E[r, p, d]   (AdaptiveAvgPool1d(1), cma_policy.py:105-108)
+__global__ void mean_positions_kernel(const float* __restrict__ E, long long lde_r, long long lde_p,
+                                      float* __restrict__ out, long long ldo, int R, int P, int D) {
+  const long long total = (long long)R * D;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / D), d = (int)(idx % D);
+    float acc = 0.f;
+    for (int p = 0; p < P; ++p) acc += E[r * lde_r + p * lde_p + d];
+    out[r * ldo + d] = acc / (float)P;
+  }
+}
+
+// E[r, s, c_off + c'] = table_flat[c' * P + s]: the raw `.view(1, 64, 4, 4)` of the (16, 64)
+// spatial-embedding table (resnet_encoders.py:97-113, 201-217).
+__global__ void spatial_embed_fill_kernel(const float* __restrict__ table, float* __restrict__ E,
+                                          long long lde_r, long long lde_p, int c_off, int R, int P,
+                                          int Cs) {
+  const long long total = (long long)R * P * Cs;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cs);
+    const int s = (int)((idx / Cs) % P);
+    const int r = (int)(idx / ((long long)Cs * P));
+    E[r * lde_r + s * lde_p + c_off + c] = __ldg(table + c * P + s);
+  }
+}
+
+// (R, P, C) channels-last -> (R, C*P) NCHW-flatten order (torch Flatten of (R,C,4,4))
+__global__ void positions_to_nchw_kernel(const float* __restrict__ E, long long lde_r, long long lde_p,
+                                         float* __restrict__ out, long long ldo, int R, int P, int C) {
+  const long long total = (long long)R * P * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(idx % P);
+    const int c = (int)((idx / P) % C);
+    const int r = (int)(idx / ((long long)P * C));
+    out[r * ldo + (long long)c * P + s] = E[r * lde_r + s * lde_p + c];
+  }
+}
+
+// log-softmax over A <= 32 logits per row, in place (torch.distributions.Categorical(logits=.))
+__global__ void log_softmax_rows_kernel(float* __restrict__ x, int rows, int A) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float* p = x + (size_t)r * A;
+  float mx = -INFINITY;
+  for (int a = 0; a < A; ++a) mx = fmaxf(mx, p[a]);
+  float s = 0.f;
+  for (int a = 0; a < A; ++a) s += expf(p[a] - mx);
+  const float lse = mx + logf(s);
+  for (int a = 0; a < A; ++a) p[a] -= lse;
+}
+
+// argmax over probs (CustomFixedCategorical.mode, models/utils.py:288-289): first maximum
+__global__ void argmax_rows_kernel(const float* __restrict__ x, long long* __restrict__ out, int rows,
+                                   int A) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* p = x + (size_t)r * A;
+  int best = 0;
+  float bv = p[0];
+  for (int a = 1; a < A; ++a)
+    if (p[a] > bv) { bv = p[a]; best = a; }
+  out[r] = best;
+}
+
+inline unsigned grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148ll * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+}  // namespace vlnce
+
+using namespace vlnce;
+
+extern "C" int vlnce_embedding_fwd(const long long* ids, const float* table, float* out,
+                                   long long rows, int dim, int ldo, int vocab, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(ids && table && out && rows > 0 && dim > 0 && ldo >= dim, "embedding_fwd: bad arguments");
+  embedding_fwd_kernel<<<grid_for(rows * dim, 256), 256, 0, stream>>>(ids, table, out, rows, dim, ldo, vocab);
+  VLNCE_LAUNCH_CHECK("embedding_fwd_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_prev_action_embed(const long long* prev_actions, const float* masks,
+                                       const float* table, float* out, int ldo, float* out2, int ldo2,
+                                       int rows, int dim, int table_rows, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(prev_actions && masks && table && out && rows > 0, "prev_action_embed: bad arguments");
+  prev_action_embed_kernel<<<grid_for((long long)rows * dim, 256), 256, 0, stream>>>(
+      prev_actions, masks, table, out, out2, rows, dim, ldo, ldo2, table_rows);
+  VLNCE_LAUNCH_CHECK("prev_action_embed_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_token_lengths(const long long* ids, int* lengths, int rows, int L,
+                                   cudaStream_t stream) {
+  VLNCE_CHECK_ARG(ids && lengths && rows > 0 && L > 0, "token_lengths: bad arguments");
+  token_lengths_kernel<<<cdiv(rows, 8), 256, 0, stream>>>(ids, lengths, rows, L);
+  VLNCE_LAUNCH_CHECK("token_lengths_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_feature_lengths(const float* x, int* lengths, int rows, int L, int D,
+                                     cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && lengths && rows > 0 && L > 0 && D > 0, "feature_lengths: bad arguments");
+  feature_lengths_kernel<<<rows, 256, 0, stream>>>(x, lengths, L, D);
+  VLNCE_LAUNCH_CHECK("feature_lengths_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_lstm_seq_fwd(const float* gx, const float* whh_f, const float* whh_b,
+                                  const float* bhh_f, const float* bhh_b, const int* lengths,
+                                  float* out, float* hn, float* save_gates, float* save_c, int R, int L,
+                                  int H, int dirs, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(gx && whh_f && bhh_f && lengths && out && R > 0 && L > 0 && (dirs == 1 || dirs == 2),
+                  "lstm_seq_fwd: bad arguments");
+  VLNCE_CHECK_ARG(dirs == 1 || (whh_b && bhh_b), "lstm_seq_fwd: reverse-direction weights missing");
+  VLNCE_CHECK_ARG(H == 128, "lstm_seq_fwd: hidden size %d not built (128 only)", H);
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)R * L * dirs * H, stream);
+  if (e != cudaSuccess) return cuda_status(e, "lstm_seq_fwd memset");
+  dim3 grid(R, dirs);
+  constexpr int H_ = 128;
+  const size_t smem = sizeof(float) * ((size_t)(H_ / 2) * 4 * H_ + H_ + 4 * H_);
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(lstm_seq_fwd_kernel<H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lstm_seq_fwd)");
+    configured = true;
+  }
+  lstm_seq_fwd_kernel<H_><<<grid, 4 * H_, smem, stream>>>(gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save_gates,
+                                                        save_c, R, L, dirs);
+  VLNCE_LAUNCH_CHECK("lstm_seq_fwd_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_gru_pointwise_fwd(const float* gi, const float* gh, const float* h, long long ldh,
+                                       float* hout, long long ldo, float* hout2, long long ldo2,
+                                       float* save, int rows, int H, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(gi && gh && h && hout && rows > 0 && H > 0, "gru_pointwise_fwd: bad arguments");
+  gru_pointwise_fwd_kernel<<<grid_for((long long)rows * H, 256), 256, 0, stream>>>(
+      gi, gh, h, ldh, hout, ldo, hout2, ldo2, save, rows, H);
+  VLNCE_LAUNCH_CHECK("gru_pointwise_fwd_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_mask_rows(const float* h, long long ldh, const float* mask, float* out,
+                               long long ldo, int rows, int H, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(h && mask && out && rows > 0 && H > 0, "mask_rows: bad arguments");
+  mask_rows_kernel<<<grid_for((long long)rows * H, 256), 256, 0, stream>>>(h, ldh, mask, out, ldo, rows, H);
+  VLNCE_LAUNCH_CHECK("mask_rows_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_attn_pool_fwd(const float* q, long long ldq, const float* E, long long lde_r,
+                                   long long lde_p, const int* lengths, float scale, float* probs,
+                                   float* out, long long ldo, int R, int P, int D,
+                                   cudaStream_t stream) {
+  VLNCE_CHECK_ARG(q && E && out && R > 0 && P > 0 && D > 0, "attn_pool_fwd: bad arguments");
+  VLNCE_CHECK_ARG(P <= 8192, "attn_pool_fwd: P=%d too long", P);
+  const size_t smem = sizeof(float) * (P + 32);
+  attn_pool_fwd_kernel<<<R, 256, smem, stream>>>(q, ldq, E, lde_r, lde_p, lengths, scale, probs, out, ldo, P, D);
+  VLNCE_LAUNCH_CHECK("attn_pool_fwd_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_mean_positions(const float* E, long long lde_r, long long lde_p, float* out,
+                                    long long ldo, int R, int P, int D, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(E && out && R > 0 && P > 0 && D > 0, "mean_positions: bad arguments");
+  mean_positions_kernel<<<grid_for((long long)R * D, 256), 256, 0, stream>>>(E, lde_r, lde_p, out, ldo, R, P, D);
+  VLNCE_LAUNCH_CHECK("mean_positions_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_spatial_embed_fill(const float* table, float* E, long long lde_r, long long lde_p,
+                                        int c_off, int R, int P, int Cs, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(table && E && R > 0 && P > 0 && Cs > 0, "spatial_embed_fill: bad arguments");
+  spatial_embed_fill_kernel<<<grid_for((long long)R * P * Cs, 256), 256, 0, stream>>>(table, E, lde_r, lde_p,
+                                                                                     c_off, R, P, Cs);
+  VLNCE_LAUNCH_CHECK("spatial_embed_fill_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_positions_to_nchw(const float* E, long long lde_r, long long lde_p, float* out,
+                                       long long ldo, int R, int P, int C, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(E && out && R > 0 && P > 0 && C > 0, "positions_to_nchw: bad arguments");
+  positions_to_nchw_kernel<<<grid_for((long long)R * P * C, 256), 256, 0, stream>>>(E, lde_r, lde_p, out, ldo,
+                                                                                   R, P, C);
+  VLNCE_LAUNCH_CHECK("positions_to_nchw_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_log_softmax_rows(float* x, int rows, int A, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && rows > 0 && A > 0, "log_softmax_rows: bad arguments");
+  log_softmax_rows_kernel<<<cdiv(rows, 128), 128, 0, stream>>>(x, rows, A);
+  VLNCE_LAUNCH_CHECK("log_softmax_rows_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_argmax_rows(const float* x, long long* out, int rows, int A, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && out && rows > 0 && A > 0, "argmax_rows: bad arguments");
+  argmax_rows_kernel<<<cdiv(rows, 128), 128, 0, stream>>>(x, out, rows, A);
+  VLNCE_LAUNCH_CHECK("argmax_rows_kernel");
+  return VLNCE_OK;
+}

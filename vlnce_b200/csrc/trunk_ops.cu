@@ -1,0 +1,533 @@
+// CUDA-core kernels around the tensor-core conv tiles: the fp32-accumulate reference conv
+// (fp32-exact mode + on-device cross-check), stem operand builders, pooling, GroupNorm /
+// train-mode BatchNorm statistics and the fused normalise(+residual)(+ReLU) pass.
+// All HBM-bound: coalesced channel-fastest accesses, 16-byte vectors where the layout allows.
+#include "common.cuh"
+
+namespace vlnce {
+namespace {
+
+// ------------------------------------------------------------------------------------
+// Reference conv: one thread per output element, fp32 accumulation in K order (r, s, c).
+// ------------------------------------------------------------------------------------
+template <typename TX, typename TW, typename TY, typename TR>
+__global__ void conv_ref_kernel(const TX* __restrict__ x, const TW* __restrict__ w,
+                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                const TR* __restrict__ residual, TY* __restrict__ y, int N, int H,
+                                int W, int C, int K, int R, int S, int stride, int pad, int P, int Q,
+                                int relu) {
+  const long long total = (long long)N * P * Q * K;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % K);
+    const long long m = idx / K;
+    const int q = (int)(m % Q);
+    const int p = (int)((m / Q) % P);
+    const int n = (int)(m / ((long long)P * Q));
+    float acc = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const int ih = p * stride + r - pad;
+      if ((unsigned)ih >= (unsigned)H) continue;
+      for (int s = 0; s < S; ++s) {
+        const int iw = q * stride + s - pad;
+        if ((unsigned)iw >= (unsigned)W) continue;
+        const TX* xp = x + ((size_t)(n * H + ih) * W + iw) * C;
+        const TW* wp = w + ((size_t)(k * R + r) * S + s) * C;
+        for (int c = 0; c < C; ++c) acc = fmaf(to_float<TX>(xp[c]), to_float<TW>(wp[c]), acc);
+      }
+    }
+    if (scale != nullptr) acc = fmaf(acc, scale[k], shift[k]);
+    if (residual != nullptr) acc += to_float<TR>(residual[idx]);
+    if (relu) acc = fmaxf(acc, 0.f);
+    y[idx] = from_float<TY>(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Stem operand builders (explicit im2col of the two 7x7/2 stems only; every other conv is
+// implicit).  One thread writes one 16-byte chunk (8 bf16) of an operand row.
+// ------------------------------------------------------------------------------------
+template <typename TX>
+__global__ void im2col_rgb_stem_kernel(const TX* __restrict__ x, __nv_bfloat16* __restrict__ a,
+                                       int N, int H, int W, int P, int Q) {
+  constexpr int KP = 192, CHUNKS = KP / 8;
+  const long long total = (long long)N * P * Q * CHUNKS;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % CHUNKS);
+    const long long m = idx / CHUNKS;
+    const int q = (int)(m % Q);
+    const int p = (int)((m / Q) % P);
+    const int n = (int)(m / ((long long)P * Q));
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kk = ch * 8 + e;
+      float f = 0.f;
+      if (kk < 147) {
+        const int c = kk % 3, tap = kk / 3;
+        const int s = tap % 7, r = tap / 7;
+        const int ih = p * 2 + r - 3, iw = q * 2 + s - 3;
+        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
+          f = to_float<TX>(__ldg(x + ((size_t)(n * H + ih) * W + iw) * 3 + c));
+      }
+      v[e] = __float2bfloat16_rn(f);
+    }
+    *reinterpret_cast<uint4*>(a + m * KP + ch * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+__global__ void im2col_depth_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a,
+                                         int N, int H, int W, int P, int Q) {
+  // x: (N,H,W,1); pooled image is (H/2, W/2); output pixel (p,q) of the 7x7/2 pad-3 conv
+  constexpr int KP = 64, CHUNKS = KP / 8;
+  const int Hp = H / 2, Wp = W / 2;
+  const long long total = (long long)N * P * Q * CHUNKS;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % CHUNKS);
+    const long long m = idx / CHUNKS;
+    const int q = (int)(m % Q);
+    const int p = (int)((m / Q) % P);
+    const int n = (int)(m / ((long long)P * Q));
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int kk = ch * 8 + e;
+      float f = 0.f;
+      if (kk < 49) {
+        const int s = kk % 7, r = kk / 7;
+        const int ih = p * 2 + r - 3, iw = q * 2 + s - 3;
+        if ((unsigned)ih < (unsigned)Hp && (unsigned)iw < (unsigned)Wp) {
+          const float* b = x + ((size_t)(n * H + 2 * ih) * W + 2 * iw);
+          f = ((__ldg(b) + __ldg(b + 1)) + (__ldg(b + W) + __ldg(b + W + 1))) * 0.25f;
+        }
+      }
+      v[e] = __float2bfloat16_rn(f);
+    }
+    *reinterpret_cast<uint4*>(a + m * KP + ch * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+__global__ void avgpool2x2_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H,
+                                  int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long long m = idx / C;
+    const int q = (int)(m % Wo);
+    const int p = (int)((m / Wo) % Ho);
+    const int n = (int)(m / ((long long)Ho * Wo));
+    const float* b = x + ((size_t)(n * H + 2 * p) * W + 2 * q) * C + c;
+    y[idx] = ((b[0] + b[C]) + (b[(size_t)W * C] + b[(size_t)W * C + C])) * 0.25f;
+  }
+}
+
+template <typename T>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W,
+                                    int C, int P, int Q) {
+  const long long total = (long long)N * P * Q * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const long long m = idx / C;
+    const int q = (int)(m % Q);
+    const int p = (int)((m / Q) % P);
+    const int n = (int)(m / ((long long)P * Q));
+    float best = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = p * 2 + r - 1;
+      if ((unsigned)ih >= (unsigned)H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = q * 2 + s - 1;
+        if ((unsigned)iw >= (unsigned)W) continue;
+        best = fmaxf(best, to_float<T>(x[((size_t)(n * H + ih) * W + iw) * C + c]));
+      }
+    }
+    y[idx] = from_float<T>(best);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// GroupNorm statistics: one CTA per (sample, group).  fp32 partials, fp64 combine.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void groupnorm_stats_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float* __restrict__ scale,
+                                       float* __restrict__ shift, int HW, int C, int groups, float eps) {
+  const int n = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cpg = C / groups;
+  const long long count = (long long)HW * cpg;
+  const T* base = x + (size_t)n * HW * C + g * cpg;
+  float s = 0.f, ss = 0.f;
+  for (long long e = threadIdx.x; e < count; e += blockDim.x) {
+    const int pix = (int)(e / cpg), ch = (int)(e % cpg);
+    const float v = to_float<T>(base[(size_t)pix * C + ch]);
+    s += v;
+    ss = fmaf(v, v, ss);
+  }
+  __shared__ double sh_s[32], sh_ss[32];
+  double ds = s, dss = ss;
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dss += __shfl_xor_sync(0xffffffffu, dss, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { sh_s[wid] = ds; sh_ss[wid] = dss; }
+  __syncthreads();
+  if (wid == 0) {
+    ds = lane < nw ? sh_s[lane] : 0.0;
+    dss = lane < nw ? sh_ss[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      dss += __shfl_xor_sync(0xffffffffu, dss, o);
+    }
+    if (lane == 0) { sh_s[0] = ds; sh_ss[0] = dss; }
+  }
+  __syncthreads();
+  const double mean = sh_s[0] / (double)count;
+  double var = sh_ss[0] / (double)count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  for (int ch = threadIdx.x; ch < cpg; ch += blockDim.x) {
+    const int c = g * cpg + ch;
+    const float sc = rstd * gamma[c];
+    scale[(size_t)n * C + c] = sc;
+    shift[(size_t)n * C + c] = beta[c] - (float)mean * sc;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Train-mode BatchNorm statistics: per-channel sums over all rows.
+// Pass 1: grid (row splits) accumulates fp64 partial sums with atomics into workspace[2*C]
+// (zeroed by the caller-visible memset below); pass 2 finalises + updates running stats.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bn_partial_kernel(const T* __restrict__ x, double* __restrict__ ws, long long rows,
+                                  int C) {
+  // blockDim.x threads walk channels (coalesced), blockIdx.y splits rows
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = per * blockIdx.y, r1 = min(rows, r0 + per);
+  float s = 0.f, ss = 0.f;
+  double ds = 0.0, dss = 0.0;
+  int cnt = 0;
+  for (long long r = r0; r < r1; ++r) {
+    const float v = to_float<T>(x[(size_t)r * C + c]);
+    s += v;
+    ss = fmaf(v, v, ss);
+    if (++cnt == 256) { ds += s; dss += ss; s = 0.f; ss = 0.f; cnt = 0; }
+  }
+  ds += s; dss += ss;
+  atomicAdd(&ws[c], ds);
+  atomicAdd(&ws[C + c], dss);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   long long rows, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = ws[c] / (double)rows;
+  double var = ws[C + c] / (double)rows - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = rstd * gamma[c];
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)mean * sc;
+  if (running_mean != nullptr) {
+    const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// y = act(x * scale[n|0, c] + shift (+ residual)); 8 channels (16 B of bf16) per thread.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void affine_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int scale_stride_n,
+                                    const T* __restrict__ residual, T* __restrict__ y, int HW, int C,
+                                    long long total_vec, int relu) {
+  constexpr int V = 8;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_vec;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long e0 = idx * V;
+    const int c0 = (int)(e0 % C);
+    const long long row = e0 / C;
+    const int n = (int)(row / HW);
+    const float* sc = scale + (size_t)n * scale_stride_n + c0;
+    const float* sh = shift + (size_t)n * scale_stride_n + c0;
+    float f[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) f[e] = fmaf(to_float<T>(x[e0 + e]), sc[e], sh[e]);
+    if (residual != nullptr) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) f[e] += to_float<T>(residual[e0 + e]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) f[e] = fmaxf(f[e], 0.f);
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) y[e0 + e] = from_float<T>(f[e]);
+  }
+}
+
+// adaptive_avg_pool2d -> (O,O): bin i covers [floor(i*H/O), ceil((i+1)*H/O))
+template <typename T>
+__global__ void adaptive_avgpool_kernel(const T* __restrict__ x, float* __restrict__ y, int ldy,
+                                        int N, int H, int W, int C, int O) {
+  const int OO = O * O;
+  const long long total = (long long)N * OO * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int pos = (int)((idx / C) % OO);
+    const int n = (int)(idx / ((long long)OO * C));
+    const int oi = pos / O, oj = pos % O;
+    const int h0 = (oi * H) / O, h1 = ((oi + 1) * H + O - 1) / O;
+    const int w0 = (oj * W) / O, w1 = ((oj + 1) * W + O - 1) / O;
+    float acc = 0.f;
+    for (int ih = h0; ih < h1; ++ih)
+      for (int iw = w0; iw < w1; ++iw) acc += to_float<T>(x[((size_t)(n * H + ih) * W + iw) * C + c]);
+    y[((size_t)n * OO + pos) * ldy + c] = acc / (float)((h1 - h0) * (w1 - w0));
+  }
+}
+
+// (N, C, P) -> (N, P, ldy) slice.  32x32 smem transpose per (n, tile).
+__global__ void nchw_to_positions_kernel(const float* __restrict__ x, float* __restrict__ y, int ldy,
+                                         int C, int P) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+  const float* xb = x + (size_t)n * C * P;
+  float* yb = y + (size_t)n * P * ldy;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < P) ? xb[(size_t)c * P + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < P) yb[(size_t)p * ldy + c] = tile[threadIdx.x][i];
+  }
+}
+
+inline unsigned grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148ll * 32;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <typename TX, typename TW>
+int conv_ref_dispatch_y(const void* x, const void* w, const float* scale, const float* shift,
+                        const void* residual, int res_dtype, void* y, int y_dtype, int N, int H, int W,
+                        int C, int K, int R, int S, int stride, int pad, int P, int Q, int relu,
+                        cudaStream_t st) {
+  const long long total = (long long)N * P * Q * K;
+  const unsigned grid = grid_for(total, 256);
+#define GO(TY, TR)                                                                              \
+  conv_ref_kernel<TX, TW, TY, TR><<<grid, 256, 0, st>>>(                                        \
+      (const TX*)x, (const TW*)w, scale, shift, (const TR*)residual, (TY*)y, N, H, W, C, K, R, S, \
+      stride, pad, P, Q, relu)
+  const bool rb = residual != nullptr && res_dtype == VLNCE_BF16;
+  if (y_dtype == VLNCE_F32) {
+    if (rb) GO(float, __nv_bfloat16); else GO(float, float);
+  } else {
+    if (rb || residual == nullptr) GO(__nv_bfloat16, __nv_bfloat16); else GO(__nv_bfloat16, float);
+  }
+#undef GO
+  VLNCE_LAUNCH_CHECK("conv_ref_kernel");
+  return VLNCE_OK;
+}
+
+}  // namespace
+}  // namespace vlnce
+
+using namespace vlnce;
+
+extern "C" int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w_dtype,
+                                const float* scale, const float* shift, const void* residual,
+                                int res_dtype, void* y, int y_dtype, int N, int H, int W, int C, int K,
+                                int R, int S, int stride, int pad, int relu, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && w && y, "conv2d_ref: null tensor");
+  VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv2d_ref: scale/shift must come together");
+  VLNCE_CHECK_ARG(y_dtype == VLNCE_F32 || y_dtype == VLNCE_BF16, "conv2d_ref: y dtype");
+  VLNCE_CHECK_ARG(w_dtype == VLNCE_F32 || w_dtype == VLNCE_BF16, "conv2d_ref: w dtype");
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  VLNCE_CHECK_ARG(P > 0 && Q > 0, "conv2d_ref: empty output");
+#define ARGS x, w, scale, shift, residual, res_dtype, y, y_dtype, N, H, W, C, K, R, S, stride, pad, P, Q, relu, stream
+  if (w_dtype == VLNCE_F32) {
+    if (x_dtype == VLNCE_F32) return conv_ref_dispatch_y<float, float>(ARGS);
+    if (x_dtype == VLNCE_U8) return conv_ref_dispatch_y<uint8_t, float>(ARGS);
+    if (x_dtype == VLNCE_BF16) return conv_ref_dispatch_y<__nv_bfloat16, float>(ARGS);
+  } else {
+    if (x_dtype == VLNCE_F32) return conv_ref_dispatch_y<float, __nv_bfloat16>(ARGS);
+    if (x_dtype == VLNCE_U8) return conv_ref_dispatch_y<uint8_t, __nv_bfloat16>(ARGS);
+    if (x_dtype == VLNCE_BF16) return conv_ref_dispatch_y<__nv_bfloat16, __nv_bfloat16>(ARGS);
+  }
+#undef ARGS
+  set_error("conv2d_ref: unsupported x dtype %d", x_dtype);
+  return VLNCE_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int N, int H, int W,
+                                     cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && a && N > 0 && H > 0 && W > 0, "im2col_rgb_stem: bad arguments");
+  const int P = (H + 6 - 7) / 2 + 1, Q = (W + 6 - 7) / 2 + 1;
+  const long long total = (long long)N * P * Q * 24;
+  if (x_dtype == VLNCE_U8)
+    im2col_rgb_stem_kernel<uint8_t><<<grid_for(total, 256), 256, 0, stream>>>(
+        (const uint8_t*)x, (__nv_bfloat16*)a, N, H, W, P, Q);
+  else if (x_dtype == VLNCE_F32)
+    im2col_rgb_stem_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(
+        (const float*)x, (__nv_bfloat16*)a, N, H, W, P, Q);
+  else {
+    set_error("im2col_rgb_stem: rgb must be u8 or f32");
+    return VLNCE_ERR_INVALID_ARGUMENT;
+  }
+  VLNCE_LAUNCH_CHECK("im2col_rgb_stem_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_im2col_depth_stem(const float* x, void* a, int N, int H, int W,
+                                       cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && a && N > 0 && H > 1 && W > 1 && H % 2 == 0 && W % 2 == 0,
+                  "im2col_depth_stem: bad arguments");
+  const int Hp = H / 2, Wp = W / 2;
+  const int P = (Hp + 6 - 7) / 2 + 1, Q = (Wp + 6 - 7) / 2 + 1;
+  const long long total = (long long)N * P * Q * 8;
+  im2col_depth_stem_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)a, N, H, W, P, Q);
+  VLNCE_LAUNCH_CHECK("im2col_depth_stem_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_avgpool2x2(const float* x, float* y, int N, int H, int W, int C,
+                                cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && y && H % 2 == 0 && W % 2 == 0, "avgpool2x2: bad arguments");
+  const long long total = (long long)N * (H / 2) * (W / 2) * C;
+  avgpool2x2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, y, N, H, W, C);
+  VLNCE_LAUNCH_CHECK("avgpool2x2_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_maxpool3x3s2(const void* x, void* y, int dtype, int N, int H, int W, int C,
+                                  cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && y, "maxpool3x3s2: null tensor");
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * P * Q * C;
+  if (dtype == VLNCE_BF16)
+    maxpool3x3s2_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, P, Q);
+  else if (dtype == VLNCE_F32)
+    maxpool3x3s2_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>((const float*)x, (float*)y, N,
+                                                                         H, W, C, P, Q);
+  else {
+    set_error("maxpool3x3s2: dtype");
+    return VLNCE_ERR_INVALID_ARGUMENT;
+  }
+  VLNCE_LAUNCH_CHECK("maxpool3x3s2_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_groupnorm_stats(const void* x, int dtype, const float* gamma, const float* beta,
+                                     float* scale, float* shift, int N, int HW, int C, int groups,
+                                     float eps, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && gamma && beta && scale && shift && groups > 0 && C % groups == 0,
+                  "groupnorm_stats: bad arguments");
+  if (dtype == VLNCE_BF16)
+    groupnorm_stats_kernel<__nv_bfloat16><<<N * groups, 256, 0, stream>>>(
+        (const __nv_bfloat16*)x, gamma, beta, scale, shift, HW, C, groups, eps);
+  else if (dtype == VLNCE_F32)
+    groupnorm_stats_kernel<float><<<N * groups, 256, 0, stream>>>((const float*)x, gamma, beta, scale,
+                                                                  shift, HW, C, groups, eps);
+  else {
+    set_error("groupnorm_stats: dtype");
+    return VLNCE_ERR_INVALID_ARGUMENT;
+  }
+  VLNCE_LAUNCH_CHECK("groupnorm_stats_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_batchnorm_train_stats(const void* x, int dtype, const float* gamma,
+                                           const float* beta, float* running_mean, float* running_var,
+                                           float momentum, float* scale, float* shift,
+                                           double* workspace, long long rows, int C, float eps,
+                                           cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && gamma && beta && scale && shift && workspace && rows > 0 && C > 0,
+                  "batchnorm_train_stats: bad arguments");
+  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * C, stream);
+  if (e != cudaSuccess) return cuda_status(e, "batchnorm_train_stats memset");
+  const int splits = (int)(rows / 512 < 1 ? 1 : (rows / 512 > 512 ? 512 : rows / 512));
+  dim3 grid(cdiv(C, 128), splits);
+  if (dtype == VLNCE_BF16)
+    bn_partial_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)x, workspace, rows, C);
+  else if (dtype == VLNCE_F32)
+    bn_partial_kernel<float><<<grid, 128, 0, stream>>>((const float*)x, workspace, rows, C);
+  else {
+    set_error("batchnorm_train_stats: dtype");
+    return VLNCE_ERR_INVALID_ARGUMENT;
+  }
+  VLNCE_LAUNCH_CHECK("bn_partial_kernel");
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, stream>>>(workspace, gamma, beta, running_mean, running_var,
+                                                      momentum, scale, shift, rows, C, eps);
+  VLNCE_LAUNCH_CHECK("bn_finalize_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_affine_apply(const void* x, const float* scale, const float* shift,
+                                  int scale_stride_n, const void* residual, void* y, int dtype, int N,
+                                  int HW, int C, int relu, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && y && scale && shift && C % 8 == 0, "affine_apply: bad arguments (C %% 8)");
+  const long long total_vec = (long long)N * HW * C / 8;
+  if (dtype == VLNCE_BF16)
+    affine_apply_kernel<__nv_bfloat16><<<grid_for(total_vec, 256), 256, 0, stream>>>(
+        (const __nv_bfloat16*)x, scale, shift, scale_stride_n, (const __nv_bfloat16*)residual,
+        (__nv_bfloat16*)y, HW, C, total_vec, relu);
+  else if (dtype == VLNCE_F32)
+    affine_apply_kernel<float><<<grid_for(total_vec, 256), 256, 0, stream>>>(
+        (const float*)x, scale, shift, scale_stride_n, (const float*)residual, (float*)y, HW, C,
+        total_vec, relu);
+  else {
+    set_error("affine_apply: dtype");
+    return VLNCE_ERR_INVALID_ARGUMENT;
+  }
+  VLNCE_LAUNCH_CHECK("affine_apply_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_adaptive_avgpool(const void* x, int dtype, float* y, int ldy, int N, int H, int W,
+                                      int C, int O, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && y && ldy >= C && (O == 1 || O == 4), "adaptive_avgpool: bad arguments");
+  const long long total = (long long)N * O * O * C;
+  if (dtype == VLNCE_BF16)
+    adaptive_avgpool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
+        (const __nv_bfloat16*)x, y, ldy, N, H, W, C, O);
+  else if (dtype == VLNCE_F32)
+    adaptive_avgpool_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>((const float*)x, y, ldy, N,
+                                                                             H, W, C, O);
+  else {
+    set_error("adaptive_avgpool: dtype");
+    return VLNCE_ERR_INVALID_ARGUMENT;
+  }
+  VLNCE_LAUNCH_CHECK("adaptive_avgpool_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_nchw_to_positions(const float* x, float* y, int ldy, int N, int C, int P,
+                                       cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && y && ldy >= C, "nchw_to_positions: bad arguments");
+  dim3 grid(cdiv(C, 32), cdiv(P, 32), N), block(32, 8);
+  nchw_to_positions_kernel<<<grid, block, 0, stream>>>(x, y, ldy, C, P);
+  VLNCE_LAUNCH_CHECK("nchw_to_positions_kernel");
+  return VLNCE_OK;
+}

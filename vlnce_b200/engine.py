@@ -1,0 +1,256 @@
+"""Launch sequencing of the CMA head (forward and hand-written backward) over the C-ABI
+kernels.  Follows ``CMANet.forward`` (``cma_policy.py:219-309``) step by step; the only
+algebraic change is the re-association of the three single-query attentions
+(``_attn``, ``cma_policy.py:207-217``): with k_p = W_k e_p + b_k,
+
+    q.k_p = (W_k^T q).e_p + q.b_k        (the constant cancels in the softmax)
+    sum_p a_p (W_v e_p + b_v) = W_v (sum_p a_p e_p) + b_v
+
+so keys/values are never materialised — the raw embedding is attention-pooled once and the
+value projection runs on the pooled vector (16x fewer MACs for the visual attentions, 80x for
+the text keys).  Everything is fp32; rows are time-major (T*N, .) as ``collate_fn`` builds them.
+
+Python here only orders kernel launches on the current CUDA stream and owns the persistent
+workspace (static addresses, CUDA-graph capturable).  No tensor arithmetic happens in torch.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import lib
+from .lib import C, ptr
+from .trunk import BufferPool
+
+
+def _gemm(a, lda_m, lda_k, b, ldb_k, ldb_n, c, ldc, bias, m, n, k, beta=0.0, act=0):
+    C.vlnce_sgemm(a, lda_m, lda_k, b, ldb_k, ldb_n, c, ldc, bias, m, n, k, float(beta), int(act),
+                  lib.stream())
+
+
+def linear(x, ldx, w, out, ldo, bias, rows, n_out, n_in, act=0, beta=0.0, ldw=None):
+    """out[rows, n_out] = act(x[rows, n_in] @ w[n_out, n_in]^T + bias) — pointers, not tensors."""
+    ldw = n_in if ldw is None else ldw
+    _gemm(x, ldx, 1, w, 1, ldw, out, ldo, bias, rows, n_out, n_in, beta, act)
+
+
+def linear_dx(dy, lddy, w, dx, lddx, rows, n_out, n_in, beta=0.0, ldw=None):
+    """dx[rows, n_in] (+)= dy[rows, n_out] @ w[n_out, n_in]"""
+    ldw = n_in if ldw is None else ldw
+    _gemm(dy, lddy, 1, w, ldw, 1, dx, lddx, None, rows, n_in, n_out, beta, 0)
+
+
+def linear_dw(dy, lddy, x, ldx, dw, lddw, rows, n_out, n_in, beta=0.0):
+    """dw[n_out, n_in] (+)= dy[rows, n_out]^T @ x[rows, n_in]"""
+    _gemm(dy, 1, lddy, x, ldx, 1, dw, lddw, None, n_out, n_in, rows, beta, 0)
+
+
+F4 = 4  # sizeof(float)
+
+
+def off(t: torch.Tensor, elems: int) -> int:
+    """device pointer of ``t`` advanced by ``elems`` fp32 elements"""
+    return t.data_ptr() + F4 * elems
+
+
+class CMAEngine:
+    """Forward/backward launch plan bound to one ``CMANet`` (+ action head)."""
+
+    def __init__(self, net, precision: str = "bf16"):
+        self.net = net
+        self.precision = precision
+        self.pool: Optional[BufferPool] = None
+        self.ctx: Dict[str, object] = {}
+        cfg = net.model_config
+        self.H = cfg.STATE_ENCODER.hidden_size
+        self.rgb_out = cfg.RGB_ENCODER.output_size
+        self.depth_out = cfg.DEPTH_ENCODER.output_size
+        ie = net.instruction_encoder
+        self.Hs = ie.config.hidden_size
+        self.dirs = 2 if ie.config.bidirectional else 1
+        self.E = ie.config.embedding_size
+        self.Dt = self.Hs * self.dirs  # instruction feature size
+        self.Crgb = net.rgb_encoder.output_shape[0]      # 2112
+        self.Cdep = net.depth_encoder.output_shape[0]    # 192
+        self.P = 16
+        self.state_in = self.rgb_out + self.depth_out + 32
+        self.cat = self.H + self.Dt + self.rgb_out + self.depth_out + 32
+
+    def buf(self, name, shape, dtype=torch.float32):
+        return self.pool.get(name, shape, dtype)
+
+    # ------------------------------------------------------------------ GRU helper
+    def _gru_forward(self, tag, rnn, x, ldx, in_size, h0, ldh0, masks_f, out, ldo, h_final, ldhf, T, N,
+                     save):
+        """habitat_baselines v0.1.7 RNNStateEncoder forward (single step when T == 1, else a
+        T-step sequence with hidden reset where masks == 0); writes all T*N outputs into
+        ``out`` and the final hidden state into ``h_final``."""
+        H = self.H
+        R = T * N
+        gi = self.buf(tag + "_gi", (R, 3 * H))
+        linear(x, ldx, ptr(rnn.weight_ih_l0), ptr(gi), 3 * H, ptr(rnn.bias_ih_l0), R, 3 * H, in_size)
+        hm_all = self.buf(tag + "_hm", (R, H))
+        gh = self.buf(tag + "_gh", (N, 3 * H))
+        sv = self.buf(tag + "_save", (R, 4 * H)) if save else None
+        st = lib.stream()
+        for t in range(T):
+            hm = off(hm_all, t * N * H)
+            if t == 0:
+                C.vlnce_mask_rows(h0, ldh0, off(masks_f, 0), hm, H, N, H, st)
+            else:
+                C.vlnce_mask_rows(out + F4 * (t - 1) * N * ldo, ldo, off(masks_f, t * N), hm, H, N, H, st)
+            linear(hm, H, ptr(rnn.weight_hh_l0), ptr(gh), 3 * H, ptr(rnn.bias_hh_l0), N, 3 * H, H)
+            last = t == T - 1
+            C.vlnce_gru_pointwise_fwd(off(gi, t * N * 3 * H), ptr(gh), hm, H, out + F4 * t * N * ldo, ldo,
+                                      h_final if last else None, ldhf,
+                                      off(sv, t * N * 4 * H) if save else None, N, H, st)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, observations, rnn_states, prev_actions, masks, save: bool):
+        net = self.net
+        dev = rnn_states.device
+        lib.require_cuda(rnn_states, "rnn_states")
+        if self.pool is None or self.pool.device != dev:
+            self.pool = BufferPool(dev)
+        st = lib.stream()
+        H, P = self.H, self.P
+        N = rnn_states.shape[0]
+        R = prev_actions.shape[0]
+        assert R % N == 0, "rows must be T*N (time-major)"
+        T = R // N
+        rnn_states = rnn_states.contiguous().float()
+        masks_f = self.buf("masks_f", (R,))
+        masks_f.copy_(masks.reshape(-1))  # dtype cast only (uint8/bool/float -> f32)
+        prev = prev_actions.reshape(-1)
+        if prev.dtype != torch.int64:
+            prev = prev.long()
+        prev = prev.contiguous()
+
+        # ---- instruction encoder (instruction_encoder.py:63-94)
+        ie = net.instruction_encoder
+        lengths = self.buf("lengths", (R,), torch.int32)
+        if ie.config.sensor_uuid == "instruction":
+            ids = observations["instruction"]
+            lib.require_cuda(ids, "instruction")
+            ids = ids.long().contiguous()
+            L = ids.shape[1]
+            C.vlnce_token_lengths(ptr(ids), ptr(lengths), R, L, st)
+            emb = self.buf("instr_emb", (R * L, self.E))
+            C.vlnce_embedding_fwd(ptr(ids), ptr(ie.embedding_layer.weight), ptr(emb), R * L, self.E, self.E,
+                                  ie.embedding_layer.num_embeddings, st)
+            self.ctx["ids"] = ids
+        else:
+            emb = observations["rxr_instruction"]
+            lib.require_cuda(emb, "rxr_instruction")
+            emb = emb.contiguous().float()
+            L = emb.shape[1]
+            C.vlnce_feature_lengths(ptr(emb), ptr(lengths), R, L, self.E, st)
+        Hs, dirs = self.Hs, self.dirs
+        rnn = ie.encoder_rnn
+        gx = self.buf("lstm_gx", (dirs, R, L, 4 * Hs))
+        wih = [rnn.weight_ih_l0] + ([rnn.weight_ih_l0_reverse] if dirs == 2 else [])
+        bih = [rnn.bias_ih_l0] + ([rnn.bias_ih_l0_reverse] if dirs == 2 else [])
+        for d in range(dirs):
+            linear(ptr(emb), self.E, ptr(wih[d]), off(gx, d * R * L * 4 * Hs), 4 * Hs, ptr(bih[d]), R * L,
+                   4 * Hs, self.E)
+        instr = self.buf("instr_out", (R, L, self.Dt))
+        hn = self.buf("lstm_hn", (dirs, R, Hs))
+        sg = self.buf("lstm_gates", (dirs, R, L, 4 * Hs)) if save else None
+        sc = self.buf("lstm_c", (dirs, R, L, Hs)) if save else None
+        C.vlnce_lstm_seq_fwd(ptr(gx), ptr(rnn.weight_hh_l0),
+                             ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None, ptr(rnn.bias_hh_l0),
+                             ptr(rnn.bias_hh_l0_reverse) if dirs == 2 else None, ptr(lengths), ptr(instr),
+                             ptr(hn), ptr(sg), ptr(sc), R, L, Hs, dirs, st)
+
+        # ---- visual encoders + spatial embeddings (cma_policy.py:227-231)
+        rgb_e = self.buf("rgb_emb", (R, P, self.Crgb))
+        dep_e = self.buf("depth_emb", (R, P, self.Cdep))
+        c_rgb = net.rgb_encoder.resnet_layer_size
+        c_dep = net.depth_encoder.visual_encoder.output_shape[0]
+        net.rgb_encoder.features_into(observations, rgb_e, self.Crgb, self.precision)
+        net.depth_encoder.features_into(observations, dep_e, self.Cdep, self.precision)
+        C.vlnce_spatial_embed_fill(ptr(net.rgb_encoder.spatial_embeddings.weight), ptr(rgb_e), P * self.Crgb,
+                                   self.Crgb, c_rgb, R, P, 64, st)
+        C.vlnce_spatial_embed_fill(ptr(net.depth_encoder.spatial_embeddings.weight), ptr(dep_e),
+                                   P * self.Cdep, self.Cdep, c_dep, R, P, 64, st)
+
+        # ---- prev-action embedding into both concat slices (cma_policy.py:233-235, Q6)
+        state_in = self.buf("state_in", (R, self.state_in))
+        xcat = self.buf("xcat", (R, self.cat))
+        pa_w = net.prev_action_embedding.weight
+        C.vlnce_prev_action_embed(ptr(prev), ptr(masks_f), ptr(pa_w), off(state_in, self.rgb_out + self.depth_out),
+                                  self.state_in, off(xcat, self.cat - 32), self.cat, R, 32, pa_w.shape[0], st)
+        self.ctx["prev"] = prev
+
+        # ---- rgb_linear / depth_linear (cma_policy.py:244-245)
+        rgb_mean = self.buf("rgb_mean", (R, self.Crgb))
+        C.vlnce_mean_positions(ptr(rgb_e), P * self.Crgb, self.Crgb, ptr(rgb_mean), self.Crgb, R, P, self.Crgb, st)
+        lin = net.rgb_linear[2]
+        linear(ptr(rgb_mean), self.Crgb, ptr(lin.weight), ptr(state_in), self.state_in, ptr(lin.bias), R,
+               self.rgb_out, self.Crgb, act=1)
+        dep_flat = self.buf("depth_flat", (R, self.Cdep * P))
+        C.vlnce_positions_to_nchw(ptr(dep_e), P * self.Cdep, self.Cdep, ptr(dep_flat), self.Cdep * P, R, P,
+                                  self.Cdep, st)
+        lin = net.depth_linear[1]
+        linear(ptr(dep_flat), self.Cdep * P, ptr(lin.weight), off(state_in, self.rgb_out), self.state_in,
+               ptr(lin.bias), R, self.depth_out, self.Cdep * P, act=1)
+
+        # ---- first GRU -> xcat[:, 0:H]  (cma_policy.py:247-256)
+        h_out = self.buf("rnn_states_out", (N, 2, H))
+        self._gru_forward("gru1", net.state_encoder.rnn, ptr(state_in), self.state_in, self.state_in,
+                          ptr(rnn_states), 2 * H, masks_f, ptr(xcat), self.cat, ptr(h_out), 2 * H, T, N, save)
+
+        # ---- text attention (cma_policy.py:258-263)
+        if "scale" not in self.__dict__:
+            self.scale = float(net._scale)  # one host sync, cached
+        scale = self.scale
+        hk = H // 2
+        q_s = self.buf("q_state", (R, hk))
+        linear(ptr(xcat), self.cat, ptr(net.state_q.weight), ptr(q_s), hk, ptr(net.state_q.bias), R, hk, H)
+        q_t = self.buf("q_text", (R, self.Dt))
+        linear_dx(ptr(q_s), hk, ptr(net.text_k.weight), ptr(q_t), self.Dt, R, hk, self.Dt)  # W_k^T q
+        p_text = self.buf("p_text", (R, L)) if save else None
+        C.vlnce_attn_pool_fwd(ptr(q_t), self.Dt, ptr(instr), L * self.Dt, self.Dt, ptr(lengths), scale,
+                              ptr(p_text), off(xcat, H), self.cat, R, L, self.Dt, st)
+
+        # ---- visual attentions (cma_policy.py:265-274)
+        text_q = self.buf("text_q", (R, hk))
+        linear(off(xcat, H), self.cat, ptr(net.text_q.weight), ptr(text_q), hk, ptr(net.text_q.bias), R, hk, self.Dt)
+        for name, E_, Cc, kv, v_out, col in (
+                ("rgb", rgb_e, self.Crgb, net.rgb_kv, self.rgb_out, H + self.Dt),
+                ("depth", dep_e, self.Cdep, net.depth_kv, self.depth_out, H + self.Dt + self.rgb_out)):
+            qv = self.buf("q_" + name, (R, Cc))
+            linear_dx(ptr(text_q), hk, ptr(kv.weight), ptr(qv), Cc, R, hk, Cc)  # W_k = rows [0, hk)
+            probs = self.buf("p_" + name, (R, P)) if save else None
+            pooled = self.buf("pooled_" + name, (R, Cc))
+            C.vlnce_attn_pool_fwd(ptr(qv), Cc, ptr(E_), P * Cc, Cc, None, scale, ptr(probs), ptr(pooled), Cc,
+                                  R, P, Cc, st)
+            linear(ptr(pooled), Cc, off(kv.weight, hk * Cc), off(xcat, col), self.cat, off(kv.bias, hk), R,
+                   v_out, Cc)  # W_v = rows [hk, hk+v_out)
+
+        # ---- compress + second GRU (cma_policy.py:276-294)
+        x2 = self.buf("x2", (R, H))
+        lin = net.second_state_compress[0]
+        linear(ptr(xcat), self.cat, ptr(lin.weight), ptr(x2), H, ptr(lin.bias), R, H, self.cat, act=1)
+        x_out = self.buf("x_out", (R, H))
+        self._gru_forward("gru2", net.second_state_encoder.rnn, ptr(x2), H, H, off(rnn_states, H), 2 * H,
+                          masks_f, ptr(x_out), H, off(h_out, H), 2 * H, T, N, save)
+
+        # ---- progress monitor (cma_policy.py:296) — tanh(Linear(x)); the loss lives in the caller
+        hat = None
+        if net.model_config.PROGRESS_MONITOR.use:
+            hat = self.buf("progress_hat", (R, 1))
+            pm = net.progress_monitor
+            linear(ptr(x_out), H, ptr(pm.weight), ptr(hat), 1, ptr(pm.bias), R, 1, H, act=2)
+        self.ctx.update(R=R, N=N, T=T, L=L, lengths=lengths, saved=save)
+        return x_out, h_out, hat
+
+    # ------------------------------------------------------------------ action head
+    def action_logits(self, head_linear, x_out, R):
+        """CategoricalNet (policy.py:19-21,37): Linear then the log-softmax Categorical applies."""
+        A = head_linear.weight.shape[0]
+        logits = self.buf("logits", (R, A))
+        linear(ptr(x_out), self.H, ptr(head_linear.weight), ptr(logits), A, ptr(head_linear.bias), R, A, self.H)
+        C.vlnce_log_softmax_rows(ptr(logits), R, A, lib.stream())
+        return logits

@@ -1,0 +1,302 @@
+"""Launch plans for the two frozen conv trunks of the policy, driving the C-ABI kernels.
+
+* RGB: torchvision ResNet-50/18 v1.5 with BatchNorm (``resnet_encoders.py:118-229``):
+  eval-mode BN is folded into the conv epilogue (scale/shift + residual + ReLU); train-mode
+  BN (the constructor default) runs conv -> batch statistics -> fused apply and
+  updates the running statistics like ``torch.nn.BatchNorm2d``.
+* Depth: DD-PPO GroupNorm ResNet-50 + 3x3 compression (``resnet_encoders.py:17-115``;
+  habitat_baselines v0.1.7 ``ResNetEncoder``): conv (raw) -> GroupNorm statistics -> fused
+  normalise(+residual)(+ReLU).
+
+Activations are NHWC (the simulator's layout, so no permute) in bf16 (``precision="bf16"``,
+tcgen05 tensor-core tiles) or fp32 (``precision="fp32"``, CUDA-core reference conv — the
+1e-3 parity mode).  Weights are re-packed (KRSC, folded norms) whenever the parameters'
+version counters change.  Python only sequences launches; all arithmetic is in the library.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import lib
+from .lib import C, ptr
+
+
+class BufferPool:
+    """Named persistent device buffers (static addresses -> CUDA-graph friendly)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, shape, dtype) -> torch.Tensor:
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        b = self._bufs.get(name)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            self._bufs[name] = b
+        return b[:nbytes].view(dtype).view(*shape)
+
+    def nbytes(self) -> int:
+        return sum(b.numel() for b in self._bufs.values())
+
+
+def _version(params) -> tuple:
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+class _Conv:
+    """One packed convolution (+ its normalisation)."""
+
+    def __init__(self, conv: nn.Conv2d, norm: nn.Module, precision: str, in_scale: float = 1.0,
+                 stem: Optional[str] = None):
+        self.conv, self.norm, self.precision, self.in_scale, self.stem = conv, norm, precision, in_scale, stem
+        self.K, self.Cin, self.R, self.S = conv.weight.shape
+        self.stride, self.pad = conv.stride[0], conv.padding[0]
+        self.w = self.scale = self.shift = None
+        self._ver = None
+
+    def params(self):
+        ps = [self.conv.weight]
+        ps += [p for p in self.norm.parameters()] + [b for b in self.norm.buffers()]
+        return ps
+
+    def pack(self):
+        ver = _version(self.params())
+        if ver == self._ver:
+            return
+        w = self.conv.weight.detach()
+        wdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        krsc = w.permute(0, 2, 3, 1).contiguous()
+        if self.precision == "bf16" and self.stem == "rgb":  # im2col operand: (r*7+s)*3+c, pad 147->192
+            flat = krsc.reshape(self.K, -1)
+            krsc = torch.zeros(self.K, 192, device=w.device, dtype=w.dtype)
+            krsc[:, : flat.shape[1]] = flat
+        elif self.precision == "bf16" and self.stem == "depth":  # r*7+s, pad 49->64
+            flat = krsc.reshape(self.K, -1)
+            krsc = torch.zeros(self.K, 64, device=w.device, dtype=w.dtype)
+            krsc[:, : flat.shape[1]] = flat
+        self.w = krsc.to(wdt).contiguous()
+        if isinstance(self.norm, nn.BatchNorm2d):
+            n = self.norm
+            sc = n.weight.detach().float() / torch.sqrt(n.running_var.detach().float() + n.eps)
+            sh = n.bias.detach().float() - n.running_mean.detach().float() * sc
+            self.scale = (sc * self.in_scale).contiguous()
+            self.shift = sh.contiguous()
+            self.pre_scale = torch.full_like(sc, self.in_scale)
+            self.pre_shift = torch.zeros_like(sc)
+        self._ver = ver
+
+
+class ConvTrunk:
+    def __init__(self, device, precision: str = "bf16"):
+        assert precision in ("bf16", "fp32")
+        self.device = device
+        self.precision = precision
+        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.pool = BufferPool(device)
+        self._slot = 0
+
+    # -------------------------------------------------------------- low-level steps
+    def _act(self, tag: str, shape):
+        return self.pool.get(tag, shape, self.adt)
+
+    def _conv(self, x, shape_in, cv: _Conv, y, *, scale, shift, residual=None, relu=False,
+              gemm_c: Optional[int] = None):
+        """x NHWC (n,h,w,c) -> y; ``gemm_c`` set = x is an explicit stem operand (n*p*q, gemm_c)."""
+        n, h, w, c = shape_in
+        st = lib.stream()
+        if self.precision == "bf16":
+            if gemm_c is not None:
+                C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y),
+                                    lib.BF16, n * h * w, 1, 1, gemm_c, cv.K, 1, 1, 1, 0, int(relu), 0, st)
+            else:
+                C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y),
+                                    lib.BF16, n, h, w, c, cv.K, cv.R, cv.S, cv.stride, cv.pad, int(relu),
+                                    0, st)
+        else:
+            C.vlnce_conv2d_ref(ptr(x), lib.code(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift),
+                               ptr(residual), lib.F32, ptr(y), lib.F32, n, h, w, c, cv.K, cv.R, cv.S,
+                               cv.stride, cv.pad, int(relu), st)
+
+    @staticmethod
+    def _out_hw(h, w, cv: _Conv):
+        return ((h + 2 * cv.pad - cv.R) // cv.stride + 1, (w + 2 * cv.pad - cv.S) // cv.stride + 1)
+
+
+# ======================================================================================
+class RGBTrunk(ConvTrunk):
+    """torchvision ResNet trunk; ``cnn`` = the nn.Sequential holding conv1,bn1,relu,maxpool,
+    layer1..4 (state_dict keys ``net.rgb_encoder.cnn.{0..7}.*``)."""
+
+    def __init__(self, cnn: nn.Sequential, device, precision="bf16"):
+        super().__init__(device, precision)
+        mods = list(cnn.children())
+        self.stem = _Conv(mods[0], mods[1], precision, in_scale=1.0 / 255.0, stem="rgb")
+        self.blocks = []
+        for layer in mods[4:8]:
+            for blk in layer.children():
+                d = {"c1": _Conv(blk.conv1, blk.bn1, precision), "c2": _Conv(blk.conv2, blk.bn2, precision)}
+                if hasattr(blk, "conv3"):
+                    d["c3"] = _Conv(blk.conv3, blk.bn3, precision)
+                if blk.downsample is not None:
+                    d["ds"] = _Conv(blk.downsample[0], blk.downsample[1], precision)
+                self.blocks.append(d)
+        self.out_channels = self.blocks[-1]["c3" if "c3" in self.blocks[-1] else "c2"].K
+        self._bn_ws = None
+
+    def _all(self) -> List[_Conv]:
+        out = [self.stem]
+        for b in self.blocks:
+            out += list(b.values())
+        return out
+
+    def _norm_conv(self, x, shape_in, cv: _Conv, tag, *, residual=None, relu=True, gemm_c=None,
+                   out_hw=None):
+        n, h, w, _ = shape_in
+        p, q = out_hw if out_hw is not None else self._out_hw(h, w, cv)
+        y = self._act(tag, (n, p, q, cv.K))
+        bn: nn.BatchNorm2d = cv.norm
+        if not bn.training:
+            self._conv(x, shape_in, cv, y, scale=cv.scale, shift=cv.shift, residual=residual, relu=relu,
+                       gemm_c=gemm_c)
+            return y, (n, p, q, cv.K)
+        # train-mode BN (Q1): raw conv (input scaling only) -> batch stats -> fused apply
+        raw = self._act("bn_raw", (n, p, q, cv.K))
+        self._conv(x, shape_in, cv, raw, scale=cv.pre_scale if cv.in_scale != 1.0 else None,
+                   shift=cv.pre_shift if cv.in_scale != 1.0 else None, gemm_c=gemm_c)
+        st = lib.stream()
+        sc = self.pool.get("bn_scale", (cv.K,), torch.float32)
+        sh = self.pool.get("bn_shift", (cv.K,), torch.float32)
+        ws = self.pool.get("bn_ws", (2 * cv.K,), torch.float64)
+        mom = 0.1 if bn.momentum is None else bn.momentum
+        C.vlnce_batchnorm_train_stats(ptr(raw), lib.code(raw), ptr(bn.weight), ptr(bn.bias),
+                                      ptr(bn.running_mean), ptr(bn.running_var), float(mom), ptr(sc),
+                                      ptr(sh), ptr(ws), n * p * q, cv.K, float(bn.eps), st)
+        bn.num_batches_tracked += 1
+        cv._ver = None  # running stats changed under the folded eval-mode scale/shift
+        C.vlnce_affine_apply(ptr(raw), ptr(sc), ptr(sh), 0, ptr(residual), ptr(y), lib.code(raw), n,
+                             p * q, cv.K, int(relu), st)
+        return y, (n, p, q, cv.K)
+
+    def forward(self, rgb: torch.Tensor, out: torch.Tensor, ld_out: int, out_hw: int = 4):
+        """rgb (R,H,W,3) u8|f32 in 0..255 -> out[(R,16,ld_out) f32][:, :, :C] = 4x4-pooled features."""
+        for cv in self._all():
+            cv.pack()
+        n, h, w, _ = rgb.shape
+        st = lib.stream()
+        cv = self.stem
+        p, q = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+        if self.precision == "bf16":
+            a = self.pool.get("stem_a", (n * p * q, 192), torch.bfloat16)
+            C.vlnce_im2col_rgb_stem(ptr(rgb), lib.code(rgb), ptr(a), n, h, w, st)
+            x, shp = self._norm_conv(a, (n, p, q, 192), cv, "stem_y", gemm_c=192, out_hw=(p, q))
+        else:
+            x, shp = self._norm_conv(rgb, (n, h, w, 3), cv, "stem_y")
+        n, h, w, c = shp
+        p, q = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        y = self._act("pool_y", (n, p, q, c))
+        C.vlnce_maxpool3x3s2(ptr(x), ptr(y), lib.code(x), n, h, w, c, st)
+        x, shp = y, (n, p, q, c)
+        slot = 0
+        for b in self.blocks:
+            identity = x
+            if "ds" in b:
+                identity, _ = self._norm_conv(x, shp, b["ds"], "ds", relu=False)
+            o, s1 = self._norm_conv(x, shp, b["c1"], "t1")
+            if "c3" in b:
+                o, s2 = self._norm_conv(o, s1, b["c2"], "t2")
+                x, shp = self._norm_conv(o, s2, b["c3"], f"blk{slot}", residual=identity, relu=True)
+            else:
+                x, shp = self._norm_conv(o, s1, b["c2"], f"blk{slot}", residual=identity, relu=True)
+            slot ^= 1
+        n, h, w, c = shp
+        C.vlnce_adaptive_avgpool(ptr(x), lib.code(x), ptr(out), ld_out, n, h, w, c, out_hw, st)
+        return shp
+
+
+# ======================================================================================
+class DepthTrunk(ConvTrunk):
+    """DD-PPO GroupNorm ResNet encoder; ``enc`` has ``backbone`` (conv1, maxpool, layer1..4 of
+    blocks with ``convs`` / ``downsample`` Sequentials) and ``compression``."""
+
+    def __init__(self, enc: nn.Module, device, precision="bf16"):
+        super().__init__(device, precision)
+        bb = enc.backbone
+        self.stem = _Conv(bb.conv1[0], bb.conv1[1], precision, stem="depth")
+        self.blocks = []
+        for layer in (bb.layer1, bb.layer2, bb.layer3, bb.layer4):
+            for blk in layer.children():
+                convs = list(blk.convs.children())
+                pairs = [(convs[i], convs[i + 1]) for i in range(len(convs)) if isinstance(convs[i], nn.Conv2d)]
+                d = {"convs": [_Conv(c, g, precision) for c, g in pairs]}
+                if blk.downsample is not None:
+                    d["ds"] = _Conv(blk.downsample[0], blk.downsample[1], precision)
+                self.blocks.append(d)
+        self.compress = _Conv(enc.compression[0], enc.compression[1], precision)
+        self.out_channels = self.compress.K
+
+    def _all(self):
+        out = [self.stem, self.compress]
+        for b in self.blocks:
+            out += b["convs"] + ([b["ds"]] if "ds" in b else [])
+        return out
+
+    def _gn_conv(self, x, shape_in, cv: _Conv, tag, *, residual=None, relu=True, gemm_c=None, out_hw=None):
+        n, h, w, _ = shape_in
+        p, q = out_hw if out_hw is not None else self._out_hw(h, w, cv)
+        raw = self._act("gn_raw", (n, p, q, cv.K))
+        self._conv(x, shape_in, cv, raw, scale=None, shift=None, gemm_c=gemm_c)
+        gn: nn.GroupNorm = cv.norm
+        st = lib.stream()
+        sc = self.pool.get("gn_scale", (n, cv.K), torch.float32)
+        sh = self.pool.get("gn_shift", (n, cv.K), torch.float32)
+        C.vlnce_groupnorm_stats(ptr(raw), lib.code(raw), ptr(gn.weight), ptr(gn.bias), ptr(sc), ptr(sh), n,
+                                p * q, cv.K, gn.num_groups, float(gn.eps), st)
+        y = self._act(tag, (n, p, q, cv.K))
+        C.vlnce_affine_apply(ptr(raw), ptr(sc), ptr(sh), cv.K, ptr(residual), ptr(y), lib.code(raw), n,
+                             p * q, cv.K, int(relu), st)
+        return y, (n, p, q, cv.K)
+
+    def forward(self, depth: torch.Tensor, out: torch.Tensor, ld_out: int, out_hw: int = 4):
+        """depth (R,H,W,1) f32 -> out[(R,16,ld_out) f32][:, :, :128]."""
+        for cv in self._all():
+            cv.pack()
+        n, h, w, _ = depth.shape
+        st = lib.stream()
+        hp, wp = h // 2, w // 2
+        p, q = (hp + 6 - 7) // 2 + 1, (wp + 6 - 7) // 2 + 1
+        if self.precision == "bf16":
+            a = self.pool.get("stem_a", (n * p * q, 64), torch.bfloat16)
+            C.vlnce_im2col_depth_stem(ptr(depth), ptr(a), n, h, w, st)
+            x, shp = self._gn_conv(a, (n, p, q, 64), self.stem, "stem_y", gemm_c=64, out_hw=(p, q))
+        else:
+            pooled = self.pool.get("stem_a", (n, hp, wp, 1), torch.float32)
+            C.vlnce_avgpool2x2(ptr(depth), ptr(pooled), n, h, w, 1, st)
+            x, shp = self._gn_conv(pooled, (n, hp, wp, 1), self.stem, "stem_y")
+        n, h, w, c = shp
+        p, q = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        y = self._act("pool_y", (n, p, q, c))
+        C.vlnce_maxpool3x3s2(ptr(x), ptr(y), lib.code(x), n, h, w, c, st)
+        x, shp = y, (n, p, q, c)
+        slot = 0
+        for b in self.blocks:
+            identity = x
+            if "ds" in b:
+                identity, _ = self._gn_conv(x, shp, b["ds"], "ds", relu=False)
+            o, s = x, shp
+            for i, cv in enumerate(b["convs"]):
+                last = i == len(b["convs"]) - 1
+                o, s = self._gn_conv(o, s, cv, f"blk{slot}" if last else f"t{i}",
+                                     residual=identity if last else None, relu=True)
+            x, shp = o, s
+            slot ^= 1
+        x, shp = self._gn_conv(x, shp, self.compress, "cmp", relu=True)
+        n, h, w, c = shp
+        C.vlnce_adaptive_avgpool(ptr(x), lib.code(x), ptr(out), ld_out, n, h, w, c, out_hw, st)
+        return shp
