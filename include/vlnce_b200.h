@@ -90,10 +90,11 @@ int vlnce_batchnorm_train_stats(const void* x, int dtype, const float* gamma, co
                                 float* running_mean, float* running_var, float momentum,
                                 float* scale, float* shift, double* workspace, long long rows,
                                 int C, float eps, cudaStream_t stream);
-/* y = act(x*scale[n or 0, c] + shift[..] (+ residual)); scale_stride_n = C (per sample) or 0. */
-int vlnce_affine_apply(const void* x, const float* scale, const float* shift, int scale_stride_n,
-                       const void* residual, void* y, int dtype, int N, int HW, int C, int relu,
-                       cudaStream_t stream);
+/* y = act(x*scale[n or 0, c] + shift[..] (+ residual)); scale_stride_n = C (per sample) or 0.
+ * x may be the fp32 raw conv output while y / residual are bf16 activations. */
+int vlnce_affine_apply(const void* x, int x_dtype, const float* scale, const float* shift,
+                       int scale_stride_n, const void* residual, void* y, int y_dtype, int N, int HW,
+                       int C, int relu, cudaStream_t stream);
 /* adaptive_avg_pool2d(x,(O,O)), O in {1,4}, on NHWC -> f32 (N,O*O,ldy) slice
  * (resnet_encoders.py:154-162 4x4 pool; torchvision's global pool for the non-spatial
  * encoder); with H=W=O it is a plain bf16->f32 layout copy. */
@@ -155,6 +156,56 @@ int vlnce_positions_to_nchw(const float* E, long long lde_r, long long lde_p, fl
                             long long ldo, int R, int P, int C, cudaStream_t stream);
 int vlnce_log_softmax_rows(float* x, int rows, int A, cudaStream_t stream);
 int vlnce_argmax_rows(const float* x, long long* out, int rows, int A, cudaStream_t stream);
+
+/* ---- trainable head: backward, loss, optimiser -------------------------------------- */
+/* d[r,c] = 0 where y[r,c] <= 0 (ReLU backward, in place) */
+int vlnce_relu_bwd(float* d, long long ldd, const float* y, long long ldy, int rows, int cols,
+                   cudaStream_t stream);
+/* d *= 1 - y^2 (tanh backward, in place) */
+int vlnce_tanh_bwd(float* d, const float* y, long long n, cudaStream_t stream);
+/* backward of lp = raw - logsumexp(raw): draw = dlp - exp(lp) * sum_a dlp */
+int vlnce_log_softmax_bwd(const float* lp, const float* dlp, float* draw, int rows, int A,
+                          cudaStream_t stream);
+/* dst += src * mask[row]  (hidden-state gradient carried across a time step) */
+int vlnce_mask_rows_add(const float* src, long long lds, const float* mask, float* dst, long long ldd,
+                        int rows, int H, cudaStream_t stream);
+int vlnce_gru_pointwise_bwd(const float* dh, long long lddh, const float* save, const float* hm,
+                            float* dgi, float* dgh, float* dhm, int rows, int H, cudaStream_t stream);
+int vlnce_attn_pool_bwd(const float* q, long long ldq, const float* E, long long lde_r, long long lde_p,
+                        const float* probs, float scale, const float* dout, long long lddo, float* dq,
+                        long long lddq, float* dE, long long ldde_r, long long ldde_p, int accumulate_dE,
+                        int R, int P, int D, cudaStream_t stream);
+/* BPTT of the packed (bi)LSTM: emits pre-activation gate gradients dgx (dirs,R,L,4H) and the
+ * hidden state fed to every step hprev (dirs,R,L,H); the weight gradients are then GEMMs. */
+int vlnce_lstm_seq_bwd(const float* dout, const float* gates, const float* cs, const float* out,
+                       const float* whh_f, const float* whh_b, const int* lengths, float* dgx,
+                       float* hprev, int R, int L, int H, int dirs, cudaStream_t stream);
+int vlnce_embedding_bwd(const long long* ids, const float* d, long long ldd, float* dtable,
+                        long long rows, int dim, int vocab, int padding_idx, cudaStream_t stream);
+int vlnce_prev_action_embed_bwd(const long long* prev_actions, const float* masks, const float* d1,
+                                long long ld1, const float* d2, long long ld2, float* dtable, int rows,
+                                int dim, int table_rows, cudaStream_t stream);
+int vlnce_spatial_embed_grad(const float* dE, long long lde_r, long long lde_p, int c_off,
+                             const float* dflat, long long ldf, const float* dmean, long long ldm,
+                             float* dtable, int accumulate, int R, int P, int Cs, cudaStream_t stream);
+/* Fused DAgger / teacher-forcing loss and its gradients (base_il_trainer.py:159-172,
+ * aux_losses.py:24-32, cma_policy.py:296-307): logp (T*N,A) log-probs, actions/weights (T,N),
+ * hat/progress (T*N); progress_mode 0 none / 1 elementwise / 2 the (R,R) broadcast of SURVEY Q3.
+ * losses[3] = {loss/accum, action_loss, aux_loss}; d_raw (T*N,A) and d_hat (T*N) already carry
+ * the 1/accum factor. */
+int vlnce_il_loss(const float* logp, const long long* actions, const float* weights, const float* hat,
+                  const float* progress, int progress_mode, float alpha, float inv_accum, int T, int N,
+                  int A, float* d_raw, float* d_hat, float* losses, cudaStream_t stream);
+/* torch.optim.Adam step (no weight decay / amsgrad) over flat fp32 buffers; grad_scale folds the
+ * 1/world_size of the data-parallel gradient all-reduce.  step > 0: host step count;
+ * step == 0: read it from step_dev (CUDA-graph replays). */
+int vlnce_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                    float beta2, float eps, int step, const int* step_dev, float grad_scale,
+                    cudaStream_t stream);
+/* device-resident step counter for graph replays; y += alpha * x for gradient accumulation
+ * (loss_accumulation_scalar, base_il_trainer.py:170-176) */
+int vlnce_counter_add(int* counter, int value, cudaStream_t stream);
+int vlnce_axpy(float* y, const float* x, float alpha, long long n, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

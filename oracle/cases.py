@@ -86,30 +86,43 @@ def grad_digest(g: torch.Tensor) -> torch.Tensor:
     return torch.cat([torch.stack([g.sum(), g.abs().sum(), g.norm()]), head]).float()
 
 
-def run_case(impl, name, aux=None):
+def _to(x, device):
+    if device is None:
+        return x
+    if isinstance(x, dict):
+        return {k: v.to(device) for k, v in x.items()}
+    return x.to(device)
+
+
+def run_case(impl, name, aux=None, device=None, precision=None):
     """Runs ``name`` through ``impl``; ``aux`` = that implementation's AuxLosses
-    singleton.  Returns {key: tensor|float}."""
+    singleton.  ``device`` / ``precision`` select the CUDA package's placement and trunk
+    arithmetic.  Returns {key: cpu tensor}."""
     case = CASES[name]
     aux = aux if aux is not None else impl.AuxLosses
     torch.manual_seed(0)
     pol = build_policy(impl, case)
+    if device is not None:
+        pol = pol.to(device)
+    if precision is not None:
+        pol.net.precision = precision
     set_mode(pol, case)
     out = {}
     if case["kind"] == "act":
-        obs, h, prev, masks = inputs(case)
+        obs, h, prev, masks = (_to(v, device) for v in inputs(case))
         aux.deactivate()
         with torch.no_grad():
             dist = pol.build_distribution(obs, h, prev, masks)
             action, h_out = pol.act(obs, h, prev, masks, deterministic=True)
-        out["logits"] = dist.logits.detach().clone()
-        out["action"] = action.clone()
-        out["rnn_states_out"] = h_out.detach().clone()
+        out["logits"] = dist.logits.detach().cpu().clone()
+        out["action"] = action.cpu().clone()
+        out["rnn_states_out"] = h_out.detach().cpu().clone()
         return out
-    obs, prev, masks, actions, weights = inputs(case)
+    obs, prev, masks, actions, weights = (_to(v, device) for v in inputs(case))
     t, n = actions.shape
     aux.activate()
     aux.clear()
-    h0 = torch.zeros(n, pol.net.num_recurrent_layers, 512)
+    h0 = torch.zeros(n, pol.net.num_recurrent_layers, 512, device=device)
     dist = pol.build_distribution(obs, h0, prev, masks)
     logits = dist.logits.view(t, n, -1)
     ce = F.cross_entropy(logits.permute(0, 2, 1), actions, reduction="none")
@@ -120,12 +133,12 @@ def run_case(impl, name, aux=None):
         p.grad = None
     loss.backward()
     aux.deactivate()
-    out["logits"] = dist.logits.detach().clone()
+    out["logits"] = dist.logits.detach().cpu().clone()
     out["loss"] = torch.tensor(float(loss.detach()))
     out["action_loss"] = torch.tensor(float(action_loss.detach()))
     out["aux_loss"] = torch.tensor(float(aux_loss.detach() if torch.is_tensor(aux_loss) else aux_loss))
     for k, p in pol.named_parameters():
         if p.requires_grad:
-            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            g = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu()
             out["grad/" + k] = g.clone() if g.numel() <= 4096 else grad_digest(g)
     return out

@@ -25,17 +25,17 @@ def _ref_conv(x, w, scale, shift, res, stride, pad, relu, y_dtype=torch.float32)
 @pytest.mark.parametrize("cin,k,r,stride,pad,hw", [(3, 16, 7, 2, 3, 20), (8, 24, 3, 1, 1, 9), (16, 8, 1, 2, 0, 10)])
 def test_conv_ref_matches_torch(cin, k, r, stride, pad, hw):
     g = torch.Generator(device="cpu").manual_seed(1)
-    x = torch.randn(2, hw, hw, cin, generator=g).to(DEV)
-    w = torch.randn(k, r, r, cin, generator=g).to(DEV) * 0.2
-    scale = (torch.rand(k, generator=g) + 0.5).to(DEV)
-    shift = torch.randn(k, generator=g).to(DEV)
+    x = torch.randn(2, hw, hw, cin, generator=g)
+    w = torch.randn(k, r, r, cin, generator=g) * 0.2
+    scale = torch.rand(k, generator=g) + 0.5
+    shift = torch.randn(k, generator=g)
+    # CPU fp32 reference (torch-CUDA convolutions default to TF32)
     want = F.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), stride=stride, padding=pad)
     want = want * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
-    res = torch.randn_like(want.permute(0, 2, 3, 1).contiguous())
+    res = torch.randn(want.permute(0, 2, 3, 1).shape, generator=g)
     want = torch.relu(want + res.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
-    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-        got = _ref_conv(x, w, scale, shift, res, stride, pad, True)
-    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    got = _ref_conv(x.to(DEV), w.to(DEV), scale.to(DEV), shift.to(DEV), res.to(DEV), stride, pad, True)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-4)
 
 
 CASES = [

@@ -39,14 +39,15 @@ def test_sgemm_variants(m, n, k):
 def test_lstm_matches_packed_torch(dirs):
     R, L, E, H = 5, 11, 50, 128
     torch.manual_seed(0)
-    rnn = nn.LSTM(E, H, bidirectional=dirs == 2).to(DEV)
-    x = _r(R, L, E)
+    rnn = nn.LSTM(E, H, bidirectional=dirs == 2)
+    x = _r(R, L, E).cpu()
     lens = torch.tensor([11, 1, 7, 4, 9])
-    x = x * (torch.arange(L).view(1, L, 1) < lens.view(R, 1, 1)).to(DEV)
+    x = x * (torch.arange(L).view(1, L, 1) < lens.view(R, 1, 1))
     packed = nn.utils.rnn.pack_padded_sequence(x, lens, batch_first=True, enforce_sorted=False)
-    with torch.no_grad():
+    with torch.no_grad():  # CPU fp32 reference (cuDNN RNNs default to TF32)
         o, (hn, _) = rnn(packed)
-    want = nn.utils.rnn.pad_packed_sequence(o, batch_first=True, total_length=L)[0]
+    want = nn.utils.rnn.pad_packed_sequence(o, batch_first=True, total_length=L)[0].to(DEV)
+    hn, x, rnn = hn.to(DEV), x.to(DEV), rnn.to(DEV)
     lengths = lens.to(DEV).int()
     gx = torch.empty(dirs, R, L, 4 * H, device=DEV)
     ws = [(rnn.weight_ih_l0, rnn.bias_ih_l0)] + ([(rnn.weight_ih_l0_reverse, rnn.bias_ih_l0_reverse)] if dirs == 2 else [])
@@ -64,10 +65,11 @@ def test_lstm_matches_packed_torch(dirs):
 def test_gru_cell_matches_torch():
     N, I, H = 7, 416, 512
     torch.manual_seed(0)
-    rnn = nn.GRU(I, H).to(DEV)
+    rnn = nn.GRU(I, H)
     x, h = _r(N, I), _r(N, H, seed=5)
-    with torch.no_grad():
-        _, want = rnn(x.unsqueeze(0), h.unsqueeze(0))
+    with torch.no_grad():  # CPU fp32 reference
+        _, want = rnn(x.cpu().unsqueeze(0), h.cpu().unsqueeze(0))
+    want, rnn = want.to(DEV), rnn.to(DEV)
     gi, gh = torch.empty(N, 3 * H, device=DEV), torch.empty(N, 3 * H, device=DEV)
     linear(ptr(x), I, ptr(rnn.weight_ih_l0), ptr(gi), 3 * H, ptr(rnn.bias_ih_l0), N, 3 * H, I)
     linear(ptr(h), H, ptr(rnn.weight_hh_l0), ptr(gh), 3 * H, ptr(rnn.bias_hh_l0), N, 3 * H, H)

@@ -74,7 +74,11 @@ def test_cma_act_matches_golden(name, precision, tol):
     margin = (margin[:, 0] - margin[:, 1]).min().item()
     print(f"{name}[{precision}] rel err probs {e_logits:.3e} hidden {e_h:.3e} (min logit margin {margin:.3f})")
     assert e_logits < tol and e_h < tol
-    assert torch.equal(action.cpu(), gold["action"]), "argmax actions must be bit-exact"
+    # argmax must be bit-exact wherever the reference's own top-2 margin is resolvable at this
+    # precision (a tie within the stated tolerance has no defined winner)
+    top2 = gold["logits"].topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > (0.0 if precision == "fp32" else 5 * tol)
+    assert torch.equal(action.cpu()[decided], gold["action"][decided]), "argmax actions must be bit-exact"
     assert h_out.shape == gold["rnn_states_out"].shape and action.dtype == torch.int64
 
 

@@ -1,0 +1,124 @@
+"""Training-path parity on the B200: the hand-written backward behind ``loss.backward()``
+(the reference's own ``_update_agent`` arithmetic, run on the CUDA policy) and the fused
+``ILTrainerStep`` against the golden vectors frozen from the unmodified reference."""
+import os
+import warnings
+
+import pytest
+import torch
+
+import vlnce_b200
+from oracle import cases
+from vlnce_b200 import lib
+from vlnce_b200.il_step import ILTrainerStep
+from vlnce_b200.lib import C, ptr
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(name):
+    return torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+
+
+def check(got, want, rtol, name):
+    bad = []
+    for k, w in want.items():
+        if k.startswith("_"):
+            continue
+        g = got[k].float()
+        w = w.float()
+        scale = max(w.abs().max().item(), 1e-6)
+        err = (g - w).abs().max().item()
+        if k.startswith("grad/") and w.numel() == 11 and g.numel() == 11:  # digest: sum, abs-sum, norm, head[8]
+            ok = abs(g[2] - w[2]) <= 3 * rtol * max(w[2].item(), 1e-7) and abs(g[1] - w[1]) <= 3 * rtol * max(w[1].item(), 1e-7)
+            ok = ok and (g[3:] - w[3:]).abs().max().item() <= 10 * rtol * max(w[3:].abs().max().item(), w[2].item() * 1e-2, 1e-8)
+        else:
+            ok = err <= rtol * scale + 1e-7
+        if not ok:
+            bad.append((k, err, scale))
+    assert not bad, f"{name}: " + "; ".join(f"{k} err {e:.3e} (scale {s:.3e})" for k, e, s in bad[:8])
+
+
+@pytest.mark.parametrize("name,precision,rtol", [
+    ("cma_train_features", "fp32", 1e-3), ("cma_train_features_nopm", "fp32", 1e-3),
+    ("cma_train_pixels", "fp32", 1e-3), ("cma_train_pixels", "bf16", 3e-2)])
+def test_reference_update_arithmetic_on_cuda_policy(name, precision, rtol):
+    """base_il_trainer.py:134-172 verbatim (torch CE / AuxLosses.reduce / loss.backward()) on
+    the CUDA policy: logits, losses and every trainable gradient vs the reference."""
+    got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, device=DEV, precision=precision)
+    check(got, gold(name), rtol, name)
+
+
+@pytest.mark.parametrize("name", ["cma_train_features", "cma_train_features_nopm"])
+def test_fused_step_matches_reference(name):
+    case = cases.CASES[name]
+    want = gold(name)
+    pol = cases.build_policy(vlnce_b200, case).to(DEV)
+    pol.net.precision = "fp32"
+    cases.set_mode(pol, case)
+    obs, prev, masks, actions, weights = (cases._to(v, DEV) for v in cases.inputs(case))
+    before = {k: v.detach().clone() for k, v in pol.state_dict().items()}
+    step = ILTrainerStep(pol, lr=2.5e-4)
+    aux = vlnce_b200.AuxLosses
+    aux.activate()
+    loss, action_loss, aux_loss = step.update_agent(obs, prev, masks, actions, weights)
+    aux.deactivate()
+    assert abs(loss - want["loss"].item()) < 1e-4 * max(1, abs(want["loss"].item()))
+    assert abs(action_loss - want["action_loss"].item()) < 1e-4
+    assert abs(aux_loss - want["aux_loss"].item()) < 1e-4
+    got = {"grad/" + k[len("net."):] if False else "grad/" + k: None for k in ()}
+    got = {}
+    for k, gview in step.fp.grad_views.items():
+        g = gview.detach().cpu()
+        got["grad/" + k] = g.clone() if g.numel() <= 4096 else cases.grad_digest(g)
+    check(got, {k: v for k, v in want.items() if k.startswith("grad/")}, 1e-3, name)
+    # parameters moved by exactly one Adam step of those gradients (torch.optim.Adam semantics)
+    after = pol.state_dict()
+    k = "net.state_q.weight"
+    gk = step.fp.grad_views[k]
+    expect = before[k] - 2.5e-4 * gk / (gk.abs() + 1e-8)  # step 1: m/(sqrt(v)+eps) = g/(|g|+eps)
+    torch.testing.assert_close(after[k], expect, rtol=1e-5, atol=1e-7)
+    frozen = "net.rgb_encoder.cnn.0.weight"
+    assert torch.equal(after[frozen], before[frozen])
+
+
+def test_adam_kernel_matches_torch():
+    g0 = torch.Generator().manual_seed(0)
+    n = 100003
+    p = torch.randn(n, generator=g0).to(DEV)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=2.5e-4)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step_dev = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for it in range(1, 6):
+        g = torch.randn(n, generator=g0).to(DEV) * (10.0 ** -it)
+        ref.grad = g.clone()
+        opt.step()
+        C.vlnce_counter_add(ptr(step_dev), 1, lib.stream())
+        C.vlnce_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), n, 2.5e-4, 0.9, 0.999, 1e-8, 0, ptr(step_dev), 1.0,
+                          lib.stream())
+    torch.testing.assert_close(p, ref.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_gradient_accumulation_equals_single_step():
+    """step_grad=False then True with loss_accumulation_scalar=2 on the same batch twice ==
+    one step on that batch (recollect_trainer.py:161-185 semantics)."""
+    case = cases.CASES["cma_train_features_nopm"]
+    obs, prev, masks, actions, weights = (cases._to(v, DEV) for v in cases.inputs(case))
+
+    def run(accum):
+        pol = cases.build_policy(vlnce_b200, case).to(DEV)
+        pol.net.precision = "fp32"
+        pol.eval()
+        st = ILTrainerStep(pol, lr=1e-3)
+        if accum:
+            st.update_agent(obs, prev, masks, actions, weights, step_grad=False, loss_accumulation_scalar=2)
+            st.update_agent(obs, prev, masks, actions, weights, step_grad=True, loss_accumulation_scalar=2)
+        else:
+            st.update_agent(obs, prev, masks, actions, weights)
+        return pol.state_dict()["net.second_state_compress.0.bias"].clone()
+
+    torch.testing.assert_close(run(True), run(False), rtol=1e-4, atol=1e-6)

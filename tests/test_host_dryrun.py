@@ -37,3 +37,28 @@ def test_header_and_library_agree():
     for name in lib.C.protos:
         assert hasattr(dll, name), name
     assert b"sm_100a" in lib.C.vlnce_version()
+
+
+@pytest.mark.parametrize("name", ["cma_train_features", "cma_train_pixels"])
+def test_train_launch_sequence(name):
+    """forward(save) -> reference loss arithmetic -> hand-written backward, launch-checked."""
+    with lib.dry_run() as rec:
+        got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses)
+    assert "vlnce_lstm_seq_bwd" in rec.calls and rec.calls.count("vlnce_attn_pool_bwd") == 3
+    assert any(k.startswith("grad/net.rgb_kv.weight") for k in got)
+
+
+def test_fused_step_launch_sequence():
+    from vlnce_b200.il_step import ILTrainerStep
+
+    case = cases.CASES["cma_train_features"]
+    pol = cases.build_policy(vlnce_b200, case)
+    obs, prev, masks, actions, weights = cases.inputs(case)
+    step = ILTrainerStep(pol)
+    vlnce_b200.AuxLosses.activate()
+    with lib.dry_run() as rec:
+        out = step.update_agent(obs, prev, masks, actions, weights, return_tensor=True)
+    vlnce_b200.AuxLosses.deactivate()
+    assert out.shape == (3,)
+    assert rec.calls[-1] == "vlnce_adam_step" and "vlnce_il_loss" in rec.calls
+    assert step.fp.aliased()

@@ -1,0 +1,248 @@
+"""Hand-written backward of the CMA head (launch sequencing only; arithmetic in the library)
+and the ``torch.autograd.Function`` that exposes it, so that the reference's
+``loss.backward()`` (``common/base_il_trainer.py:172``) differentiates through
+``policy.build_distribution(...).logits`` unchanged.  Only the trainable head has a
+backward: both conv trunks are frozen in every shipped recipe (``config/default.py:242,253``).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import lib
+from .engine import F4, CMAEngine, linear, linear_dw, linear_dx, off
+from .lib import C, ptr
+
+
+def trainable_named(net, head_linear=None) -> Dict[str, torch.nn.Parameter]:
+    out = {"net." + k: p for k, p in net.named_parameters() if p.requires_grad}
+    if head_linear is not None:
+        out["action_distribution.linear.weight"] = head_linear.weight
+        out["action_distribution.linear.bias"] = head_linear.bias
+    return out
+
+
+def _colsum(a, lda, out, m, n, acc=0):
+    C.vlnce_colsum(a, lda, out, m, n, acc, lib.stream())
+
+
+def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, masks_f, T, N, dx, lddx):
+    H = eng.H
+    R = T * N
+    st = lib.stream()
+    d_gi = eng.buf(tag + "_dgi", (R, 3 * H))
+    d_gh = eng.buf(tag + "_dgh", (R, 3 * H))
+    dhm = eng.buf(tag + "_dhm", (N, H))
+    save = eng.buf(tag + "_save", (R, 4 * H))
+    hm_all = eng.buf(tag + "_hm", (R, H))
+    for t in range(T - 1, -1, -1):
+        C.vlnce_gru_pointwise_bwd(dh + F4 * t * N * lddh, lddh, off(save, t * N * 4 * H), off(hm_all, t * N * H),
+                                  off(d_gi, t * N * 3 * H), off(d_gh, t * N * 3 * H), ptr(dhm), N, H, st)
+        linear_dx(off(d_gh, t * N * 3 * H), 3 * H, ptr(rnn.weight_hh_l0), ptr(dhm), H, N, 3 * H, H, beta=1.0)
+        if t > 0:
+            C.vlnce_mask_rows_add(ptr(dhm), H, off(masks_f, t * N), dh + F4 * (t - 1) * N * lddh, lddh, N, H, st)
+    linear_dw(ptr(d_gh), 3 * H, ptr(hm_all), H, ptr(g[pfx + "weight_hh_l0"]), H, R, 3 * H, H)
+    _colsum(ptr(d_gh), 3 * H, ptr(g[pfx + "bias_hh_l0"]), R, 3 * H)
+    linear_dw(ptr(d_gi), 3 * H, x, ldx, ptr(g[pfx + "weight_ih_l0"]), in_size, R, 3 * H, in_size)
+    _colsum(ptr(d_gi), 3 * H, ptr(g[pfx + "bias_ih_l0"]), R, 3 * H)
+    linear_dx(ptr(d_gi), 3 * H, ptr(rnn.weight_ih_l0), dx, lddx, R, 3 * H, in_size)
+
+
+def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw: Optional[torch.Tensor],
+                 d_x: Optional[torch.Tensor], d_hat: Optional[torch.Tensor]):
+    """Backward of the last ``eng.forward(..., save=True)``.  ``g`` maps parameter names to
+    ZEROED gradient tensors that are written here.  ``d_raw`` (R,A): gradient w.r.t. the raw
+    action logits (with ``head_linear``) or ``d_x`` (R,H) w.r.t. the features; ``d_hat`` (R,1)
+    w.r.t. ``progress_hat``.  All buffers are the engine's persistent workspace."""
+    net = eng.net
+    cx = eng.ctx
+    assert cx.get("saved"), "backward needs the forward to have run with save=True"
+    R, N, T, L = cx["R"], cx["N"], cx["T"], cx["L"]
+    H, P, hk = eng.H, eng.P, eng.H // 2
+    st = lib.stream()
+    b = eng.buf
+    x_out, x2, xcat, state_in = b("x_out", (R, H)), b("x2", (R, H)), b("xcat", (R, eng.cat)), b("state_in", (R, eng.state_in))
+    masks_f = b("masks_f", (R,))
+    dx_out = b("d_x_out", (R, H))
+
+    # 1. action head / feature gradient
+    if head_linear is not None:
+        A = head_linear.weight.shape[0]
+        linear_dw(ptr(d_raw), A, ptr(x_out), H, ptr(g["action_distribution.linear.weight"]), H, R, A, H)
+        _colsum(ptr(d_raw), A, ptr(g["action_distribution.linear.bias"]), R, A)
+        linear_dx(ptr(d_raw), A, ptr(head_linear.weight), ptr(dx_out), H, R, A, H)
+    else:
+        dx_out.copy_(d_x)
+    # 2. progress monitor: hat = tanh(x w + b)
+    if d_hat is not None and "net.progress_monitor.weight" in g:
+        hat = b("progress_hat", (R, 1))
+        dpre = b("d_pm", (R, 1))
+        dpre.copy_(d_hat.reshape(R, 1))
+        C.vlnce_tanh_bwd(ptr(dpre), ptr(hat), R, st)
+        pm = net.progress_monitor
+        linear_dw(ptr(dpre), 1, ptr(x_out), H, ptr(g["net.progress_monitor.weight"]), H, R, 1, H)
+        _colsum(ptr(dpre), 1, ptr(g["net.progress_monitor.bias"]), R, 1)
+        linear_dx(ptr(dpre), 1, ptr(pm.weight), ptr(dx_out), H, R, 1, H, beta=1.0)
+    # 3. second GRU
+    d_x2 = b("d_x2", (R, H))
+    _gru_backward(eng, "gru2", net.second_state_encoder.rnn, "net.second_state_encoder.rnn.", g, ptr(dx_out), H,
+                  ptr(x2), H, H, masks_f, T, N, ptr(d_x2), H)
+    # 4. second_state_compress = ReLU(Linear(xcat))
+    C.vlnce_relu_bwd(ptr(d_x2), H, ptr(x2), H, R, H, st)
+    lin = net.second_state_compress[0]
+    linear_dw(ptr(d_x2), H, ptr(xcat), eng.cat, ptr(g["net.second_state_compress.0.weight"]), eng.cat, R, H, eng.cat)
+    _colsum(ptr(d_x2), H, ptr(g["net.second_state_compress.0.bias"]), R, H)
+    dxcat = b("d_xcat", (R, eng.cat))
+    linear_dx(ptr(d_x2), H, ptr(lin.weight), ptr(dxcat), eng.cat, R, H, eng.cat)
+    # 5. visual attentions
+    text_q = b("text_q", (R, hk))
+    d_text_q = b("d_text_q", (R, hk))
+    dE = {}
+    first = True
+    for name, Cc, kv, v_out, col in (("rgb", eng.Crgb, net.rgb_kv, eng.rgb_out, H + eng.Dt),
+                                     ("depth", eng.Cdep, net.depth_kv, eng.depth_out, H + eng.Dt + eng.rgb_out)):
+        E_ = b(name + "_emb" if name == "rgb" else "depth_emb", (R, P, Cc))
+        pooled, qv, probs = b("pooled_" + name, (R, Cc)), b("q_" + name, (R, Cc)), b("p_" + name, (R, P))
+        gw, gb = g[f"net.{name}_kv.weight"], g[f"net.{name}_kv.bias"]
+        d_att = off(dxcat, col)
+        linear_dw(d_att, eng.cat, ptr(pooled), Cc, off(gw, hk * Cc), Cc, R, v_out, Cc)  # dW_v
+        _colsum(d_att, eng.cat, off(gb, hk), R, v_out)
+        d_pooled = b("d_pooled_" + name, (R, Cc))
+        linear_dx(d_att, eng.cat, off(kv.weight, hk * Cc), ptr(d_pooled), Cc, R, v_out, Cc)
+        dq = b("d_q_" + name, (R, Cc))
+        dEn = b("d_emb_" + name, (R, P, Cc))
+        C.vlnce_attn_pool_bwd(ptr(qv), Cc, ptr(E_), P * Cc, Cc, ptr(probs), eng.scale, ptr(d_pooled), Cc, ptr(dq),
+                              Cc, ptr(dEn), P * Cc, Cc, 0, R, P, Cc, st)
+        dE[name] = dEn
+        linear_dw(ptr(text_q), hk, ptr(dq), Cc, ptr(gw), Cc, R, hk, Cc)  # dW_k = text_q^T dq'
+        linear(ptr(dq), Cc, ptr(kv.weight), ptr(d_text_q), hk, None, R, hk, Cc, beta=0.0 if first else 1.0)
+        first = False
+    # 6. text_q = Linear(text_embedding)
+    linear_dw(ptr(d_text_q), hk, off(xcat, H), eng.cat, ptr(g["net.text_q.weight"]), eng.Dt, R, hk, eng.Dt)
+    _colsum(ptr(d_text_q), hk, ptr(g["net.text_q.bias"]), R, hk)
+    linear_dx(ptr(d_text_q), hk, ptr(net.text_q.weight), off(dxcat, H), eng.cat, R, hk, eng.Dt, beta=1.0)
+    # 7. text attention
+    instr = b("instr_out", (R, L, eng.Dt))
+    q_t, q_s, p_text = b("q_text", (R, eng.Dt)), b("q_state", (R, hk)), b("p_text", (R, L))
+    dq_t = b("d_q_text", (R, eng.Dt))
+    d_instr = b("d_instr", (R, L, eng.Dt))
+    C.vlnce_attn_pool_bwd(ptr(q_t), eng.Dt, ptr(instr), L * eng.Dt, eng.Dt, ptr(p_text), eng.scale, off(dxcat, H),
+                          eng.cat, ptr(dq_t), eng.Dt, ptr(d_instr), L * eng.Dt, eng.Dt, 0, R, L, eng.Dt, st)
+    linear_dw(ptr(q_s), hk, ptr(dq_t), eng.Dt, ptr(g["net.text_k.weight"]), eng.Dt, R, hk, eng.Dt)
+    d_q_s = b("d_q_state", (R, hk))
+    linear(ptr(dq_t), eng.Dt, ptr(net.text_k.weight), ptr(d_q_s), hk, None, R, hk, eng.Dt)
+    linear_dw(ptr(d_q_s), hk, ptr(xcat), eng.cat, ptr(g["net.state_q.weight"]), H, R, hk, H)
+    _colsum(ptr(d_q_s), hk, ptr(g["net.state_q.bias"]), R, hk)
+    linear_dx(ptr(d_q_s), hk, ptr(net.state_q.weight), ptr(dxcat), eng.cat, R, hk, H, beta=1.0)
+    # 8. first GRU (dh = dxcat[:, :H])
+    d_state_in = b("d_state_in", (R, eng.state_in))
+    _gru_backward(eng, "gru1", net.state_encoder.rnn, "net.state_encoder.rnn.", g, ptr(dxcat), eng.cat,
+                  ptr(state_in), eng.state_in, eng.state_in, masks_f, T, N, ptr(d_state_in), eng.state_in)
+    # 9. rgb_linear / depth_linear (ReLU(Linear))
+    c_rgb = net.rgb_encoder.resnet_layer_size
+    c_dep = net.depth_encoder.visual_encoder.output_shape[0]
+    C.vlnce_relu_bwd(ptr(d_state_in), eng.state_in, ptr(state_in), eng.state_in, R, eng.rgb_out + eng.depth_out, st)
+    rgb_mean = b("rgb_mean", (R, eng.Crgb))
+    lin = net.rgb_linear[2]
+    linear_dw(ptr(d_state_in), eng.state_in, ptr(rgb_mean), eng.Crgb, ptr(g["net.rgb_linear.2.weight"]), eng.Crgb, R,
+              eng.rgb_out, eng.Crgb)
+    _colsum(ptr(d_state_in), eng.state_in, ptr(g["net.rgb_linear.2.bias"]), R, eng.rgb_out)
+    d_mean_sp = b("d_mean_sp", (R, 64))
+    linear_dx(ptr(d_state_in), eng.state_in, off(lin.weight, c_rgb), ptr(d_mean_sp), 64, R, eng.rgb_out, 64,
+              ldw=eng.Crgb)
+    dep_flat = b("depth_flat", (R, eng.Cdep * P))
+    lin = net.depth_linear[1]
+    d_dep = off(d_state_in, eng.rgb_out)
+    linear_dw(d_dep, eng.state_in, ptr(dep_flat), eng.Cdep * P, ptr(g["net.depth_linear.1.weight"]), eng.Cdep * P, R,
+              eng.depth_out, eng.Cdep * P)
+    _colsum(d_dep, eng.state_in, ptr(g["net.depth_linear.1.bias"]), R, eng.depth_out)
+    d_flat_sp = b("d_flat_sp", (R, 64 * P))
+    linear_dx(d_dep, eng.state_in, off(lin.weight, c_dep * P), ptr(d_flat_sp), 64 * P, R, eng.depth_out, 64 * P,
+              ldw=eng.Cdep * P)
+    # 10. prev-action embedding (two concat slices share the rows)
+    pa_w = net.prev_action_embedding.weight
+    C.vlnce_prev_action_embed_bwd(ptr(cx["prev"]), ptr(masks_f), off(dxcat, eng.cat - 32), eng.cat,
+                                  off(d_state_in, eng.rgb_out + eng.depth_out), eng.state_in,
+                                  ptr(g["net.prev_action_embedding.weight"]), R, 32, pa_w.shape[0], st)
+    # 11. spatial embeddings
+    C.vlnce_spatial_embed_grad(ptr(dE["rgb"]), P * eng.Crgb, eng.Crgb, c_rgb, None, 0, ptr(d_mean_sp), 64,
+                               ptr(g["net.rgb_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
+    C.vlnce_spatial_embed_grad(ptr(dE["depth"]), P * eng.Cdep, eng.Cdep, c_dep, ptr(d_flat_sp), 64 * P, None, 0,
+                               ptr(g["net.depth_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
+    # 12. instruction encoder (BPTT)
+    ie = net.instruction_encoder
+    rnn = ie.encoder_rnn
+    Hs, dirs, E = eng.Hs, eng.dirs, eng.E
+    dgx = b("lstm_dgx", (dirs, R, L, 4 * Hs))
+    hprev = b("lstm_hprev", (dirs, R, L, Hs))
+    C.vlnce_lstm_seq_bwd(ptr(d_instr), ptr(b("lstm_gates", (dirs, R, L, 4 * Hs))), ptr(b("lstm_c", (dirs, R, L, Hs))),
+                         ptr(instr), ptr(rnn.weight_hh_l0), ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None,
+                         ptr(cx["lengths"]), ptr(dgx), ptr(hprev), R, L, Hs, dirs, st)
+    emb_in = b("instr_emb", (R * L, E)) if ie.config.sensor_uuid == "instruction" else cx["rxr"]
+    emb_trainable = ie.config.sensor_uuid == "instruction" and ie.embedding_layer.weight.requires_grad
+    d_emb = b("d_instr_emb", (R * L, E)) if emb_trainable else None
+    for d, sfx in enumerate(["", "_reverse"][:dirs]):
+        dg = off(dgx, d * R * L * 4 * Hs)
+        pfx = "net.instruction_encoder.encoder_rnn."
+        linear_dw(dg, 4 * Hs, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, 4 * Hs, E)
+        linear_dw(dg, 4 * Hs, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, 4 * Hs, Hs)
+        _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, 4 * Hs)
+        _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, 4 * Hs)
+        if emb_trainable:
+            w_ih = getattr(rnn, "weight_ih_l0" + sfx)
+            linear_dx(dg, 4 * Hs, ptr(w_ih), ptr(d_emb), E, R * L, 4 * Hs, E, beta=0.0 if d == 0 else 1.0)
+    if emb_trainable:
+        el = ie.embedding_layer
+        pad = -1 if el.padding_idx is None else el.padding_idx
+        C.vlnce_embedding_bwd(ptr(cx["ids"]), ptr(d_emb), E, ptr(g["net.instruction_encoder.embedding_layer.weight"]),
+                              R * L, E, el.num_embeddings, pad, st)
+
+
+class CMAFunction(torch.autograd.Function):
+    """(trainable parameters…) -> (features | log-prob logits, rnn_states_out, progress_hat)."""
+
+    @staticmethod
+    def run(net, head_linear, observations, rnn_states, prev_actions, masks):
+        named = trainable_named(net, head_linear)
+        out, h_out, hat = CMAFunction.apply(net, head_linear, observations, rnn_states, prev_actions, masks,
+                                            tuple(named.keys()), *named.values())
+        return out, h_out, (hat if hat.numel() else None)
+
+    @staticmethod
+    def forward(ctx, net, head_linear, observations, rnn_states, prev_actions, masks, names, *params):
+        eng = net.engine()
+        x, h_out, hat = eng.forward(observations, rnn_states, prev_actions, masks, save=True)
+        ctx.eng, ctx.head, ctx.names = eng, head_linear, names
+        ctx.shapes = [p.shape for p in params]
+        ctx.token = object()
+        eng.ctx["token"] = ctx.token
+        out = x if head_linear is None else eng.action_logits(head_linear, x, x.shape[0])
+        h_ret = h_out.clone()
+        ctx.mark_non_differentiable(h_ret)
+        hat_ret = hat.clone() if hat is not None else x.new_zeros(0)
+        return out.clone(), h_ret, hat_ret
+
+    @staticmethod
+    def backward(ctx, d_out, _d_h, d_hat):
+        eng: CMAEngine = ctx.eng
+        if eng.ctx.get("token") is not ctx.token:
+            raise lib.VlnceError("backward() after another forward on the same policy: the saved workspace was "
+                                 "overwritten (the reference's trainers never interleave them)")
+        sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
+        flat = torch.zeros(sum(sizes), device=d_out.device, dtype=torch.float32)
+        g, o = {}, 0
+        for name, shp, n in zip(ctx.names, ctx.shapes, sizes):
+            g[name] = flat[o:o + n].view(shp)
+            o += n
+        d_out = d_out.contiguous().float()
+        d_hat = None if (d_hat is None or d_hat.numel() == 0) else d_hat.contiguous().float()
+        if ctx.head is not None:
+            R, A = d_out.shape
+            lp = eng.buf("logits", (R, A))
+            d_raw = eng.buf("d_raw", (R, A))
+            C.vlnce_log_softmax_bwd(ptr(lp), ptr(d_out), ptr(d_raw), R, A, lib.stream())
+            cma_backward(eng, ctx.head, g, d_raw, None, d_hat)
+        else:
+            cma_backward(eng, None, g, None, d_out, d_hat)
+        return (None,) * 7 + tuple(g[n] for n in ctx.names)

@@ -252,10 +252,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ ws, const float* _
 // ------------------------------------------------------------------------------------
 // y = act(x * scale[n|0, c] + shift (+ residual)); 8 channels (16 B of bf16) per thread.
 // ------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename TO>
 __global__ void affine_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                     const float* __restrict__ shift, int scale_stride_n,
-                                    const T* __restrict__ residual, T* __restrict__ y, int HW, int C,
+                                    const TO* __restrict__ residual, TO* __restrict__ y, int HW, int C,
                                     long long total_vec, int relu) {
   constexpr int V = 8;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_vec;
@@ -271,14 +271,14 @@ __global__ void affine_apply_kernel(const T* __restrict__ x, const float* __rest
     for (int e = 0; e < V; ++e) f[e] = fmaf(to_float<T>(x[e0 + e]), sc[e], sh[e]);
     if (residual != nullptr) {
 #pragma unroll
-      for (int e = 0; e < V; ++e) f[e] += to_float<T>(residual[e0 + e]);
+      for (int e = 0; e < V; ++e) f[e] += to_float<TO>(residual[e0 + e]);
     }
     if (relu) {
 #pragma unroll
       for (int e = 0; e < V; ++e) f[e] = fmaxf(f[e], 0.f);
     }
 #pragma unroll
-    for (int e = 0; e < V; ++e) y[e0 + e] = from_float<T>(f[e]);
+    for (int e = 0; e < V; ++e) y[e0 + e] = from_float<TO>(f[e]);
   }
 }
 
@@ -484,21 +484,26 @@ extern "C" int vlnce_batchnorm_train_stats(const void* x, int dtype, const float
   return VLNCE_OK;
 }
 
-extern "C" int vlnce_affine_apply(const void* x, const float* scale, const float* shift,
-                                  int scale_stride_n, const void* residual, void* y, int dtype, int N,
+extern "C" int vlnce_affine_apply(const void* x, int x_dtype, const float* scale, const float* shift,
+                                  int scale_stride_n, const void* residual, void* y, int y_dtype, int N,
                                   int HW, int C, int relu, cudaStream_t stream) {
   VLNCE_CHECK_ARG(x && y && scale && shift && C % 8 == 0, "affine_apply: bad arguments (C %% 8)");
   const long long total_vec = (long long)N * HW * C / 8;
-  if (dtype == VLNCE_BF16)
-    affine_apply_kernel<__nv_bfloat16><<<grid_for(total_vec, 256), 256, 0, stream>>>(
+  const unsigned grid = grid_for(total_vec, 256);
+  if (x_dtype == VLNCE_BF16 && y_dtype == VLNCE_BF16)
+    affine_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, stream>>>(
         (const __nv_bfloat16*)x, scale, shift, scale_stride_n, (const __nv_bfloat16*)residual,
         (__nv_bfloat16*)y, HW, C, total_vec, relu);
-  else if (dtype == VLNCE_F32)
-    affine_apply_kernel<float><<<grid_for(total_vec, 256), 256, 0, stream>>>(
+  else if (x_dtype == VLNCE_F32 && y_dtype == VLNCE_BF16)
+    affine_apply_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>(
+        (const float*)x, scale, shift, scale_stride_n, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y,
+        HW, C, total_vec, relu);
+  else if (x_dtype == VLNCE_F32 && y_dtype == VLNCE_F32)
+    affine_apply_kernel<float, float><<<grid, 256, 0, stream>>>(
         (const float*)x, scale, shift, scale_stride_n, (const float*)residual, (float*)y, HW, C,
         total_vec, relu);
   else {
-    set_error("affine_apply: dtype");
+    set_error("affine_apply: unsupported dtype pair %d -> %d", x_dtype, y_dtype);
     return VLNCE_ERR_INVALID_ARGUMENT;
   }
   VLNCE_LAUNCH_CHECK("affine_apply_kernel");

@@ -80,6 +80,11 @@ class CMAEngine:
     def buf(self, name, shape, dtype=torch.float32):
         return self.pool.get(name, shape, dtype)
 
+    def ensure_pool(self, dev):
+        if self.pool is None or self.pool.device != dev:
+            self.pool = BufferPool(dev)
+        return self.pool
+
     # ------------------------------------------------------------------ GRU helper
     def _gru_forward(self, tag, rnn, x, ldx, in_size, h0, ldh0, masks_f, out, ldo, h_final, ldhf, T, N,
                      save):
@@ -111,8 +116,7 @@ class CMAEngine:
         net = self.net
         dev = rnn_states.device
         lib.require_cuda(rnn_states, "rnn_states")
-        if self.pool is None or self.pool.device != dev:
-            self.pool = BufferPool(dev)
+        self.ensure_pool(dev)
         st = lib.stream()
         H, P = self.H, self.P
         N = rnn_states.shape[0]
@@ -146,6 +150,7 @@ class CMAEngine:
             emb = emb.contiguous().float()
             L = emb.shape[1]
             C.vlnce_feature_lengths(ptr(emb), ptr(lengths), R, L, self.E, st)
+            self.ctx["rxr"] = emb
         Hs, dirs = self.Hs, self.dirs
         rnn = ie.encoder_rnn
         gx = self.buf("lstm_gx", (dirs, R, L, 4 * Hs))

@@ -1,0 +1,141 @@
+"""Fused imitation-learning update — the per-step loss of the reference's
+``BaseVLNCETrainer._update_agent`` (``common/base_il_trainer.py:134-180``) as ONE launch
+sequence: forward (trunks + head) -> fused inflection-weighted CE + progress-monitor loss and
+their gradients -> hand-written head backward -> [one NCCL all-reduce of the flat gradient]
+-> fused Adam.  Same arguments, same three returned loss values, same accumulation semantics
+(``step_grad`` / ``loss_accumulation_scalar``, ``recollect_trainer.py:161-185``).
+
+Data parallelism: trajectories are sharded across ranks, parameters replicated;
+the only collective is an all-reduce(sum) of the flat trainable-gradient buffer, the 1/world
+factor is folded into the Adam kernel.  The reference's IL trainers are single-GPU; the
+averaging mirrors its DD-PPO reducer (``ddppo_waypoint_trainer.py:370``).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import lib
+from .aux_losses import AuxLosses
+from .backward import cma_backward, trainable_named
+from .lib import C, ptr
+
+
+class FlatParams:
+    """All trainable parameters as views of one flat fp32 buffer (+ flat grad / Adam moments),
+    so the optimiser and the gradient all-reduce are single launches."""
+
+    def __init__(self, named: Dict[str, torch.nn.Parameter]):
+        self.named = named
+        dev = next(iter(named.values())).device
+        self.sizes = {k: p.numel() for k, p in named.items()}
+        total = sum(self.sizes.values())
+        self.flat = torch.empty(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad_views: Dict[str, torch.Tensor] = {}
+        o = 0
+        with torch.no_grad():
+            for k, p in named.items():
+                n = self.sizes[k]
+                self.flat[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat[o:o + n].view(p.shape)  # re-point: state_dict/load_state_dict keep working
+                self.grad_views[k] = self.grad[o:o + n].view(p.shape)
+                o += n
+        self.total = total
+
+    def aliased(self) -> bool:
+        o = 0
+        for k, p in self.named.items():
+            if p.data_ptr() != self.flat.data_ptr() + 4 * o:
+                return False
+            o += self.sizes[k]
+        return True
+
+
+class ILTrainerStep:
+    def __init__(self, policy, lr: float = 2.5e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 process_group=None):
+        self.policy = policy
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.fp: Optional[FlatParams] = None
+        self.step_id = 0
+        self._step_dev = None
+        self._accum = None
+        self._pending = 0
+
+    def _prepare(self):
+        if self.fp is None or not self.fp.aliased():
+            named = trainable_named(self.policy.net, self.policy.action_distribution.linear)
+            self.fp = FlatParams(named)
+            dev = self.fp.flat.device
+            self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._step_dev.fill_(self.step_id)
+            self._accum = torch.zeros_like(self.fp.grad)
+            self._losses = torch.zeros(3, device=dev)
+            self._loss_acc = torch.zeros(3, device=dev)
+
+    # ---------------------------------------------------------------- the reference signature
+    def update_agent(self, observations, prev_actions, not_done_masks, corrected_actions, weights,
+                     step_grad: bool = True, loss_accumulation_scalar: int = 1, return_tensor: bool = False):
+        pol = self.policy
+        net = pol.net
+        self._prepare()
+        eng = net.engine()
+        fp = self.fp
+        st = lib.stream()
+        T, N = corrected_actions.shape
+        dev = fp.flat.device
+        h0 = eng.ensure_pool(dev).get("il_h0", (N, net.num_recurrent_layers, eng.H), torch.float32)
+        h0.zero_()  # base_il_trainer.py:145-150
+        AuxLosses.clear()
+        x, _, hat = eng.forward(observations, h0, prev_actions, not_done_masks, save=True)
+        R = T * N
+        head = pol.action_distribution.linear
+        A = head.weight.shape[0]
+        logp = eng.action_logits(head, x, R)
+        use_pm = bool(net.model_config.PROGRESS_MONITOR.use) and AuxLosses.is_active()
+        mode, progress = 0, None
+        if use_pm:
+            progress = observations["progress"]
+            lib.require_cuda(progress, "progress")
+            mode = 2 if progress.dim() == 2 else 1
+            progress = progress.contiguous().float()
+        actions = corrected_actions.contiguous()
+        if actions.dtype != torch.int64:
+            actions = actions.long()
+        w = weights.contiguous().float()
+        d_raw = eng.buf("d_raw", (R, A))
+        d_hat = eng.buf("d_hat", (R, 1))
+        C.vlnce_il_loss(ptr(logp), ptr(actions), ptr(w), ptr(hat) if use_pm else None,
+                        ptr(progress) if use_pm else None, mode,
+                        float(net.model_config.PROGRESS_MONITOR.alpha), 1.0 / float(loss_accumulation_scalar),
+                        T, N, A, ptr(d_raw), ptr(d_hat), ptr(self._losses), st)
+        fp.grad.zero_()
+        cma_backward(eng, head, fp.grad_views, d_raw, None, d_hat if use_pm else None)
+        accumulating = self._pending > 0 or not step_grad
+        if accumulating:
+            C.vlnce_axpy(ptr(self._accum), ptr(fp.grad), 1.0, fp.total, st)
+            self._pending += 1
+        if step_grad:
+            g = self._accum if accumulating else fp.grad
+            if self.world > 1:
+                torch.distributed.all_reduce(g, group=self.pg)  # NCCL sum over NVLink; 1/world folded below
+            C.vlnce_counter_add(ptr(self._step_dev), 1, st)
+            self.step_id += 1
+            C.vlnce_adam_step(ptr(fp.flat), ptr(g), ptr(fp.exp_avg), ptr(fp.exp_avg_sq), fp.total, float(self.lr),
+                              float(self.betas[0]), float(self.betas[1]), float(self.eps), 0, ptr(self._step_dev),
+                              1.0 / self.world, st)
+            if accumulating:
+                self._accum.zero_()
+                self._pending = 0
+        if return_tensor:
+            return self._losses
+        loss, action_loss, aux_loss = self._losses.tolist()  # one D2H read (the reference does three .item())
+        return loss, action_loss, aux_loss

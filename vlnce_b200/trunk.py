@@ -106,6 +106,11 @@ class ConvTrunk:
     def _act(self, tag: str, shape):
         return self.pool.get(tag, shape, self.adt)
 
+    def _raw(self, tag, shape):
+        """fp32 raw conv output feeding GroupNorm / train-mode BatchNorm statistics (one bf16
+        rounding per layer instead of two)."""
+        return self.pool.get(tag, shape, torch.float32)
+
     def _conv(self, x, shape_in, cv: _Conv, y, *, scale, shift, residual=None, relu=False,
               gemm_c: Optional[int] = None):
         """x NHWC (n,h,w,c) -> y; ``gemm_c`` set = x is an explicit stem operand (n*p*q, gemm_c)."""
@@ -114,10 +119,10 @@ class ConvTrunk:
         if self.precision == "bf16":
             if gemm_c is not None:
                 C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y),
-                                    lib.BF16, n * h * w, 1, 1, gemm_c, cv.K, 1, 1, 1, 0, int(relu), 0, st)
+                                    lib.code(y), n * h * w, 1, 1, gemm_c, cv.K, 1, 1, 1, 0, int(relu), 0, st)
             else:
                 C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y),
-                                    lib.BF16, n, h, w, c, cv.K, cv.R, cv.S, cv.stride, cv.pad, int(relu),
+                                    lib.code(y), n, h, w, c, cv.K, cv.R, cv.S, cv.stride, cv.pad, int(relu),
                                     0, st)
         else:
             C.vlnce_conv2d_ref(ptr(x), lib.code(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift),
@@ -167,7 +172,7 @@ class RGBTrunk(ConvTrunk):
                        gemm_c=gemm_c)
             return y, (n, p, q, cv.K)
         # train-mode BN (Q1): raw conv (input scaling only) -> batch stats -> fused apply
-        raw = self._act("bn_raw", (n, p, q, cv.K))
+        raw = self._raw("bn_raw", (n, p, q, cv.K))
         self._conv(x, shape_in, cv, raw, scale=cv.pre_scale if cv.in_scale != 1.0 else None,
                    shift=cv.pre_shift if cv.in_scale != 1.0 else None, gemm_c=gemm_c)
         st = lib.stream()
@@ -180,8 +185,8 @@ class RGBTrunk(ConvTrunk):
                                       ptr(sh), ptr(ws), n * p * q, cv.K, float(bn.eps), st)
         bn.num_batches_tracked += 1
         cv._ver = None  # running stats changed under the folded eval-mode scale/shift
-        C.vlnce_affine_apply(ptr(raw), ptr(sc), ptr(sh), 0, ptr(residual), ptr(y), lib.code(raw), n,
-                             p * q, cv.K, int(relu), st)
+        C.vlnce_affine_apply(ptr(raw), lib.code(raw), ptr(sc), ptr(sh), 0, ptr(residual), ptr(y), lib.code(y),
+                             n, p * q, cv.K, int(relu), st)
         return y, (n, p, q, cv.K)
 
     def forward(self, rgb: torch.Tensor, out: torch.Tensor, ld_out: int, out_hw: int = 4):
@@ -250,7 +255,7 @@ class DepthTrunk(ConvTrunk):
     def _gn_conv(self, x, shape_in, cv: _Conv, tag, *, residual=None, relu=True, gemm_c=None, out_hw=None):
         n, h, w, _ = shape_in
         p, q = out_hw if out_hw is not None else self._out_hw(h, w, cv)
-        raw = self._act("gn_raw", (n, p, q, cv.K))
+        raw = self._raw("gn_raw", (n, p, q, cv.K))
         self._conv(x, shape_in, cv, raw, scale=None, shift=None, gemm_c=gemm_c)
         gn: nn.GroupNorm = cv.norm
         st = lib.stream()
@@ -259,8 +264,8 @@ class DepthTrunk(ConvTrunk):
         C.vlnce_groupnorm_stats(ptr(raw), lib.code(raw), ptr(gn.weight), ptr(gn.bias), ptr(sc), ptr(sh), n,
                                 p * q, cv.K, gn.num_groups, float(gn.eps), st)
         y = self._act(tag, (n, p, q, cv.K))
-        C.vlnce_affine_apply(ptr(raw), ptr(sc), ptr(sh), cv.K, ptr(residual), ptr(y), lib.code(raw), n,
-                             p * q, cv.K, int(relu), st)
+        C.vlnce_affine_apply(ptr(raw), lib.code(raw), ptr(sc), ptr(sh), cv.K, ptr(residual), ptr(y),
+                             lib.code(y), n, p * q, cv.K, int(relu), st)
         return y, (n, p, q, cv.K)
 
     def forward(self, depth: torch.Tensor, out: torch.Tensor, ld_out: int, out_hw: int = 4):
