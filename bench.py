@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the VLN-CE policy hot path (BASELINE.json metric: policy steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one ``_update_agent`` call (``common/base_il_trainer.py:134-180``) on the
+BASELINE config C2 batch: CMAPolicy (bi-LSTM instruction encoder, progress monitor), T=1,
+64 trajectories per GPU, synthetic 256x256 RGB (u8) + depth (f32) + 80-token instructions:
+obs -> both conv trunks -> CMA head -> inflection-weighted CE + progress loss -> head backward
+-> (grad all-reduce) -> Adam.  ``value`` = policy steps (rows) per second over all GPUs.
+
+Prints ONE JSON line (see the task contract): value (inputs resident in HBM), e2e (host
+buffers through the public ILTrainerStep API, H2D/D2H inside the timed region), roofline of
+the dominant kernel (tcgen05 conv tiles), cpu_baseline (the CPU oracle port on the host
+cores), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+import torch  # noqa: E402
+
+ROWS_PER_GPU = 64
+HW = 256
+LENGTH = 80
+METRIC = "policy steps/sec (batch 64, 256x256 RGB-D, 80-tok instr)"
+WORKLOAD = ("C2: CMAPolicy fwd+DAgger loss+bwd+Adam, T=1 N=64/GPU, rgb u8 256x256x3, depth f32 256x256x1, "
+            "L=80, progress monitor on, conv trunks frozen/eval-mode norms")
+
+
+def model_case():
+    from oracle import cases  # case table + seeded-weight builder only (no oracle compute here)
+
+    return dict(cases.CASES["cma_train_pixels"], t=1, n=ROWS_PER_GPU)
+
+
+# ----------------------------------------------------------------------------------------
+def clocks_sampler(stop, out):
+    q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    dev = os.environ.get("LOCAL_RANK", "0")
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                              "-i", dev], stdout=subprocess.PIPE, text=True)
+    except Exception:
+        return
+    t = threading.Thread(target=lambda: [out.append(line) for line in p.stdout], daemon=True)
+    t.start()
+    stop.wait()
+    p.terminate()
+    t.join(timeout=2)
+
+
+def summarize_clocks(lines):
+    sm, mx, reasons = [], [], set()
+    for ln in lines:
+        f = [x.strip() for x in ln.split(",")]
+        if len(f) < 7:
+            continue
+        try:
+            sm.append(float(f[0]))
+            mx.append(float(f[1]))
+        except ValueError:
+            continue
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+    return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path on the host cores: the oracle port
+    (``kind: port`` — /root/reference does not exist on the GPU box), bounded sample."""
+    if rank != 0:
+        return
+    from oracle import cases, vlnce as oracle_vlnce
+
+    rows = 16  # bounded sample of the 64-row step
+    torch.set_num_threads(os.cpu_count() or 1)
+    case = dict(model_case(), n=rows)
+    pol = cases.build_policy(oracle_vlnce, case).eval()
+    opt = torch.optim.Adam(pol.parameters(), lr=2.5e-4)
+    obs, prev, masks, actions, weights = cases.inputs(case)
+    oracle_vlnce.AuxLosses.activate()
+
+    def step():
+        return oracle_vlnce.update_agent(pol, opt, obs, prev, masks, actions, weights)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = rows * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "policy steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows_per_step": rows},
+        "cpu_baseline": {"value": val, "unit": "policy steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{rows} of {ROWS_PER_GPU} rows per step, {args.steps} steps, torch {torch.__version__} CPU fp32"},
+        "e2e": {"value": val, "unit": "policy steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+def cpu_baseline_leg(seconds=15.0):
+    from oracle import cases, vlnce as oracle_vlnce
+
+    rows = 8
+    torch.set_num_threads(os.cpu_count() or 1)
+    case = dict(model_case(), n=rows)
+    pol = cases.build_policy(oracle_vlnce, case).eval()
+    opt = torch.optim.Adam(pol.parameters(), lr=2.5e-4)
+    obs, prev, masks, actions, weights = cases.inputs(case)
+    oracle_vlnce.AuxLosses.activate()
+    oracle_vlnce.update_agent(pol, opt, obs, prev, masks, actions, weights)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        oracle_vlnce.update_agent(pol, opt, obs, prev, masks, actions, weights)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds or n >= 12:
+            break
+    oracle_vlnce.AuxLosses.deactivate()
+    return {"value": rows * n / dt, "unit": "policy steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps of {rows} rows (same workload, batch cut from {ROWS_PER_GPU}), oracle/vlnce.py on torch-CPU fp32"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+
+    import vlnce_b200
+    from oracle import cases
+    from vlnce_b200 import lib, synth
+    from vlnce_b200.il_step import ILTrainerStep
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    case = model_case()
+    pol = cases.build_policy(vlnce_b200, case).to(dev).eval()
+    pol.net.precision = args.precision
+    vlnce_b200.AuxLosses.activate()
+    step = ILTrainerStep(pol, lr=2.5e-4)
+
+    # ---- inputs: NSETS distinct batches, rotated so that consecutive steps never re-read the
+    # same inputs from L2 (6 x 29.4 MB > 126 MB L2); pinned host copies for the e2e leg
+    NSETS = 6
+    host_sets, dev_sets = [], []
+    for i in range(NSETS):
+        b = synth.make_train_batch(1000 + 17 * rank + i, 1, ROWS_PER_GPU, hw=HW, length=LENGTH)
+        obs, prev, masks, actions, weights = b
+        flat = dict(obs, prev_actions=prev, masks=masks, actions=actions, weights=weights)
+        host_sets.append({k: v.pin_memory() for k, v in flat.items()})
+        dev_sets.append({k: v.to(dev) for k, v in flat.items()})
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+    static = {k: torch.empty_like(v) for k, v in dev_sets[0].items()}
+
+    def split(d):
+        obs = {k: d[k] for k in ("instruction", "rgb", "depth", "progress")}
+        return obs, d["prev_actions"], d["masks"], d["actions"], d["weights"]
+
+    def eager_step(d):
+        return step.update_agent(*split(d), return_tensor=True)
+
+    def load_static(src, non_blocking=False):
+        for k, v in static.items():
+            v.copy_(src[k], non_blocking=non_blocking)
+
+    # ---- warm-up (eager), count launches per step, then capture the step into a CUDA graph
+    for i in range(2):
+        load_static(dev_sets[i % NSETS])
+        eager_step(static)
+    torch.cuda.synchronize()
+    c0 = lib.C.vlnce_launch_count()
+    load_static(dev_sets[0])
+    eager_step(static)
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.C.vlnce_launch_count() - c0)
+    graph = None
+    losses = step._losses
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                eager_step(static)
+                side.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    eager_step(static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+        except Exception as e:  # graph capture is an optimisation, not a requirement
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            eager_step(static)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- leg 1: inputs resident in HBM ----------------------------------------------------
+    for i in range(args.warmup):
+        load_static(dev_sets[i % NSETS])
+        run_step()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples), daemon=True)
+    th.start()
+    time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        load_static(dev_sets[i % NSETS])  # device->device rotation of the input set (see config.l2)
+        run_step()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    rows_total = ROWS_PER_GPU * world * args.steps
+    value = rows_total / (ms_total * 1e-3)
+
+    # ---- leg 2: end to end through the public API, host buffers ---------------------------
+    host_loss = torch.empty(3).pin_memory()
+    for i in range(args.warmup):
+        load_static(host_sets[i % NSETS], non_blocking=True)
+        run_step()
+        host_loss.copy_(losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record()
+    last = None
+    for i in range(args.steps):
+        load_static(host_sets[i % NSETS], non_blocking=True)   # H2D from pinned memory
+        run_step()
+        host_loss.copy_(losses, non_blocking=True)               # D2H of the step result
+        torch.cuda.current_stream().synchronize()
+        last = host_loss.tolist()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_wall = time.perf_counter() - t_wall
+    e2e_value = rows_total / (max(e2e_ms * 1e-3, e2e_wall if world == 1 else 0.0))
+    stop.set()
+    th.join(timeout=3)
+
+    # ---- roofline of the dominant kernel (tcgen05 conv tiles), timed live with CUDA events
+    # around every conv launch of 3 further eager steps on the launching stream
+    from vlnce_b200 import trunk as trunk_mod
+
+    rec = []
+    orig = trunk_mod.ConvTrunk._conv
+
+    def timed_conv(self, x, shape_in, cv, y, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig(self, x, shape_in, cv, y, **kw)
+        b.record()
+        n, h, w, c = shape_in
+        gemm_c = kw.get("gemm_c")
+        if gemm_c is not None:
+            flops = 2.0 * n * h * w * gemm_c * cv.K
+        else:
+            p, q = self._out_hw(h, w, cv)
+            flops = 2.0 * n * p * q * cv.K * cv.R * cv.S * c
+        rec.append((a, b, flops, type(self).__name__))
+
+    roof = None
+    if args.precision == "bf16":
+        trunk_mod.ConvTrunk._conv = timed_conv
+        for i in range(3):
+            load_static(dev_sets[i % NSETS])
+            eager_step(static)
+        torch.cuda.synchronize()
+        trunk_mod.ConvTrunk._conv = orig
+        conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
+        conv_flops = sum(f for _, _, f, _ in rec)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv, all 107 launches/step)", "bound": "tensor",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
+                "launches_timed": len(rec), "conv_ms_per_step": conv_ms / 3,
+                "algorithmic_gflop_per_step": conv_flops / 3 / 1e9}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_leg()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "policy steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": ROWS_PER_GPU * world, "rows_per_gpu": ROWS_PER_GPU,
+                       "parallelism": f"dp{world}", "precision": "rgb trunk bf16 / depth trunk fp16 tcgen05, head fp32"
+                       if args.precision == "bf16" else "fp32 CUDA cores",
+                       "l2": f"inputs rotated over {NSETS} distinct batches ({NSETS * h2d_bytes / 1e6:.0f} MB > L2)",
+                       "cuda_graph": graph is not None},
+            "e2e": {"value": e2e_value, "unit": "policy steps/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps, "last_losses": last},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": summarize_clocks(samples),
+        }
+        if roof is not None:
+            line["roofline"] = roof
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,7 @@
  *   - every call enqueues on `stream` and returns immediately; 0 = ok, <0 = bad argument,
  *     >=1000 = 1000 + cudaError_t.  vlnce_last_error() gives the message (thread-local).
  *   - activations are channels-last: images NHWC, sequences (rows, positions, channels).
- *   - dtype codes: VLNCE_F32, VLNCE_BF16, VLNCE_U8, VLNCE_I64.
+ *   - dtype codes: VLNCE_F32, VLNCE_BF16, VLNCE_U8, VLNCE_I64, VLNCE_F16.
  */
 #ifndef VLNCE_B200_H_
 #define VLNCE_B200_H_
@@ -38,6 +38,7 @@ typedef struct CUstream_st* cudaStream_t;
 #define VLNCE_BF16 1
 #define VLNCE_U8 2
 #define VLNCE_I64 3
+#define VLNCE_F16 4
 
 /* ---- library ---------------------------------------------------------------------- */
 const char* vlnce_version(void);
@@ -46,15 +47,17 @@ const char* vlnce_last_error(void);
 long long vlnce_launch_count(void);
 
 /* ---- convolution trunks ------------------------------------------------------------ */
-/* Implicit-GEMM NHWC conv on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM):
+/* Implicit-GEMM NHWC conv on tcgen05 tensor cores (16-bit operands, fp32 accumulate in TMEM):
  *   y = act(scale[k] * conv(x, w) + shift[k] (+ residual)).
- * x (N,H,W,C) bf16, w (K,R,S,C) bf16, y (N,P,Q,K) bf16|f32, residual like y in bf16 or NULL,
+ * ab_dtype = VLNCE_BF16 or VLNCE_F16 is the type of x, w and residual (fp16 for the
+ * GroupNorm depth trunk whose activations are O(1): 8x finer than bf16 at the same cost).
+ * x (N,H,W,C), w (K,R,S,C), y (N,P,Q,K) ab_dtype|f32, residual (N,P,Q,K) ab_dtype or NULL,
  * scale/shift (K) f32 or both NULL (raw conv).  C % 32 == 0, K % 32 == 0.  block_n: 0 = auto.
  * Replaces torch.nn.Conv2d + folded BatchNorm2d/ReLU/residual in torchvision ResNet
  * (resnet_encoders.py:198-199) and the convs of the DD-PPO GroupNorm ResNet
  * (resnet_encoders.py:95; habitat_baselines v0.1.7 rl/ddppo/policy/resnet.py). */
-int vlnce_conv2d_bf16(const void* x, const void* w, const float* scale, const float* shift,
-                      const void* residual, void* y, int y_dtype, int N, int H, int W, int C,
+int vlnce_conv2d_bf16(const void* x, const void* w, int ab_dtype, const float* scale,
+                      const float* shift, const void* residual, void* y, int y_dtype, int N, int H, int W, int C,
                       int K, int R, int S, int stride, int pad, int relu, int block_n,
                       cudaStream_t stream);
 
@@ -71,9 +74,10 @@ int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w_dtype, con
 int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int N, int H, int W,
                           cudaStream_t stream);
 /* Depth stem operand: depth (N,H,W,1) f32 -> avg_pool2d(2) -> 7x7/2 pad-3 im2col rows
- * (N*P*Q, 64) bf16, K index r*7+s, zero padded 49..63 (habitat_baselines v0.1.7
+ * (N*P*Q, 64) bf16|f16, K index r*7+s, zero padded 49..63 (habitat_baselines v0.1.7
  * ResNetEncoder.forward: permute, avg_pool2d(2), backbone.conv1). */
-int vlnce_im2col_depth_stem(const float* x, void* a, int N, int H, int W, cudaStream_t stream);
+int vlnce_im2col_depth_stem(const float* x, void* a, int a_dtype, int N, int H, int W,
+                            cudaStream_t stream);
 /* avg_pool2d(2) on (N,H,W,C) f32 -> (N,H/2,W/2,C) f32 (fp32-exact mode of the depth stem) */
 int vlnce_avgpool2x2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);
 /* MaxPool2d(3, stride 2, pad 1) NHWC */

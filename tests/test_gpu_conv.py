@@ -53,27 +53,28 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("half", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
-def test_conv_umma_matches_reference(case):
+def test_conv_umma_matches_reference(case, half):
     n, h, w, c, k, r, stride, pad, bn, epi = case
-    g = torch.Generator(device="cpu").manual_seed(hash(case) % 1000)
-    x = torch.randn(n, h, w, c, generator=g).to(DEV).bfloat16()
-    wt = (torch.randn(k, r, r, c, generator=g) * (2.0 / (r * r * c)) ** 0.5).to(DEV).bfloat16()
+    g = torch.Generator(device="cpu").manual_seed(sum(case[:9]))
+    x = torch.randn(n, h, w, c, generator=g).to(DEV).to(half)
+    wt = (torch.randn(k, r, r, c, generator=g) * (2.0 / (r * r * c)) ** 0.5).to(DEV).to(half)
     p, q = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - r) // stride + 1
     scale = shift = res = None
     if "affine" in epi:
         scale = (torch.rand(k, generator=g) + 0.5).to(DEV)
         shift = torch.randn(k, generator=g).to(DEV) * 0.1
     if "res" in epi:
-        res = torch.randn(n, p, q, k, generator=g).to(DEV).bfloat16()
+        res = torch.randn(n, p, q, k, generator=g).to(DEV).to(half)
     relu = "relu" in epi
     want = _ref_conv(x, wt, scale, shift, res, stride, pad, relu)  # fp32 out, same bf16 operands
-    for y_dtype in (torch.bfloat16, torch.float32):
+    for y_dtype in (half, torch.float32):
         y = torch.full((n, p, q, k), float("nan"), device=DEV, dtype=y_dtype)
-        C.vlnce_conv2d_bf16(ptr(x), ptr(wt), ptr(scale), ptr(shift), ptr(res), ptr(y), lib.code(y), n, h, w,
-                            c, k, r, r, stride, pad, int(relu), bn, lib.stream())
+        C.vlnce_conv2d_bf16(ptr(x), ptr(wt), lib.code(x), ptr(scale), ptr(shift), ptr(res), ptr(y), lib.code(y),
+                            n, h, w, c, k, r, r, stride, pad, int(relu), bn, lib.stream())
         torch.cuda.synchronize()
-        tol = 2e-2 if y_dtype == torch.bfloat16 else 2e-3
+        tol = {torch.bfloat16: 2e-2, torch.float16: 3e-3, torch.float32: 2e-3}[y_dtype]
         err = (y.float() - want).abs().max().item()
         ref = want.abs().max().item()
         assert torch.isfinite(y.float()).all(), f"non-finite output ({y_dtype})"
@@ -85,5 +86,5 @@ def test_conv_umma_rejects_bad_shapes():
     w = torch.zeros(32, 1, 1, 24, device=DEV, dtype=torch.bfloat16)
     y = torch.zeros(1, 4, 4, 32, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(lib.VlnceError, match="multiple of 32"):
-        C.vlnce_conv2d_bf16(ptr(x), ptr(w), None, None, None, ptr(y), lib.BF16, 1, 4, 4, 24, 32, 1, 1, 1, 0, 0,
-                            0, lib.stream())
+        C.vlnce_conv2d_bf16(ptr(x), ptr(w), lib.BF16, None, None, None, ptr(y), lib.BF16, 1, 4, 4, 24, 32, 1, 1, 1,
+                            0, 0, 0, lib.stream())

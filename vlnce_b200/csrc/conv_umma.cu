@@ -45,7 +45,8 @@ struct ConvParams {
   int num_k_iters;  // R*S*c_chunks
   int n_tiles;      // K / BLOCK_N
   int relu;
-  int y_fp32;       // 1: store fp32 instead of bf16
+  int y_fp32;       // 1: store fp32 instead of the 16-bit activation type
+  int ab_half;      // 1: operands / residual / 16-bit output are fp16, else bf16
 };
 
 template <int BLOCK_N, int BLOCK_K>
@@ -188,8 +189,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
             const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              f[q4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
-              f[q4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xffff0000u);
+              if (p.ab_half) {
+                const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                f[q4 * 8 + e * 2 + 0] += h2.x;
+                f[q4 * 8 + e * 2 + 1] += h2.y;
+              } else {
+                f[q4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
+                f[q4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xffff0000u);
+              }
             }
           }
         }
@@ -209,8 +216,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q4 * 8 + e * 2], f[q4 * 8 + e * 2 + 1]);
-              w[e] = *reinterpret_cast<uint32_t*>(&h2);
+              if (p.ab_half) {
+                __half2 h2 = __floats2half2_rn(f[q4 * 8 + e * 2], f[q4 * 8 + e * 2 + 1]);
+                w[e] = *reinterpret_cast<uint32_t*>(&h2);
+              } else {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[q4 * 8 + e * 2], f[q4 * 8 + e * 2 + 1]);
+                w[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
             }
             yp[q4] = make_uint4(w[0], w[1], w[2], w[3]);
           }
@@ -219,7 +231,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+    const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, p.ab_half ? 0u : 1u);
     for (int it = 0; it < p.num_k_iters; ++it) {
       const int stage = it % kStages;
       const uint32_t phase = (it / kStages) & 1;
@@ -296,7 +308,7 @@ int launch(const CUtensorMap& tmap, const ConvParams& p, cudaStream_t stream) {
 
 using namespace vlnce;
 
-extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, const float* scale,
+extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, int ab_dtype, const float* scale,
                                  const float* shift, const void* residual, void* y, int y_dtype,
                                  int N, int H, int W, int C, int K, int R, int S, int stride,
                                  int pad, int relu, int block_n, cudaStream_t stream) {
@@ -306,7 +318,8 @@ extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, const float* scal
   VLNCE_CHECK_ARG(C % 32 == 0, "conv2d_bf16: C=%d must be a multiple of 32", C);
   VLNCE_CHECK_ARG(K % 32 == 0, "conv2d_bf16: K=%d must be a multiple of 32", K);
   VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv2d_bf16: scale/shift must come together");
-  VLNCE_CHECK_ARG(y_dtype == VLNCE_BF16 || y_dtype == VLNCE_F32, "conv2d_bf16: y dtype");
+  VLNCE_CHECK_ARG(ab_dtype == VLNCE_BF16 || ab_dtype == VLNCE_F16, "conv2d_bf16: operand dtype must be bf16 or f16");
+  VLNCE_CHECK_ARG(y_dtype == ab_dtype || y_dtype == VLNCE_F32, "conv2d_bf16: y dtype must be the operand type or f32");
   VLNCE_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
@@ -339,7 +352,7 @@ extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, const float* scal
   const cuuint64_t gstride[1] = {(cuuint64_t)R * S * C * 2};
   const cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)bn};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride,
+  CUresult cr = encode(&tmap, ab_dtype == VLNCE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride,
                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -362,6 +375,7 @@ extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, const float* scal
   p.n_tiles = K / bn;
   p.relu = relu;
   p.y_fp32 = (y_dtype == VLNCE_F32);
+  p.ab_half = (ab_dtype == VLNCE_F16);
 
 #define VLNCE_CONV_CASE(BN, BK) \
   if (bn == BN && block_k == BK) return launch<BN, BK>(tmap, p, stream);

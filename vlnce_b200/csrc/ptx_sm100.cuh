@@ -174,11 +174,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;
   return d;
 }
-// Instruction descriptor for kind::f16, A/B = bf16 (K-major both), D = fp32.
-//   [4,6) D fmt 1=f32   [7,10) A fmt 1=bf16   [10,13) B fmt 1=bf16
+// Instruction descriptor for kind::f16, A/B = bf16 or fp16 (K-major both), D = fp32.
+//   [4,6) D fmt 1=f32   [7,10) A fmt 0=f16 1=bf16   [10,13) B fmt likewise
 //   [15] A major 0=K    [16] B major 0=K      [17,23) N>>3      [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n, uint32_t ab_is_bf16) {
+  return (1u << 4) | (ab_is_bf16 << 7) | (ab_is_bf16 << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // Byte offset inside a 1024B-aligned operand tile of element (row, 16B-chunk) under the

@@ -77,7 +77,8 @@ __global__ void im2col_rgb_stem_kernel(const TX* __restrict__ x, __nv_bfloat16* 
   }
 }
 
-__global__ void im2col_depth_stem_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a,
+template <typename TA>
+__global__ void im2col_depth_stem_kernel(const float* __restrict__ x, TA* __restrict__ a,
                                          int N, int H, int W, int P, int Q) {
   // x: (N,H,W,1); pooled image is (H/2, W/2); output pixel (p,q) of the 7x7/2 pad-3 conv
   constexpr int KP = 64, CHUNKS = KP / 8;
@@ -90,7 +91,7 @@ __global__ void im2col_depth_stem_kernel(const float* __restrict__ x, __nv_bfloa
     const int q = (int)(m % Q);
     const int p = (int)((m / Q) % P);
     const int n = (int)(m / ((long long)P * Q));
-    __align__(16) __nv_bfloat16 v[8];
+    __align__(16) TA v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int kk = ch * 8 + e;
@@ -103,7 +104,7 @@ __global__ void im2col_depth_stem_kernel(const float* __restrict__ x, __nv_bfloa
           f = ((__ldg(b) + __ldg(b + 1)) + (__ldg(b + W) + __ldg(b + W + 1))) * 0.25f;
         }
       }
-      v[e] = __float2bfloat16_rn(f);
+      v[e] = from_float<TA>(f);
     }
     *reinterpret_cast<uint4*>(a + m * KP + ch * 8) = *reinterpret_cast<const uint4*>(v);
   }
@@ -340,7 +341,13 @@ int conv_ref_dispatch_y(const void* x, const void* w, const float* scale, const 
       (const TX*)x, (const TW*)w, scale, shift, (const TR*)residual, (TY*)y, N, H, W, C, K, R, S, \
       stride, pad, P, Q, relu)
   const bool rb = residual != nullptr && res_dtype == VLNCE_BF16;
-  if (y_dtype == VLNCE_F32) {
+  if (residual != nullptr && res_dtype == VLNCE_F16) {
+    if (y_dtype != VLNCE_F32) {
+      set_error("conv2d_ref: f16 residual needs f32 output");
+      return VLNCE_ERR_INVALID_ARGUMENT;
+    }
+    GO(float, __half);
+  } else if (y_dtype == VLNCE_F32) {
     if (rb) GO(float, __nv_bfloat16); else GO(float, float);
   } else {
     if (rb || residual == nullptr) GO(__nv_bfloat16, __nv_bfloat16); else GO(__nv_bfloat16, float);
@@ -362,7 +369,13 @@ extern "C" int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w
   VLNCE_CHECK_ARG(x && w && y, "conv2d_ref: null tensor");
   VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv2d_ref: scale/shift must come together");
   VLNCE_CHECK_ARG(y_dtype == VLNCE_F32 || y_dtype == VLNCE_BF16, "conv2d_ref: y dtype");
-  VLNCE_CHECK_ARG(w_dtype == VLNCE_F32 || w_dtype == VLNCE_BF16, "conv2d_ref: w dtype");
+  VLNCE_CHECK_ARG(w_dtype == VLNCE_F32 || w_dtype == VLNCE_BF16 || w_dtype == VLNCE_F16, "conv2d_ref: w dtype");
+  if (w_dtype == VLNCE_F16) {
+    VLNCE_CHECK_ARG(x_dtype == VLNCE_F16, "conv2d_ref: f16 weights need f16 input");
+    const int P_ = (H + 2 * pad - R) / stride + 1, Q_ = (W + 2 * pad - S) / stride + 1;
+    return conv_ref_dispatch_y<__half, __half>(x, w, scale, shift, residual, res_dtype, y, y_dtype, N, H, W, C, K,
+                                               R, S, stride, pad, P_, Q_, relu, stream);
+  }
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
   VLNCE_CHECK_ARG(P > 0 && Q > 0, "conv2d_ref: empty output");
 #define ARGS x, w, scale, shift, residual, res_dtype, y, y_dtype, N, H, W, C, K, R, S, stride, pad, P, Q, relu, stream
@@ -399,14 +412,22 @@ extern "C" int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int N,
   return VLNCE_OK;
 }
 
-extern "C" int vlnce_im2col_depth_stem(const float* x, void* a, int N, int H, int W,
+extern "C" int vlnce_im2col_depth_stem(const float* x, void* a, int a_dtype, int N, int H, int W,
                                        cudaStream_t stream) {
   VLNCE_CHECK_ARG(x && a && N > 0 && H > 1 && W > 1 && H % 2 == 0 && W % 2 == 0,
                   "im2col_depth_stem: bad arguments");
   const int Hp = H / 2, Wp = W / 2;
   const int P = (Hp + 6 - 7) / 2 + 1, Q = (Wp + 6 - 7) / 2 + 1;
   const long long total = (long long)N * P * Q * 8;
-  im2col_depth_stem_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)a, N, H, W, P, Q);
+  if (a_dtype == VLNCE_F16)
+    im2col_depth_stem_kernel<__half><<<grid_for(total, 256), 256, 0, stream>>>(x, (__half*)a, N, H, W, P, Q);
+  else if (a_dtype == VLNCE_BF16)
+    im2col_depth_stem_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(x, (__nv_bfloat16*)a, N, H,
+                                                                                       W, P, Q);
+  else {
+    set_error("im2col_depth_stem: operand dtype must be bf16 or f16");
+    return VLNCE_ERR_INVALID_ARGUMENT;
+  }
   VLNCE_LAUNCH_CHECK("im2col_depth_stem_kernel");
   return VLNCE_OK;
 }
@@ -428,6 +449,9 @@ extern "C" int vlnce_maxpool3x3s2(const void* x, void* y, int dtype, int N, int 
   if (dtype == VLNCE_BF16)
     maxpool3x3s2_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, P, Q);
+  else if (dtype == VLNCE_F16)
+    maxpool3x3s2_kernel<__half><<<grid_for(total, 256), 256, 0, stream>>>((const __half*)x, (__half*)y, N, H, W, C,
+                                                                          P, Q);
   else if (dtype == VLNCE_F32)
     maxpool3x3s2_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>((const float*)x, (float*)y, N,
                                                                          H, W, C, P, Q);
@@ -498,6 +522,10 @@ extern "C" int vlnce_affine_apply(const void* x, int x_dtype, const float* scale
     affine_apply_kernel<float, __nv_bfloat16><<<grid, 256, 0, stream>>>(
         (const float*)x, scale, shift, scale_stride_n, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y,
         HW, C, total_vec, relu);
+  else if (x_dtype == VLNCE_F32 && y_dtype == VLNCE_F16)
+    affine_apply_kernel<float, __half><<<grid, 256, 0, stream>>>(
+        (const float*)x, scale, shift, scale_stride_n, (const __half*)residual, (__half*)y, HW, C, total_vec,
+        relu);
   else if (x_dtype == VLNCE_F32 && y_dtype == VLNCE_F32)
     affine_apply_kernel<float, float><<<grid, 256, 0, stream>>>(
         (const float*)x, scale, shift, scale_stride_n, (const float*)residual, (float*)y, HW, C,
@@ -517,6 +545,9 @@ extern "C" int vlnce_adaptive_avgpool(const void* x, int dtype, float* y, int ld
   if (dtype == VLNCE_BF16)
     adaptive_avgpool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
         (const __nv_bfloat16*)x, y, ldy, N, H, W, C, O);
+  else if (dtype == VLNCE_F16)
+    adaptive_avgpool_kernel<__half><<<grid_for(total, 256), 256, 0, stream>>>((const __half*)x, y, ldy, N, H, W, C,
+                                                                              O);
   else if (dtype == VLNCE_F32)
     adaptive_avgpool_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>((const float*)x, y, ldy, N,
                                                                              H, W, C, O);

@@ -17,8 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "vlnce_b200.h")
 LIB_PATH = os.path.join(HERE, "libvlnce_b200.so")
 
-F32, BF16, U8, I64 = 0, 1, 2, 3
-_DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8, torch.int64: I64}
+F32, BF16, U8, I64, F16 = 0, 1, 2, 3, 4
+_DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8, torch.int64: I64, torch.float16: F16}
 
 
 class VlnceError(RuntimeError):

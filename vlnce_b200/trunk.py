@@ -54,8 +54,9 @@ class _Conv:
     """One packed convolution (+ its normalisation)."""
 
     def __init__(self, conv: nn.Conv2d, norm: nn.Module, precision: str, in_scale: float = 1.0,
-                 stem: Optional[str] = None):
+                 stem: Optional[str] = None, wdt=torch.bfloat16):
         self.conv, self.norm, self.precision, self.in_scale, self.stem = conv, norm, precision, in_scale, stem
+        self.wdt = wdt if precision == "bf16" else torch.float32
         self.K, self.Cin, self.R, self.S = conv.weight.shape
         self.stride, self.pad = conv.stride[0], conv.padding[0]
         self.w = self.scale = self.shift = None
@@ -71,7 +72,7 @@ class _Conv:
         if ver == self._ver:
             return
         w = self.conv.weight.detach()
-        wdt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        wdt = self.wdt
         krsc = w.permute(0, 2, 3, 1).contiguous()
         if self.precision == "bf16" and self.stem == "rgb":  # im2col operand: (r*7+s)*3+c, pad 147->192
             flat = krsc.reshape(self.K, -1)
@@ -94,11 +95,16 @@ class _Conv:
 
 
 class ConvTrunk:
+    # 16-bit tensor-core operand type of the "bf16" precision mode: bf16 for the BN-folded RGB
+    # trunk (unbounded residual stream), fp16 for the GroupNorm depth trunk (activations are
+    # renormalised to O(1) every layer; fp16 carries 3 more significand bits at the same cost).
+    half_dtype = torch.bfloat16
+
     def __init__(self, device, precision: str = "bf16"):
         assert precision in ("bf16", "fp32")
         self.device = device
         self.precision = precision
-        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.adt = self.half_dtype if precision == "bf16" else torch.float32
         self.pool = BufferPool(device)
         self._slot = 0
 
@@ -118,12 +124,13 @@ class ConvTrunk:
         st = lib.stream()
         if self.precision == "bf16":
             if gemm_c is not None:
-                C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y),
-                                    lib.code(y), n * h * w, 1, 1, gemm_c, cv.K, 1, 1, 1, 0, int(relu), 0, st)
+                C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
+                                    ptr(y), lib.code(y), n * h * w, 1, 1, gemm_c, cv.K, 1, 1, 1, 0, int(relu), 0,
+                                    st)
             else:
-                C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y),
-                                    lib.code(y), n, h, w, c, cv.K, cv.R, cv.S, cv.stride, cv.pad, int(relu),
-                                    0, st)
+                C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
+                                    ptr(y), lib.code(y), n, h, w, c, cv.K, cv.R, cv.S, cv.stride, cv.pad,
+                                    int(relu), 0, st)
         else:
             C.vlnce_conv2d_ref(ptr(x), lib.code(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift),
                                ptr(residual), lib.F32, ptr(y), lib.F32, n, h, w, c, cv.K, cv.R, cv.S,
@@ -230,20 +237,23 @@ class DepthTrunk(ConvTrunk):
     """DD-PPO GroupNorm ResNet encoder; ``enc`` has ``backbone`` (conv1, maxpool, layer1..4 of
     blocks with ``convs`` / ``downsample`` Sequentials) and ``compression``."""
 
+    half_dtype = torch.float16
+
     def __init__(self, enc: nn.Module, device, precision="bf16"):
         super().__init__(device, precision)
         bb = enc.backbone
-        self.stem = _Conv(bb.conv1[0], bb.conv1[1], precision, stem="depth")
+        _C = lambda c, g, p, **kw: _Conv(c, g, p, wdt=torch.float16, **kw)  # noqa: E731
+        self.stem = _C(bb.conv1[0], bb.conv1[1], precision, stem="depth")
         self.blocks = []
         for layer in (bb.layer1, bb.layer2, bb.layer3, bb.layer4):
             for blk in layer.children():
                 convs = list(blk.convs.children())
                 pairs = [(convs[i], convs[i + 1]) for i in range(len(convs)) if isinstance(convs[i], nn.Conv2d)]
-                d = {"convs": [_Conv(c, g, precision) for c, g in pairs]}
+                d = {"convs": [_C(c, g, precision) for c, g in pairs]}
                 if blk.downsample is not None:
-                    d["ds"] = _Conv(blk.downsample[0], blk.downsample[1], precision)
+                    d["ds"] = _C(blk.downsample[0], blk.downsample[1], precision)
                 self.blocks.append(d)
-        self.compress = _Conv(enc.compression[0], enc.compression[1], precision)
+        self.compress = _C(enc.compression[0], enc.compression[1], precision)
         self.out_channels = self.compress.K
 
     def _all(self):
@@ -277,8 +287,8 @@ class DepthTrunk(ConvTrunk):
         hp, wp = h // 2, w // 2
         p, q = (hp + 6 - 7) // 2 + 1, (wp + 6 - 7) // 2 + 1
         if self.precision == "bf16":
-            a = self.pool.get("stem_a", (n * p * q, 64), torch.bfloat16)
-            C.vlnce_im2col_depth_stem(ptr(depth), ptr(a), n, h, w, st)
+            a = self.pool.get("stem_a", (n * p * q, 64), self.adt)
+            C.vlnce_im2col_depth_stem(ptr(depth), ptr(a), lib.code(a), n, h, w, st)
             x, shp = self._gn_conv(a, (n, p, q, 64), self.stem, "stem_y", gemm_c=64, out_hw=(p, q))
         else:
             pooled = self.pool.get("stem_a", (n, hp, wp, 1), torch.float32)
