@@ -84,6 +84,18 @@ def summarize_clocks(lines):
     return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores() -> int:
+    """CPU threads this process may really use: affinity mask capped by the cgroup quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 # ----------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path on the host cores: the oracle port
@@ -93,7 +105,7 @@ def run_reference(args, rank, world):
     from oracle import cases, vlnce as oracle_vlnce
 
     rows = 16  # bounded sample of the 64-row step
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     case = dict(model_case(), n=rows)
     pol = cases.build_policy(oracle_vlnce, case).eval()
     opt = torch.optim.Adam(pol.parameters(), lr=2.5e-4)
@@ -127,7 +139,7 @@ def cpu_baseline_leg(seconds=15.0):
     from oracle import cases, vlnce as oracle_vlnce
 
     rows = 8
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     case = dict(model_case(), n=rows)
     pol = cases.build_policy(oracle_vlnce, case).eval()
     opt = torch.optim.Adam(pol.parameters(), lr=2.5e-4)

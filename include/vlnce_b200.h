@@ -68,10 +68,10 @@ int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w_dtype, con
                      int y_dtype, int N, int H, int W, int C, int K, int R, int S, int stride,
                      int pad, int relu, cudaStream_t stream);
 
-/* RGB stem operand: x (N,H,W,3) u8|f32 0..255 -> im2col rows (N*P*Q, 192) bf16 of the 7x7/2
+/* RGB stem operand: x (N,H,W,3) u8|f32 0..255 -> im2col rows (N*P*Q, 192) bf16|f16 of the 7x7/2
  * pad-3 window, K index (r*7+s)*3+c, zero padded 147..191 (resnet_encoders.py:182,198:
  * permute + /255 + conv1; the /255 and optional mean/std live in the folded scale/shift). */
-int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int N, int H, int W,
+int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int a_dtype, int N, int H, int W,
                           cudaStream_t stream);
 /* Depth stem operand: depth (N,H,W,1) f32 -> avg_pool2d(2) -> 7x7/2 pad-3 im2col rows
  * (N*P*Q, 64) bf16|f16, K index r*7+s, zero padded 49..63 (habitat_baselines v0.1.7
@@ -84,10 +84,11 @@ int vlnce_avgpool2x2(const float* x, float* y, int N, int H, int W, int C, cudaS
 int vlnce_maxpool3x3s2(const void* x, void* y, int dtype, int N, int H, int W, int C,
                        cudaStream_t stream);
 /* GroupNorm statistics of raw conv output x (N, HW, C): writes per-(n,c) scale/shift with the
- * affine folded: scale = rstd*gamma, shift = beta - mean*rstd*gamma (torch.nn.GroupNorm). */
+ * affine folded: scale = rstd*gamma, shift = beta - mean*rstd*gamma (torch.nn.GroupNorm).
+ * workspace (caller-owned, optional) enables the coalesced two-stage reduction. */
 int vlnce_groupnorm_stats(const void* x, int dtype, const float* gamma, const float* beta,
-                          float* scale, float* shift, int N, int HW, int C, int groups, float eps,
-                          cudaStream_t stream);
+                          float* scale, float* shift, float* workspace, size_t workspace_bytes, int N,
+                          int HW, int C, int groups, float eps, cudaStream_t stream);
 /* Train-mode BatchNorm2d statistics over all N*HW rows: per-channel scale/shift
  * from batch mean / biased var; updates running_mean/var (momentum, unbiased var) in place. */
 int vlnce_batchnorm_train_stats(const void* x, int dtype, const float* gamma, const float* beta,
@@ -112,12 +113,13 @@ int vlnce_nchw_to_positions(const float* x, float* y, int ldy, int N, int C, int
 /* ---- trainable head: dense algebra --------------------------------------------------- */
 /* C[m,n] = act(sum_k A[m*lda_m + k*lda_k] * B[k*ldb_k + n*ldb_n] + bias[n] + beta*C[m,n]),
  * fp32 on CUDA cores; act 0 none / 1 ReLU / 2 tanh.  One routine for every Linear / Conv1d(k=1) of
+ * workspace (optional, caller-owned) enables a deterministic split-K for skinny problems.
  * the head forward and backward (cma_policy.py:101-184: rgb_linear, depth_linear, state_q,
  * text_k, text_q, rgb_kv, depth_kv, second_state_compress, progress_monitor; policy.py:19-21
  * CategoricalNet; GRU / LSTM input and hidden projections). */
 int vlnce_sgemm(const float* A, long long lda_m, long long lda_k, const float* B, long long ldb_k,
                 long long ldb_n, float* C, long long ldc, const float* bias, int M, int N, int K,
-                float beta, int act, cudaStream_t stream);
+                float beta, int act, float* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* out[n] (+)= sum_m A[m*lda + n]  — bias gradients */
 int vlnce_colsum(const float* A, long long lda, float* out, int M, int N, int accumulate,
                  cudaStream_t stream);

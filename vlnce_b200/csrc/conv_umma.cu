@@ -28,8 +28,8 @@ namespace {
 using namespace ptx;
 
 constexpr int BLOCK_M = 128;
-constexpr int kStages = 4;
-constexpr int kLag = 2;  // cp.async groups kept in flight before a stage is published
+constexpr int kMaxStages = 4;  // ring depth is chosen per launch: min(4, k-iterations)
+constexpr int kLag = 2;        // cp.async groups kept in flight before a stage is published
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 192;
 
@@ -45,6 +45,7 @@ struct ConvParams {
   int num_k_iters;  // R*S*c_chunks
   int n_tiles;      // K / BLOCK_N
   int relu;
+  int stages;       // smem ring depth (1..4); short K loops take less smem -> more CTAs per SM
   int y_fp32;       // 1: store fp32 instead of the 16-bit activation type
   int ab_half;      // 1: operands / residual / 16-bit output are fp16, else bf16
 };
@@ -58,8 +59,7 @@ struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * ROW_BYTES;
   static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = kStages * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 + 1024;  // + barriers + align slack
+  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 256 + 1024; }  // + barriers + align
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must stay 1024B aligned");
 };
 
@@ -70,9 +70,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* accum_bar = empty_bar + kStages;
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* accum_bar = empty_bar + kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -83,7 +84,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
   const int n0 = n_tile * BLOCK_N;
 
   if (threadIdx.x == 5 * 32) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], kProducerThreads + 1);  // 128 gather threads + the TMA issuer
       mbar_init(&empty_bar[s], 1);                    // one tcgen05.commit
     }
@@ -100,7 +101,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t smem_a0 = smem_u32(smem);
-  const uint32_t smem_b0 = smem_a0 + kStages * C::A_BYTES;
+  const uint32_t smem_b0 = smem_a0 + stages * C::A_BYTES;
 
   if (warp < 4) {
     // ------------------------------------------------------------ A gather (producers)
@@ -129,9 +130,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
       }
     }
     int rf = 0, sf = 0, cc = 0;
+    const int lag = min(kLag, stages - 1);
+    int stage = 0, pub = 0;  // ring slot being filled / next slot to publish
+    uint32_t phase = 0;
     for (int it = 0; it < p.num_k_iters; ++it) {
-      const int stage = it % kStages;
-      const uint32_t phase = (it / kStages) & 1;
       mbar_wait(&empty_bar[stage], phase ^ 1, 1);
       const uint32_t a_stage = smem_a0 + stage * C::A_BYTES;
       const int c_off = cc * BLOCK_K + chunk * 8;
@@ -144,20 +146,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
         cp_async_16(a_stage + dst_off[i], src, ok ? 16u : 0u);
       }
       cp_async_commit();
-      if (it >= kLag) {
-        cp_async_wait<kLag>();
+      if (it >= lag) {
+        if (lag == 2) cp_async_wait<2>();
+        else if (lag == 1) cp_async_wait<1>();
+        else cp_async_wait<0>();
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the MMA (async proxy)
-        mbar_arrive(&full_bar[(it - kLag) % kStages]);
+        mbar_arrive(&full_bar[pub]);
+        if (++pub == stages) pub = 0;
       }
       if (++cc == p.c_chunks) {
         cc = 0;
         if (++sf == p.S) { sf = 0; ++rf; }
       }
+      if (++stage == stages) { stage = 0; phase ^= 1; }
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
-    for (int it = (p.num_k_iters > kLag ? p.num_k_iters - kLag : 0); it < p.num_k_iters; ++it)
-      mbar_arrive(&full_bar[it % kStages]);
+    for (int it = (p.num_k_iters > lag ? p.num_k_iters - lag : 0); it < p.num_k_iters; ++it) {
+      mbar_arrive(&full_bar[pub]);
+      if (++pub == stages) pub = 0;
+    }
 
     // ------------------------------------------------------------ epilogue
     mbar_wait(accum_bar, 0, 2);
@@ -232,9 +240,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
   } else if (warp == 4) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, p.ab_half ? 0u : 1u);
+    int stage = 0;
+    uint32_t phase = 0;
     for (int it = 0; it < p.num_k_iters; ++it) {
-      const int stage = it % kStages;
-      const uint32_t phase = (it / kStages) & 1;
       mbar_wait(&full_bar[stage], phase, 3);
       tc_fence_after_sync();
       if (lane == 0) {
@@ -248,18 +256,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p)
         umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
       }
       __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
     }
     if (lane == 0) umma_commit(accum_bar);
     __syncwarp();
   } else {
     // ------------------------------------------------------------ weight TMA (warp 5)
     if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
       for (int it = 0; it < p.num_k_iters; ++it) {
-        const int stage = it % kStages;
-        const uint32_t phase = (it / kStages) & 1;
         mbar_wait(&empty_bar[stage], phase ^ 1, 4);
         mbar_arrive_expect_tx(&full_bar[stage], C::B_BYTES);
         tma_load_2d(smem_b0 + stage * C::B_BYTES, &tmap_w, &full_bar[stage], it * BLOCK_K, n0);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
@@ -293,12 +303,12 @@ int launch(const CUtensorMap& tmap, const ConvParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BLOCK_N, BLOCK_K>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes(kMaxStages));
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(conv_umma)");
     configured = true;
   }
   const long long tiles = (long long)cdiv(p.M, BLOCK_M) * p.n_tiles;
-  conv_umma_kernel<BLOCK_N, BLOCK_K><<<(unsigned)tiles, kThreads, C::SMEM_BYTES, stream>>>(tmap, p);
+  conv_umma_kernel<BLOCK_N, BLOCK_K><<<(unsigned)tiles, kThreads, C::smem_bytes(p.stages), stream>>>(tmap, p);
   VLNCE_LAUNCH_CHECK("conv_umma_kernel");
   return VLNCE_OK;
 }
@@ -374,6 +384,7 @@ extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, int ab_dtype, con
   p.num_k_iters = R * S * p.c_chunks;
   p.n_tiles = K / bn;
   p.relu = relu;
+  p.stages = p.num_k_iters < kMaxStages ? p.num_k_iters : kMaxStages;
   p.y_fp32 = (y_dtype == VLNCE_F32);
   p.ab_half = (ab_dtype == VLNCE_F16);
 

@@ -13,7 +13,8 @@ constexpr int TM = 64, TN = 64, TK = 16;
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
              const float* __restrict__ B, long long ldb_k, long long ldb_n, float* __restrict__ C,
-             long long ldc, const float* __restrict__ bias, int M, int N, int K, float beta, int act) {
+             long long ldc, const float* __restrict__ bias, int M, int N, int K, float beta, int act,
+             float* __restrict__ partial, int k_per_split) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -23,14 +24,17 @@ sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
   // load mappings: favour the contiguous dimension of each operand
   const bool a_kfast = (lda_k == 1);
   const bool b_nfast = (ldb_n == 1);
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  // split-K: blockIdx.z owns K range [kb, ke); partial sums go to partial[z][M][N]
+  const int kb = blockIdx.z * k_per_split;
+  const int ke = min(K, kb + k_per_split);
+  for (int k0 = kb; k0 < ke; k0 += TK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = tid + i * 256;  // 1024 elements of the 64x16 A tile
       int mm, kk;
       if (a_kfast) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
       const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < K) ? __ldg(A + gm * lda_m + gk * lda_k) : 0.f;
+      As[kk][mm] = (gm < M && gk < ke) ? __ldg(A + gm * lda_m + gk * lda_k) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -38,7 +42,7 @@ sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
       int nn, kk;
       if (b_nfast) { nn = e % TN; kk = e / TN; } else { kk = e % TK; nn = e / TK; }
       const int gn = n0 + nn, gk = k0 + kk;
-      Bs[kk][nn] = (gn < N && gk < K) ? __ldg(B + gk * ldb_k + gn * ldb_n) : 0.f;
+      Bs[kk][nn] = (gn < N && gk < ke) ? __ldg(B + gk * ldb_k + gn * ldb_n) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -63,6 +67,10 @@ sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
       float v = acc[i][j];
+      if (partial != nullptr) {
+        partial[((size_t)blockIdx.z * M + gm) * N + gn] = v;
+        continue;
+      }
       if (bias != nullptr) v += bias[gn];
       float* cp = C + gm * ldc + gn;
       if (beta != 0.f) v += beta * (*cp);
@@ -70,6 +78,26 @@ sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
       else if (act == 2) v = tanhf(v);
       *cp = v;
     }
+  }
+}
+
+// C = act(sum_z partial[z] + bias + beta*C)  — second stage of the split-K GEMM (fixed order:
+// deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ C,
+                                     long long ldc, const float* __restrict__ bias, int M, int N,
+                                     float beta, int act) {
+  const long long total = (long long)M * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(idx / N), n = (int)(idx % N);
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += partial[(size_t)z * total + idx];
+    if (bias != nullptr) v += bias[n];
+    float* cp = C + m * ldc + n;
+    if (beta != 0.f) v += beta * (*cp);
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 2) v = tanhf(v);
+    *cp = v;
   }
 }
 
@@ -99,14 +127,35 @@ using namespace vlnce;
 extern "C" int vlnce_sgemm(const float* A, long long lda_m, long long lda_k, const float* B,
                            long long ldb_k, long long ldb_n, float* C, long long ldc,
                            const float* bias, int M, int N, int K, float beta, int act,
-                           cudaStream_t stream) {
+                           float* workspace, size_t workspace_bytes, cudaStream_t stream) {
   VLNCE_CHECK_ARG(A && B && C, "sgemm: null operand");
   VLNCE_CHECK_ARG(M > 0 && N > 0 && K > 0, "sgemm: empty problem %dx%dx%d", M, N, K);
   VLNCE_CHECK_ARG(act >= 0 && act <= 2, "sgemm: act must be 0 (none), 1 (relu) or 2 (tanh)");
   dim3 grid(cdiv(N, TN), cdiv(M, TM));
-  sgemm_kernel<<<grid, 256, 0, stream>>>(A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta,
-                                         act);
-  VLNCE_LAUNCH_CHECK("sgemm_kernel");
+  // Skinny problems (M = 64 policy rows) leave most of the 148 SMs idle: split K across
+  // blockIdx.z until the grid covers ~2 waves, partial sums reduced in a second launch.
+  const int tiles = grid.x * grid.y;
+  int splits = 1;
+  if (workspace != nullptr && tiles < 96 && K >= 128) {
+    splits = min(min(296 / tiles, K / 64), 32);
+    while (splits > 1 && (size_t)splits * M * N * sizeof(float) > workspace_bytes) --splits;
+  }
+  if (splits <= 1) {
+    sgemm_kernel<<<grid, 256, 0, stream>>>(A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta, act,
+                                           nullptr, K);
+    VLNCE_LAUNCH_CHECK("sgemm_kernel");
+    return VLNCE_OK;
+  }
+  int k_per = cdiv(cdiv(K, splits), TK) * TK;
+  splits = cdiv(K, k_per);
+  grid.z = splits;
+  sgemm_kernel<<<grid, 256, 0, stream>>>(A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta, act,
+                                         workspace, k_per);
+  VLNCE_LAUNCH_CHECK("sgemm_kernel(split-K)");
+  const long long total = (long long)M * N;
+  const int rgrid = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+  splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(workspace, splits, C, ldc, bias, M, N, beta, act);
+  VLNCE_LAUNCH_CHECK("splitk_reduce_kernel");
   return VLNCE_OK;
 }
 

@@ -7,6 +7,68 @@
 namespace vlnce {
 namespace {
 
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = to_float<T>(p[e]);
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+    f[2 * e] = h.x; f[2 * e + 1] = h.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __uint_as_float(w[e] << 16);
+    f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&f)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) p[e] = from_float<T>(f[e]);
+}
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__half>(__half* p, const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __half2 h = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+    w[e] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    w[e] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+
 // ------------------------------------------------------------------------------------
 // Reference conv: one thread per output element, fp32 accumulation in K order (r, s, c).
 // ------------------------------------------------------------------------------------
@@ -47,8 +109,8 @@ __global__ void conv_ref_kernel(const TX* __restrict__ x, const TW* __restrict__
 // Stem operand builders (explicit im2col of the two 7x7/2 stems only; every other conv is
 // implicit).  One thread writes one 16-byte chunk (8 bf16) of an operand row.
 // ------------------------------------------------------------------------------------
-template <typename TX>
-__global__ void im2col_rgb_stem_kernel(const TX* __restrict__ x, __nv_bfloat16* __restrict__ a,
+template <typename TX, typename TA>
+__global__ void im2col_rgb_stem_kernel(const TX* __restrict__ x, TA* __restrict__ a,
                                        int N, int H, int W, int P, int Q) {
   constexpr int KP = 192, CHUNKS = KP / 8;
   const long long total = (long long)N * P * Q * CHUNKS;
@@ -59,7 +121,7 @@ __global__ void im2col_rgb_stem_kernel(const TX* __restrict__ x, __nv_bfloat16* 
     const int q = (int)(m % Q);
     const int p = (int)((m / Q) % P);
     const int n = (int)(m / ((long long)P * Q));
-    __align__(16) __nv_bfloat16 v[8];
+    __align__(16) TA v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int kk = ch * 8 + e;
@@ -71,7 +133,7 @@ __global__ void im2col_rgb_stem_kernel(const TX* __restrict__ x, __nv_bfloat16* 
         if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W)
           f = to_float<TX>(__ldg(x + ((size_t)(n * H + ih) * W + iw) * 3 + c));
       }
-      v[e] = __float2bfloat16_rn(f);
+      v[e] = from_float<TA>(f);
     }
     *reinterpret_cast<uint4*>(a + m * KP + ch * 8) = *reinterpret_cast<const uint4*>(v);
   }
@@ -129,15 +191,19 @@ __global__ void avgpool2x2_kernel(const float* __restrict__ x, float* __restrict
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W,
                                     int C, int P, int Q) {
-  const long long total = (long long)N * P * Q * C;
+  // 8 channels per thread (C % 8 == 0): one 16-byte load per window tap
+  const int CV = C / 8;
+  const long long total = (long long)N * P * Q * CV;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    const long long m = idx / C;
+    const int cv = (int)(idx % CV);
+    const long long m = idx / CV;
     const int q = (int)(m % Q);
     const int p = (int)((m / Q) % P);
     const int n = (int)(m / ((long long)P * Q));
-    float best = -INFINITY;
+    float best[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int ih = p * 2 + r - 1;
@@ -146,10 +212,13 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, 
       for (int s = 0; s < 3; ++s) {
         const int iw = q * 2 + s - 1;
         if ((unsigned)iw >= (unsigned)W) continue;
-        best = fmaxf(best, to_float<T>(x[((size_t)(n * H + ih) * W + iw) * C + c]));
+        float v[8];
+        load8<T>(x + ((size_t)(n * H + ih) * W + iw) * C + cv * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) best[e] = fmaxf(best[e], v[e]);
       }
     }
-    y[idx] = from_float<T>(best);
+    store8<T>(y + m * C + cv * 8, best);
   }
 }
 
@@ -196,6 +265,65 @@ __global__ void groupnorm_stats_kernel(const T* __restrict__ x, const float* __r
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   for (int ch = threadIdx.x; ch < cpg; ch += blockDim.x) {
     const int c = g * cpg + ch;
+    const float sc = rstd * gamma[c];
+    scale[(size_t)n * C + c] = sc;
+    shift[(size_t)n * C + c] = beta[c] - (float)mean * sc;
+  }
+}
+
+// Coalesced two-stage GroupNorm statistics for fp32 raw conv output (C % 4 == 0, C/4 <= 256,
+// 256 % (C/4) == 0): stage 1 = grid (N, S) CTAs stream float4 rows and bin (sum, sumsq) per
+// group in shared memory; stage 2 combines the S slices in fp64 and writes scale/shift.
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const float* __restrict__ x, float* __restrict__ part /*[N][S][G][2]*/, int HW, int C,
+                  int groups) {
+  __shared__ float bins[2 * 64];
+  const int n = blockIdx.x, s = blockIdx.y, S = gridDim.y;
+  const int c4n = C / 4;
+  const int lane_c = threadIdx.x % c4n, lane_r = threadIdx.x / c4n, rstep = 256 / c4n;
+  const int cpg = C / groups;
+  for (int i = threadIdx.x; i < 2 * groups; i += 256) bins[i] = 0.f;
+  __syncthreads();
+  const int rows_per = (HW + S - 1) / S;
+  const int r0 = s * rows_per, r1 = min(HW, r0 + rows_per);
+  float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;
+  const float* base = x + (size_t)n * HW * C + lane_c * 4;
+  for (int r = r0 + lane_r; r < r1; r += rstep) {
+    const float4 v = *reinterpret_cast<const float4*>(base + (size_t)r * C);
+    s01 += v.x + v.y; q01 = fmaf(v.x, v.x, fmaf(v.y, v.y, q01));
+    s23 += v.z + v.w; q23 = fmaf(v.z, v.z, fmaf(v.w, v.w, q23));
+  }
+  const int g01 = (lane_c * 4) / cpg, g23 = (lane_c * 4 + 2) / cpg;
+  if (g01 == g23) {
+    atomicAdd(&bins[2 * g01], s01 + s23);
+    atomicAdd(&bins[2 * g01 + 1], q01 + q23);
+  } else {
+    atomicAdd(&bins[2 * g01], s01); atomicAdd(&bins[2 * g01 + 1], q01);
+    atomicAdd(&bins[2 * g23], s23); atomicAdd(&bins[2 * g23 + 1], q23);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += 256)
+    part[((size_t)(n * S + s) * groups) * 2 + i] = bins[i];
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ part, int S, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale,
+                                   float* __restrict__ shift, int HW, int C, int groups, float eps) {
+  const int n = blockIdx.x;
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    double sum = 0.0, sq = 0.0;
+    for (int s = 0; s < S; ++s) {
+      const float* p = part + ((size_t)(n * S + s) * groups + g) * 2;
+      sum += p[0];
+      sq += p[1];
+    }
+    const double cnt = (double)HW * cpg;
+    const double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float sc = rstd * gamma[c];
     scale[(size_t)n * C + c] = sc;
     shift[(size_t)n * C + c] = beta[c] - (float)mean * sc;
@@ -258,28 +386,30 @@ __global__ void affine_apply_kernel(const T* __restrict__ x, const float* __rest
                                     const float* __restrict__ shift, int scale_stride_n,
                                     const TO* __restrict__ residual, TO* __restrict__ y, int HW, int C,
                                     long long total_vec, int relu) {
-  constexpr int V = 8;
+  constexpr int V = 8;  // 8 channels per thread: 16/32-byte vector accesses
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_vec;
        idx += (long long)gridDim.x * blockDim.x) {
     const long long e0 = idx * V;
     const int c0 = (int)(e0 % C);
     const long long row = e0 / C;
     const int n = (int)(row / HW);
-    const float* sc = scale + (size_t)n * scale_stride_n + c0;
-    const float* sh = shift + (size_t)n * scale_stride_n + c0;
-    float f[V];
+    float f[V], sc[V], sh[V];
+    load8<T>(x + e0, f);
+    load8<float>(scale + (size_t)n * scale_stride_n + c0, sc);
+    load8<float>(shift + (size_t)n * scale_stride_n + c0, sh);
 #pragma unroll
-    for (int e = 0; e < V; ++e) f[e] = fmaf(to_float<T>(x[e0 + e]), sc[e], sh[e]);
+    for (int e = 0; e < V; ++e) f[e] = fmaf(f[e], sc[e], sh[e]);
     if (residual != nullptr) {
+      float r[V];
+      load8<TO>(residual + e0, r);
 #pragma unroll
-      for (int e = 0; e < V; ++e) f[e] += to_float<TO>(residual[e0 + e]);
+      for (int e = 0; e < V; ++e) f[e] += r[e];
     }
     if (relu) {
 #pragma unroll
       for (int e = 0; e < V; ++e) f[e] = fmaxf(f[e], 0.f);
     }
-#pragma unroll
-    for (int e = 0; e < V; ++e) y[e0 + e] = from_float<TO>(f[e]);
+    store8<TO>(y + e0, f);
   }
 }
 
@@ -393,21 +523,21 @@ extern "C" int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w
   return VLNCE_ERR_INVALID_ARGUMENT;
 }
 
-extern "C" int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int N, int H, int W,
+extern "C" int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int a_dtype, int N, int H, int W,
                                      cudaStream_t stream) {
   VLNCE_CHECK_ARG(x && a && N > 0 && H > 0 && W > 0, "im2col_rgb_stem: bad arguments");
+  VLNCE_CHECK_ARG(a_dtype == VLNCE_BF16 || a_dtype == VLNCE_F16, "im2col_rgb_stem: operand dtype must be bf16 or f16");
+  VLNCE_CHECK_ARG(x_dtype == VLNCE_U8 || x_dtype == VLNCE_F32, "im2col_rgb_stem: rgb must be u8 or f32");
   const int P = (H + 6 - 7) / 2 + 1, Q = (W + 6 - 7) / 2 + 1;
   const long long total = (long long)N * P * Q * 24;
-  if (x_dtype == VLNCE_U8)
-    im2col_rgb_stem_kernel<uint8_t><<<grid_for(total, 256), 256, 0, stream>>>(
-        (const uint8_t*)x, (__nv_bfloat16*)a, N, H, W, P, Q);
-  else if (x_dtype == VLNCE_F32)
-    im2col_rgb_stem_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(
-        (const float*)x, (__nv_bfloat16*)a, N, H, W, P, Q);
-  else {
-    set_error("im2col_rgb_stem: rgb must be u8 or f32");
-    return VLNCE_ERR_INVALID_ARGUMENT;
+  const unsigned grid = grid_for(total, 256);
+#define GO(TX, TA) im2col_rgb_stem_kernel<TX, TA><<<grid, 256, 0, stream>>>((const TX*)x, (TA*)a, N, H, W, P, Q)
+  if (x_dtype == VLNCE_U8) {
+    if (a_dtype == VLNCE_BF16) GO(uint8_t, __nv_bfloat16); else GO(uint8_t, __half);
+  } else {
+    if (a_dtype == VLNCE_BF16) GO(float, __nv_bfloat16); else GO(float, __half);
   }
+#undef GO
   VLNCE_LAUNCH_CHECK("im2col_rgb_stem_kernel");
   return VLNCE_OK;
 }
@@ -443,9 +573,9 @@ extern "C" int vlnce_avgpool2x2(const float* x, float* y, int N, int H, int W, i
 
 extern "C" int vlnce_maxpool3x3s2(const void* x, void* y, int dtype, int N, int H, int W, int C,
                                   cudaStream_t stream) {
-  VLNCE_CHECK_ARG(x && y, "maxpool3x3s2: null tensor");
+  VLNCE_CHECK_ARG(x && y && C % 8 == 0, "maxpool3x3s2: null tensor or C %% 8 != 0");
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
-  const long long total = (long long)N * P * Q * C;
+  const long long total = (long long)N * P * Q * (C / 8);
   if (dtype == VLNCE_BF16)
     maxpool3x3s2_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, stream>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, P, Q);
@@ -464,10 +594,24 @@ extern "C" int vlnce_maxpool3x3s2(const void* x, void* y, int dtype, int N, int 
 }
 
 extern "C" int vlnce_groupnorm_stats(const void* x, int dtype, const float* gamma, const float* beta,
-                                     float* scale, float* shift, int N, int HW, int C, int groups,
-                                     float eps, cudaStream_t stream) {
+                                     float* scale, float* shift, float* workspace, size_t workspace_bytes,
+                                     int N, int HW, int C, int groups, float eps, cudaStream_t stream) {
   VLNCE_CHECK_ARG(x && gamma && beta && scale && shift && groups > 0 && C % groups == 0,
                   "groupnorm_stats: bad arguments");
+  const int c4n = C / 4;
+  if (dtype == VLNCE_F32 && workspace != nullptr && C % 4 == 0 && c4n <= 256 && 256 % c4n == 0 &&
+      (C / groups) % 2 == 0 && groups <= 64) {
+    int S = cdiv((long long)HW * C, 32768);  // ~128 KB of raw data per CTA
+    if (S > HW) S = HW;
+    while (S > 1 && (size_t)N * S * groups * 2 * sizeof(float) > workspace_bytes) --S;
+    if ((size_t)N * S * groups * 2 * sizeof(float) <= workspace_bytes) {
+      gn_partial_kernel<<<dim3(N, S), 256, 0, stream>>>((const float*)x, workspace, HW, C, groups);
+      VLNCE_LAUNCH_CHECK("gn_partial_kernel");
+      gn_finalize_kernel<<<N, 256, 0, stream>>>(workspace, S, gamma, beta, scale, shift, HW, C, groups, eps);
+      VLNCE_LAUNCH_CHECK("gn_finalize_kernel");
+      return VLNCE_OK;
+    }
+  }
   if (dtype == VLNCE_BF16)
     groupnorm_stats_kernel<__nv_bfloat16><<<N * groups, 256, 0, stream>>>(
         (const __nv_bfloat16*)x, gamma, beta, scale, shift, HW, C, groups, eps);

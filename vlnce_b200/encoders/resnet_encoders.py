@@ -187,9 +187,10 @@ class _RGBSequential(nn.Sequential):
     def trunk(self, precision) -> RGBTrunk:
         dev = self[0].weight.device
         cache = self.__dict__.setdefault("_trunks", {})
-        key = (precision, dev)
+        half = torch.float16 if self[1].training else torch.bfloat16
+        key = (precision, dev, half)
         if key not in cache:
-            cache[key] = RGBTrunk(self, dev, precision)
+            cache[key] = RGBTrunk(self, dev, precision, half)
         return cache[key]
 
     def forward(self, x):

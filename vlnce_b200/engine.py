@@ -24,9 +24,23 @@ from .lib import C, ptr
 from .trunk import BufferPool
 
 
+_WS = {}
+
+
+def gemm_workspace(nbytes: int = 32 << 20):
+    """Caller-owned split-K scratch (one per device), handed to every vlnce_sgemm call."""
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    ws = _WS.get(dev)
+    if ws is None:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda" if dev >= 0 else "cpu")
+        _WS[dev] = ws
+    return ws
+
+
 def _gemm(a, lda_m, lda_k, b, ldb_k, ldb_n, c, ldc, bias, m, n, k, beta=0.0, act=0):
+    ws = gemm_workspace()
     C.vlnce_sgemm(a, lda_m, lda_k, b, ldb_k, ldb_n, c, ldc, bias, m, n, k, float(beta), int(act),
-                  lib.stream())
+                  ws.data_ptr(), ws.numel(), lib.stream())
 
 
 def linear(x, ldx, w, out, ldo, bias, rows, n_out, n_in, act=0, beta=0.0, ldw=None):

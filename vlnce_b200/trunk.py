@@ -46,6 +46,11 @@ class BufferPool:
         return sum(b.numel() for b in self._bufs.values())
 
 
+import os as _os
+
+AUTOTUNE = _os.environ.get("VLNCE_AUTOTUNE", "1") != "0"
+
+
 def _version(params) -> tuple:
     return tuple((p.data_ptr(), p._version) for p in params)
 
@@ -61,6 +66,7 @@ class _Conv:
         self.stride, self.pad = conv.stride[0], conv.padding[0]
         self.w = self.scale = self.shift = None
         self._ver = None
+        self.block_n = {}  # tuned tile width per problem shape (0 = library heuristic)
 
     def params(self):
         ps = [self.conv.weight]
@@ -124,17 +130,46 @@ class ConvTrunk:
         st = lib.stream()
         if self.precision == "bf16":
             if gemm_c is not None:
-                C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
-                                    ptr(y), lib.code(y), n * h * w, 1, 1, gemm_c, cv.K, 1, 1, 1, 0, int(relu), 0,
-                                    st)
+                geom = (n * h * w, 1, 1, gemm_c, cv.K, 1, 1, 1, 0)
             else:
+                geom = (n, h, w, c, cv.K, cv.R, cv.S, cv.stride, cv.pad)
+
+            def launch(bn):
                 C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
-                                    ptr(y), lib.code(y), n, h, w, c, cv.K, cv.R, cv.S, cv.stride, cv.pad,
-                                    int(relu), 0, st)
+                                    ptr(y), lib.code(y), *geom, int(relu), bn, st)
+
+            key = (geom, lib.code(y), residual is not None)
+            bn = cv.block_n.get(key)
+            if bn is None:
+                tune = AUTOTUNE and x.is_cuda and not torch.cuda.is_current_stream_capturing()
+                bn = self._tune(launch, cv.K) if tune else 0
+                cv.block_n[key] = bn
+            launch(bn)
         else:
             C.vlnce_conv2d_ref(ptr(x), lib.code(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift),
                                ptr(residual), lib.F32, ptr(y), lib.F32, n, h, w, c, cv.K, cv.R, cv.S,
                                cv.stride, cv.pad, int(relu), st)
+
+    @staticmethod
+    def _tune(launch, K):
+        """Pick the output-tile width empirically (once per layer shape): CUDA-event timing of
+        the legal candidates on the real operands; the winner is cached on the layer."""
+        cands = [bn for bn in (32, 64, 128, 256) if K % bn == 0 and bn >= min(K, 32)]
+        if len(cands) <= 1:
+            return 0
+        best, best_t = 0, float("inf")
+        for bn in cands:
+            launch(bn)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                launch(bn)
+            b.record()
+            b.synchronize()
+            t = a.elapsed_time(b)
+            if t < best_t:
+                best, best_t = bn, t
+        return best
 
     @staticmethod
     def _out_hw(h, w, cv: _Conv):
@@ -146,18 +181,22 @@ class RGBTrunk(ConvTrunk):
     """torchvision ResNet trunk; ``cnn`` = the nn.Sequential holding conv1,bn1,relu,maxpool,
     layer1..4 (state_dict keys ``net.rgb_encoder.cnn.{0..7}.*``)."""
 
-    def __init__(self, cnn: nn.Sequential, device, precision="bf16"):
+    def __init__(self, cnn: nn.Sequential, device, precision="bf16", half_dtype=torch.bfloat16):
+        # eval-mode (folded) BatchNorm leaves the residual stream unbounded -> bf16 range;
+        # train-mode BatchNorm (SURVEY Q1) renormalises every layer to O(1) -> fp16 precision.
+        self.half_dtype = half_dtype
         super().__init__(device, precision)
         mods = list(cnn.children())
-        self.stem = _Conv(mods[0], mods[1], precision, in_scale=1.0 / 255.0, stem="rgb")
+        _C = lambda c, g, p, **kw: _Conv(c, g, p, wdt=half_dtype, **kw)  # noqa: E731
+        self.stem = _C(mods[0], mods[1], precision, in_scale=1.0 / 255.0, stem="rgb")
         self.blocks = []
         for layer in mods[4:8]:
             for blk in layer.children():
-                d = {"c1": _Conv(blk.conv1, blk.bn1, precision), "c2": _Conv(blk.conv2, blk.bn2, precision)}
+                d = {"c1": _C(blk.conv1, blk.bn1, precision), "c2": _C(blk.conv2, blk.bn2, precision)}
                 if hasattr(blk, "conv3"):
-                    d["c3"] = _Conv(blk.conv3, blk.bn3, precision)
+                    d["c3"] = _C(blk.conv3, blk.bn3, precision)
                 if blk.downsample is not None:
-                    d["ds"] = _Conv(blk.downsample[0], blk.downsample[1], precision)
+                    d["ds"] = _C(blk.downsample[0], blk.downsample[1], precision)
                 self.blocks.append(d)
         self.out_channels = self.blocks[-1]["c3" if "c3" in self.blocks[-1] else "c2"].K
         self._bn_ws = None
@@ -205,8 +244,8 @@ class RGBTrunk(ConvTrunk):
         cv = self.stem
         p, q = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
         if self.precision == "bf16":
-            a = self.pool.get("stem_a", (n * p * q, 192), torch.bfloat16)
-            C.vlnce_im2col_rgb_stem(ptr(rgb), lib.code(rgb), ptr(a), n, h, w, st)
+            a = self.pool.get("stem_a", (n * p * q, 192), self.adt)
+            C.vlnce_im2col_rgb_stem(ptr(rgb), lib.code(rgb), ptr(a), lib.code(a), n, h, w, st)
             x, shp = self._norm_conv(a, (n, p, q, 192), cv, "stem_y", gemm_c=192, out_hw=(p, q))
         else:
             x, shp = self._norm_conv(rgb, (n, h, w, 3), cv, "stem_y")
@@ -271,8 +310,9 @@ class DepthTrunk(ConvTrunk):
         st = lib.stream()
         sc = self.pool.get("gn_scale", (n, cv.K), torch.float32)
         sh = self.pool.get("gn_shift", (n, cv.K), torch.float32)
-        C.vlnce_groupnorm_stats(ptr(raw), lib.code(raw), ptr(gn.weight), ptr(gn.bias), ptr(sc), ptr(sh), n,
-                                p * q, cv.K, gn.num_groups, float(gn.eps), st)
+        ws = self.pool.get("gn_ws", (1 << 20,), torch.float32)
+        C.vlnce_groupnorm_stats(ptr(raw), lib.code(raw), ptr(gn.weight), ptr(gn.bias), ptr(sc), ptr(sh), ptr(ws),
+                                ws.numel() * 4, n, p * q, cv.K, gn.num_groups, float(gn.eps), st)
         y = self._act(tag, (n, p, q, cv.K))
         C.vlnce_affine_apply(ptr(raw), lib.code(raw), ptr(sc), ptr(sh), cv.K, ptr(residual), ptr(y),
                              lib.code(y), n, p * q, cv.K, int(relu), st)
