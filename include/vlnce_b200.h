@@ -122,7 +122,7 @@ int vlnce_sgemm(const float* A, long long lda_m, long long lda_k, const float* B
                 float beta, int act, float* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* out[n] (+)= sum_m A[m*lda + n]  — bias gradients */
 int vlnce_colsum(const float* A, long long lda, float* out, int M, int N, int accumulate,
-                 cudaStream_t stream);
+                 float* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- trainable head: forward -------------------------------------------------------- */
 /* nn.Embedding gather (instruction_encoder.py:70-73): out[r, :dim] = table[ids[r]] */

@@ -31,7 +31,13 @@ def test_sgemm_variants(m, n, k):
     linear_dw(ptr(dy), n, ptr(x), k, ptr(dw), k, m, n, k, beta=1.0)
     torch.testing.assert_close(dw, 1 + dy.t() @ x, rtol=1e-4, atol=2e-4)
     cs = torch.empty(n, device=DEV)
-    C.vlnce_colsum(ptr(dy), n, ptr(cs), m, n, 0, lib.stream())
+    from vlnce_b200.engine import gemm_workspace
+    ws = gemm_workspace()
+    C.vlnce_colsum(ptr(dy), n, ptr(cs), m, n, 0, ws.data_ptr(), ws.numel(), lib.stream())
+    big = _r(5120, 512, seed=4)
+    cs2 = torch.empty(512, device=DEV)
+    C.vlnce_colsum(ptr(big), 512, ptr(cs2), 5120, 512, 0, ws.data_ptr(), ws.numel(), lib.stream())
+    torch.testing.assert_close(cs2, big.sum(0), rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(cs, dy.sum(0), rtol=1e-4, atol=1e-4)
 
 

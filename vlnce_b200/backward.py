@@ -24,7 +24,10 @@ def trainable_named(net, head_linear=None) -> Dict[str, torch.nn.Parameter]:
 
 
 def _colsum(a, lda, out, m, n, acc=0):
-    C.vlnce_colsum(a, lda, out, m, n, acc, lib.stream())
+    from .engine import gemm_workspace
+
+    ws = gemm_workspace()
+    C.vlnce_colsum(a, lda, out, m, n, acc, ws.data_ptr(), ws.numel(), lib.stream())
 
 
 def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, masks_f, T, N, dx, lddx):

@@ -101,22 +101,37 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
   }
 }
 
-// out[n] = (accumulate ? out[n] : 0) + sum_m A[m*lda + n]   (bias gradients)
+// out[n] = (accumulate ? out[n] : 0) + sum_m A[m*lda + n]   (bias gradients).  grid (N/32, S):
+// each CTA sums a row slice of 32 columns (8 row lanes x coalesced 128B reads); S > 1 writes
+// partial[S][N] for the fixed-order second stage below.
 __global__ void colsum_kernel(const float* __restrict__ A, long long lda, float* __restrict__ out,
-                              int M, int N, int accumulate) {
+                              int M, int N, int accumulate, float* __restrict__ partial) {
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int slice = threadIdx.x >> 5, nslices = blockDim.x >> 5;
+  const int S = gridDim.y;
+  const int rows_per = (M + S - 1) / S;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
   __shared__ float part[8][33];
   float s = 0.f;
   if (n < N)
-    for (int m = slice; m < M; m += nslices) s += A[m * lda + n];
+    for (int m = r0 + slice; m < r1; m += nslices) s += A[m * lda + n];
   part[slice][threadIdx.x & 31] = s;
   __syncthreads();
   if (slice == 0 && n < N) {
     float t = 0.f;
     for (int i = 0; i < nslices; ++i) t += part[i][threadIdx.x & 31];
-    out[n] = accumulate ? out[n] + t : t;
+    if (partial != nullptr) partial[(size_t)blockIdx.y * N + n] = t;
+    else out[n] = accumulate ? out[n] + t : t;
   }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int S, float* __restrict__ out, int N,
+                                    int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int s = 0; s < S; ++s) t += partial[(size_t)s * N + n];
+  out[n] = accumulate ? out[n] + t : t;
 }
 
 }  // namespace
@@ -160,9 +175,19 @@ extern "C" int vlnce_sgemm(const float* A, long long lda_m, long long lda_k, con
 }
 
 extern "C" int vlnce_colsum(const float* A, long long lda, float* out, int M, int N, int accumulate,
-                            cudaStream_t stream) {
+                            float* workspace, size_t workspace_bytes, cudaStream_t stream) {
   VLNCE_CHECK_ARG(A && out && M > 0 && N > 0, "colsum: bad arguments");
-  colsum_kernel<<<cdiv(N, 32), 256, 0, stream>>>(A, lda, out, M, N, accumulate);
+  int S = 1;
+  if (workspace != nullptr && M >= 256) {
+    S = min(64, M / 128);
+    while (S > 1 && (size_t)S * N * sizeof(float) > workspace_bytes) --S;
+  }
+  dim3 grid(cdiv(N, 32), S);
+  colsum_kernel<<<grid, 256, 0, stream>>>(A, lda, out, M, N, accumulate, S > 1 ? workspace : nullptr);
   VLNCE_LAUNCH_CHECK("colsum_kernel");
+  if (S > 1) {
+    colsum_final_kernel<<<cdiv(N, 128), 128, 0, stream>>>(workspace, S, out, N, accumulate);
+    VLNCE_LAUNCH_CHECK("colsum_final_kernel");
+  }
   return VLNCE_OK;
 }
