@@ -52,7 +52,8 @@ long long vlnce_launch_count(void);
  * ab_dtype = VLNCE_BF16 or VLNCE_F16 is the type of x, w and residual (fp16 for the
  * GroupNorm depth trunk whose activations are O(1): 8x finer than bf16 at the same cost).
  * x (N,H,W,C), w (K,R,S,C), y (N,P,Q,K) ab_dtype|f32, residual (N,P,Q,K) ab_dtype or NULL,
- * scale/shift (K) f32 or both NULL (raw conv).  C % 32 == 0, K % 32 == 0.  block_n: 0 = auto.
+ * scale/shift (K) f32 or both NULL (raw conv).  C % 32 == 0, K % 32 == 0.  block_n: 0 = auto,
+ * else the output-tile width (32/64/128/256) | optional smem ring depth (1..4) << 16.
  * Replaces torch.nn.Conv2d + folded BatchNorm2d/ReLU/residual in torchvision ResNet
  * (resnet_encoders.py:198-199) and the convs of the DD-PPO GroupNorm ResNet
  * (resnet_encoders.py:95; habitat_baselines v0.1.7 rl/ddppo/policy/resnet.py). */

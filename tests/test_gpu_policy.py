@@ -82,6 +82,18 @@ def test_cma_act_matches_golden(name, precision, tol):
     assert h_out.shape == gold["rnn_states_out"].shape and action.dtype == torch.int64
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
+def test_seq2seq_act_matches_golden(precision, tol):
+    """BASELINE config C1: Seq2SeqPolicy, batch 2, 256x256 RGB-D, 80-token instruction."""
+    name = "seq2seq_act"
+    gold = torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+    got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, device=DEV, precision=precision)
+    e_p, e_h = rel(got["logits"].exp(), gold["logits"].exp()), rel(got["rnn_states_out"], gold["rnn_states_out"])
+    print(f"{name}[{precision}] rel err probs {e_p:.3e} hidden {e_h:.3e}")
+    assert e_p < tol and e_h < tol
+    assert torch.equal(got["action"], gold["action"])
+
+
 def test_no_cpu_fallback():
     case = cases.CASES["cma_act"]
     pol = cases.build_policy(vlnce_b200, case)  # parameters left on the CPU

@@ -62,3 +62,19 @@ def test_fused_step_launch_sequence():
     assert out.shape == (3,)
     assert rec.calls[-1] == "vlnce_adam_step" and "vlnce_il_loss" in rec.calls
     assert step.fp.aliased()
+
+
+def test_seq2seq_act_launch_sequence_and_keys():
+    """BASELINE config C1 (Seq2Seq, batch 2): same state_dict keys as the reference; launch walk."""
+    from oracle import vlnce as oracle_vlnce
+
+    case = cases.CASES["seq2seq_act"]
+    pol = cases.build_policy(vlnce_b200, case)
+    ref = cases.build_policy(oracle_vlnce, case)
+    assert list(pol.state_dict()) == list(ref.state_dict())
+    pol.eval()
+    obs, h, prev, masks = cases.inputs(case)
+    with lib.dry_run() as rec:
+        action, h_out = pol.act(obs, h, prev, masks, deterministic=True)
+    assert action.shape == (2, 1) and h_out.shape == (2, 1, 512)
+    assert sum(c.startswith("vlnce_conv2d") for c in rec.calls) == 107

@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
+#include <stdlib.h>
+
 namespace vlnce {
 namespace {
 
@@ -425,7 +427,7 @@ int make_map_2d(EncodeTiledFn encode, CUtensorMap* map, const void* base, CUtens
 
 template <int BLOCK_N, int BLOCK_K>
 int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
-           ConvParams& p, cudaStream_t stream) {
+           ConvParams& p, int stages_cap, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, BLOCK_K>;
   static bool configured = false;
   if (!configured) {
@@ -434,8 +436,22 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, 
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(conv_umma)");
     configured = true;
   }
+  // Ring depth: deep enough to cover the K loop, but small enough that TWO CTAs fit on an SM
+  // (one CTA's epilogue then overlaps the other's main loop); VLNCE_CONV_SMEM_KB overrides the
+  // per-CTA budget for experiments.
+  static int budget = -1;
+  if (budget < 0) {
+    const char* e = getenv("VLNCE_CONV_SMEM_KB");
+    budget = e ? atoi(e) * 1024 : 113 * 1024;
+    if (budget > kSmemBudget) budget = kSmemBudget;
+  }
   int stages = p.num_k_iters < kMaxStages ? p.num_k_iters : kMaxStages;
-  while (stages > 1 && C::smem_bytes(stages, p.out_tma, p.y_fp32) > kSmemBudget) --stages;
+  if (stages_cap > 0) {  // tuned by the caller: ring depth given, only the hardware limit applies
+    if (stages > stages_cap) stages = stages_cap;
+    while (stages > 1 && C::smem_bytes(stages, p.out_tma, p.y_fp32) > kSmemBudget) --stages;
+  } else {
+    while (stages > 1 && C::smem_bytes(stages, p.out_tma, p.y_fp32) > budget) --stages;
+  }
   if (C::smem_bytes(stages, p.out_tma, p.y_fp32) > kSmemBudget) {  // staged tile too large: store directly
     p.out_tma = 0;
     stages = p.num_k_iters < kMaxStages ? p.num_k_iters : kMaxStages;
@@ -478,6 +494,8 @@ extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, int ab_dtype, con
                   "conv2d_bf16: tensor too large for 32-bit offsets");
   const int block_k = (C % 64 == 0) ? 64 : 32;
   const int m_tiles = cdiv((long long)N * P * Q, BLOCK_M);
+  const int stages_cap = (block_n >> 16) & 0xf;  // optional tuned ring depth in bits [16,20)
+  block_n &= 0xffff;
   int bn = block_n;
   if (bn == 0) {
     // widest tile that still gives every SM (148) a CTA; otherwise the narrowest legal one >= 64
@@ -537,7 +555,7 @@ extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, int ab_dtype, con
   }
 
 #define VLNCE_CONV_CASE(BN, BK) \
-  if (bn == BN && block_k == BK) return launch<BN, BK>(tw, tx, ty, tr, p, stream);
+  if (bn == BN && block_k == BK) return launch<BN, BK>(tw, tx, ty, tr, p, stages_cap, stream);
   VLNCE_CONV_CASE(256, 64)
   VLNCE_CONV_CASE(128, 64)
   VLNCE_CONV_CASE(64, 64)

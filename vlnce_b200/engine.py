@@ -68,28 +68,15 @@ def off(t: torch.Tensor, elems: int) -> int:
     return t.data_ptr() + F4 * elems
 
 
-class CMAEngine:
-    """Forward/backward launch plan bound to one ``CMANet`` (+ action head)."""
+class HeadEngine:
+    """Shared pieces of the policy launch plans: workspace, GRU state encoder, action head."""
 
     def __init__(self, net, precision: str = "bf16"):
         self.net = net
         self.precision = precision
         self.pool: Optional[BufferPool] = None
         self.ctx: Dict[str, object] = {}
-        cfg = net.model_config
-        self.H = cfg.STATE_ENCODER.hidden_size
-        self.rgb_out = cfg.RGB_ENCODER.output_size
-        self.depth_out = cfg.DEPTH_ENCODER.output_size
-        ie = net.instruction_encoder
-        self.Hs = ie.config.hidden_size
-        self.dirs = 2 if ie.config.bidirectional else 1
-        self.E = ie.config.embedding_size
-        self.Dt = self.Hs * self.dirs  # instruction feature size
-        self.Crgb = net.rgb_encoder.output_shape[0]      # 2112
-        self.Cdep = net.depth_encoder.output_shape[0]    # 192
-        self.P = 16
-        self.state_in = self.rgb_out + self.depth_out + 32
-        self.cat = self.H + self.Dt + self.rgb_out + self.depth_out + 32
+        self.H = net.model_config.STATE_ENCODER.hidden_size
 
     def buf(self, name, shape, dtype=torch.float32):
         return self.pool.get(name, shape, dtype)
@@ -98,6 +85,61 @@ class CMAEngine:
         if self.pool is None or self.pool.device != dev:
             self.pool = BufferPool(dev)
         return self.pool
+
+    def _prep_rows(self, rnn_states, prev_actions, masks):
+        dev = rnn_states.device
+        lib.require_cuda(rnn_states, "rnn_states")
+        self.ensure_pool(dev)
+        N = rnn_states.shape[0]
+        R = prev_actions.shape[0]
+        assert R % N == 0, "rows must be T*N (time-major)"
+        rnn_states = rnn_states.contiguous().float()
+        masks_f = self.buf("masks_f", (R,))
+        masks_f.copy_(masks.reshape(-1))  # dtype cast only (uint8/bool/float -> f32)
+        prev = prev_actions.reshape(-1)
+        if prev.dtype != torch.int64:
+            prev = prev.long()
+        return rnn_states, masks_f, prev.contiguous(), R, N, R // N
+
+    def _encode_instruction(self, observations, R, save):
+        """instruction_encoder.py:63-94: lengths, embedding, input projection, persistent LSTM.
+        Returns (per-token outputs (R,L,dirs*Hs), final states (dirs,R,Hs), lengths, L)."""
+        ie = self.net.instruction_encoder
+        st = lib.stream()
+        Hs, dirs, E = ie.config.hidden_size, (2 if ie.config.bidirectional else 1), ie.config.embedding_size
+        lengths = self.buf("lengths", (R,), torch.int32)
+        if ie.config.sensor_uuid == "instruction":
+            ids = observations["instruction"]
+            lib.require_cuda(ids, "instruction")
+            ids = ids.long().contiguous()
+            L = ids.shape[1]
+            C.vlnce_token_lengths(ptr(ids), ptr(lengths), R, L, st)
+            emb = self.buf("instr_emb", (R * L, E))
+            C.vlnce_embedding_fwd(ptr(ids), ptr(ie.embedding_layer.weight), ptr(emb), R * L, E, E,
+                                  ie.embedding_layer.num_embeddings, st)
+            self.ctx["ids"] = ids
+        else:
+            emb = observations["rxr_instruction"]
+            lib.require_cuda(emb, "rxr_instruction")
+            emb = emb.contiguous().float()
+            L = emb.shape[1]
+            C.vlnce_feature_lengths(ptr(emb), ptr(lengths), R, L, E, st)
+            self.ctx["rxr"] = emb
+        rnn = ie.encoder_rnn
+        gx = self.buf("lstm_gx", (dirs, R, L, 4 * Hs))
+        wih = [rnn.weight_ih_l0] + ([rnn.weight_ih_l0_reverse] if dirs == 2 else [])
+        bih = [rnn.bias_ih_l0] + ([rnn.bias_ih_l0_reverse] if dirs == 2 else [])
+        for d in range(dirs):
+            linear(ptr(emb), E, ptr(wih[d]), off(gx, d * R * L * 4 * Hs), 4 * Hs, ptr(bih[d]), R * L, 4 * Hs, E)
+        instr = self.buf("instr_out", (R, L, dirs * Hs))
+        hn = self.buf("lstm_hn", (dirs, R, Hs))
+        sg = self.buf("lstm_gates", (dirs, R, L, 4 * Hs)) if save else None
+        sc = self.buf("lstm_c", (dirs, R, L, Hs)) if save else None
+        C.vlnce_lstm_seq_fwd(ptr(gx), ptr(rnn.weight_hh_l0),
+                             ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None, ptr(rnn.bias_hh_l0),
+                             ptr(rnn.bias_hh_l0_reverse) if dirs == 2 else None, ptr(lengths), ptr(instr),
+                             ptr(hn), ptr(sg), ptr(sc), R, L, Hs, dirs, st)
+        return instr, hn, lengths, L
 
     # ------------------------------------------------------------------ GRU helper
     def _gru_forward(self, tag, rnn, x, ldx, in_size, h0, ldh0, masks_f, out, ldo, h_final, ldhf, T, N,
@@ -125,62 +167,45 @@ class CMAEngine:
                                       h_final if last else None, ldhf,
                                       off(sv, t * N * 4 * H) if save else None, N, H, st)
 
+    # ------------------------------------------------------------------ action head
+    def action_logits(self, head_linear, x_out, R):
+        """CategoricalNet (policy.py:19-21,37): Linear then the log-softmax Categorical applies."""
+        A = head_linear.weight.shape[0]
+        logits = self.buf("logits", (R, A))
+        linear(ptr(x_out), self.H, ptr(head_linear.weight), ptr(logits), A, ptr(head_linear.bias), R, A, self.H)
+        C.vlnce_log_softmax_rows(ptr(logits), R, A, lib.stream())
+        return logits
+
+
+class CMAEngine(HeadEngine):
+    """Forward/backward launch plan bound to one ``CMANet`` (+ action head)."""
+
+    def __init__(self, net, precision: str = "bf16"):
+        super().__init__(net, precision)
+        cfg = net.model_config
+        self.H = cfg.STATE_ENCODER.hidden_size
+        self.rgb_out = cfg.RGB_ENCODER.output_size
+        self.depth_out = cfg.DEPTH_ENCODER.output_size
+        ie = net.instruction_encoder
+        self.Hs = ie.config.hidden_size
+        self.dirs = 2 if ie.config.bidirectional else 1
+        self.E = ie.config.embedding_size
+        self.Dt = self.Hs * self.dirs  # instruction feature size
+        self.Crgb = net.rgb_encoder.output_shape[0]      # 2112
+        self.Cdep = net.depth_encoder.output_shape[0]    # 192
+        self.P = 16
+        self.state_in = self.rgb_out + self.depth_out + 32
+        self.cat = self.H + self.Dt + self.rgb_out + self.depth_out + 32
+
     # ------------------------------------------------------------------ forward
     def forward(self, observations, rnn_states, prev_actions, masks, save: bool):
         net = self.net
-        dev = rnn_states.device
-        lib.require_cuda(rnn_states, "rnn_states")
-        self.ensure_pool(dev)
+        rnn_states, masks_f, prev, R, N, T = self._prep_rows(rnn_states, prev_actions, masks)
         st = lib.stream()
         H, P = self.H, self.P
-        N = rnn_states.shape[0]
-        R = prev_actions.shape[0]
-        assert R % N == 0, "rows must be T*N (time-major)"
-        T = R // N
-        rnn_states = rnn_states.contiguous().float()
-        masks_f = self.buf("masks_f", (R,))
-        masks_f.copy_(masks.reshape(-1))  # dtype cast only (uint8/bool/float -> f32)
-        prev = prev_actions.reshape(-1)
-        if prev.dtype != torch.int64:
-            prev = prev.long()
-        prev = prev.contiguous()
 
         # ---- instruction encoder (instruction_encoder.py:63-94)
-        ie = net.instruction_encoder
-        lengths = self.buf("lengths", (R,), torch.int32)
-        if ie.config.sensor_uuid == "instruction":
-            ids = observations["instruction"]
-            lib.require_cuda(ids, "instruction")
-            ids = ids.long().contiguous()
-            L = ids.shape[1]
-            C.vlnce_token_lengths(ptr(ids), ptr(lengths), R, L, st)
-            emb = self.buf("instr_emb", (R * L, self.E))
-            C.vlnce_embedding_fwd(ptr(ids), ptr(ie.embedding_layer.weight), ptr(emb), R * L, self.E, self.E,
-                                  ie.embedding_layer.num_embeddings, st)
-            self.ctx["ids"] = ids
-        else:
-            emb = observations["rxr_instruction"]
-            lib.require_cuda(emb, "rxr_instruction")
-            emb = emb.contiguous().float()
-            L = emb.shape[1]
-            C.vlnce_feature_lengths(ptr(emb), ptr(lengths), R, L, self.E, st)
-            self.ctx["rxr"] = emb
-        Hs, dirs = self.Hs, self.dirs
-        rnn = ie.encoder_rnn
-        gx = self.buf("lstm_gx", (dirs, R, L, 4 * Hs))
-        wih = [rnn.weight_ih_l0] + ([rnn.weight_ih_l0_reverse] if dirs == 2 else [])
-        bih = [rnn.bias_ih_l0] + ([rnn.bias_ih_l0_reverse] if dirs == 2 else [])
-        for d in range(dirs):
-            linear(ptr(emb), self.E, ptr(wih[d]), off(gx, d * R * L * 4 * Hs), 4 * Hs, ptr(bih[d]), R * L,
-                   4 * Hs, self.E)
-        instr = self.buf("instr_out", (R, L, self.Dt))
-        hn = self.buf("lstm_hn", (dirs, R, Hs))
-        sg = self.buf("lstm_gates", (dirs, R, L, 4 * Hs)) if save else None
-        sc = self.buf("lstm_c", (dirs, R, L, Hs)) if save else None
-        C.vlnce_lstm_seq_fwd(ptr(gx), ptr(rnn.weight_hh_l0),
-                             ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None, ptr(rnn.bias_hh_l0),
-                             ptr(rnn.bias_hh_l0_reverse) if dirs == 2 else None, ptr(lengths), ptr(instr),
-                             ptr(hn), ptr(sg), ptr(sc), R, L, Hs, dirs, st)
+        instr, _, lengths, L = self._encode_instruction(observations, R, save)
 
         # ---- visual encoders + spatial embeddings (cma_policy.py:227-231)
         rgb_e = self.buf("rgb_emb", (R, P, self.Crgb))
@@ -265,11 +290,3 @@ class CMAEngine:
         self.ctx.update(R=R, N=N, T=T, L=L, lengths=lengths, saved=save)
         return x_out, h_out, hat
 
-    # ------------------------------------------------------------------ action head
-    def action_logits(self, head_linear, x_out, R):
-        """CategoricalNet (policy.py:19-21,37): Linear then the log-softmax Categorical applies."""
-        A = head_linear.weight.shape[0]
-        logits = self.buf("logits", (R, A))
-        linear(ptr(x_out), self.H, ptr(head_linear.weight), ptr(logits), A, ptr(head_linear.bias), R, A, self.H)
-        C.vlnce_log_softmax_rows(ptr(logits), R, A, lib.stream())
-        return logits

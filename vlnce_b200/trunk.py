@@ -154,9 +154,8 @@ class ConvTrunk:
     def _tune(launch, K):
         """Pick the output-tile width empirically (once per layer shape): CUDA-event timing of
         the legal candidates on the real operands; the winner is cached on the layer."""
-        cands = [bn for bn in (32, 64, 128, 256) if K % bn == 0 and bn >= min(K, 32)]
-        if len(cands) <= 1:
-            return 0
+        widths = [bn for bn in (64, 128, 256) if K % bn == 0] or [32]
+        cands = [bn | (st << 16) for bn in widths for st in (1, 2, 4)]
         best, best_t = 0, float("inf")
         for _ in range(12):  # bring the clocks up before timing anything
             launch(cands[-1])
