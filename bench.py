@@ -215,6 +215,9 @@ def main():
     def eager_step(d):
         return step.update_agent(*split(d), return_tensor=True)
 
+    def grads_only(d):
+        step.compute_grads(*split(d))
+
     def load_static(src, non_blocking=False):
         for k, v in static.items():
             v.copy_(src[k], non_blocking=non_blocking)
@@ -233,14 +236,17 @@ def main():
     losses = step._losses
     if not args.no_graph:
         try:
+            # N = 1: the whole step is one graph.  N > 1: forward+loss+backward is captured, the NCCL
+            # all-reduce and the Adam launch stay eager between replays (no collectives inside graphs).
+            body = eager_step if world == 1 else grads_only
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                eager_step(static)
+                body(static)
                 side.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=side):
-                    eager_step(static)
+                    body(static)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
         except Exception as e:  # graph capture is an optimisation, not a requirement
@@ -251,6 +257,8 @@ def main():
     def run_step():
         if graph is not None:
             graph.replay()
+            if world > 1:
+                step.apply_grads(True)
         else:
             eager_step(static)
 
@@ -385,8 +393,14 @@ def main():
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+    torch.cuda.synchronize()
+    # Hard exit: tearing down CUDA graphs / NCCL communicators at interpreter shutdown can block
+    # on each other; the measurement is complete and flushed, nothing is left to clean up.
+    os._exit(0)
 
 
 if __name__ == "__main__":

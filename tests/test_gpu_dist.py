@@ -74,4 +74,5 @@ def test_allreduced_gradient_equals_single_gpu_gradient():
     assert torch.equal(g0, g1) and torch.equal(p0, p1), "ranks diverged after the all-reduce"
     # equal-sized shards: mean of per-shard action losses == whole-batch loss (base_il_trainer.py:165)
     torch.testing.assert_close(g0, g_single, rtol=1e-4, atol=1e-7)
-    torch.testing.assert_close(p0, p_single, rtol=1e-5, atol=1e-6)
+    # first Adam step = lr*g/(|g|+eps): entries with |g| ~ eps amplify 1e-9-level gradient noise
+    torch.testing.assert_close(p0, p_single, rtol=1e-5, atol=5e-5)

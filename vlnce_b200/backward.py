@@ -11,7 +11,7 @@ from typing import Dict, Optional
 import torch
 
 from . import lib
-from .engine import F4, CMAEngine, linear, linear_dw, linear_dx, off
+from .engine import F4, OVERLAP, Branch, CMAEngine, linear, linear_dw, linear_dx, off
 from .lib import C, ptr
 
 
@@ -138,6 +138,35 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     linear_dw(ptr(d_q_s), hk, ptr(xcat), eng.cat, ptr(g["net.state_q.weight"]), H, R, hk, H)
     _colsum(ptr(d_q_s), hk, ptr(g["net.state_q.bias"]), R, hk)
     linear_dx(ptr(d_q_s), hk, ptr(net.state_q.weight), ptr(dxcat), eng.cat, R, hk, H, beta=1.0)
+    with Branch("lstm_bwd", OVERLAP) as br_lstm:
+        # 12. instruction encoder (BPTT) — independent of steps 8-11: own stream
+        ie = net.instruction_encoder
+        rnn = ie.encoder_rnn
+        Hs, dirs, E = eng.Hs, eng.dirs, eng.E
+        dgx = b("lstm_dgx", (dirs, R, L, 4 * Hs))
+        hprev = b("lstm_hprev", (dirs, R, L, Hs))
+        C.vlnce_lstm_seq_bwd(ptr(d_instr), ptr(b("lstm_gates", (dirs, R, L, 4 * Hs))), ptr(b("lstm_c", (dirs, R, L, Hs))),
+                             ptr(instr), ptr(rnn.weight_hh_l0), ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None,
+                             ptr(cx["lengths"]), ptr(dgx), ptr(hprev), R, L, Hs, dirs, lib.stream())
+        emb_in = b("instr_emb", (R * L, E)) if ie.config.sensor_uuid == "instruction" else cx["rxr"]
+        emb_trainable = ie.config.sensor_uuid == "instruction" and ie.embedding_layer.weight.requires_grad
+        d_emb = b("d_instr_emb", (R * L, E)) if emb_trainable else None
+        for d, sfx in enumerate(["", "_reverse"][:dirs]):
+            dg = off(dgx, d * R * L * 4 * Hs)
+            pfx = "net.instruction_encoder.encoder_rnn."
+            linear_dw(dg, 4 * Hs, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, 4 * Hs, E)
+            linear_dw(dg, 4 * Hs, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, 4 * Hs, Hs)
+            _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, 4 * Hs)
+            _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, 4 * Hs)
+            if emb_trainable:
+                w_ih = getattr(rnn, "weight_ih_l0" + sfx)
+                linear_dx(dg, 4 * Hs, ptr(w_ih), ptr(d_emb), E, R * L, 4 * Hs, E, beta=0.0 if d == 0 else 1.0)
+        if emb_trainable:
+            el = ie.embedding_layer
+            pad = -1 if el.padding_idx is None else el.padding_idx
+            C.vlnce_embedding_bwd(ptr(cx["ids"]), ptr(d_emb), E, ptr(g["net.instruction_encoder.embedding_layer.weight"]),
+                                  R * L, E, el.num_embeddings, pad, lib.stream())
+
     # 8. first GRU (dh = dxcat[:, :H])
     d_state_in = b("d_state_in", (R, eng.state_in))
     _gru_backward(eng, "gru1", net.state_encoder.rnn, "net.state_encoder.rnn.", g, ptr(dxcat), eng.cat,
@@ -173,33 +202,7 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
                                ptr(g["net.rgb_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
     C.vlnce_spatial_embed_grad(ptr(dE["depth"]), P * eng.Cdep, eng.Cdep, c_dep, ptr(d_flat_sp), 64 * P, None, 0,
                                ptr(g["net.depth_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
-    # 12. instruction encoder (BPTT)
-    ie = net.instruction_encoder
-    rnn = ie.encoder_rnn
-    Hs, dirs, E = eng.Hs, eng.dirs, eng.E
-    dgx = b("lstm_dgx", (dirs, R, L, 4 * Hs))
-    hprev = b("lstm_hprev", (dirs, R, L, Hs))
-    C.vlnce_lstm_seq_bwd(ptr(d_instr), ptr(b("lstm_gates", (dirs, R, L, 4 * Hs))), ptr(b("lstm_c", (dirs, R, L, Hs))),
-                         ptr(instr), ptr(rnn.weight_hh_l0), ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None,
-                         ptr(cx["lengths"]), ptr(dgx), ptr(hprev), R, L, Hs, dirs, st)
-    emb_in = b("instr_emb", (R * L, E)) if ie.config.sensor_uuid == "instruction" else cx["rxr"]
-    emb_trainable = ie.config.sensor_uuid == "instruction" and ie.embedding_layer.weight.requires_grad
-    d_emb = b("d_instr_emb", (R * L, E)) if emb_trainable else None
-    for d, sfx in enumerate(["", "_reverse"][:dirs]):
-        dg = off(dgx, d * R * L * 4 * Hs)
-        pfx = "net.instruction_encoder.encoder_rnn."
-        linear_dw(dg, 4 * Hs, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, 4 * Hs, E)
-        linear_dw(dg, 4 * Hs, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, 4 * Hs, Hs)
-        _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, 4 * Hs)
-        _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, 4 * Hs)
-        if emb_trainable:
-            w_ih = getattr(rnn, "weight_ih_l0" + sfx)
-            linear_dx(dg, 4 * Hs, ptr(w_ih), ptr(d_emb), E, R * L, 4 * Hs, E, beta=0.0 if d == 0 else 1.0)
-    if emb_trainable:
-        el = ie.embedding_layer
-        pad = -1 if el.padding_idx is None else el.padding_idx
-        C.vlnce_embedding_bwd(ptr(cx["ids"]), ptr(d_emb), E, ptr(g["net.instruction_encoder.embedding_layer.weight"]),
-                              R * L, E, el.num_embeddings, pad, st)
+    br_lstm.join()
 
 
 class CMAFunction(torch.autograd.Function):

@@ -27,14 +27,53 @@ from .trunk import BufferPool
 _WS = {}
 
 
-def gemm_workspace(nbytes: int = 32 << 20):
-    """Caller-owned split-K scratch (one per device), handed to every vlnce_sgemm call."""
-    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
-    ws = _WS.get(dev)
+def gemm_workspace(nbytes: int = 16 << 20):
+    """Caller-owned split-K scratch, one per (device, stream) — concurrent branches of the
+    step run on their own streams and must not share scratch."""
+    if torch.cuda.is_available():
+        key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    else:
+        key = (-1, 0)
+    ws = _WS.get(key)
     if ws is None:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda" if dev >= 0 else "cpu")
-        _WS[dev] = ws
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda" if key[0] >= 0 else "cpu")
+        _WS[key] = ws
     return ws
+
+
+class Branch:
+    """Fork/join of an independent branch of the step onto a side stream (captured as parallel
+    graph branches under CUDA-graph capture).  No-op without CUDA (CPU dry-run walks)."""
+
+    _streams = {}
+
+    def __init__(self, name: str, enabled: bool = True):
+        self.enabled = enabled and torch.cuda.is_available()
+        self.name = name
+        self.ctx = None
+        if self.enabled:
+            key = (torch.cuda.current_device(), name)
+            if key not in Branch._streams:
+                Branch._streams[key] = torch.cuda.Stream()
+            self.stream = Branch._streams[key]
+            self.done = torch.cuda.Event()
+
+    def __enter__(self):
+        if self.enabled:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(self.stream)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self.done.record(self.stream)
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.enabled:
+            torch.cuda.current_stream().wait_event(self.done)
 
 
 def _gemm(a, lda_m, lda_k, b, ldb_k, ldb_n, c, ldc, bias, m, n, k, beta=0.0, act=0):
@@ -60,6 +99,9 @@ def linear_dw(dy, lddy, x, ldx, dw, lddw, rows, n_out, n_in, beta=0.0):
     _gemm(dy, 1, lddy, x, ldx, 1, dw, lddw, None, n_out, n_in, rows, beta, 0)
 
 
+import os as _os
+
+OVERLAP = _os.environ.get("VLNCE_OVERLAP", "1") != "0"  # multi-stream branches on/off
 F4 = 4  # sizeof(float)
 
 
@@ -204,20 +246,24 @@ class CMAEngine(HeadEngine):
         st = lib.stream()
         H, P = self.H, self.P
 
-        # ---- instruction encoder (instruction_encoder.py:63-94)
-        instr, _, lengths, L = self._encode_instruction(observations, R, save)
+        # ---- three independent producers run concurrently: instruction encoder and depth trunk
+        # on side streams, RGB trunk on the caller's stream (joined where first consumed)
+        with Branch("instr", OVERLAP) as br_instr:
+            instr, _, lengths, L = self._encode_instruction(observations, R, save)
 
         # ---- visual encoders + spatial embeddings (cma_policy.py:227-231)
         rgb_e = self.buf("rgb_emb", (R, P, self.Crgb))
         dep_e = self.buf("depth_emb", (R, P, self.Cdep))
         c_rgb = net.rgb_encoder.resnet_layer_size
         c_dep = net.depth_encoder.visual_encoder.output_shape[0]
+        with Branch("depth", OVERLAP) as br_depth:
+            net.depth_encoder.features_into(observations, dep_e, self.Cdep, self.precision)
+            C.vlnce_spatial_embed_fill(ptr(net.depth_encoder.spatial_embeddings.weight), ptr(dep_e),
+                                       P * self.Cdep, self.Cdep, c_dep, R, P, 64, lib.stream())
         net.rgb_encoder.features_into(observations, rgb_e, self.Crgb, self.precision)
-        net.depth_encoder.features_into(observations, dep_e, self.Cdep, self.precision)
         C.vlnce_spatial_embed_fill(ptr(net.rgb_encoder.spatial_embeddings.weight), ptr(rgb_e), P * self.Crgb,
                                    self.Crgb, c_rgb, R, P, 64, st)
-        C.vlnce_spatial_embed_fill(ptr(net.depth_encoder.spatial_embeddings.weight), ptr(dep_e),
-                                   P * self.Cdep, self.Cdep, c_dep, R, P, 64, st)
+        br_depth.join()
 
         # ---- prev-action embedding into both concat slices (cma_policy.py:233-235, Q6)
         state_in = self.buf("state_in", (R, self.state_in))
@@ -246,6 +292,7 @@ class CMAEngine(HeadEngine):
                           ptr(rnn_states), 2 * H, masks_f, ptr(xcat), self.cat, ptr(h_out), 2 * H, T, N, save)
 
         # ---- text attention (cma_policy.py:258-263)
+        br_instr.join()
         if "scale" not in self.__dict__:
             self.scale = float(net._scale)  # one host sync, cached
         scale = self.scale

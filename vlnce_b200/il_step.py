@@ -84,6 +84,17 @@ class ILTrainerStep:
     # ---------------------------------------------------------------- the reference signature
     def update_agent(self, observations, prev_actions, not_done_masks, corrected_actions, weights,
                      step_grad: bool = True, loss_accumulation_scalar: int = 1, return_tensor: bool = False):
+        self.compute_grads(observations, prev_actions, not_done_masks, corrected_actions, weights,
+                           loss_accumulation_scalar)
+        self.apply_grads(step_grad)
+        if return_tensor:
+            return self._losses
+        loss, action_loss, aux_loss = self._losses.tolist()  # one D2H read (the reference does three .item())
+        return loss, action_loss, aux_loss
+
+    # The two phases are separately CUDA-graph capturable; the NCCL all-reduce sits between them.
+    def compute_grads(self, observations, prev_actions, not_done_masks, corrected_actions, weights,
+                      loss_accumulation_scalar: int = 1):
         pol = self.policy
         net = pol.net
         self._prepare()
@@ -119,13 +130,17 @@ class ILTrainerStep:
                         T, N, A, ptr(d_raw), ptr(d_hat), ptr(self._losses), st)
         fp.grad.zero_()
         cma_backward(eng, head, fp.grad_views, d_raw, None, d_hat if use_pm else None)
+
+    def apply_grads(self, step_grad: bool = True, allreduce: bool = True):
+        fp = self.fp
+        st = lib.stream()
         accumulating = self._pending > 0 or not step_grad
         if accumulating:
             C.vlnce_axpy(ptr(self._accum), ptr(fp.grad), 1.0, fp.total, st)
             self._pending += 1
         if step_grad:
             g = self._accum if accumulating else fp.grad
-            if self.world > 1:
+            if self.world > 1 and allreduce:
                 torch.distributed.all_reduce(g, group=self.pg)  # NCCL sum over NVLink; 1/world folded below
             C.vlnce_counter_add(ptr(self._step_dev), 1, st)
             self.step_id += 1
@@ -135,7 +150,3 @@ class ILTrainerStep:
             if accumulating:
                 self._accum.zero_()
                 self._pending = 0
-        if return_tensor:
-            return self._losses
-        loss, action_loss, aux_loss = self._losses.tolist()  # one D2H read (the reference does three .item())
-        return loss, action_loss, aux_loss
