@@ -62,6 +62,13 @@ int vlnce_conv2d_bf16(const void* x, const void* w, int ab_dtype, const float* s
                       int K, int R, int S, int stride, int pad, int relu, int block_n,
                       cudaStream_t stream);
 
+/* RGB stem (torchvision conv1: 7x7/2 pad 3 on the (N,H,W,3) u8|f32 image, resnet_encoders.py:182,198)
+ * on the same tensor-core tiles with the im2col row formed on the fly inside the producer warps:
+ * w is the packed (K,192) matrix (K index (r*7+s)*3+c, zero padded 147..191); y (N,P,Q,K). */
+int vlnce_conv2d_stem_rgb(const void* x, int x_dtype, const void* w, int ab_dtype, const float* scale,
+                          const float* shift, void* y, int y_dtype, int N, int H, int W, int K, int relu,
+                          int block_n, cudaStream_t stream);
+
 /* Same contract on CUDA cores with fp32 accumulation and arbitrary C/K: the fp32-exact mode
  * and the on-device cross-check of the tensor-core tiles.  dtypes per tensor. */
 int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w_dtype, const float* scale,

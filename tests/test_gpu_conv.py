@@ -90,3 +90,30 @@ def test_conv_umma_rejects_bad_shapes():
     with pytest.raises(lib.VlnceError, match="multiple of 32"):
         C.vlnce_conv2d_bf16(ptr(x), ptr(w), lib.BF16, None, None, None, ptr(y), lib.BF16, 1, 4, 4, 24, 32, 1, 1, 1,
                             0, 0, 0, lib.stream())
+
+
+@pytest.mark.parametrize("img_dtype", [torch.uint8, torch.float32])
+@pytest.mark.parametrize("half", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_fused_rgb_stem_matches_reference(img_dtype, half):
+    """7x7/2 pad-3 stem with the im2col row built inside the tile vs the fp32 reference conv."""
+    g = torch.Generator().manual_seed(3)
+    n, hw, k = 3, 40, 64
+    img = torch.randint(0, 256, (n, hw, hw, 3), generator=g, dtype=torch.uint8)
+    if img_dtype == torch.float32:
+        img = img.float()
+    w = torch.randn(k, 7, 7, 3, generator=g) * 0.05
+    wp = torch.zeros(k, 192)
+    wp[:, :147] = w.reshape(k, -1)
+    scale, shift = (torch.rand(k, generator=g) + 0.5) / 255.0, torch.randn(k, generator=g) * 0.1
+    img_d, w_d, wp_d = img.to(DEV), w.to(DEV).to(half), wp.to(DEV).to(half)
+    scale, shift = scale.to(DEV), shift.to(DEV)
+    want = _ref_conv(img_d, w_d.float(), scale, shift, None, 2, 3, True)
+    p = (hw + 6 - 7) // 2 + 1
+    for y_dtype in (half, torch.float32):
+        y = torch.full((n, p, p, k), float("nan"), device=DEV, dtype=y_dtype)
+        C.vlnce_conv2d_stem_rgb(ptr(img_d), lib.code(img_d), ptr(wp_d), lib.code(wp_d), ptr(scale), ptr(shift), ptr(y),
+                                lib.code(y), n, hw, hw, k, 1, 0, lib.stream())
+        torch.cuda.synchronize()
+        err = (y.float() - want).abs().max().item()
+        assert torch.isfinite(y.float()).all()
+        assert err <= (2e-2 if y_dtype == torch.bfloat16 else 4e-3) * max(want.abs().max().item(), 1.0), err

@@ -55,6 +55,8 @@ struct ConvParams {
   int y_fp32;       // 1: store fp32 instead of the 16-bit activation type
   int ab_half;      // 1: operands / residual / 16-bit output are fp16, else bf16
   int a_tma;        // 1: activation tile comes by TMA (1x1 stride-1 pad-0)
+  int stem;         // 1: x is the raw (N,H,W,3) u8 image, 2: f32 image — 7x7/2 pad-3 RGB stem, the
+                    //    im2col row (r,s,c) is formed on the fly (K padded 147 -> 192)
   int out_tma;      // 1: epilogue stages the tile in smem and stores it with TMA
 };
 
@@ -127,7 +129,79 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    if (!p.a_tma) {
+    if (p.stem) {
+      // ---------------------------------------------------------- RGB stem: im2col on the fly
+      // A row = the 7x7x3 window of one output pixel, K index (r*7+s)*3+c; this thread fills the
+      // 8-element (16 B) chunk `chunk` of rows t/8 + 16 i.  Byte loads hit L1 (each input byte is
+      // used by ~12 windows); values 0..255 are exact in bf16/fp16.
+      const int t = threadIdx.x;
+      const int chunk = t % 8;
+      const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x);
+      const float* xf = reinterpret_cast<const float*>(p.x);
+      int ih0[8], iw0[8], img_off[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + t / 8 + i * 16;
+        if (m < p.M) {
+          const int pq = p.P * p.Q;
+          const int n_img = m / pq;
+          const int rem = m - n_img * pq;
+          const int po = rem / p.Q;
+          ih0[i] = po * 2 - 3;
+          iw0[i] = (rem - po * p.Q) * 2 - 3;
+          img_off[i] = n_img * p.H * p.W * 3;
+        } else {
+          ih0[i] = -(1 << 20);
+          iw0[i] = 0;
+          img_off[i] = 0;
+        }
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        const uint32_t a_stage = smem_a0 + stage * C::A_BYTES;
+        int dr[8], ds[8], dc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int kk = it * 64 + chunk * 8 + e;
+          const int tap = kk / 3;
+          dc[e] = kk - tap * 3;
+          dr[e] = kk < 147 ? tap / 7 : (1 << 20);  // padded K columns read nothing
+          ds[e] = tap % 7;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = t / 8 + i * 16;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int ih = ih0[i] + dr[e], iw = iw0[i] + ds[e];
+            const bool ok = (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+            const int off = img_off[i] + (ih * p.W + iw) * 3 + dc[e];
+            v[e] = ok ? (p.stem == 1 ? (float)__ldg(xb + off) : __ldg(xf + off)) : 0.f;
+          }
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (p.ab_half) {
+              __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+              o[e] = *reinterpret_cast<uint32_t*>(&h2);
+            } else {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+              o[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+          }
+          const uint32_t addr = a_stage + swizzled_offset(row, chunk, 128);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                       "r"(o[3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full_bar[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    } else if (!p.a_tma) {
       // ---------------------------------------------------------- A gather (producers)
       const int t = threadIdx.x;
       const int chunk = t % C::CPR;
@@ -469,7 +543,29 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, 
 
 using namespace vlnce;
 
+static int conv2d_impl(const void* x, int stem, const void* w, int ab_dtype, const float* scale,
+                       const float* shift, const void* residual, void* y, int y_dtype, int N, int H, int W,
+                       int C, int K, int R, int S, int stride, int pad, int relu, int block_n,
+                       cudaStream_t stream);
+
 extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, int ab_dtype, const float* scale,
+                                 const float* shift, const void* residual, void* y, int y_dtype,
+                                 int N, int H, int W, int C, int K, int R, int S, int stride,
+                                 int pad, int relu, int block_n, cudaStream_t stream) {
+  return conv2d_impl(x, 0, w, ab_dtype, scale, shift, residual, y, y_dtype, N, H, W, C, K, R, S, stride, pad, relu,
+                     block_n, stream);
+}
+
+extern "C" int vlnce_conv2d_stem_rgb(const void* x, int x_dtype, const void* w, int ab_dtype,
+                                     const float* scale, const float* shift, void* y, int y_dtype, int N,
+                                     int H, int W, int K, int relu, int block_n, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x_dtype == VLNCE_U8 || x_dtype == VLNCE_F32, "conv2d_stem_rgb: image must be u8 or f32");
+  // geometry handed to the tile kernel: an (N*P*Q) x 192 GEMM whose A rows are built from the image
+  return conv2d_impl(x, x_dtype == VLNCE_U8 ? 1 : 2, w, ab_dtype, scale, shift, nullptr, y, y_dtype, N, H, W, 192,
+                     K, 1, 1, 1, 0, relu, block_n, stream);
+}
+
+static int conv2d_impl(const void* x, int stem, const void* w, int ab_dtype, const float* scale,
                                  const float* shift, const void* residual, void* y, int y_dtype,
                                  int N, int H, int W, int C, int K, int R, int S, int stride,
                                  int pad, int relu, int block_n, cudaStream_t stream) {
@@ -487,8 +583,8 @@ extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, int ab_dtype, con
                       (reinterpret_cast<uintptr_t>(residual) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0,
                   "conv2d_bf16: tensors must be 16-byte aligned");
-  const int P = (H + 2 * pad - R) / stride + 1;
-  const int Q = (W + 2 * pad - S) / stride + 1;
+  const int P = stem ? (H + 6 - 7) / 2 + 1 : (H + 2 * pad - R) / stride + 1;
+  const int Q = stem ? (W + 6 - 7) / 2 + 1 : (W + 2 * pad - S) / stride + 1;
   VLNCE_CHECK_ARG(P > 0 && Q > 0, "conv2d_bf16: empty output");
   VLNCE_CHECK_ARG((long long)N * H * W * C < (1ll << 31) && (long long)N * P * Q * K < (1ll << 40),
                   "conv2d_bf16: tensor too large for 32-bit offsets");
@@ -531,7 +627,8 @@ extern "C" int vlnce_conv2d_bf16(const void* x, const void* w, int ab_dtype, con
   p.stages = 1;
   p.y_fp32 = (y_dtype == VLNCE_F32);
   p.ab_half = (ab_dtype == VLNCE_F16);
-  p.a_tma = (R == 1 && S == 1 && stride == 1 && pad == 0) ? 1 : 0;
+  p.stem = stem;
+  p.a_tma = (!stem && R == 1 && S == 1 && stride == 1 && pad == 0) ? 1 : 0;
   p.out_tma = (bn >= 64) ? 1 : 0;
 
   CUtensorMap tw, tx, ty, tr;

@@ -49,6 +49,7 @@ class BufferPool:
 import os as _os
 
 AUTOTUNE = _os.environ.get("VLNCE_AUTOTUNE", "1") != "0"
+FUSED_STEM = _os.environ.get("VLNCE_FUSED_STEM", "1") != "0"
 # Tuned (tile width | ring depth << 16) per conv geometry, optionally persisted so that later
 # processes on the same box (profilers, the second bench leg) skip the timing sweep.
 _TUNE_CACHE_PATH = _os.environ.get("VLNCE_AUTOTUNE_CACHE", "")
@@ -146,17 +147,24 @@ class ConvTrunk:
         return self.pool.get(tag, shape, torch.float32)
 
     def _conv(self, x, shape_in, cv: _Conv, y, *, scale, shift, residual=None, relu=False,
-              gemm_c: Optional[int] = None):
-        """x NHWC (n,h,w,c) -> y; ``gemm_c`` set = x is an explicit stem operand (n*p*q, gemm_c)."""
+              gemm_c: Optional[int] = None, stem_rgb: bool = False):
+        """x NHWC (n,h,w,c) -> y; ``gemm_c`` set = x is an explicit stem operand (n*p*q, gemm_c);
+        ``stem_rgb`` = x is the raw (n,h,w,3) image and the 7x7/2 window is gathered in-kernel."""
         n, h, w, c = shape_in
         st = lib.stream()
         if self.precision == "bf16":
-            if gemm_c is not None:
+            if stem_rgb:
+                geom = ("stem", n, h, w, cv.K)
+            elif gemm_c is not None:
                 geom = (n * h * w, 1, 1, gemm_c, cv.K, 1, 1, 1, 0)
             else:
                 geom = (n, h, w, c, cv.K, cv.R, cv.S, cv.stride, cv.pad)
 
             def launch(bn):
+                if stem_rgb:
+                    C.vlnce_conv2d_stem_rgb(ptr(x), lib.code(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift),
+                                            ptr(y), lib.code(y), n, h, w, cv.K, int(relu), bn, st)
+                    return
                 C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
                                     ptr(y), lib.code(y), *geom, int(relu), bn, st)
 
@@ -238,19 +246,19 @@ class RGBTrunk(ConvTrunk):
         return out
 
     def _norm_conv(self, x, shape_in, cv: _Conv, tag, *, residual=None, relu=True, gemm_c=None,
-                   out_hw=None):
+                   out_hw=None, stem_rgb=False):
         n, h, w, _ = shape_in
         p, q = out_hw if out_hw is not None else self._out_hw(h, w, cv)
         y = self._act(tag, (n, p, q, cv.K))
         bn: nn.BatchNorm2d = cv.norm
         if not bn.training:
             self._conv(x, shape_in, cv, y, scale=cv.scale, shift=cv.shift, residual=residual, relu=relu,
-                       gemm_c=gemm_c)
+                       gemm_c=gemm_c, stem_rgb=stem_rgb)
             return y, (n, p, q, cv.K)
         # train-mode BN (Q1): raw conv (input scaling only) -> batch stats -> fused apply
         raw = self._raw("bn_raw", (n, p, q, cv.K))
         self._conv(x, shape_in, cv, raw, scale=cv.pre_scale if cv.in_scale != 1.0 else None,
-                   shift=cv.pre_shift if cv.in_scale != 1.0 else None, gemm_c=gemm_c)
+                   shift=cv.pre_shift if cv.in_scale != 1.0 else None, gemm_c=gemm_c, stem_rgb=stem_rgb)
         st = lib.stream()
         sc = self.pool.get("bn_scale", (cv.K,), torch.float32)
         sh = self.pool.get("bn_shift", (cv.K,), torch.float32)
@@ -273,7 +281,10 @@ class RGBTrunk(ConvTrunk):
         st = lib.stream()
         cv = self.stem
         p, q = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
-        if self.precision == "bf16":
+        if self.precision == "bf16" and FUSED_STEM:
+            # im2col-free stem: the 7x7x3 windows are gathered inside the conv tile's producer warps
+            x, shp = self._norm_conv(rgb, (n, h, w, 3), cv, "stem_y", out_hw=(p, q), stem_rgb=True)
+        elif self.precision == "bf16":
             a = self.pool.get("stem_a", (n * p * q, 192), self.adt)
             C.vlnce_im2col_rgb_stem(ptr(rgb), lib.code(rgb), ptr(a), lib.code(a), n, h, w, st)
             x, shp = self._norm_conv(a, (n, p, q, 192), cv, "stem_y", gemm_c=192, out_hw=(p, q))
