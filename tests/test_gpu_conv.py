@@ -92,12 +92,14 @@ def test_conv_umma_rejects_bad_shapes():
                             0, 0, 0, lib.stream())
 
 
+@pytest.mark.parametrize("hw", [40, 256], ids=["generic", "row-tile-fast-path"])
 @pytest.mark.parametrize("img_dtype", [torch.uint8, torch.float32])
 @pytest.mark.parametrize("half", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
-def test_fused_rgb_stem_matches_reference(img_dtype, half):
-    """7x7/2 pad-3 stem with the im2col row built inside the tile vs the fp32 reference conv."""
+def test_fused_rgb_stem_matches_reference(img_dtype, half, hw):
+    """7x7/2 pad-3 stem with the im2col row built inside the tile vs the fp32 reference conv
+    (hw=256: one tile = one output row, input rows staged in shared memory)."""
     g = torch.Generator().manual_seed(3)
-    n, hw, k = 3, 40, 64
+    n, k = (3 if hw < 100 else 2), 64
     img = torch.randint(0, 256, (n, hw, hw, 3), generator=g, dtype=torch.uint8)
     if img_dtype == torch.float32:
         img = img.float()

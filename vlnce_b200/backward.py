@@ -30,7 +30,23 @@ def _colsum(a, lda, out, m, n, acc=0):
     C.vlnce_colsum(a, lda, out, m, n, acc, ws.data_ptr(), ws.numel(), lib.stream())
 
 
-def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, masks_f, T, N, dx, lddx):
+class _Leaves:
+    """Weight/bias gradients are leaves of the backward graph: they run on a side stream while
+    the dX chain continues on the caller's stream; ``join()`` once at the end."""
+
+    def __init__(self):
+        self.last = None
+
+    def __call__(self):
+        self.last = Branch("dw", OVERLAP)
+        return self.last
+
+    def join(self):
+        if self.last is not None:
+            self.last.join()
+
+
+def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, masks_f, T, N, dx, lddx, leaves):
     H = eng.H
     R = T * N
     st = lib.stream()
@@ -45,10 +61,11 @@ def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, m
         linear_dx(off(d_gh, t * N * 3 * H), 3 * H, ptr(rnn.weight_hh_l0), ptr(dhm), H, N, 3 * H, H, beta=1.0)
         if t > 0:
             C.vlnce_mask_rows_add(ptr(dhm), H, off(masks_f, t * N), dh + F4 * (t - 1) * N * lddh, lddh, N, H, st)
-    linear_dw(ptr(d_gh), 3 * H, ptr(hm_all), H, ptr(g[pfx + "weight_hh_l0"]), H, R, 3 * H, H)
-    _colsum(ptr(d_gh), 3 * H, ptr(g[pfx + "bias_hh_l0"]), R, 3 * H)
-    linear_dw(ptr(d_gi), 3 * H, x, ldx, ptr(g[pfx + "weight_ih_l0"]), in_size, R, 3 * H, in_size)
-    _colsum(ptr(d_gi), 3 * H, ptr(g[pfx + "bias_ih_l0"]), R, 3 * H)
+    with leaves():
+        linear_dw(ptr(d_gh), 3 * H, ptr(hm_all), H, ptr(g[pfx + "weight_hh_l0"]), H, R, 3 * H, H)
+        _colsum(ptr(d_gh), 3 * H, ptr(g[pfx + "bias_hh_l0"]), R, 3 * H)
+        linear_dw(ptr(d_gi), 3 * H, x, ldx, ptr(g[pfx + "weight_ih_l0"]), in_size, R, 3 * H, in_size)
+        _colsum(ptr(d_gi), 3 * H, ptr(g[pfx + "bias_ih_l0"]), R, 3 * H)
     linear_dx(ptr(d_gi), 3 * H, ptr(rnn.weight_ih_l0), dx, lddx, R, 3 * H, in_size)
 
 
@@ -68,12 +85,14 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     x_out, x2, xcat, state_in = b("x_out", (R, H)), b("x2", (R, H)), b("xcat", (R, eng.cat)), b("state_in", (R, eng.state_in))
     masks_f = b("masks_f", (R,))
     dx_out = b("d_x_out", (R, H))
+    leaves = _Leaves()
 
     # 1. action head / feature gradient
     if head_linear is not None:
         A = head_linear.weight.shape[0]
-        linear_dw(ptr(d_raw), A, ptr(x_out), H, ptr(g["action_distribution.linear.weight"]), H, R, A, H)
-        _colsum(ptr(d_raw), A, ptr(g["action_distribution.linear.bias"]), R, A)
+        with leaves():
+            linear_dw(ptr(d_raw), A, ptr(x_out), H, ptr(g["action_distribution.linear.weight"]), H, R, A, H)
+            _colsum(ptr(d_raw), A, ptr(g["action_distribution.linear.bias"]), R, A)
         linear_dx(ptr(d_raw), A, ptr(head_linear.weight), ptr(dx_out), H, R, A, H)
     else:
         dx_out.copy_(d_x)
@@ -84,18 +103,20 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
         dpre.copy_(d_hat.reshape(R, 1))
         C.vlnce_tanh_bwd(ptr(dpre), ptr(hat), R, st)
         pm = net.progress_monitor
-        linear_dw(ptr(dpre), 1, ptr(x_out), H, ptr(g["net.progress_monitor.weight"]), H, R, 1, H)
-        _colsum(ptr(dpre), 1, ptr(g["net.progress_monitor.bias"]), R, 1)
+        with leaves():
+            linear_dw(ptr(dpre), 1, ptr(x_out), H, ptr(g["net.progress_monitor.weight"]), H, R, 1, H)
+            _colsum(ptr(dpre), 1, ptr(g["net.progress_monitor.bias"]), R, 1)
         linear_dx(ptr(dpre), 1, ptr(pm.weight), ptr(dx_out), H, R, 1, H, beta=1.0)
     # 3. second GRU
     d_x2 = b("d_x2", (R, H))
     _gru_backward(eng, "gru2", net.second_state_encoder.rnn, "net.second_state_encoder.rnn.", g, ptr(dx_out), H,
-                  ptr(x2), H, H, masks_f, T, N, ptr(d_x2), H)
+                  ptr(x2), H, H, masks_f, T, N, ptr(d_x2), H, leaves)
     # 4. second_state_compress = ReLU(Linear(xcat))
     C.vlnce_relu_bwd(ptr(d_x2), H, ptr(x2), H, R, H, st)
     lin = net.second_state_compress[0]
-    linear_dw(ptr(d_x2), H, ptr(xcat), eng.cat, ptr(g["net.second_state_compress.0.weight"]), eng.cat, R, H, eng.cat)
-    _colsum(ptr(d_x2), H, ptr(g["net.second_state_compress.0.bias"]), R, H)
+    with leaves():
+        linear_dw(ptr(d_x2), H, ptr(xcat), eng.cat, ptr(g["net.second_state_compress.0.weight"]), eng.cat, R, H, eng.cat)
+        _colsum(ptr(d_x2), H, ptr(g["net.second_state_compress.0.bias"]), R, H)
     dxcat = b("d_xcat", (R, eng.cat))
     linear_dx(ptr(d_x2), H, ptr(lin.weight), ptr(dxcat), eng.cat, R, H, eng.cat)
     # 5. visual attentions
@@ -109,8 +130,9 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
         pooled, qv, probs = b("pooled_" + name, (R, Cc)), b("q_" + name, (R, Cc)), b("p_" + name, (R, P))
         gw, gb = g[f"net.{name}_kv.weight"], g[f"net.{name}_kv.bias"]
         d_att = off(dxcat, col)
-        linear_dw(d_att, eng.cat, ptr(pooled), Cc, off(gw, hk * Cc), Cc, R, v_out, Cc)  # dW_v
-        _colsum(d_att, eng.cat, off(gb, hk), R, v_out)
+        with leaves():
+            linear_dw(d_att, eng.cat, ptr(pooled), Cc, off(gw, hk * Cc), Cc, R, v_out, Cc)  # dW_v
+            _colsum(d_att, eng.cat, off(gb, hk), R, v_out)
         d_pooled = b("d_pooled_" + name, (R, Cc))
         linear_dx(d_att, eng.cat, off(kv.weight, hk * Cc), ptr(d_pooled), Cc, R, v_out, Cc)
         dq = b("d_q_" + name, (R, Cc))
@@ -118,12 +140,14 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
         C.vlnce_attn_pool_bwd(ptr(qv), Cc, ptr(E_), P * Cc, Cc, ptr(probs), eng.scale, ptr(d_pooled), Cc, ptr(dq),
                               Cc, ptr(dEn), P * Cc, Cc, 0, R, P, Cc, st)
         dE[name] = dEn
-        linear_dw(ptr(text_q), hk, ptr(dq), Cc, ptr(gw), Cc, R, hk, Cc)  # dW_k = text_q^T dq'
+        with leaves():
+            linear_dw(ptr(text_q), hk, ptr(dq), Cc, ptr(gw), Cc, R, hk, Cc)  # dW_k = text_q^T dq'
         linear(ptr(dq), Cc, ptr(kv.weight), ptr(d_text_q), hk, None, R, hk, Cc, beta=0.0 if first else 1.0)
         first = False
     # 6. text_q = Linear(text_embedding)
-    linear_dw(ptr(d_text_q), hk, off(xcat, H), eng.cat, ptr(g["net.text_q.weight"]), eng.Dt, R, hk, eng.Dt)
-    _colsum(ptr(d_text_q), hk, ptr(g["net.text_q.bias"]), R, hk)
+    with leaves():
+        linear_dw(ptr(d_text_q), hk, off(xcat, H), eng.cat, ptr(g["net.text_q.weight"]), eng.Dt, R, hk, eng.Dt)
+        _colsum(ptr(d_text_q), hk, ptr(g["net.text_q.bias"]), R, hk)
     linear_dx(ptr(d_text_q), hk, ptr(net.text_q.weight), off(dxcat, H), eng.cat, R, hk, eng.Dt, beta=1.0)
     # 7. text attention
     instr = b("instr_out", (R, L, eng.Dt))
@@ -132,11 +156,13 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     d_instr = b("d_instr", (R, L, eng.Dt))
     C.vlnce_attn_pool_bwd(ptr(q_t), eng.Dt, ptr(instr), L * eng.Dt, eng.Dt, ptr(p_text), eng.scale, off(dxcat, H),
                           eng.cat, ptr(dq_t), eng.Dt, ptr(d_instr), L * eng.Dt, eng.Dt, 0, R, L, eng.Dt, st)
-    linear_dw(ptr(q_s), hk, ptr(dq_t), eng.Dt, ptr(g["net.text_k.weight"]), eng.Dt, R, hk, eng.Dt)
+    with leaves():
+        linear_dw(ptr(q_s), hk, ptr(dq_t), eng.Dt, ptr(g["net.text_k.weight"]), eng.Dt, R, hk, eng.Dt)
     d_q_s = b("d_q_state", (R, hk))
     linear(ptr(dq_t), eng.Dt, ptr(net.text_k.weight), ptr(d_q_s), hk, None, R, hk, eng.Dt)
-    linear_dw(ptr(d_q_s), hk, ptr(xcat), eng.cat, ptr(g["net.state_q.weight"]), H, R, hk, H)
-    _colsum(ptr(d_q_s), hk, ptr(g["net.state_q.bias"]), R, hk)
+    with leaves():
+        linear_dw(ptr(d_q_s), hk, ptr(xcat), eng.cat, ptr(g["net.state_q.weight"]), H, R, hk, H)
+        _colsum(ptr(d_q_s), hk, ptr(g["net.state_q.bias"]), R, hk)
     linear_dx(ptr(d_q_s), hk, ptr(net.state_q.weight), ptr(dxcat), eng.cat, R, hk, H, beta=1.0)
     with Branch("lstm_bwd", OVERLAP) as br_lstm:
         # 12. instruction encoder (BPTT) — independent of steps 8-11: own stream
@@ -170,7 +196,7 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     # 8. first GRU (dh = dxcat[:, :H])
     d_state_in = b("d_state_in", (R, eng.state_in))
     _gru_backward(eng, "gru1", net.state_encoder.rnn, "net.state_encoder.rnn.", g, ptr(dxcat), eng.cat,
-                  ptr(state_in), eng.state_in, eng.state_in, masks_f, T, N, ptr(d_state_in), eng.state_in)
+                  ptr(state_in), eng.state_in, eng.state_in, masks_f, T, N, ptr(d_state_in), eng.state_in, leaves)
     # 9. rgb_linear / depth_linear (ReLU(Linear))
     c_rgb = net.rgb_encoder.resnet_layer_size
     c_dep = net.depth_encoder.visual_encoder.output_shape[0]
@@ -203,6 +229,7 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     C.vlnce_spatial_embed_grad(ptr(dE["depth"]), P * eng.Cdep, eng.Cdep, c_dep, ptr(d_flat_sp), 64 * P, None, 0,
                                ptr(g["net.depth_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
     br_lstm.join()
+    leaves.join()
 
 
 class CMAFunction(torch.autograd.Function):

@@ -57,6 +57,7 @@ struct ConvParams {
   int a_tma;        // 1: activation tile comes by TMA (1x1 stride-1 pad-0)
   int stem;         // 1: x is the raw (N,H,W,3) u8 image, 2: f32 image — 7x7/2 pad-3 RGB stem, the
                     //    im2col row (r,s,c) is formed on the fly (K padded 147 -> 192)
+  int stem_patch;   // byte offset of the input-patch scratch after the staging buffer (0: none)
   int out_tma;      // 1: epilogue stages the tile in smem and stores it with TMA
 };
 
@@ -73,8 +74,8 @@ struct Cfg {
   static constexpr int staging_bytes(bool out_tma, bool y_fp32) {
     return out_tma ? BLOCK_M * BLOCK_N * (y_fp32 ? 4 : 2) : 0;
   }
-  static constexpr int smem_bytes(int stages, bool out_tma, bool y_fp32) {
-    return stages * STAGE_BYTES + BAR_BYTES + staging_bytes(out_tma, y_fp32) + 1024;  // + align slack
+  static constexpr int smem_bytes(int stages, bool out_tma, bool y_fp32, int extra = 0) {
+    return stages * STAGE_BYTES + BAR_BYTES + staging_bytes(out_tma, y_fp32) + extra + 1024;  // + align slack
   }
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must stay 1024B aligned");
 };
@@ -156,6 +157,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           img_off[i] = 0;
         }
       }
+      // Fast path (one tile = one output row, Q % 128 == 0): stage the 7 input rows the tile reads
+      // in shared memory once (coalesced 16-byte loads, zero-filled padding), then build the
+      // im2col chunks from shared memory — no per-element global loads or bounds checks.
+      constexpr int PATCH_W = 788;  // (2*127 + 6 + 1 + 1) * 3 bytes rounded up; x-origin at iw = -4
+      const bool patch = p.stem_patch != 0;
+      uint8_t* pb = smem + stages * C::STAGE_BYTES + C::BAR_BYTES + p.stem_patch;
+      if (patch) {
+        const int pq = p.P * p.Q;
+        const int n_img = m0 / pq;
+        const int rem = m0 - n_img * pq;
+        const int po = rem / p.Q, q0 = rem - po * p.Q;
+        const int esz = p.stem == 1 ? 1 : 4;
+        const int row_bytes = p.W * 3 * esz;                 // multiple of 16 (W % 128 == 0)
+        const int x_off = (2 * q0 - 4) * 3 * esz;            // byte offset of the patch origin in a row
+        for (int r = 0; r < 7; ++r) {
+          const int ih = po * 2 - 3 + r;
+          uint8_t* prow = pb + r * PATCH_W * esz;
+          const bool row_ok = (unsigned)ih < (unsigned)p.H;
+          const uint8_t* grow = xb + ((size_t)(n_img * p.H + ih) * p.W) * 3 * esz;
+          // the patch spans bytes [x_off, x_off + PATCH_W*esz) of the row; 4-byte granules
+          for (int w4 = t; w4 < PATCH_W * esz / 4; w4 += kProducerThreads) {
+            const int gb = x_off + w4 * 4;
+            uint32_t v = 0;
+            if (row_ok && gb >= 0 && gb + 4 <= row_bytes) v = __ldg(reinterpret_cast<const uint32_t*>(grow + gb));
+            *reinterpret_cast<uint32_t*>(prow + w4 * 4) = v;
+          }
+        }
+        named_barrier_sync(2, kProducerThreads);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < p.num_k_iters; ++it) {
@@ -174,12 +204,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         for (int i = 0; i < 8; ++i) {
           const int row = t / 8 + i * 16;
           float v[8];
+          if (patch) {
+            const int qrow = (m0 + row) % p.Q - (m0 % p.Q);  // pixel index inside the tile's row
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int ih = ih0[i] + dr[e], iw = iw0[i] + ds[e];
-            const bool ok = (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
-            const int off = img_off[i] + (ih * p.W + iw) * 3 + dc[e];
-            v[e] = ok ? (p.stem == 1 ? (float)__ldg(xb + off) : __ldg(xf + off)) : 0.f;
+            for (int e = 0; e < 8; ++e) {
+              const int off = dr[e] * PATCH_W + (2 * qrow + ds[e] + 1) * 3 + dc[e];
+              v[e] = dr[e] >= 7 ? 0.f : (p.stem == 1 ? (float)pb[off] : reinterpret_cast<const float*>(pb)[off]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int ih = ih0[i] + dr[e], iw = iw0[i] + ds[e];
+              const bool ok = (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+              const int off = img_off[i] + (ih * p.W + iw) * 3 + dc[e];
+              v[e] = ok ? (p.stem == 1 ? (float)__ldg(xb + off) : __ldg(xf + off)) : 0.f;
+            }
           }
           uint32_t o[4];
 #pragma unroll
@@ -519,20 +558,25 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, 
     budget = e ? atoi(e) * 1024 : 113 * 1024;
     if (budget > kSmemBudget) budget = kSmemBudget;
   }
+  // stem fast path: 7 x 788 input elements of scratch (u8 or f32) behind the staging buffer
+  int extra = 0;
+  p.stem_patch = 0;
+  if (p.stem && p.Q % BLOCK_M == 0 && p.W % 128 == 0) extra = 7 * 788 * (p.stem == 1 ? 1 : 4) + 64;
   int stages = p.num_k_iters < kMaxStages ? p.num_k_iters : kMaxStages;
   if (stages_cap > 0) {  // tuned by the caller: ring depth given, only the hardware limit applies
     if (stages > stages_cap) stages = stages_cap;
-    while (stages > 1 && C::smem_bytes(stages, p.out_tma, p.y_fp32) > kSmemBudget) --stages;
+    while (stages > 1 && C::smem_bytes(stages, p.out_tma, p.y_fp32, extra) > kSmemBudget) --stages;
   } else {
-    while (stages > 1 && C::smem_bytes(stages, p.out_tma, p.y_fp32) > budget) --stages;
+    while (stages > 1 && C::smem_bytes(stages, p.out_tma, p.y_fp32, extra) > budget) --stages;
   }
-  if (C::smem_bytes(stages, p.out_tma, p.y_fp32) > kSmemBudget) {  // staged tile too large: store directly
+  if (C::smem_bytes(stages, p.out_tma, p.y_fp32, extra) > kSmemBudget) {  // staged tile too large: store directly
     p.out_tma = 0;
     stages = p.num_k_iters < kMaxStages ? p.num_k_iters : kMaxStages;
   }
   p.stages = stages;
+  if (extra) p.stem_patch = C::staging_bytes(p.out_tma, p.y_fp32) + 16;  // never 0 when enabled
   const long long tiles = (long long)cdiv(p.M, BLOCK_M) * p.n_tiles;
-  conv_umma_kernel<BLOCK_N, BLOCK_K><<<(unsigned)tiles, kThreads, C::smem_bytes(stages, p.out_tma, p.y_fp32),
+  conv_umma_kernel<BLOCK_N, BLOCK_K><<<(unsigned)tiles, kThreads, C::smem_bytes(stages, p.out_tma, p.y_fp32, extra),
                                        stream>>>(tw, tx, ty, tr, p);
   VLNCE_LAUNCH_CHECK("conv_umma_kernel");
   return VLNCE_OK;
