@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="also write gpurun_out/step_profile.json")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -363,6 +364,22 @@ def main():
         rec.append((a, b, flops, type(self).__name__))
 
     roof = None
+    from vlnce_b200 import engine as engine_mod
+
+    engine_mod.set_overlap(False)  # serial launches: clean per-kernel times
+    if args.profile:
+        with lib.profile() as prof:
+            for i in range(3):
+                load_static(dev_sets[i % NSETS])
+                eager_step(static)
+        summ = prof.summary()
+        for v in summ.values():
+            v["us"] = round(v["us"] / 3, 1)
+            v["calls"] //= 3
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump({"note": "CUDA-event time per C-ABI call, serial streams, warm caches, per step",
+                   "total_us": round(sum(v["us"] for v in summ.values()), 1), "calls": summ},
+                  open("gpurun_out/step_profile.json", "w"), indent=1)
     if args.precision == "bf16":
         trunk_mod.ConvTrunk._conv = timed_conv
         for i in range(3):

@@ -11,7 +11,7 @@ from typing import Dict, Optional
 import torch
 
 from . import lib
-from .engine import F4, OVERLAP, Branch, CMAEngine, linear, linear_dw, linear_dx, off
+from .engine import F4, Branch, CMAEngine, linear, linear_dw, linear_dx, off
 from .lib import C, ptr
 
 
@@ -38,7 +38,7 @@ class _Leaves:
         self.last = None
 
     def __call__(self):
-        self.last = Branch("dw", OVERLAP)
+        self.last = Branch("dw")
         return self.last
 
     def join(self):
@@ -164,7 +164,7 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
         linear_dw(ptr(d_q_s), hk, ptr(xcat), eng.cat, ptr(g["net.state_q.weight"]), H, R, hk, H)
         _colsum(ptr(d_q_s), hk, ptr(g["net.state_q.bias"]), R, hk)
     linear_dx(ptr(d_q_s), hk, ptr(net.state_q.weight), ptr(dxcat), eng.cat, R, hk, H, beta=1.0)
-    with Branch("lstm_bwd", OVERLAP) as br_lstm:
+    with Branch("lstm_bwd") as br_lstm:
         # 12. instruction encoder (BPTT) — independent of steps 8-11: own stream
         ie = net.instruction_encoder
         rnn = ie.encoder_rnn

@@ -47,8 +47,8 @@ class Branch:
 
     _streams = {}
 
-    def __init__(self, name: str, enabled: bool = True):
-        self.enabled = enabled and torch.cuda.is_available()
+    def __init__(self, name: str, enabled=None):
+        self.enabled = (OVERLAP if enabled is None else enabled) and torch.cuda.is_available()
         self.name = name
         self.ctx = None
         if self.enabled:
@@ -102,6 +102,12 @@ def linear_dw(dy, lddy, x, ldx, dw, lddw, rows, n_out, n_in, beta=0.0):
 import os as _os
 
 OVERLAP = _os.environ.get("VLNCE_OVERLAP", "1") != "0"  # multi-stream branches on/off
+
+
+def set_overlap(on: bool):
+    """Toggle the multi-stream branches at run time (profiling passes want serial launches)."""
+    global OVERLAP
+    OVERLAP = bool(on)
 F4 = 4  # sizeof(float)
 
 
@@ -248,7 +254,7 @@ class CMAEngine(HeadEngine):
 
         # ---- three independent producers run concurrently: instruction encoder and depth trunk
         # on side streams, RGB trunk on the caller's stream (joined where first consumed)
-        with Branch("instr", OVERLAP) as br_instr:
+        with Branch("instr") as br_instr:
             instr, _, lengths, L = self._encode_instruction(observations, R, save)
 
         # ---- visual encoders + spatial embeddings (cma_policy.py:227-231)
@@ -256,7 +262,7 @@ class CMAEngine(HeadEngine):
         dep_e = self.buf("depth_emb", (R, P, self.Cdep))
         c_rgb = net.rgb_encoder.resnet_layer_size
         c_dep = net.depth_encoder.visual_encoder.output_shape[0]
-        with Branch("depth", OVERLAP) as br_depth:
+        with Branch("depth") as br_depth:
             net.depth_encoder.features_into(observations, dep_e, self.Cdep, self.precision)
             C.vlnce_spatial_embed_fill(ptr(net.depth_encoder.spatial_embeddings.weight), ptr(dep_e),
                                        P * self.Cdep, self.Cdep, c_dep, R, P, 64, lib.stream())

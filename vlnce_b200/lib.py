@@ -173,3 +173,60 @@ class dry_run:
             if getattr(mod, "__name__", "").startswith("vlnce_b200") and getattr(mod, "C", None) is checker:
                 mod.C = C
         return False
+
+
+class profile:
+    """Device-time profile of the library calls issued inside the context: a CUDA-event pair
+    around every C-ABI call on its launching stream (run with VLNCE_OVERLAP=0 semantics for
+    clean serial numbers).  ``summary()`` -> {function: {calls, us}} after a device sync."""
+
+    def __init__(self):
+        self.events = []
+
+    def __enter__(self):
+        global C
+        self._saved = C
+        real, outer = C, self
+
+        class _Timed:
+            protos = real.protos
+
+            def __getattr__(self, name):
+                fn = getattr(real, name)
+                if real.protos.get(name, ("",))[0] != "int":
+                    return fn
+
+                def call(*args):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn(*args)
+                    b.record()
+                    outer.events.append((name, a, b))
+
+                return call
+
+        C = _Timed()
+        import sys
+        for mod in list(sys.modules.values()):
+            if getattr(mod, "__name__", "").startswith("vlnce_b200") and getattr(mod, "C", None) is real:
+                mod.C = C
+        return self
+
+    def __exit__(self, *exc):
+        global C
+        timed = C
+        C = self._saved
+        import sys
+        for mod in list(sys.modules.values()):
+            if getattr(mod, "__name__", "").startswith("vlnce_b200") and getattr(mod, "C", None) is timed:
+                mod.C = C
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.events:
+            d = out.setdefault(name, {"calls": 0, "us": 0.0})
+            d["calls"] += 1
+            d["us"] += a.elapsed_time(b) * 1e3
+        return dict(sorted(out.items(), key=lambda kv: -kv[1]["us"]))
