@@ -69,6 +69,14 @@ int vlnce_conv2d_stem_rgb(const void* x, int x_dtype, const void* w, int ab_dtyp
                           const float* shift, void* y, int y_dtype, int N, int H, int W, int K, int relu,
                           int block_n, cudaStream_t stream);
 
+/* 3x3 stride-1 pad-1 conv with TMA halo loads (one (16+2)x(8+2)-pixel box per 64-channel chunk,
+ * nine shifted UMMA descriptors = the nine taps): same epilogue contract as vlnce_conv2d_bf16.
+ * Needs H % 16 == 0, W % 8 == 0, C % 64 == 0, K % 64 == 0.  block_n: 0 = auto, else width
+ * (64/128/256) | weight-ring depth << 16. */
+int vlnce_conv3x3_halo(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
+                       const void* residual, void* y, int y_dtype, int N, int H, int W, int C, int K, int relu,
+                       int block_n, cudaStream_t stream);
+
 /* Same contract on CUDA cores with fp32 accumulation and arbitrary C/K: the fp32-exact mode
  * and the on-device cross-check of the tensor-core tiles.  dtypes per tensor. */
 int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w_dtype, const float* scale,

@@ -119,3 +119,43 @@ def test_fused_rgb_stem_matches_reference(img_dtype, half, hw):
         err = (y.float() - want).abs().max().item()
         assert torch.isfinite(y.float()).all()
         assert err <= (2e-2 if y_dtype == torch.bfloat16 else 4e-3) * max(want.abs().max().item(), 1.0), err
+
+
+HALO_CASES = [
+    # n, h, w, c, k, block_n | ring<<16, epilogue
+    (2, 16, 16, 64, 64, 0, "affine_relu"),
+    (3, 32, 32, 128, 128, 128 | (3 << 16), "affine_res_relu"),
+    (2, 16, 8, 256, 256, 256 | (2 << 16), "raw"),
+    (1, 64, 64, 64, 64, 64 | (6 << 16), "affine_relu"),
+    (2, 32, 16, 128, 256, 128, "affine_res_relu"),
+]
+
+
+@pytest.mark.parametrize("half", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", HALO_CASES, ids=[str(c) for c in HALO_CASES])
+def test_conv3x3_halo_matches_reference(case, half):
+    """TMA-halo 3x3 kernel (nine shifted descriptors into one shared-memory tile) vs the fp32
+    reference conv; image borders exercise the TMA zero fill = padding."""
+    n, h, w, c, k, code, epi = case
+    g = torch.Generator(device="cpu").manual_seed(sum(case[:5]))
+    x = torch.randn(n, h, w, c, generator=g).to(DEV).to(half)
+    wt = (torch.randn(k, 3, 3, c, generator=g) * (2.0 / (9 * c)) ** 0.5).to(DEV).to(half)
+    scale = shift = res = None
+    if "affine" in epi:
+        scale = (torch.rand(k, generator=g) + 0.5).to(DEV)
+        shift = torch.randn(k, generator=g).to(DEV) * 0.1
+    if "res" in epi:
+        res = torch.randn(n, h, w, k, generator=g).to(DEV).to(half)
+    relu = "relu" in epi
+    want = _ref_conv(x, wt, scale, shift, res, 1, 1, relu)
+    for y_dtype in (half, torch.float32):
+        if res is not None and y_dtype == torch.float32:
+            continue
+        y = torch.full((n, h, w, k), float("nan"), device=DEV, dtype=y_dtype)
+        C.vlnce_conv3x3_halo(ptr(x), ptr(wt), lib.code(x), ptr(scale), ptr(shift), ptr(res), ptr(y), lib.code(y),
+                             n, h, w, c, k, int(relu), code, lib.stream())
+        torch.cuda.synchronize()
+        tol = {torch.bfloat16: 2e-2, torch.float16: 3e-3, torch.float32: 2e-3}[y_dtype]
+        err = (y.float() - want).abs().max().item()
+        assert torch.isfinite(y.float()).all(), f"non-finite output ({y_dtype})"
+        assert err <= tol * max(want.abs().max().item(), 1.0), f"{case} {y_dtype}: max err {err}"
