@@ -69,6 +69,15 @@ int vlnce_conv2d_stem_rgb(const void* x, int x_dtype, const void* w, int ab_dtyp
                           const float* shift, void* y, int y_dtype, int N, int H, int W, int K, int relu,
                           int block_n, cudaStream_t stream);
 
+/* Persistent, fully TMA-fed tiles for stride-1 convolutions (R = 1: 1x1 pad 0 over the [M,C] row
+ * matrix; R = 3: 3x3 pad 1 with halo boxes, needs H % 16 == 0 and W % 8 == 0): one CTA per SM walks a
+ * static tile schedule, the epilogue of tile i-1 overlaps the accumulation of tile i (two TMEM
+ * accumulators).  C % 64 == 0, K % 64 == 0; same epilogue contract as vlnce_conv2d_bf16.
+ * block_n: 0 = auto, else width (64/128/256) | weight-ring depth << 16. */
+int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
+                   const void* residual, void* y, int y_dtype, int N, int H, int W, int C, int K, int R,
+                   int relu, int block_n, cudaStream_t stream);
+
 /* 3x3 stride-1 pad-1 conv with TMA halo loads (one (16+2)x(8+2)-pixel box per 64-channel chunk,
  * nine shifted UMMA descriptors = the nine taps): same epilogue contract as vlnce_conv2d_bf16.
  * Needs H % 16 == 0, W % 8 == 0, C % 64 == 0, K % 64 == 0.  block_n: 0 = auto, else width

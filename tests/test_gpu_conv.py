@@ -159,3 +159,45 @@ def test_conv3x3_halo_matches_reference(case, half):
         err = (y.float() - want).abs().max().item()
         assert torch.isfinite(y.float()).all(), f"non-finite output ({y_dtype})"
         assert err <= tol * max(want.abs().max().item(), 1.0), f"{case} {y_dtype}: max err {err}"
+
+
+TMA_CASES = [
+    # n, h, w, c, k, R, block_n, epilogue   (grids larger than 148 tiles exercise the persistent loop)
+    (2, 16, 16, 64, 64, 1, 0, "affine_relu"),
+    (3, 12, 12, 128, 256, 1, 128, "affine_res_relu"),      # rows mode, ragged last tile (M = 432)
+    (40, 16, 16, 256, 128, 1, 128, "affine_res_relu"),     # 80 m-tiles x 1 = persistent, multi-chunk
+    (64, 16, 16, 64, 256, 1, 64, "raw"),                   # 128 m-tiles x 4 n-tiles = 512 tiles on 148 CTAs
+    (2, 16, 16, 64, 64, 3, 0, "affine_relu"),
+    (3, 32, 32, 128, 128, 3, 128, "affine_res_relu"),
+    (24, 32, 16, 64, 128, 3, 64, "affine_res_relu"),       # 192 patches x 2 n-tiles, persistent halo
+    (2, 16, 8, 256, 256, 3, 256, "raw"),
+]
+
+
+@pytest.mark.parametrize("half", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", TMA_CASES, ids=[str(c) for c in TMA_CASES])
+def test_conv_tma_persistent_matches_reference(case, half):
+    """Persistent TMA-fed kernel (overlapped epilogue, two TMEM accumulators) vs the reference conv."""
+    n, h, w, c, k, r, code, epi = case
+    g = torch.Generator(device="cpu").manual_seed(sum(case[:6]))
+    x = torch.randn(n, h, w, c, generator=g).to(DEV).to(half)
+    wt = (torch.randn(k, r, r, c, generator=g) * (2.0 / (r * r * c)) ** 0.5).to(DEV).to(half)
+    scale = shift = res = None
+    if "affine" in epi:
+        scale = (torch.rand(k, generator=g) + 0.5).to(DEV)
+        shift = torch.randn(k, generator=g).to(DEV) * 0.1
+    if "res" in epi:
+        res = torch.randn(n, h, w, k, generator=g).to(DEV).to(half)
+    relu = "relu" in epi
+    want = _ref_conv(x, wt, scale, shift, res, 1, r // 2, relu)
+    for y_dtype in (half, torch.float32):
+        if res is not None and y_dtype == torch.float32:
+            continue
+        y = torch.full((n, h, w, k), float("nan"), device=DEV, dtype=y_dtype)
+        C.vlnce_conv_tma(ptr(x), ptr(wt), lib.code(x), ptr(scale), ptr(shift), ptr(res), ptr(y), lib.code(y),
+                         n, h, w, c, k, r, int(relu), code, lib.stream())
+        torch.cuda.synchronize()
+        tol = {torch.bfloat16: 2e-2, torch.float16: 3e-3, torch.float32: 2e-3}[y_dtype]
+        err = (y.float() - want).abs().max().item()
+        assert torch.isfinite(y.float()).all(), f"non-finite output ({y_dtype})"
+        assert err <= tol * max(want.abs().max().item(), 1.0), f"{case} {y_dtype}: max err {err}"

@@ -24,7 +24,7 @@ def test_act_launch_sequence(name, precision):
         action, h_out = pol.act(obs, h, prev, masks, deterministic=True)
     assert action.shape == (case["n"], 1) and action.dtype == torch.int64
     assert h_out.shape == h.shape
-    n_conv = sum(c.startswith("vlnce_conv2d") for c in rec.calls)
+    n_conv = sum(c.startswith("vlnce_conv") for c in rec.calls)
     assert n_conv == 53 + 54, n_conv  # torchvision ResNet-50 + DD-PPO ResNet-50 & compression
     assert rec.calls.count("vlnce_attn_pool_fwd") == 3
     assert rec.calls.count("vlnce_lstm_seq_fwd") == 1
@@ -77,4 +77,4 @@ def test_seq2seq_act_launch_sequence_and_keys():
     with lib.dry_run() as rec:
         action, h_out = pol.act(obs, h, prev, masks, deterministic=True)
     assert action.shape == (2, 1) and h_out.shape == (2, 1, 512)
-    assert sum(c.startswith("vlnce_conv2d") for c in rec.calls) == 107
+    assert sum(c.startswith("vlnce_conv") for c in rec.calls) == 107

@@ -341,6 +341,9 @@ extern "C" int vlnce_conv3x3_halo(const void* x, const void* w, int ab_dtype, co
   int bn = block_n & 0xffff;
   if (bn == 0) bn = (K % 256 == 0) ? 256 : (K % 128 == 0 ? 128 : 64);
   VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && K % bn == 0, "conv3x3_halo: block_n=%d vs K=%d", bn, K);
+  // fp32 staging of a 128 x 256 tile (128 KB) does not fit beside the rings: narrow the tile
+  while (bn > 64 && kAStages * A_BYTES + 2 * bn * 128 + 2048 + 128 * bn * (y_dtype == VLNCE_F32 ? 4 : 2) > kSmemBudget)
+    bn /= 2;
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("conv3x3_halo: cuTensorMapEncodeTiled unavailable");

@@ -1,0 +1,496 @@
+// Persistent, fully TMA-fed convolution tiles on tcgen05 — the main conv engine for every
+// stride-1 layer of the two ResNet trunks:
+//
+//   mode ROWS  1x1 stride-1 conv: the NHWC activation is a row-major [M, C] matrix; a tile is
+//              128 consecutive pixels x BLOCK_N filters, A tiles are 2-D TMA boxes.
+//   mode HALO  3x3 stride-1 pad-1 conv: a tile is a 16 x 8 pixel patch; per 64-channel chunk ONE
+//              4-D TMA box loads the (16+2) x (8+2) halo (image borders arrive as zeros) and the
+//              nine taps are nine shifted UMMA descriptors into it (see conv3x3_halo.cu).
+//
+// Persistent CTAs (one per SM) walk a static round-robin tile schedule.  Three roles run
+// concurrently and never wait for each other's whole tile:
+//
+//   warp 5     TMA producer: activation ring (requested one channel chunk ahead, across tile
+//              boundaries), weight ring, residual tile prefetch into the staging buffer.
+//   warp 4     MMA issuer: accumulates tile i into TMEM buffer i&1 (2 x BLOCK_N columns allocated).
+//   warps 0-3  epilogue of tile i-1 WHILE tile i is being accumulated: tcgen05.ld, scale/shift,
+//              residual, ReLU, swizzled staging (double buffered when it fits), TMA store.
+//
+// Barrier protocol (all mbarriers, phases tracked per role): a_full/a_empty, b_full/b_empty rings;
+// acc_full[2] (MMA -> epilogue, tcgen05.commit), acc_empty[2] (epilogue -> MMA, 128 arrivals after the
+// last tcgen05.ld of the tile); res_full[s] (residual landed in staging s); stg_free[s] (the TMA
+// store that last read staging s has finished reading it).
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace vlnce {
+namespace {
+
+using namespace ptx;
+
+constexpr int TH = 16, TW = 8;
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kMaxA = 4, kMaxB = 8;
+
+struct TmaConvParams {
+  const float* scale;
+  const float* shift;
+  int mode;        // 0 rows (1x1), 1 halo (3x3)
+  int M;           // rows mode: N*H*W
+  int N, H, W, C, K;
+  int c_chunks, n_tiles, m_tiles, tiles_x, tiles_y;
+  int taps;        // 1 | 9
+  int halo_w;      // 8 (rows mode: plain 8-row groups) | 10
+  int a_bytes;     // ring slot size (1024-multiple), a_tx = bytes the TMA delivers
+  int a_tx;
+  int a_stages, b_stages, stg_bufs;
+  int relu, y_fp32, ab_half, has_res;
+};
+
+__device__ __forceinline__ void tma_store_4d_(const void* tmap, uint32_t src_smem, int32_t c0, int32_t c1, int32_t c2,
+                                              int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   (uint64_t)tmap),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct Tile {
+  int n0;            // first filter
+  int m0;            // rows mode: first pixel row
+  int x0, y0, img;   // halo mode: patch origin
+};
+
+__device__ __forceinline__ Tile decode_tile(const TmaConvParams& p, int t, int block_n) {
+  Tile ti;
+  const int n_tile = t % p.n_tiles;
+  int m = t / p.n_tiles;
+  ti.n0 = n_tile * block_n;
+  ti.m0 = m * 128;
+  ti.x0 = (m % p.tiles_x) * TW;
+  m /= p.tiles_x;
+  ti.y0 = (m % p.tiles_y) * TH;
+  ti.img = m / p.tiles_y;
+  return ti;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_res,
+                const TmaConvParams p) {
+  constexpr int B_BYTES = BLOCK_N * 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const uint32_t smem_a0 = smem_u32(smem);
+  const uint32_t smem_b0 = smem_a0 + p.a_stages * p.a_bytes;
+  uint8_t* bar_base = smem + p.a_stages * p.a_bytes + p.b_stages * B_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* a_empty = a_full + kMaxA;
+  uint64_t* b_full = a_empty + kMaxA;
+  uint64_t* b_empty = b_full + kMaxB;
+  uint64_t* acc_full = b_empty + kMaxB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* res_full = acc_empty + 2;
+  uint64_t* stg_free = res_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
+  const uint32_t stg_bytes = 128u * BLOCK_N * (p.y_fp32 ? 4u : 2u);
+  const uint32_t stage_out = smem_b0 + p.b_stages * B_BYTES + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 5 * 32) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 128);
+      mbar_init(&res_full[s], 1);
+      mbar_init(&stg_free[s], 1);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_y);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0 && my_tiles > 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      const int steps = my_tiles * p.c_chunks;
+      auto load_a = [&](int j) {  // activation tile of chunk-step j (tile j / c_chunks, chunk j % c_chunks)
+        const Tile ti = decode_tile(p, blockIdx.x + (j / p.c_chunks) * gridDim.x, BLOCK_N);
+        const int cc = j % p.c_chunks;
+        mbar_wait(&a_empty[as], aph ^ 1, 21);
+        mbar_arrive_expect_tx(&a_full[as], p.a_tx);
+        if (p.mode == 0) tma_load_2d(smem_a0 + as * p.a_bytes, &tmap_x, &a_full[as], cc * 64, ti.m0);
+        else tma_load_4d(smem_a0 + as * p.a_bytes, &tmap_x, &a_full[as], cc * 64, ti.x0 - 1, ti.y0 - 1, ti.img);
+        if (++as == p.a_stages) { as = 0; aph ^= 1; }
+      };
+      load_a(0);
+      for (int j = 0; j < steps; ++j) {
+        if (j + 1 < steps) load_a(j + 1);  // one chunk ahead, across tile boundaries
+        const int it = j / p.c_chunks, cc = j % p.c_chunks;
+        const Tile ti = decode_tile(p, blockIdx.x + it * gridDim.x, BLOCK_N);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          mbar_wait(&b_empty[bs], bph ^ 1, 22);
+          mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
+          tma_load_2d(smem_b0 + bs * B_BYTES, &tmap_w, &b_full[bs], tap * p.C + cc * 64, ti.n0);
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        }
+        if (p.has_res && cc == p.c_chunks - 1) {
+          // residual tile of this tile -> its staging buffer (free once the store that last used it
+          // has been read out)
+          const int sb = it % p.stg_bufs;
+          const uint32_t v = (uint32_t)(it / p.stg_bufs);
+          mbar_wait(&stg_free[sb], (v & 1) ^ 1, 23);
+          mbar_arrive_expect_tx(&res_full[sb], 128 * BLOCK_N * 2);
+          for (int b = 0; b < BLOCK_N / 64; ++b) {
+            const uint32_t dst = stage_out + sb * stg_bytes + (uint32_t)b * (128 * 128);
+            if (p.mode == 0) tma_load_2d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.m0);
+            else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.x0, ti.y0, ti.img);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_f16(128, BLOCK_N, p.ab_half ? 0u : 1u);
+    const uint32_t sbo = (uint32_t)p.halo_w * 128u;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int buf = it & 1;
+      const uint32_t u = (uint32_t)(it >> 1);
+      mbar_wait(&acc_empty[buf], (u & 1) ^ 1, 24);  // epilogue has drained this accumulator
+      tc_fence_after_sync();
+      const uint32_t tmem_acc = tmem_base + buf * BLOCK_N;
+      for (int cc = 0; cc < p.c_chunks; ++cc) {
+        mbar_wait(&a_full[as], aph, 25);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          mbar_wait(&b_full[bs], bph, 26);
+          tc_fence_after_sync();
+          if (lane == 0) {
+            const int r = tap / 3, s = tap - 3 * r;
+            const uint64_t adesc = desc_sbo(smem_a0 + as * p.a_bytes + (r * p.halo_w + s) * 128, sbo);
+            const uint64_t bdesc = make_smem_desc(smem_b0 + bs * B_BYTES, 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((cc | tap | k) != 0));
+            umma_commit(&b_empty[bs]);
+            if (tap == p.taps - 1) umma_commit(&a_empty[as]);
+          }
+          __syncwarp();
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        }
+        if (++as == p.a_stages) { as = 0; aph ^= 1; }
+      }
+      if (lane == 0) umma_commit(&acc_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 0-3)
+    const int row = warp * 32 + lane;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int buf = it & 1;
+      const uint32_t u = (uint32_t)(it >> 1);
+      const int sb = it % p.stg_bufs;
+      const uint32_t v = (uint32_t)(it / p.stg_bufs);
+      const Tile ti = decode_tile(p, blockIdx.x + it * gridDim.x, BLOCK_N);
+      const uint32_t stg = stage_out + sb * stg_bytes;
+      mbar_wait(&acc_full[buf], u & 1, 27);
+      tc_fence_after_sync();
+      if (p.has_res) mbar_wait(&res_full[sb], v & 1, 28);   // residual landed (implies staging free)
+      else mbar_wait(&stg_free[sb], (v & 1) ^ 1, 29);       // previous store has left the staging buffer
+      const uint32_t t_row = tmem_base + buf * BLOCK_N + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+        uint32_t vv[32];
+        tmem_ld_32x32(t_row + cb * 32, vv);
+        tmem_ld_wait();
+        if (cb == BLOCK_N / 32 - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
+        }
+        const int col0 = ti.n0 + cb * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vv[j]);
+        if (p.scale != nullptr) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + j4);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + j4);
+            f[j4 * 4 + 0] = fmaf(f[j4 * 4 + 0], sc.x, sh.x);
+            f[j4 * 4 + 1] = fmaf(f[j4 * 4 + 1], sc.y, sh.y);
+            f[j4 * 4 + 2] = fmaf(f[j4 * 4 + 2], sc.z, sh.z);
+            f[j4 * 4 + 3] = fmaf(f[j4 * 4 + 3], sc.w, sh.w);
+          }
+        }
+        if (p.y_fp32) {
+          const uint32_t box = stg + (uint32_t)cb * (128 * 128) + (uint32_t)row * 128;
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const uint32_t addr = box + (uint32_t)((q4 ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f[q4 * 4]), "f"(f[q4 * 4 + 1]),
+                         "f"(f[q4 * 4 + 2]), "f"(f[q4 * 4 + 3])
+                         : "memory");
+          }
+        } else {
+          const uint32_t box = stg + (uint32_t)(cb >> 1) * (128 * 128) + (uint32_t)row * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t addr = box + (uint32_t)((((cb & 1) * 4 + q4) ^ (row & 7)) << 4);
+            if (p.has_res) {
+              uint32_t w0, w1, w2, w3;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                           : "r"(addr)
+                           : "memory");
+              const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (p.ab_half) {
+                  const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                  f[q4 * 8 + e * 2 + 0] += h2.x;
+                  f[q4 * 8 + e * 2 + 1] += h2.y;
+                } else {
+                  f[q4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
+                  f[q4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                }
+              }
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = f[q4 * 8 + e * 2], b = f[q4 * 8 + e * 2 + 1];
+              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              if (p.ab_half) {
+                __half2 h2 = __floats2half2_rn(a, b);
+                o[e] = *reinterpret_cast<uint32_t*>(&h2);
+              } else {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                o[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                         "r"(o[3])
+                         : "memory");
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      named_barrier_sync(1, 128);
+      if (threadIdx.x == 0) {
+        const int boxes = p.y_fp32 ? BLOCK_N / 32 : BLOCK_N / 64;
+        const int cols = p.y_fp32 ? 32 : 64;
+        for (int b = 0; b < boxes; ++b) {
+          const uint32_t src = stg + (uint32_t)b * (128 * 128);
+          if (p.mode == 0) tma_store_2d(&tmap_y, src, ti.n0 + b * cols, ti.m0);
+          else tma_store_4d_(&tmap_y, src, ti.n0 + b * cols, ti.x0, ti.y0, ti.img);
+        }
+        tma_store_commit();
+        // release the staging buffer whose store has now been read out of shared memory
+        if (p.stg_bufs == 2) {
+          tma_store_wait_read_n<1>();
+          if (it >= 1) mbar_arrive(&stg_free[(it - 1) & 1]);
+        } else {
+          tma_store_wait_read_n<0>();
+          mbar_arrive(&stg_free[0]);
+        }
+      }
+    }
+    if (threadIdx.x == 0) tma_store_wait_read_n<0>();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_enc() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+int map_nd(EncodeTiledFn enc, CUtensorMap* m, const void* base, CUtensorMapDataType dt, int rank,
+           const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box, const char* what) {
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, dt, rank, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tma: cuTensorMapEncodeTiled(%s) failed (%d)", what, (int)r);
+    return VLNCE_ERR_CUDA_BASE + 1;
+  }
+  return VLNCE_OK;
+}
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr,
+           TmaConvParams& p, int b_stages_req, cudaStream_t stream) {
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBudget);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(conv_tma)");
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+    configured = true;
+  }
+  const int stg = 128 * BLOCK_N * (p.y_fp32 ? 4 : 2);
+  const int B_BYTES = BLOCK_N * 128;
+  auto bytes = [&](int as, int bs, int sbufs) { return as * p.a_bytes + bs * B_BYTES + 1024 + sbufs * stg + 1024; };
+  // preference order: double staging, deep rings; shrink until it fits
+  int as = p.mode == 1 ? 3 : 4, bs = b_stages_req > 0 ? b_stages_req : (p.mode == 1 ? 4 : 4), sbufs = 2;
+  if (bs > kMaxB) bs = kMaxB;
+  while (bytes(as, bs, sbufs) > kSmemBudget) {
+    if (bs > 3) --bs;
+    else if (as > 2) --as;
+    else if (sbufs > 1) --sbufs;
+    else if (bs > 2) --bs;
+    else {
+      set_error("conv_tma: tile does not fit shared memory (BLOCK_N=%d)", BLOCK_N);
+      return VLNCE_ERR_INVALID_ARGUMENT;
+    }
+  }
+  p.a_stages = as; p.b_stages = bs; p.stg_bufs = sbufs;
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  conv_tma_kernel<BLOCK_N><<<grid, kThreads, bytes(as, bs, sbufs), stream>>>(tx, tw, ty, tr, p);
+  VLNCE_LAUNCH_CHECK("conv_tma_kernel");
+  return VLNCE_OK;
+}
+
+}  // namespace
+}  // namespace vlnce
+
+using namespace vlnce;
+
+// R = 1 (1x1, pad 0) or R = 3 (3x3, pad 1); stride 1.
+extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
+                              const void* residual, void* y, int y_dtype, int N, int H, int W, int C, int K, int R,
+                              int relu, int block_n, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0, "conv_tma: null tensor / empty shape");
+  VLNCE_CHECK_ARG(R == 1 || R == 3, "conv_tma: only 1x1 and 3x3 stride-1 convolutions");
+  VLNCE_CHECK_ARG(C % 64 == 0 && K % 64 == 0, "conv_tma: C and K must be multiples of 64");
+  VLNCE_CHECK_ARG(R == 1 || (H % TH == 0 && W % TW == 0), "conv_tma: 3x3 needs H %% 16 == 0 and W %% 8 == 0");
+  VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_tma: scale/shift must come together");
+  VLNCE_CHECK_ARG(ab_dtype == VLNCE_BF16 || ab_dtype == VLNCE_F16, "conv_tma: operand dtype");
+  VLNCE_CHECK_ARG(y_dtype == ab_dtype || y_dtype == VLNCE_F32, "conv_tma: y dtype");
+  VLNCE_CHECK_ARG(!(residual && y_dtype == VLNCE_F32), "conv_tma: residual needs a 16-bit output");
+  VLNCE_CHECK_ARG((long long)N * H * W < (1ll << 31), "conv_tma: too many pixels");
+  const int b_stages = (block_n >> 16) & 0xf;
+  int bn = block_n & 0xffff;
+  if (bn == 0) bn = (K % 128 == 0) ? 128 : 64;
+  VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && K % bn == 0, "conv_tma: block_n=%d vs K=%d", bn, K);
+  EncodeTiledFn enc = get_enc();
+  if (!enc) {
+    set_error("conv_tma: cuTensorMapEncodeTiled unavailable");
+    return VLNCE_ERR_NO_DRIVER;
+  }
+  const CUtensorMapDataType dt16 = ab_dtype == VLNCE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const bool f32 = y_dtype == VLNCE_F32;
+  const long long M = (long long)N * H * W;
+  CUtensorMap tx, tw, ty, tr;
+  int rc;
+  {  // weights [K, R*R*C]
+    const cuuint64_t gd[2] = {(cuuint64_t)R * R * C, (cuuint64_t)K};
+    const cuuint64_t gs[1] = {(cuuint64_t)R * R * C * 2};
+    const cuuint32_t bx[2] = {64, (cuuint32_t)bn};
+    if ((rc = map_nd(enc, &tw, w, dt16, 2, gd, gs, bx, "weights")) != VLNCE_OK) return rc;
+  }
+  TmaConvParams p;
+  if (R == 1) {
+    const cuuint64_t gd[2] = {(cuuint64_t)C, (cuuint64_t)M};
+    const cuuint64_t gs[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t bx[2] = {64, 128};
+    if ((rc = map_nd(enc, &tx, x, dt16, 2, gd, gs, bx, "activation")) != VLNCE_OK) return rc;
+    const cuuint64_t yd[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t ys[1] = {(cuuint64_t)K * (f32 ? 4 : 2)};
+    const cuuint32_t yb[2] = {(cuuint32_t)(f32 ? 32 : 64), 128};
+    if ((rc = map_nd(enc, &ty, y, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16, 2, yd, ys, yb, "output")) != VLNCE_OK)
+      return rc;
+    tr = ty;
+    if (residual) {
+      const cuuint64_t rs[1] = {(cuuint64_t)K * 2};
+      const cuuint32_t rb[2] = {64, 128};
+      if ((rc = map_nd(enc, &tr, residual, dt16, 2, yd, rs, rb, "residual")) != VLNCE_OK) return rc;
+    }
+    p.mode = 0; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024;
+    p.m_tiles = cdiv(M, 128); p.tiles_x = 1; p.tiles_y = 1;
+  } else {
+    const cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t gs[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t bx[4] = {64, TW + 2, TH + 2, 1};
+    if ((rc = map_nd(enc, &tx, x, dt16, 4, gd, gs, bx, "halo")) != VLNCE_OK) return rc;
+    const int esz = f32 ? 4 : 2;
+    const cuuint64_t yd[4] = {(cuuint64_t)K, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t ys[3] = {(cuuint64_t)K * esz, (cuuint64_t)W * K * esz, (cuuint64_t)H * W * K * esz};
+    const cuuint32_t yb[4] = {(cuuint32_t)(f32 ? 32 : 64), TW, TH, 1};
+    if ((rc = map_nd(enc, &ty, y, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16, 4, yd, ys, yb, "output")) != VLNCE_OK)
+      return rc;
+    tr = ty;
+    if (residual) {
+      const cuuint64_t rs[3] = {(cuuint64_t)K * 2, (cuuint64_t)W * K * 2, (cuuint64_t)H * W * K * 2};
+      const cuuint32_t rb[4] = {64, TW, TH, 1};
+      if ((rc = map_nd(enc, &tr, residual, dt16, 4, yd, rs, rb, "residual")) != VLNCE_OK) return rc;
+    }
+    p.mode = 1; p.taps = 9; p.halo_w = TW + 2; p.a_bytes = 23 * 1024; p.a_tx = (TW + 2) * (TH + 2) * 128;
+    p.tiles_x = W / TW; p.tiles_y = H / TH; p.m_tiles = N * p.tiles_x * p.tiles_y;
+  }
+  p.scale = scale; p.shift = shift;
+  p.M = (int)M; p.N = N; p.H = H; p.W = W; p.C = C; p.K = K;
+  p.c_chunks = C / 64;
+  p.n_tiles = K / bn;
+  p.relu = relu; p.y_fp32 = f32; p.ab_half = (ab_dtype == VLNCE_F16); p.has_res = residual != nullptr;
+  p.a_stages = p.b_stages = p.stg_bufs = 0;
+  if (bn == 256) return launch<256>(tx, tw, ty, tr, p, b_stages, stream);
+  if (bn == 128) return launch<128>(tx, tw, ty, tr, p, b_stages, stream);
+  return launch<64>(tx, tw, ty, tr, p, b_stages, stream);
+}

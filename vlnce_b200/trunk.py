@@ -51,7 +51,9 @@ import os as _os
 AUTOTUNE = _os.environ.get("VLNCE_AUTOTUNE", "1") != "0"
 FUSED_STEM = _os.environ.get("VLNCE_FUSED_STEM", "1") != "0"
 HALO_3X3 = _os.environ.get("VLNCE_HALO_3X3", "1") != "0"
+PERSISTENT = _os.environ.get("VLNCE_PERSISTENT", "1") != "0"
 HALO = 1 << 24  # tuning-code flag: TMA-halo 3x3 kernel instead of the generic tile
+TMAP = 1 << 25  # tuning-code flag: persistent TMA-fed kernel (1x1 rows / 3x3 halo, overlapped epilogue)
 # Tuned (tile width | ring depth << 16) per conv geometry, optionally persisted so that later
 # processes on the same box (profilers, the second bench leg) skip the timing sweep.
 _TUNE_CACHE_PATH = _os.environ.get("VLNCE_AUTOTUNE_CACHE", "")
@@ -166,6 +168,10 @@ class ConvTrunk:
                 if stem_rgb:
                     C.vlnce_conv2d_stem_rgb(ptr(x), lib.code(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift),
                                             ptr(y), lib.code(y), n, h, w, cv.K, int(relu), code, st)
+                elif code & TMAP:
+                    C.vlnce_conv_tma(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y),
+                                     lib.code(y), geom[0], geom[1], geom[2], geom[3], cv.K, geom[5], int(relu),
+                                     code & 0xfffff, st)
                 elif code & HALO:
                     C.vlnce_conv3x3_halo(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
                                          ptr(y), lib.code(y), n, h, w, c, cv.K, int(relu), code & ~HALO, st)
@@ -173,21 +179,25 @@ class ConvTrunk:
                     C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
                                         ptr(y), lib.code(y), *geom, int(relu), code, st)
 
+            c_in = geom[3] if not stem_rgb else 0
+            tma_ok = (PERSISTENT and not stem_rgb and c_in % 64 == 0 and cv.K % 64 == 0 and geom[7:] in ((1, 0), (1, 1))
+                      and ((geom[5] == 1 and geom[8] == 0)
+                           or (geom[5] == 3 and geom[8] == 1 and geom[1] % 16 == 0 and geom[2] % 8 == 0)))
             halo_ok = (HALO_3X3 and not stem_rgb and gemm_c is None and cv.R == 3 and cv.S == 3 and cv.stride == 1
                        and cv.pad == 1 and c % 64 == 0 and cv.K % 64 == 0 and h % 16 == 0 and w % 8 == 0)
             key = (geom, lib.code(y), residual is not None)
             bn = cv.block_n.get(key)
             if bn is None:
-                skey = repr((key, lib.code(cv.w), scale is not None, relu, halo_ok))
+                skey = repr((key, lib.code(cv.w), scale is not None, relu, halo_ok, tma_ok))
                 if skey in _TUNE_CACHE:
                     bn = int(_TUNE_CACHE[skey])
                 else:
                     tune = AUTOTUNE and x.is_cuda and not torch.cuda.is_current_stream_capturing()
                     if tune:
-                        bn = self._tune(launch, cv.K, halo_ok)
+                        bn = self._tune(launch, cv.K, halo_ok, tma_ok)
                         _tune_cache_put(skey, bn)
                     else:
-                        bn = (HALO if halo_ok else 0)
+                        bn = TMAP if tma_ok else (HALO if halo_ok else 0)
                 cv.block_n[key] = bn
             launch(bn)
         else:
@@ -196,7 +206,7 @@ class ConvTrunk:
                                cv.stride, cv.pad, int(relu), st)
 
     @staticmethod
-    def _tune(launch, K, halo_ok=False):
+    def _tune(launch, K, halo_ok=False, tma_ok=False):
         """Pick kernel variant, output-tile width and ring depth empirically (once per layer
         shape): CUDA-event timing of the legal candidates on the real operands; the winner is
         cached on the layer."""
@@ -204,6 +214,8 @@ class ConvTrunk:
         cands = [bn | (st << 16) for bn in widths for st in (1, 2, 4)]
         if halo_ok:
             cands += [HALO | bn | (st << 16) for bn in widths for st in (3, 6)]
+        if tma_ok:
+            cands += [TMAP | bn | (st << 16) for bn in widths for st in (4,)]
         best, best_t = 0, float("inf")
         for _ in range(12):  # bring the clocks up before timing anything
             launch(cands[-1])
