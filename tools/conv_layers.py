@@ -97,6 +97,22 @@ def main():
                     us = a.elapsed_time(b) * 1e3 / args.reps
                     row["bn"][f"halo{bn}r{ring}"] = {"us": round(us, 1), "tflops": round(flops / us / 1e6, 1),
                                                     "min_traffic_gbs": round(bytes_min / us / 1e3, 0)}
+        if stride == 1 and r in (1, 3) and cin % 64 == 0 and cout % 64 == 0 and args.bn < 0 and (r == 1 or hw % 16 == 0):
+            for bn in [b for b in (64, 128, 256) if cout % b == 0]:
+                def launch():
+                    C.vlnce_conv_tma(ptr(x), ptr(w), lib.BF16, ptr(scale), ptr(shift), ptr(resid), ptr(y), lib.BF16,
+                                     geom[0], geom[1], geom[2], geom[3], cout, r, 1, bn | (4 << 16), lib.stream())
+                for _ in range(3):
+                    launch()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(args.reps):
+                    launch()
+                b.record()
+                b.synchronize()
+                us = a.elapsed_time(b) * 1e3 / args.reps
+                row["bn"][f"P{bn}"] = {"us": round(us, 1), "tflops": round(flops / us / 1e6, 1),
+                                      "min_traffic_gbs": round(bytes_min / us / 1e3, 0)}
         best = min(row["bn"].items(), key=lambda kv: kv[1]["us"])
         row["best_bn"], row["best_us"] = best[0], best[1]["us"]
         total_best += best[1]["us"] * count

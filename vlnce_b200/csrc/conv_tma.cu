@@ -429,6 +429,10 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
   int bn = block_n & 0xffff;
   if (bn == 0) bn = (K % 128 == 0) ? 128 : 64;
   VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && K % bn == 0, "conv_tma: block_n=%d vs K=%d", bn, K);
+  {  // the smallest configuration (2+2 ring slots, one staging buffer) must fit: narrow wide fp32 tiles
+    const int a_b = R == 1 ? 16 * 1024 : 23 * 1024;
+    while (bn > 64 && 2 * a_b + 2 * bn * 128 + 2048 + 128 * bn * (y_dtype == VLNCE_F32 ? 4 : 2) > kSmemBudget) bn /= 2;
+  }
   EncodeTiledFn enc = get_enc();
   if (!enc) {
     set_error("conv_tma: cuTensorMapEncodeTiled unavailable");
