@@ -114,6 +114,13 @@ int vlnce_maxpool3x3s2(const void* x, void* y, int dtype, int N, int H, int W, i
 int vlnce_groupnorm_stats(const void* x, int dtype, const float* gamma, const float* beta,
                           float* scale, float* shift, float* workspace, size_t workspace_bytes, int N,
                           int HW, int C, int groups, float eps, cudaStream_t stream);
+/* GroupNorm (+residual)(+ReLU) of the fp32 raw conv output in two launches: partial statistics,
+ * then finalize+normalise (each CTA rebuilds its image's scale/shift from the partials).
+ * scale/shift_scratch (N*C f32 each) are used only by the fallback path. */
+int vlnce_groupnorm_fused(const float* x, const float* gamma, const float* beta, const void* residual, void* y,
+                          int y_dtype, float* workspace, size_t workspace_bytes, float* scale_scratch,
+                          float* shift_scratch, int N, int HW, int C, int groups, float eps, int relu,
+                          cudaStream_t stream);
 /* Train-mode BatchNorm2d statistics over all N*HW rows: per-channel scale/shift
  * from batch mean / biased var; updates running_mean/var (momentum, unbiased var) in place. */
 int vlnce_batchnorm_train_stats(const void* x, int dtype, const float* gamma, const float* beta,

@@ -171,17 +171,50 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const int esz = p.stem == 1 ? 1 : 4;
         const int row_bytes = p.W * 3 * esz;                 // multiple of 16 (W % 128 == 0)
         const int x_off = (2 * q0 - 4) * 3 * esz;            // byte offset of the patch origin in a row
-        for (int r = 0; r < 7; ++r) {
-          const int ih = po * 2 - 3 + r;
-          uint8_t* prow = pb + r * PATCH_W * esz;
-          const bool row_ok = (unsigned)ih < (unsigned)p.H;
-          const uint8_t* grow = xb + ((size_t)(n_img * p.H + ih) * p.W) * 3 * esz;
-          // the patch spans bytes [x_off, x_off + PATCH_W*esz) of the row; 4-byte granules
-          for (int w4 = t; w4 < PATCH_W * esz / 4; w4 += kProducerThreads) {
-            const int gb = x_off + w4 * 4;
-            uint32_t v = 0;
-            if (row_ok && gb >= 0 && gb + 4 <= row_bytes) v = __ldg(reinterpret_cast<const uint32_t*>(grow + gb));
-            *reinterpret_cast<uint32_t*>(prow + w4 * 4) = v;
+        // 7 rows x 197 four-byte granules (788 B) per row, 2 granules per thread and row: all 14
+        // loads are issued before the first shared-memory store (one L2 round trip, not fourteen)
+        constexpr int G = PATCH_W / 4;  // granules per row for u8; f32 rows are 4x longer
+        if (esz == 1) {
+          uint32_t v[7][2];
+#pragma unroll
+          for (int r = 0; r < 7; ++r) {
+            const int ih = po * 2 - 3 + r;
+            const bool row_ok = (unsigned)ih < (unsigned)p.H;
+            const uint8_t* grow = xb + ((size_t)(n_img * p.H + ih) * p.W) * 3;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int w4 = t + h * kProducerThreads;
+              const int gb = x_off + w4 * 4;
+              v[r][h] = (row_ok && w4 < G && gb >= 0 && gb + 4 <= row_bytes)
+                            ? __ldg(reinterpret_cast<const uint32_t*>(grow + gb)) : 0u;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int w4 = t + h * kProducerThreads;
+              if (w4 < G) *reinterpret_cast<uint32_t*>(pb + r * PATCH_W + w4 * 4) = v[r][h];
+            }
+        } else {
+          for (int r = 0; r < 7; ++r) {
+            const int ih = po * 2 - 3 + r;
+            uint8_t* prow = pb + r * PATCH_W * 4;
+            const bool row_ok = (unsigned)ih < (unsigned)p.H;
+            const uint8_t* grow = xb + ((size_t)(n_img * p.H + ih) * p.W) * 3 * 4;
+            uint32_t v[7];
+#pragma unroll
+            for (int h = 0; h < 7; ++h) {  // 788 granules per f32 row: 7 per thread
+              const int w4 = t + h * kProducerThreads;
+              const int gb = x_off + w4 * 4;
+              v[h] = (row_ok && w4 < PATCH_W && gb >= 0 && gb + 4 <= row_bytes)
+                         ? __ldg(reinterpret_cast<const uint32_t*>(grow + gb)) : 0u;
+            }
+#pragma unroll
+            for (int h = 0; h < 7; ++h) {
+              const int w4 = t + h * kProducerThreads;
+              if (w4 < PATCH_W) *reinterpret_cast<uint32_t*>(prow + w4 * 4) = v[h];
+            }
           }
         }
         named_barrier_sync(2, kProducerThreads);

@@ -8,7 +8,7 @@
 namespace vlnce {
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TM = 64, TN = 64, TK = 32;
 
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
@@ -27,24 +27,49 @@ sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
   // split-K: blockIdx.z owns K range [kb, ke); partial sums go to partial[z][M][N]
   const int kb = blockIdx.z * k_per_split;
   const int ke = min(K, kb + k_per_split);
-  for (int k0 = kb; k0 < ke; k0 += TK) {
+  constexpr int LD = TM * TK / 256;  // 8 elements of each operand tile per thread
+  float ra[LD], rb[LD];
+  // global -> registers for the k-tile starting at k0 (issued one tile ahead of its use, so the
+  // L2 latency of tile i+1 hides behind the FMAs of tile i)
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = tid + i * 256;  // 1024 elements of the 64x16 A tile
+    for (int i = 0; i < LD; ++i) {
+      const int e = tid + i * 256;
       int mm, kk;
       if (a_kfast) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
       const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < ke) ? __ldg(A + gm * lda_m + gk * lda_k) : 0.f;
+      ra[i] = (gm < M && gk < ke) ? __ldg(A + gm * lda_m + gk * lda_k) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < LD; ++i) {
       const int e = tid + i * 256;
       int nn, kk;
       if (b_nfast) { nn = e % TN; kk = e / TN; } else { kk = e % TK; nn = e / TK; }
       const int gn = n0 + nn, gk = k0 + kk;
-      Bs[kk][nn] = (gn < N && gk < ke) ? __ldg(B + gk * ldb_k + gn * ldb_n) : 0.f;
+      rb[i] = (gn < N && gk < ke) ? __ldg(B + gk * ldb_k + gn * ldb_n) : 0.f;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < LD; ++i) {
+      const int e = tid + i * 256;
+      int mm, kk;
+      if (a_kfast) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
+      As[kk][mm] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LD; ++i) {
+      const int e = tid + i * 256;
+      int nn, kk;
+      if (b_nfast) { nn = e % TN; kk = e / TN; } else { kk = e % TK; nn = e / TK; }
+      Bs[kk][nn] = rb[i];
+    }
+  };
+  if (kb < ke) fetch(kb);
+  for (int k0 = kb; k0 < ke; k0 += TK) {
+    stash();
     __syncthreads();
+    if (k0 + TK < ke) fetch(k0 + TK);
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);

@@ -413,6 +413,62 @@ __global__ void affine_apply_kernel(const T* __restrict__ x, const float* __rest
   }
 }
 
+// GroupNorm finalize + apply in one pass: every CTA first rebuilds the per-channel scale/shift of
+// its image from the stage-1 partial sums (S x G pairs, fp64 combine), then normalises its slice
+// of rows: y = act(raw * scale[c] + shift[c] (+ residual)).  grid (N, slices).
+template <typename TO>
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, int S,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
+                const TO* __restrict__ residual, TO* __restrict__ y, int HW, int C, int relu) {
+  extern __shared__ float gn_sm[];
+  float* sc = gn_sm;
+  float* sh = gn_sm + C;
+  const int n = blockIdx.x;
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    double sum = 0.0, sq = 0.0;
+    for (int s = 0; s < S; ++s) {
+      const float* p = part + ((size_t)(n * S + s) * groups + g) * 2;
+      sum += p[0];
+      sq += p[1];
+    }
+    const double cnt = (double)HW * cpg;
+    const double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float a = rstd * gamma[c];
+    sc[c] = a;
+    sh[c] = beta[c] - (float)mean * a;
+  }
+  __syncthreads();
+  const int cv = C / 8;
+  const long long vec_per_img = (long long)HW * cv;
+  const long long per = (vec_per_img + gridDim.y - 1) / gridDim.y;
+  const long long v0 = per * blockIdx.y, v1 = min(vec_per_img, v0 + per);
+  for (long long v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+    const int c0 = (int)(v % cv) * 8;
+    const long long e0 = ((long long)n * HW) * C + v * 8;
+    float f[8];
+    load8<float>(x + e0, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[c0 + e], sh[c0 + e]);
+    if (residual != nullptr) {
+      float r[8];
+      load8<TO>(residual + e0, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += r[e];
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+    }
+    store8<TO>(y + e0, f);
+  }
+}
+
 // adaptive_avg_pool2d -> (O,O): bin i covers [floor(i*H/O), ceil((i+1)*H/O))
 template <typename T>
 __global__ void adaptive_avgpool_kernel(const T* __restrict__ x, float* __restrict__ y, int ldy,
@@ -601,7 +657,7 @@ extern "C" int vlnce_groupnorm_stats(const void* x, int dtype, const float* gamm
   const int c4n = C / 4;
   if (dtype == VLNCE_F32 && workspace != nullptr && C % 4 == 0 && c4n <= 256 && 256 % c4n == 0 &&
       (C / groups) % 2 == 0 && groups <= 64) {
-    int S = cdiv((long long)HW * C, 32768);  // ~128 KB of raw data per CTA
+    int S = cdiv((long long)HW * C, 4096);  // ~16 KB of raw data per CTA: enough CTAs to cover the SMs
     if (S > HW) S = HW;
     while (S > 1 && (size_t)N * S * groups * 2 * sizeof(float) > workspace_bytes) --S;
     if ((size_t)N * S * groups * 2 * sizeof(float) <= workspace_bytes) {
@@ -709,5 +765,49 @@ extern "C" int vlnce_nchw_to_positions(const float* x, float* y, int ldy, int N,
   dim3 grid(cdiv(C, 32), cdiv(P, 32), N), block(32, 8);
   nchw_to_positions_kernel<<<grid, block, 0, stream>>>(x, y, ldy, C, P);
   VLNCE_LAUNCH_CHECK("nchw_to_positions_kernel");
+  return VLNCE_OK;
+}
+
+
+// GroupNorm(+residual)(+ReLU) of fp32 raw conv output in two launches (partial statistics, then
+// finalize+apply); falls back to the three-kernel path when the layout preconditions fail.
+extern "C" int vlnce_groupnorm_fused(const float* x, const float* gamma, const float* beta, const void* residual,
+                                     void* y, int y_dtype, float* workspace, size_t workspace_bytes,
+                                     float* scale_scratch, float* shift_scratch, int N, int HW, int C, int groups,
+                                     float eps, int relu, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && gamma && beta && y && workspace && groups > 0 && C % groups == 0 && C % 8 == 0,
+                  "groupnorm_fused: bad arguments");
+  const int c4n = C / 4;
+  const bool fast = c4n <= 256 && 256 % c4n == 0 && (C / groups) % 2 == 0 && groups <= 64 &&
+                    (y_dtype == VLNCE_F16 || y_dtype == VLNCE_BF16 || y_dtype == VLNCE_F32);
+  if (!fast) {
+    int rc = vlnce_groupnorm_stats(x, VLNCE_F32, gamma, beta, scale_scratch, shift_scratch, workspace,
+                                   workspace_bytes, N, HW, C, groups, eps, stream);
+    if (rc != VLNCE_OK) return rc;
+    return vlnce_affine_apply(x, VLNCE_F32, scale_scratch, shift_scratch, C, residual, y, y_dtype, N, HW, C, relu,
+                              stream);
+  }
+  int S = cdiv((long long)HW * C, 4096);
+  if (S > HW) S = HW;
+  if (S > 64) S = 64;
+  while (S > 1 && (size_t)N * S * groups * 2 * sizeof(float) > workspace_bytes) --S;
+  VLNCE_CHECK_ARG((size_t)N * S * groups * 2 * sizeof(float) <= workspace_bytes, "groupnorm_fused: workspace too small");
+  gn_partial_kernel<<<dim3(N, S), 256, 0, stream>>>(x, workspace, HW, C, groups);
+  VLNCE_LAUNCH_CHECK("gn_partial_kernel");
+  int slices = cdiv((long long)HW * C, 16384);
+  if (slices > 32) slices = 32;
+  const size_t smem = sizeof(float) * 2 * C;
+  dim3 grid(N, slices);
+  if (y_dtype == VLNCE_F16)
+    gn_apply_kernel<__half><<<grid, 256, smem, stream>>>(x, workspace, S, gamma, beta, groups, eps,
+                                                         (const __half*)residual, (__half*)y, HW, C, relu);
+  else if (y_dtype == VLNCE_BF16)
+    gn_apply_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(x, workspace, S, gamma, beta, groups, eps,
+                                                                (const __nv_bfloat16*)residual, (__nv_bfloat16*)y,
+                                                                HW, C, relu);
+  else
+    gn_apply_kernel<float><<<grid, 256, smem, stream>>>(x, workspace, S, gamma, beta, groups, eps,
+                                                        (const float*)residual, (float*)y, HW, C, relu);
+  VLNCE_LAUNCH_CHECK("gn_apply_kernel");
   return VLNCE_OK;
 }

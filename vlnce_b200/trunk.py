@@ -376,11 +376,16 @@ class DepthTrunk(ConvTrunk):
         sc = self.pool.get("gn_scale", (n, cv.K), torch.float32)
         sh = self.pool.get("gn_shift", (n, cv.K), torch.float32)
         ws = self.pool.get("gn_ws", (1 << 20,), torch.float32)
-        C.vlnce_groupnorm_stats(ptr(raw), lib.code(raw), ptr(gn.weight), ptr(gn.bias), ptr(sc), ptr(sh), ptr(ws),
-                                ws.numel() * 4, n, p * q, cv.K, gn.num_groups, float(gn.eps), st)
         y = self._act(tag, (n, p, q, cv.K))
-        C.vlnce_affine_apply(ptr(raw), lib.code(raw), ptr(sc), ptr(sh), cv.K, ptr(residual), ptr(y),
-                             lib.code(y), n, p * q, cv.K, int(relu), st)
+        if raw.dtype == torch.float32:
+            C.vlnce_groupnorm_fused(ptr(raw), ptr(gn.weight), ptr(gn.bias), ptr(residual), ptr(y), lib.code(y), ptr(ws),
+                                    ws.numel() * 4, ptr(sc), ptr(sh), n, p * q, cv.K, gn.num_groups, float(gn.eps),
+                                    int(relu), st)
+        else:
+            C.vlnce_groupnorm_stats(ptr(raw), lib.code(raw), ptr(gn.weight), ptr(gn.bias), ptr(sc), ptr(sh), ptr(ws),
+                                    ws.numel() * 4, n, p * q, cv.K, gn.num_groups, float(gn.eps), st)
+            C.vlnce_affine_apply(ptr(raw), lib.code(raw), ptr(sc), ptr(sh), cv.K, ptr(residual), ptr(y),
+                                 lib.code(y), n, p * q, cv.K, int(relu), st)
         return y, (n, p, q, cv.K)
 
     def forward(self, depth: torch.Tensor, out: torch.Tensor, ld_out: int, out_hw: int = 4):
