@@ -134,3 +134,37 @@ def test_gradient_accumulation_equals_single_step():
         return pol.state_dict()["net.second_state_compress.0.bias"].clone()
 
     torch.testing.assert_close(run(True), run(False), rtol=1e-4, atol=1e-6)
+
+
+def test_pipelined_loop_equals_plain_loop():
+    """Trunks of batch i+1 overlapped with the head update of batch i (ILTrainerStep.pipelined_step)
+    must reproduce the plain sequential loop: same losses every step, same parameters at the end."""
+    from vlnce_b200 import synth
+
+    case = dict(cases.CASES["cma_train_pixels"], t=2, n=4)
+    batches = [synth.make_train_batch(900 + i, 2, 4, hw=256, length=24) for i in range(3)]
+    batches = [tuple(cases._to(v, DEV) for v in b) for b in batches]
+
+    def make():
+        pol = cases.build_policy(vlnce_b200, case).to(DEV).eval()
+        pol.net.precision = "bf16"
+        return pol, ILTrainerStep(pol, lr=1e-3)
+
+    aux = vlnce_b200.AuxLosses
+    aux.activate()
+    pol_a, st_a = make()
+    plain = [st_a.update_agent(*b) for b in batches]
+    pol_b, st_b = make()
+    st_b._prepare()
+    st_b.prefetch_visual(batches[0][0])
+    st_b.rotate_visual(batches[0][1].shape[0])
+    piped = []
+    for i, b in enumerate(batches):
+        nxt = batches[(i + 1) % len(batches)][0]
+        obs_nv = {k: v for k, v in b[0].items() if k not in ("rgb", "depth")}
+        piped.append(st_b.pipelined_step(obs_nv, b[1], b[2], b[3], b[4], nxt).tolist())
+    aux.deactivate()
+    torch.cuda.synchronize()
+    for p, q in zip(plain, piped):
+        assert max(abs(a - c) for a, c in zip(p, q)) < 1e-5, (plain, piped)
+    torch.testing.assert_close(st_a.fp.flat, st_b.fp.flat, rtol=1e-5, atol=1e-6)

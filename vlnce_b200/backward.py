@@ -126,7 +126,7 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     first = True
     for name, Cc, kv, v_out, col in (("rgb", eng.Crgb, net.rgb_kv, eng.rgb_out, H + eng.Dt),
                                      ("depth", eng.Cdep, net.depth_kv, eng.depth_out, H + eng.Dt + eng.rgb_out)):
-        E_ = b(name + "_emb" if name == "rgb" else "depth_emb", (R, P, Cc))
+        E_ = cx["rgb_e"] if name == "rgb" else cx["dep_e"]
         pooled, qv, probs = b("pooled_" + name, (R, Cc)), b("q_" + name, (R, Cc)), b("p_" + name, (R, P))
         gw, gb = g[f"net.{name}_kv.weight"], g[f"net.{name}_kv.bias"]
         d_att = off(dxcat, col)

@@ -246,7 +246,22 @@ class CMAEngine(HeadEngine):
         self.cat = self.H + self.Dt + self.rgb_out + self.depth_out + 32
 
     # ------------------------------------------------------------------ forward
-    def forward(self, observations, rnn_states, prev_actions, masks, save: bool):
+    def visual_buffers(self, R, slot: str):
+        """(rgb (R,16,2112), depth (R,16,192)) fp32 feature buffers of a named slot."""
+        return (self.buf(f"rgb_emb_{slot}", (R, self.P, self.Crgb)), self.buf(f"depth_emb_{slot}", (R, self.P, self.Cdep)))
+
+    def encode_visual(self, observations, rgb_e, dep_e):
+        """Both frozen conv trunks (depth on a forked stream) -> channels [0, C_trunk) of the
+        feature buffers.  Independent of every trainable parameter, so a training loop may run it
+        for batch i+1 while the head of batch i trains (``ILTrainerStep.pipelined_step``)."""
+        net = self.net
+        self.ensure_pool(rgb_e.device)
+        with Branch("depth") as br_depth:
+            net.depth_encoder.features_into(observations, dep_e, self.Cdep, self.precision)
+        net.rgb_encoder.features_into(observations, rgb_e, self.Crgb, self.precision)
+        br_depth.join()
+
+    def forward(self, observations, rnn_states, prev_actions, masks, save: bool, visual=None):
         net = self.net
         rnn_states, masks_f, prev, R, N, T = self._prep_rows(rnn_states, prev_actions, masks)
         st = lib.stream()
@@ -258,18 +273,19 @@ class CMAEngine(HeadEngine):
             instr, _, lengths, L = self._encode_instruction(observations, R, save)
 
         # ---- visual encoders + spatial embeddings (cma_policy.py:227-231)
-        rgb_e = self.buf("rgb_emb", (R, P, self.Crgb))
-        dep_e = self.buf("depth_emb", (R, P, self.Cdep))
         c_rgb = net.rgb_encoder.resnet_layer_size
         c_dep = net.depth_encoder.visual_encoder.output_shape[0]
-        with Branch("depth") as br_depth:
-            net.depth_encoder.features_into(observations, dep_e, self.Cdep, self.precision)
-            C.vlnce_spatial_embed_fill(ptr(net.depth_encoder.spatial_embeddings.weight), ptr(dep_e),
-                                       P * self.Cdep, self.Cdep, c_dep, R, P, 64, lib.stream())
-        net.rgb_encoder.features_into(observations, rgb_e, self.Crgb, self.precision)
+        if visual is None:
+            rgb_e = self.buf("rgb_emb", (R, P, self.Crgb))
+            dep_e = self.buf("depth_emb", (R, P, self.Cdep))
+            self.encode_visual(observations, rgb_e, dep_e)
+        else:  # trunk features were produced ahead of time (pipelined training loop)
+            rgb_e, dep_e = visual
+        C.vlnce_spatial_embed_fill(ptr(net.depth_encoder.spatial_embeddings.weight), ptr(dep_e),
+                                   P * self.Cdep, self.Cdep, c_dep, R, P, 64, st)
         C.vlnce_spatial_embed_fill(ptr(net.rgb_encoder.spatial_embeddings.weight), ptr(rgb_e), P * self.Crgb,
                                    self.Crgb, c_rgb, R, P, 64, st)
-        br_depth.join()
+        self.ctx["rgb_e"], self.ctx["dep_e"] = rgb_e, dep_e
 
         # ---- prev-action embedding into both concat slices (cma_policy.py:233-235, Q6)
         state_in = self.buf("state_in", (R, self.state_in))

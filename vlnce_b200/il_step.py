@@ -93,8 +93,41 @@ class ILTrainerStep:
         return loss, action_loss, aux_loss
 
     # The two phases are separately CUDA-graph capturable; the NCCL all-reduce sits between them.
+    # ---- pipelined training loop: the frozen trunks of batch i+1 run concurrently with the head
+    # forward/backward/Adam of batch i (they depend on no trainable parameter); bit-identical results
+    def prefetch_visual(self, observations_next):
+        """Trunk features of the NEXT batch into the 'next' slot (call inside a forked stream or
+        let ``pipelined_step`` do it)."""
+        eng = self.policy.net.engine()
+        rgb = observations_next["rgb"] if "rgb" in observations_next else observations_next["rgb_features"]
+        eng.ensure_pool(rgb.device)
+        R = rgb.shape[0]
+        eng.encode_visual(observations_next, *eng.visual_buffers(R, "next"))
+
+    def rotate_visual(self, R):
+        eng = self.policy.net.engine()
+        for cur, nxt in zip(eng.visual_buffers(R, "cur"), eng.visual_buffers(R, "next")):
+            cur.copy_(nxt)
+
+    def pipelined_step(self, observations, prev_actions, not_done_masks, corrected_actions, weights,
+                       observations_next, apply: bool = True):
+        """One update on the CURRENT batch (its trunk features were prefetched by the previous
+        call) while the trunks of ``observations_next`` run on a forked stream."""
+        from .engine import Branch
+
+        R = prev_actions.shape[0]
+        with Branch("visual_next") as br:
+            self.prefetch_visual(observations_next)
+        self.compute_grads(observations, prev_actions, not_done_masks, corrected_actions, weights,
+                           visual_slot="cur")
+        if apply:
+            self.apply_grads(True)
+        br.join()
+        self.rotate_visual(R)
+        return self._losses
+
     def compute_grads(self, observations, prev_actions, not_done_masks, corrected_actions, weights,
-                      loss_accumulation_scalar: int = 1):
+                      loss_accumulation_scalar: int = 1, visual_slot=None):
         pol = self.policy
         net = pol.net
         self._prepare()
@@ -106,8 +139,9 @@ class ILTrainerStep:
         h0 = eng.ensure_pool(dev).get("il_h0", (N, net.num_recurrent_layers, eng.H), torch.float32)
         h0.zero_()  # base_il_trainer.py:145-150
         AuxLosses.clear()
-        x, _, hat = eng.forward(observations, h0, prev_actions, not_done_masks, save=True)
         R = T * N
+        visual = eng.visual_buffers(R, visual_slot) if visual_slot is not None else None
+        x, _, hat = eng.forward(observations, h0, prev_actions, not_done_masks, save=True, visual=visual)
         head = pol.action_distribution.linear
         A = head.weight.shape[0]
         logp = eng.action_logits(head, x, R)
