@@ -211,7 +211,7 @@ def main():
     static_next = {k: torch.empty_like(dev_sets[0][k]) for k in ("rgb", "depth")}
 
     def split(d):
-        obs = {k: d[k] for k in ("instruction", "rgb", "depth", "progress")}
+        obs = {k: d[k] for k in ("instruction", "rgb", "depth", "progress") if k in d}
         return obs, d["prev_actions"], d["masks"], d["actions"], d["weights"]
 
     VIS = ("rgb", "depth")
