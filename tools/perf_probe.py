@@ -1,6 +1,5 @@
-"""Quick device-time probe of policy.act() phases (not the benchmark): CUDA-event timings of
-the RGB trunk, depth trunk and the whole act() at the BASELINE batch (N=64, 256x256, L=80)."""
-import argparse
+"""Device-time probe of the step's phases (not the benchmark): CUDA-graph replays of the RGB
+trunk, the depth trunk, both trunks concurrently, the head update alone, at the BASELINE batch."""
 import json
 import os
 import sys
@@ -11,58 +10,64 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 warnings.filterwarnings("ignore")
 import vlnce_b200  # noqa: E402
-from oracle import cases  # noqa: E402  (only for the seeded-policy builder)
+from oracle import cases  # noqa: E402  (seeded-policy builder only)
+from vlnce_b200 import synth  # noqa: E402
+from vlnce_b200.il_step import ILTrainerStep  # noqa: E402
 
 
-def timed(fn, iters, warmup):
-    for _ in range(warmup):
+def graph_time(fn, iters=20):
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
         fn()
-    torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    for a, b in ev:
-        a.record()
         fn()
-        b.record()
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(3):
+        g.replay()
     torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(b) for a, b in ev)
-    return ts[len(ts) // 2], ts[0]
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
 
 
 def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=64)
-    ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--precision", default="bf16")
-    args = ap.parse_args()
-    case = dict(cases.CASES["cma_act"], n=args.n)
+    n = 64
+    case = dict(cases.CASES["cma_train_pixels"], t=1, n=n)
     pol = cases.build_policy(vlnce_b200, case).cuda().eval()
-    pol.net.precision = args.precision
-    obs, h, prev, masks = cases.inputs(case)
-    obs = {k: v.cuda() for k, v in obs.items()}
-    h, prev, masks = h.cuda(), prev.cuda(), masks.cuda()
-    n = args.n
-    out_rgb = torch.zeros(n, 16, 2112, device="cuda")
-    out_dep = torch.zeros(n, 16, 192, device="cuda")
-    res = {"n": n, "precision": args.precision}
-    res["rgb_trunk_ms"] = timed(lambda: pol.net.rgb_encoder.features_into(obs, out_rgb, 2112, args.precision),
-                                args.iters, args.warmup)
-    res["depth_trunk_ms"] = timed(lambda: pol.net.depth_encoder.features_into(obs, out_dep, 192, args.precision),
-                                  args.iters, args.warmup)
-    res["act_ms"] = timed(lambda: pol.act(obs, h, prev, masks, deterministic=True), args.iters, args.warmup)
-    g = torch.cuda.CUDAGraph()
-    s = torch.cuda.Stream()
-    with torch.cuda.stream(s):
-        pol.act(obs, h, prev, masks, deterministic=True)
-        torch.cuda.synchronize()
-        with torch.cuda.graph(g, stream=s):
-            pol.act(obs, h, prev, masks, deterministic=True)
-    res["act_graph_ms"] = timed(g.replay, args.iters, args.warmup)
-    res["rgb_tflops"] = 10.68e9 * n / (res["rgb_trunk_ms"][0] * 1e-3) / 1e12
+    vlnce_b200.AuxLosses.activate()
+    step = ILTrainerStep(pol)
+    obs, prev, masks, actions, weights = (cases._to(v, "cuda") for v in synth.make_train_batch(1, 1, n))
+    eng = pol.net.engine()
+    eng.ensure_pool(torch.device("cuda"))
+    step._prepare()
+    rgb_e, dep_e = eng.visual_buffers(n, "next")
+    res = {}
+    res["rgb_trunk_ms"] = graph_time(lambda: pol.net.rgb_encoder.features_into(obs, rgb_e, eng.Crgb, "bf16"))
+    res["depth_trunk_ms"] = graph_time(lambda: pol.net.depth_encoder.features_into(obs, dep_e, eng.Cdep, "bf16"))
+    res["both_trunks_ms"] = graph_time(lambda: eng.encode_visual(obs, rgb_e, dep_e))
+    step.prefetch_visual(obs)
+    step.rotate_visual(n)
+    obs_nv = {k: v for k, v in obs.items() if k not in ("rgb", "depth")}
+
+    def head():
+        step.compute_grads(obs_nv, prev, masks, actions, weights, visual_slot="cur")
+        step.apply_grads(True)
+
+    res["head_update_ms"] = graph_time(head)
+    res["full_step_ms"] = graph_time(lambda: step.update_agent(obs, prev, masks, actions, weights, return_tensor=True))
+    res["pipelined_step_ms"] = graph_time(
+        lambda: step.pipelined_step(obs_nv, prev, masks, actions, weights, {k: obs[k] for k in ("rgb", "depth")}))
     print(json.dumps(res))
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/perf_probe.jsonl", "a") as f:
-        f.write(json.dumps(res) + "\n")
+    open("gpurun_out/phases.json", "w").write(json.dumps(res, indent=1))
 
 
 if __name__ == "__main__":

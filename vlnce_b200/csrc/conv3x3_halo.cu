@@ -298,7 +298,7 @@ int make_map_nhwc(EncodeTiledFn enc, CUtensorMap* m, const void* base, CUtensorM
 
 template <int BLOCK_N>
 int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr, HaloParams& p,
-           int b_stages, cudaStream_t stream) {
+           int b_stages, int exclusive, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -317,7 +317,9 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   }
   p.b_stages = bs;
   const long long tiles = (long long)p.N * p.tiles_x * p.tiles_y * p.n_tiles;
-  conv3x3_halo_kernel<BLOCK_N><<<(unsigned)tiles, kThreads, bytes(bs), stream>>>(tx, tw, ty, tr, p);
+  int smem = bytes(bs);
+  if (exclusive && smem < 116 * 1024) smem = 116 * 1024;  // one CTA per SM, rest of the SM left to other branches
+  conv3x3_halo_kernel<BLOCK_N><<<(unsigned)tiles, kThreads, smem, stream>>>(tx, tw, ty, tr, p);
   VLNCE_LAUNCH_CHECK("conv3x3_halo_kernel");
   return VLNCE_OK;
 }
@@ -338,6 +340,7 @@ extern "C" int vlnce_conv3x3_halo(const void* x, const void* w, int ab_dtype, co
   VLNCE_CHECK_ARG(y_dtype == ab_dtype || y_dtype == VLNCE_F32, "conv3x3_halo: y dtype");
   VLNCE_CHECK_ARG(!(residual && y_dtype == VLNCE_F32), "conv3x3_halo: residual needs a 16-bit output");
   const int b_stages = (block_n >> 16) & 0xf;
+  const int exclusive = (block_n >> 20) & 1;
   int bn = block_n & 0xffff;
   if (bn == 0) bn = (K % 256 == 0) ? 256 : (K % 128 == 0 ? 128 : 64);
   VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && K % bn == 0, "conv3x3_halo: block_n=%d vs K=%d", bn, K);
@@ -384,7 +387,7 @@ extern "C" int vlnce_conv3x3_halo(const void* x, const void* w, int ab_dtype, co
   p.relu = relu; p.y_fp32 = (y_dtype == VLNCE_F32); p.ab_half = (ab_dtype == VLNCE_F16);
   p.has_res = residual != nullptr;
   p.b_stages = 0;
-  if (bn == 256) return launch<256>(tx, tw, ty, tr, p, b_stages, stream);
-  if (bn == 128) return launch<128>(tx, tw, ty, tr, p, b_stages, stream);
-  return launch<64>(tx, tw, ty, tr, p, b_stages, stream);
+  if (bn == 256) return launch<256>(tx, tw, ty, tr, p, b_stages, exclusive, stream);
+  if (bn == 128) return launch<128>(tx, tw, ty, tr, p, b_stages, exclusive, stream);
+  return launch<64>(tx, tw, ty, tr, p, b_stages, exclusive, stream);
 }

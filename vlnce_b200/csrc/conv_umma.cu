@@ -573,7 +573,7 @@ int make_map_2d(EncodeTiledFn encode, CUtensorMap* map, const void* base, CUtens
 
 template <int BLOCK_N, int BLOCK_K>
 int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
-           ConvParams& p, int stages_cap, cudaStream_t stream) {
+           ConvParams& p, int stages_cap, int exclusive, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, BLOCK_K>;
   static bool configured = false;
   if (!configured) {
@@ -609,8 +609,12 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, 
   p.stages = stages;
   if (extra) p.stem_patch = C::staging_bytes(p.out_tma, p.y_fp32) + 16;  // never 0 when enabled
   const long long tiles = (long long)cdiv(p.M, BLOCK_M) * p.n_tiles;
-  conv_umma_kernel<BLOCK_N, BLOCK_K><<<(unsigned)tiles, kThreads, C::smem_bytes(stages, p.out_tma, p.y_fp32, extra),
-                                       stream>>>(tw, tx, ty, tr, p);
+  // "exclusive": request just over half of the SM's shared memory so that exactly ONE of these CTAs
+  // is resident per SM and the other half stays free for kernels of concurrent graph branches
+  // (depth trunk / head run beside the RGB trunk instead of queueing behind it).
+  int smem = C::smem_bytes(stages, p.out_tma, p.y_fp32, extra);
+  if (exclusive && smem < 116 * 1024) smem = 116 * 1024;
+  conv_umma_kernel<BLOCK_N, BLOCK_K><<<(unsigned)tiles, kThreads, smem, stream>>>(tw, tx, ty, tr, p);
   VLNCE_LAUNCH_CHECK("conv_umma_kernel");
   return VLNCE_OK;
 }
@@ -668,6 +672,7 @@ static int conv2d_impl(const void* x, int stem, const void* w, int ab_dtype, con
   const int block_k = (C % 64 == 0) ? 64 : 32;
   const int m_tiles = cdiv((long long)N * P * Q, BLOCK_M);
   const int stages_cap = (block_n >> 16) & 0xf;  // optional tuned ring depth in bits [16,20)
+  const int exclusive = (block_n >> 20) & 1;      // bit 20: one CTA per SM (see launch())
   block_n &= 0xffff;
   int bn = block_n;
   if (bn == 0) {
@@ -729,7 +734,7 @@ static int conv2d_impl(const void* x, int stem, const void* w, int ab_dtype, con
   }
 
 #define VLNCE_CONV_CASE(BN, BK) \
-  if (bn == BN && block_k == BK) return launch<BN, BK>(tw, tx, ty, tr, p, stages_cap, stream);
+  if (bn == BN && block_k == BK) return launch<BN, BK>(tw, tx, ty, tr, p, stages_cap, exclusive, stream);
   VLNCE_CONV_CASE(256, 64)
   VLNCE_CONV_CASE(128, 64)
   VLNCE_CONV_CASE(64, 64)

@@ -54,6 +54,8 @@ HALO_3X3 = _os.environ.get("VLNCE_HALO_3X3", "1") != "0"
 PERSISTENT = _os.environ.get("VLNCE_PERSISTENT", "1") != "0"
 HALO = 1 << 24  # tuning-code flag: TMA-halo 3x3 kernel instead of the generic tile
 TMAP = 1 << 25  # tuning-code flag: persistent TMA-fed kernel (1x1 rows / 3x3 halo, overlapped epilogue)
+EXCL = 1 << 20  # launch flag understood by the conv entry points: one CTA per SM
+RGB_EXCLUSIVE = _os.environ.get("VLNCE_RGB_EXCLUSIVE", "0") != "0"
 # Tuned (tile width | ring depth << 16) per conv geometry, optionally persisted so that later
 # processes on the same box (profilers, the second bench leg) skip the timing sweep.
 _TUNE_CACHE_PATH = _os.environ.get("VLNCE_AUTOTUNE_CACHE", "")
@@ -128,6 +130,10 @@ class _Conv:
 
 
 class ConvTrunk:
+    # RGB trunk only: its conv CTAs claim just over half an SM's shared memory (one CTA per SM) so the
+    # depth trunk / head kernels of concurrent graph branches co-run on the other half
+    exclusive = False
+
     # 16-bit tensor-core operand type of the "bf16" precision mode: bf16 for the BN-folded RGB
     # trunk (unbounded residual stream), fp16 for the GroupNorm depth trunk (activations are
     # renormalised to O(1) every layer; fp16 carries 3 more significand bits at the same cost).
@@ -165,6 +171,8 @@ class ConvTrunk:
                 geom = (n, h, w, c, cv.K, cv.R, cv.S, cv.stride, cv.pad)
 
             def launch(code):
+                if self.exclusive and not (code & TMAP):
+                    code |= EXCL
                 if stem_rgb:
                     C.vlnce_conv2d_stem_rgb(ptr(x), lib.code(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift),
                                             ptr(y), lib.code(y), n, h, w, cv.K, int(relu), code, st)
@@ -174,7 +182,7 @@ class ConvTrunk:
                                      code & 0xfffff, st)
                 elif code & HALO:
                     C.vlnce_conv3x3_halo(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
-                                         ptr(y), lib.code(y), n, h, w, c, cv.K, int(relu), code & ~HALO, st)
+                                         ptr(y), lib.code(y), n, h, w, c, cv.K, int(relu), code & 0x1fffff, st)
                 else:
                     C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
                                         ptr(y), lib.code(y), *geom, int(relu), code, st)
@@ -188,7 +196,7 @@ class ConvTrunk:
             key = (geom, lib.code(y), residual is not None)
             bn = cv.block_n.get(key)
             if bn is None:
-                skey = repr((key, lib.code(cv.w), scale is not None, relu, halo_ok, tma_ok))
+                skey = repr((key, lib.code(cv.w), scale is not None, relu, halo_ok, tma_ok, self.exclusive))
                 if skey in _TUNE_CACHE:
                     bn = int(_TUNE_CACHE[skey])
                 else:
@@ -242,6 +250,8 @@ class ConvTrunk:
 class RGBTrunk(ConvTrunk):
     """torchvision ResNet trunk; ``cnn`` = the nn.Sequential holding conv1,bn1,relu,maxpool,
     layer1..4 (state_dict keys ``net.rgb_encoder.cnn.{0..7}.*``)."""
+
+    exclusive = RGB_EXCLUSIVE
 
     def __init__(self, cnn: nn.Sequential, device, precision="bf16", half_dtype=torch.bfloat16):
         # eval-mode (folded) BatchNorm leaves the residual stream unbounded -> bf16 range;
