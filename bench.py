@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="also write gpurun_out/step_profile.json")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="after warm-up run ONE eager, serial step between cudaProfilerStart/Stop and exit "
+                         "(for `ncu --profile-from-start off`); prints no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -256,6 +259,20 @@ def main():
     launches_per_step = int(lib.C.vlnce_launch_count() - c0)
     graph = None
     losses = step._losses
+    if args.ncu_step:
+        from vlnce_b200 import engine as engine_mod
+
+        engine_mod.set_overlap(False)
+        load_static(dev_sets[3 % NSETS], src_next=dev_sets[4 % NSETS])
+        eager_step(static)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        load_static(dev_sets[4 % NSETS], src_next=dev_sets[5 % NSETS])
+        eager_step(static)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_step": True, "launches": launches_per_step}), flush=True)
+        os._exit(0)
     if not args.no_graph:
         try:
             # N = 1: the whole step is one graph.  N > 1: forward+loss+backward is captured, the NCCL
@@ -394,7 +411,9 @@ def main():
         with lib.profile() as prof:
             for i in range(3):
                 load_static(dev_sets[i % NSETS], src_next=dev_sets[(i + 1) % NSETS])
+                torch.cuda._sleep(30_000_000)  # enqueue the step behind a spin: device time, not launch latency
                 eager_step(static)
+                torch.cuda.synchronize()
         summ = prof.summary()
         for v in summ.values():
             v["us"] = round(v["us"] / 3, 1)
@@ -407,8 +426,11 @@ def main():
         trunk_mod.ConvTrunk._conv = timed_conv
         for i in range(3):
             load_static(dev_sets[i % NSETS], src_next=dev_sets[(i + 1) % NSETS])
+            # park the stream behind a ~15 ms spin so the whole step is enqueued before its first kernel
+            # runs: the event pairs then bracket back-to-back device time, not the host's launch latency
+            torch.cuda._sleep(30_000_000)
             eager_step(static)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
         trunk_mod.ConvTrunk._conv = orig
         conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
         conv_flops = sum(f for _, _, f, _ in rec)
