@@ -396,7 +396,9 @@ def main():
         b.record()
         n, h, w, c = shape_in
         gemm_c = kw.get("gemm_c")
-        if gemm_c is not None:
+        if kw.get("stem_s2d"):  # x = s2d cells, (h, w) = the stem's output size; algorithmic 7x7x3 taps
+            flops = 2.0 * n * h * w * cv.K * 147
+        elif gemm_c is not None:
             flops = 2.0 * n * h * w * gemm_c * cv.K
         else:
             p, q = self._out_hw(h, w, cv)

@@ -73,10 +73,27 @@ int vlnce_conv2d_stem_rgb(const void* x, int x_dtype, const void* w, int ab_dtyp
  * matrix; R = 3: 3x3 pad 1 with halo boxes, needs H % 16 == 0 and W % 8 == 0): one CTA per SM walks a
  * static tile schedule, the epilogue of tile i-1 overlaps the accumulation of tile i (two TMEM
  * accumulators).  C % 64 == 0, K % 64 == 0; same epilogue contract as vlnce_conv2d_bf16.
- * block_n: 0 = auto, else width (64/128/256) | weight-ring depth << 16. */
+ * block_n: 0 = auto, else width (64/128/256) | weight-ring depth << 16 | (1 << 21): two 128-pixel
+ * sub-tiles per scheduled tile share every weight stage (halves the weight bytes per MAC pulled from
+ * L2; needs an even tile count and width <= 128) | (1 << 22): never keep the CTA's weight slice
+ * stationary in shared memory (by default it is loaded once whenever K == width and it fits). */
 int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
                    const void* residual, void* y, int y_dtype, int N, int H, int W, int C, int K, int R,
                    int relu, int block_n, cudaStream_t stream);
+
+/* RGB stem (torchvision conv1 7x7/2 pad 3, resnet_encoders.py:182,198) as a stride-1 4x4 convolution
+ * over the 2x2 space-to-depth image, fully TMA-fed:
+ *   vlnce_stem_s2d      x (N,H,W,3) u8|f32 0..255 -> xs (N, P+3, Q+3, 16) bf16|f16 cells, cell (Y,X) =
+ *                       input pixels (2Y+dy-3, 2X+dx-3) as channels (dy*2+dx)*3+c, 4 zero channels,
+ *                       zeros outside the image; P = (H-1)/2+1, Q = (W-1)/2+1.
+ *   vlnce_conv_stem_tma y (N,P,Q,K) = act(scale * (xs (*) w) + shift), w (K,256) = [k][r'][s'][16] with
+ *                       w[k][r'][s'][(dy*2+dx)*3+c] = conv1.weight[k][c][2r'+dy][2s'+dx] (0 where the index
+ *                       is 7 or the channel is padding).  K % 64 == 0; block_n as vlnce_conv_tma. */
+int vlnce_stem_s2d(const void* x, int x_dtype, void* out, int out_dtype, int N, int H, int W,
+                   cudaStream_t stream);
+int vlnce_conv_stem_tma(const void* xs, const void* w, int ab_dtype, const float* scale, const float* shift,
+                        void* y, int y_dtype, int N, int P, int Q, int K, int relu, int block_n,
+                        cudaStream_t stream);
 
 /* 3x3 stride-1 pad-1 conv with TMA halo loads (one (16+2)x(8+2)-pixel box per 64-channel chunk,
  * nine shifted UMMA descriptors = the nine taps): same epilogue contract as vlnce_conv2d_bf16.

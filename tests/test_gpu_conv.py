@@ -174,11 +174,17 @@ TMA_CASES = [
 ]
 
 
+MT2, NOSTAT = 1 << 21, 1 << 22  # conv_tma block_n flags (include/vlnce_b200.h)
+
+
+@pytest.mark.parametrize("flags", [0, MT2, NOSTAT, MT2 | NOSTAT], ids=["auto", "mt2", "stream", "mt2-stream"])
 @pytest.mark.parametrize("half", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("case", TMA_CASES, ids=[str(c) for c in TMA_CASES])
-def test_conv_tma_persistent_matches_reference(case, half):
-    """Persistent TMA-fed kernel (overlapped epilogue, two TMEM accumulators) vs the reference conv."""
+def test_conv_tma_persistent_matches_reference(case, half, flags):
+    """Persistent TMA-fed kernel (overlapped epilogue, two TMEM accumulator sets) vs the reference conv;
+    flags: paired pixel sub-tiles sharing each weight stage, stationary vs streamed weights."""
     n, h, w, c, k, r, code, epi = case
+    code |= flags
     g = torch.Generator(device="cpu").manual_seed(sum(case[:6]))
     x = torch.randn(n, h, w, c, generator=g).to(DEV).to(half)
     wt = (torch.randn(k, r, r, c, generator=g) * (2.0 / (r * r * c)) ** 0.5).to(DEV).to(half)
@@ -201,3 +207,48 @@ def test_conv_tma_persistent_matches_reference(case, half):
         err = (y.float() - want).abs().max().item()
         assert torch.isfinite(y.float()).all(), f"non-finite output ({y_dtype})"
         assert err <= tol * max(want.abs().max().item(), 1.0), f"{case} {y_dtype}: max err {err}"
+
+
+@pytest.mark.parametrize("flags", [0, MT2, NOSTAT | MT2], ids=["auto", "mt2", "mt2-stream"])
+@pytest.mark.parametrize("hw", [40, 224, 256])
+@pytest.mark.parametrize("img_dtype", [torch.uint8, torch.float32])
+@pytest.mark.parametrize("half", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_s2d_stem_matches_reference(img_dtype, half, hw, flags):
+    """7x7/2 pad-3 stem as a stride-1 4x4 conv over 2x2 space-to-depth cells (overlapping-window TMA
+    boxes, no im2col matrix) vs the fp32 reference conv on the image; hw=40/224: ragged row tiles."""
+    g = torch.Generator().manual_seed(5)
+    n, k = (3 if hw < 100 else 2), 64
+    img = torch.randint(0, 256, (n, hw, hw, 3), generator=g, dtype=torch.uint8)
+    if img_dtype == torch.float32:
+        img = img.float()
+    w = torch.randn(k, 7, 7, 3, generator=g) * 0.05
+    # cell weights: [k][r'][s'][(dy*2+dx)*3+c] = w[k][2r'+dy][2s'+dx][c], zero where the index is 7
+    ws = torch.zeros(k, 4, 4, 16)
+    for rp in range(4):
+        for sp in range(4):
+            for dy in range(2):
+                for dx in range(2):
+                    if 2 * rp + dy < 7 and 2 * sp + dx < 7:
+                        ws[:, rp, sp, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = w[:, 2 * rp + dy, 2 * sp + dx]
+    scale, shift = (torch.rand(k, generator=g) + 0.5) / 255.0, torch.randn(k, generator=g) * 0.1
+    img_d, w_d, ws_d = img.to(DEV), w.to(DEV).to(half), ws.reshape(k, 256).to(DEV).to(half)
+    scale, shift = scale.to(DEV), shift.to(DEV)
+    want = _ref_conv(img_d, w_d.float(), scale, shift, None, 2, 3, True)
+    p = (hw + 6 - 7) // 2 + 1
+    cells = torch.full((n, p + 3, p + 3, 16), float("nan"), device=DEV, dtype=half)
+    C.vlnce_stem_s2d(ptr(img_d), lib.code(img_d), ptr(cells), lib.code(cells), n, hw, hw, lib.stream())
+    torch.cuda.synchronize()
+    # the cell image against a torch gather of the same definition
+    pad = torch.zeros(n, 2 * (p + 3), 2 * (p + 3), 3)
+    pad[:, 3:3 + hw, 3:3 + hw] = img.float()[:, :min(hw, 2 * (p + 3) - 3), :min(hw, 2 * (p + 3) - 3)]
+    want_cells = pad.reshape(n, p + 3, 2, p + 3, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(n, p + 3, p + 3, 12)
+    assert torch.equal(cells[..., :12].float().cpu(), want_cells)
+    assert (cells[..., 12:].float() == 0).all()
+    for y_dtype in (half, torch.float32):
+        y = torch.full((n, p, p, k), float("nan"), device=DEV, dtype=y_dtype)
+        C.vlnce_conv_stem_tma(ptr(cells), ptr(ws_d), lib.code(ws_d), ptr(scale), ptr(shift), ptr(y), lib.code(y),
+                              n, p, p, k, 1, 64 | flags, lib.stream())
+        torch.cuda.synchronize()
+        err = (y.float() - want).abs().max().item()
+        assert torch.isfinite(y.float()).all()
+        assert err <= (2e-2 if y_dtype == torch.bfloat16 else 4e-3) * max(want.abs().max().item(), 1.0), err

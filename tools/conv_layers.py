@@ -98,27 +98,67 @@ def main():
                     row["bn"][f"halo{bn}r{ring}"] = {"us": round(us, 1), "tflops": round(flops / us / 1e6, 1),
                                                     "min_traffic_gbs": round(bytes_min / us / 1e3, 0)}
         if stride == 1 and r in (1, 3) and cin % 64 == 0 and cout % 64 == 0 and args.bn < 0 and (r == 1 or hw % 16 == 0):
+            MT2, NOSTAT = 1 << 21, 1 << 22
             for bn in [b for b in (64, 128, 256) if cout % b == 0]:
-                def launch():
-                    C.vlnce_conv_tma(ptr(x), ptr(w), lib.BF16, ptr(scale), ptr(shift), ptr(resid), ptr(y), lib.BF16,
-                                     geom[0], geom[1], geom[2], geom[3], cout, r, 1, bn | (4 << 16), lib.stream())
-                for _ in range(3):
-                    launch()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(args.reps):
-                    launch()
-                b.record()
-                b.synchronize()
-                us = a.elapsed_time(b) * 1e3 / args.reps
-                row["bn"][f"P{bn}"] = {"us": round(us, 1), "tflops": round(flops / us / 1e6, 1),
-                                      "min_traffic_gbs": round(bytes_min / us / 1e3, 0)}
+                for tag, fl in (("", NOSTAT), ("s", 0), ("m", MT2 | NOSTAT), ("ms", MT2)):
+                    if "m" in tag and bn == 256:
+                        continue
+                    def launch():
+                        C.vlnce_conv_tma(ptr(x), ptr(w), lib.BF16, ptr(scale), ptr(shift), ptr(resid), ptr(y), lib.BF16,
+                                         geom[0], geom[1], geom[2], geom[3], cout, r, 1, bn | (4 << 16) | fl, lib.stream())
+                    for _ in range(3):
+                        launch()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(args.reps):
+                        launch()
+                    b.record()
+                    b.synchronize()
+                    us = a.elapsed_time(b) * 1e3 / args.reps
+                    row["bn"][f"P{bn}{tag}"] = {"us": round(us, 1), "tflops": round(flops / us / 1e6, 1),
+                                               "min_traffic_gbs": round(bytes_min / us / 1e3, 0)}
         best = min(row["bn"].items(), key=lambda kv: kv[1]["us"])
         row["best_bn"], row["best_us"] = best[0], best[1]["us"]
         total_best += best[1]["us"] * count
         print(f"{name:28s} x{count} M={m:7d} {flops/1e9:6.1f} GF  " +
               "  ".join(f"bn{bn}:{v['us']:7.1f}us/{v['tflops']:6.1f}TF" for bn, v in row["bn"].items()), flush=True)
         out.append(row)
+    if not args.only or "stem" in args.only:
+        # s2d stem: cell image + TMA conv, each variant; and the gather stem for reference
+        n, hw = args.n, 256
+        img = torch.randint(0, 256, (n, hw, hw, 3), device=dev, dtype=torch.uint8)
+        cells = torch.empty(n, 131, 131, 16, device=dev, dtype=torch.bfloat16)
+        ws = (torch.randn(64, 256, device=dev) * 0.05).bfloat16()
+        wg = (torch.randn(64, 192, device=dev) * 0.05).bfloat16()
+        scale, shift = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+        y = torch.empty(n, 128, 128, 64, device=dev, dtype=torch.bfloat16)
+        MT2, NOSTAT = 1 << 21, 1 << 22
+
+        def timeit(fn):
+            for _ in range(3):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.reps):
+                fn()
+            b.record()
+            b.synchronize()
+            return a.elapsed_time(b) * 1e3 / args.reps
+
+        res = {"gather_stem": timeit(lambda: C.vlnce_conv2d_stem_rgb(
+            ptr(img), lib.U8, ptr(wg), lib.BF16, ptr(scale), ptr(shift), ptr(y), lib.BF16, n, hw, hw, 64, 1, 0,
+            lib.stream()))}
+        try:
+            res["s2d_cells"] = timeit(lambda: C.vlnce_stem_s2d(ptr(img), lib.U8, ptr(cells), lib.BF16, n, hw, hw,
+                                                               lib.stream()))
+            for tag, fl in (("", NOSTAT), ("s", 0), ("m", MT2 | NOSTAT), ("ms", MT2)):
+                res["s2d_conv64" + tag] = timeit(lambda: C.vlnce_conv_stem_tma(
+                    ptr(cells), ptr(ws), lib.BF16, ptr(scale), ptr(shift), ptr(y), lib.BF16, n, 128, 128, 64, 1,
+                    64 | (4 << 16) | fl, lib.stream()))
+        except lib.VlnceError as e:
+            res["s2d_error"] = str(e)
+        print("stem (us):", {k: (round(v, 1) if isinstance(v, float) else v) for k, v in res.items()}, flush=True)
+        out.append({"layer": "rgb stem variants", "us": res})
     print(f"sum of best per-layer times x count: {total_best:.0f} us")
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/conv_layers.json", "w"), indent=1)

@@ -7,6 +7,18 @@
 //              4-D TMA box loads the (16+2) x (8+2) halo (image borders arrive as zeros) and the
 //              nine taps are nine shifted UMMA descriptors into it (see conv3x3_halo.cu).
 //
+//   mode STEM  the 7x7/2 RGB stem as a stride-1 4x4 convolution over the 2x2 space-to-depth image
+//              (12 real + 4 zero channels per cell, see stem_s2d_kernel): a tile is 128 consecutive
+//              output pixels of one output row; K chunk r' (one of four cell rows) is ONE 4-D TMA box
+//              whose pixel stride (one cell = 32 B) is smaller than its 128-byte extent, i.e. the
+//              overlapping 4-cell windows are read straight from the s2d image — no im2col matrix.
+//
+// L2 -> SM bandwidth is what bounds these tiles (B200: ~42 B/clk/SM against 64 B/clk of weight
+// traffic for a 128-row tile), so a scheduled tile may hold MT = 2 pixel sub-tiles that share every
+// weight stage (two accumulators, weight bytes per MAC halved), and when one CTA's whole weight
+// slice fits in shared memory next to the activation ring it is loaded ONCE ("stationary") and
+// only activations stream afterwards.
+//
 // Persistent CTAs (one per SM) walk a static round-robin tile schedule.  Three roles run
 // concurrently and never wait for each other's whole tile:
 //
@@ -31,15 +43,18 @@ using namespace ptx;
 constexpr int TH = 16, TW = 8;
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kMaxA = 4, kMaxB = 8;
+constexpr int kMaxA = 4, kMaxB = 18;
 
 struct TmaConvParams {
   const float* scale;
   const float* shift;
-  int mode;        // 0 rows (1x1), 1 halo (3x3)
+  int mode;        // 0 rows (1x1), 1 halo (3x3), 2 stem (s2d 4x4, chunk = cell row)
   int M;           // rows mode: N*H*W
   int N, H, W, C, K;
   int c_chunks, n_tiles, m_tiles, tiles_x, tiles_y;
+  int tw, th;      // output patch of one sub-tile (halo 8x16, stem 128x1)
+  int w_cols;      // K extent of one filter tap in the weight matrix (C; stem: 0, chunks are consecutive)
+  int b_stationary;  // 1: b_stages == taps*c_chunks and the weight slice is loaded once per CTA
   int taps;        // 1 | 9
   int halo_w;      // 8 (rows mode: plain 8-row groups) | 10
   int a_bytes;     // ring slot size (1024-multiple), a_tx = bytes the TMA delivers
@@ -75,31 +90,34 @@ struct Tile {
   int x0, y0, img;   // halo mode: patch origin
 };
 
-__device__ __forceinline__ Tile decode_tile(const TmaConvParams& p, int t, int block_n) {
+// scheduled tile t = (pixel super-tile, filter tile); sub-tile h of MT
+__device__ __forceinline__ Tile decode_tile(const TmaConvParams& p, int t, int block_n, int mt, int h) {
   Tile ti;
   const int n_tile = t % p.n_tiles;
-  int m = t / p.n_tiles;
+  int m = (t / p.n_tiles) * mt + h;
   ti.n0 = n_tile * block_n;
   ti.m0 = m * 128;
-  ti.x0 = (m % p.tiles_x) * TW;
+  ti.x0 = (m % p.tiles_x) * p.tw;
   m /= p.tiles_x;
-  ti.y0 = (m % p.tiles_y) * TH;
+  ti.y0 = (m % p.tiles_y) * p.th;
   ti.img = m / p.tiles_y;
   return ti;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                 const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_res,
                 const TmaConvParams p) {
+  static_assert(2 * MT * BLOCK_N <= 512, "two accumulator sets must fit the 512 TMEM columns");
   constexpr int B_BYTES = BLOCK_N * 128;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const uint32_t a_slot = (uint32_t)(MT * p.a_bytes);  // one ring slot = the MT sub-tiles of one K chunk
   const uint32_t smem_a0 = smem_u32(smem);
-  const uint32_t smem_b0 = smem_a0 + p.a_stages * p.a_bytes;
-  uint8_t* bar_base = smem + p.a_stages * p.a_bytes + p.b_stages * B_BYTES;
+  const uint32_t smem_b0 = smem_a0 + p.a_stages * a_slot;
+  uint8_t* bar_base = smem + p.a_stages * a_slot + p.b_stages * B_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* a_empty = a_full + kMaxA;
   uint64_t* b_full = a_empty + kMaxA;
@@ -113,7 +131,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t stage_out = smem_b0 + p.b_stages * B_BYTES + 1024;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = (p.m_tiles / MT) * p.n_tiles;  // host guarantees m_tiles % MT == 0
   const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (threadIdx.x == 5 * 32) {
@@ -131,7 +149,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     tma_prefetch_desc(&tmap_y);
   }
   if (warp == 4) {
-    tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tmem_alloc(tmem_slot, 2 * MT * BLOCK_N);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -145,37 +163,51 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       const int steps = my_tiles * p.c_chunks;
-      auto load_a = [&](int j) {  // activation tile of chunk-step j (tile j / c_chunks, chunk j % c_chunks)
-        const Tile ti = decode_tile(p, blockIdx.x + (j / p.c_chunks) * gridDim.x, BLOCK_N);
+      auto load_a = [&](int j) {  // activation slot of chunk-step j (tile j / c_chunks, chunk j % c_chunks)
+        const int t = blockIdx.x + (j / p.c_chunks) * gridDim.x;
         const int cc = j % p.c_chunks;
         mbar_wait(&a_empty[as], aph ^ 1, 21);
-        mbar_arrive_expect_tx(&a_full[as], p.a_tx);
-        if (p.mode == 0) tma_load_2d(smem_a0 + as * p.a_bytes, &tmap_x, &a_full[as], cc * 64, ti.m0);
-        else tma_load_4d(smem_a0 + as * p.a_bytes, &tmap_x, &a_full[as], cc * 64, ti.x0 - 1, ti.y0 - 1, ti.img);
+        mbar_arrive_expect_tx(&a_full[as], MT * p.a_tx);
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+          const Tile ti = decode_tile(p, t, BLOCK_N, MT, h);
+          const uint32_t dst = smem_a0 + as * a_slot + h * p.a_bytes;
+          if (p.mode == 0) tma_load_2d(dst, &tmap_x, &a_full[as], cc * 64, ti.m0);
+          else if (p.mode == 1) tma_load_4d(dst, &tmap_x, &a_full[as], cc * 64, ti.x0 - 1, ti.y0 - 1, ti.img);
+          else tma_load_4d(dst, &tmap_x, &a_full[as], 0, ti.x0, ti.y0 + cc, ti.img);
+        }
         if (++as == p.a_stages) { as = 0; aph ^= 1; }
       };
       load_a(0);
       for (int j = 0; j < steps; ++j) {
         if (j + 1 < steps) load_a(j + 1);  // one chunk ahead, across tile boundaries
         const int it = j / p.c_chunks, cc = j % p.c_chunks;
-        const Tile ti = decode_tile(p, blockIdx.x + it * gridDim.x, BLOCK_N);
-        for (int tap = 0; tap < p.taps; ++tap) {
-          mbar_wait(&b_empty[bs], bph ^ 1, 22);
-          mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
-          tma_load_2d(smem_b0 + bs * B_BYTES, &tmap_w, &b_full[bs], tap * p.C + cc * 64, ti.n0);
-          if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+        const int t = blockIdx.x + it * gridDim.x;
+        const int n0 = (t % p.n_tiles) * BLOCK_N;
+        if (!p.b_stationary || it == 0) {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            mbar_wait(&b_empty[bs], bph ^ 1, 22);
+            mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
+            tma_load_2d(smem_b0 + bs * B_BYTES, &tmap_w, &b_full[bs], tap * p.w_cols + cc * 64, n0);
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+          }
         }
         if (p.has_res && cc == p.c_chunks - 1) {
-          // residual tile of this tile -> its staging buffer (free once the store that last used it
-          // has been read out)
-          const int sb = it % p.stg_bufs;
-          const uint32_t v = (uint32_t)(it / p.stg_bufs);
-          mbar_wait(&stg_free[sb], (v & 1) ^ 1, 23);
-          mbar_arrive_expect_tx(&res_full[sb], 128 * BLOCK_N * 2);
-          for (int b = 0; b < BLOCK_N / 64; ++b) {
-            const uint32_t dst = stage_out + sb * stg_bytes + (uint32_t)b * (128 * 128);
-            if (p.mode == 0) tma_load_2d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.m0);
-            else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.x0, ti.y0, ti.img);
+          // residual tiles of this tile's sub-tiles -> their staging buffers (free once the store that
+          // last used the buffer has been read out of shared memory)
+#pragma unroll
+          for (int h = 0; h < MT; ++h) {
+            const int vt = it * MT + h;
+            const int sb = vt % p.stg_bufs;
+            const uint32_t v = (uint32_t)(vt / p.stg_bufs);
+            const Tile ti = decode_tile(p, t, BLOCK_N, MT, h);
+            mbar_wait(&stg_free[sb], (v & 1) ^ 1, 23);
+            mbar_arrive_expect_tx(&res_full[sb], 128 * BLOCK_N * 2);
+            for (int b = 0; b < BLOCK_N / 64; ++b) {
+              const uint32_t dst = stage_out + sb * stg_bytes + (uint32_t)b * (128 * 128);
+              if (p.mode == 0) tma_load_2d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.m0);
+              else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.x0, ti.y0, ti.img);
+            }
           }
         }
       }
@@ -190,22 +222,27 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int it = 0; it < my_tiles; ++it) {
       const int buf = it & 1;
       const uint32_t u = (uint32_t)(it >> 1);
-      mbar_wait(&acc_empty[buf], (u & 1) ^ 1, 24);  // epilogue has drained this accumulator
+      mbar_wait(&acc_empty[buf], (u & 1) ^ 1, 24);  // epilogue has drained this accumulator set
       tc_fence_after_sync();
-      const uint32_t tmem_acc = tmem_base + buf * BLOCK_N;
+      const uint32_t tmem_acc = tmem_base + buf * (MT * BLOCK_N);
       for (int cc = 0; cc < p.c_chunks; ++cc) {
         mbar_wait(&a_full[as], aph, 25);
         for (int tap = 0; tap < p.taps; ++tap) {
-          mbar_wait(&b_full[bs], bph, 26);
+          if (!p.b_stationary || it == 0) mbar_wait(&b_full[bs], bph, 26);
           tc_fence_after_sync();
           if (lane == 0) {
             const int r = tap / 3, s = tap - 3 * r;
-            const uint64_t adesc = desc_sbo(smem_a0 + as * p.a_bytes + (r * p.halo_w + s) * 128, sbo);
             const uint64_t bdesc = make_smem_desc(smem_b0 + bs * B_BYTES, 128);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((cc | tap | k) != 0));
-            umma_commit(&b_empty[bs]);
+            for (int h = 0; h < MT; ++h) {
+              const uint64_t adesc =
+                  desc_sbo(smem_a0 + as * a_slot + h * p.a_bytes + (r * p.halo_w + s) * 128, sbo);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_acc + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc,
+                          (uint32_t)((cc | tap | k) != 0));
+            }
+            if (!p.b_stationary) umma_commit(&b_empty[bs]);
             if (tap == p.taps - 1) umma_commit(&a_empty[as]);
           }
           __syncwarp();
@@ -222,114 +259,121 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int it = 0; it < my_tiles; ++it) {
       const int buf = it & 1;
       const uint32_t u = (uint32_t)(it >> 1);
-      const int sb = it % p.stg_bufs;
-      const uint32_t v = (uint32_t)(it / p.stg_bufs);
-      const Tile ti = decode_tile(p, blockIdx.x + it * gridDim.x, BLOCK_N);
-      const uint32_t stg = stage_out + sb * stg_bytes;
       mbar_wait(&acc_full[buf], u & 1, 27);
       tc_fence_after_sync();
-      if (p.has_res) mbar_wait(&res_full[sb], v & 1, 28);   // residual landed (implies staging free)
-      else mbar_wait(&stg_free[sb], (v & 1) ^ 1, 29);       // previous store has left the staging buffer
-      const uint32_t t_row = tmem_base + buf * BLOCK_N + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-      for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
-        uint32_t vv[32];
-        tmem_ld_32x32(t_row + cb * 32, vv);
-        tmem_ld_wait();
-        if (cb == BLOCK_N / 32 - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-          tc_fence_before_sync();
-          mbar_arrive(&acc_empty[buf]);
-        }
-        const int col0 = ti.n0 + cb * 32;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vv[j]);
-        if (p.scale != nullptr) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + j4);
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + j4);
-            f[j4 * 4 + 0] = fmaf(f[j4 * 4 + 0], sc.x, sh.x);
-            f[j4 * 4 + 1] = fmaf(f[j4 * 4 + 1], sc.y, sh.y);
-            f[j4 * 4 + 2] = fmaf(f[j4 * 4 + 2], sc.z, sh.z);
-            f[j4 * 4 + 3] = fmaf(f[j4 * 4 + 3], sc.w, sh.w);
+      for (int h = 0; h < MT; ++h) {
+        const int vt = it * MT + h;   // sub-tiles are the unit of staging / residual / store
+        const int sb = vt % p.stg_bufs;
+        const uint32_t v = (uint32_t)(vt / p.stg_bufs);
+        const Tile ti = decode_tile(p, blockIdx.x + it * gridDim.x, BLOCK_N, MT, h);
+        const uint32_t stg = stage_out + sb * stg_bytes;
+        if (p.has_res) mbar_wait(&res_full[sb], v & 1, 28);   // residual landed (implies staging free)
+        else mbar_wait(&stg_free[sb], (v & 1) ^ 1, 29);       // previous store has left the staging buffer
+        const uint32_t t_row = tmem_base + (buf * MT + h) * BLOCK_N + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
+          uint32_t vv[32];
+          tmem_ld_32x32(t_row + cb * 32, vv);
+          tmem_ld_wait();
+          if (h == MT - 1 && cb == BLOCK_N / 32 - 1) {  // accumulators fully read: hand them back to the MMA warp
+            tc_fence_before_sync();
+            mbar_arrive(&acc_empty[buf]);
           }
-        }
-        if (p.y_fp32) {
-          const uint32_t box = stg + (uint32_t)cb * (128 * 128) + (uint32_t)row * 128;
-          if (p.relu) {
+          const int col0 = ti.n0 + cb * 32;
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vv[j]);
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + j4);
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + j4);
+              f[j4 * 4 + 0] = fmaf(f[j4 * 4 + 0], sc.x, sh.x);
+              f[j4 * 4 + 1] = fmaf(f[j4 * 4 + 1], sc.y, sh.y);
+              f[j4 * 4 + 2] = fmaf(f[j4 * 4 + 2], sc.z, sh.z);
+              f[j4 * 4 + 3] = fmaf(f[j4 * 4 + 3], sc.w, sh.w);
+            }
           }
+          if (p.y_fp32) {
+            const uint32_t box = stg + (uint32_t)cb * (128 * 128) + (uint32_t)row * 128;
+            if (p.relu) {
 #pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            const uint32_t addr = box + (uint32_t)((q4 ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f[q4 * 4]), "f"(f[q4 * 4 + 1]),
-                         "f"(f[q4 * 4 + 2]), "f"(f[q4 * 4 + 3])
-                         : "memory");
-          }
-        } else {
-          const uint32_t box = stg + (uint32_t)(cb >> 1) * (128 * 128) + (uint32_t)row * 128;
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const uint32_t addr = box + (uint32_t)((((cb & 1) * 4 + q4) ^ (row & 7)) << 4);
-            if (p.has_res) {
-              uint32_t w0, w1, w2, w3;
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                           : "r"(addr)
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const uint32_t addr = box + (uint32_t)((q4 ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(f[q4 * 4]), "f"(f[q4 * 4 + 1]),
+                           "f"(f[q4 * 4 + 2]), "f"(f[q4 * 4 + 3])
                            : "memory");
-              const uint32_t w[4] = {w0, w1, w2, w3};
+            }
+          } else {
+            const uint32_t box = stg + (uint32_t)(cb >> 1) * (128 * 128) + (uint32_t)row * 128;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (p.ab_half) {
-                  const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-                  f[q4 * 8 + e * 2 + 0] += h2.x;
-                  f[q4 * 8 + e * 2 + 1] += h2.y;
-                } else {
-                  f[q4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
-                  f[q4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint32_t addr = box + (uint32_t)((((cb & 1) * 4 + q4) ^ (row & 7)) << 4);
+              if (p.has_res) {
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                             : "r"(addr)
+                             : "memory");
+                const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (p.ab_half) {
+                    const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                    f[q4 * 8 + e * 2 + 0] += h2.x;
+                    f[q4 * 8 + e * 2 + 1] += h2.y;
+                  } else {
+                    f[q4 * 8 + e * 2 + 0] += __uint_as_float(w[e] << 16);
+                    f[q4 * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                  }
                 }
               }
-            }
-            uint32_t o[4];
+              uint32_t o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a = f[q4 * 8 + e * 2], b = f[q4 * 8 + e * 2 + 1];
-              if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              if (p.ab_half) {
-                __half2 h2 = __floats2half2_rn(a, b);
-                o[e] = *reinterpret_cast<uint32_t*>(&h2);
-              } else {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-                o[e] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int e = 0; e < 4; ++e) {
+                float a = f[q4 * 8 + e * 2], b = f[q4 * 8 + e * 2 + 1];
+                if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                if (p.ab_half) {
+                  __half2 h2 = __floats2half2_rn(a, b);
+                  o[e] = *reinterpret_cast<uint32_t*>(&h2);
+                } else {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                  o[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
               }
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+                           "r"(o[3])
+                           : "memory");
             }
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]),
-                         "r"(o[3])
-                         : "memory");
           }
         }
-      }
-      fence_proxy_async_smem();
-      named_barrier_sync(1, 128);
-      if (threadIdx.x == 0) {
-        const int boxes = p.y_fp32 ? BLOCK_N / 32 : BLOCK_N / 64;
-        const int cols = p.y_fp32 ? 32 : 64;
-        for (int b = 0; b < boxes; ++b) {
-          const uint32_t src = stg + (uint32_t)b * (128 * 128);
-          if (p.mode == 0) tma_store_2d(&tmap_y, src, ti.n0 + b * cols, ti.m0);
-          else tma_store_4d_(&tmap_y, src, ti.n0 + b * cols, ti.x0, ti.y0, ti.img);
+        fence_proxy_async_smem();
+        named_barrier_sync(1, 128);
+        if (threadIdx.x == 0) {
+          const int boxes = p.y_fp32 ? BLOCK_N / 32 : BLOCK_N / 64;
+          const int cols = p.y_fp32 ? 32 : 64;
+          for (int b = 0; b < boxes; ++b) {
+            const uint32_t src = stg + (uint32_t)b * (128 * 128);
+            if (p.mode == 0) tma_store_2d(&tmap_y, src, ti.n0 + b * cols, ti.m0);
+            else tma_store_4d_(&tmap_y, src, ti.n0 + b * cols, ti.x0, ti.y0, ti.img);
+          }
+          tma_store_commit();
+          // release the staging buffer whose store has now been read out of shared memory
+          if (p.stg_bufs == 2) {
+            tma_store_wait_read_n<1>();
+            if (vt >= 1) mbar_arrive(&stg_free[(vt - 1) & 1]);
+          } else {
+            tma_store_wait_read_n<0>();
+            mbar_arrive(&stg_free[0]);
+          }
         }
-        tma_store_commit();
-        // release the staging buffer whose store has now been read out of shared memory
-        if (p.stg_bufs == 2) {
-          tma_store_wait_read_n<1>();
-          if (it >= 1) mbar_arrive(&stg_free[(it - 1) & 1]);
-        } else {
-          tma_store_wait_read_n<0>();
-          mbar_arrive(&stg_free[0]);
-        }
+        // with a single staging buffer the other 127 threads must not start overwriting it for the
+        // next sub-tile before thread 0 has seen the bulk read complete: they wait on stg_free /
+        // res_full at the top of the next iteration, which thread 0 arrives on only after the wait
       }
     }
     if (threadIdx.x == 0) tma_store_wait_read_n<0>();
@@ -337,7 +381,48 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  if (warp == 4) tmem_dealloc(tmem_base, 2 * MT * BLOCK_N);
+}
+
+// ---------------------------------------------------------------------------------------
+// Space-to-depth operand of the RGB stem: cell (Y, X) of image n holds the 2x2 block of input
+// pixels (2Y+dy-3, 2X+dx-3), dy,dx in {0,1}, as 12 channels (dy*2+dx)*3+c followed by 4 zeros
+// (16 x 16-bit = 32 B per cell); pixels outside the image are zero (= the conv's padding of 3).
+// With it the 7x7/2 conv is a stride-1 4x4 conv: tap (r', s') channel (dy,dx,c) carries the
+// original weight (2r'+dy, 2s'+dx, c) (zero where that index is 7).
+// ---------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void stem_s2d_kernel(const TI* __restrict__ x, TO* __restrict__ out, int N, int H, int W, int Ys,
+                                int Xs) {
+  const long long cells = (long long)N * Ys * Xs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cells;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % Xs);
+    const int Y = (int)((i / Xs) % Ys);
+    const int n = (int)(i / ((long long)Xs * Ys));
+    float f[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int ih = 2 * Y + dy - 3;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iw = 2 * X + dx - 3;
+        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
+          const TI* px = x + ((size_t)(n * H + ih) * W + iw) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f[(dy * 2 + dx) * 3 + c] = to_float<TI>(px[c]);
+        }
+      }
+    }
+    __align__(16) TO o[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) o[e] = from_float<TO>(f[e]);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)i * 16);
+    dst[0] = *reinterpret_cast<const uint4*>(&o[0]);
+    dst[1] = *reinterpret_cast<const uint4*>(&o[8]);
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -368,13 +453,13 @@ int map_nd(EncodeTiledFn enc, CUtensorMap* m, const void* base, CUtensorMapDataT
   return VLNCE_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT>
 int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr,
-           TmaConvParams& p, int b_stages_req, cudaStream_t stream) {
+           TmaConvParams& p, int b_stages_req, int no_stationary, cudaStream_t stream) {
   static bool configured = false;
   static int num_sms = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BLOCK_N, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBudget);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(conv_tma)");
     int dev = 0;
@@ -385,32 +470,64 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   }
   const int stg = 128 * BLOCK_N * (p.y_fp32 ? 4 : 2);
   const int B_BYTES = BLOCK_N * 128;
-  auto bytes = [&](int as, int bs, int sbufs) { return as * p.a_bytes + bs * B_BYTES + 1024 + sbufs * stg + 1024; };
-  // preference order: double staging, deep rings; shrink until it fits
-  int as = p.mode == 1 ? 3 : 4, bs = b_stages_req > 0 ? b_stages_req : (p.mode == 1 ? 4 : 4), sbufs = 2;
-  if (bs > kMaxB) bs = kMaxB;
-  while (bytes(as, bs, sbufs) > kSmemBudget) {
-    if (bs > 3) --bs;
-    else if (as > 2) --as;
-    else if (sbufs > 1) --sbufs;
-    else if (bs > 2) --bs;
-    else {
-      set_error("conv_tma: tile does not fit shared memory (BLOCK_N=%d)", BLOCK_N);
-      return VLNCE_ERR_INVALID_ARGUMENT;
+  const int a_slot = MT * p.a_bytes;
+  auto bytes = [&](int as, int bs, int sbufs) { return as * a_slot + bs * B_BYTES + 1024 + sbufs * stg + 1024; };
+  int as, bs, sbufs;
+  // (1) stationary weights: this CTA's whole weight slice (all taps x chunks) stays in shared memory
+  const int b_all = p.taps * p.c_chunks;
+  p.b_stationary = 0;
+  if (!no_stationary && p.n_tiles == 1 && b_all <= kMaxB) {
+    as = p.mode == 1 ? 3 : 4; sbufs = 2;
+    while (bytes(as, b_all, sbufs) > kSmemBudget) {
+      if (as > 2) --as;
+      else if (sbufs > 1) --sbufs;
+      else break;
+    }
+    if (bytes(as, b_all, sbufs) <= kSmemBudget) { p.b_stationary = 1; bs = b_all; }
+  }
+  if (!p.b_stationary) {
+    // (2) streaming: preference order double staging, deep rings; shrink until it fits
+    as = p.mode == 1 ? 3 : 4; bs = b_stages_req > 0 ? b_stages_req : 4; sbufs = 2;
+    if (bs > kMaxB) bs = kMaxB;
+    while (bytes(as, bs, sbufs) > kSmemBudget) {
+      if (bs > 3) --bs;
+      else if (as > 2) --as;
+      else if (sbufs > 1) --sbufs;
+      else if (bs > 2) --bs;
+      else {
+        set_error("conv_tma: tile does not fit shared memory (BLOCK_N=%d, MT=%d)", BLOCK_N, MT);
+        return VLNCE_ERR_INVALID_ARGUMENT;
+      }
     }
   }
   p.a_stages = as; p.b_stages = bs; p.stg_bufs = sbufs;
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = (p.m_tiles / MT) * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
-  conv_tma_kernel<BLOCK_N><<<grid, kThreads, bytes(as, bs, sbufs), stream>>>(tx, tw, ty, tr, p);
+  conv_tma_kernel<BLOCK_N, MT><<<grid, kThreads, bytes(as, bs, sbufs), stream>>>(tx, tw, ty, tr, p);
   VLNCE_LAUNCH_CHECK("conv_tma_kernel");
   return VLNCE_OK;
+}
+
+int dispatch(int bn, int mt, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty,
+             const CUtensorMap& tr, TmaConvParams& p, int b_stages, int no_stationary, cudaStream_t stream) {
+  if (mt == 2 && (p.m_tiles % 2 != 0 || bn == 256)) mt = 1;  // pairs need an even tile count and 4 accumulators
+  if (bn == 256) return launch<256, 1>(tx, tw, ty, tr, p, b_stages, no_stationary, stream);
+  if (bn == 128) return mt == 2 ? launch<128, 2>(tx, tw, ty, tr, p, b_stages, no_stationary, stream)
+                                : launch<128, 1>(tx, tw, ty, tr, p, b_stages, no_stationary, stream);
+  return mt == 2 ? launch<64, 2>(tx, tw, ty, tr, p, b_stages, no_stationary, stream)
+                 : launch<64, 1>(tx, tw, ty, tr, p, b_stages, no_stationary, stream);
 }
 
 }  // namespace
 }  // namespace vlnce
 
 using namespace vlnce;
+
+// block_n argument of the conv_tma entry points: tile width (64/128/256, 0 = auto) | weight ring depth << 16
+// | (1 << 21): two pixel sub-tiles per scheduled tile share each weight stage | (1 << 22): never keep the
+// weight slice stationary in shared memory.
+#define VLNCE_TMA_MT2 (1 << 21)
+#define VLNCE_TMA_NO_STATIONARY (1 << 22)
 
 // R = 1 (1x1, pad 0) or R = 3 (3x3, pad 1); stride 1.
 extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
@@ -426,11 +543,13 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
   VLNCE_CHECK_ARG(!(residual && y_dtype == VLNCE_F32), "conv_tma: residual needs a 16-bit output");
   VLNCE_CHECK_ARG((long long)N * H * W < (1ll << 31), "conv_tma: too many pixels");
   const int b_stages = (block_n >> 16) & 0xf;
+  const int mt = (block_n & VLNCE_TMA_MT2) ? 2 : 1;
+  const int no_stationary = (block_n & VLNCE_TMA_NO_STATIONARY) ? 1 : 0;
   int bn = block_n & 0xffff;
   if (bn == 0) bn = (K % 128 == 0) ? 128 : 64;
   VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && K % bn == 0, "conv_tma: block_n=%d vs K=%d", bn, K);
   {  // the smallest configuration (2+2 ring slots, one staging buffer) must fit: narrow wide fp32 tiles
-    const int a_b = R == 1 ? 16 * 1024 : 23 * 1024;
+    const int a_b = (R == 1 ? 16 * 1024 : 23 * 1024) * mt;
     while (bn > 64 && 2 * a_b + 2 * bn * 128 + 2048 + 128 * bn * (y_dtype == VLNCE_F32 ? 4 : 2) > kSmemBudget) bn /= 2;
   }
   EncodeTiledFn enc = get_enc();
@@ -467,7 +586,7 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
       if ((rc = map_nd(enc, &tr, residual, dt16, 2, yd, rs, rb, "residual")) != VLNCE_OK) return rc;
     }
     p.mode = 0; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024;
-    p.m_tiles = cdiv(M, 128); p.tiles_x = 1; p.tiles_y = 1;
+    p.m_tiles = cdiv(M, 128); p.tiles_x = 1; p.tiles_y = 1; p.tw = 128; p.th = 1;
   } else {
     const cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t gs[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
@@ -486,15 +605,97 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
       if ((rc = map_nd(enc, &tr, residual, dt16, 4, yd, rs, rb, "residual")) != VLNCE_OK) return rc;
     }
     p.mode = 1; p.taps = 9; p.halo_w = TW + 2; p.a_bytes = 23 * 1024; p.a_tx = (TW + 2) * (TH + 2) * 128;
-    p.tiles_x = W / TW; p.tiles_y = H / TH; p.m_tiles = N * p.tiles_x * p.tiles_y;
+    p.tiles_x = W / TW; p.tiles_y = H / TH; p.m_tiles = N * p.tiles_x * p.tiles_y; p.tw = TW; p.th = TH;
   }
   p.scale = scale; p.shift = shift;
   p.M = (int)M; p.N = N; p.H = H; p.W = W; p.C = C; p.K = K;
   p.c_chunks = C / 64;
+  p.w_cols = C;
   p.n_tiles = K / bn;
   p.relu = relu; p.y_fp32 = f32; p.ab_half = (ab_dtype == VLNCE_F16); p.has_res = residual != nullptr;
-  p.a_stages = p.b_stages = p.stg_bufs = 0;
-  if (bn == 256) return launch<256>(tx, tw, ty, tr, p, b_stages, stream);
-  if (bn == 128) return launch<128>(tx, tw, ty, tr, p, b_stages, stream);
-  return launch<64>(tx, tw, ty, tr, p, b_stages, stream);
+  p.a_stages = p.b_stages = p.stg_bufs = 0; p.b_stationary = 0;
+  return dispatch(bn, mt, tx, tw, ty, tr, p, b_stages, no_stationary, stream);
+}
+
+// (N,H,W,3) u8|f32 image -> (N, P+3, Q+3, 16) 16-bit space-to-depth cells (see stem_s2d_kernel);
+// P = (H-1)/2+1, Q = (W-1)/2+1 are the stem's output size.
+extern "C" int vlnce_stem_s2d(const void* x, int x_dtype, void* out, int out_dtype, int N, int H, int W,
+                              cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && out && N > 0 && H > 0 && W > 0, "stem_s2d: null tensor / empty shape");
+  VLNCE_CHECK_ARG(x_dtype == VLNCE_U8 || x_dtype == VLNCE_F32, "stem_s2d: image must be u8 or f32");
+  VLNCE_CHECK_ARG(out_dtype == VLNCE_BF16 || out_dtype == VLNCE_F16, "stem_s2d: output must be bf16 or f16");
+  VLNCE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "stem_s2d: output must be 16-byte aligned");
+  const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
+  const int Ys = P + 3, Xs = Q + 3;
+  const long long cells = (long long)N * Ys * Xs;
+  const int grid = (int)((cells + 255) / 256 < 148 * 16 ? (cells + 255) / 256 : 148 * 16);
+#define S2D_CASE(TI, TO) \
+  stem_s2d_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)x, (TO*)out, N, H, W, Ys, Xs)
+  if (x_dtype == VLNCE_U8 && out_dtype == VLNCE_BF16) S2D_CASE(uint8_t, __nv_bfloat16);
+  else if (x_dtype == VLNCE_U8) S2D_CASE(uint8_t, __half);
+  else if (out_dtype == VLNCE_BF16) S2D_CASE(float, __nv_bfloat16);
+  else S2D_CASE(float, __half);
+#undef S2D_CASE
+  VLNCE_LAUNCH_CHECK("stem_s2d_kernel");
+  return VLNCE_OK;
+}
+
+// RGB stem on the s2d operand: xs (N, P+3, Q+3, 16), w (K, 256) = [k][r'][s'][16 cell channels],
+// y (N, P, Q, K) ab_dtype | f32.  K % 64 == 0.
+extern "C" int vlnce_conv_stem_tma(const void* xs, const void* w, int ab_dtype, const float* scale,
+                                   const float* shift, void* y, int y_dtype, int N, int P, int Q, int K, int relu,
+                                   int block_n, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(xs && w && y && N > 0 && P > 0 && Q > 0, "conv_stem_tma: null tensor / empty shape");
+  VLNCE_CHECK_ARG(K % 64 == 0, "conv_stem_tma: K must be a multiple of 64");
+  VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_stem_tma: scale/shift must come together");
+  VLNCE_CHECK_ARG(ab_dtype == VLNCE_BF16 || ab_dtype == VLNCE_F16, "conv_stem_tma: operand dtype");
+  VLNCE_CHECK_ARG(y_dtype == ab_dtype || y_dtype == VLNCE_F32, "conv_stem_tma: y dtype");
+  const int b_stages = (block_n >> 16) & 0xf;
+  const int mt = (block_n & VLNCE_TMA_MT2) ? 2 : 1;
+  const int no_stationary = (block_n & VLNCE_TMA_NO_STATIONARY) ? 1 : 0;
+  int bn = block_n & 0xffff;
+  if (bn == 0) bn = 64;
+  VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && K % bn == 0, "conv_stem_tma: block_n=%d vs K=%d", bn, K);
+  EncodeTiledFn enc = get_enc();
+  if (!enc) {
+    set_error("conv_stem_tma: cuTensorMapEncodeTiled unavailable");
+    return VLNCE_ERR_NO_DRIVER;
+  }
+  const CUtensorMapDataType dt16 = ab_dtype == VLNCE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const bool f32 = y_dtype == VLNCE_F32;
+  const int Ys = P + 3, Xs = Q + 3;
+  CUtensorMap tx, tw, ty;
+  int rc;
+  {  // weights [K, 256]
+    const cuuint64_t gd[2] = {256, (cuuint64_t)K};
+    const cuuint64_t gs[1] = {512};
+    const cuuint32_t bx[2] = {64, (cuuint32_t)bn};
+    if ((rc = map_nd(enc, &tw, w, dt16, 2, gd, gs, bx, "stem weights")) != VLNCE_OK) return rc;
+  }
+  {  // overlapping 4-cell windows: dim0 = 64 elements from cell x, dim1 = x with a stride of ONE cell (32 B)
+    const cuuint64_t gd[4] = {64, (cuuint64_t)Q, (cuuint64_t)Ys, (cuuint64_t)N};
+    const cuuint64_t gs[3] = {32, (cuuint64_t)Xs * 32, (cuuint64_t)Ys * Xs * 32};
+    const cuuint32_t bx[4] = {64, 128, 1, 1};
+    if ((rc = map_nd(enc, &tx, xs, dt16, 4, gd, gs, bx, "s2d windows")) != VLNCE_OK) return rc;
+  }
+  {
+    const int esz = f32 ? 4 : 2;
+    const cuuint64_t yd[4] = {(cuuint64_t)K, (cuuint64_t)Q, (cuuint64_t)P, (cuuint64_t)N};
+    const cuuint64_t ys[3] = {(cuuint64_t)K * esz, (cuuint64_t)Q * K * esz, (cuuint64_t)P * Q * K * esz};
+    const cuuint32_t yb[4] = {(cuuint32_t)(f32 ? 32 : 64), 128, 1, 1};
+    if ((rc = map_nd(enc, &ty, y, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16, 4, yd, ys, yb, "stem output")) != VLNCE_OK)
+      return rc;
+  }
+  TmaConvParams p;
+  p.mode = 2; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024;
+  p.tw = 128; p.th = 1;
+  p.tiles_x = cdiv(Q, 128); p.tiles_y = P; p.m_tiles = N * p.tiles_x * p.tiles_y;
+  p.scale = scale; p.shift = shift;
+  p.M = N * P * Q; p.N = N; p.H = P; p.W = Q; p.C = 256; p.K = K;
+  p.c_chunks = 4;
+  p.w_cols = 0;
+  p.n_tiles = K / bn;
+  p.relu = relu; p.y_fp32 = f32; p.ab_half = (ab_dtype == VLNCE_F16); p.has_res = 0;
+  p.a_stages = p.b_stages = p.stg_bufs = 0; p.b_stationary = 0;
+  return dispatch(bn, mt, tx, tw, ty, ty, p, b_stages, no_stationary, stream);
 }

@@ -424,24 +424,31 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, int
   extern __shared__ float gn_sm[];
   float* sc = gn_sm;
   float* sh = gn_sm + C;
+  __shared__ float g_mean[64], g_rstd[64];
   const int n = blockIdx.x;
   const int cpg = C / groups;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
+  // one thread per GROUP combines the S slices (fp64), then every channel takes its group's moments
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double sum = 0.0, sq = 0.0;
+    const float2* p = reinterpret_cast<const float2*>(part) + (size_t)n * S * groups + g;
     for (int s = 0; s < S; ++s) {
-      const float* p = part + ((size_t)(n * S + s) * groups + g) * 2;
-      sum += p[0];
-      sq += p[1];
+      const float2 v = __ldg(p + (size_t)s * groups);
+      sum += v.x;
+      sq += v.y;
     }
     const double cnt = (double)HW * cpg;
     const double mean = sum / cnt;
     double var = sq / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float a = rstd * gamma[c];
+    g_mean[g] = (float)mean;
+    g_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a = g_rstd[g] * gamma[c];
     sc[c] = a;
-    sh[c] = beta[c] - (float)mean * a;
+    sh[c] = beta[c] - g_mean[g] * a;
   }
   __syncthreads();
   const int cv = C / 8;
@@ -789,13 +796,13 @@ extern "C" int vlnce_groupnorm_fused(const float* x, const float* gamma, const f
   }
   int S = cdiv((long long)HW * C, 4096);
   if (S > HW) S = HW;
-  if (S > 64) S = 64;
+  if (S > 8) S = 8;  // N x S CTAs already fill the chip at N >= 19; fewer slices = a shorter combine in apply
   while (S > 1 && (size_t)N * S * groups * 2 * sizeof(float) > workspace_bytes) --S;
   VLNCE_CHECK_ARG((size_t)N * S * groups * 2 * sizeof(float) <= workspace_bytes, "groupnorm_fused: workspace too small");
   gn_partial_kernel<<<dim3(N, S), 256, 0, stream>>>(x, workspace, HW, C, groups);
   VLNCE_LAUNCH_CHECK("gn_partial_kernel");
-  int slices = cdiv((long long)HW * C, 16384);
-  if (slices > 32) slices = 32;
+  int slices = cdiv((long long)HW * C, 8192);
+  if (slices > 64) slices = 64;
   const size_t smem = sizeof(float) * 2 * C;
   dim3 grid(N, slices);
   if (y_dtype == VLNCE_F16)

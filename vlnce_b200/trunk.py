@@ -52,6 +52,9 @@ AUTOTUNE = _os.environ.get("VLNCE_AUTOTUNE", "1") != "0"
 FUSED_STEM = _os.environ.get("VLNCE_FUSED_STEM", "1") != "0"
 HALO_3X3 = _os.environ.get("VLNCE_HALO_3X3", "1") != "0"
 PERSISTENT = _os.environ.get("VLNCE_PERSISTENT", "1") != "0"
+S2D_STEM = _os.environ.get("VLNCE_S2D_STEM", "1") != "0"
+MT2 = 1 << 21     # conv_tma flag: two pixel sub-tiles share each weight stage
+NOSTAT = 1 << 22  # conv_tma flag: do not keep the weight slice stationary in shared memory
 HALO = 1 << 24  # tuning-code flag: TMA-halo 3x3 kernel instead of the generic tile
 TMAP = 1 << 25  # tuning-code flag: persistent TMA-fed kernel (1x1 rows / 3x3 halo, overlapped epilogue)
 EXCL = 1 << 20  # launch flag understood by the conv entry points: one CTA per SM
@@ -118,6 +121,15 @@ class _Conv:
             krsc = torch.zeros(self.K, 64, device=w.device, dtype=w.dtype)
             krsc[:, : flat.shape[1]] = flat
         self.w = krsc.to(wdt).contiguous()
+        self.w_s2d = None
+        if self.precision == "bf16" and self.stem == "rgb":
+            # stride-1 4x4 conv over 2x2 space-to-depth cells: [k][r'][s'][(dy*2+dx)*3+c] (+4 zero channels)
+            w8 = torch.zeros(self.K, 8, 8, 3, device=w.device, dtype=w.dtype)
+            w8[:, :7, :7] = w.permute(0, 2, 3, 1)
+            w8 = w8.reshape(self.K, 4, 2, 4, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(self.K, 4, 4, 12)
+            ws = torch.zeros(self.K, 4, 4, 16, device=w.device, dtype=w.dtype)
+            ws[..., :12] = w8
+            self.w_s2d = ws.reshape(self.K, 256).to(wdt).contiguous()
         if isinstance(self.norm, nn.BatchNorm2d):
             n = self.norm
             sc = n.weight.detach().float() / torch.sqrt(n.running_var.detach().float() + n.eps)
@@ -157,13 +169,15 @@ class ConvTrunk:
         return self.pool.get(tag, shape, torch.float32)
 
     def _conv(self, x, shape_in, cv: _Conv, y, *, scale, shift, residual=None, relu=False,
-              gemm_c: Optional[int] = None, stem_rgb: bool = False):
+              gemm_c: Optional[int] = None, stem_rgb: bool = False, stem_s2d: bool = False):
         """x NHWC (n,h,w,c) -> y; ``gemm_c`` set = x is an explicit stem operand (n*p*q, gemm_c);
         ``stem_rgb`` = x is the raw (n,h,w,3) image and the 7x7/2 window is gathered in-kernel."""
         n, h, w, c = shape_in
         st = lib.stream()
         if self.precision == "bf16":
-            if stem_rgb:
+            if stem_s2d:  # x = s2d cells, (n, h, w) = the stem's OUTPUT size
+                geom = ("stem_s2d", n, h, w, cv.K)
+            elif stem_rgb:
                 geom = ("stem", n, h, w, cv.K)
             elif gemm_c is not None:
                 geom = (n * h * w, 1, 1, gemm_c, cv.K, 1, 1, 1, 0)
@@ -173,13 +187,16 @@ class ConvTrunk:
             def launch(code):
                 if self.exclusive and not (code & TMAP):
                     code |= EXCL
-                if stem_rgb:
+                if stem_s2d:
+                    C.vlnce_conv_stem_tma(ptr(x), ptr(cv.w_s2d), lib.code(cv.w_s2d), ptr(scale), ptr(shift), ptr(y),
+                                          lib.code(y), n, h, w, cv.K, int(relu), code & 0x6fffff, st)
+                elif stem_rgb:
                     C.vlnce_conv2d_stem_rgb(ptr(x), lib.code(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift),
                                             ptr(y), lib.code(y), n, h, w, cv.K, int(relu), code, st)
                 elif code & TMAP:
                     C.vlnce_conv_tma(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y),
                                      lib.code(y), geom[0], geom[1], geom[2], geom[3], cv.K, geom[5], int(relu),
-                                     code & 0xfffff, st)
+                                     code & 0x6fffff, st)
                 elif code & HALO:
                     C.vlnce_conv3x3_halo(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
                                          ptr(y), lib.code(y), n, h, w, c, cv.K, int(relu), code & 0x1fffff, st)
@@ -187,8 +204,8 @@ class ConvTrunk:
                     C.vlnce_conv2d_bf16(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual),
                                         ptr(y), lib.code(y), *geom, int(relu), code, st)
 
-            c_in = geom[3] if not stem_rgb else 0
-            tma_ok = (PERSISTENT and not stem_rgb and c_in % 64 == 0 and cv.K % 64 == 0 and geom[7:] in ((1, 0), (1, 1))
+            c_in = geom[3] if not (stem_rgb or stem_s2d) else 0
+            tma_ok = (PERSISTENT and not stem_rgb and not stem_s2d and c_in % 64 == 0 and cv.K % 64 == 0 and geom[7:] in ((1, 0), (1, 1))
                       and ((geom[5] == 1 and geom[8] == 0)
                            or (geom[5] == 3 and geom[8] == 1 and geom[1] % 16 == 0 and geom[2] % 8 == 0)))
             halo_ok = (HALO_3X3 and not stem_rgb and gemm_c is None and cv.R == 3 and cv.S == 3 and cv.stride == 1
@@ -202,8 +219,10 @@ class ConvTrunk:
                 else:
                     tune = AUTOTUNE and x.is_cuda and not torch.cuda.is_current_stream_capturing()
                     if tune:
-                        bn = self._tune(launch, cv.K, halo_ok, tma_ok)
+                        bn = self._tune(launch, cv.K, halo_ok, tma_ok, stem_s2d)
                         _tune_cache_put(skey, bn)
+                    elif stem_s2d:
+                        bn = 64 | MT2
                     else:
                         bn = TMAP if tma_ok else (HALO if halo_ok else 0)
                 cv.block_n[key] = bn
@@ -214,7 +233,7 @@ class ConvTrunk:
                                cv.stride, cv.pad, int(relu), st)
 
     @staticmethod
-    def _tune(launch, K, halo_ok=False, tma_ok=False):
+    def _tune(launch, K, halo_ok=False, tma_ok=False, stem_s2d=False):
         """Pick kernel variant, output-tile width and ring depth empirically (once per layer
         shape): CUDA-event timing of the legal candidates on the real operands; the winner is
         cached on the layer."""
@@ -223,7 +242,10 @@ class ConvTrunk:
         if halo_ok:
             cands += [HALO | bn | (st << 16) for bn in widths for st in (3, 6)]
         if tma_ok:
-            cands += [TMAP | bn | (st << 16) for bn in widths for st in (4,)]
+            cands += [TMAP | bn | (4 << 16) | fl for bn in widths for fl in (0, NOSTAT)]
+            cands += [TMAP | bn | (4 << 16) | MT2 | fl for bn in widths if bn <= 128 for fl in (0, NOSTAT)]
+        if stem_s2d:  # only the persistent TMA kernel runs this geometry
+            cands = [bn | (4 << 16) | fl for bn in widths if bn <= 128 for fl in (0, MT2, NOSTAT, MT2 | NOSTAT)]
         best, best_t = 0, float("inf")
         for _ in range(12):  # bring the clocks up before timing anything
             launch(cands[-1])
@@ -272,6 +294,7 @@ class RGBTrunk(ConvTrunk):
                 self.blocks.append(d)
         self.out_channels = self.blocks[-1]["c3" if "c3" in self.blocks[-1] else "c2"].K
         self._bn_ws = None
+        self._s2d_ok = self.stem.K % 64 == 0
 
     def _all(self) -> List[_Conv]:
         out = [self.stem]
@@ -280,19 +303,20 @@ class RGBTrunk(ConvTrunk):
         return out
 
     def _norm_conv(self, x, shape_in, cv: _Conv, tag, *, residual=None, relu=True, gemm_c=None,
-                   out_hw=None, stem_rgb=False):
+                   out_hw=None, stem_rgb=False, stem_s2d=False):
         n, h, w, _ = shape_in
         p, q = out_hw if out_hw is not None else self._out_hw(h, w, cv)
         y = self._act(tag, (n, p, q, cv.K))
         bn: nn.BatchNorm2d = cv.norm
         if not bn.training:
             self._conv(x, shape_in, cv, y, scale=cv.scale, shift=cv.shift, residual=residual, relu=relu,
-                       gemm_c=gemm_c, stem_rgb=stem_rgb)
+                       gemm_c=gemm_c, stem_rgb=stem_rgb, stem_s2d=stem_s2d)
             return y, (n, p, q, cv.K)
         # train-mode BN (Q1): raw conv (input scaling only) -> batch stats -> fused apply
         raw = self._raw("bn_raw", (n, p, q, cv.K))
         self._conv(x, shape_in, cv, raw, scale=cv.pre_scale if cv.in_scale != 1.0 else None,
-                   shift=cv.pre_shift if cv.in_scale != 1.0 else None, gemm_c=gemm_c, stem_rgb=stem_rgb)
+                   shift=cv.pre_shift if cv.in_scale != 1.0 else None, gemm_c=gemm_c, stem_rgb=stem_rgb,
+                   stem_s2d=stem_s2d)
         st = lib.stream()
         sc = self.pool.get("bn_scale", (cv.K,), torch.float32)
         sh = self.pool.get("bn_shift", (cv.K,), torch.float32)
@@ -315,7 +339,23 @@ class RGBTrunk(ConvTrunk):
         st = lib.stream()
         cv = self.stem
         p, q = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
-        if self.precision == "bf16" and FUSED_STEM:
+        x = None
+        if self.precision == "bf16" and S2D_STEM and self._s2d_ok:
+            # stem as a stride-1 4x4 conv over 2x2 space-to-depth cells, fully TMA-fed (overlapping
+            # 4-cell windows read straight from the cell image); falls back to the gather stem if the
+            # driver rejects the overlapping-stride tensor map
+            cells = self.pool.get("stem_s2d", (n, p + 3, q + 3, 16), self.adt)
+            try:
+                C.vlnce_stem_s2d(ptr(rgb), lib.code(rgb), ptr(cells), lib.code(cells), n, h, w, st)
+                x, shp = self._norm_conv(cells, (n, p, q, 16), cv, "stem_y", out_hw=(p, q), stem_s2d=True)
+            except lib.VlnceError:
+                if torch.cuda.is_current_stream_capturing():
+                    raise
+                self._s2d_ok = False
+                x = None
+        if x is not None:
+            pass
+        elif self.precision == "bf16" and FUSED_STEM:
             # im2col-free stem: the 7x7x3 windows are gathered inside the conv tile's producer warps
             x, shp = self._norm_conv(rgb, (n, h, w, 3), cv, "stem_y", out_hw=(p, q), stem_rgb=True)
         elif self.precision == "bf16":
