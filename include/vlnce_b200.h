@@ -89,6 +89,9 @@ int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scal
  *   vlnce_conv_stem_tma y (N,P,Q,K) = act(scale * (xs (*) w) + shift), w (K,256) = [k][r'][s'][16] with
  *                       w[k][r'][s'][(dy*2+dx)*3+c] = conv1.weight[k][c][2r'+dy][2s'+dx] (0 where the index
  *                       is 7 or the channel is padding).  K % 64 == 0; block_n as vlnce_conv_tma. */
+/* Debug aid of the persistent conv tiles: a device buffer of 4*768*2 int64 that CTA 0 of every later
+ * vlnce_conv_tma / vlnce_conv_stem_tma launch fills with per-role (event, clock64) records; NULL = off. */
+int vlnce_debug_set_trace(void* buffer);
 int vlnce_stem_s2d(const void* x, int x_dtype, void* out, int out_dtype, int N, int H, int W,
                    cudaStream_t stream);
 int vlnce_conv_stem_tma(const void* xs, const void* w, int ab_dtype, const float* scale, const float* shift,
@@ -235,6 +238,10 @@ int vlnce_attn_pool_bwd(const float* q, long long ldq, const float* E, long long
 int vlnce_lstm_seq_bwd(const float* dout, const float* gates, const float* cs, const float* out,
                        const float* whh_f, const float* whh_b, const int* lengths, float* dgx,
                        float* hprev, int R, int L, int H, int dirs, cudaStream_t stream);
+/* Gradient entering a final-state-only instruction encoder (instruction_encoder.py:87-90; Seq2Seq):
+ * dout (R,L,H) = 0 except dout[r, lengths[r]-1, :] = dh[r, :] — then vlnce_lstm_seq_bwd as usual. */
+int vlnce_scatter_last_token(const float* dh, long long lddh, const int* lengths, float* dout, int R,
+                             int L, int H, cudaStream_t stream);
 int vlnce_embedding_bwd(const long long* ids, const float* d, long long ldd, float* dtable,
                         long long rows, int dim, int vocab, int padding_idx, cudaStream_t stream);
 int vlnce_prev_action_embed_bwd(const long long* prev_actions, const float* masks, const float* d1,

@@ -33,6 +33,13 @@ CASES = {
     # BASELINE config C1: Seq2Seq, batch 2
     "seq2seq_act": dict(policy="Seq2SeqPolicy", pm=False, kind="act", n=2, hw=256, length=80,
                         wseed=16, iseed=106, bn_train=False),
+    # Seq2Seq training (seq2seq_r2n.yaml recipe family): raw pixels with the progress monitor, and the
+    # DAgger cached-feature layout with the prev-action embedding (seq2seq_policy.py:158-162)
+    "seq2seq_train_pixels": dict(policy="Seq2SeqPolicy", pm=True, kind="train", t=3, n=2, hw=256,
+                                 length=40, wseed=17, iseed=107, bn_train=False, features=False),
+    "seq2seq_train_features": dict(policy="Seq2SeqPolicy", pm=False, kind="train", t=4, n=3, hw=256,
+                                   length=24, wseed=18, iseed=108, bn_train=False, features=True,
+                                   prev_action=True),
 }
 
 
@@ -40,6 +47,8 @@ def model_config(case) -> hb017.Config:
     over = dict(PROGRESS_MONITOR=dict(use=bool(case["pm"]), alpha=1.0))
     if case["policy"] == "CMAPolicy":
         return vlnce.cma_model_config(**over)
+    if case.get("prev_action"):
+        over["SEQ2SEQ"] = dict(use_prev_action=True)
     return vlnce.default_model_config(policy_name="Seq2SeqPolicy", **over)
 
 
@@ -76,7 +85,8 @@ def inputs(case):
                                     layers=layers_of(case))
     return synth.make_train_batch(case["iseed"], case["t"], case["n"], hw=case["hw"],
                                   rgb_hw=case.get("rgb_hw"), length=case["length"],
-                                  features=case["features"])
+                                  features=case["features"],
+                                  rgb_feature_hw=1 if case["policy"] == "Seq2SeqPolicy" else 4)
 
 
 def grad_digest(g: torch.Tensor) -> torch.Tensor:

@@ -47,7 +47,7 @@ def _worker(rank, world, port, out):
         for v in g.values():
             v.fill_(float(rank + 1))
 
-    il_step.cma_backward = fake_backward
+    backward.cma_backward = fake_backward  # CMAEngine.run_backward resolves it at call time
     step = il_step.ILTrainerStep(pol, lr=1e-3)
     assert step.world == world
     with lib.dry_run() as rec:

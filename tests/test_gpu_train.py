@@ -56,7 +56,9 @@ def check(got, want, rtol, name, grad_norm_tol=None):
 
 @pytest.mark.parametrize("name,precision,rtol", [
     ("cma_train_features", "fp32", 1e-3), ("cma_train_features_nopm", "fp32", 1e-3),
-    ("cma_train_pixels", "fp32", 1e-3), ("cma_train_pixels", "bf16", 1e-2)])
+    ("cma_train_pixels", "fp32", 1e-3), ("cma_train_pixels", "bf16", 1e-2),
+    ("seq2seq_train_features", "fp32", 1e-3), ("seq2seq_train_pixels", "fp32", 1e-3),
+    ("seq2seq_train_pixels", "bf16", 1e-2)])
 def test_reference_update_arithmetic_on_cuda_policy(name, precision, rtol):
     """base_il_trainer.py:134-172 verbatim (torch CE / AuxLosses.reduce / loss.backward()) on
     the CUDA policy: logits, losses and every trainable gradient vs the reference."""
@@ -64,7 +66,8 @@ def test_reference_update_arithmetic_on_cuda_policy(name, precision, rtol):
     check(got, gold(name), rtol, name, grad_norm_tol=0.1 if precision == "bf16" else None)
 
 
-@pytest.mark.parametrize("name", ["cma_train_features", "cma_train_features_nopm"])
+@pytest.mark.parametrize("name", ["cma_train_features", "cma_train_features_nopm", "seq2seq_train_features",
+                                  "seq2seq_train_pixels"])
 def test_fused_step_matches_reference(name):
     case = cases.CASES[name]
     want = gold(name)
@@ -89,7 +92,7 @@ def test_fused_step_matches_reference(name):
     check(got, {k: v for k, v in want.items() if k.startswith("grad/")}, 1e-3, name)
     # parameters moved by exactly one Adam step of those gradients (torch.optim.Adam semantics)
     after = pol.state_dict()
-    k = "net.state_q.weight"
+    k = "net.state_q.weight" if case["policy"] == "CMAPolicy" else "net.state_encoder.rnn.weight_hh_l0"
     gk = step.fp.grad_views[k]
     expect = before[k] - 2.5e-4 * gk / (gk.abs() + 1e-8)  # step 1: m/(sqrt(v)+eps) = g/(|g|+eps)
     torch.testing.assert_close(after[k], expect, rtol=1e-5, atol=1e-7)

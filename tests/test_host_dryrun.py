@@ -48,6 +48,35 @@ def test_train_launch_sequence(name):
     assert any(k.startswith("grad/net.rgb_kv.weight") for k in got)
 
 
+@pytest.mark.parametrize("name", ["seq2seq_train_features", "seq2seq_train_pixels"])
+def test_seq2seq_train_launch_sequence(name):
+    """Seq2Seq training path: one autograd node, final-state scatter -> LSTM BPTT, GRU BPTT."""
+    from oracle import vlnce as oracle_vlnce
+
+    with lib.dry_run() as rec:
+        got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses)
+    assert rec.calls.count("vlnce_scatter_last_token") == 1 and rec.calls.count("vlnce_lstm_seq_bwd") == 1
+    case = cases.CASES[name]
+    assert rec.calls.count("vlnce_gru_pointwise_bwd") == case["t"]
+    if case.get("prev_action"):
+        assert "vlnce_prev_action_embed_bwd" in rec.calls
+    ref = cases.build_policy(oracle_vlnce, case)
+    want = {"grad/" + k for k, p in ref.named_parameters() if p.requires_grad}
+    assert {k for k in got if k.startswith("grad/")} == want
+
+
+def test_seq2seq_fused_step_launch_sequence():
+    from vlnce_b200.il_step import ILTrainerStep
+
+    case = cases.CASES["seq2seq_train_features"]
+    pol = cases.build_policy(vlnce_b200, case)
+    obs, prev, masks, actions, weights = cases.inputs(case)
+    step = ILTrainerStep(pol)
+    with lib.dry_run() as rec:
+        out = step.update_agent(obs, prev, masks, actions, weights, return_tensor=True)
+    assert out.shape == (3,) and rec.calls[-1] == "vlnce_adam_step" and "vlnce_scatter_last_token" in rec.calls
+
+
 def test_fused_step_launch_sequence():
     from vlnce_b200.il_step import ILTrainerStep
 

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.skipif(not reference_import.available(),
 warnings.filterwarnings("ignore")
 
 
-@pytest.mark.parametrize("name", ["cma_act_bntrain", "cma_train_features", "seq2seq_act"])
+@pytest.mark.parametrize("name", ["cma_act_bntrain", "cma_train_features", "seq2seq_act", "seq2seq_train_features"])
 def test_oracle_equals_reference_live(name):
     ref = reference_import.load()
     a = cases.run_case(ref, name, aux=ref.AuxLosses)

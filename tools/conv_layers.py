@@ -43,7 +43,7 @@ def main():
         torch.randn(4096, 4096, device=dev) @ torch.randn(4096, 4096, device=dev)
     total_best = 0.0
     for name, hw, cin, cout, r, stride, res, count in RGB:
-        if args.only and args.only not in name:
+        if args.only and not any(o in name for o in args.only.split(",")):
             continue
         n = args.n
         pad = r // 2
@@ -123,7 +123,7 @@ def main():
         print(f"{name:28s} x{count} M={m:7d} {flops/1e9:6.1f} GF  " +
               "  ".join(f"bn{bn}:{v['us']:7.1f}us/{v['tflops']:6.1f}TF" for bn, v in row["bn"].items()), flush=True)
         out.append(row)
-    if not args.only or "stem" in args.only:
+    if not args.only or "stem" in args.only.split(","):
         # s2d stem: cell image + TMA conv, each variant; and the gather stem for reference
         n, hw = args.n, 256
         img = torch.randint(0, 256, (n, hw, hw, 3), device=dev, dtype=torch.uint8)

@@ -69,6 +69,118 @@ def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, m
     linear_dx(ptr(d_gi), 3 * H, ptr(rnn.weight_ih_l0), dx, lddx, R, 3 * H, in_size)
 
 
+def instruction_backward(eng, g: Dict[str, torch.Tensor], d_instr: torch.Tensor):
+    """BPTT of the packed (bi)LSTM instruction encoder (instruction_encoder.py:63-94) from the
+    gradient w.r.t. its per-token outputs ``d_instr`` (R, L, dirs*Hs): pre-activation gate gradients
+    from the persistent kernel, then the weight / embedding gradients as GEMMs + a scatter."""
+    net, cx, b = eng.net, eng.ctx, eng.buf
+    R, L = cx["R"], cx["L"]
+    ie = net.instruction_encoder
+    rnn = ie.encoder_rnn
+    Hs, dirs, E = eng.Hs, eng.dirs, eng.E
+    instr = b("instr_out", (R, L, dirs * Hs))
+    dgx = b("lstm_dgx", (dirs, R, L, 4 * Hs))
+    hprev = b("lstm_hprev", (dirs, R, L, Hs))
+    C.vlnce_lstm_seq_bwd(ptr(d_instr), ptr(b("lstm_gates", (dirs, R, L, 4 * Hs))), ptr(b("lstm_c", (dirs, R, L, Hs))),
+                         ptr(instr), ptr(rnn.weight_hh_l0), ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None,
+                         ptr(cx["lengths"]), ptr(dgx), ptr(hprev), R, L, Hs, dirs, lib.stream())
+    emb_in = b("instr_emb", (R * L, E)) if ie.config.sensor_uuid == "instruction" else cx["rxr"]
+    emb_trainable = ie.config.sensor_uuid == "instruction" and ie.embedding_layer.weight.requires_grad
+    d_emb = b("d_instr_emb", (R * L, E)) if emb_trainable else None
+    for d, sfx in enumerate(["", "_reverse"][:dirs]):
+        dg = off(dgx, d * R * L * 4 * Hs)
+        pfx = "net.instruction_encoder.encoder_rnn."
+        linear_dw(dg, 4 * Hs, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, 4 * Hs, E)
+        linear_dw(dg, 4 * Hs, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, 4 * Hs, Hs)
+        _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, 4 * Hs)
+        _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, 4 * Hs)
+        if emb_trainable:
+            w_ih = getattr(rnn, "weight_ih_l0" + sfx)
+            linear_dx(dg, 4 * Hs, ptr(w_ih), ptr(d_emb), E, R * L, 4 * Hs, E, beta=0.0 if d == 0 else 1.0)
+    if emb_trainable:
+        el = ie.embedding_layer
+        pad = -1 if el.padding_idx is None else el.padding_idx
+        C.vlnce_embedding_bwd(ptr(cx["ids"]), ptr(d_emb), E, ptr(g["net.instruction_encoder.embedding_layer.weight"]),
+                              R * L, E, el.num_embeddings, pad, lib.stream())
+
+
+def head_and_progress_backward(eng, head_linear, g, d_raw, d_x, d_hat, leaves):
+    """Steps shared by both nets: action head (or a feature gradient) and the progress monitor
+    ``hat = tanh(x w + b)``; returns the gradient buffer w.r.t. the net's output features."""
+    net, cx, b = eng.net, eng.ctx, eng.buf
+    R, H = cx["R"], eng.H
+    st = lib.stream()
+    x_out = b("x_out", (R, H))
+    dx_out = b("d_x_out", (R, H))
+    if head_linear is not None:
+        A = head_linear.weight.shape[0]
+        with leaves():
+            linear_dw(ptr(d_raw), A, ptr(x_out), H, ptr(g["action_distribution.linear.weight"]), H, R, A, H)
+            _colsum(ptr(d_raw), A, ptr(g["action_distribution.linear.bias"]), R, A)
+        linear_dx(ptr(d_raw), A, ptr(head_linear.weight), ptr(dx_out), H, R, A, H)
+    else:
+        dx_out.copy_(d_x)
+    if d_hat is not None and "net.progress_monitor.weight" in g:
+        hat = b("progress_hat", (R, 1))
+        dpre = b("d_pm", (R, 1))
+        dpre.copy_(d_hat.reshape(R, 1))
+        C.vlnce_tanh_bwd(ptr(dpre), ptr(hat), R, st)
+        pm = net.progress_monitor
+        with leaves():
+            linear_dw(ptr(dpre), 1, ptr(x_out), H, ptr(g["net.progress_monitor.weight"]), H, R, 1, H)
+            _colsum(ptr(dpre), 1, ptr(g["net.progress_monitor.bias"]), R, 1)
+        linear_dx(ptr(dpre), 1, ptr(pm.weight), ptr(dx_out), H, R, 1, H, beta=1.0)
+    return dx_out
+
+
+def seq2seq_backward(eng, head_linear, g: Dict[str, torch.Tensor], d_raw: Optional[torch.Tensor],
+                     d_x: Optional[torch.Tensor], d_hat: Optional[torch.Tensor]):
+    """Backward of ``Seq2SeqEngine.forward(..., save=True)`` (seq2seq_policy.py:142-179): action head /
+    progress monitor -> GRU (BPTT over the T rows blocks) -> the four concat slices: instruction final
+    state (scattered to its token, then the LSTM's BPTT), depth fc, rgb fc (ReLU(Linear); the conv
+    trunks are frozen, ``config/default.py:242,253``) and the optional prev-action embedding."""
+    net, cx, b = eng.net, eng.ctx, eng.buf
+    assert cx.get("saved"), "backward needs the forward to have run with save=True"
+    R, N, T, L = cx["R"], cx["N"], cx["T"], cx["L"]
+    H, Hs = eng.H, eng.Hs
+    d_out, r_out, width = cx["d_out"], cx["r_out"], cx["width"]
+    st = lib.stream()
+    masks_f = b("masks_f", (R,))
+    xin = b("s2s_in", (R, width))
+    leaves = _Leaves()
+    dx_out = head_and_progress_backward(eng, head_linear, g, d_raw, d_x, d_hat, leaves)
+    d_xin = b("d_s2s_in", (R, width))
+    _gru_backward(eng, "gru", net.state_encoder.rnn, "net.state_encoder.rnn.", g, ptr(dx_out), H, ptr(xin), width,
+                  width, masks_f, T, N, ptr(d_xin), width, leaves)
+    # instruction final state -> its token's output gradient -> LSTM BPTT (own stream)
+    with Branch("lstm_bwd") as br_lstm:
+        d_instr = b("d_instr", (R, L, Hs))
+        C.vlnce_scatter_last_token(ptr(d_xin), width, ptr(cx["lengths"]), ptr(d_instr), R, L, Hs, lib.stream())
+        instruction_backward(eng, g, d_instr)
+    # depth fc | rgb fc: ReLU'(y) then dW, db (inputs saved by the forward)
+    C.vlnce_relu_bwd(off(d_xin, Hs), width, off(xin, Hs), width, R, d_out + r_out, st)
+    c, h, w = net.depth_encoder.visual_encoder.output_shape
+    dep_flat = b("s2s_depth_flat", (R, c * h * w))
+    if "net.depth_encoder.visual_fc.1.weight" in g:
+        with leaves():
+            linear_dw(off(d_xin, Hs), width, ptr(dep_flat), c * h * w, ptr(g["net.depth_encoder.visual_fc.1.weight"]),
+                      c * h * w, R, d_out, c * h * w)
+            _colsum(off(d_xin, Hs), width, ptr(g["net.depth_encoder.visual_fc.1.bias"]), R, d_out)
+    cr = net.rgb_encoder.resnet_layer_size
+    rgb = b("s2s_rgb", (R, 1, cr))
+    if "net.rgb_encoder.fc.1.weight" in g:
+        with leaves():
+            linear_dw(off(d_xin, Hs + d_out), width, ptr(rgb), cr, ptr(g["net.rgb_encoder.fc.1.weight"]), cr, R,
+                      r_out, cr)
+            _colsum(off(d_xin, Hs + d_out), width, ptr(g["net.rgb_encoder.fc.1.bias"]), R, r_out)
+    if net.model_config.SEQ2SEQ.use_prev_action:  # seq2seq_policy.py:158-162
+        pa_w = net.prev_action_embedding.weight
+        C.vlnce_prev_action_embed_bwd(ptr(cx["prev"]), ptr(masks_f), off(d_xin, width - 32), width, None, 0,
+                                      ptr(g["net.prev_action_embedding.weight"]), R, 32, pa_w.shape[0], st)
+    br_lstm.join()
+    leaves.join()
+
+
 def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw: Optional[torch.Tensor],
                  d_x: Optional[torch.Tensor], d_hat: Optional[torch.Tensor]):
     """Backward of the last ``eng.forward(..., save=True)``.  ``g`` maps parameter names to
@@ -166,32 +278,7 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     linear_dx(ptr(d_q_s), hk, ptr(net.state_q.weight), ptr(dxcat), eng.cat, R, hk, H, beta=1.0)
     with Branch("lstm_bwd") as br_lstm:
         # 12. instruction encoder (BPTT) — independent of steps 8-11: own stream
-        ie = net.instruction_encoder
-        rnn = ie.encoder_rnn
-        Hs, dirs, E = eng.Hs, eng.dirs, eng.E
-        dgx = b("lstm_dgx", (dirs, R, L, 4 * Hs))
-        hprev = b("lstm_hprev", (dirs, R, L, Hs))
-        C.vlnce_lstm_seq_bwd(ptr(d_instr), ptr(b("lstm_gates", (dirs, R, L, 4 * Hs))), ptr(b("lstm_c", (dirs, R, L, Hs))),
-                             ptr(instr), ptr(rnn.weight_hh_l0), ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None,
-                             ptr(cx["lengths"]), ptr(dgx), ptr(hprev), R, L, Hs, dirs, lib.stream())
-        emb_in = b("instr_emb", (R * L, E)) if ie.config.sensor_uuid == "instruction" else cx["rxr"]
-        emb_trainable = ie.config.sensor_uuid == "instruction" and ie.embedding_layer.weight.requires_grad
-        d_emb = b("d_instr_emb", (R * L, E)) if emb_trainable else None
-        for d, sfx in enumerate(["", "_reverse"][:dirs]):
-            dg = off(dgx, d * R * L * 4 * Hs)
-            pfx = "net.instruction_encoder.encoder_rnn."
-            linear_dw(dg, 4 * Hs, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, 4 * Hs, E)
-            linear_dw(dg, 4 * Hs, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, 4 * Hs, Hs)
-            _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, 4 * Hs)
-            _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, 4 * Hs)
-            if emb_trainable:
-                w_ih = getattr(rnn, "weight_ih_l0" + sfx)
-                linear_dx(dg, 4 * Hs, ptr(w_ih), ptr(d_emb), E, R * L, 4 * Hs, E, beta=0.0 if d == 0 else 1.0)
-        if emb_trainable:
-            el = ie.embedding_layer
-            pad = -1 if el.padding_idx is None else el.padding_idx
-            C.vlnce_embedding_bwd(ptr(cx["ids"]), ptr(d_emb), E, ptr(g["net.instruction_encoder.embedding_layer.weight"]),
-                                  R * L, E, el.num_embeddings, pad, lib.stream())
+        instruction_backward(eng, g, d_instr)
 
     # 8. first GRU (dh = dxcat[:, :H])
     d_state_in = b("d_state_in", (R, eng.state_in))
@@ -258,7 +345,7 @@ class CMAFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, _d_h, d_hat):
-        eng: CMAEngine = ctx.eng
+        eng = ctx.eng  # CMAEngine | Seq2SeqEngine: both expose run_backward
         if eng.ctx.get("token") is not ctx.token:
             raise lib.VlnceError("backward() after another forward on the same policy: the saved workspace was "
                                  "overwritten (the reference's trainers never interleave them)")
@@ -275,7 +362,7 @@ class CMAFunction(torch.autograd.Function):
             lp = eng.buf("logits", (R, A))
             d_raw = eng.buf("d_raw", (R, A))
             C.vlnce_log_softmax_bwd(ptr(lp), ptr(d_out), ptr(d_raw), R, A, lib.stream())
-            cma_backward(eng, ctx.head, g, d_raw, None, d_hat)
+            eng.run_backward(ctx.head, g, d_raw, None, d_hat)
         else:
-            cma_backward(eng, None, g, None, d_out, d_hat)
+            eng.run_backward(None, g, None, d_out, d_hat)
         return (None,) * 7 + tuple(g[n] for n in ctx.names)

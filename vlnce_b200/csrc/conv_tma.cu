@@ -35,15 +35,19 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
+#include <stdlib.h>
+
 namespace vlnce {
 namespace {
 
 using namespace ptx;
 
 constexpr int TH = 16, TW = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                       // two groups of four: each TMEM lane quarter is read by 2 warps
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = kEpiThreads + 3 * 32;     // + MMA issuer, activation producer, weight producer
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kMaxA = 4, kMaxB = 18;
+constexpr int kMaxA = 8, kMaxB = 18;
 
 struct TmaConvParams {
   const float* scale;
@@ -52,9 +56,11 @@ struct TmaConvParams {
   int M;           // rows mode: N*H*W
   int N, H, W, C, K;
   int c_chunks, n_tiles, m_tiles, tiles_x, tiles_y;
+  float rcp_n_tiles, rcp_tiles_x, rcp_tiles_y;  // float reciprocals for the division-free tile decode
   int tw, th;      // output patch of one sub-tile (halo 8x16, stem 128x1)
   int w_cols;      // K extent of one filter tap in the weight matrix (C; stem: 0, chunks are consecutive)
   int b_stationary;  // 1: b_stages == taps*c_chunks and the weight slice is loaded once per CTA
+  long long* trace;  // debug: per-role (event, clock64) records of CTA 0 (vlnce_debug_set_trace), else NULL
   int taps;        // 1 | 9
   int halo_w;      // 8 (rows mode: plain 8-row groups) | 10
   int a_bytes;     // ring slot size (1024-multiple), a_tx = bytes the TMA delivers
@@ -84,23 +90,52 @@ __device__ __forceinline__ uint64_t desc_sbo(uint32_t smem_addr, uint32_t sbo_by
   return d;
 }
 
+// Debug trace (CTA 0 only): role 0 activation producer / 1 MMA issuer / 2 epilogue thread 0 / 3 weight
+// producer; up to kTraceCap
+// records per role of {event << 32 | index, clock64}.
+constexpr int kTraceCap = 768;
+struct Trace {
+  long long* base;
+  int n;
+  __device__ __forceinline__ Trace(long long* t, int role) : base(t ? t + (size_t)role * kTraceCap * 2 : nullptr), n(0) {
+    if (blockIdx.x != 0) base = nullptr;
+  }
+  __device__ __forceinline__ void rec(int ev, int idx) {
+    if (base != nullptr && n < kTraceCap) {
+      base[2 * n] = ((long long)ev << 32) | (unsigned)idx;
+      base[2 * n + 1] = clock64();
+      ++n;
+    }
+  }
+};
+
 struct Tile {
   int n0;            // first filter
   int m0;            // rows mode: first pixel row
   int x0, y0, img;   // halo mode: patch origin
 };
 
+// q = a / d, r = a % d for 0 <= a < 2^24 without the ~100-cycle integer-division sequence (the
+// producer / epilogue roles are single threads: their instruction latency IS the pipeline's period)
+__device__ __forceinline__ int fast_divmod(int a, int d, float rcp, int& r) {
+  int q = __float2int_rz(__int2float_rn(a) * rcp);
+  r = a - q * d;
+  if (r < 0) { --q; r += d; }
+  else if (r >= d) { ++q; r -= d; }
+  return q;
+}
+
 // scheduled tile t = (pixel super-tile, filter tile); sub-tile h of MT
 __device__ __forceinline__ Tile decode_tile(const TmaConvParams& p, int t, int block_n, int mt, int h) {
   Tile ti;
-  const int n_tile = t % p.n_tiles;
-  int m = (t / p.n_tiles) * mt + h;
+  int n_tile, xi, yi;
+  int m = fast_divmod(t, p.n_tiles, p.rcp_n_tiles, n_tile) * mt + h;
   ti.n0 = n_tile * block_n;
   ti.m0 = m * 128;
-  ti.x0 = (m % p.tiles_x) * p.tw;
-  m /= p.tiles_x;
-  ti.y0 = (m % p.tiles_y) * p.th;
-  ti.img = m / p.tiles_y;
+  m = fast_divmod(m, p.tiles_x, p.rcp_tiles_x, xi);
+  ti.x0 = xi * p.tw;
+  ti.img = fast_divmod(m, p.tiles_y, p.rcp_tiles_y, yi);
+  ti.y0 = yi * p.th;
   return ti;
 }
 
@@ -111,6 +146,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                 const TmaConvParams p) {
   static_assert(2 * MT * BLOCK_N <= 512, "two accumulator sets must fit the 512 TMEM columns");
   constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int NI = BLOCK_N / 64;  // 32-column epilogue iterations per warp (each warp owns half the columns)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -134,12 +170,12 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const int total_tiles = (p.m_tiles / MT) * p.n_tiles;  // host guarantees m_tiles % MT == 0
   const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (threadIdx.x == 5 * 32) {
+  if (threadIdx.x == (kEpiWarps + 1) * 32) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 128);
+      mbar_init(&acc_empty[s], kEpiThreads);
       mbar_init(&res_full[s], 1);
       mbar_init(&stg_free[s], 1);
     }
@@ -148,7 +184,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_y);
   }
-  if (warp == 4) {
+  if (warp == kEpiWarps) {
     tmem_alloc(tmem_slot, 2 * MT * BLOCK_N);
     tmem_relinquish();
   }
@@ -157,142 +193,179 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0 && my_tiles > 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      const int steps = my_tiles * p.c_chunks;
-      auto load_a = [&](int j) {  // activation slot of chunk-step j (tile j / c_chunks, chunk j % c_chunks)
-        const int t = blockIdx.x + (j / p.c_chunks) * gridDim.x;
-        const int cc = j % p.c_chunks;
-        mbar_wait(&a_empty[as], aph ^ 1, 21);
-        mbar_arrive_expect_tx(&a_full[as], MT * p.a_tx);
-#pragma unroll
-        for (int h = 0; h < MT; ++h) {
-          const Tile ti = decode_tile(p, t, BLOCK_N, MT, h);
-          const uint32_t dst = smem_a0 + as * a_slot + h * p.a_bytes;
-          if (p.mode == 0) tma_load_2d(dst, &tmap_x, &a_full[as], cc * 64, ti.m0);
-          else if (p.mode == 1) tma_load_4d(dst, &tmap_x, &a_full[as], cc * 64, ti.x0 - 1, ti.y0 - 1, ti.img);
-          else tma_load_4d(dst, &tmap_x, &a_full[as], 0, ti.x0, ti.y0 + cc, ti.img);
-        }
-        if (++as == p.a_stages) { as = 0; aph ^= 1; }
-      };
-      load_a(0);
-      for (int j = 0; j < steps; ++j) {
-        if (j + 1 < steps) load_a(j + 1);  // one chunk ahead, across tile boundaries
-        const int it = j / p.c_chunks, cc = j % p.c_chunks;
+  if (warp == kEpiWarps + 1) {
+    // ------------------------------------------------------------ activation producer (one thread)
+    if (lane == 0) {
+      int as = 0;
+      uint32_t aph = 0;
+      Trace tr(p.trace, 0);
+      for (int it = 0; it < my_tiles; ++it) {
         const int t = blockIdx.x + it * gridDim.x;
-        const int n0 = (t % p.n_tiles) * BLOCK_N;
-        if (!p.b_stationary || it == 0) {
-          for (int tap = 0; tap < p.taps; ++tap) {
-            mbar_wait(&b_empty[bs], bph ^ 1, 22);
-            mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
-            tma_load_2d(smem_b0 + bs * B_BYTES, &tmap_w, &b_full[bs], tap * p.w_cols + cc * 64, n0);
-            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-          }
-        }
-        if (p.has_res && cc == p.c_chunks - 1) {
-          // residual tiles of this tile's sub-tiles -> their staging buffers (free once the store that
-          // last used the buffer has been read out of shared memory)
+        Tile ti[MT];
+#pragma unroll
+        for (int h = 0; h < MT; ++h) ti[h] = decode_tile(p, t, BLOCK_N, MT, h);
+        for (int cc = 0; cc < p.c_chunks; ++cc) {
+          mbar_wait(&a_empty[as], aph ^ 1, 21);
+          tr.rec(2, it * p.c_chunks + cc);
+          mbar_arrive_expect_tx(&a_full[as], MT * p.a_tx);
 #pragma unroll
           for (int h = 0; h < MT; ++h) {
-            const int vt = it * MT + h;
-            const int sb = vt % p.stg_bufs;
-            const uint32_t v = (uint32_t)(vt / p.stg_bufs);
-            const Tile ti = decode_tile(p, t, BLOCK_N, MT, h);
-            mbar_wait(&stg_free[sb], (v & 1) ^ 1, 23);
-            mbar_arrive_expect_tx(&res_full[sb], 128 * BLOCK_N * 2);
-            for (int b = 0; b < BLOCK_N / 64; ++b) {
-              const uint32_t dst = stage_out + sb * stg_bytes + (uint32_t)b * (128 * 128);
-              if (p.mode == 0) tma_load_2d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.m0);
-              else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.x0, ti.y0, ti.img);
-            }
+            const uint32_t dst = smem_a0 + as * a_slot + h * p.a_bytes;
+            if (p.mode == 0) tma_load_2d(dst, &tmap_x, &a_full[as], cc * 64, ti[h].m0);
+            else if (p.mode == 1) tma_load_4d(dst, &tmap_x, &a_full[as], cc * 64, ti[h].x0 - 1, ti[h].y0 - 1, ti[h].img);
+            else tma_load_4d(dst, &tmap_x, &a_full[as], 0, ti[h].x0, ti[h].y0 + cc, ti[h].img);
+          }
+          tr.rec(3, it * p.c_chunks + cc);
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kEpiWarps + 2) {
+    // ------------------------------------------------------------ weight producer (one thread)
+    if (lane == 0) {
+      int bs = 0;
+      uint32_t bph = 0;
+      Trace tr(p.trace, 3);
+      const int tiles_b = p.b_stationary ? (my_tiles > 0 ? 1 : 0) : my_tiles;  // stationary: loaded once
+      for (int it = 0; it < tiles_b; ++it) {
+        int n_tile;
+        fast_divmod(blockIdx.x + it * gridDim.x, p.n_tiles, p.rcp_n_tiles, n_tile);
+        const int n0 = n_tile * BLOCK_N;
+        for (int cc = 0; cc < p.c_chunks; ++cc) {
+          int col = cc * 64;
+          for (int tap = 0; tap < p.taps; ++tap, col += p.w_cols) {
+            mbar_wait(&b_empty[bs], bph ^ 1, 22);
+            tr.rec(4, it * p.c_chunks + cc);
+            mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
+            tma_load_2d(smem_b0 + bs * B_BYTES, &tmap_w, &b_full[bs], col, n0);
+            tr.rec(5, it * p.c_chunks + cc);
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
-    // ------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_f16(128, BLOCK_N, p.ab_half ? 0u : 1u);
-    const uint32_t sbo = (uint32_t)p.halo_w * 128u;
-    int as = 0, bs = 0;
-    uint32_t aph = 0, bph = 0;
-    for (int it = 0; it < my_tiles; ++it) {
-      const int buf = it & 1;
-      const uint32_t u = (uint32_t)(it >> 1);
-      mbar_wait(&acc_empty[buf], (u & 1) ^ 1, 24);  // epilogue has drained this accumulator set
-      tc_fence_after_sync();
-      const uint32_t tmem_acc = tmem_base + buf * (MT * BLOCK_N);
-      for (int cc = 0; cc < p.c_chunks; ++cc) {
-        mbar_wait(&a_full[as], aph, 25);
-        for (int tap = 0; tap < p.taps; ++tap) {
-          if (!p.b_stationary || it == 0) mbar_wait(&b_full[bs], bph, 26);
-          tc_fence_after_sync();
-          if (lane == 0) {
-            const int r = tap / 3, s = tap - 3 * r;
-            const uint64_t bdesc = make_smem_desc(smem_b0 + bs * B_BYTES, 128);
+  } else if (warp == kEpiWarps) {
+    // ------------------------------------------------------------ MMA issuer (one thread: no per-step
+    // warp reconvergence; this thread's instruction latency bounds the pipeline period)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, BLOCK_N, p.ab_half ? 0u : 1u);
+      const uint32_t sbo = (uint32_t)p.halo_w * 128u;
+      // descriptor constants: only the 14-bit start-address field changes between MMAs
+      const uint64_t a_hi = desc_sbo(0, sbo), b_hi = make_smem_desc(0, 128);
+      const int rs = p.taps == 9 ? 3 : 1;
+      const uint32_t row_step = (uint32_t)p.halo_w * 128u;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      Trace tr(p.trace, 1);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int buf = it & 1;
+        const uint32_t u = (uint32_t)(it >> 1);
+        mbar_wait(&acc_empty[buf], (u & 1) ^ 1, 24);  // epilogue has drained this accumulator set
+        tr.rec(10, it);
+        tc_fence_after_sync();
+        const uint32_t tmem_acc = tmem_base + buf * (MT * BLOCK_N);
+        const bool wait_b = !p.b_stationary || it == 0;
+        uint32_t first = 0;  // 0 until the first MMA of the tile has been issued (it overwrites the accumulator)
+        for (int cc = 0; cc < p.c_chunks; ++cc) {
+          mbar_wait(&a_full[as], aph, 25);
+          tr.rec(11, it * p.c_chunks + cc);
+          uint32_t a_row = smem_a0 + as * a_slot;
+          for (int r = 0; r < rs; ++r, a_row += row_step) {
+            uint32_t a_tap = a_row;
+            for (int sx = 0; sx < rs; ++sx, a_tap += 128) {
+              if (wait_b) mbar_wait(&b_full[bs], bph, 26);
+              tc_fence_after_sync();
+              const uint64_t bdesc = b_hi | (uint64_t)(((smem_b0 + bs * B_BYTES) & 0x3FFFFu) >> 4);
 #pragma unroll
-            for (int h = 0; h < MT; ++h) {
-              const uint64_t adesc =
-                  desc_sbo(smem_a0 + as * a_slot + h * p.a_bytes + (r * p.halo_w + s) * 128, sbo);
+              for (int h = 0; h < MT; ++h) {
+                const uint64_t adesc = a_hi | (uint64_t)(((a_tap + h * p.a_bytes) & 0x3FFFFu) >> 4);
+                umma_bf16(tmem_acc + h * BLOCK_N, adesc, bdesc, idesc, first);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_acc + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc,
-                          (uint32_t)((cc | tap | k) != 0));
+                for (int k = 1; k < 4; ++k) umma_bf16(tmem_acc + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+              }
+              first = 1;
+              if (!p.b_stationary) umma_commit(&b_empty[bs]);
+              if (r == rs - 1 && sx == rs - 1) umma_commit(&a_empty[as]);
+              tr.rec(13, it * p.c_chunks + cc);
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
             }
-            if (!p.b_stationary) umma_commit(&b_empty[bs]);
-            if (tap == p.taps - 1) umma_commit(&a_empty[as]);
           }
-          __syncwarp();
-          if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
-        if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        umma_commit(&acc_full[buf]);
       }
-      if (lane == 0) umma_commit(&acc_full[buf]);
-      __syncwarp();
     }
+    __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue (warps 0-3)
-    const int row = warp * 32 + lane;
+    // ------------------------------------------------------------ epilogue (warps 0-7)
+    // warp w reads TMEM lanes 32*(w&3).. (its hardware-accessible quarter) and the column half w>>2.
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const int total_vt = my_tiles * MT;
+    Trace tr(threadIdx.x == 0 ? p.trace : nullptr, 2);
+    // thread 0 also owns the residual prefetch: a staging buffer is refilled with the residual of its
+    // next sub-tile as soon as the TMA store that last read it has drained (no producer round trip)
+    auto issue_res = [&](int vt) {
+      const int it2 = vt / MT, h2 = vt % MT;
+      const int sb = vt % p.stg_bufs;
+      const Tile ti = decode_tile(p, blockIdx.x + it2 * gridDim.x, BLOCK_N, MT, h2);
+      mbar_arrive_expect_tx(&res_full[sb], 128 * BLOCK_N * 2);
+      for (int b = 0; b < BLOCK_N / 64; ++b) {
+        const uint32_t dst = stage_out + sb * stg_bytes + (uint32_t)b * (128 * 128);
+        if (p.mode == 0) tma_load_2d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.m0);
+        else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.x0, ti.y0, ti.img);
+      }
+    };
+    if (threadIdx.x == 0 && p.has_res)
+      for (int vt = 0; vt < p.stg_bufs && vt < total_vt; ++vt) issue_res(vt);
     for (int it = 0; it < my_tiles; ++it) {
       const int buf = it & 1;
       const uint32_t u = (uint32_t)(it >> 1);
+      int n_tile;
+      fast_divmod(blockIdx.x + it * gridDim.x, p.n_tiles, p.rcp_n_tiles, n_tile);
+      const int n0 = n_tile * BLOCK_N;
+      // this warp's folded-norm constants for the tile, fetched while the accumulators are still filling
+      tr.rec(20, it);
       mbar_wait(&acc_full[buf], u & 1, 27);
+      tr.rec(21, it);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int h = 0; h < MT; ++h) {
         const int vt = it * MT + h;   // sub-tiles are the unit of staging / residual / store
         const int sb = vt % p.stg_bufs;
         const uint32_t v = (uint32_t)(vt / p.stg_bufs);
-        const Tile ti = decode_tile(p, blockIdx.x + it * gridDim.x, BLOCK_N, MT, h);
         const uint32_t stg = stage_out + sb * stg_bytes;
         if (p.has_res) mbar_wait(&res_full[sb], v & 1, 28);   // residual landed (implies staging free)
         else mbar_wait(&stg_free[sb], (v & 1) ^ 1, 29);       // previous store has left the staging buffer
-        const uint32_t t_row = tmem_base + (buf * MT + h) * BLOCK_N + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-        for (int cb = 0; cb < BLOCK_N / 32; ++cb) {
-          uint32_t vv[32];
-          tmem_ld_32x32(t_row + cb * 32, vv);
-          tmem_ld_wait();
-          if (h == MT - 1 && cb == BLOCK_N / 32 - 1) {  // accumulators fully read: hand them back to the MMA warp
-            tc_fence_before_sync();
-            mbar_arrive(&acc_empty[buf]);
+        const uint32_t t_row = tmem_base + (buf * MT + h) * BLOCK_N + ((uint32_t)(q * 32) << 16);
+        uint32_t vv[2][32];
+        tmem_ld_32x32(t_row + (half * NI) * 32, vv[0]);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int cb = half * NI + i;
+          const int col0 = n0 + cb * 32;
+          float4 sc[8], sh[8];
+          if (p.scale != nullptr) {   // issued before the TMEM wait: both latencies overlap
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              sc[j4] = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + j4);
+              sh[j4] = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + j4);
+            }
           }
-          const int col0 = ti.n0 + cb * 32;
+          tmem_ld_wait();
+          if (i + 1 < NI) tmem_ld_32x32(t_row + (cb + 1) * 32, vv[(i + 1) & 1]);
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vv[j]);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vv[i & 1][j]);
           if (p.scale != nullptr) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0) + j4);
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0) + j4);
-              f[j4 * 4 + 0] = fmaf(f[j4 * 4 + 0], sc.x, sh.x);
-              f[j4 * 4 + 1] = fmaf(f[j4 * 4 + 1], sc.y, sh.y);
-              f[j4 * 4 + 2] = fmaf(f[j4 * 4 + 2], sc.z, sh.z);
-              f[j4 * 4 + 3] = fmaf(f[j4 * 4 + 3], sc.w, sh.w);
+              f[j4 * 4 + 0] = fmaf(f[j4 * 4 + 0], sc[j4].x, sh[j4].x);
+              f[j4 * 4 + 1] = fmaf(f[j4 * 4 + 1], sc[j4].y, sh[j4].y);
+              f[j4 * 4 + 2] = fmaf(f[j4 * 4 + 2], sc[j4].z, sh[j4].z);
+              f[j4 * 4 + 3] = fmaf(f[j4 * 4 + 3], sc[j4].w, sh[j4].w);
             }
           }
           if (p.y_fp32) {
@@ -351,9 +424,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             }
           }
         }
+        if (h == MT - 1) {  // this thread's share of both accumulators is in registers / staged: hand them back
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
+        }
+        tr.rec(22, vt);
         fence_proxy_async_smem();
-        named_barrier_sync(1, 128);
+        named_barrier_sync(1, kEpiThreads);
+        tr.rec(23, vt);
         if (threadIdx.x == 0) {
+          const Tile ti = decode_tile(p, blockIdx.x + it * gridDim.x, BLOCK_N, MT, h);
           const int boxes = p.y_fp32 ? BLOCK_N / 32 : BLOCK_N / 64;
           const int cols = p.y_fp32 ? 32 : 64;
           for (int b = 0; b < boxes; ++b) {
@@ -362,18 +442,21 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             else tma_store_4d_(&tmap_y, src, ti.n0 + b * cols, ti.x0, ti.y0, ti.img);
           }
           tma_store_commit();
-          // release the staging buffer whose store has now been read out of shared memory
+          // a staging buffer is reusable once the store that read it has drained: release it to the other
+          // epilogue threads (stg_free) or refill it with its next sub-tile's residual (res_full)
           if (p.stg_bufs == 2) {
             tma_store_wait_read_n<1>();
-            if (vt >= 1) mbar_arrive(&stg_free[(vt - 1) & 1]);
+            if (vt >= 1) {
+              if (!p.has_res) mbar_arrive(&stg_free[(vt - 1) & 1]);
+              else if (vt + 1 < total_vt) issue_res(vt + 1);
+            }
           } else {
             tma_store_wait_read_n<0>();
-            mbar_arrive(&stg_free[0]);
+            if (!p.has_res) mbar_arrive(&stg_free[0]);
+            else if (vt + 1 < total_vt) issue_res(vt + 1);
           }
+          tr.rec(24, vt);
         }
-        // with a single staging buffer the other 127 threads must not start overwriting it for the
-        // next sub-tile before thread 0 has seen the bulk read complete: they wait on stg_free /
-        // res_full at the top of the next iteration, which thread 0 arrives on only after the wait
       }
     }
     if (threadIdx.x == 0) tma_store_wait_read_n<0>();
@@ -381,7 +464,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 2 * MT * BLOCK_N);
+  if (warp == kEpiWarps) tmem_dealloc(tmem_base, 2 * MT * BLOCK_N);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -453,6 +536,8 @@ int map_nd(EncodeTiledFn enc, CUtensorMap* m, const void* base, CUtensorMapDataT
   return VLNCE_OK;
 }
 
+long long* g_trace = nullptr;
+
 template <int BLOCK_N, int MT>
 int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr,
            TmaConvParams& p, int b_stages_req, int no_stationary, cudaStream_t stream) {
@@ -500,9 +585,34 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
       }
     }
   }
+  // experiment overrides (ring depths / staging buffers / resident CTAs per SM), read once
+  static int ov_as = -1, ov_bs = -1, ov_stg = -1, ov_ctas = -1;
+  if (ov_as < 0) {
+    const char* e;
+    ov_as = (e = getenv("VLNCE_TMA_AS")) ? atoi(e) : 0;
+    ov_bs = (e = getenv("VLNCE_TMA_BS")) ? atoi(e) : 0;
+    ov_stg = (e = getenv("VLNCE_TMA_STG")) ? atoi(e) : 0;
+    ov_ctas = (e = getenv("VLNCE_TMA_CTAS")) ? atoi(e) : 0;
+  }
+  if (ov_as > 0 && ov_as <= kMaxA) as = ov_as;
+  if (ov_bs > 0 && ov_bs <= kMaxB && !p.b_stationary) bs = ov_bs;
+  if (ov_stg > 0 && ov_stg <= 2) sbufs = ov_stg;
+  while (bytes(as, bs, sbufs) > kSmemBudget) {  // overrides must still fit
+    if (!p.b_stationary && bs > 2) --bs;
+    else if (as > 2) --as;
+    else if (sbufs > 1) --sbufs;
+    else break;
+  }
   p.a_stages = as; p.b_stages = bs; p.stg_bufs = sbufs;
+  p.trace = g_trace;
+  p.rcp_n_tiles = 1.0f / (float)p.n_tiles;
+  p.rcp_tiles_x = 1.0f / (float)p.tiles_x;
+  p.rcp_tiles_y = 1.0f / (float)p.tiles_y;
   const int total = (p.m_tiles / MT) * p.n_tiles;
-  const int grid = total < num_sms ? total : num_sms;
+  int ctas = num_sms;
+  if (ov_ctas > 1 && bytes(as, bs, sbufs) * ov_ctas <= 228 * 1024 - 1024 * ov_ctas && 2 * MT * BLOCK_N * ov_ctas <= 512)
+    ctas = num_sms * ov_ctas;
+  const int grid = total < ctas ? total : ctas;
   conv_tma_kernel<BLOCK_N, MT><<<grid, kThreads, bytes(as, bs, sbufs), stream>>>(tx, tw, ty, tr, p);
   VLNCE_LAUNCH_CHECK("conv_tma_kernel");
   return VLNCE_OK;
@@ -615,6 +725,13 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
   p.relu = relu; p.y_fp32 = f32; p.ab_half = (ab_dtype == VLNCE_F16); p.has_res = residual != nullptr;
   p.a_stages = p.b_stages = p.stg_bufs = 0; p.b_stationary = 0;
   return dispatch(bn, mt, tx, tw, ty, tr, p, b_stages, no_stationary, stream);
+}
+
+// Debug: device buffer of 4 * 768 * 2 int64 that CTA 0 of every later conv_tma launch fills with
+// (event, clock64) records per role (producer / MMA issuer / epilogue); NULL switches tracing off.
+extern "C" int vlnce_debug_set_trace(void* buffer) {
+  g_trace = reinterpret_cast<long long*>(buffer);
+  return VLNCE_OK;
 }
 
 // (N,H,W,3) u8|f32 image -> (N, P+3, Q+3, 16) 16-bit space-to-depth cells (see stem_s2d_kernel);

@@ -211,6 +211,23 @@ lstm_seq_bwd_kernel(const float* __restrict__ dout,   // (R, L, dirs*H)
 }
 
 // ------------------------------------------------------------------------------------
+// Gradient of a final-state-only sequence encoder (instruction_encoder.py:87-90, h_n of the packed
+// sequence = the output at token lengths[r]-1): dout (R, L, H) = 0 except dout[r, lengths[r]-1, :] = dh[r].
+// ------------------------------------------------------------------------------------
+__global__ void scatter_last_token_kernel(const float* __restrict__ dh, long long lddh,
+                                          const int* __restrict__ lengths, float* __restrict__ dout, int R,
+                                          int L, int H) {
+  const long long total = (long long)R * L * H;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % H);
+    const int t = (int)((idx / H) % L);
+    const int r = (int)(idx / ((long long)H * L));
+    dout[idx] = (t == lengths[r] - 1) ? dh[r * lddh + c] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // embedding-table scatters (few rows per entry -> fp32 atomics)
 // ------------------------------------------------------------------------------------
 __global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ d,
@@ -237,7 +254,7 @@ __global__ void prev_action_embed_bwd_kernel(const long long* __restrict__ prev,
     const int r = idx / dim, c = idx % dim;
     long long id = (long long)(((float)prev[r] + 1.f) * masks[r]);
     if (id < 0 || id >= table_rows) id = 0;
-    atomicAdd(dtable + id * dim + c, d1[r * ld1 + c] + d2[r * ld2 + c]);
+    atomicAdd(dtable + id * dim + c, d1[r * ld1 + c] + (d2 != nullptr ? d2[r * ld2 + c] : 0.f));
   }
 }
 
@@ -461,6 +478,14 @@ extern "C" int vlnce_lstm_seq_bwd(const float* dout, const float* gates, const f
   return VLNCE_OK;
 }
 
+extern "C" int vlnce_scatter_last_token(const float* dh, long long lddh, const int* lengths, float* dout, int R,
+                                        int L, int H, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(dh && lengths && dout && R > 0 && L > 0 && H > 0, "scatter_last_token: bad arguments");
+  scatter_last_token_kernel<<<grid_for((long long)R * L * H, 256), 256, 0, stream>>>(dh, lddh, lengths, dout, R, L, H);
+  VLNCE_LAUNCH_CHECK("scatter_last_token_kernel");
+  return VLNCE_OK;
+}
+
 extern "C" int vlnce_embedding_bwd(const long long* ids, const float* d, long long ldd, float* dtable,
                                    long long rows, int dim, int vocab, int padding_idx,
                                    cudaStream_t stream) {
@@ -474,7 +499,7 @@ extern "C" int vlnce_embedding_bwd(const long long* ids, const float* d, long lo
 extern "C" int vlnce_prev_action_embed_bwd(const long long* prev_actions, const float* masks, const float* d1,
                                            long long ld1, const float* d2, long long ld2, float* dtable,
                                            int rows, int dim, int table_rows, cudaStream_t stream) {
-  VLNCE_CHECK_ARG(prev_actions && masks && d1 && d2 && dtable && rows > 0, "prev_action_embed_bwd: bad arguments");
+  VLNCE_CHECK_ARG(prev_actions && masks && d1 && dtable && rows > 0, "prev_action_embed_bwd: bad arguments");
   prev_action_embed_bwd_kernel<<<grid_for((long long)rows * dim, 256), 256, 0, stream>>>(
       prev_actions, masks, d1, ld1, d2, ld2, dtable, rows, dim, table_rows);
   VLNCE_LAUNCH_CHECK("prev_action_embed_bwd_kernel");

@@ -245,6 +245,12 @@ class CMAEngine(HeadEngine):
         self.state_in = self.rgb_out + self.depth_out + 32
         self.cat = self.H + self.Dt + self.rgb_out + self.depth_out + 32
 
+    def run_backward(self, head_linear, g, d_raw, d_x, d_hat):
+        """Hand-written backward of the last ``forward(save=True)`` (backward.cma_backward)."""
+        from .backward import cma_backward
+
+        return cma_backward(self, head_linear, g, d_raw, d_x, d_hat)
+
     # ------------------------------------------------------------------ forward
     def visual_buffers(self, R, slot: str):
         """(rgb (R,16,2112), depth (R,16,192)) fp32 feature buffers of a named slot."""

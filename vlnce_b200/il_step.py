@@ -18,7 +18,7 @@ import torch
 
 from . import lib
 from .aux_losses import AuxLosses
-from .backward import cma_backward, trainable_named
+from .backward import trainable_named
 from .lib import C, ptr
 
 
@@ -163,7 +163,7 @@ class ILTrainerStep:
                         float(net.model_config.PROGRESS_MONITOR.alpha), 1.0 / float(loss_accumulation_scalar),
                         T, N, A, ptr(d_raw), ptr(d_hat), ptr(self._losses), st)
         fp.grad.zero_()
-        cma_backward(eng, head, fp.grad_views, d_raw, None, d_hat if use_pm else None)
+        eng.run_backward(head, fp.grad_views, d_raw, None, d_hat if use_pm else None)
 
     def apply_grads(self, step_grad: bool = True, allreduce: bool = True):
         fp = self.fp

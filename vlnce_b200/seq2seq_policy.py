@@ -21,7 +21,19 @@ from .policy import ILPolicy
 class Seq2SeqEngine(HeadEngine):
     """Launch plan of ``Seq2SeqNet.forward`` (seq2seq_policy.py:142-179)."""
 
-    def forward(self, observations, rnn_states, prev_actions, masks, save: bool = False):
+    def __init__(self, net, precision: str = "bf16"):
+        super().__init__(net, precision)
+        ie = net.instruction_encoder
+        self.Hs, self.dirs, self.E = ie.config.hidden_size, (2 if ie.config.bidirectional else 1), ie.config.embedding_size
+
+    def run_backward(self, head_linear, g, d_raw, d_x, d_hat):
+        """Hand-written backward of the last ``forward(save=True)`` (backward.seq2seq_backward)."""
+        from .backward import seq2seq_backward
+
+        return seq2seq_backward(self, head_linear, g, d_raw, d_x, d_hat)
+
+    def forward(self, observations, rnn_states, prev_actions, masks, save: bool = False, visual=None):
+        assert visual is None, "the pipelined trunk prefetch is built for the CMA engine only"
         net = self.net
         cfg = net.model_config
         rnn_states, masks_f, prev, R, N, T = self._prep_rows(rnn_states, prev_actions, masks)
@@ -36,7 +48,7 @@ class Seq2SeqEngine(HeadEngine):
         width = Hs + d_out + r_out + (32 if cfg.SEQ2SEQ.use_prev_action else 0)
         xin = self.buf("s2s_in", (R, width))
         # instruction final hidden state -> xin[:, :Hs]
-        _, hn, _, _ = self._encode_instruction(observations, R, save)
+        _, hn, lengths, L = self._encode_instruction(observations, R, save)
         ones = self.buf("ones", (R,))
         ones.fill_(1.0)
         C.vlnce_mask_rows(ptr(hn), Hs, ptr(ones), ptr(xin), width, R, Hs, st)
@@ -67,7 +79,8 @@ class Seq2SeqEngine(HeadEngine):
             hat = self.buf("progress_hat", (R, 1))
             pm = net.progress_monitor
             linear(ptr(x_out), H, ptr(pm.weight), ptr(hat), 1, ptr(pm.bias), R, 1, H, act=2)
-        self.ctx.update(R=R, N=N, T=T, saved=save)
+        self.ctx.update(R=R, N=N, T=T, L=L, lengths=lengths, prev=prev, d_out=d_out, r_out=r_out, width=width,
+                        saved=save)
         return x_out, h_out, hat
 
 
@@ -122,17 +135,13 @@ class Seq2SeqNet(Net):
         return eng
 
     def _run(self, head_linear, observations, rnn_states, prev_actions, masks):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "Seq2SeqPolicy training (hand-written backward) is not built yet; wrap calls in torch.no_grad() — "
-                "act()/eval/inference run on the CUDA library.  (CMAPolicy trains; see DESIGN.md scope table.)")
-        eng = self.engine()
-        x, h_out, hat = eng.forward(observations, rnn_states, prev_actions, masks, save=False)
-        out = x if head_linear is None else eng.action_logits(head_linear, x, x.shape[0])
+        from .autograd import cma_features  # one autograd node around the engine (forward + hand-written backward)
+
+        out, h_out, hat = cma_features(self, head_linear, observations, rnn_states, prev_actions, masks)
         if hat is not None and AuxLosses.is_active():  # seq2seq_policy.py:166-177
-            loss = F.mse_loss(hat.clone().squeeze(1), observations["progress"], reduction="none")
+            loss = F.mse_loss(hat.squeeze(1), observations["progress"], reduction="none")
             AuxLosses.register_loss("progress_monitor", loss, self.model_config.PROGRESS_MONITOR.alpha)
-        return out.clone(), h_out.clone()
+        return out, h_out
 
     def forward(self, observations, rnn_states, prev_actions, masks):
         return self._run(None, observations, rnn_states, prev_actions, masks)

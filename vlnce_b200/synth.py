@@ -60,7 +60,7 @@ def make_act_batch(seed: int, n: int, hw: int = 256, rgb_hw: int | None = None,
 
 def make_train_batch(seed: int, t: int, n: int, hw: int = 256, rgb_hw: int | None = None,
                      length: int = 80, vocab: int = 2504, num_actions: int = 4,
-                     coef: float = 3.2, ragged: bool = True, features: bool = False):
+                     coef: float = 3.2, ragged: bool = True, features: bool = False, rgb_feature_hw: int = 4):
     """One ``_update_agent`` call in the collate_fn layout: returns
     (observations, prev_actions (T*N,1), not_done_masks (T*N,1) u8,
     corrected_actions (T,N) i64, weights (T,N) f32)."""
@@ -71,7 +71,8 @@ def make_train_batch(seed: int, t: int, n: int, hw: int = 256, rgb_hw: int | Non
     instr = make_instruction(gen, n, length, vocab).unsqueeze(0).expand(t, n, length).reshape(r, length)
     obs: Dict[str, torch.Tensor] = {"instruction": instr.contiguous()}
     if features:  # DAgger caches frozen-CNN features (dagger_trainer.py:300-314)
-        obs["rgb_features"] = torch.rand(r, 2048, 4, 4, generator=gen)
+        # spatial encoders (CMA) cache the 4x4 map, the Seq2Seq encoder its globally pooled 1x1 output
+        obs["rgb_features"] = torch.rand(r, 2048, rgb_feature_hw, rgb_feature_hw, generator=gen)
         obs["depth_features"] = torch.rand(r, 128, 4, 4, generator=gen)
     else:
         obs["rgb"] = torch.randint(0, 256, (r, rgb_hw, rgb_hw, 3), generator=gen, dtype=torch.uint8)
