@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Turn the raw ncu outputs of a GPU visit (gpurun_out/) into the tracked summaries under profiles/.
+
+    python tools/summarize_profiles.py launches gpurun_out/launches_step.csv profiles/r01c_launches_step.md
+    python tools/summarize_profiles.py full gpurun_out/x.ncu-rep profiles/r01c_conv_tma_ncu_full.md
+"""
+import collections
+import csv
+import io
+import re
+import subprocess
+import sys
+
+METRICS = [
+    "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+]
+
+
+def short(k):
+    k = re.sub(r"void |vlnce::|<unnamed>::|unnamed>::|\(anonymous namespace\)::", "", k)
+    return re.sub(r"\(.*", "", k)
+
+
+def launches(src, dst, note=""):
+    txt = open(src).read()
+    rows = list(csv.DictReader(io.StringIO(txt[txt.index('"ID"'):])))
+    agg, tot, n = collections.OrderedDict(), 0.0, 0
+    for r in rows:
+        if r["Metric Name"] != "gpu__time_duration.sum":
+            continue
+        us = float(r["Metric Value"]) / 1e3
+        a = agg.setdefault(short(r["Kernel Name"]), [0, 0.0])
+        a[0] += 1
+        a[1] += us
+        tot += us
+        n += 1
+    conv = sum(us for k, (_, us) in agg.items() if k.startswith("conv_"))
+    with open(dst, "w") as f:
+        f.write("# launch list of one training step (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n")
+        f.write("Command: `ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv "
+                "python bench.py --ncu-step --no-cpu-baseline` (one eager, serial-stream step between "
+                "cudaProfilerStart/Stop; B200, batch 64, bf16/fp16 trunks).  Cold-cache serialised launch times: "
+                "compare SHARES, not absolutes.\n" + note + "\n")
+        f.write(f"One step = {n} launches, {tot:.0f} us summed device time.\n\n| kernel | launches | us | share |\n|---|---:|---:|---:|\n")
+        for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {c} | {us:.1f} | {100 * us / tot:.1f}% |\n")
+        f.write(f"\ntcgen05 conv tiles (`conv_tma_kernel` + `conv_umma_kernel`, all shapes): {conv:.0f} us = "
+                f"{100 * conv / tot:.1f}% of the step (bench.py's live CUDA-event measurement of the same launches: "
+                "`roofline.conv_ms_per_step`).\n")
+
+
+def full(src, dst, note=""):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    with open(dst, "w") as f:
+        f.write("# ncu --set full captures\n\n" + note + "\n\n")
+        for i, r in enumerate(rows[2:]):
+            f.write(f"## launch {i}: `{short(r[hdr.index('Kernel Name')])}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for m in METRICS:
+                if m in hdr:
+                    j = hdr.index(m)
+                    f.write(f"| `{m}` | {r[j]} | {units[j]} |\n")
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])
