@@ -40,10 +40,30 @@ CASES = {
     "seq2seq_train_features": dict(policy="Seq2SeqPolicy", pm=False, kind="train", t=4, n=3, hw=256,
                                    length=24, wseed=18, iseed=108, bn_train=False, features=True,
                                    prev_action=True),
+    # Waypoint path (BASELINE config C4 dims, 1-wpn-cc.yaml): act on a fresh/continuing env pair,
+    # and one PPO mini-batch (evaluate_actions -> WDDPPO losses -> gradients)
+    "wp_act": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=40, wseed=21, iseed=201),
+    "wp_act_u8": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=24, wseed=22, iseed=202, rgb_u8=True),
+    "wp_eval": dict(policy="WaypointPolicy", kind="wp_eval", t=3, n=2, length=32, wseed=23, iseed=203),
 }
+
+WP_OBS_SPACE = dict(rgb=(12, 224, 224, 3), depth=(12, 256, 256, 1))
+
+
+def oracle_impl(case):
+    """The restatement namespace that implements ``case`` (oracle.vlnce or oracle.waypoint)."""
+    if case["policy"] == "WaypointPolicy":
+        from . import waypoint
+
+        return waypoint
+    return vlnce
 
 
 def model_config(case) -> hb017.Config:
+    if case["policy"] == "WaypointPolicy":
+        from . import waypoint
+
+        return waypoint.waypoint_model_config()
     over = dict(PROGRESS_MONITOR=dict(use=bool(case["pm"]), alpha=1.0))
     if case["policy"] == "CMAPolicy":
         return vlnce.cma_model_config(**over)
@@ -53,6 +73,9 @@ def model_config(case) -> hb017.Config:
 
 
 def obs_space(case):
+    if case["policy"] == "WaypointPolicy":
+        return hb017.Dict({"rgb": hb017.Box(0, 255, WP_OBS_SPACE["rgb"], "uint8"),
+                           "depth": hb017.Box(0.0, 1.0, WP_OBS_SPACE["depth"], "float32")})
     rgb_hw = case.get("rgb_hw", case["hw"])
     return hb017.Dict({"rgb": hb017.Box(0, 255, (rgb_hw, rgb_hw, 3), "uint8"),
                        "depth": hb017.Box(0.0, 1.0, (case["hw"], case["hw"], 1), "float32")})
@@ -61,7 +84,8 @@ def obs_space(case):
 def build_policy(impl, case, num_actions=4):
     """impl: namespace with CMAPolicy / Seq2SeqPolicy (reference import, oracle.vlnce
     or the CUDA package)."""
-    cfg = hb017.Config(MODEL=model_config(case), TORCH_GPU_ID=0)
+    cfg = hb017.Config(MODEL=model_config(case), TORCH_GPU_ID=0,
+                       TASK_CONFIG=dict(TASK=dict(PANO_ROTATIONS=12)))
     cls = getattr(impl, case["policy"])
     pol = cls.from_config(cfg, obs_space(case), hb017.Discrete(num_actions))
     pol.load_state_dict(synth.seeded_state_dict(pol, case["wseed"]))
@@ -69,6 +93,13 @@ def build_policy(impl, case, num_actions=4):
 
 
 def set_mode(pol, case):
+    if case["policy"] == "WaypointPolicy":
+        # ddppo_waypoint_trainer.py:496 (rollouts: agent.eval()) / :526-530 (updates: train() with both
+        # visual encoders forced to eval) — the frozen trunks always run with eval-mode norms
+        pol.train(case["kind"] == "wp_eval")
+        pol.net.rgb_encoder.eval()
+        pol.net.depth_encoder.eval()
+        return
     """``bn_train=False``: whole policy in eval() (what eval/inference and DD-PPO use,
     ``base_il_trainer.py:278``); True: the constructor default (SURVEY Q1)."""
     pol.train(bool(case["bn_train"]))
@@ -79,6 +110,11 @@ def layers_of(case):
 
 
 def inputs(case):
+    if case["kind"] == "wp_act":
+        return synth.make_waypoint_act_batch(case["iseed"], case["n"], length=case["length"],
+                                             rgb_u8=case.get("rgb_u8", False))
+    if case["kind"] == "wp_eval":
+        return synth.make_waypoint_eval_batch(case["iseed"], case["t"], case["n"], length=case["length"])
     if case["kind"] == "act":
         return synth.make_act_batch(case["iseed"], case["n"], hw=case["hw"],
                                     rgb_hw=case.get("rgb_hw"), length=case["length"],
@@ -109,7 +145,7 @@ def run_case(impl, name, aux=None, device=None, precision=None):
     singleton.  ``device`` / ``precision`` select the CUDA package's placement and trunk
     arithmetic.  Returns {key: cpu tensor}."""
     case = CASES[name]
-    aux = aux if aux is not None else impl.AuxLosses
+    aux = aux if aux is not None else getattr(impl, "AuxLosses", None)
     torch.manual_seed(0)
     pol = build_policy(impl, case)
     if device is not None:
@@ -118,6 +154,8 @@ def run_case(impl, name, aux=None, device=None, precision=None):
         pol.net.precision = precision
     set_mode(pol, case)
     out = {}
+    if case["kind"].startswith("wp_"):
+        return _run_waypoint(impl, pol, case, device)
     if case["kind"] == "act":
         obs, h, prev, masks = (_to(v, device) for v in inputs(case))
         aux.deactivate()
@@ -152,3 +190,61 @@ def run_case(impl, name, aux=None, device=None, precision=None):
             g = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu()
             out["grad/" + k] = g.clone() if g.numel() <= 4096 else grad_digest(g)
     return out
+
+
+PPO_KW = dict(clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, use_clipped_value_loss=True,
+              offset_regularize_coef=0.1146, pano_entropy_coef=1.0, offset_entropy_coef=1.0,
+              distance_entropy_coef=1.0)  # config/default.py:179-201; offset/distance entropy coefficients
+# raised from the recipe's 0.0 so that the TruncatedNormal entropy gradients are exercised
+
+
+def _run_waypoint(impl, pol, case, device):
+    """``wp_act``: deterministic ``WaypointPolicy.act`` + ``get_value``.  ``wp_eval``: one PPO mini-batch
+    — ``evaluate_actions`` -> the WDDPPO loss (``common/ddppo_alg.py:56-124``) -> gradients."""
+    out = {}
+    if case["kind"] == "wp_act":
+        obs, h, prev, masks = (_to(v, device) for v in inputs(case))
+        with torch.no_grad():
+            (value, actions, elems, modes, variances, lp, h_out, dist) = pol.act(
+                obs, h, {k: v.clone() for k, v in prev.items()}, masks, deterministic=True)
+            v2 = pol.get_value(obs, h, {k: v.clone() for k, v in prev.items()}, masks)
+        out["value"], out["get_value"] = value.cpu().clone(), v2.cpu().clone()
+        out["pano_stop_logits"] = dist.logits.detach().cpu().clone()
+        out["action_log_probs"] = lp.cpu().clone()
+        out["rnn_states_out"] = h_out.cpu().clone()
+        for k, v in elems.items():
+            out["action/" + k] = v.cpu().clone()
+        for k, v in modes.items():
+            out["mode/" + k] = v.cpu().clone()
+        for k, v in variances.items():
+            out["variance/" + k] = v.cpu().clone()
+        out["stop"] = torch.tensor([a["action"] == "STOP" for a in actions])
+        out["r_theta"] = torch.tensor([[a["action"]["action_args"]["r"], a["action"]["action_args"]["theta"]]
+                                       if a["action"] != "STOP" else [0.0, 0.0] for a in actions])
+        return out
+    sample = tuple(_to(v, device) for v in inputs(case))
+    for p in pol.parameters():
+        p.grad = None
+    loss, parts = wddppo_loss(impl, pol, sample)
+    loss.backward()
+    out["loss"] = torch.tensor(float(loss.detach()))
+    for k, v in parts.items():
+        out["ppo/" + k] = v.detach().cpu().clone() if torch.is_tensor(v) else torch.tensor(float(v))
+    for k, p in pol.named_parameters():
+        if p.requires_grad:
+            g = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu()
+            out["grad/" + k] = g.clone() if g.numel() <= 4096 else grad_digest(g)
+    return out
+
+
+def wddppo_loss(impl, pol, sample):
+    """The mini-batch loss of ``WDDPPO.update`` through ``impl``'s ``evaluate_actions``.  The arithmetic after
+    ``evaluate_actions`` is the restated one (``oracle.waypoint.wddppo_losses``) for every implementation; the
+    reference's own ``WDDPPO.update`` is pinned separately in tests/test_oracle_vs_reference.py."""
+    from . import waypoint
+
+    loss, parts = waypoint.wddppo_losses(pol, sample, **PPO_KW)
+    values, lp, ent, h_out = pol.evaluate_actions(sample[0], sample[1], sample[3], sample[6], sample[2])
+    parts = dict(parts, values=values, action_log_probs=lp, rnn_states_out=h_out,
+                 entropy_pano=ent["pano"], entropy_offset=ent["offset"], entropy_distance=ent["distance"])
+    return loss, parts

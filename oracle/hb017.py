@@ -420,3 +420,50 @@ class Policy(nn.Module, metaclass=abc.ABCMeta):
         self.dim_actions = dim_actions
         self.action_distribution = CategoricalNet(self.net.output_size, self.dim_actions)
         self.critic = CriticHead(self.net.output_size)
+
+
+# --------------------------------------------------------------------------- #
+# habitat_baselines/rl/ppo/ppo.py + rl/ddppo/algo/ddppo.py (v0.1.7): only what
+# ``common/ddppo_alg.py:9-149`` inherits — the constructor (Adam over the parameters
+# that require grad), the four hooks around backward/step (``before_step`` clips the global
+# gradient norm).  The distributed mixin's reducer priming (``before_backward``) is a
+# no-op in a single process.  habitat_baselines/common/rollout_storage.py: the reference
+# subclass overrides every method it uses, so the base is an empty shell.
+# --------------------------------------------------------------------------- #
+class PPO(nn.Module):
+    def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef,
+                 entropy_coef, lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=True,
+                 use_normalized_advantage=True):
+        super().__init__()
+        self.actor_critic = actor_critic
+        self.clip_param, self.ppo_epoch, self.num_mini_batch = clip_param, ppo_epoch, num_mini_batch
+        self.value_loss_coef, self.entropy_coef = value_loss_coef, entropy_coef
+        self.max_grad_norm = max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.use_normalized_advantage = use_normalized_advantage
+        self.optimizer = torch.optim.Adam(
+            [p for p in actor_critic.parameters() if p.requires_grad], lr=lr, eps=eps)
+        self.device = next(actor_critic.parameters()).device
+
+    def forward(self, *x):
+        raise NotImplementedError
+
+    def before_backward(self, loss):
+        pass
+
+    def after_backward(self, loss):
+        pass
+
+    def before_step(self):
+        nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
+
+    def after_step(self):
+        pass
+
+
+class DDPPO(PPO):
+    pass
+
+
+class RolloutStorage:
+    pass

@@ -70,6 +70,9 @@ def load():
     _mod("habitat_baselines.rl.models.rnn_state_encoder",
          build_rnn_state_encoder=hb017.build_rnn_state_encoder)
     _mod("habitat_baselines.rl.ddppo")
+    _mod("habitat_baselines.rl.ddppo.algo")
+    _mod("habitat_baselines.rl.ddppo.algo.ddppo", DDPPO=hb017.DDPPO)
+    _mod("habitat_baselines.common.rollout_storage", RolloutStorage=hb017.RolloutStorage)
     _mod("habitat_baselines.rl.ddppo.policy", resnet=hb017.resnet)
     _mod("habitat_baselines.rl.ddppo.policy.resnet", resnet18=hb017.resnet18,
          resnet50=hb017.resnet50)
@@ -112,6 +115,15 @@ def load():
     ns.policy = importlib.import_module("vlnce_baselines.models.policy")
     ns.cma_policy = importlib.import_module("vlnce_baselines.models.cma_policy")
     ns.seq2seq_policy = importlib.import_module("vlnce_baselines.models.seq2seq_policy")
+    # waypoint path
+    ns.waypoint_predictors = importlib.import_module("vlnce_baselines.models.waypoint_predictors")
+    ns.waypoint_policy = importlib.import_module("vlnce_baselines.models.waypoint_policy")
+    ns.ddppo_alg = importlib.import_module("vlnce_baselines.common.ddppo_alg")
+    ns.rollout_storage = importlib.import_module("vlnce_baselines.common.rollout_storage")
+    ns.WaypointPolicy = ns.waypoint_policy.WaypointPolicy
+    ns.WDDPPO = ns.ddppo_alg.WDDPPO
+    ns.ActionDictRolloutStorage = ns.rollout_storage.ActionDictRolloutStorage
+    ns.TruncatedNormal = ns.utils.TruncatedNormal
     ns.AuxLosses = ns.aux_losses.AuxLosses
     ns.CMAPolicy = ns.cma_policy.CMAPolicy
     ns.Seq2SeqPolicy = ns.seq2seq_policy.Seq2SeqPolicy

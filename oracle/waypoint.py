@@ -533,3 +533,36 @@ class ActionDictRolloutStorage:
                    {k: tm(v) for k, v in self.prev_actions.items()},
                    tm(self.value_preds), tm(self.returns), tm(self.masks), tm(self.action_log_probs),
                    tm(advantages))
+
+
+def ppo_update(policy, optimizer, rollouts, ppo_epoch=2, num_mini_batch=4, max_grad_norm=0.2,
+               use_normalized_advantage=False, **loss_kw):
+    """``WDDPPO.update`` (ddppo_alg.py:37-149): epochs x recurrent mini-batches of
+    evaluate_actions -> loss -> backward -> clip_grad_norm_ (hb PPO.before_step) -> Adam.
+    Returns the six epoch-averaged scalars in the reference's order."""
+    adv = advantages_of(rollouts, use_normalized_advantage)
+    keys = ("value_loss", "action_loss", "entropy_loss", "pano_entropy", "offset_entropy", "distance_entropy")
+    sums = dict.fromkeys(keys, 0.0)
+    for _ in range(ppo_epoch):
+        for sample in rollouts.recurrent_generator(adv, num_mini_batch):
+            loss, parts = wddppo_losses(policy, sample, **loss_kw)
+            optimizer.zero_grad()
+            loss.backward()
+            nn.utils.clip_grad_norm_(policy.parameters(), max_grad_norm)
+            optimizer.step()
+            for k in keys:
+                sums[k] += float(parts[k].detach()) if torch.is_tensor(parts[k]) else float(parts[k])
+    n = ppo_epoch * num_mini_batch
+    return tuple(sums[k] / n for k in keys)
+
+
+def storage_obs_space(rgb=(12, 224, 224, 3), depth=(12, 256, 256, 1), length=80):
+    """The observation space the waypoint trainer hands to the rollout storage
+    (``ddppo_waypoint_trainer.py:60-100``: policy sensors + the two history frames)."""
+    return hb017.Dict({
+        "rgb": hb017.Box(0, 255, rgb, "float32"), "depth": hb017.Box(0.0, 1.0, depth, "float32"),
+        "rgb_history": hb017.Box(0, 255, rgb[1:], "float32"),
+        "depth_history": hb017.Box(0.0, 1.0, depth[1:], "float32"),
+        "angle_features": hb017.Box(-1.0, 1.0, (rgb[0], 4), "float32"),
+        "instruction": hb017.Box(0, 2503, (length,), "float32"),
+    })

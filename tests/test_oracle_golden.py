@@ -19,7 +19,7 @@ def load(name):
 @pytest.mark.parametrize("name", list(cases.CASES))
 def test_oracle_matches_reference_golden(name):
     gold = load(name)
-    got = cases.run_case(vlnce, name, aux=vlnce.AuxLosses)
+    got = cases.run_case(cases.oracle_impl(cases.CASES[name]), name, aux=vlnce.AuxLosses)
     for k, v in got.items():
         g = gold[k]
         if v.dtype in (torch.int64, torch.uint8):
@@ -34,6 +34,6 @@ def test_seeded_inputs_checksum():
     """Weights / inputs regenerate bit-identically from the seeds."""
     from oracle.make_golden import checksum
 
-    for name in ("cma_act", "cma_train_features"):
+    for name in ("cma_act", "cma_train_features", "wp_act", "wp_eval"):
         gold = load(name)
         assert torch.equal(checksum(cases.CASES[name]), gold["_checksum"]), name

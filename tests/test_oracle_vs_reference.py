@@ -12,14 +12,17 @@ pytestmark = pytest.mark.skipif(not reference_import.available(),
 warnings.filterwarnings("ignore")
 
 
-@pytest.mark.parametrize("name", ["cma_act_bntrain", "cma_train_features", "seq2seq_act", "seq2seq_train_features"])
+@pytest.mark.parametrize("name", ["cma_act_bntrain", "cma_train_features", "seq2seq_act", "seq2seq_train_features",
+                                  "wp_act", "wp_eval"])
 def test_oracle_equals_reference_live(name):
     ref = reference_import.load()
     a = cases.run_case(ref, name, aux=ref.AuxLosses)
-    b = cases.run_case(vlnce, name, aux=vlnce.AuxLosses)
+    b = cases.run_case(cases.oracle_impl(cases.CASES[name]), name, aux=vlnce.AuxLosses)
     assert set(a) == set(b)
     for k in a:
-        assert torch.equal(a[k], b[k]) or torch.allclose(a[k], b[k], rtol=1e-6, atol=1e-7), k
+        tol = 2e-5 if name.startswith("wp_") else 1e-6  # waypoint: einsum vs bmm reduction order
+        assert torch.equal(a[k], b[k]) or torch.allclose(a[k], b[k], rtol=tol, atol=tol * 0.1 * float(a[k].abs().max())
+                                                         + 1e-7), k
 
 
 def test_state_dict_keys_match_reference():

@@ -108,6 +108,7 @@ def seeded_state_dict(module: torch.nn.Module, seed: int) -> Dict[str, torch.Ten
     gen = torch.Generator().manual_seed(seed)
     out: Dict[str, torch.Tensor] = {}
     sd = module.state_dict()
+    basic_blocks = not any(".bn3." in k for k in sd)  # torchvision ResNet-18/34: bn2 closes a block
     for name, ref in sd.items():
         shape = tuple(ref.shape)
         leaf = name.rsplit(".", 1)[-1]
@@ -123,7 +124,8 @@ def seeded_state_dict(module: torch.nn.Module, seed: int) -> Dict[str, torch.Ten
             t = torch.rand(shape, generator=gen) + 0.5
         elif ref.dim() == 1 and leaf == "weight":  # norm scale
             damp = (".bn3." in name or name.endswith("convs.7.weight")
-                    or ".downsample.1." in name or name.endswith("convs.4.weight"))
+                    or ".downsample.1." in name or name.endswith("convs.4.weight")
+                    or (basic_blocks and ".bn2." in name))
             t = torch.rand(shape, generator=gen) * (0.2 if damp else 1.0) + (0.2 if damp else 0.5)
         elif ref.dim() == 1 or "bias" in leaf:
             t = torch.randn(shape, generator=gen) * 0.05
@@ -138,6 +140,82 @@ def seeded_state_dict(module: torch.nn.Module, seed: int) -> Dict[str, torch.Ten
             gain = 2.0 if ref.dim() == 4 else 1.0
             if "action_distribution" in name:
                 gain = 4.0
+            if "_var_linear." in name or "distance_linear." in name or "offset_linear." in name:
+                gain = 8.0  # waypoint heads: spread the sigmoid / tanh outputs without saturating them
             t = torch.randn(shape, generator=gen) * (gain / fan_in) ** 0.5
         out[name] = t.to(ref.dtype)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Waypoint path: panoramic observations of ``1-wpn-cc.yaml``
+# ---------------------------------------------------------------------------------------------
+def angle_features(n: int, panos: int = 12) -> torch.Tensor:
+    """``habitat_extensions/sensors.py:102-105``: [sin, cos, sin, cos] of each pano heading."""
+    a = torch.arange(panos, dtype=torch.float32) * (2 * 3.141592653589793 / panos)
+    f = torch.stack([torch.sin(a), torch.cos(a), torch.sin(a), torch.cos(a)], 1)
+    return f.unsqueeze(0).expand(n, panos, 4).contiguous()
+
+
+def make_waypoint_rows(gen, rows: int, rgb_hw: int = 224, hw: int = 256, length: int = 80, panos: int = 12,
+                       vocab: int = 2504, rgb_u8: bool = False, instruction=None) -> Dict[str, torch.Tensor]:
+    """Observations of ``rows`` policy steps in the layout ``ddppo_waypoint_trainer.py:222-246``
+    feeds the policy: every sensor float32 (``batch_obs`` + ``.float()``), rgb 0..255."""
+    rgb = torch.randint(0, 256, (rows, panos, rgb_hw, rgb_hw, 3), generator=gen, dtype=torch.uint8)
+    rgb_h = torch.randint(0, 256, (rows, rgb_hw, rgb_hw, 3), generator=gen, dtype=torch.uint8)
+    instr = make_instruction(gen, rows, length, vocab) if instruction is None else instruction
+    return {
+        "rgb": rgb if rgb_u8 else rgb.float(),
+        "depth": torch.rand(rows, panos, hw, hw, 1, generator=gen),
+        "rgb_history": rgb_h if rgb_u8 else rgb_h.float(),
+        "depth_history": torch.rand(rows, hw, hw, 1, generator=gen),
+        "angle_features": angle_features(rows, panos),
+        "instruction": instr if rgb_u8 else instr.float(),
+    }
+
+
+def make_waypoint_actions(gen, rows: int, panos: int = 12, dmin: float = 0.25, dmax: float = 4.0):
+    """Action components as ``WaypointPolicy.act`` emits them (continuous heads): pano in
+    0..panos (panos = STOP), offset in [-pi/panos, pi/panos], distance in [dmin, dmax]."""
+    lim = 3.141592653589793 / panos
+    return {
+        "pano": torch.randint(0, panos + 1, (rows, 1), generator=gen, dtype=torch.int64),
+        "offset": (torch.rand(rows, 1, generator=gen) * 2 - 1) * lim * 0.98,
+        "distance": dmin + torch.rand(rows, 1, generator=gen) * (dmax - dmin),
+    }
+
+
+def make_waypoint_act_batch(seed: int, n: int, hidden: int = 256, layers: int = 2, rgb_u8: bool = False, **kw):
+    """One ``WaypointPolicy.act`` call: (observations, rnn_states, prev_actions, masks)."""
+    gen = torch.Generator().manual_seed(seed)
+    obs = make_waypoint_rows(gen, n, rgb_u8=rgb_u8, **kw)
+    h = torch.randn(n, layers, hidden, generator=gen) * 0.5
+    prev = make_waypoint_actions(gen, n)
+    masks = torch.ones(n, 1, dtype=torch.uint8)
+    masks[0] = 0  # one env at an episode start (history frame and prev action zeroed)
+    return obs, h, prev, masks
+
+
+def make_waypoint_eval_batch(seed: int, t: int, n: int, hidden: int = 256, layers: int = 2, **kw):
+    """One PPO mini-batch as ``ActionDictRolloutStorage.recurrent_generator`` yields it
+    (``rollout_storage.py:154-276``), time-major rows: (obs, h0 (N,Lr,H), actions, prev_actions,
+    value_preds, returns, masks, old_action_log_probs, adv_targ)."""
+    gen = torch.Generator().manual_seed(seed)
+    r = t * n
+    length = kw.pop("length", 80)
+    instr = make_instruction(gen, n, length).unsqueeze(0).expand(t, n, length).reshape(r, length).contiguous()
+    obs = make_waypoint_rows(gen, r, length=length, instruction=instr, **kw)
+    h0 = torch.randn(n, layers, hidden, generator=gen) * 0.5
+    actions = make_waypoint_actions(gen, r)
+    actions["pano"][1] = 12  # make sure a STOP row is covered
+    prev = {k: torch.zeros_like(v) for k, v in actions.items()}
+    for k in actions:
+        prev[k][n:] = actions[k][:-n]
+    masks = (torch.rand(r, 1, generator=gen) > 0.25).to(torch.uint8)
+    prev = {k: v * masks.to(v.dtype) for k, v in prev.items()}
+    actions = {k: v.float() for k, v in actions.items()}  # the storage keeps actions as float (rollout_storage.py:49-52)
+    v_old = torch.randn(r, 1, generator=gen) * 0.5
+    ret = v_old + torch.randn(r, 1, generator=gen) * 0.5
+    lp_old = -2.0 + torch.randn(r, 1, generator=gen) * 0.3
+    adv = torch.randn(r, 1, generator=gen)
+    return obs, h0, actions, prev, v_old, ret, masks, lp_old, adv
