@@ -119,10 +119,15 @@ class dry_run:
     """Test helper: inside this context every C-ABI call is validated against the header
     prototype (argument count and kinds) and recorded, but NOT executed, and the CUDA-device
     check is waived — it lets the CPU test-suite walk the whole launch sequence (shapes,
-    pointer arithmetic, attribute names) without a GPU.  Never used by the product path."""
+    pointer arithmetic, attribute names) without a GPU.  Never used by the product path.
 
-    def __init__(self):
+    ``executor``: optional test-supplied callable ``(name, args)`` run after the validation of each
+    call (``tests/abi_emulator.py`` passes a numpy model of the head kernels so that the launch
+    plans can be checked numerically on host memory).  The package itself ships no executor."""
+
+    def __init__(self, executor=None):
         self.calls = []
+        self.executor = executor
 
     def __enter__(self):
         global C, require_cuda, stream
@@ -150,6 +155,8 @@ class dry_run:
                         if not ok:
                             raise TypeError(f"{name}: argument {i} ({t}) got {type(a).__name__} {a!r}")
                     outer.calls.append(name)
+                    if outer.executor is not None:
+                        outer.executor(name, args)
                     return 0
 
                 return call
