@@ -269,6 +269,83 @@ int vlnce_adam_step(float* p, const float* g, float* m, float* v, long long n, f
 int vlnce_counter_add(int* counter, int value, cudaStream_t stream);
 int vlnce_axpy(float* y, const float* x, float alpha, long long n, cudaStream_t stream);
 
+/* ---- waypoint path --------------------------------------------- */
+/* waypoint_predictors.py:327-366: out = [B*P pano frames | B history frames, zeroed where masks == 0],
+ * one trunk batch; byte movement only (frame_bytes = H*W*C*sizeof(element)). */
+int vlnce_wp_stack_frames(const void* cur, const void* hist, const float* masks, void* out, int B, int P,
+                          long long frame_bytes, cudaStream_t stream);
+/* E[r,p,0:C] = E[r,0,0:C], p >= 1 (single_spatial_filter=False keeps the global pool,
+ * resnet_encoders.py:154-162) */
+int vlnce_broadcast_positions(float* E, long long lde_r, long long lde_p, int R, int P, int C,
+                              cudaStream_t stream);
+/* waypoint_predictors.py:268-275,372-384: [sin h, cos h, off_a + off_b*offset, dist_a + dist_b*distance] * mask,
+ * h = pano * 2pi / panos; written to two concat slices */
+int vlnce_wp_prev_action(const long long* pano, const float* offset, const float* distance, const float* masks,
+                         float* out, long long ldo, float* out2, long long ldo2, int rows, int panos, float off_a,
+                         float off_b, float dist_a, float dist_b, cudaStream_t stream);
+/* waypoint_predictors.py:419-424 with the multiplicative inverted mask of utils.py:173-175 in closed
+ * form; instr (R,L,D) zero beyond each row's length; save (R,2) */
+int vlnce_wp_inst_attn_fwd(const float* q, long long ldq, const float* bk, const float* instr, const int* lengths,
+                           float scale, float* out, long long ldo, float* save, int R, int L, int D, int Dk,
+                           cudaStream_t stream);
+int vlnce_wp_inst_attn_bwd(const float* save, const float* out, long long ldo, const float* dout, long long lddo,
+                           const int* lengths, float scale, float* dcs, float* d_instr, int R, int L, int D,
+                           cudaStream_t stream);
+/* waypoint_predictors.py:459-464: out.flat[m] = q.flat[m / P] (repeat_interleave of ELEMENTS) and its adjoint */
+int vlnce_wp_scramble_query(const float* q, float* out, long long n_in, int P, cudaStream_t stream);
+int vlnce_wp_scramble_query_bwd(const float* dout, float* dq, long long n_in, int P, cudaStream_t stream);
+/* nn.LayerNorm over the last dimension (utils.py:214-215,263-265); save (R,2) = mean, rstd;
+ * bwd also emits prod = dy * xhat whose column sum is d_gamma */
+int vlnce_layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float* y, long long ldy,
+                        float* save, int R, int D, float eps, cudaStream_t stream);
+int vlnce_layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
+                        const float* save, float* dx, long long lddx, float* prod, long long ldp, int R, int D,
+                        cudaStream_t stream);
+/* waypoint_predictors.py:556-559: out[b,i] = F[b,i,:] . xs[b,:] and its adjoints */
+int vlnce_wp_dot_frames_fwd(const float* F, long long ldf_r, long long ldf_p, const float* xs, long long ldx,
+                            float* out, long long ldo, int B, int P, int D, cudaStream_t stream);
+int vlnce_wp_dot_frames_bwd(const float* F, long long ldf_r, long long ldf_p, const float* xs, long long ldx,
+                            const float* dout, long long lddo, float* dF, long long lddf_r, long long lddf_p,
+                            int accumulate_dF, float* dxs, long long lddx, int B, int P, int D, cudaStream_t stream);
+/* out[b,i,:] = x[b,:] (waypoint_predictors.py:561-567) / out[r,:] (+)= sum_p E[r,p,:] */
+int vlnce_broadcast_rows(const float* x, long long ldx, float* out, long long ldo_r, long long ldo_p, int B, int P,
+                         int D, cudaStream_t stream);
+int vlnce_sum_positions(const float* E, long long lde_r, long long lde_p, float* out, long long ldo, int accumulate,
+                        int R, int P, int D, cudaStream_t stream);
+/* Output activations of the continuous heads (waypoint_predictors.py:573-613).  raw (n,4): distance, distance
+ * variance, offset, offset variance pre-activations.  consts_host: HOST pointer to 8 floats {d_span, d_min,
+ * dv_span, dv_min, o_scale, 1/temperature, ov_span, ov_min}. */
+int vlnce_wp_head_act_fwd(const float* raw, float* d1, float* d2, float* o1, float* o2, long long n,
+                          const float* consts_host, cudaStream_t stream);
+int vlnce_wp_head_act_bwd(const float* raw, const float* g_d1, const float* g_d2, const float* g_o1, const float* g_o2,
+                          float* g_raw, long long n, const float* consts_host, cudaStream_t stream);
+/* WaypointPolicy.act post-processing (waypoint_policy.py:129-247; TruncatedNormal utils.py:24-152).
+ * logp (B,P+1) log-probs; o1,o2,d1,d2 (B,P).  pano_stop (B) i64; fout (B,10) = offset, distance,
+ * action_log_prob, var_distance, var_offset, mode_offset, mode_distance, r, theta, stop.
+ * act_consts_host: HOST pointer to 5 floats {d_lo, d_hi, offset_limit, predict_distance, predict_offset}. */
+int vlnce_wp_act(const float* logp, const float* o1, const float* o2, const float* d1, const float* d2,
+                 long long* pano_stop, float* fout, int B, int P, int deterministic, unsigned long long seed,
+                 unsigned long long offset, const float* act_consts_host, cudaStream_t stream);
+/* evaluate_actions (waypoint_policy.py:265-333) fused with the WDDPPO mini-batch loss and its gradients
+ * (common/ddppo_alg.py:56-124).  eval_out (R,4) = action_log_prob, entropy pano/offset/distance; losses[8] =
+ * loss, value_loss, action_loss, entropy_loss, offset_loss, mean entropies (pano, offset, distance).
+ * losses and the gradient outputs may be NULL.  ppo_consts_host: HOST pointer to 10 floats {clip, value_coef,
+ * entropy_coef, offset_regularize_coef, pano/offset/distance entropy coefs, clipped_value_loss, off_a, off_b}. */
+int vlnce_wp_ppo_loss(const float* logp, const float* o1, const float* o2, const float* d1, const float* d2,
+                      const float* values, const float* a_pano, const float* a_offset, const float* a_distance,
+                      const float* v_old, const float* ret, const float* lp_old, const float* adv, int R, int P,
+                      const float* act_consts_host, const float* ppo_consts_host, float* eval_out, float* losses,
+                      float* d_raw, float* d_o1, float* d_o2, float* d_d1, float* d_d2, float* d_values,
+                      cudaStream_t stream);
+/* torch.nn.utils.clip_grad_norm_ (habitat_baselines v0.1.7 PPO.before_step; ddppo_alg.py:131): g *= pre_scale *
+ * min(1, max_norm / (pre_scale * ||g|| + 1e-6)); ws >= 1026 floats, ws[1024] = norm, ws[1025] = factor. */
+int vlnce_clip_grad_norm(float* g, long long n, float max_norm, float pre_scale, float* ws, size_t ws_bytes,
+                         cudaStream_t stream);
+/* ActionDictRolloutStorage.compute_returns (common/rollout_storage.py:127-152): rewards (T,N), value_preds and
+ * returns (T+1,N), masks (T+1,N) u8, next_value (N). */
+int vlnce_gae_returns(const float* rewards, float* value_preds, const unsigned char* masks, const float* next_value,
+                      float* returns, int T, int N, float gamma, float tau, int use_gae, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,3 +331,277 @@ class Emulator:
 
     def axpy(self, y, x, alpha, n, st):
         _flat(y, n)[...] += alpha * _flat(x, n)
+
+
+# ======================================================================================
+# waypoint path (csrc/waypoint.cu)
+# ======================================================================================
+_S2PI = math.sqrt(2 * math.pi)
+
+
+def _phi(x):
+    return np.exp(-0.5 * x * x) / _S2PI
+
+
+def _Phi(x):
+    from scipy.special import erf
+
+    return 0.5 * (1 + erf(x / math.sqrt(2)))
+
+
+def _tn_stats(mu, sg, lo, hi):
+    a, b = (lo - mu) / sg, (hi - mu) / sg
+    pa, pb = _phi(a), _phi(b)
+    Z = _Phi(b) - _Phi(a)
+    dz = (pb - pa) / Z
+    return dict(a=a, b=b, pa=pa, pb=pb, Z=Z, mean=mu - sg * dz,
+                var=sg * sg * (1 - (b * pb - a * pa) / Z - dz * dz),
+                ent=0.5 * math.log(2 * math.pi * math.e) + np.log(sg * Z) + (a * pa - b * pb) / (2 * Z))
+
+
+def _tn_logp(y, mu, sg, Z):
+    u = (y - mu) / sg
+    return -0.5 * u * u - np.log(sg * _S2PI * Z)
+
+
+def _tn_grads(t, y, mu, sg):
+    inv = 1 / sg
+    u = (y - mu) * inv
+    dZm = (t["pa"] - t["pb"]) * inv
+    N = t["a"] * t["pa"] - t["b"] * t["pb"]
+    dZs = N * inv
+    dlp_dmu = u * inv - dZm / t["Z"]
+    dlp_ds = u * u * inv - inv - dZs / t["Z"]
+    dNm = ((1 - t["b"] ** 2) * t["pb"] - (1 - t["a"] ** 2) * t["pa"]) * inv
+    dNs = (t["b"] * (1 - t["b"] ** 2) * t["pb"] - t["a"] * (1 - t["a"] ** 2) * t["pa"]) * inv
+    dH_dmu = dZm / t["Z"] + dNm / (2 * t["Z"]) - N * dZm / (2 * t["Z"] ** 2)
+    dH_ds = inv + dZs / t["Z"] + dNs / (2 * t["Z"]) - N * dZs / (2 * t["Z"] ** 2)
+    return dlp_dmu, dlp_ds * 0.5 * inv, dH_dmu, dH_ds * 0.5 * inv
+
+
+def _host_floats(ptr, n):
+    return [float(v) for v in _flat(ptr, n)]
+
+
+class WaypointOps:
+    def wp_stack_frames(self, cur, hist, masks, out, B, P, frame_bytes, st):
+        o = _flat(out, B * (P + 1) * frame_bytes, np.uint8)
+        o[: B * P * frame_bytes] = _flat(cur, B * P * frame_bytes, np.uint8)
+        h = _flat(hist, B * frame_bytes, np.uint8).reshape(B, frame_bytes)
+        m = _flat(masks, B) != 0
+        o[B * P * frame_bytes:].reshape(B, frame_bytes)[...] = np.where(m[:, None], h, 0)
+
+    def broadcast_positions(self, E, lde_r, lde_p, R, P, C, st):
+        e = _ten3(E, R, P, C, lde_r, lde_p)
+        e[:, 1:, :] = e[:, :1, :]
+
+    def wp_prev_action(self, pano, offset, distance, masks, out, ldo, out2, ldo2, rows, panos, off_a, off_b, dist_a,
+                       dist_b, st):
+        h = _flat(pano, rows, I64).astype(np.float64) * (2 * math.pi / panos)
+        m = _flat(masks, rows).astype(np.float64)
+        v = np.stack([np.sin(h), np.cos(h), off_a + off_b * _flat(offset, rows), dist_a + dist_b * _flat(distance, rows)],
+                     1) * m[:, None]
+        _mat(out, rows, 4, ldo)[...] = v
+        if out2:
+            _mat(out2, rows, 4, ldo2)[...] = v
+
+    def wp_inst_attn_fwd(self, q, ldq, bk, instr, lengths, scale, out, ldo, save, R, L, D, Dk, st):
+        lens = np.minimum(_flat(lengths, R, I32), L)
+        lmax = int(lens.max())
+        c = (_mat(q, R, Dk, ldq).astype(np.float64) @ _flat(bk, Dk).astype(np.float64)) * scale
+        x = _flat(instr, R * L * D).reshape(R, L, D).astype(np.float64)
+        sv = _mat(save, R, 2, 2)
+        for r in range(R):
+            npad = lmax - lens[r]
+            z = lens[r] + npad * math.exp(c[r])
+            a_v = 1.0 / z
+            _mat(out, R, D, ldo)[r] = a_v * x[r, : lens[r]].sum(0)
+            sv[r] = [a_v, npad * math.exp(c[r]) / z]
+
+    def wp_inst_attn_bwd(self, save, out, ldo, dout, lddo, lengths, scale, dcs, d_instr, R, L, D, st):
+        sv = _mat(save, R, 2, 2).astype(np.float64)
+        o, do = _mat(out, R, D, ldo).astype(np.float64), _mat(dout, R, D, lddo).astype(np.float64)
+        _flat(dcs, R)[...] = -(o * do).sum(1) * sv[:, 1] * scale
+        lens = np.minimum(_flat(lengths, R, I32), L)
+        di = _flat(d_instr, R * L * D).reshape(R, L, D)
+        di[...] = 0
+        for r in range(R):
+            di[r, : lens[r]] = sv[r, 0] * do[r]
+
+    def wp_scramble_query(self, q, out, n_in, P, st):
+        _flat(out, n_in * P)[...] = np.repeat(_flat(q, n_in), P)
+
+    def wp_scramble_query_bwd(self, dout, dq, n_in, P, st):
+        _flat(dq, n_in)[...] = _flat(dout, n_in * P).reshape(n_in, P).astype(np.float64).sum(1)
+
+    def layernorm_fwd(self, x, ldx, gamma, beta, y, ldy, save, R, D, eps, st):
+        xv = _mat(x, R, D, ldx).astype(np.float64)
+        mean = xv.mean(1, keepdims=True)
+        rstd = 1 / np.sqrt(((xv - mean) ** 2).mean(1, keepdims=True) + eps)
+        _mat(y, R, D, ldy)[...] = (xv - mean) * rstd * _flat(gamma, D) + _flat(beta, D)
+        if save:
+            _mat(save, R, 2, 2)[...] = np.concatenate([mean, rstd], 1)
+
+    def layernorm_bwd(self, dy, lddy, x, ldx, gamma, save, dx, lddx, prod, ldp, R, D, st):
+        sv = _mat(save, R, 2, 2).astype(np.float64)
+        xh = (_mat(x, R, D, ldx).astype(np.float64) - sv[:, :1]) * sv[:, 1:]
+        d = _mat(dy, R, D, lddy).astype(np.float64)
+        g = d * _flat(gamma, D)
+        _mat(dx, R, D, lddx)[...] = sv[:, 1:] * (g - g.mean(1, keepdims=True) - xh * (g * xh).mean(1, keepdims=True))
+        _mat(prod, R, D, ldp)[...] = d * xh
+
+    def wp_dot_frames_fwd(self, F, ldf_r, ldf_p, xs, ldx, out, ldo, B, P, D, st):
+        f = _ten3(F, B, P, D, ldf_r, ldf_p).astype(np.float64)
+        _mat(out, B, P, ldo)[...] = np.einsum("bpd,bd->bp", f, _mat(xs, B, D, ldx).astype(np.float64))
+
+    def wp_dot_frames_bwd(self, F, ldf_r, ldf_p, xs, ldx, dout, lddo, dF, lddf_r, lddf_p, acc, dxs, lddx, B, P, D, st):
+        f = _ten3(F, B, P, D, ldf_r, ldf_p).astype(np.float64)
+        g = _mat(dout, B, P, lddo).astype(np.float64)
+        x = _mat(xs, B, D, ldx).astype(np.float64)
+        v = g[:, :, None] * x[:, None, :]
+        df = _ten3(dF, B, P, D, lddf_r, lddf_p)
+        df[...] = (df + v) if acc else v
+        _mat(dxs, B, D, lddx)[...] = np.einsum("bp,bpd->bd", g, f)
+
+    def broadcast_rows(self, x, ldx, out, ldo_r, ldo_p, B, P, D, st):
+        _ten3(out, B, P, D, ldo_r, ldo_p)[...] = _mat(x, B, D, ldx)[:, None, :]
+
+    def sum_positions(self, E, lde_r, lde_p, out, ldo, acc, R, P, D, st):
+        s = _ten3(E, R, P, D, lde_r, lde_p).astype(np.float64).sum(1)
+        o = _mat(out, R, D, ldo)
+        o[...] = (o + s) if acc else s
+
+    def wp_head_act_fwd(self, raw, d1, d2, o1, o2, n, consts, st):
+        c = _host_floats(consts, 8)
+        r = _mat(raw, n, 4, 4).astype(np.float64)
+        _flat(d1, n)[...] = c[0] * _sig(r[:, 0]) + c[1]
+        _flat(d2, n)[...] = c[2] * _sig(r[:, 1]) + c[3]
+        _flat(o1, n)[...] = c[4] * np.tanh(r[:, 2] * c[5])
+        _flat(o2, n)[...] = c[6] * _sig(r[:, 3]) + c[7]
+
+    def wp_head_act_bwd(self, raw, g_d1, g_d2, g_o1, g_o2, g_raw, n, consts, st):
+        c = _host_floats(consts, 8)
+        r = _mat(raw, n, 4, 4).astype(np.float64)
+        s0, s1, s3, t = _sig(r[:, 0]), _sig(r[:, 1]), _sig(r[:, 3]), np.tanh(r[:, 2] * c[5])
+        _mat(g_raw, n, 4, 4)[...] = np.stack([
+            _flat(g_d1, n) * c[0] * s0 * (1 - s0), _flat(g_d2, n) * c[2] * s1 * (1 - s1),
+            _flat(g_o1, n) * c[4] * (1 - t * t) * c[5], _flat(g_o2, n) * c[6] * s3 * (1 - s3)], 1)
+
+    def wp_act(self, logp, o1, o2, d1, d2, pano_stop, fout, B, P, deterministic, seed, offset, consts, st):
+        d_lo, d_hi, o_lim, pd, po = _host_floats(consts, 5)
+        lp = _mat(logp, B, P + 1, P + 1).astype(np.float64)
+        rng = np.random.default_rng(seed + offset)
+        f = _mat(fout, B, 10, 10)
+        for b in range(B):
+            if deterministic:
+                ps = int(np.exp(lp[b]).argmax())
+            else:
+                ps = int(min(np.searchsorted(np.cumsum(np.exp(lp[b])), rng.random(), side="right"), P))
+            pano, go = ps % P, float(ps != P)
+            mu_d, sg_d = float(_mat(d1, B, P, P)[b, pano]), math.sqrt(float(_mat(d2, B, P, P)[b, pano]))
+            mu_o, sg_o = float(_mat(o1, B, P, P)[b, pano]), math.sqrt(float(_mat(o2, B, P, P)[b, pano]))
+            td, to = _tn_stats(mu_d, sg_d, d_lo, d_hi), _tn_stats(mu_o, sg_o, -o_lim, o_lim)
+
+            def draw(mu, sg, lo, hi):
+                while True:
+                    s = rng.normal(mu, sg)
+                    if lo <= s <= hi:
+                        return s
+
+            dist = mu_d if deterministic else draw(mu_d, sg_d, d_lo, d_hi)
+            ofs = mu_o if deterministic else draw(mu_o, sg_o, -o_lim, o_lim)
+            lp_d, lp_o = _tn_logp(dist, mu_d, sg_d, td["Z"]), _tn_logp(ofs, mu_o, sg_o, to["Z"])
+            a_d, a_o, var_d, var_o = dist, ofs, td["var"], to["var"]
+            if not po:
+                a_o = ofs = var_o = 0.0
+            if not pd:
+                a_d = dist = 0.25
+                var_d = 0.0
+            theta = (pano * (2 * math.pi / P) + a_o) % (2 * math.pi)
+            alp = lp[b, ps] + (go * lp_d if pd else 0.0) + (go * lp_o if po else 0.0)
+            _flat(pano_stop, B, I64)[b] = ps
+            f[b] = [ofs, dist, alp, var_d, var_o, mu_o, mu_d, a_d if go else 0.0, theta if go else 0.0, 1.0 - go]
+
+    def wp_ppo_loss(self, logp, o1, o2, d1, d2, values, a_pano, a_offset, a_distance, v_old, ret, lp_old, adv, R, P,
+                    act_consts, ppo_consts, eval_out, losses, d_raw, d_o1, d_o2, d_d1, d_d2, d_values, st):
+        d_lo, d_hi, o_lim, pd, po = _host_floats(act_consts, 5)
+        lp = _mat(logp, R, P + 1, P + 1).astype(np.float64)
+        a = _flat(a_pano, R).astype(np.int64)
+        idx, go = a % P, (a != P).astype(np.float64)
+        dm, om = go * float(pd != 0), go * float(po != 0)
+        rows = np.arange(R)
+        p = np.exp(lp)
+        Hp = -(p * lp).sum(1)
+        g64 = lambda x: _mat(x, R, P, P).astype(np.float64)[rows, idx]  # noqa: E731
+        mu_d, v_d, mu_o, v_o = g64(d1), g64(d2), g64(o1), g64(o2)
+        sg_d, sg_o = np.sqrt(v_d), np.sqrt(v_o)
+        td, to = _tn_stats(mu_d, sg_d, d_lo, d_hi), _tn_stats(mu_o, sg_o, -o_lim, o_lim)
+        y_d, y_o = _flat(a_distance, R).astype(np.float64), _flat(a_offset, R).astype(np.float64)
+        alp = lp[rows, a] + dm * _tn_logp(y_d, mu_d, sg_d, td["Z"]) + om * _tn_logp(y_o, mu_o, sg_o, to["Z"])
+        Ho, Hd = om * to["ent"], dm * td["ent"]
+        if eval_out:
+            _mat(eval_out, R, 4, 4)[...] = np.stack([alp, Hp, Ho, Hd], 1)
+        if not losses:
+            return
+        c = _host_floats(ppo_consts, 10)
+        clip, vcoef, ecoef, oreg, cp, co, cd, clipped, off_a, off_b = c
+        ratio = np.exp(alp - _flat(lp_old, R))
+        A = _flat(adv, R).astype(np.float64)
+        s1, s2 = ratio * A, np.clip(ratio, 1 - clip, 1 + clip) * A
+        v, vo, rt = (_flat(x, R).astype(np.float64) for x in (values, v_old, ret))
+        diff = v - vo
+        vc = vo + np.clip(diff, -clip, clip)
+        l1, l2 = (v - rt) ** 2, (vc - rt) ** 2
+        value_loss = (0.5 * np.maximum(l1, l2) if clipped else 0.5 * l1).mean() * vcoef
+        action_loss = -np.minimum(s1, s2).mean()
+        entropy_loss = (cp * Hp + co * Ho + cd * Hd).mean() * ecoef
+        offset_loss = oreg * np.abs(off_a + off_b * y_o).mean()
+        _flat(losses, 8)[...] = [value_loss + action_loss + offset_loss - entropy_loss, value_loss, action_loss,
+                                 entropy_loss, offset_loss, Hp.mean(), Ho.mean(), Hd.mean()]
+        if not d_raw:
+            return
+        inside = (ratio >= 1 - clip) & (ratio <= 1 + clip)
+        g_lp = np.where(inside | (s1 < s2), -ratio * A / R, 0.0)
+        g_ent = -ecoef / R
+        onehot = np.zeros((R, P + 1))
+        onehot[rows, a] = 1
+        _mat(d_raw, R, P + 1, P + 1)[...] = g_lp[:, None] * (onehot - p) + g_ent * cp * (-p * (lp + Hp[:, None]))
+        for t, y, mu, sg, m, ce, o_mu, o_v in ((td, y_d, mu_d, sg_d, dm, cd, d_d1, d_d2), (to, y_o, mu_o, sg_o, om, co, d_o1, d_o2)):
+            dlm, dlv, dhm, dhv = _tn_grads(t, y, mu, sg)
+            gm, gv = _mat(o_mu, R, P, P), _mat(o_v, R, P, P)
+            gm[...] = 0
+            gv[...] = 0
+            gm[rows, idx] = m * (g_lp * dlm + g_ent * ce * dhm)
+            gv[rows, idx] = m * (g_lp * dlv + g_ent * ce * dhv)
+        dv = np.where((l1 >= l2) | (not clipped), v - rt, np.where(np.abs(diff) < clip, vc - rt, 0.0))
+        _flat(d_values, R)[...] = vcoef * dv / R
+
+    def clip_grad_norm(self, g, n, max_norm, pre_scale, ws, ws_bytes, st):
+        gv = _flat(g, n)
+        norm = math.sqrt(float((gv.astype(np.float64) ** 2).sum())) * pre_scale
+        f = min(1.0, max_norm / (norm + 1e-6)) * pre_scale
+        w = _flat(ws, 1026)
+        w[1024], w[1025] = norm, f
+        gv *= np.float32(f)
+
+    def gae_returns(self, rewards, value_preds, masks, next_value, returns, T, N, gamma, tau, use_gae, st):
+        rw = _flat(rewards, T * N).reshape(T, N)
+        vp = _flat(value_preds, (T + 1) * N).reshape(T + 1, N)
+        m = _flat(masks, (T + 1) * N, np.uint8).reshape(T + 1, N).astype(F32)
+        rt = _flat(returns, (T + 1) * N).reshape(T + 1, N)
+        nv = _flat(next_value, N)
+        if use_gae:
+            vp[T] = nv
+            gae = np.zeros(N, F32)
+            for t in range(T - 1, -1, -1):
+                delta = rw[t] + np.float32(gamma) * vp[t + 1] * m[t + 1] - vp[t]
+                gae = delta + np.float32(gamma * tau) * m[t + 1] * gae
+                rt[t] = gae + vp[t]
+        else:
+            rt[T] = nv
+            for t in range(T - 1, -1, -1):
+                rt[t] = rt[t + 1] * np.float32(gamma) * m[t + 1] + rw[t]
+
+
+for _name in [n for n in vars(WaypointOps) if not n.startswith("_")]:
+    setattr(Emulator, _name, getattr(WaypointOps, _name))
