@@ -337,6 +337,12 @@ int vlnce_wp_ppo_loss(const float* logp, const float* o1, const float* o2, const
                       const float* act_consts_host, const float* ppo_consts_host, float* eval_out, float* losses,
                       float* d_raw, float* d_o1, float* d_o2, float* d_d1, float* d_d2, float* d_values,
                       cudaStream_t stream);
+/* backward of evaluate_actions for arbitrary upstream gradients (R,4) = d{action_log_prob, entropy_pano,
+ * entropy_offset, entropy_distance} — what the reference's own loss.backward() (ddppo_alg.py:127) needs */
+int vlnce_wp_eval_bwd(const float* logp, const float* o1, const float* o2, const float* d1, const float* d2,
+                      const float* a_pano, const float* a_offset, const float* a_distance, const float* upstream,
+                      int R, int P, const float* act_consts_host, float* d_raw, float* d_o1, float* d_o2,
+                      float* d_d1, float* d_d2, cudaStream_t stream);
 /* torch.nn.utils.clip_grad_norm_ (habitat_baselines v0.1.7 PPO.before_step; ddppo_alg.py:131): g *= pre_scale *
  * min(1, max_norm / (pre_scale * ||g|| + 1e-6)); ws >= 1026 floats, ws[1024] = norm, ws[1025] = factor. */
 int vlnce_clip_grad_norm(float* g, long long n, float max_norm, float pre_scale, float* ws, size_t ws_bytes,

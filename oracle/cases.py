@@ -244,7 +244,4 @@ def wddppo_loss(impl, pol, sample):
     from . import waypoint
 
     loss, parts = waypoint.wddppo_losses(pol, sample, **PPO_KW)
-    values, lp, ent, h_out = pol.evaluate_actions(sample[0], sample[1], sample[3], sample[6], sample[2])
-    parts = dict(parts, values=values, action_log_probs=lp, rnn_states_out=h_out,
-                 entropy_pano=ent["pano"], entropy_offset=ent["offset"], entropy_distance=ent["distance"])
     return loss, parts

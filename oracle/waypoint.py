@@ -426,7 +426,7 @@ def wddppo_losses(policy, sample, clip_param=0.2, value_loss_coef=0.5, entropy_c
     """One mini-batch of ``WDDPPO.update`` (:56-124) up to the scalar loss.  Returns
     (loss, {value_loss, action_loss, entropy_loss, offset_loss, entropies...})."""
     obs, h0, actions, prev, v_old, ret, masks, lp_old, adv = sample
-    values, lp, ent, _ = policy.evaluate_actions(obs, h0, prev, masks, actions)
+    values, lp, ent, h_out = policy.evaluate_actions(obs, h0, prev, masks, actions)
     entropy_loss = (pano_entropy_coef * ent["pano"] + offset_entropy_coef * ent["offset"]
                     + distance_entropy_coef * ent["distance"]).mean() * entropy_coef
     ratio = torch.exp(lp - lp_old)
@@ -443,7 +443,9 @@ def wddppo_losses(policy, sample, clip_param=0.2, value_loss_coef=0.5, entropy_c
     loss = value_loss + action_loss + offset_loss - entropy_loss
     return loss, dict(value_loss=value_loss, action_loss=action_loss, entropy_loss=entropy_loss,
                       offset_loss=offset_loss, pano_entropy=ent["pano"].mean(),
-                      offset_entropy=ent["offset"].mean(), distance_entropy=ent["distance"].mean())
+                      offset_entropy=ent["offset"].mean(), distance_entropy=ent["distance"].mean(),
+                      values=values, action_log_probs=lp, rnn_states_out=h_out, entropy_pano=ent["pano"],
+                      entropy_offset=ent["offset"], entropy_distance=ent["distance"])
 
 
 def advantages_of(rollouts, normalize=True):  # :30-35

@@ -605,3 +605,34 @@ class WaypointOps:
 
 for _name in [n for n in vars(WaypointOps) if not n.startswith("_")]:
     setattr(Emulator, _name, getattr(WaypointOps, _name))
+
+
+def _wp_eval_bwd(self, logp, o1, o2, d1, d2, a_pano, a_offset, a_distance, upstream, R, P, act_consts, d_raw, d_o1,
+                 d_o2, d_d1, d_d2, st):
+    d_lo, d_hi, o_lim, pd, po = _host_floats(act_consts, 5)
+    lp = _mat(logp, R, P + 1, P + 1).astype(np.float64)
+    a = _flat(a_pano, R).astype(np.int64)
+    idx, go = a % P, (a != P).astype(np.float64)
+    dm, om = go * float(pd != 0), go * float(po != 0)
+    rows = np.arange(R)
+    p = np.exp(lp)
+    Hp = -(p * lp).sum(1)
+    up = _mat(upstream, R, 4, 4).astype(np.float64)
+    onehot = np.zeros((R, P + 1))
+    onehot[rows, a] = 1
+    _mat(d_raw, R, P + 1, P + 1)[...] = up[:, 0:1] * (onehot - p) + up[:, 1:2] * (-p * (lp + Hp[:, None]))
+    g64 = lambda x: _mat(x, R, P, P).astype(np.float64)[rows, idx]  # noqa: E731
+    for (mu, v, lo, hi, y, m, g_h, o_mu, o_v) in (
+            (g64(d1), g64(d2), d_lo, d_hi, _flat(a_distance, R).astype(np.float64), dm, up[:, 3], d_d1, d_d2),
+            (g64(o1), g64(o2), -o_lim, o_lim, _flat(a_offset, R).astype(np.float64), om, up[:, 2], d_o1, d_o2)):
+        sg = np.sqrt(v)
+        t = _tn_stats(mu, sg, lo, hi)
+        dlm, dlv, dhm, dhv = _tn_grads(t, y, mu, sg)
+        gm, gv = _mat(o_mu, R, P, P), _mat(o_v, R, P, P)
+        gm[...] = 0
+        gv[...] = 0
+        gm[rows, idx] = m * (up[:, 0] * dlm + g_h * dhm)
+        gv[rows, idx] = m * (up[:, 0] * dlv + g_h * dhv)
+
+
+Emulator.wp_eval_bwd = _wp_eval_bwd

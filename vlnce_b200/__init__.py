@@ -12,4 +12,8 @@ def __getattr__(name):  # lazy: importing the package must not require torchvisi
         from .seq2seq_policy import Seq2SeqPolicy
 
         return Seq2SeqPolicy
+    if name == "WaypointPolicy":
+        from .waypoint_policy import WaypointPolicy
+
+        return WaypointPolicy
     raise AttributeError(name)

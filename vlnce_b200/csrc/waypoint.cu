@@ -418,6 +418,55 @@ __global__ void wp_act_kernel(const float* __restrict__ logp, const float* __res
   f[7] = go != 0.f ? a_dist : 0.f; f[8] = go != 0.f ? theta : 0.f; f[9] = 1.f - go;
 }
 
+// Gradients of one row of evaluate_actions' outputs w.r.t. the net outputs, given the upstream gradients of
+// {action_log_prob, entropy_pano, entropy_offset, entropy_distance}.
+__device__ __forceinline__ void wp_row_grads(const float* lp, int a, int idx, int P, float Hp, const TN& td,
+                                             const TN& to, float y_d, float y_o, float mu_d, float sg_d, float mu_o,
+                                             float sg_o, float dm, float om, float g_lp, float g_hp, float g_ho,
+                                             float g_hd, float* d_raw, float* d_o1, float* d_o2, float* d_d1,
+                                             float* d_d2) {
+  for (int j = 0; j <= P; ++j) {
+    const float p = expf(lp[j]);
+    d_raw[j] = g_lp * ((j == a ? 1.f : 0.f) - p) + g_hp * (-p * (lp[j] + Hp));
+  }
+  for (int j = 0; j < P; ++j) { d_d1[j] = 0.f; d_d2[j] = 0.f; d_o1[j] = 0.f; d_o2[j] = 0.f; }
+  float dlp_dmu, dlp_dv, dH_dmu, dH_dv;
+  tn_grads(td, y_d, mu_d, sg_d, &dlp_dmu, &dlp_dv, &dH_dmu, &dH_dv);
+  d_d1[idx] = dm * (g_lp * dlp_dmu + g_hd * dH_dmu);
+  d_d2[idx] = dm * (g_lp * dlp_dv + g_hd * dH_dv);
+  tn_grads(to, y_o, mu_o, sg_o, &dlp_dmu, &dlp_dv, &dH_dmu, &dH_dv);
+  d_o1[idx] = om * (g_lp * dlp_dmu + g_ho * dH_dmu);
+  d_o2[idx] = om * (g_lp * dlp_dv + g_ho * dH_dv);
+}
+
+// backward of evaluate_actions for arbitrary upstream gradients up (R,4) = d{action_log_prob, entropy_pano,
+// entropy_offset, entropy_distance} (the autograd bridge; the fused PPO kernel below inlines its own)
+__global__ void wp_eval_bwd_kernel(const float* __restrict__ logp, const float* __restrict__ o1,
+                                   const float* __restrict__ o2, const float* __restrict__ d1,
+                                   const float* __restrict__ d2, const float* __restrict__ a_pano,
+                                   const float* __restrict__ a_offset, const float* __restrict__ a_distance,
+                                   const float* __restrict__ up, int R, int P, ActConsts ac, float* __restrict__ d_raw,
+                                   float* __restrict__ d_o1, float* __restrict__ d_o2, float* __restrict__ d_d1,
+                                   float* __restrict__ d_d2) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float* lp = logp + (size_t)r * (P + 1);
+  const int a = (int)a_pano[r];
+  const int idx = a % P;
+  const float go = a != P ? 1.f : 0.f;
+  const float dm = go * (float)ac.predict_distance, om = go * (float)ac.predict_offset;
+  float Hp = 0.f;
+  for (int j = 0; j <= P; ++j) Hp -= expf(lp[j]) * lp[j];
+  const float mu_d = d1[(size_t)r * P + idx], sg_d = sqrtf(d2[(size_t)r * P + idx]);
+  const float mu_o = o1[(size_t)r * P + idx], sg_o = sqrtf(o2[(size_t)r * P + idx]);
+  const TN td = tn_stats(mu_d, sg_d, ac.d_lo, ac.d_hi);
+  const TN to = tn_stats(mu_o, sg_o, -ac.o_lim, ac.o_lim);
+  const float* u = up + (size_t)r * 4;
+  wp_row_grads(lp, a, idx, P, Hp, td, to, a_distance[r], a_offset[r], mu_d, sg_d, mu_o, sg_o, dm, om, u[0], u[1], u[2],
+               u[3], d_raw + (size_t)r * (P + 1), d_o1 + (size_t)r * P, d_o2 + (size_t)r * P, d_d1 + (size_t)r * P,
+               d_d2 + (size_t)r * P);
+}
+
 struct PPOConsts {
   float clip, value_coef, entropy_coef, offset_reg, c_pano, c_offset, c_distance;
   int clipped_value;
@@ -487,25 +536,13 @@ __global__ void wp_ppo_loss_kernel(const float* __restrict__ logp, const float* 
     const bool inside = ratio >= 1.f - pc.clip && ratio <= 1.f + pc.clip;
     const float g_lp = (inside || s1 < s2) ? -invR * ratio * A : 0.f;
     const float g_ent = -pc.entropy_coef * invR;  // loss -= entropy_coef * mean(...)
-    for (int j = 0; j <= P; ++j) {
-      const float p = expf(lp[j]);
-      d_raw[(size_t)r * (P + 1) + j] = g_lp * ((j == a ? 1.f : 0.f) - p) + g_ent * pc.c_pano * (-p * (lp[j] + Hp));
-    }
-    float dlp_dmu, dlp_dv, dH_dmu, dH_dv;
-    for (int j = 0; j < P; ++j) {
-      d_d1[(size_t)r * P + j] = 0.f; d_d2[(size_t)r * P + j] = 0.f;
-      d_o1[(size_t)r * P + j] = 0.f; d_o2[(size_t)r * P + j] = 0.f;
-    }
-    tn_grads(td, y_d, mu_d, sg_d, &dlp_dmu, &dlp_dv, &dH_dmu, &dH_dv);
-    d_d1[(size_t)r * P + idx] = dm * (g_lp * dlp_dmu + g_ent * pc.c_distance * dH_dmu);
-    d_d2[(size_t)r * P + idx] = dm * (g_lp * dlp_dv + g_ent * pc.c_distance * dH_dv);
-    tn_grads(to, y_o, mu_o, sg_o, &dlp_dmu, &dlp_dv, &dH_dmu, &dH_dv);
-    d_o1[(size_t)r * P + idx] = om * (g_lp * dlp_dmu + g_ent * pc.c_offset * dH_dmu);
-    d_o2[(size_t)r * P + idx] = om * (g_lp * dlp_dv + g_ent * pc.c_offset * dH_dv);
     float dv;
     if (!pc.clipped_value || l1 >= l2) dv = v - rt;
     else dv = (diff > -pc.clip && diff < pc.clip) ? (vc - rt) : 0.f;
     d_values[r] = pc.value_coef * invR * dv;
+    wp_row_grads(lp, a, idx, P, Hp, td, to, y_d, y_o, mu_d, sg_d, mu_o, sg_o, dm, om, g_lp, g_ent * pc.c_pano,
+                 g_ent * pc.c_offset, g_ent * pc.c_distance, d_raw + (size_t)r * (P + 1), d_o1 + (size_t)r * P,
+                 d_o2 + (size_t)r * P, d_d1 + (size_t)r * P, d_d2 + (size_t)r * P);
   }
   if (!with_loss) return;
   const float t_val = block_sum(s_val, red); __syncthreads();
@@ -778,6 +815,19 @@ extern "C" int vlnce_wp_ppo_loss(const float* logp, const float* o1, const float
                                             lp_old, adv, R, P, act_consts(act_consts_host), pc, eval_out, losses, d_raw,
                                             d_o1, d_o2, d_d1, d_d2, d_values);
   VLNCE_LAUNCH_CHECK("wp_ppo_loss_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_wp_eval_bwd(const float* logp, const float* o1, const float* o2, const float* d1, const float* d2,
+                                 const float* a_pano, const float* a_offset, const float* a_distance,
+                                 const float* upstream, int R, int P, const float* act_consts_host, float* d_raw,
+                                 float* d_o1, float* d_o2, float* d_d1, float* d_d2, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(logp && o1 && o2 && d1 && d2 && a_pano && a_offset && a_distance && upstream && R > 0 && P > 0 &&
+                      act_consts_host && d_raw && d_o1 && d_o2 && d_d1 && d_d2,
+                  "wp_eval_bwd: bad arguments");
+  wp_eval_bwd_kernel<<<cdiv(R, 128), 128, 0, stream>>>(logp, o1, o2, d1, d2, a_pano, a_offset, a_distance, upstream, R,
+                                                      P, act_consts(act_consts_host), d_raw, d_o1, d_o2, d_d1, d_d2);
+  VLNCE_LAUNCH_CHECK("wp_eval_bwd_kernel");
   return VLNCE_OK;
 }
 

@@ -163,7 +163,7 @@ def make_waypoint_rows(gen, rows: int, rgb_hw: int = 224, hw: int = 256, length:
     feeds the policy: every sensor float32 (``batch_obs`` + ``.float()``), rgb 0..255."""
     rgb = torch.randint(0, 256, (rows, panos, rgb_hw, rgb_hw, 3), generator=gen, dtype=torch.uint8)
     rgb_h = torch.randint(0, 256, (rows, rgb_hw, rgb_hw, 3), generator=gen, dtype=torch.uint8)
-    instr = make_instruction(gen, rows, length, vocab) if instruction is None else instruction
+    instr = make_instruction(gen, rows, length, vocab, min_len=length // 2) if instruction is None else instruction
     return {
         "rgb": rgb if rgb_u8 else rgb.float(),
         "depth": torch.rand(rows, panos, hw, hw, 1, generator=gen),
@@ -203,7 +203,8 @@ def make_waypoint_eval_batch(seed: int, t: int, n: int, hidden: int = 256, layer
     gen = torch.Generator().manual_seed(seed)
     r = t * n
     length = kw.pop("length", 80)
-    instr = make_instruction(gen, n, length).unsqueeze(0).expand(t, n, length).reshape(r, length).contiguous()
+    instr = make_instruction(gen, n, length, min_len=length // 2)
+    instr = instr.unsqueeze(0).expand(t, n, length).reshape(r, length).contiguous()
     obs = make_waypoint_rows(gen, r, length=length, instruction=instr, **kw)
     h0 = torch.randn(n, layers, hidden, generator=gen) * 0.5
     actions = make_waypoint_actions(gen, r)
