@@ -348,9 +348,11 @@ int vlnce_wp_eval_bwd(const float* logp, const float* o1, const float* o2, const
 int vlnce_clip_grad_norm(float* g, long long n, float max_norm, float pre_scale, float* ws, size_t ws_bytes,
                          cudaStream_t stream);
 /* ActionDictRolloutStorage.compute_returns (common/rollout_storage.py:127-152): rewards (T,N), value_preds and
- * returns (T+1,N), masks (T+1,N) u8, next_value (N). */
+ * returns (T+1,N), masks (T+1,N) u8, next_value (N); optional advantages (T,N) = returns - value_preds
+ * (WDDPPO.get_advantages, common/ddppo_alg.py:30-32). */
 int vlnce_gae_returns(const float* rewards, float* value_preds, const unsigned char* masks, const float* next_value,
-                      float* returns, int T, int N, float gamma, float tau, int use_gae, cudaStream_t stream);
+                      float* returns, float* advantages, int T, int N, float gamma, float tau, int use_gae,
+                      cudaStream_t stream);
 
 #ifdef __cplusplus
 }

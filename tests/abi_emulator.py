@@ -58,7 +58,8 @@ class Emulator:
         if fn is None:
             raise NotImplementedError(f"abi_emulator: {name} is not emulated (conv-trunk entry point?)")
         self.count += 1
-        fn(*args)
+        with np.errstate(all="ignore"):  # uninitialised workspace beyond a row's length is read but never used
+            fn(*args)
 
     # ---- dense algebra ---------------------------------------------------------------
     def sgemm(self, A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta, act, ws, wsb, st):
@@ -584,7 +585,7 @@ class WaypointOps:
         w[1024], w[1025] = norm, f
         gv *= np.float32(f)
 
-    def gae_returns(self, rewards, value_preds, masks, next_value, returns, T, N, gamma, tau, use_gae, st):
+    def gae_returns(self, rewards, value_preds, masks, next_value, returns, advantages, T, N, gamma, tau, use_gae, st):
         rw = _flat(rewards, T * N).reshape(T, N)
         vp = _flat(value_preds, (T + 1) * N).reshape(T + 1, N)
         m = _flat(masks, (T + 1) * N, np.uint8).reshape(T + 1, N).astype(F32)
@@ -601,6 +602,8 @@ class WaypointOps:
             rt[T] = nv
             for t in range(T - 1, -1, -1):
                 rt[t] = rt[t + 1] * np.float32(gamma) * m[t + 1] + rw[t]
+        if advantages:
+            _flat(advantages, T * N).reshape(T, N)[...] = rt[:T] - vp[:T]
 
 
 for _name in [n for n in vars(WaypointOps) if not n.startswith("_")]:

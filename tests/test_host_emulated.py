@@ -102,3 +102,61 @@ def test_waypoint_plan_matches_golden(name):
     assert set(got) == {k for k in want if not k.startswith("_")}
     worst = check(got, want, 3e-4)
     print(name, "worst", worst)
+
+
+def _fill_rollouts(st, T, N, length=12):
+    from vlnce_b200 import synth
+
+    g = torch.Generator().manual_seed(9)
+    first = synth.make_waypoint_rows(g, N, length=length)
+    for k in st.observations:
+        st.observations[k][0].copy_(first[k])
+    for t in range(T):
+        a = synth.make_waypoint_actions(g, N)
+        st.insert(synth.make_waypoint_rows(g, N, length=length), torch.randn(N, 2, 256, generator=g) * 0.3, a,
+                  -2 + 0.2 * torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g) * 0.3,
+                  torch.randn(N, 1, generator=g), torch.ones(N, 1, dtype=torch.uint8))
+    return torch.randn(N, 1, generator=g) * 0.3
+
+
+def test_fused_wddppo_update_matches_oracle_loop():
+    """``WDDPPOStep.update`` (fused loss+gradient kernel, hand-written backward, clip, Adam; device-style rollout
+    storage with the GAE kernel) against the restated ``WDDPPO.update`` loop (itself pinned to the reference's
+    class in tests/test_waypoint_oracle.py): same six scalars, same updated parameters."""
+    from oracle import waypoint as oracle_wp
+    from vlnce_b200.ppo_step import ActionDictRolloutStorage, WDDPPOStep
+
+    case = cases.CASES["wp_eval"]
+    T, N = 2, 2
+    kw = dict(clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, offset_regularize_coef=0.1146,
+              pano_entropy_coef=1.0, offset_entropy_coef=1.0, distance_entropy_coef=1.0)
+    space = oracle_wp.storage_obs_space(length=12)
+    # oracle
+    opol = cases.build_policy(oracle_wp, case)
+    cases.set_mode(opol, case)
+    ost = oracle_wp.ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2)
+    nv = _fill_rollouts(ost, T, N)
+    ost.compute_returns(nv, True, 0.99, 0.95)
+    opt = torch.optim.Adam([p for p in opol.parameters() if p.requires_grad], lr=2e-4, eps=1e-5)
+    torch.manual_seed(21)
+    want = oracle_wp.ppo_update(opol, opt, ost, ppo_epoch=1, num_mini_batch=2, max_grad_norm=0.2,
+                                use_clipped_value_loss=True, **kw)
+    # fused path on the emulator
+    pol = cases.build_policy(vlnce_b200, case)
+    cases.set_mode(pol, case)
+    substitute_trunks(pol, case)
+    st = ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2)
+    nv2 = _fill_rollouts(st, T, N)
+    with lib.dry_run(executor=Emulator()):
+        st.compute_returns(nv2, True, 0.99, 0.95)
+        torch.testing.assert_close(st.returns, ost.returns, rtol=1e-6, atol=1e-6)
+        agent = WDDPPOStep(pol, ppo_epoch=1, num_mini_batch=2, lr=2e-4, eps=1e-5, max_grad_norm=0.2,
+                           use_clipped_value_loss=True, **kw)
+        torch.manual_seed(21)
+        got = agent.update(st)
+    torch.testing.assert_close(torch.tensor(got), torch.tensor(want), rtol=2e-4, atol=2e-6)
+    ref = dict(opol.named_parameters())
+    for k, p in pol.named_parameters():
+        if p.requires_grad:
+            # Adam's first steps move every weight by ~lr regardless of the gradient's size: compare the UPDATE
+            torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=4e-5, msg=lambda m: f"{k}: {m}")

@@ -596,7 +596,8 @@ __global__ void scale_by_dev_kernel(float* __restrict__ g, long long n, const fl
 // ------------------------------------------------------------------------------------
 __global__ void gae_returns_kernel(const float* __restrict__ rewards, float* __restrict__ value_preds,
                                    const unsigned char* __restrict__ masks, const float* __restrict__ next_value,
-                                   float* __restrict__ returns, int T, int N, float gamma, float tau, int use_gae) {
+                                   float* __restrict__ returns, float* __restrict__ advantages, int T, int N,
+                                   float gamma, float tau, int use_gae) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   if (use_gae) {
@@ -615,6 +616,9 @@ __global__ void gae_returns_kernel(const float* __restrict__ rewards, float* __r
       returns[(size_t)t * N + n] = returns[(size_t)(t + 1) * N + n] * gamma * (float)masks[(size_t)(t + 1) * N + n] +
                                    rewards[(size_t)t * N + n];
   }
+  if (advantages != nullptr)  // WDDPPO.get_advantages (ddppo_alg.py:30-32)
+    for (int t = 0; t < T; ++t)
+      advantages[(size_t)t * N + n] = returns[(size_t)t * N + n] - value_preds[(size_t)t * N + n];
 }
 
 }  // namespace
@@ -845,11 +849,11 @@ extern "C" int vlnce_clip_grad_norm(float* g, long long n, float max_norm, float
 }
 
 extern "C" int vlnce_gae_returns(const float* rewards, float* value_preds, const unsigned char* masks,
-                                 const float* next_value, float* returns, int T, int N, float gamma, float tau,
-                                 int use_gae, cudaStream_t stream) {
+                                 const float* next_value, float* returns, float* advantages, int T, int N, float gamma,
+                                 float tau, int use_gae, cudaStream_t stream) {
   VLNCE_CHECK_ARG(rewards && value_preds && masks && next_value && returns && T > 0 && N > 0, "gae_returns: bad arguments");
-  gae_returns_kernel<<<cdiv(N, 128), 128, 0, stream>>>(rewards, value_preds, masks, next_value, returns, T, N, gamma,
-                                                      tau, use_gae);
+  gae_returns_kernel<<<cdiv(N, 128), 128, 0, stream>>>(rewards, value_preds, masks, next_value, returns, advantages, T,
+                                                      N, gamma, tau, use_gae);
   VLNCE_LAUNCH_CHECK("gae_returns_kernel");
   return VLNCE_OK;
 }
