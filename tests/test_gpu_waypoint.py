@@ -257,17 +257,19 @@ def test_waypoint_act_matches_golden(name, precision, tol):
     probs = rel(got["pano_stop_logits"].exp(), want["pano_stop_logits"].exp())
     print(f"{name}[{precision}] rel err probs {probs:.3e} value {errs['value']:.3e} hidden {errs['rnn_states_out']:.3e} "
           f"log_prob {errs['action_log_probs']:.3e} modes {errs['mode/distance']:.3e}/{errs['mode/offset']:.3e}")
-    assert probs < tol and errs["value"] < 3 * tol and errs["rnn_states_out"] < 3 * tol
-    for k in ("mode/distance", "mode/offset", "variance/distance", "variance/offset", "get_value"):
-        assert errs[k] < 3 * tol, (k, errs[k])
+    assert probs < tol and errs["value"] < 3 * tol and errs["rnn_states_out"] < 3 * tol and errs["get_value"] < 3 * tol
+    # everything below is a function of the chosen pano: compare the rows whose argmax is decided by more than the
+    # tolerance (bit-exact there), a near-tie may legitimately flip under 16-bit trunk noise
     lg = want["pano_stop_logits"].exp()
     top2 = lg.topk(2, dim=1).values
     safe = (top2[:, 0] - top2[:, 1]) > 4 * tol * top2[:, 0]
-    assert torch.equal(got["action/pano"][safe], want["action/pano"][safe])   # argmax bit-exact off ties
-    if bool(safe.all()):
-        assert torch.equal(got["stop"], want["stop"])
-        for k in ("action/distance", "action/offset", "action_log_probs", "r_theta"):
-            assert errs[k] < 3 * tol, (k, errs[k])
+    assert precision != "fp32" or bool(safe.all())
+    assert torch.equal(got["action/pano"][safe], want["action/pano"][safe])
+    assert torch.equal(got["stop"][safe], want["stop"][safe])
+    for k in ("mode/distance", "mode/offset", "variance/distance", "variance/offset", "action/distance",
+              "action/offset", "action_log_probs", "r_theta"):
+        e = rel(got[k][safe], want[k][safe]) if bool(safe.any()) else 0.0
+        assert e < 3 * tol, (k, e)
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
@@ -285,12 +287,11 @@ def test_waypoint_ppo_minibatch_matches_golden(precision, tol):
         if e > worst[1]:
             worst = (k, e)
     print(f"wp_eval[{precision}] loss {float(got['loss']):.6f} vs {float(want['loss']):.6f}; worst {worst}")
-    for k in ("loss", "ppo/value_loss", "ppo/action_loss", "ppo/entropy_loss", "ppo/values", "ppo/action_log_probs"):
-        assert rel(got[k], want[k]) < tol, (k, rel(got[k], want[k]))
-    gtol = tol if precision == "fp32" else 5 * tol
-    for k in got:
-        if k.startswith("grad/") and float(want[k].abs().max()) > 1e-6:
-            assert rel(got[k], want[k]) < gtol, (k, rel(got[k], want[k]))
+    from test_gpu_train import check
+
+    # fp32: element-wise 1e-3; 16-bit trunks: outputs/losses at tol, gradients by relative L2 norm (same rule as the
+    # CMA / Seq2Seq training tests: single entries move discontinuously when a ReLU unit flips under feature noise)
+    check(got, want, tol, "wp_eval", grad_norm_tol=0.1 if precision == "bf16" else None)
 
 
 def test_fused_wddppo_update_matches_oracle_loop():
