@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="also write gpurun_out/step_profile.json")
+    ap.add_argument("--pdl", type=int, default=None, choices=[0, 1],
+                    help="programmatic dependent launch of the chained kernels (default: VLNCE_PDL / library default)")
     ap.add_argument("--ncu-step", action="store_true",
                     help="after warm-up run ONE eager, serial step between cudaProfilerStart/Stop and exit "
                          "(for `ncu --profile-from-start off`); prints no bench line")
@@ -193,6 +195,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.pdl is not None:
+        lib.C.vlnce_set_pdl(int(args.pdl))
     case = model_case()
     pol = cases.build_policy(vlnce_b200, case).to(dev).eval()
     pol.net.precision = args.precision
@@ -448,7 +452,8 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
-        roof = {"kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv, all 107 launches/step)", "bound": "tensor",
+        roof = {"kernel": "conv_tma_kernel + conv_umma_kernel (tcgen05 implicit-GEMM conv tiles, all 107 conv launches/step)",
+                "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
                 "launches_timed": len(rec), "conv_ms_per_step": conv_ms / 3,
@@ -467,7 +472,7 @@ def main():
                        "parallelism": f"dp{world}", "precision": "rgb trunk bf16 / depth trunk fp16 tcgen05, head fp32"
                        if args.precision == "bf16" else "fp32 CUDA cores",
                        "l2": f"inputs rotated over {NSETS} distinct batches ({NSETS * h2d_bytes / 1e6:.0f} MB > L2)",
-                       "cuda_graph": graph is not None,
+                       "cuda_graph": graph is not None, "pdl": bool(lib.C.vlnce_get_pdl()),
                        "schedule": "pipelined loop: frozen trunks of batch i+1 overlap head fwd/bwd/Adam of batch i "
                                    "(every timed step = one trunk pass + one head update; fill done in warm-up)"},
             "e2e": {"value": e2e_value, "unit": "policy steps/s", "h2d_bytes_per_step": h2d_bytes,

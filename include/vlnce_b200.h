@@ -45,6 +45,10 @@ const char* vlnce_version(void);
 const char* vlnce_last_error(void);
 /* number of kernel launches issued through this library since process start */
 long long vlnce_launch_count(void);
+/* Programmatic dependent launch of the chained trunk / GEMM kernels (launch-latency overlap; csrc/common.cuh).
+ * Default: environment VLNCE_PDL (unset = off). */
+int vlnce_set_pdl(int on);
+long long vlnce_get_pdl(void);
 
 /* ---- convolution trunks ------------------------------------------------------------ */
 /* Implicit-GEMM NHWC conv on tcgen05 tensor cores (16-bit operands, fp32 accumulate in TMEM):

@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace vlnce {
 
@@ -23,8 +24,26 @@ int cuda_status(cudaError_t e, const char* what) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("VLNCE_PDL");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+
 }  // namespace vlnce
 
 extern "C" const char* vlnce_version(void) { return "vlnce_b200 0.1 (sm_100a)"; }
 extern "C" const char* vlnce_last_error(void) { return vlnce::g_err; }
 extern "C" long long vlnce_launch_count(void) { return vlnce::g_launches.load(); }
+namespace vlnce { void set_pdl(int on); }
+extern "C" int vlnce_set_pdl(int on) {
+  vlnce::set_pdl(on);
+  return VLNCE_OK;
+}
+extern "C" long long vlnce_get_pdl(void) { return vlnce::pdl_enabled() ? 1 : 0; }

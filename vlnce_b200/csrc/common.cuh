@@ -34,6 +34,36 @@ void count_launch();
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// The step is a chain of ~370 short dependent kernels; with the programmatic-stream-serialization launch
+// attribute kernel i+1 is scheduled while kernel i still runs and parks at griddepcontrol.wait (which
+// returns once kernel i has completed and its memory is visible), so launch latency and the prologue
+// (barrier init, tensor-map prefetch, TMEM allocation) overlap the predecessor's tail.  Every kernel
+// launched through launch_pdl() executes pdl_wait() before its first global-memory access and
+// pdl_trigger() only after it owns its on-chip resources (TMEM).  VLNCE_PDL=0 turns the attribute off.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- tiny device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

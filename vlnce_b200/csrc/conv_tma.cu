@@ -192,6 +192,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: this CTA owns its TMEM columns and barriers -> let the next kernel in the stream get scheduled; then
+  // wait for the producer of our operands before the first global access (TMA loads / stores below)
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == kEpiWarps + 1) {
     // ------------------------------------------------------------ activation producer (one thread)
@@ -613,7 +617,8 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   if (ov_ctas > 1 && bytes(as, bs, sbufs) * ov_ctas <= 228 * 1024 - 1024 * ov_ctas && 2 * MT * BLOCK_N * ov_ctas <= 512)
     ctas = num_sms * ov_ctas;
   const int grid = total < ctas ? total : ctas;
-  conv_tma_kernel<BLOCK_N, MT><<<grid, kThreads, bytes(as, bs, sbufs), stream>>>(tx, tw, ty, tr, p);
+  launch_pdl(conv_tma_kernel<BLOCK_N, MT>, dim3(grid), dim3(kThreads), (size_t)bytes(as, bs, sbufs), stream, tx, tw, ty,
+             tr, p);
   VLNCE_LAUNCH_CHECK("conv_tma_kernel");
   return VLNCE_OK;
 }

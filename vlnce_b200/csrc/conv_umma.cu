@@ -128,6 +128,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // PDL (common.cuh): TMEM is ours; dependents may be scheduled, operands are read after the wait
+  pdl_wait();
 
   if (warp < 4) {
     if (p.stem) {
@@ -614,7 +616,8 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, 
   // (depth trunk / head run beside the RGB trunk instead of queueing behind it).
   int smem = C::smem_bytes(stages, p.out_tma, p.y_fp32, extra);
   if (exclusive && smem < 116 * 1024) smem = 116 * 1024;
-  conv_umma_kernel<BLOCK_N, BLOCK_K><<<(unsigned)tiles, kThreads, smem, stream>>>(tw, tx, ty, tr, p);
+  launch_pdl(conv_umma_kernel<BLOCK_N, BLOCK_K>, dim3((unsigned)tiles), dim3(kThreads), (size_t)smem, stream, tw, tx, ty,
+             tr, p);
   VLNCE_LAUNCH_CHECK("conv_umma_kernel");
   return VLNCE_OK;
 }

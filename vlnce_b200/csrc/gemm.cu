@@ -15,6 +15,8 @@ sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
              const float* __restrict__ B, long long ldb_k, long long ldb_n, float* __restrict__ C,
              long long ldc, const float* __restrict__ bias, int M, int N, int K, float beta, int act,
              float* __restrict__ partial, int k_per_split) {
+  pdl_trigger();  // PDL (common.cuh)
+  pdl_wait();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -111,6 +113,8 @@ sgemm_kernel(const float* __restrict__ A, long long lda_m, long long lda_k,
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ C,
                                      long long ldc, const float* __restrict__ bias, int M, int N,
                                      float beta, int act) {
+  pdl_trigger();  // PDL (common.cuh)
+  pdl_wait();
   const long long total = (long long)M * N;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -131,6 +135,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 // partial[S][N] for the fixed-order second stage below.
 __global__ void colsum_kernel(const float* __restrict__ A, long long lda, float* __restrict__ out,
                               int M, int N, int accumulate, float* __restrict__ partial) {
+  pdl_trigger();  // PDL (common.cuh)
+  pdl_wait();
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int slice = threadIdx.x >> 5, nslices = blockDim.x >> 5;
   const int S = gridDim.y;
@@ -152,6 +158,8 @@ __global__ void colsum_kernel(const float* __restrict__ A, long long lda, float*
 
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int S, float* __restrict__ out, int N,
                                     int accumulate) {
+  pdl_trigger();  // PDL (common.cuh)
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float t = 0.f;
@@ -181,20 +189,21 @@ extern "C" int vlnce_sgemm(const float* A, long long lda_m, long long lda_k, con
     while (splits > 1 && (size_t)splits * M * N * sizeof(float) > workspace_bytes) --splits;
   }
   if (splits <= 1) {
-    sgemm_kernel<<<grid, 256, 0, stream>>>(A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta, act,
-                                           nullptr, K);
+    launch_pdl(sgemm_kernel, grid, dim3(256), 0, stream, A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta, act,
+               (float*)nullptr, K);
     VLNCE_LAUNCH_CHECK("sgemm_kernel");
     return VLNCE_OK;
   }
   int k_per = cdiv(cdiv(K, splits), TK) * TK;
   splits = cdiv(K, k_per);
   grid.z = splits;
-  sgemm_kernel<<<grid, 256, 0, stream>>>(A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta, act,
-                                         workspace, k_per);
+  launch_pdl(sgemm_kernel, grid, dim3(256), 0, stream, A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta, act,
+             workspace, k_per);
   VLNCE_LAUNCH_CHECK("sgemm_kernel(split-K)");
   const long long total = (long long)M * N;
   const int rgrid = (int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
-  splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(workspace, splits, C, ldc, bias, M, N, beta, act);
+  launch_pdl(splitk_reduce_kernel, dim3(rgrid), dim3(256), 0, stream, (const float*)workspace, splits, C, ldc, bias, M, N,
+             beta, act);
   VLNCE_LAUNCH_CHECK("splitk_reduce_kernel");
   return VLNCE_OK;
 }
@@ -208,10 +217,10 @@ extern "C" int vlnce_colsum(const float* A, long long lda, float* out, int M, in
     while (S > 1 && (size_t)S * N * sizeof(float) > workspace_bytes) --S;
   }
   dim3 grid(cdiv(N, 32), S);
-  colsum_kernel<<<grid, 256, 0, stream>>>(A, lda, out, M, N, accumulate, S > 1 ? workspace : nullptr);
+  launch_pdl(colsum_kernel, grid, dim3(256), 0, stream, A, lda, out, M, N, accumulate, S > 1 ? workspace : (float*)nullptr);
   VLNCE_LAUNCH_CHECK("colsum_kernel");
   if (S > 1) {
-    colsum_final_kernel<<<cdiv(N, 128), 128, 0, stream>>>(workspace, S, out, N, accumulate);
+    launch_pdl(colsum_final_kernel, dim3(cdiv(N, 128)), dim3(128), 0, stream, (const float*)workspace, S, out, N, accumulate);
     VLNCE_LAUNCH_CHECK("colsum_final_kernel");
   }
   return VLNCE_OK;

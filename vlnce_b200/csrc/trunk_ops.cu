@@ -142,6 +142,8 @@ __global__ void im2col_rgb_stem_kernel(const TX* __restrict__ x, TA* __restrict_
 template <typename TA>
 __global__ void im2col_depth_stem_kernel(const float* __restrict__ x, TA* __restrict__ a,
                                          int N, int H, int W, int P, int Q) {
+  pdl_trigger();  // PDL (common.cuh)
+  pdl_wait();
   // x: (N,H,W,1); pooled image is (H/2, W/2); output pixel (p,q) of the 7x7/2 pad-3 conv
   constexpr int KP = 64, CHUNKS = KP / 8;
   const int Hp = H / 2, Wp = W / 2;
@@ -191,6 +193,8 @@ __global__ void avgpool2x2_kernel(const float* __restrict__ x, float* __restrict
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W,
                                     int C, int P, int Q) {
+  pdl_trigger();  // PDL (common.cuh)
+  pdl_wait();
   // 8 channels per thread (C % 8 == 0): one 16-byte load per window tap
   const int CV = C / 8;
   const long long total = (long long)N * P * Q * CV;
@@ -277,6 +281,8 @@ __global__ void groupnorm_stats_kernel(const T* __restrict__ x, const float* __r
 __global__ void __launch_bounds__(256)
 gn_partial_kernel(const float* __restrict__ x, float* __restrict__ part /*[N][S][G][2]*/, int HW, int C,
                   int groups) {
+  pdl_trigger();  // PDL (common.cuh)
+  pdl_wait();
   __shared__ float bins[2 * 64];
   const int n = blockIdx.x, s = blockIdx.y, S = gridDim.y;
   const int c4n = C / 4;
@@ -421,6 +427,8 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, int S,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                 const TO* __restrict__ residual, TO* __restrict__ y, int HW, int C, int relu) {
+  pdl_trigger();  // PDL (common.cuh)
+  pdl_wait();
   extern __shared__ float gn_sm[];
   float* sc = gn_sm;
   float* sh = gn_sm + C;
@@ -480,6 +488,8 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, int
 template <typename T>
 __global__ void adaptive_avgpool_kernel(const T* __restrict__ x, float* __restrict__ y, int ldy,
                                         int N, int H, int W, int C, int O) {
+  pdl_trigger();  // PDL (common.cuh)
+  pdl_wait();
   const int OO = O * O;
   const long long total = (long long)N * OO * C;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -799,22 +809,21 @@ extern "C" int vlnce_groupnorm_fused(const float* x, const float* gamma, const f
   if (S > 8) S = 8;  // N x S CTAs already fill the chip at N >= 19; fewer slices = a shorter combine in apply
   while (S > 1 && (size_t)N * S * groups * 2 * sizeof(float) > workspace_bytes) --S;
   VLNCE_CHECK_ARG((size_t)N * S * groups * 2 * sizeof(float) <= workspace_bytes, "groupnorm_fused: workspace too small");
-  gn_partial_kernel<<<dim3(N, S), 256, 0, stream>>>(x, workspace, HW, C, groups);
+  launch_pdl(gn_partial_kernel, dim3(N, S), dim3(256), 0, stream, x, workspace, HW, C, groups);
   VLNCE_LAUNCH_CHECK("gn_partial_kernel");
   int slices = cdiv((long long)HW * C, 8192);
   if (slices > 64) slices = 64;
   const size_t smem = sizeof(float) * 2 * C;
   dim3 grid(N, slices);
   if (y_dtype == VLNCE_F16)
-    gn_apply_kernel<__half><<<grid, 256, smem, stream>>>(x, workspace, S, gamma, beta, groups, eps,
-                                                         (const __half*)residual, (__half*)y, HW, C, relu);
+    launch_pdl(gn_apply_kernel<__half>, grid, dim3(256), smem, stream, x, (const float*)workspace, S, gamma, beta, groups,
+               eps, (const __half*)residual, (__half*)y, HW, C, relu);
   else if (y_dtype == VLNCE_BF16)
-    gn_apply_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(x, workspace, S, gamma, beta, groups, eps,
-                                                                (const __nv_bfloat16*)residual, (__nv_bfloat16*)y,
-                                                                HW, C, relu);
+    launch_pdl(gn_apply_kernel<__nv_bfloat16>, grid, dim3(256), smem, stream, x, (const float*)workspace, S, gamma, beta,
+               groups, eps, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, HW, C, relu);
   else
-    gn_apply_kernel<float><<<grid, 256, smem, stream>>>(x, workspace, S, gamma, beta, groups, eps,
-                                                        (const float*)residual, (float*)y, HW, C, relu);
+    launch_pdl(gn_apply_kernel<float>, grid, dim3(256), smem, stream, x, (const float*)workspace, S, gamma, beta, groups,
+               eps, (const float*)residual, (float*)y, HW, C, relu);
   VLNCE_LAUNCH_CHECK("gn_apply_kernel");
   return VLNCE_OK;
 }
