@@ -40,6 +40,12 @@ CASES = {
     "seq2seq_train_features": dict(policy="Seq2SeqPolicy", pm=False, kind="train", t=4, n=3, hw=256,
                                    length=24, wseed=18, iseed=108, bn_train=False, features=True,
                                    prev_action=True),
+    # BASELINE config C5 shape family (rxr_cma_en.yaml): precomputed multilingual-BERT instruction features
+    # (768-d, zero rows beyond the instruction), 6 actions; L cut from 512 to keep the CPU oracle fast
+    "cma_rxr_act": dict(policy="CMAPolicy", pm=False, kind="act", n=3, hw=256, rgb_hw=224, length=48, wseed=19,
+                        iseed=109, bn_train=False, rxr=768, actions=6),
+    "cma_rxr_train_features": dict(policy="CMAPolicy", pm=True, kind="train", t=3, n=3, hw=256, length=40, wseed=20,
+                                   iseed=110, bn_train=False, features=True, rxr=768, actions=6, coef=1.9),
     # Waypoint path (BASELINE config C4 dims, 1-wpn-cc.yaml): act on a fresh/continuing env pair,
     # and one PPO mini-batch (evaluate_actions -> WDDPPO losses -> gradients)
     "wp_act": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=40, wseed=21, iseed=201),
@@ -65,6 +71,8 @@ def model_config(case) -> hb017.Config:
 
         return waypoint.waypoint_model_config()
     over = dict(PROGRESS_MONITOR=dict(use=bool(case["pm"]), alpha=1.0))
+    if case.get("rxr"):  # rxr_cma_en.yaml:43-48
+        over["INSTRUCTION_ENCODER"] = dict(sensor_uuid="rxr_instruction", embedding_size=int(case["rxr"]))
     if case["policy"] == "CMAPolicy":
         return vlnce.cma_model_config(**over)
     if case.get("prev_action"):
@@ -81,12 +89,13 @@ def obs_space(case):
                        "depth": hb017.Box(0.0, 1.0, (case["hw"], case["hw"], 1), "float32")})
 
 
-def build_policy(impl, case, num_actions=4):
+def build_policy(impl, case, num_actions=None):
     """impl: namespace with CMAPolicy / Seq2SeqPolicy (reference import, oracle.vlnce
     or the CUDA package)."""
     cfg = hb017.Config(MODEL=model_config(case), TORCH_GPU_ID=0,
                        TASK_CONFIG=dict(TASK=dict(PANO_ROTATIONS=12)))
     cls = getattr(impl, case["policy"])
+    num_actions = num_actions or case.get("actions", 4)
     pol = cls.from_config(cfg, obs_space(case), hb017.Discrete(num_actions))
     pol.load_state_dict(synth.seeded_state_dict(pol, case["wseed"]))
     return pol
@@ -118,11 +127,14 @@ def inputs(case):
     if case["kind"] == "act":
         return synth.make_act_batch(case["iseed"], case["n"], hw=case["hw"],
                                     rgb_hw=case.get("rgb_hw"), length=case["length"],
-                                    layers=layers_of(case))
+                                    layers=layers_of(case), num_actions=case.get("actions", 4),
+                                    rxr_dim=case.get("rxr", 0))
     return synth.make_train_batch(case["iseed"], case["t"], case["n"], hw=case["hw"],
                                   rgb_hw=case.get("rgb_hw"), length=case["length"],
                                   features=case["features"],
-                                  rgb_feature_hw=1 if case["policy"] == "Seq2SeqPolicy" else 4)
+                                  rgb_feature_hw=1 if case["policy"] == "Seq2SeqPolicy" else 4,
+                                  num_actions=case.get("actions", 4), coef=case.get("coef", 3.2),
+                                  rxr_dim=case.get("rxr", 0))
 
 
 def grad_digest(g: torch.Tensor) -> torch.Tensor:

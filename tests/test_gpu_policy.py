@@ -54,7 +54,7 @@ def test_trunks_match_oracle(precision, tol):
     assert e_rgb < tol and e_dep < tol
 
 
-@pytest.mark.parametrize("name", ["cma_act", "cma_act_rgb224", "cma_act_bntrain"])
+@pytest.mark.parametrize("name", ["cma_act", "cma_act_rgb224", "cma_act_bntrain", "cma_rxr_act"])
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
 def test_cma_act_matches_golden(name, precision, tol):
     case = cases.CASES[name]

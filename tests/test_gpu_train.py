@@ -56,6 +56,7 @@ def check(got, want, rtol, name, grad_norm_tol=None):
 
 @pytest.mark.parametrize("name,precision,rtol", [
     ("cma_train_features", "fp32", 1e-3), ("cma_train_features_nopm", "fp32", 1e-3),
+    ("cma_rxr_train_features", "fp32", 1e-3),  # BASELINE C5 family: RxR BERT-feature instructions, 6 actions
     ("cma_train_pixels", "fp32", 1e-3), ("cma_train_pixels", "bf16", 1e-2),
     ("seq2seq_train_features", "fp32", 1e-3), ("seq2seq_train_pixels", "fp32", 1e-3),
     ("seq2seq_train_pixels", "bf16", 1e-2)])

@@ -13,7 +13,8 @@ warnings.filterwarnings("ignore")
 
 
 @pytest.mark.parametrize("name,precision", [("cma_act", "bf16"), ("cma_act", "fp32"),
-                                            ("cma_act_bntrain", "bf16"), ("cma_act_rgb224", "bf16")])
+                                            ("cma_act_bntrain", "bf16"), ("cma_act_rgb224", "bf16"),
+                                            ("cma_rxr_act", "bf16")])
 def test_act_launch_sequence(name, precision):
     case = cases.CASES[name]
     pol = cases.build_policy(vlnce_b200, case)

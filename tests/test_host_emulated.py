@@ -39,7 +39,8 @@ def check(got, want, tol, skip=()):
     return worst
 
 
-@pytest.mark.parametrize("name", ["cma_train_features", "cma_train_features_nopm", "seq2seq_train_features"])
+@pytest.mark.parametrize("name", ["cma_train_features", "cma_train_features_nopm", "seq2seq_train_features",
+                                  "cma_rxr_train_features"])
 def test_il_train_plan_matches_golden(name):
     with lib.dry_run(executor=Emulator()):
         got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses)

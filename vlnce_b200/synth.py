@@ -38,15 +38,20 @@ def make_rxr_instruction(gen, rows: int, length: int = 512, dim: int = 768,
 def make_act_batch(seed: int, n: int, hw: int = 256, rgb_hw: int | None = None,
                    length: int = 80, hidden: int = 512, layers: int = 2,
                    vocab: int = 2504, num_actions: int = 4,
-                   fresh: bool = False) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, torch.Tensor, torch.Tensor]:
-    """One ``policy.act`` call: (observations, rnn_states, prev_actions, masks)."""
+                   fresh: bool = False, rxr_dim: int = 0) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, torch.Tensor, torch.Tensor]:
+    """One ``policy.act`` call: (observations, rnn_states, prev_actions, masks).  ``rxr_dim`` > 0: the
+    instruction arrives as precomputed multilingual-BERT features ``rxr_instruction`` (R, L, rxr_dim), zero rows
+    beyond each instruction's length (``rxr_cma_en.yaml:43-48``, ``instruction_encoder.py:74-78``)."""
     gen = torch.Generator().manual_seed(seed)
     rgb_hw = rgb_hw or hw
     obs = {
         "rgb": torch.randint(0, 256, (n, rgb_hw, rgb_hw, 3), generator=gen, dtype=torch.uint8),
         "depth": torch.rand(n, hw, hw, 1, generator=gen),
-        "instruction": make_instruction(gen, n, length, vocab),
     }
+    if rxr_dim:
+        obs["rxr_instruction"] = make_rxr_instruction(gen, n, length, rxr_dim, min_len=length // 2)
+    else:
+        obs["instruction"] = make_instruction(gen, n, length, vocab)
     if fresh:
         h = torch.zeros(n, layers, hidden)
         prev = torch.zeros(n, 1, dtype=torch.int64)
@@ -60,7 +65,8 @@ def make_act_batch(seed: int, n: int, hw: int = 256, rgb_hw: int | None = None,
 
 def make_train_batch(seed: int, t: int, n: int, hw: int = 256, rgb_hw: int | None = None,
                      length: int = 80, vocab: int = 2504, num_actions: int = 4,
-                     coef: float = 3.2, ragged: bool = True, features: bool = False, rgb_feature_hw: int = 4):
+                     coef: float = 3.2, ragged: bool = True, features: bool = False, rgb_feature_hw: int = 4,
+                     rxr_dim: int = 0):
     """One ``_update_agent`` call in the collate_fn layout: returns
     (observations, prev_actions (T*N,1), not_done_masks (T*N,1) u8,
     corrected_actions (T,N) i64, weights (T,N) f32)."""
@@ -68,8 +74,13 @@ def make_train_batch(seed: int, t: int, n: int, hw: int = 256, rgb_hw: int | Non
     rgb_hw = rgb_hw or hw
     r = t * n
     # the same instruction for all T rows of a trajectory (dagger_trainer.py:342-362)
-    instr = make_instruction(gen, n, length, vocab).unsqueeze(0).expand(t, n, length).reshape(r, length)
-    obs: Dict[str, torch.Tensor] = {"instruction": instr.contiguous()}
+    if rxr_dim:
+        feats = make_rxr_instruction(gen, n, length, rxr_dim, min_len=length // 2)
+        obs: Dict[str, torch.Tensor] = {
+            "rxr_instruction": feats.unsqueeze(0).expand(t, n, length, rxr_dim).reshape(r, length, rxr_dim).contiguous()}
+    else:
+        instr = make_instruction(gen, n, length, vocab).unsqueeze(0).expand(t, n, length).reshape(r, length)
+        obs = {"instruction": instr.contiguous()}
     if features:  # DAgger caches frozen-CNN features (dagger_trainer.py:300-314)
         # spatial encoders (CMA) cache the 4x4 map, the Seq2Seq encoder its globally pooled 1x1 output
         obs["rgb_features"] = torch.rand(r, 2048, rgb_feature_hw, rgb_feature_hw, generator=gen)
