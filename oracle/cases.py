@@ -51,6 +51,11 @@ CASES = {
     "wp_act": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=40, wseed=21, iseed=201),
     "wp_act_u8": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=24, wseed=22, iseed=202, rgb_u8=True),
     "wp_eval": dict(policy="WaypointPolicy", kind="wp_eval", t=3, n=2, length=32, wseed=23, iseed=203),
+    # heading-prediction variants (5-hpn-_c.yaml: fixed 0.25 m distance; 6-hpn-__.yaml: neither head sampled)
+    "wp_act_hpn": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=24, wseed=24, iseed=204,
+                       waypoint=dict(predict_distance=False)),
+    "wp_eval_hpn": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=25, iseed=205,
+                        waypoint=dict(predict_distance=False, predict_offset=False)),
 }
 
 WP_OBS_SPACE = dict(rgb=(12, 224, 224, 3), depth=(12, 256, 256, 1))
@@ -69,7 +74,7 @@ def model_config(case) -> hb017.Config:
     if case["policy"] == "WaypointPolicy":
         from . import waypoint
 
-        return waypoint.waypoint_model_config()
+        return waypoint.waypoint_model_config(WAYPOINT=dict(case.get("waypoint", {})))
     over = dict(PROGRESS_MONITOR=dict(use=bool(case["pm"]), alpha=1.0))
     if case.get("rxr"):  # rxr_cma_en.yaml:43-48
         over["INSTRUCTION_ENCODER"] = dict(sensor_uuid="rxr_instruction", embedding_size=int(case["rxr"]))

@@ -247,7 +247,7 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max()) / (float(b.abs().max()) + 1e-12)
 
 
-@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8"])
+@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_act_hpn"])
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
 def test_waypoint_act_matches_golden(name, precision, tol):
     want = gold(name)
@@ -271,12 +271,13 @@ def test_waypoint_act_matches_golden(name, precision, tol):
         assert e < 3 * tol, (k, e)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
-def test_waypoint_ppo_minibatch_matches_golden(precision, tol):
+@pytest.mark.parametrize("name,precision,tol", [("wp_eval", "fp32", 1e-3), ("wp_eval", "bf16", 2e-2),
+                                                ("wp_eval_hpn", "fp32", 1e-3)])
+def test_waypoint_ppo_minibatch_matches_golden(name, precision, tol):
     """evaluate_actions -> the reference's WDDPPO loss arithmetic in torch -> loss.backward() through the
     one-node autograd bridge (hand-written CUDA backward)."""
-    want = gold("wp_eval")
-    got = cases.run_case(vlnce_b200, "wp_eval", aux=vlnce_b200.AuxLosses, device=DEV, precision=precision)
+    want = gold(name)
+    got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, device=DEV, precision=precision)
     assert set(got) == {k for k in want if not k.startswith("_")}
     worst = ("", 0.0)
     for k, v in got.items():
@@ -285,11 +286,11 @@ def test_waypoint_ppo_minibatch_matches_golden(precision, tol):
             e = 0.0
         if e > worst[1]:
             worst = (k, e)
-    print(f"wp_eval[{precision}] loss {float(got['loss']):.6f} vs {float(want['loss']):.6f}; worst {worst}")
+    print(f"{name}[{precision}] loss {float(got['loss']):.6f} vs {float(want['loss']):.6f}; worst {worst}")
     from test_gpu_train import check
 
     if precision == "fp32":  # element-wise 1e-3 (digests of the large tensors included)
-        check(got, want, tol, "wp_eval")
+        check(got, want, tol, name)
         return
     # 16-bit trunks: outputs / losses at tol; gradients by relative L2 norm per tensor.  On a 6-row batch a
     # single ReLU unit flipping under 2e-3 feature noise moves a bias gradient by ~10 %, so the per-tensor bound

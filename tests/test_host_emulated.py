@@ -94,7 +94,7 @@ class _Impl:
         return Wrapped
 
 
-@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_eval"])
+@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_eval", "wp_act_hpn", "wp_eval_hpn"])
 def test_waypoint_plan_matches_golden(name):
     case = cases.CASES[name]
     with lib.dry_run(executor=Emulator()):
