@@ -95,6 +95,8 @@ int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scal
  *                       is 7 or the channel is padding).  K % 64 == 0; block_n as vlnce_conv_tma. */
 /* Debug aid of the persistent conv tiles: a device buffer of 4*768*2 int64 that CTA 0 of every later
  * vlnce_conv_tma / vlnce_conv_stem_tma launch fills with per-role (event, clock64) records; NULL = off. */
+/* cap on the persistent conv_tma grid (0 = one CTA per SM; default: environment VLNCE_TMA_CTA_CAP) */
+int vlnce_set_tma_cta_cap(int cap);
 int vlnce_debug_set_trace(void* buffer);
 int vlnce_stem_s2d(const void* x, int x_dtype, void* out, int out_dtype, int N, int H, int W,
                    cudaStream_t stream);
@@ -145,6 +147,10 @@ int vlnce_groupnorm_fused(const float* x, const float* gamma, const float* beta,
                           int y_dtype, float* workspace, size_t workspace_bytes, float* scale_scratch,
                           float* shift_scratch, int N, int HW, int C, int groups, float eps, int relu,
                           cudaStream_t stream);
+/* the same for an fp16 raw conv output (x, residual, y all fp16): half the bytes per pass */
+int vlnce_groupnorm_fused16(const void* x, const float* gamma, const float* beta, const void* residual, void* y,
+                            float* workspace, size_t workspace_bytes, int N, int HW, int C, int groups, float eps,
+                            int relu, cudaStream_t stream);
 /* Train-mode BatchNorm2d statistics over all N*HW rows: per-channel scale/shift
  * from batch mean / biased var; updates running_mean/var (momentum, unbiased var) in place. */
 int vlnce_batchnorm_train_stats(const void* x, int dtype, const float* gamma, const float* beta,

@@ -39,6 +39,14 @@ def graph_time(fn, iters=20):
 
 
 def main():
+    import argparse
+
+    from vlnce_b200 import lib
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--caps", default="0", help="comma-separated persistent-grid caps for conv_tma (0 = none)")
+    ap.add_argument("--chunks", default="", help="comma-separated depth-trunk chunk counts to sweep")
+    args = ap.parse_args()
     n = 64
     case = dict(cases.CASES["cma_train_pixels"], t=1, n=n)
     pol = cases.build_policy(vlnce_b200, case).cuda().eval()
@@ -49,7 +57,30 @@ def main():
     eng.ensure_pool(torch.device("cuda"))
     step._prepare()
     rgb_e, dep_e = eng.visual_buffers(n, "next")
-    res = {}
+    eng.encode_visual(obs, rgb_e, dep_e)  # autotune every layer once, uncapped
+    torch.cuda.synchronize()
+    sweep = {}
+    for cap in [int(c) for c in args.caps.split(",")][1:]:
+        lib.C.vlnce_set_tma_cta_cap(cap)
+        sweep[cap] = {
+            "rgb_trunk_ms": graph_time(lambda: pol.net.rgb_encoder.features_into(obs, rgb_e, eng.Crgb, "bf16")),
+            "both_trunks_ms": graph_time(lambda: eng.encode_visual(obs, rgb_e, dep_e))}
+        print("cap", cap, json.dumps(sweep[cap]), flush=True)
+    lib.C.vlnce_set_tma_cta_cap(int(args.caps.split(",")[0]))
+    from vlnce_b200 import trunk as trunk_mod
+
+    csweep = {}
+    for k in [int(c) for c in args.chunks.split(",") if c]:
+        trunk_mod.DEPTH_CHUNKS = k
+        pol.net.depth_encoder.features_into(obs, dep_e, eng.Cdep, "bf16")  # tune the chunk geometries
+        torch.cuda.synchronize()
+        csweep[k] = {
+            "depth_trunk_ms": graph_time(lambda: pol.net.depth_encoder.features_into(obs, dep_e, eng.Cdep, "bf16")),
+            "both_trunks_ms": graph_time(lambda: eng.encode_visual(obs, rgb_e, dep_e)),
+            "pipelined_step_ms": None}
+        print("chunks", k, json.dumps(csweep[k]), flush=True)
+    trunk_mod.DEPTH_CHUNKS = int(os.environ.get("VLNCE_DEPTH_CHUNKS", "1"))
+    res = {"cap": int(args.caps.split(",")[0]), "cap_sweep": sweep, "chunk_sweep": csweep}
     res["rgb_trunk_ms"] = graph_time(lambda: pol.net.rgb_encoder.features_into(obs, rgb_e, eng.Crgb, "bf16"))
     res["depth_trunk_ms"] = graph_time(lambda: pol.net.depth_encoder.features_into(obs, dep_e, eng.Cdep, "bf16"))
     res["both_trunks_ms"] = graph_time(lambda: eng.encode_visual(obs, rgb_e, dep_e))

@@ -1,6 +1,8 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <mutex>
+#include <unordered_set>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -35,6 +37,19 @@ bool pdl_enabled() {
   return v != 0;
 }
 void set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+
+bool carveout_first_use(const void* kernel) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> seen;
+  static int enabled = -1;
+  std::lock_guard<std::mutex> lock(mu);
+  if (enabled < 0) {
+    const char* e = getenv("VLNCE_CARVEOUT");
+    enabled = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (!enabled) return false;
+  return seen.insert(kernel).second;
+}
 
 }  // namespace vlnce
 

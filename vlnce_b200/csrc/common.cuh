@@ -42,6 +42,10 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // launched through launch_pdl() executes pdl_wait() before its first global-memory access and
 // pdl_trigger() only after it owns its on-chip resources (TMEM).  VLNCE_PDL=0 turns the attribute off.
 bool pdl_enabled();
+// Pin the L1/shared-memory split of every kernel launched through launch_pdl() to "max shared" (once per
+// kernel): the trunks alternate tensor-core tiles (>100 KB dynamic smem) with small statistics / pointwise
+// kernels, and an SM has to drain before it can change its carve-out.  VLNCE_CARVEOUT=0 leaves the driver default.
+bool carveout_first_use(const void* kernel);
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -49,6 +53,8 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args... args) {
+  if (carveout_first_use(reinterpret_cast<const void*>(kernel)))
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;

@@ -541,6 +541,9 @@ int map_nd(EncodeTiledFn enc, CUtensorMap* m, const void* base, CUtensorMapDataT
 }
 
 long long* g_trace = nullptr;
+// Upper bound on the persistent grid (0 = one CTA per SM): leaving a few SMs free lets the short kernels of
+// concurrent graph branches (depth trunk, head) run beside the RGB trunk instead of queueing behind it.
+int g_cta_cap = -1;
 
 template <int BLOCK_N, int MT>
 int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const CUtensorMap& tr,
@@ -614,6 +617,11 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   p.rcp_tiles_y = 1.0f / (float)p.tiles_y;
   const int total = (p.m_tiles / MT) * p.n_tiles;
   int ctas = num_sms;
+  if (g_cta_cap < 0) {
+    const char* e = getenv("VLNCE_TMA_CTA_CAP");
+    g_cta_cap = e ? atoi(e) : 0;
+  }
+  if (g_cta_cap > 0 && g_cta_cap < ctas) ctas = g_cta_cap;
   if (ov_ctas > 1 && bytes(as, bs, sbufs) * ov_ctas <= 228 * 1024 - 1024 * ov_ctas && 2 * MT * BLOCK_N * ov_ctas <= 512)
     ctas = num_sms * ov_ctas;
   const int grid = total < ctas ? total : ctas;
@@ -645,6 +653,11 @@ using namespace vlnce;
 #define VLNCE_TMA_NO_STATIONARY (1 << 22)
 
 // R = 1 (1x1, pad 0) or R = 3 (3x3, pad 1); stride 1.
+extern "C" int vlnce_set_tma_cta_cap(int cap) {
+  g_cta_cap = cap < 0 ? 0 : cap;
+  return VLNCE_OK;
+}
+
 extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
                               const void* residual, void* y, int y_dtype, int N, int H, int W, int C, int K, int R,
                               int relu, int block_n, cudaStream_t stream) {

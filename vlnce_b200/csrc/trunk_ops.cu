@@ -278,8 +278,21 @@ __global__ void groupnorm_stats_kernel(const T* __restrict__ x, const float* __r
 // Coalesced two-stage GroupNorm statistics for fp32 raw conv output (C % 4 == 0, C/4 <= 256,
 // 256 % (C/4) == 0): stage 1 = grid (N, S) CTAs stream float4 rows and bin (sum, sumsq) per
 // group in shared memory; stage 2 combines the S slices in fp64 and writes scale/shift.
+template <typename TI>
+__device__ __forceinline__ float4 load4f(const TI* p);
+template <>
+__device__ __forceinline__ float4 load4f<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 load4f<__half>(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename TI>
 __global__ void __launch_bounds__(256)
-gn_partial_kernel(const float* __restrict__ x, float* __restrict__ part /*[N][S][G][2]*/, int HW, int C,
+gn_partial_kernel(const TI* __restrict__ x, float* __restrict__ part /*[N][S][G][2]*/, int HW, int C,
                   int groups) {
   pdl_trigger();  // PDL (common.cuh)
   pdl_wait();
@@ -293,9 +306,9 @@ gn_partial_kernel(const float* __restrict__ x, float* __restrict__ part /*[N][S]
   const int rows_per = (HW + S - 1) / S;
   const int r0 = s * rows_per, r1 = min(HW, r0 + rows_per);
   float s01 = 0.f, q01 = 0.f, s23 = 0.f, q23 = 0.f;
-  const float* base = x + (size_t)n * HW * C + lane_c * 4;
+  const TI* base = x + (size_t)n * HW * C + lane_c * 4;
   for (int r = r0 + lane_r; r < r1; r += rstep) {
-    const float4 v = *reinterpret_cast<const float4*>(base + (size_t)r * C);
+    const float4 v = load4f<TI>(base + (size_t)r * C);
     s01 += v.x + v.y; q01 = fmaf(v.x, v.x, fmaf(v.y, v.y, q01));
     s23 += v.z + v.w; q23 = fmaf(v.z, v.z, fmaf(v.w, v.w, q23));
   }
@@ -422,9 +435,9 @@ __global__ void affine_apply_kernel(const T* __restrict__ x, const float* __rest
 // GroupNorm finalize + apply in one pass: every CTA first rebuilds the per-channel scale/shift of
 // its image from the stage-1 partial sums (S x G pairs, fp64 combine), then normalises its slice
 // of rows: y = act(raw * scale[c] + shift[c] (+ residual)).  grid (N, slices).
-template <typename TO>
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, int S,
+gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ part, int S,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int groups, float eps,
                 const TO* __restrict__ residual, TO* __restrict__ y, int HW, int C, int relu) {
   pdl_trigger();  // PDL (common.cuh)
@@ -467,7 +480,7 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, int
     const int c0 = (int)(v % cv) * 8;
     const long long e0 = ((long long)n * HW) * C + v * 8;
     float f[8];
-    load8<float>(x + e0, f);
+    load8<TI>(x + e0, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], sc[c0 + e], sh[c0 + e]);
     if (residual != nullptr) {
@@ -678,7 +691,7 @@ extern "C" int vlnce_groupnorm_stats(const void* x, int dtype, const float* gamm
     if (S > HW) S = HW;
     while (S > 1 && (size_t)N * S * groups * 2 * sizeof(float) > workspace_bytes) --S;
     if ((size_t)N * S * groups * 2 * sizeof(float) <= workspace_bytes) {
-      gn_partial_kernel<<<dim3(N, S), 256, 0, stream>>>((const float*)x, workspace, HW, C, groups);
+      gn_partial_kernel<float><<<dim3(N, S), 256, 0, stream>>>((const float*)x, workspace, HW, C, groups);
       VLNCE_LAUNCH_CHECK("gn_partial_kernel");
       gn_finalize_kernel<<<N, 256, 0, stream>>>(workspace, S, gamma, beta, scale, shift, HW, C, groups, eps);
       VLNCE_LAUNCH_CHECK("gn_finalize_kernel");
@@ -809,21 +822,49 @@ extern "C" int vlnce_groupnorm_fused(const float* x, const float* gamma, const f
   if (S > 8) S = 8;  // N x S CTAs already fill the chip at N >= 19; fewer slices = a shorter combine in apply
   while (S > 1 && (size_t)N * S * groups * 2 * sizeof(float) > workspace_bytes) --S;
   VLNCE_CHECK_ARG((size_t)N * S * groups * 2 * sizeof(float) <= workspace_bytes, "groupnorm_fused: workspace too small");
-  launch_pdl(gn_partial_kernel, dim3(N, S), dim3(256), 0, stream, x, workspace, HW, C, groups);
+  launch_pdl(gn_partial_kernel<float>, dim3(N, S), dim3(256), 0, stream, x, workspace, HW, C, groups);
   VLNCE_LAUNCH_CHECK("gn_partial_kernel");
   int slices = cdiv((long long)HW * C, 8192);
   if (slices > 64) slices = 64;
   const size_t smem = sizeof(float) * 2 * C;
   dim3 grid(N, slices);
   if (y_dtype == VLNCE_F16)
-    launch_pdl(gn_apply_kernel<__half>, grid, dim3(256), smem, stream, x, (const float*)workspace, S, gamma, beta, groups,
+    launch_pdl(gn_apply_kernel<float, __half>, grid, dim3(256), smem, stream, x, (const float*)workspace, S, gamma, beta, groups,
                eps, (const __half*)residual, (__half*)y, HW, C, relu);
   else if (y_dtype == VLNCE_BF16)
-    launch_pdl(gn_apply_kernel<__nv_bfloat16>, grid, dim3(256), smem, stream, x, (const float*)workspace, S, gamma, beta,
+    launch_pdl(gn_apply_kernel<float, __nv_bfloat16>, grid, dim3(256), smem, stream, x, (const float*)workspace, S, gamma, beta,
                groups, eps, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, HW, C, relu);
   else
-    launch_pdl(gn_apply_kernel<float>, grid, dim3(256), smem, stream, x, (const float*)workspace, S, gamma, beta, groups,
+    launch_pdl(gn_apply_kernel<float, float>, grid, dim3(256), smem, stream, x, (const float*)workspace, S, gamma, beta, groups,
                eps, (const float*)residual, (float*)y, HW, C, relu);
+  VLNCE_LAUNCH_CHECK("gn_apply_kernel");
+  return VLNCE_OK;
+}
+
+
+// Same two-launch GroupNorm for an fp16 raw conv output (x and y fp16): halves the bytes the statistics and the
+// apply pass stream compared with the fp32 raw tensor (the depth trunk is bound by that traffic).  The statistics
+// are those of the fp16-rounded values (fp32 bins, fp64 combine).  Layout preconditions as the fast path above.
+extern "C" int vlnce_groupnorm_fused16(const void* x, const float* gamma, const float* beta, const void* residual,
+                                       void* y, float* workspace, size_t workspace_bytes, int N, int HW, int C,
+                                       int groups, float eps, int relu, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && gamma && beta && y && workspace && groups > 0 && C % groups == 0 && C % 8 == 0,
+                  "groupnorm_fused16: bad arguments");
+  const int c4n = C / 4;
+  VLNCE_CHECK_ARG(c4n <= 256 && 256 % c4n == 0 && (C / groups) % 2 == 0 && groups <= 64,
+                  "groupnorm_fused16: layout not supported (C=%d groups=%d)", C, groups);
+  int S = cdiv((long long)HW * C, 4096);
+  if (S > HW) S = HW;
+  if (S > 8) S = 8;
+  while (S > 1 && (size_t)N * S * groups * 2 * sizeof(float) > workspace_bytes) --S;
+  VLNCE_CHECK_ARG((size_t)N * S * groups * 2 * sizeof(float) <= workspace_bytes, "groupnorm_fused16: workspace too small");
+  launch_pdl(gn_partial_kernel<__half>, dim3(N, S), dim3(256), 0, stream, (const __half*)x, workspace, HW, C, groups);
+  VLNCE_LAUNCH_CHECK("gn_partial_kernel");
+  int slices = cdiv((long long)HW * C, 8192);
+  if (slices > 64) slices = 64;
+  const size_t smem = sizeof(float) * 2 * C;
+  launch_pdl(gn_apply_kernel<__half, __half>, dim3(N, slices), dim3(256), smem, stream, (const __half*)x,
+             (const float*)workspace, S, gamma, beta, groups, eps, (const __half*)residual, (__half*)y, HW, C, relu);
   VLNCE_LAUNCH_CHECK("gn_apply_kernel");
   return VLNCE_OK;
 }

@@ -59,6 +59,9 @@ HALO = 1 << 24  # tuning-code flag: TMA-halo 3x3 kernel instead of the generic t
 TMAP = 1 << 25  # tuning-code flag: persistent TMA-fed kernel (1x1 rows / 3x3 halo, overlapped epilogue)
 EXCL = 1 << 20  # launch flag understood by the conv entry points: one CTA per SM
 RGB_EXCLUSIVE = _os.environ.get("VLNCE_RGB_EXCLUSIVE", "0") != "0"
+# fp16 instead of fp32 raw conv output under GroupNorm (depth trunk): half the bytes of the statistics/apply passes
+GN_RAW16 = _os.environ.get("VLNCE_GN_RAW16", "0") != "0"
+DEPTH_CHUNKS = int(_os.environ.get("VLNCE_DEPTH_CHUNKS", "1"))  # independent batch chunks of the depth trunk
 # Tuned (tile width | ring depth << 16) per conv geometry, optionally persisted so that later
 # processes on the same box (profilers, the second bench leg) skip the timing sweep.
 _TUNE_CACHE_PATH = _os.environ.get("VLNCE_AUTOTUNE_CACHE", "")
@@ -160,13 +163,15 @@ class ConvTrunk:
         self._slot = 0
 
     # -------------------------------------------------------------- low-level steps
+    _pfx = ""  # buffer-name prefix of the batch chunk being sequenced (chunks run concurrently: own buffers)
+
     def _act(self, tag: str, shape):
-        return self.pool.get(tag, shape, self.adt)
+        return self.pool.get(self._pfx + tag, shape, self.adt)
 
     def _raw(self, tag, shape):
         """fp32 raw conv output feeding GroupNorm / train-mode BatchNorm statistics (one bf16
         rounding per layer instead of two)."""
-        return self.pool.get(tag, shape, torch.float32)
+        return self.pool.get(self._pfx + tag, shape, torch.float32)
 
     def _conv(self, x, shape_in, cv: _Conv, y, *, scale, shift, residual=None, relu=False,
               gemm_c: Optional[int] = None, stem_rgb: bool = False, stem_s2d: bool = False):
@@ -419,15 +424,21 @@ class DepthTrunk(ConvTrunk):
     def _gn_conv(self, x, shape_in, cv: _Conv, tag, *, residual=None, relu=True, gemm_c=None, out_hw=None):
         n, h, w, _ = shape_in
         p, q = out_hw if out_hw is not None else self._out_hw(h, w, cv)
-        raw = self._raw("gn_raw", (n, p, q, cv.K))
-        self._conv(x, shape_in, cv, raw, scale=None, shift=None, gemm_c=gemm_c)
         gn: nn.GroupNorm = cv.norm
+        c4n = cv.K // 4
+        raw16 = (GN_RAW16 and self.adt == torch.float16 and c4n <= 256 and 256 % c4n == 0
+                 and (cv.K // gn.num_groups) % 2 == 0 and gn.num_groups <= 64)
+        raw = self._act("gn_raw16", (n, p, q, cv.K)) if raw16 else self._raw("gn_raw", (n, p, q, cv.K))
+        self._conv(x, shape_in, cv, raw, scale=None, shift=None, gemm_c=gemm_c)
         st = lib.stream()
-        sc = self.pool.get("gn_scale", (n, cv.K), torch.float32)
-        sh = self.pool.get("gn_shift", (n, cv.K), torch.float32)
-        ws = self.pool.get("gn_ws", (1 << 20,), torch.float32)
+        sc = self.pool.get(self._pfx + "gn_scale", (n, cv.K), torch.float32)
+        sh = self.pool.get(self._pfx + "gn_shift", (n, cv.K), torch.float32)
+        ws = self.pool.get(self._pfx + "gn_ws", (1 << 20,), torch.float32)
         y = self._act(tag, (n, p, q, cv.K))
-        if raw.dtype == torch.float32:
+        if raw16:
+            C.vlnce_groupnorm_fused16(ptr(raw), ptr(gn.weight), ptr(gn.bias), ptr(residual), ptr(y), ptr(ws),
+                                      ws.numel() * 4, n, p * q, cv.K, gn.num_groups, float(gn.eps), int(relu), st)
+        elif raw.dtype == torch.float32:
             C.vlnce_groupnorm_fused(ptr(raw), ptr(gn.weight), ptr(gn.bias), ptr(residual), ptr(y), lib.code(y), ptr(ws),
                                     ws.numel() * 4, ptr(sc), ptr(sh), n, p * q, cv.K, gn.num_groups, float(gn.eps),
                                     int(relu), st)
@@ -439,15 +450,41 @@ class DepthTrunk(ConvTrunk):
         return y, (n, p, q, cv.K)
 
     def forward(self, depth: torch.Tensor, out: torch.Tensor, ld_out: int, out_hw: int = 4):
-        """depth (R,H,W,1) f32 -> out[(R,16,ld_out) f32][:, :, :128]."""
+        """depth (R,H,W,1) f32 -> out[(R,16,ld_out) f32][:, :, :128].
+
+        GroupNorm normalises per sample, so the batch can be cut into independent chunks with bit-identical
+        results: with ``DEPTH_CHUNKS`` > 1 every chunk runs the whole trunk on its own stream (parallel branches
+        of a captured graph).  The trunk is a chain of ~160 short kernels of 16-128 CTAs each; several chains side
+        by side fill the SMs that one chain leaves idle."""
         for cv in self._all():
             cv.pack()
+        n = depth.shape[0]
+        k = DEPTH_CHUNKS if (self.precision == "bf16" and depth.is_cuda and n >= 8 * DEPTH_CHUNKS) else 1
+        if k <= 1:
+            return self._forward_chunk(depth, out, ld_out, out_hw, "")
+        from .engine import Branch
+
+        per = (n + k - 1) // k
+        branches, shp = [], None
+        for i in range(k):
+            lo, hi = i * per, min(n, (i + 1) * per)
+            if lo >= hi:
+                break
+            with Branch(f"depth_chunk{i}") as br:
+                shp = self._forward_chunk(depth[lo:hi], out[lo:hi], ld_out, out_hw, f"c{i}_")
+            branches.append(br)
+        for br in branches:
+            br.join()
+        return (n,) + tuple(shp[1:])
+
+    def _forward_chunk(self, depth: torch.Tensor, out: torch.Tensor, ld_out: int, out_hw: int, pfx: str):
+        self._pfx = pfx
         n, h, w, _ = depth.shape
         st = lib.stream()
         hp, wp = h // 2, w // 2
         p, q = (hp + 6 - 7) // 2 + 1, (wp + 6 - 7) // 2 + 1
         if self.precision == "bf16":
-            a = self.pool.get("stem_a", (n * p * q, 64), self.adt)
+            a = self.pool.get(self._pfx + "stem_a", (n * p * q, 64), self.adt)
             C.vlnce_im2col_depth_stem(ptr(depth), ptr(a), lib.code(a), n, h, w, st)
             x, shp = self._gn_conv(a, (n, p, q, 64), self.stem, "stem_y", gemm_c=64, out_hw=(p, q))
         else:
