@@ -332,15 +332,19 @@ int vlnce_wp_head_act_bwd(const float* raw, const float* g_d1, const float* g_d2
 /* WaypointPolicy.act post-processing (waypoint_policy.py:129-247; TruncatedNormal utils.py:24-152).
  * logp (B,P+1) log-probs; o1,o2,d1,d2 (B,P).  pano_stop (B) i64; fout (B,10) = offset, distance,
  * action_log_prob, var_distance, var_offset, mode_offset, mode_distance, r, theta, stop.
- * act_consts_host: HOST pointer to 5 floats {d_lo, d_hi, offset_limit, predict_distance, predict_offset}. */
+ * act_consts_host: HOST pointer to 11 floats {d_lo, d_hi, offset_limit, predict_distance, predict_offset,
+ * #distance classes, #offset classes (0 = continuous TruncatedNormal head), dist_a, dist_b, off_a, off_b
+ * (to_continuous = a + b * value)}.  A discrete head passes its logits (B,P,classes) as d1 / o1 and NULL for
+ * d2 / o2; fout then carries class indices and NaN variances (torch Categorical.variance). */
 int vlnce_wp_act(const float* logp, const float* o1, const float* o2, const float* d1, const float* d2,
                  long long* pano_stop, float* fout, int B, int P, int deterministic, unsigned long long seed,
                  unsigned long long offset, const float* act_consts_host, cudaStream_t stream);
 /* evaluate_actions (waypoint_policy.py:265-333) fused with the WDDPPO mini-batch loss and its gradients
  * (common/ddppo_alg.py:56-124).  eval_out (R,4) = action_log_prob, entropy pano/offset/distance; losses[8] =
  * loss, value_loss, action_loss, entropy_loss, offset_loss, mean entropies (pano, offset, distance).
- * losses and the gradient outputs may be NULL.  ppo_consts_host: HOST pointer to 10 floats {clip, value_coef,
- * entropy_coef, offset_regularize_coef, pano/offset/distance entropy coefs, clipped_value_loss, off_a, off_b}. */
+ * losses and the gradient outputs may be NULL.  ppo_consts_host: HOST pointer to 8 floats {clip, value_coef,
+ * entropy_coef, offset_regularize_coef, pano/offset/distance entropy coefs, clipped_value_loss}.  Gradient blocks
+ * of a discrete head are (R,P,classes) in d_d1 / d_o1 (d_d2 / d_o2 unused). */
 int vlnce_wp_ppo_loss(const float* logp, const float* o1, const float* o2, const float* d1, const float* d2,
                       const float* values, const float* a_pano, const float* a_offset, const float* a_distance,
                       const float* v_old, const float* ret, const float* lp_old, const float* adv, int R, int P,

@@ -56,6 +56,16 @@ CASES = {
                        waypoint=dict(predict_distance=False)),
     "wp_eval_hpn": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=25, iseed=205,
                         waypoint=dict(predict_distance=False, predict_offset=False)),
+    # discrete heads: 2-wpn-dc.yaml (discrete distance, continuous offset), 3-wpn-dd.yaml (both discrete),
+    # 4-wpn-d_.yaml (discrete distance, offset not predicted)
+    "wp_act_dc": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=24, wseed=46, iseed=206,
+                      waypoint=dict(continuous_distance=False)),
+    "wp_act_dd": dict(policy="WaypointPolicy", kind="wp_act", n=3, length=24, wseed=55, iseed=207,
+                      waypoint=dict(continuous_distance=False, continuous_offset=False)),
+    "wp_eval_dd": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=28, iseed=208,
+                       waypoint=dict(continuous_distance=False, continuous_offset=False)),
+    "wp_eval_d_": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=29, iseed=209,
+                       waypoint=dict(continuous_distance=False, predict_offset=False)),
 }
 
 WP_OBS_SPACE = dict(rgb=(12, 224, 224, 3), depth=(12, 256, 256, 1))
@@ -124,11 +134,15 @@ def layers_of(case):
 
 
 def inputs(case):
-    if case["kind"] == "wp_act":
-        return synth.make_waypoint_act_batch(case["iseed"], case["n"], length=case["length"],
-                                             rgb_u8=case.get("rgb_u8", False))
-    if case["kind"] == "wp_eval":
-        return synth.make_waypoint_eval_batch(case["iseed"], case["t"], case["n"], length=case["length"])
+    if case["kind"] in ("wp_act", "wp_eval"):
+        wp = case.get("waypoint", {})
+        classes = dict(distance=0 if wp.get("continuous_distance", True) else 6,
+                       offset=0 if wp.get("continuous_offset", True) else 7)
+        if case["kind"] == "wp_act":
+            return synth.make_waypoint_act_batch(case["iseed"], case["n"], length=case["length"],
+                                                 rgb_u8=case.get("rgb_u8", False), classes=classes)
+        return synth.make_waypoint_eval_batch(case["iseed"], case["t"], case["n"], length=case["length"],
+                                              classes=classes)
     if case["kind"] == "act":
         return synth.make_act_batch(case["iseed"], case["n"], hw=case["hw"],
                                     rgb_hw=case.get("rgb_hw"), length=case["length"],
@@ -233,8 +247,8 @@ def _run_waypoint(impl, pol, case, device):
             out["action/" + k] = v.cpu().clone()
         for k, v in modes.items():
             out["mode/" + k] = v.cpu().clone()
-        for k, v in variances.items():
-            out["variance/" + k] = v.cpu().clone()
+        for k, v in variances.items():  # torch's Categorical.variance (discrete heads) is NaN
+            out["variance/" + k] = torch.nan_to_num(v.float().cpu().clone(), nan=-777.0)
         out["stop"] = torch.tensor([a["action"] == "STOP" for a in actions])
         out["r_theta"] = torch.tensor([[a["action"]["action_args"]["r"], a["action"]["action_args"]["theta"]]
                                        if a["action"] != "STOP" else [0.0, 0.0] for a in actions])

@@ -384,6 +384,71 @@ def _host_floats(ptr, n):
     return [float(v) for v in _flat(ptr, n)]
 
 
+def _act_consts(ptr):
+    v = _host_floats(ptr, 11)
+    return dict(d_lo=v[0], d_hi=v[1], o_lim=v[2], pd=v[3] != 0, po=v[4] != 0, nd=int(v[5]), no=int(v[6]), dist_a=v[7],
+                dist_b=v[8], off_a=v[9], off_b=v[10])
+
+
+class _Comp:
+    """One action component at the selected pano of each row: TruncatedNormal(v1[idx], sqrt(v2[idx])) or a
+    Categorical over the ``ncls`` logits v1[idx, :] (mirrors ``Comp`` in csrc/waypoint.cu)."""
+
+    def __init__(self, ncls, v1, v2, R, P, rows, idx, lo, hi):
+        self.ncls, self.R, self.P, self.rows, self.idx, self.lo, self.hi = ncls, R, P, rows, idx, lo, hi
+        if ncls:
+            lg = _flat(v1, R * P * ncls).reshape(R, P, ncls).astype(np.float64)[rows, idx]
+            self.l = lg - (lg.max(1, keepdims=True) + np.log(np.exp(lg - lg.max(1, keepdims=True)).sum(1, keepdims=True)))
+        else:
+            self.mu = _mat(v1, R, P, P).astype(np.float64)[rows, idx]
+            self.sg = np.sqrt(_mat(v2, R, P, P).astype(np.float64)[rows, idx])
+            self.t = _tn_stats(self.mu, self.sg, lo, hi)
+
+    def _k(self, y):
+        return np.clip(np.asarray(y).astype(np.int64), 0, self.ncls - 1)
+
+    def log_prob(self, y):
+        if self.ncls:
+            return self.l[np.arange(len(self.l)), self._k(y)]
+        return _tn_logp(y, self.mu, self.sg, self.t["Z"])
+
+    def ent(self):
+        return -(np.exp(self.l) * self.l).sum(1) if self.ncls else self.t["ent"]
+
+    def var(self):
+        return np.full(len(self.l), np.nan) if self.ncls else self.t["var"]
+
+    def mode(self):
+        return np.exp(self.l).argmax(1).astype(np.float64) if self.ncls else self.mu
+
+    def sample(self, rng):
+        if self.ncls:
+            return float(min(np.searchsorted(np.cumsum(np.exp(self.l[0])), rng.random(), side="right"), self.ncls - 1))
+        while True:
+            s = rng.normal(self.mu[0], self.sg[0])
+            if self.lo <= s <= self.hi:
+                return s
+
+    def grads(self, y, mask, mask_h, g_lp, g_h, o1, o2):
+        R, P, w = self.R, self.P, max(self.ncls, 1)
+        g1 = _flat(o1, R * P * w).reshape(R, P, w)
+        g1[...] = 0
+        if self.ncls:
+            p = np.exp(self.l)
+            onehot = np.zeros_like(p)
+            onehot[np.arange(R), self._k(y)] = 1
+            H = self.ent()
+            mh = np.broadcast_to(np.asarray(mask_h, dtype=np.float64), (R,))
+            g1[self.rows, self.idx] = (mask[:, None] * np.asarray(g_lp)[:, None] * (onehot - p)
+                                       + mh[:, None] * np.asarray(g_h).reshape(-1, 1) * (-p * (self.l + H[:, None])))
+            return
+        g2 = _mat(o2, R, P, P)
+        g2[...] = 0
+        dlm, dlv, dhm, dhv = _tn_grads(self.t, y, self.mu, self.sg)
+        g1[self.rows, self.idx, 0] = mask * g_lp * dlm + mask_h * g_h * dhm
+        g2[self.rows, self.idx] = mask * g_lp * dlv + mask_h * g_h * dhv
+
+
 class WaypointOps:
     def wp_stack_frames(self, cur, hist, masks, out, B, P, frame_bytes, st):
         o = _flat(out, B * (P + 1) * frame_bytes, np.uint8)
@@ -489,7 +554,7 @@ class WaypointOps:
             _flat(g_o1, n) * c[4] * (1 - t * t) * c[5], _flat(g_o2, n) * c[6] * s3 * (1 - s3)], 1)
 
     def wp_act(self, logp, o1, o2, d1, d2, pano_stop, fout, B, P, deterministic, seed, offset, consts, st):
-        d_lo, d_hi, o_lim, pd, po = _host_floats(consts, 5)
+        c = _act_consts(consts)
         lp = _mat(logp, B, P + 1, P + 1).astype(np.float64)
         rng = np.random.default_rng(seed + offset)
         f = _mat(fout, B, 10, 10)
@@ -499,53 +564,47 @@ class WaypointOps:
             else:
                 ps = int(min(np.searchsorted(np.cumsum(np.exp(lp[b])), rng.random(), side="right"), P))
             pano, go = ps % P, float(ps != P)
-            mu_d, sg_d = float(_mat(d1, B, P, P)[b, pano]), math.sqrt(float(_mat(d2, B, P, P)[b, pano]))
-            mu_o, sg_o = float(_mat(o1, B, P, P)[b, pano]), math.sqrt(float(_mat(o2, B, P, P)[b, pano]))
-            td, to = _tn_stats(mu_d, sg_d, d_lo, d_hi), _tn_stats(mu_o, sg_o, -o_lim, o_lim)
-
-            def draw(mu, sg, lo, hi):
-                while True:
-                    s = rng.normal(mu, sg)
-                    if lo <= s <= hi:
-                        return s
-
-            dist = mu_d if deterministic else draw(mu_d, sg_d, d_lo, d_hi)
-            ofs = mu_o if deterministic else draw(mu_o, sg_o, -o_lim, o_lim)
-            lp_d, lp_o = _tn_logp(dist, mu_d, sg_d, td["Z"]), _tn_logp(ofs, mu_o, sg_o, to["Z"])
-            a_d, a_o, var_d, var_o = dist, ofs, td["var"], to["var"]
-            if not po:
+            idx = np.array([pano])
+            cd = _Comp(c["nd"], d1, d2, B, P, np.array([b]), idx, c["d_lo"], c["d_hi"])
+            co = _Comp(c["no"], o1, o2, B, P, np.array([b]), idx, -c["o_lim"], c["o_lim"])
+            dist = cd.mode()[0] if deterministic else cd.sample(rng)
+            ofs = co.mode()[0] if deterministic else co.sample(rng)
+            lp_d, lp_o = cd.log_prob(np.array([dist]))[0], co.log_prob(np.array([ofs]))[0]
+            a_d, a_o = c["dist_a"] + c["dist_b"] * dist, c["off_a"] + c["off_b"] * ofs
+            var_d, var_o = cd.var()[0], co.var()[0]
+            if not c["po"]:
                 a_o = ofs = var_o = 0.0
-            if not pd:
-                a_d = dist = 0.25
-                var_d = 0.0
+            if not c["pd"]:
+                a_d, dist, var_d = 0.25, (0.0 if c["nd"] else 0.25), 0.0
             theta = (pano * (2 * math.pi / P) + a_o) % (2 * math.pi)
-            alp = lp[b, ps] + (go * lp_d if pd else 0.0) + (go * lp_o if po else 0.0)
+            alp = lp[b, ps] + (go * lp_d if c["pd"] else 0.0) + (go * lp_o if c["po"] else 0.0)
             _flat(pano_stop, B, I64)[b] = ps
-            f[b] = [ofs, dist, alp, var_d, var_o, mu_o, mu_d, a_d if go else 0.0, theta if go else 0.0, 1.0 - go]
+            f[b] = [ofs, dist, alp, var_d, var_o, co.mode()[0], cd.mode()[0], a_d if go else 0.0, theta if go else 0.0,
+                    1.0 - go]
 
     def wp_ppo_loss(self, logp, o1, o2, d1, d2, values, a_pano, a_offset, a_distance, v_old, ret, lp_old, adv, R, P,
                     act_consts, ppo_consts, eval_out, losses, d_raw, d_o1, d_o2, d_d1, d_d2, d_values, st):
-        d_lo, d_hi, o_lim, pd, po = _host_floats(act_consts, 5)
+        c = _act_consts(act_consts)
         lp = _mat(logp, R, P + 1, P + 1).astype(np.float64)
         a = _flat(a_pano, R).astype(np.int64)
         idx, go = a % P, (a != P).astype(np.float64)
-        dm, om = go * float(pd != 0), go * float(po != 0)
+        dm, om = go * float(c["pd"]), go * float(c["po"])
         rows = np.arange(R)
         p = np.exp(lp)
         Hp = -(p * lp).sum(1)
-        g64 = lambda x: _mat(x, R, P, P).astype(np.float64)[rows, idx]  # noqa: E731
-        mu_d, v_d, mu_o, v_o = g64(d1), g64(d2), g64(o1), g64(o2)
-        sg_d, sg_o = np.sqrt(v_d), np.sqrt(v_o)
-        td, to = _tn_stats(mu_d, sg_d, d_lo, d_hi), _tn_stats(mu_o, sg_o, -o_lim, o_lim)
+        cd = _Comp(c["nd"], d1, d2, R, P, rows, idx, c["d_lo"], c["d_hi"])
+        co = _Comp(c["no"], o1, o2, R, P, rows, idx, -c["o_lim"], c["o_lim"])
         y_d, y_o = _flat(a_distance, R).astype(np.float64), _flat(a_offset, R).astype(np.float64)
-        alp = lp[rows, a] + dm * _tn_logp(y_d, mu_d, sg_d, td["Z"]) + om * _tn_logp(y_o, mu_o, sg_o, to["Z"])
-        Ho, Hd = om * to["ent"], dm * td["ent"]
+        alp = lp[rows, a] + dm * cd.log_prob(y_d) + om * co.log_prob(y_o)
+        # W4: a categorical head's entropy is weighted by mean(mask) (the reference's (R,1)*(R,) broadcast)
+        dmh = go.mean() * float(c["pd"]) if c["nd"] else dm
+        omh = go.mean() * float(c["po"]) if c["no"] else om
+        Ho, Hd = omh * co.ent(), dmh * cd.ent()
         if eval_out:
-            _mat(eval_out, R, 4, 4)[...] = np.stack([alp, Hp, Ho, Hd], 1)
+            _mat(eval_out, R, 4, 4)[...] = np.stack([alp, Hp, co.ent() if c["no"] else Ho, cd.ent() if c["nd"] else Hd], 1)
         if not losses:
             return
-        c = _host_floats(ppo_consts, 10)
-        clip, vcoef, ecoef, oreg, cp, co, cd, clipped, off_a, off_b = c
+        clip, vcoef, ecoef, oreg, cp, cof, cdi, clipped = _host_floats(ppo_consts, 8)
         ratio = np.exp(alp - _flat(lp_old, R))
         A = _flat(adv, R).astype(np.float64)
         s1, s2 = ratio * A, np.clip(ratio, 1 - clip, 1 + clip) * A
@@ -555,8 +614,8 @@ class WaypointOps:
         l1, l2 = (v - rt) ** 2, (vc - rt) ** 2
         value_loss = (0.5 * np.maximum(l1, l2) if clipped else 0.5 * l1).mean() * vcoef
         action_loss = -np.minimum(s1, s2).mean()
-        entropy_loss = (cp * Hp + co * Ho + cd * Hd).mean() * ecoef
-        offset_loss = oreg * np.abs(off_a + off_b * y_o).mean()
+        entropy_loss = (cp * Hp + cof * Ho + cdi * Hd).mean() * ecoef
+        offset_loss = oreg * np.abs(c["off_a"] + c["off_b"] * y_o).mean()
         _flat(losses, 8)[...] = [value_loss + action_loss + offset_loss - entropy_loss, value_loss, action_loss,
                                  entropy_loss, offset_loss, Hp.mean(), Ho.mean(), Hd.mean()]
         if not d_raw:
@@ -567,13 +626,8 @@ class WaypointOps:
         onehot = np.zeros((R, P + 1))
         onehot[rows, a] = 1
         _mat(d_raw, R, P + 1, P + 1)[...] = g_lp[:, None] * (onehot - p) + g_ent * cp * (-p * (lp + Hp[:, None]))
-        for t, y, mu, sg, m, ce, o_mu, o_v in ((td, y_d, mu_d, sg_d, dm, cd, d_d1, d_d2), (to, y_o, mu_o, sg_o, om, co, d_o1, d_o2)):
-            dlm, dlv, dhm, dhv = _tn_grads(t, y, mu, sg)
-            gm, gv = _mat(o_mu, R, P, P), _mat(o_v, R, P, P)
-            gm[...] = 0
-            gv[...] = 0
-            gm[rows, idx] = m * (g_lp * dlm + g_ent * ce * dhm)
-            gv[rows, idx] = m * (g_lp * dlv + g_ent * ce * dhv)
+        cd.grads(y_d, dm, dmh, g_lp, g_ent * cdi, d_d1, d_d2)
+        co.grads(y_o, om, omh, g_lp, g_ent * cof, d_o1, d_o2)
         dv = np.where((l1 >= l2) | (not clipped), v - rt, np.where(np.abs(diff) < clip, vc - rt, 0.0))
         _flat(d_values, R)[...] = vcoef * dv / R
 
@@ -612,11 +666,11 @@ for _name in [n for n in vars(WaypointOps) if not n.startswith("_")]:
 
 def _wp_eval_bwd(self, logp, o1, o2, d1, d2, a_pano, a_offset, a_distance, upstream, R, P, act_consts, d_raw, d_o1,
                  d_o2, d_d1, d_d2, st):
-    d_lo, d_hi, o_lim, pd, po = _host_floats(act_consts, 5)
+    c = _act_consts(act_consts)
     lp = _mat(logp, R, P + 1, P + 1).astype(np.float64)
     a = _flat(a_pano, R).astype(np.int64)
     idx, go = a % P, (a != P).astype(np.float64)
-    dm, om = go * float(pd != 0), go * float(po != 0)
+    dm, om = go * float(c["pd"]), go * float(c["po"])
     rows = np.arange(R)
     p = np.exp(lp)
     Hp = -(p * lp).sum(1)
@@ -624,18 +678,10 @@ def _wp_eval_bwd(self, logp, o1, o2, d1, d2, a_pano, a_offset, a_distance, upstr
     onehot = np.zeros((R, P + 1))
     onehot[rows, a] = 1
     _mat(d_raw, R, P + 1, P + 1)[...] = up[:, 0:1] * (onehot - p) + up[:, 1:2] * (-p * (lp + Hp[:, None]))
-    g64 = lambda x: _mat(x, R, P, P).astype(np.float64)[rows, idx]  # noqa: E731
-    for (mu, v, lo, hi, y, m, g_h, o_mu, o_v) in (
-            (g64(d1), g64(d2), d_lo, d_hi, _flat(a_distance, R).astype(np.float64), dm, up[:, 3], d_d1, d_d2),
-            (g64(o1), g64(o2), -o_lim, o_lim, _flat(a_offset, R).astype(np.float64), om, up[:, 2], d_o1, d_o2)):
-        sg = np.sqrt(v)
-        t = _tn_stats(mu, sg, lo, hi)
-        dlm, dlv, dhm, dhv = _tn_grads(t, y, mu, sg)
-        gm, gv = _mat(o_mu, R, P, P), _mat(o_v, R, P, P)
-        gm[...] = 0
-        gv[...] = 0
-        gm[rows, idx] = m * (up[:, 0] * dlm + g_h * dhm)
-        gv[rows, idx] = m * (up[:, 0] * dlv + g_h * dhv)
+    cd = _Comp(c["nd"], d1, d2, R, P, rows, idx, c["d_lo"], c["d_hi"])
+    co = _Comp(c["no"], o1, o2, R, P, rows, idx, -c["o_lim"], c["o_lim"])
+    cd.grads(_flat(a_distance, R).astype(np.float64), dm, 1.0 if c["nd"] else dm, up[:, 0], up[:, 3], d_d1, d_d2)
+    co.grads(_flat(a_offset, R).astype(np.float64), om, 1.0 if c["no"] else om, up[:, 0], up[:, 2], d_o1, d_o2)
 
 
 Emulator.wp_eval_bwd = _wp_eval_bwd

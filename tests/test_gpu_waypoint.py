@@ -59,8 +59,9 @@ def host(vals):
 
 
 HEAD, HEAD_P = host([3.75, 0.25, 3.506, 0.01, math.pi / 12, 0.25, 0.0682, 0.0003])
-ACT, ACT_P = host([0.25, 4.0, math.pi / 12, 1.0, 1.0])
-PPO, PPO_P = host([0.2, 0.5, 0.01, 0.1146, 1.0, 1.0, 1.0, 1.0, 0.0, 1.0])
+ACT, ACT_P = host([0.25, 4.0, math.pi / 12, 1.0, 1.0, 0, 0, 0.0, 1.0, 0.0, 1.0])
+ACT_DD, ACT_DD_P = host([0.25, 4.0, math.pi / 12, 1.0, 1.0, 6, 7, 0.25, 0.75, -math.pi / 12, math.pi / 36])
+PPO, PPO_P = host([0.2, 0.5, 0.01, 0.1146, 1.0, 1.0, 1.0, 1.0])
 
 
 @pytest.mark.parametrize("dtype,fb", [(torch.uint8, 224 * 224 * 3), (torch.float32, 64 * 64 * 4), (torch.uint8, 37)])
@@ -199,6 +200,30 @@ def test_ppo_loss_and_eval_bwd():
          tol=1e-3)
 
 
+def test_discrete_heads_act_loss_and_bwd():
+    """categorical distance (6) / offset (7) heads: act, fused loss + gradients, eval backward"""
+    R, P, nd, no = 29, 12, 6, 7
+    logp = torch.log_softmax(rnd(R, P + 1, seed=60), 1)
+    dlog, olog = rnd(R * P, nd, seed=61), rnd(R * P, no, seed=62)
+    g = torch.Generator().manual_seed(63)
+    a_pano = torch.randint(0, P + 1, (R,), generator=g).float()
+    a_pano[0] = P
+    a_off, a_dist = torch.randint(0, no, (R,), generator=g).float(), torch.randint(0, nd, (R,), generator=g).float()
+    ps, f = torch.zeros(R, dtype=torch.int64), torch.zeros(R, 10)
+    (gpu, cpu) = both("wp_act", [logp, olog, 0, dlog, 0, ps, f, R, P, 1, 5, 0, ACT_DD_P], [5])
+    fg, fc = torch.nan_to_num(gpu[6].cpu(), nan=-7.0), torch.nan_to_num(cpu[6], nan=-7.0)
+    torch.testing.assert_close(fg, fc, rtol=2e-5, atol=2e-6)
+    values, v_old, ret = rnd(R, seed=64), rnd(R, seed=65), rnd(R, seed=66)
+    lp_old, adv = -4.0 + rnd(R, seed=67) * 0.4, rnd(R, seed=68)
+    ev, losses, d_raw, d_v = torch.zeros(R, 4), torch.zeros(8), torch.zeros(R, P + 1), torch.zeros(R)
+    g_o1, g_d1 = torch.zeros(R * P, no), torch.zeros(R * P, nd)
+    both("wp_ppo_loss", [logp, olog, 0, dlog, 0, values, a_pano, a_off, a_dist, v_old, ret, lp_old, adv, R, P, ACT_DD_P,
+                         PPO_P, ev, losses, d_raw, g_o1, 0, g_d1, 0, d_v], [17, 18, 19, 20, 22, 24], tol=2e-4)
+    up = rnd(R, 4, seed=69)
+    both("wp_eval_bwd", [logp, olog, 0, dlog, 0, a_pano, a_off, a_dist, up, R, P, ACT_DD_P, torch.zeros(R, P + 1),
+                         torch.zeros(R * P, no), 0, torch.zeros(R * P, nd), 0], [12, 13, 15], tol=2e-4)
+
+
 def test_clip_grad_norm_and_gae():
     g = rnd(100003, seed=50)
     ws = torch.zeros(1026)
@@ -247,7 +272,7 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max()) / (float(b.abs().max()) + 1e-12)
 
 
-@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_act_hpn"])
+@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_act_hpn", "wp_act_dc", "wp_act_dd"])
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
 def test_waypoint_act_matches_golden(name, precision, tol):
     want = gold(name)
@@ -272,7 +297,8 @@ def test_waypoint_act_matches_golden(name, precision, tol):
 
 
 @pytest.mark.parametrize("name,precision,tol", [("wp_eval", "fp32", 1e-3), ("wp_eval", "bf16", 2e-2),
-                                                ("wp_eval_hpn", "fp32", 1e-3)])
+                                                ("wp_eval_hpn", "fp32", 1e-3), ("wp_eval_dd", "fp32", 1e-3),
+                                                ("wp_eval_d_", "fp32", 1e-3)])
 def test_waypoint_ppo_minibatch_matches_golden(name, precision, tol):
     """evaluate_actions -> the reference's WDDPPO loss arithmetic in torch -> loss.backward() through the
     one-node autograd bridge (hand-written CUDA backward)."""

@@ -94,7 +94,8 @@ class _Impl:
         return Wrapped
 
 
-@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_eval", "wp_act_hpn", "wp_eval_hpn"])
+@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_eval", "wp_act_hpn", "wp_eval_hpn", "wp_act_dc", "wp_act_dd",
+                                  "wp_eval_dd", "wp_eval_d_"])
 def test_waypoint_plan_matches_golden(name):
     case = cases.CASES[name]
     with lib.dry_run(executor=Emulator()):
@@ -105,7 +106,7 @@ def test_waypoint_plan_matches_golden(name):
     print(name, "worst", worst)
 
 
-def _fill_rollouts(st, T, N, length=12):
+def _fill_rollouts(st, T, N, length=12, classes=None):
     from vlnce_b200 import synth
 
     g = torch.Generator().manual_seed(9)
@@ -113,30 +114,34 @@ def _fill_rollouts(st, T, N, length=12):
     for k in st.observations:
         st.observations[k][0].copy_(first[k])
     for t in range(T):
-        a = synth.make_waypoint_actions(g, N)
+        a = synth.make_waypoint_actions(g, N, classes=classes)
         st.insert(synth.make_waypoint_rows(g, N, length=length), torch.randn(N, 2, 256, generator=g) * 0.3, a,
                   -2 + 0.2 * torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g) * 0.3,
                   torch.randn(N, 1, generator=g), torch.ones(N, 1, dtype=torch.uint8))
     return torch.randn(N, 1, generator=g) * 0.3
 
 
-def test_fused_wddppo_update_matches_oracle_loop():
+@pytest.mark.parametrize("name", ["wp_eval", "wp_eval_dd"])
+def test_fused_wddppo_update_matches_oracle_loop(name):
     """``WDDPPOStep.update`` (fused loss+gradient kernel, hand-written backward, clip, Adam; device-style rollout
     storage with the GAE kernel) against the restated ``WDDPPO.update`` loop (itself pinned to the reference's
     class in tests/test_waypoint_oracle.py): same six scalars, same updated parameters."""
     from oracle import waypoint as oracle_wp
     from vlnce_b200.ppo_step import ActionDictRolloutStorage, WDDPPOStep
 
-    case = cases.CASES["wp_eval"]
+    case = cases.CASES[name]
     T, N = 2, 2
     kw = dict(clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, offset_regularize_coef=0.1146,
               pano_entropy_coef=1.0, offset_entropy_coef=1.0, distance_entropy_coef=1.0)
     space = oracle_wp.storage_obs_space(length=12)
+    wp = case.get("waypoint", {})
+    cont = dict(continuous_offset=wp.get("continuous_offset", True), continuous_distance=wp.get("continuous_distance", True))
+    classes = dict(distance=0 if cont["continuous_distance"] else 6, offset=0 if cont["continuous_offset"] else 7)
     # oracle
     opol = cases.build_policy(oracle_wp, case)
     cases.set_mode(opol, case)
-    ost = oracle_wp.ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2)
-    nv = _fill_rollouts(ost, T, N)
+    ost = oracle_wp.ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2, **cont)
+    nv = _fill_rollouts(ost, T, N, classes=classes)
     ost.compute_returns(nv, True, 0.99, 0.95)
     opt = torch.optim.Adam([p for p in opol.parameters() if p.requires_grad], lr=2e-4, eps=1e-5)
     torch.manual_seed(21)
@@ -146,8 +151,8 @@ def test_fused_wddppo_update_matches_oracle_loop():
     pol = cases.build_policy(vlnce_b200, case)
     cases.set_mode(pol, case)
     substitute_trunks(pol, case)
-    st = ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2)
-    nv2 = _fill_rollouts(st, T, N)
+    st = ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2, **cont)
+    nv2 = _fill_rollouts(st, T, N, classes=classes)
     with lib.dry_run(executor=Emulator()):
         st.compute_returns(nv2, True, 0.99, 0.95)
         torch.testing.assert_close(st.returns, ost.returns, rtol=1e-6, atol=1e-6)

@@ -13,7 +13,7 @@ warnings.filterwarnings("ignore")
 
 
 @pytest.mark.parametrize("name", ["cma_act_bntrain", "cma_train_features", "seq2seq_act", "seq2seq_train_features",
-                                  "wp_act", "wp_eval", "wp_act_hpn", "wp_eval_hpn"])
+                                  "wp_act", "wp_eval", "wp_act_hpn", "wp_eval_hpn", "wp_act_dd", "wp_eval_d_"])
 def test_oracle_equals_reference_live(name):
     ref = reference_import.load()
     a = cases.run_case(ref, name, aux=ref.AuxLosses)

@@ -370,11 +370,85 @@ __device__ __forceinline__ float tn_sample(float mu, float sigma, float lo, floa
 struct ActConsts {
   float d_lo, d_hi, o_lim;
   int predict_distance, predict_offset;
+  int nd, no;                            // classes of a discrete distance / offset head (0 = continuous TruncatedNormal)
+  float dist_a, dist_b, off_a, off_b;    // {distance,offset}_to_continuous = a + b * value (waypoint_predictors.py:184-209)
 };
+
+// One action component (distance or offset) of one row at the selected pano frame, either a two-sided
+// TruncatedNormal(loc = v1[idx], scale = sqrt(v2[idx])) (waypoint_policy.py:48-55) or a Categorical over ncls
+// logits v1[idx, :] (:56-59, batched_index_select).
+struct Comp {
+  int ncls;
+  float mu, sg;      // continuous
+  TN t;
+  const float* lg;   // discrete: raw logits of the selected frame
+  float lse, ent;    // discrete: logsumexp, entropy
+};
+__device__ __forceinline__ Comp comp_load(int ncls, const float* v1, const float* v2, size_t row_frame, float lo, float hi) {
+  Comp c;
+  c.ncls = ncls;
+  if (ncls > 0) {
+    c.lg = v1 + row_frame * ncls;
+    float mx = -INFINITY;
+    for (int j = 0; j < ncls; ++j) mx = fmaxf(mx, c.lg[j]);
+    float s = 0.f;
+    for (int j = 0; j < ncls; ++j) s += expf(c.lg[j] - mx);
+    c.lse = mx + logf(s);
+    float h = 0.f;
+    for (int j = 0; j < ncls; ++j) { const float l = c.lg[j] - c.lse; h -= expf(l) * l; }
+    c.ent = h;
+    c.mu = c.sg = 0.f;
+  } else {
+    c.lg = nullptr;
+    c.mu = v1[row_frame];
+    c.sg = sqrtf(v2[row_frame]);
+    c.t = tn_stats(c.mu, c.sg, lo, hi);
+    c.ent = c.t.ent;
+    c.lse = 0.f;
+  }
+  return c;
+}
+__device__ __forceinline__ float comp_log_prob(const Comp& c, float y) {
+  if (c.ncls > 0) {
+    int k = (int)y;
+    k = k < 0 ? 0 : (k >= c.ncls ? c.ncls - 1 : k);
+    return c.lg[k] - c.lse;
+  }
+  return tn_log_prob(y, c.mu, c.sg, c.t.Z);
+}
+__device__ __forceinline__ float comp_mode(const Comp& c) {  // CustomFixedCategorical.mode(): first maximum
+  if (c.ncls == 0) return c.mu;
+  int best = 0;
+  float bv = expf(c.lg[0] - c.lse);
+  for (int j = 1; j < c.ncls; ++j) { const float v = expf(c.lg[j] - c.lse); if (v > bv) { bv = v; best = j; } }
+  return (float)best;
+}
+// gradients w.r.t. the head outputs of this row's frames: g1 / g2 are (P, max(ncls,1)) blocks, zero except at idx
+// (mask_lp gates the log-prob term, mask_h the entropy term: they differ for categorical heads, see W4 below)
+__device__ __forceinline__ void comp_grads(const Comp& c, float y, int P, int idx, float mask_lp, float mask_h,
+                                           float g_lp, float g_h, float* g1, float* g2) {
+  const int w = c.ncls > 0 ? c.ncls : 1;
+  for (int j = 0; j < P * w; ++j) g1[j] = 0.f;
+  if (c.ncls > 0) {
+    int k = (int)y;
+    k = k < 0 ? 0 : (k >= c.ncls ? c.ncls - 1 : k);
+    for (int j = 0; j < c.ncls; ++j) {
+      const float l = c.lg[j] - c.lse, p = expf(l);
+      g1[idx * w + j] = mask_lp * g_lp * ((j == k ? 1.f : 0.f) - p) + mask_h * g_h * (-p * (l + c.ent));
+    }
+    return;
+  }
+  for (int j = 0; j < P; ++j) g2[j] = 0.f;
+  float dlp_dmu, dlp_dv, dH_dmu, dH_dv;
+  tn_grads(c.t, y, c.mu, c.sg, &dlp_dmu, &dlp_dv, &dH_dmu, &dH_dv);
+  g1[idx] = mask_lp * g_lp * dlp_dmu + mask_h * g_h * dH_dmu;
+  g2[idx] = mask_lp * g_lp * dlp_dv + mask_h * g_h * dH_dv;
+}
 
 // ------------------------------------------------------------------------------------
 // WaypointPolicy.act post-processing (waypoint_policy.py:129-247), one thread per env.
 // fout (B, 10): offset, distance, action_log_prob, var_distance, var_offset, mode_offset, mode_distance, r, theta, stop
+// (discrete heads: offset / distance / modes are class indices, variances NaN like torch's Categorical.variance)
 // ------------------------------------------------------------------------------------
 __global__ void wp_act_kernel(const float* __restrict__ logp, const float* __restrict__ o1, const float* __restrict__ o2,
                               const float* __restrict__ d1, const float* __restrict__ d2, long long* __restrict__ pano_stop,
@@ -383,30 +457,51 @@ __global__ void wp_act_kernel(const float* __restrict__ logp, const float* __res
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* lp = logp + (size_t)b * (P + 1);
+  const unsigned long long ctr = offset + (unsigned long long)b * 65536ull;
   int ps = 0;
   if (deterministic) {  // CustomFixedCategorical.mode(): first maximum of the probabilities
     float bv = expf(lp[0]);
     for (int j = 1; j <= P; ++j) { const float v = expf(lp[j]); if (v > bv) { bv = v; ps = j; } }
   } else {
-    const float u = uniform01(seed, offset + (unsigned long long)b * 65536ull);
+    const float u = uniform01(seed, ctr);
     float acc = 0.f;
     ps = P;
     for (int j = 0; j <= P; ++j) { acc += expf(lp[j]); if (u < acc) { ps = j; break; } }
   }
   const int pano = ps % P;
   const float go = ps != P ? 1.f : 0.f;
-  const float mu_d = d1[(size_t)b * P + pano], sg_d = sqrtf(d2[(size_t)b * P + pano]);
-  const float mu_o = o1[(size_t)b * P + pano], sg_o = sqrtf(o2[(size_t)b * P + pano]);
-  const TN td = tn_stats(mu_d, sg_d, c.d_lo, c.d_hi);
-  const TN to = tn_stats(mu_o, sg_o, -c.o_lim, c.o_lim);
-  const unsigned long long ctr = offset + (unsigned long long)b * 65536ull;
-  float dist = deterministic ? mu_d : tn_sample(mu_d, sg_d, c.d_lo, c.d_hi, seed, ctr + 16);
-  float ofs = deterministic ? mu_o : tn_sample(mu_o, sg_o, -c.o_lim, c.o_lim, seed, ctr + 32768);
-  const float lp_d = tn_log_prob(dist, mu_d, sg_d, td.Z);
-  const float lp_o = tn_log_prob(ofs, mu_o, sg_o, to.Z);
-  float a_dist = dist, a_ofs = ofs, var_d = td.var, var_o = to.var;
+  const size_t rf = (size_t)b * P + pano;
+  const Comp cd = comp_load(c.nd, d1, d2, rf, c.d_lo, c.d_hi);
+  const Comp co = comp_load(c.no, o1, o2, rf, -c.o_lim, c.o_lim);
+  float dist, ofs;
+  if (c.nd > 0) {
+    dist = comp_mode(cd);
+    if (!deterministic) {
+      const float u = uniform01(seed, ctr + 8);
+      float acc = 0.f;
+      dist = (float)(c.nd - 1);
+      for (int j = 0; j < c.nd; ++j) { acc += expf(cd.lg[j] - cd.lse); if (u < acc) { dist = (float)j; break; } }
+    }
+  } else {
+    dist = deterministic ? cd.mu : tn_sample(cd.mu, cd.sg, c.d_lo, c.d_hi, seed, ctr + 16);
+  }
+  if (c.no > 0) {
+    ofs = comp_mode(co);
+    if (!deterministic) {
+      const float u = uniform01(seed, ctr + 9);
+      float acc = 0.f;
+      ofs = (float)(c.no - 1);
+      for (int j = 0; j < c.no; ++j) { acc += expf(co.lg[j] - co.lse); if (u < acc) { ofs = (float)j; break; } }
+    }
+  } else {
+    ofs = deterministic ? co.mu : tn_sample(co.mu, co.sg, -c.o_lim, c.o_lim, seed, ctr + 32768);
+  }
+  const float lp_d = comp_log_prob(cd, dist), lp_o = comp_log_prob(co, ofs);
+  float a_dist = fmaf(c.dist_b, dist, c.dist_a), a_ofs = fmaf(c.off_b, ofs, c.off_a);
+  float var_d = c.nd > 0 ? NAN : cd.t.var, var_o = c.no > 0 ? NAN : co.t.var;
+  const float mode_d = comp_mode(cd), mode_o = comp_mode(co);
   if (!c.predict_offset) { a_ofs = 0.f; ofs = 0.f; var_o = 0.f; }
-  if (!c.predict_distance) { a_dist = 0.25f; dist = 0.25f; var_d = 0.f; }
+  if (!c.predict_distance) { a_dist = 0.25f; dist = c.nd > 0 ? 0.f : 0.25f; var_d = 0.f; }
   float theta = (float)pano * (kTwoPi / (float)P) + a_ofs;
   theta -= floorf(theta / kTwoPi) * kTwoPi;  // torch `%`: sign of the divisor
   float alp = lp[ps];
@@ -414,33 +509,27 @@ __global__ void wp_act_kernel(const float* __restrict__ logp, const float* __res
   if (c.predict_offset) alp += go * lp_o;
   pano_stop[b] = ps;
   float* f = fout + (size_t)b * 10;
-  f[0] = ofs; f[1] = dist; f[2] = alp; f[3] = var_d; f[4] = var_o; f[5] = mu_o; f[6] = mu_d;
+  f[0] = ofs; f[1] = dist; f[2] = alp; f[3] = var_d; f[4] = var_o; f[5] = mode_o; f[6] = mode_d;
   f[7] = go != 0.f ? a_dist : 0.f; f[8] = go != 0.f ? theta : 0.f; f[9] = 1.f - go;
 }
 
 // Gradients of one row of evaluate_actions' outputs w.r.t. the net outputs, given the upstream gradients of
 // {action_log_prob, entropy_pano, entropy_offset, entropy_distance}.
-__device__ __forceinline__ void wp_row_grads(const float* lp, int a, int idx, int P, float Hp, const TN& td,
-                                             const TN& to, float y_d, float y_o, float mu_d, float sg_d, float mu_o,
-                                             float sg_o, float dm, float om, float g_lp, float g_hp, float g_ho,
-                                             float g_hd, float* d_raw, float* d_o1, float* d_o2, float* d_d1,
-                                             float* d_d2) {
+__device__ __forceinline__ void wp_row_grads(const float* lp, int a, int idx, int P, float Hp, const Comp& cd,
+                                             const Comp& co, float y_d, float y_o, float dm, float om, float dmh,
+                                             float omh, float g_lp, float g_hp, float g_ho, float g_hd, float* d_raw,
+                                             float* d_o1, float* d_o2, float* d_d1, float* d_d2) {
   for (int j = 0; j <= P; ++j) {
     const float p = expf(lp[j]);
     d_raw[j] = g_lp * ((j == a ? 1.f : 0.f) - p) + g_hp * (-p * (lp[j] + Hp));
   }
-  for (int j = 0; j < P; ++j) { d_d1[j] = 0.f; d_d2[j] = 0.f; d_o1[j] = 0.f; d_o2[j] = 0.f; }
-  float dlp_dmu, dlp_dv, dH_dmu, dH_dv;
-  tn_grads(td, y_d, mu_d, sg_d, &dlp_dmu, &dlp_dv, &dH_dmu, &dH_dv);
-  d_d1[idx] = dm * (g_lp * dlp_dmu + g_hd * dH_dmu);
-  d_d2[idx] = dm * (g_lp * dlp_dv + g_hd * dH_dv);
-  tn_grads(to, y_o, mu_o, sg_o, &dlp_dmu, &dlp_dv, &dH_dmu, &dH_dv);
-  d_o1[idx] = om * (g_lp * dlp_dmu + g_ho * dH_dmu);
-  d_o2[idx] = om * (g_lp * dlp_dv + g_ho * dH_dv);
+  comp_grads(cd, y_d, P, idx, dm, dmh, g_lp, g_hd, d_d1, d_d2);
+  comp_grads(co, y_o, P, idx, om, omh, g_lp, g_ho, d_o1, d_o2);
 }
 
 // backward of evaluate_actions for arbitrary upstream gradients up (R,4) = d{action_log_prob, entropy_pano,
-// entropy_offset, entropy_distance} (the autograd bridge; the fused PPO kernel below inlines its own)
+// entropy_offset, entropy_distance} (the autograd bridge; the fused PPO kernel below inlines its own).
+// Gradient blocks: d_d1 (R, P, max(nd,1)), d_d2 (R, P) [continuous only]; likewise for the offset.
 __global__ void wp_eval_bwd_kernel(const float* __restrict__ logp, const float* __restrict__ o1,
                                    const float* __restrict__ o2, const float* __restrict__ d1,
                                    const float* __restrict__ d2, const float* __restrict__ a_pano,
@@ -457,29 +546,31 @@ __global__ void wp_eval_bwd_kernel(const float* __restrict__ logp, const float* 
   const float dm = go * (float)ac.predict_distance, om = go * (float)ac.predict_offset;
   float Hp = 0.f;
   for (int j = 0; j <= P; ++j) Hp -= expf(lp[j]) * lp[j];
-  const float mu_d = d1[(size_t)r * P + idx], sg_d = sqrtf(d2[(size_t)r * P + idx]);
-  const float mu_o = o1[(size_t)r * P + idx], sg_o = sqrtf(o2[(size_t)r * P + idx]);
-  const TN td = tn_stats(mu_d, sg_d, ac.d_lo, ac.d_hi);
-  const TN to = tn_stats(mu_o, sg_o, -ac.o_lim, ac.o_lim);
+  const size_t rf = (size_t)r * P + idx;
+  const Comp cd = comp_load(ac.nd, d1, d2, rf, ac.d_lo, ac.d_hi);
+  const Comp co = comp_load(ac.no, o1, o2, rf, -ac.o_lim, ac.o_lim);
   const float* u = up + (size_t)r * 4;
-  wp_row_grads(lp, a, idx, P, Hp, td, to, a_distance[r], a_offset[r], mu_d, sg_d, mu_o, sg_o, dm, om, u[0], u[1], u[2],
-               u[3], d_raw + (size_t)r * (P + 1), d_o1 + (size_t)r * P, d_o2 + (size_t)r * P, d_d1 + (size_t)r * P,
+  const int wd = ac.nd > 0 ? ac.nd : 1, wo = ac.no > 0 ? ac.no : 1;
+  wp_row_grads(lp, a, idx, P, Hp, cd, co, a_distance[r], a_offset[r], dm, om, ac.nd > 0 ? 1.f : dm,
+               ac.no > 0 ? 1.f : om, u[0], u[1], u[2], u[3], d_raw + (size_t)r * (P + 1), d_o1 + (size_t)r * P * wo, d_o2 + (size_t)r * P, d_d1 + (size_t)r * P * wd,
                d_d2 + (size_t)r * P);
 }
 
 struct PPOConsts {
   float clip, value_coef, entropy_coef, offset_reg, c_pano, c_offset, c_distance;
   int clipped_value;
-  float off_a, off_b;  // offset_to_continuous = off_a + off_b * offset
 };
 
 // ------------------------------------------------------------------------------------
 // evaluate_actions (waypoint_policy.py:265-333) fused with the WDDPPO mini-batch loss and its
 // gradients (ddppo_alg.py:56-124), one CTA.  Rows r < R:
 //   eval_out (R,4) = {action_log_prob, entropy_pano, entropy_offset, entropy_distance}
+//   (W4: for a CATEGORICAL head the reference multiplies a (R,1) mask with the (R,) entropy, waypoint_policy.py:318-
+//   325, i.e. builds an (R,R) matrix mask_i * H_j; every mean over it equals mean(mask) * mean(H).  eval_out then
+//   carries the raw H_j and the caller forms the matrix; the loss below uses mean(mask) as the row weight.)
 //   losses[8] = {loss, value_loss, action_loss, entropy_loss, offset_loss, mean entropy pano/offset/distance}
-//   d_raw (R,P+1) w.r.t. the raw pano/stop logits, d_o1,d_o2,d_d1,d_d2 (R,P) (non-zero only at the taken
-//   pano), d_values (R).  Gradient outputs and the loss inputs may be NULL (plain evaluate_actions).
+//   d_raw (R,P+1) w.r.t. the raw pano/stop logits, d_o1,d_o2,d_d1,d_d2 (non-zero only at the taken pano; layout as
+//   in wp_eval_bwd_kernel), d_values (R).  Gradient outputs and the loss inputs may be NULL (plain evaluate_actions).
 // ------------------------------------------------------------------------------------
 __global__ void wp_ppo_loss_kernel(const float* __restrict__ logp, const float* __restrict__ o1,
                                    const float* __restrict__ o2, const float* __restrict__ d1,
@@ -495,6 +586,11 @@ __global__ void wp_ppo_loss_kernel(const float* __restrict__ logp, const float* 
   const bool with_loss = losses != nullptr;
   const bool with_grad = d_raw != nullptr;
   const float invR = 1.f / (float)R;
+  const int wd = ac.nd > 0 ? ac.nd : 1, wo = ac.no > 0 ? ac.no : 1;
+  float s_go = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) s_go += ((int)a_pano[r] != P) ? 1.f : 0.f;
+  const float go_bar = block_sum(s_go, red) * invR;  // mean of the not-STOP mask (W4)
+  __syncthreads();
   float s_val = 0.f, s_act = 0.f, s_ent = 0.f, s_off = 0.f, s_hp = 0.f, s_ho = 0.f, s_hd = 0.f;
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
     const float* lp = logp + (size_t)r * (P + 1);
@@ -502,19 +598,19 @@ __global__ void wp_ppo_loss_kernel(const float* __restrict__ logp, const float* 
     const int idx = a % P;
     const float go = a != P ? 1.f : 0.f;
     const float dm = go * (float)ac.predict_distance, om = go * (float)ac.predict_offset;
+    const float dmh = ac.nd > 0 ? go_bar * (float)ac.predict_distance : dm;  // entropy weights of this row
+    const float omh = ac.no > 0 ? go_bar * (float)ac.predict_offset : om;
     float Hp = 0.f;
     for (int j = 0; j <= P; ++j) Hp -= expf(lp[j]) * lp[j];
-    const float mu_d = d1[(size_t)r * P + idx], v_d = d2[(size_t)r * P + idx], sg_d = sqrtf(v_d);
-    const float mu_o = o1[(size_t)r * P + idx], v_o = o2[(size_t)r * P + idx], sg_o = sqrtf(v_o);
-    const TN td = tn_stats(mu_d, sg_d, ac.d_lo, ac.d_hi);
-    const TN to = tn_stats(mu_o, sg_o, -ac.o_lim, ac.o_lim);
+    const size_t rf = (size_t)r * P + idx;
+    const Comp cd = comp_load(ac.nd, d1, d2, rf, ac.d_lo, ac.d_hi);
+    const Comp co = comp_load(ac.no, o1, o2, rf, -ac.o_lim, ac.o_lim);
     const float y_d = a_distance[r], y_o = a_offset[r];
-    const float lp_d = tn_log_prob(y_d, mu_d, sg_d, td.Z), lp_o = tn_log_prob(y_o, mu_o, sg_o, to.Z);
-    const float alp = lp[a] + dm * lp_d + om * lp_o;
-    const float Ho = om * to.ent, Hd = dm * td.ent;
+    const float alp = lp[a] + dm * comp_log_prob(cd, y_d) + om * comp_log_prob(co, y_o);
+    const float Ho = omh * co.ent, Hd = dmh * cd.ent;
     if (eval_out != nullptr) {
       float* e = eval_out + (size_t)r * 4;
-      e[0] = alp; e[1] = Hp; e[2] = Ho; e[3] = Hd;
+      e[0] = alp; e[1] = Hp; e[2] = ac.no > 0 ? co.ent : Ho; e[3] = ac.nd > 0 ? cd.ent : Hd;
     }
     if (!with_loss) continue;
     const float ratio = expf(alp - lp_old[r]);
@@ -528,7 +624,7 @@ __global__ void wp_ppo_loss_kernel(const float* __restrict__ logp, const float* 
     const float l1 = (v - rt) * (v - rt), l2 = (vc - rt) * (vc - rt);
     s_val += pc.clipped_value ? 0.5f * fmaxf(l1, l2) : 0.5f * l1;
     s_ent += pc.c_pano * Hp + pc.c_offset * Ho + pc.c_distance * Hd;
-    s_off += fabsf(fmaf(pc.off_b, y_o, pc.off_a));
+    s_off += fabsf(fmaf(ac.off_b, y_o, ac.off_a));
     s_hp += Hp; s_ho += Ho; s_hd += Hd;
     if (!with_grad) continue;
     // d loss / d action_log_prob: torch.min routes to the smaller surrogate (ties inside the clip range
@@ -540,9 +636,9 @@ __global__ void wp_ppo_loss_kernel(const float* __restrict__ logp, const float* 
     if (!pc.clipped_value || l1 >= l2) dv = v - rt;
     else dv = (diff > -pc.clip && diff < pc.clip) ? (vc - rt) : 0.f;
     d_values[r] = pc.value_coef * invR * dv;
-    wp_row_grads(lp, a, idx, P, Hp, td, to, y_d, y_o, mu_d, sg_d, mu_o, sg_o, dm, om, g_lp, g_ent * pc.c_pano,
-                 g_ent * pc.c_offset, g_ent * pc.c_distance, d_raw + (size_t)r * (P + 1), d_o1 + (size_t)r * P,
-                 d_o2 + (size_t)r * P, d_d1 + (size_t)r * P, d_d2 + (size_t)r * P);
+    wp_row_grads(lp, a, idx, P, Hp, cd, co, y_d, y_o, dm, om, dmh, omh, g_lp, g_ent * pc.c_pano, g_ent * pc.c_offset,
+                 g_ent * pc.c_distance, d_raw + (size_t)r * (P + 1), d_o1 + (size_t)r * P * wo, d_o2 + (size_t)r * P,
+                 d_d1 + (size_t)r * P * wd, d_d2 + (size_t)r * P);
   }
   if (!with_loss) return;
   const float t_val = block_sum(s_val, red); __syncthreads();
@@ -780,6 +876,8 @@ static ActConsts act_consts(const float* c) {
   ActConsts a;
   a.d_lo = c[0]; a.d_hi = c[1]; a.o_lim = c[2];
   a.predict_distance = c[3] != 0.f; a.predict_offset = c[4] != 0.f;
+  a.nd = (int)c[5]; a.no = (int)c[6];
+  a.dist_a = c[7]; a.dist_b = c[8]; a.off_a = c[9]; a.off_b = c[10];
   return a;
 }
 
@@ -787,8 +885,9 @@ extern "C" int vlnce_wp_act(const float* logp, const float* o1, const float* o2,
                             long long* pano_stop, float* fout, int B, int P, int deterministic,
                             unsigned long long seed, unsigned long long offset, const float* act_consts_host,
                             cudaStream_t stream) {
-  VLNCE_CHECK_ARG(logp && o1 && o2 && d1 && d2 && pano_stop && fout && B > 0 && P > 0 && act_consts_host,
-                  "wp_act: bad arguments");
+  VLNCE_CHECK_ARG(logp && o1 && d1 && pano_stop && fout && B > 0 && P > 0 && act_consts_host, "wp_act: bad arguments");
+  VLNCE_CHECK_ARG((act_consts_host[5] != 0.f || d2) && (act_consts_host[6] != 0.f || o2),
+                  "wp_act: a continuous head needs its variance tensor");
   wp_act_kernel<<<cdiv(B, 128), 128, 0, stream>>>(logp, o1, o2, d1, d2, pano_stop, fout, B, P, deterministic, seed,
                                                  offset, act_consts(act_consts_host));
   VLNCE_LAUNCH_CHECK("wp_act_kernel");
@@ -801,11 +900,13 @@ extern "C" int vlnce_wp_ppo_loss(const float* logp, const float* o1, const float
                                  const float* adv, int R, int P, const float* act_consts_host,
                                  const float* ppo_consts_host, float* eval_out, float* losses, float* d_raw, float* d_o1,
                                  float* d_o2, float* d_d1, float* d_d2, float* d_values, cudaStream_t stream) {
-  VLNCE_CHECK_ARG(logp && o1 && o2 && d1 && d2 && a_pano && a_offset && a_distance && R > 0 && P > 0 && act_consts_host,
+  VLNCE_CHECK_ARG(logp && o1 && d1 && a_pano && a_offset && a_distance && R > 0 && P > 0 && act_consts_host,
                   "wp_ppo_loss: bad arguments");
+  const bool cont_d = act_consts_host[5] == 0.f, cont_o = act_consts_host[6] == 0.f;
+  VLNCE_CHECK_ARG((!cont_d || d2) && (!cont_o || o2), "wp_ppo_loss: a continuous head needs its variance tensor");
   VLNCE_CHECK_ARG(losses == nullptr || (values && v_old && ret && lp_old && adv && ppo_consts_host),
                   "wp_ppo_loss: the loss needs values, value_preds, returns, old log-probs, advantages and constants");
-  VLNCE_CHECK_ARG(d_raw == nullptr || (losses && d_o1 && d_o2 && d_d1 && d_d2 && d_values),
+  VLNCE_CHECK_ARG(d_raw == nullptr || (losses && d_o1 && d_d1 && d_values && (!cont_d || d_d2) && (!cont_o || d_o2)),
                   "wp_ppo_loss: gradient outputs come as a full set and need the loss");
   PPOConsts pc;
   memset(&pc, 0, sizeof(pc));
@@ -813,7 +914,6 @@ extern "C" int vlnce_wp_ppo_loss(const float* logp, const float* o1, const float
     const float* c = ppo_consts_host;
     pc.clip = c[0]; pc.value_coef = c[1]; pc.entropy_coef = c[2]; pc.offset_reg = c[3];
     pc.c_pano = c[4]; pc.c_offset = c[5]; pc.c_distance = c[6]; pc.clipped_value = c[7] != 0.f;
-    pc.off_a = c[8]; pc.off_b = c[9];
   }
   wp_ppo_loss_kernel<<<1, 256, 0, stream>>>(logp, o1, o2, d1, d2, values, a_pano, a_offset, a_distance, v_old, ret,
                                             lp_old, adv, R, P, act_consts(act_consts_host), pc, eval_out, losses, d_raw,
@@ -826,9 +926,11 @@ extern "C" int vlnce_wp_eval_bwd(const float* logp, const float* o1, const float
                                  const float* a_pano, const float* a_offset, const float* a_distance,
                                  const float* upstream, int R, int P, const float* act_consts_host, float* d_raw,
                                  float* d_o1, float* d_o2, float* d_d1, float* d_d2, cudaStream_t stream) {
-  VLNCE_CHECK_ARG(logp && o1 && o2 && d1 && d2 && a_pano && a_offset && a_distance && upstream && R > 0 && P > 0 &&
-                      act_consts_host && d_raw && d_o1 && d_o2 && d_d1 && d_d2,
+  VLNCE_CHECK_ARG(logp && o1 && d1 && a_pano && a_offset && a_distance && upstream && R > 0 && P > 0 &&
+                      act_consts_host && d_raw && d_o1 && d_d1,
                   "wp_eval_bwd: bad arguments");
+  VLNCE_CHECK_ARG((act_consts_host[5] != 0.f || (d2 && d_d2)) && (act_consts_host[6] != 0.f || (o2 && d_o2)),
+                  "wp_eval_bwd: a continuous head needs its variance tensor and gradient");
   wp_eval_bwd_kernel<<<cdiv(R, 128), 128, 0, stream>>>(logp, o1, o2, d1, d2, a_pano, a_offset, a_distance, upstream, R,
                                                       P, act_consts(act_consts_host), d_raw, d_o1, d_o2, d_d1, d_d2);
   VLNCE_LAUNCH_CHECK("wp_eval_bwd_kernel");

@@ -129,7 +129,7 @@ class WDDPPOStep:
         self.use_normalized_advantage = use_normalized_advantage
         self.ppo_consts = _host_floats([clip_param, value_loss_coef, entropy_coef, offset_regularize_coef,
                                         pano_entropy_coef, offset_entropy_coef, distance_entropy_coef,
-                                        float(bool(use_clipped_value_loss)), 0.0, 1.0])
+                                        float(bool(use_clipped_value_loss))])
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):

@@ -185,29 +185,35 @@ def make_waypoint_rows(gen, rows: int, rgb_hw: int = 224, hw: int = 256, length:
     }
 
 
-def make_waypoint_actions(gen, rows: int, panos: int = 12, dmin: float = 0.25, dmax: float = 4.0):
-    """Action components as ``WaypointPolicy.act`` emits them (continuous heads): pano in
-    0..panos (panos = STOP), offset in [-pi/panos, pi/panos], distance in [dmin, dmax]."""
+def make_waypoint_actions(gen, rows: int, panos: int = 12, dmin: float = 0.25, dmax: float = 4.0, classes=None):
+    """Action components as ``WaypointPolicy.act`` emits them: pano in 0..panos (panos = STOP); continuous heads:
+    offset in [-pi/panos, pi/panos], distance in [dmin, dmax]; discrete heads (``classes[k]`` > 0): class indices."""
     lim = 3.141592653589793 / panos
-    return {
+    classes = classes or {}
+    out = {
         "pano": torch.randint(0, panos + 1, (rows, 1), generator=gen, dtype=torch.int64),
         "offset": (torch.rand(rows, 1, generator=gen) * 2 - 1) * lim * 0.98,
         "distance": dmin + torch.rand(rows, 1, generator=gen) * (dmax - dmin),
     }
+    for k in ("offset", "distance"):
+        if classes.get(k, 0):
+            out[k] = torch.randint(0, classes[k], (rows, 1), generator=gen, dtype=torch.int64)
+    return out
 
 
-def make_waypoint_act_batch(seed: int, n: int, hidden: int = 256, layers: int = 2, rgb_u8: bool = False, **kw):
+def make_waypoint_act_batch(seed: int, n: int, hidden: int = 256, layers: int = 2, rgb_u8: bool = False,
+                            classes=None, **kw):
     """One ``WaypointPolicy.act`` call: (observations, rnn_states, prev_actions, masks)."""
     gen = torch.Generator().manual_seed(seed)
     obs = make_waypoint_rows(gen, n, rgb_u8=rgb_u8, **kw)
     h = torch.randn(n, layers, hidden, generator=gen) * 0.5
-    prev = make_waypoint_actions(gen, n)
+    prev = make_waypoint_actions(gen, n, classes=classes)
     masks = torch.ones(n, 1, dtype=torch.uint8)
     masks[0] = 0  # one env at an episode start (history frame and prev action zeroed)
     return obs, h, prev, masks
 
 
-def make_waypoint_eval_batch(seed: int, t: int, n: int, hidden: int = 256, layers: int = 2, **kw):
+def make_waypoint_eval_batch(seed: int, t: int, n: int, hidden: int = 256, layers: int = 2, classes=None, **kw):
     """One PPO mini-batch as ``ActionDictRolloutStorage.recurrent_generator`` yields it
     (``rollout_storage.py:154-276``), time-major rows: (obs, h0 (N,Lr,H), actions, prev_actions,
     value_preds, returns, masks, old_action_log_probs, adv_targ)."""
@@ -218,7 +224,7 @@ def make_waypoint_eval_batch(seed: int, t: int, n: int, hidden: int = 256, layer
     instr = instr.unsqueeze(0).expand(t, n, length).reshape(r, length).contiguous()
     obs = make_waypoint_rows(gen, r, length=length, instruction=instr, **kw)
     h0 = torch.randn(n, layers, hidden, generator=gen) * 0.5
-    actions = make_waypoint_actions(gen, r)
+    actions = make_waypoint_actions(gen, r, classes=classes)
     actions["pano"][1] = 12  # make sure a STOP row is covered
     prev = {k: torch.zeros_like(v) for k, v in actions.items()}
     for k in actions:

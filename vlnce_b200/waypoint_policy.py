@@ -7,9 +7,9 @@ drop-in: same registry name, constructor, ``from_config``, ``act`` / ``get_value
 parameters; the arithmetic runs in the CUDA library (``csrc/waypoint.cu`` + the head kernels the
 CMA policy uses), sequenced by ``WaypointEngine``.
 
-Built for the continuous heads of ``config/r2r_waypoint/1-wpn-cc.yaml`` (BASELINE config C4;
-``predict_distance`` / ``predict_offset`` switches included).  The discrete-head recipes (2-wpn-dc,
-3-wpn-dd, 4-wpn-d_) raise ``NotImplementedError``.
+All six recipes of ``config/r2r_waypoint`` are covered: continuous (TruncatedNormal) and discrete (categorical)
+distance / offset heads in any combination, with the ``predict_distance`` / ``predict_offset`` switches
+(1-wpn-cc = BASELINE config C4, 2-wpn-dc, 3-wpn-dd, 4-wpn-d_, 5-hpn-_c, 6-hpn-__).
 
 Algebra kept from the CMA engine: single-query attentions are re-associated (keys / values are never
 materialised); additionally ``mean_frames(Linear(mean_pos(x))) = Linear(mean(x))`` for the pooled RGB
@@ -76,9 +76,6 @@ class WaypointPredictionNet(Net):
         nn.Module.__init__(self)
         cfg = self.model_config = model_config
         w = self.wypt_cfg = model_config.WAYPOINT
-        if not (w.continuous_distance and w.continuous_offset):
-            raise NotImplementedError("discrete distance / offset heads (2-wpn-dc, 3-wpn-dd, 4-wpn-d_) are not built; "
-                                      "1-wpn-cc.yaml (continuous heads) is")
         for flag in ("ablate_instruction", "ablate_depth", "ablate_rgb"):
             if cfg.get(flag, False):
                 raise NotImplementedError(f"MODEL.{flag}=True is not built (ablation study switch)")
@@ -115,20 +112,41 @@ class WaypointPredictionNet(Net):
         nn.init.constant_(self.stop_linear.bias, 0)
         self.compress_x_linear = nn.Sequential(nn.Linear(H, feat), nn.ReLU(True))
         cat = H + feat
-        self.distance_linear = nn.Sequential(nn.Linear(cat, 1), nn.Sigmoid())
-        self.distance_var_linear = nn.Sequential(nn.Linear(cat, 1), nn.Sigmoid())
-        self.offset_linear = nn.Sequential(nn.Linear(cat, 1), nn.Tanh())  # TemperatureTanh: parameter-free
+        if w.continuous_distance:  # waypoint_predictors.py:223-243
+            self.distance_linear = nn.Sequential(nn.Linear(cat, 1), nn.Sigmoid())
+            self.distance_var_linear = nn.Sequential(nn.Linear(cat, 1), nn.Sigmoid())
+        else:
+            self.distance_linear = nn.Linear(cat, w.discrete_distances)
         self.offset_scale = math.pi / self._num_panos
-        self.offset_var_linear = nn.Sequential(nn.Linear(cat, 1), nn.Sigmoid())
+        if w.continuous_offset:    # :245-266
+            self.offset_linear = nn.Sequential(nn.Linear(cat, 1), nn.Tanh())  # TemperatureTanh: parameter-free
+            self.offset_var_linear = nn.Sequential(nn.Linear(cat, 1), nn.Sigmoid())
+        else:
+            self.offset_linear = nn.Linear(cat, w.discrete_offsets)
         self.precision = "bf16"
         self.train()
 
     # ---- reference attribute surface --------------------------------------------------
-    def distance_to_continuous(self, distance):  # waypoint_predictors.py:184-197 (continuous head)
-        return distance
+    def to_continuous_consts(self):
+        """(dist_a, dist_b, off_a, off_b): ``{distance,offset}_to_continuous(v) = a + b * v``
+        (waypoint_predictors.py:184-209; identity for the continuous heads)."""
+        w = self.wypt_cfg
+        da, db, oa, ob = 0.0, 1.0, 0.0, 1.0
+        if not w.continuous_distance:
+            da = w.min_distance_prediction
+            db = (w.max_distance_prediction - w.min_distance_prediction) / (w.discrete_distances - 1)
+        if not w.continuous_offset:
+            per_pano = 2 * math.pi / self._num_panos
+            oa, ob = -per_pano / 2, per_pano / (w.discrete_offsets - 1)
+        return da, db, oa, ob
+
+    def distance_to_continuous(self, distance):  # waypoint_predictors.py:184-197 (tiny, off the hot path)
+        da, db, _, _ = self.to_continuous_consts()
+        return distance if self.wypt_cfg.continuous_distance else da + distance * db
 
     def offset_to_continuous(self, offset):  # :199-209
-        return offset
+        _, _, oa, ob = self.to_continuous_consts()
+        return offset if self.wypt_cfg.continuous_offset else oa + offset * ob
 
     @property
     def num_recurrent_layers(self):
@@ -155,8 +173,9 @@ class WaypointPredictionNet(Net):
         out = self.engine().forward(observations, rnn_states, prev_actions, masks, save=False)
         B, P = out["B"], self._num_panos
         dist = CustomFixedCategorical(logits=out["logp"].clone())
-        return (dist, out["o1"].view(B, P).clone(), out["o2"].view(B, P).clone(), out["d1"].view(B, P).clone(),
-                out["d2"].view(B, P).clone(), out["x"].clone(), out["h_out"].clone())
+        shaped = lambda t: None if t is None else t.view(B, P, -1).squeeze(-1).clone()  # noqa: E731
+        return (dist, shaped(out["o1"]), shaped(out["o2"]), shaped(out["d1"]), shaped(out["d2"]), out["x"].clone(),
+                out["h_out"].clone())
 
 
 def resnet_encoders_single_frame(observation_space):
@@ -202,12 +221,30 @@ class WaypointEngine(HeadEngine):
             w.max_distance_prediction - w.min_distance_prediction, w.min_distance_prediction,
             w.max_distance_var - w.min_distance_var, w.min_distance_var, net.offset_scale,
             1.0 / w.offset_temperature, w.max_offset_var - w.min_offset_var, w.min_offset_var])
+        self.nd = 0 if w.continuous_distance else int(w.discrete_distances)   # classes of a discrete head (0 = continuous)
+        self.no = 0 if w.continuous_offset else int(w.discrete_offsets)
+        self.to_cont = net.to_continuous_consts()
         self.act_consts = _host_floats([w.min_distance_prediction, w.max_distance_prediction, math.pi / self.P,
-                                        float(bool(w.predict_distance)), float(bool(w.predict_offset))])
+                                        float(bool(w.predict_distance)), float(bool(w.predict_offset)), self.nd, self.no,
+                                        *self.to_cont])
 
     def heads(self):
-        n = self.net
-        return (n.distance_linear[0], n.distance_var_linear[0], n.offset_linear[0], n.offset_var_linear[0])
+        """(raw column, parameter prefix, Linear) of the scalar heads feeding ``wp_head_raw`` (continuous components)."""
+        n, out = self.net, []
+        if self.nd == 0:
+            out += [(0, "distance_linear.0", n.distance_linear[0]), (1, "distance_var_linear.0", n.distance_var_linear[0])]
+        if self.no == 0:
+            out += [(2, "offset_linear.0", n.offset_linear[0]), (3, "offset_var_linear.0", n.offset_var_linear[0])]
+        return out
+
+    def class_heads(self):
+        """(buffer name, parameter prefix, Linear, classes) of the categorical heads (discrete components)."""
+        n, out = self.net, []
+        if self.nd:
+            out.append(("wp_dlog", "distance_linear", n.distance_linear, self.nd))
+        if self.no:
+            out.append(("wp_olog", "offset_linear", n.offset_linear, self.no))
+        return out
 
     # ------------------------------------------------------------------ forward
     def forward(self, observations, rnn_states, prev_actions: Dict[str, torch.Tensor], masks, save: bool, critic=None):
@@ -268,7 +305,8 @@ class WaypointEngine(HeadEngine):
         p_off = prev_actions["offset"].reshape(-1).float().contiguous()
         p_dist = prev_actions["distance"].reshape(-1).float().contiguous()
         C.vlnce_wp_prev_action(ptr(pano), ptr(p_off), ptr(p_dist), ptr(masks_f), off(state_in, self.rgb_out),
-                               self.state_in, off(xcat, self.col_prev), self.xcat, B, P, 0.0, 1.0, 0.0, 1.0, st)
+                               self.state_in, off(xcat, self.col_prev), self.xcat, B, P, float(self.to_cont[2]),
+                               float(self.to_cont[3]), float(self.to_cont[0]), float(self.to_cont[1]), st)
 
         # ---- visual-history GRU inputs (:396-405)
         rgb_pm = self.buf("wp_rgb_pm", (B, self.c_rgb))  # mean over the 12 pano frames (Linear and means commute)
@@ -364,11 +402,20 @@ class WaypointEngine(HeadEngine):
         linear(ptr(x_out), H, ptr(lin.weight), off(logp, P), P + 1, ptr(lin.bias), B, 1, H)
         C.vlnce_log_softmax_rows(ptr(logp), B, P + 1, st)
         raw = self.buf("wp_head_raw", (B * P, 4))
-        for h, lin in enumerate(self.heads()):
+        if self.nd or self.no:
+            raw.zero_()  # columns of a discrete component stay unused
+        for h, _, lin in self.heads():
             linear(ptr(catted), self.cat, ptr(lin.weight), off(raw, h), 4, ptr(lin.bias), B * P, 1, self.cat)
         d1, d2 = self.buf("wp_d1", (B * P,)), self.buf("wp_d2", (B * P,))
         o1, o2 = self.buf("wp_o1", (B * P,)), self.buf("wp_o2", (B * P,))
         C.vlnce_wp_head_act_fwd(ptr(raw), ptr(d1), ptr(d2), ptr(o1), ptr(o2), B * P, ctypes.addressof(self.head_consts), st)
+        for name, _, lin, ncls in self.class_heads():  # categorical heads: raw logits (B*P, classes)
+            lg = self.buf(name, (B * P, ncls))
+            linear(ptr(catted), self.cat, ptr(lin.weight), ptr(lg), ncls, ptr(lin.bias), B * P, ncls, self.cat)
+        if self.nd:
+            d1, d2 = self.buf("wp_dlog", (B * P, self.nd)), None
+        if self.no:
+            o1, o2 = self.buf("wp_olog", (B * P, self.no)), None
         values = None
         if critic is not None:
             values = self.buf("wp_values", (B, 1))
@@ -401,16 +448,28 @@ class WaypointEngine(HeadEngine):
         linear_dx(ptr(d_values), 1, ptr(critic.fc.weight), ptr(dx_out), H, B, 1, H)
         # 2. the four heads: activations, then Linear(cat -> 1) each
         raw, graw = b("wp_head_raw", (B * P, 4)), b("wp_d_head_raw", (B * P, 4))
-        C.vlnce_wp_head_act_bwd(ptr(raw), ptr(d_d1), ptr(d_d2), ptr(d_o1), ptr(d_o2), ptr(graw), B * P,
+        zeros = b("wp_zeros", (B * P,))
+        if self.nd or self.no:
+            zeros.zero_()
+        C.vlnce_wp_head_act_bwd(ptr(raw), ptr(zeros if self.nd else d_d1), ptr(zeros if self.nd else d_d2),
+                                ptr(zeros if self.no else d_o1), ptr(zeros if self.no else d_o2), ptr(graw), B * P,
                                 ctypes.addressof(self.head_consts), st)
         d_catted = b("wp_d_catted", (B * P, self.cat))
-        names = ("distance_linear", "distance_var_linear", "offset_linear", "offset_var_linear")
-        for h, (nm, lin) in enumerate(zip(names, self.heads())):
+        first = True
+        for h, nm, lin in self.heads():
             with leaves():
-                linear_dw(off(graw, h), 4, ptr(catted), self.cat, ptr(g[f"net.{nm}.0.weight"]), self.cat, B * P, 1, self.cat)
-                _colsum(off(graw, h), 4, ptr(g[f"net.{nm}.0.bias"]), B * P, 1)
+                linear_dw(off(graw, h), 4, ptr(catted), self.cat, ptr(g[f"net.{nm}.weight"]), self.cat, B * P, 1, self.cat)
+                _colsum(off(graw, h), 4, ptr(g[f"net.{nm}.bias"]), B * P, 1)
             linear_dx(off(graw, h), 4, ptr(lin.weight), ptr(d_catted), self.cat, B * P, 1, self.cat,
-                      beta=0.0 if h == 0 else 1.0)
+                      beta=0.0 if first else 1.0)
+            first = False
+        for (_, nm, lin, ncls), dlg in zip(self.class_heads(), [t for t, n_ in ((d_d1, self.nd), (d_o1, self.no)) if n_]):
+            with leaves():
+                linear_dw(ptr(dlg), ncls, ptr(catted), self.cat, ptr(g[f"net.{nm}.weight"]), self.cat, B * P, ncls, self.cat)
+                _colsum(ptr(dlg), ncls, ptr(g[f"net.{nm}.bias"]), B * P, ncls)
+            linear_dx(ptr(dlg), ncls, ptr(lin.weight), ptr(d_catted), self.cat, B * P, ncls, self.cat,
+                      beta=0.0 if first else 1.0)
+            first = False
         # 3. pano/stop logits
         lin = net.stop_linear
         with leaves():
@@ -661,9 +720,11 @@ class WaypointPolicy(Policy):
                 else:
                     actions.append({"action": {"action": "GO_TOWARD_POINT", "action_args": {"r": r, "theta": theta}}})
             col = lambda j: f[:, j:j + 1].clone()  # noqa: E731
-            action_elements = {"pano": pano_stop, "offset": col(0), "distance": col(1)}
-            variances = {"distance": col(3), "offset": col(4)}
-            modes = {"offset": col(5), "distance": col(6)}
+            cls = lambda t, n_: t.long() if n_ else t  # noqa: E731  (categorical heads emit int64 class indices)
+            var = lambda t, n_: t.reshape(-1) if n_ else t  # noqa: E731  (torch's Categorical.variance is (B,))
+            action_elements = {"pano": pano_stop, "offset": cls(col(0), eng.no), "distance": cls(col(1), eng.nd)}
+            variances = {"distance": var(col(3), eng.nd), "offset": var(col(4), eng.no)}
+            modes = {"offset": cls(col(5), eng.no), "distance": cls(col(6), eng.nd)}
             dist = CustomFixedCategorical(logits=out["logp"].clone())
             return (out["values"].clone(), actions, action_elements, modes, variances, col(2), out["h_out"].clone(), dist)
 
@@ -696,19 +757,39 @@ class WaypointPolicy(Policy):
             evc = ev.clone()
             v, lp, hp, ho, hd, h = (out["values"].clone(), evc[:, 0:1], evc[:, 1], evc[:, 2], evc[:, 3],
                                     out["h_out"].clone())
+        # W4 (waypoint_policy.py:318-325): for a categorical head the reference multiplies its (B,1) mask with the
+        # (B,) entropy -> a (B,B) matrix mask_i * H_j (no-op squeeze); reproduced with a broadcasting view
+        eng = self.net.engine()
+        if eng.no or eng.nd:
+            go = (action_components["pano"].reshape(-1, 1) != eng.P).to(lp.dtype)
+            if eng.no:
+                ho = (go * float(bool(self.wypt_cfg.predict_offset))) * ho.view(1, -1)
+            if eng.nd:
+                hd = (go * float(bool(self.wypt_cfg.predict_distance))) * hd.view(1, -1)
         return v, lp, {"pano": hp, "offset": ho, "distance": hd}, h
 
     def _backward_from_upstream(self, eng, g, acts, upstream, d_values):
         """(B,4) upstream gradients of {log-prob, entropies} -> net-output gradients -> the net's backward."""
         B, P = eng.ctx["B"], eng.P
         bufs = self._grad_buffers(eng, B, P)
-        C.vlnce_wp_eval_bwd(ptr(eng.buf("wp_logits", (B, P + 1))), ptr(eng.buf("wp_o1", (B * P,))),
-                            ptr(eng.buf("wp_o2", (B * P,))), ptr(eng.buf("wp_d1", (B * P,))),
-                            ptr(eng.buf("wp_d2", (B * P,))), ptr(acts[0]), ptr(acts[1]), ptr(acts[2]), ptr(upstream), B, P,
-                            ctypes.addressof(eng.act_consts), *(ptr(t) for t in bufs), lib.stream())
+        o1, o2, d1, d2 = self._head_outputs(eng, B, P)
+        C.vlnce_wp_eval_bwd(ptr(eng.buf("wp_logits", (B, P + 1))), ptr(o1), ptr(o2), ptr(d1), ptr(d2), ptr(acts[0]),
+                            ptr(acts[1]), ptr(acts[2]), ptr(upstream), B, P, ctypes.addressof(eng.act_consts),
+                            *(ptr(t) for t in bufs), lib.stream())
         eng.backward(g, self.critic, *bufs, d_values)
 
     @staticmethod
+    def _head_outputs(eng, B, P):
+        """The head-output buffers of the last forward: (o1, o2, d1, d2); a categorical head has its logits in
+        the first slot and no second tensor."""
+        o1, o2 = ((eng.buf("wp_olog", (B * P, eng.no)), None) if eng.no
+                  else (eng.buf("wp_o1", (B * P,)), eng.buf("wp_o2", (B * P,))))
+        d1, d2 = ((eng.buf("wp_dlog", (B * P, eng.nd)), None) if eng.nd
+                  else (eng.buf("wp_d1", (B * P,)), eng.buf("wp_d2", (B * P,))))
+        return o1, o2, d1, d2
+
+    @staticmethod
     def _grad_buffers(eng, B, P):
-        return (eng.buf("wp_d_raw", (B, P + 1)), eng.buf("wp_g_o1", (B * P,)), eng.buf("wp_g_o2", (B * P,)),
-                eng.buf("wp_g_d1", (B * P,)), eng.buf("wp_g_d2", (B * P,)))
+        """(d_raw, d_o1, d_o2, d_d1, d_d2); categorical heads: (B*P, classes) logit gradients in the first slot."""
+        return (eng.buf("wp_d_raw", (B, P + 1)), eng.buf("wp_g_o1", (B * P, max(eng.no, 1))), eng.buf("wp_g_o2", (B * P,)),
+                eng.buf("wp_g_d1", (B * P, max(eng.nd, 1))), eng.buf("wp_g_d2", (B * P,)))
