@@ -38,7 +38,9 @@ class BufferPool:
         nbytes = numel * torch.empty((), dtype=dtype).element_size()
         b = self._bufs.get(name)
         if b is None or b.numel() < nbytes:
-            b = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+            # host memory only exists in the CPU dry-run walks of the launch plans (tests): keep those deterministic
+            alloc = torch.zeros if torch.device(self.device).type == "cpu" else torch.empty
+            b = alloc(max(nbytes, 256), dtype=torch.uint8, device=self.device)
             self._bufs[name] = b
         return b[:nbytes].view(dtype).view(*shape)
 
