@@ -274,6 +274,11 @@ int vlnce_il_loss(const float* logp, const long long* actions, const float* weig
 int vlnce_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                     float beta2, float eps, int step, const int* step_dev, float grad_scale,
                     cudaStream_t stream);
+/* Inflection weights (dagger_trainer.py:199-211, recollection_dataset.py:251-263) on the padded time-major
+ * (T,N) oracle-action matrix of collate_fn: coef where the action changes and at t = 0, 1 elsewhere, 0 where
+ * t >= lengths[n] (lengths may be NULL: no padding). */
+int vlnce_inflection_weights(const long long* actions, const int* lengths, float* weights, int T, int N, float coef,
+                             cudaStream_t stream);
 /* device-resident step counter for graph replays; y += alpha * x for gradient accumulation
  * (loss_accumulation_scalar, base_il_trainer.py:170-176) */
 int vlnce_counter_add(int* counter, int value, cudaStream_t stream);

@@ -685,3 +685,17 @@ def _wp_eval_bwd(self, logp, o1, o2, d1, d2, a_pano, a_offset, a_distance, upstr
 
 
 Emulator.wp_eval_bwd = _wp_eval_bwd
+
+
+def _inflection_weights(self, actions, lengths, weights, T, N, coef, st):
+    a = _flat(actions, T * N, I64).reshape(T, N)
+    w = _flat(weights, T * N).reshape(T, N)
+    infl = np.ones((T, N), bool)
+    infl[1:] = a[1:] != a[:-1]
+    v = np.where(infl, coef, 1.0)
+    if lengths:
+        v = v * (np.arange(T)[:, None] < _flat(lengths, N, I32)[None, :])
+    w[...] = v
+
+
+Emulator.inflection_weights = _inflection_weights

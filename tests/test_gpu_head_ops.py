@@ -138,3 +138,29 @@ def test_small_layout_ops():
     lens = torch.empty(3, dtype=torch.int32, device=DEV)
     C.vlnce_token_lengths(ptr(ids), ptr(lens), 3, 4, lib.stream())
     assert lens.tolist() == [2, 0, 4]
+
+
+def test_inflection_weights_and_device_collate():
+    """the inflection-weight kernel on the padded (T,N) matrix == the reference's per-trajectory rule
+    (dagger_trainer.py:199-211) followed by collate_fn's zero padding; collate_fn itself on device tensors."""
+    from oracle import vlnce as oracle_vlnce
+    from vlnce_b200 import collate
+
+    g = torch.Generator().manual_seed(12)
+    batch = []
+    for _ in range(37):
+        t = int(torch.randint(2, 41, (1,), generator=g))
+        a = torch.randint(0, 4, (t,), generator=g)
+        prev = torch.cat([torch.zeros(1, dtype=torch.int64), a[:-1]])
+        batch.append(({"rgb_features": torch.rand(t, 6, generator=g)}, prev, a, oracle_vlnce.inflection_weights(a, 1.9)))
+    want = oracle_vlnce.collate_fn(batch)
+    dev_batch = [({k: v.to(DEV) for k, v in o.items()}, p.to(DEV), a.to(DEV), w.to(DEV)) for o, p, a, w in batch]
+    got = collate.collate_fn(dev_batch)
+    assert torch.equal(got[0]["rgb_features"].cpu(), want[0]["rgb_features"])
+    for a, b in zip(got[1:], want[1:]):
+        assert a.is_cuda and torch.equal(a.cpu(), b)
+    lengths = torch.tensor([b[1].shape[0] for b in batch])
+    w = collate.inflection_weights(got[3], 1.9, lengths)
+    assert torch.equal(w.cpu(), want[4])
+    single = collate.inflection_weights(batch[0][2].to(DEV), 3.2)
+    assert torch.equal(single.cpu(), oracle_vlnce.inflection_weights(batch[0][2], 3.2))

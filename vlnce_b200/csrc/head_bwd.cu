@@ -374,6 +374,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 __global__ void counter_add_kernel(int* c, int v) { *c += v; }
 
+// Inflection weights of teacher-forcing trajectories (dagger_trainer.py:199-211, recollection_dataset.py:251-263)
+// on the padded (T, N) action matrix collate_fn builds: w[t,n] = coef where the oracle action changes (and at
+// t = 0), 1 elsewhere, 0 on the padding (t >= lengths[n], what collate_fn's zero fill gives).
+__global__ void inflection_weights_kernel(const long long* __restrict__ actions, const int* __restrict__ lengths,
+                                          float* __restrict__ w, int T, int N, float coef) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= T * N) return;
+  const int t = idx / N, n = idx % N;
+  float v = 0.f;
+  if (lengths == nullptr || t < lengths[n]) v = (t == 0 || actions[idx] != actions[idx - N]) ? coef : 1.f;
+  w[idx] = v;
+}
+
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
@@ -384,6 +397,14 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
 }  // namespace vlnce
 
 using namespace vlnce;
+
+extern "C" int vlnce_inflection_weights(const long long* actions, const int* lengths, float* weights, int T, int N,
+                                        float coef, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(actions && weights && T > 0 && N > 0, "inflection_weights: bad arguments");
+  inflection_weights_kernel<<<cdiv((long long)T * N, 256), 256, 0, stream>>>(actions, lengths, weights, T, N, coef);
+  VLNCE_LAUNCH_CHECK("inflection_weights_kernel");
+  return VLNCE_OK;
+}
 
 extern "C" int vlnce_counter_add(int* counter, int value, cudaStream_t stream) {
   VLNCE_CHECK_ARG(counter, "counter_add: null");
