@@ -172,6 +172,14 @@ int vlnce_adaptive_avgpool(const void* x, int dtype, float* y, int ldy, int N, i
 int vlnce_nchw_to_positions(const float* x, float* y, int ldy, int N, int C, int P,
                             cudaStream_t stream);
 
+/* ResizeShortestEdge (habitat_baselines v0.1.7 image_resize_shortest_edge, F.interpolate "area")
+ * fused with the center crop of CenterCropperPerSensor (habitat_extensions/obs_transformers.py:21-87).
+ * x (N,H,W,C) -> y (N,CH,CW,C), same dtype (VLNCE_U8 | VLNCE_F32); the virtual resized image is (RH,RW), the crop
+ * window starts at (y0,x0); y_frame_stride (elements, 0 = dense) lets the caller write straight into an ObsStack /
+ * pano-stack slot (obs_transformers.py:90-145). */
+int vlnce_resize_area_crop(const void* x, void* y, int dtype, long long y_frame_stride, int N, int H, int W, int C,
+                           int RH, int RW, int y0, int x0, int CH, int CW, cudaStream_t stream);
+
 /* ---- trainable head: dense algebra --------------------------------------------------- */
 /* C[m,n] = act(sum_k A[m*lda_m + k*lda_k] * B[k*ldb_k + n*ldb_n] + bias[n] + beta*C[m,n]),
  * fp32 on CUDA cores; act 0 none / 1 ReLU / 2 tanh.  One routine for every Linear / Conv1d(k=1) of

@@ -699,3 +699,23 @@ def _inflection_weights(self, actions, lengths, weights, T, N, coef, st):
 
 
 Emulator.inflection_weights = _inflection_weights
+
+
+def _resize_area_crop(self, x, y, dtype, y_frame_stride, N, H, W, C, RH, RW, y0, x0, CH, CW, st):
+    dt = {0: F32, 2: np.uint8}[dtype]
+    xin = _flat(x, N * H * W * C, dt).reshape(N, H, W, C).astype(np.float32)
+    stride = y_frame_stride or CH * CW * C
+    out = _flat(y, (N - 1) * stride + CH * CW * C, dt)
+    for oy in range(CH):
+        ry = oy + y0
+        h0, h1 = (ry * H) // RH, ((ry + 1) * H + RH - 1) // RH
+        for ox in range(CW):
+            rx = ox + x0
+            w0, w1 = (rx * W) // RW, ((rx + 1) * W + RW - 1) // RW
+            m = xin[:, h0:h1, w0:w1, :].sum((1, 2), dtype=np.float32) / np.float32((h1 - h0) * (w1 - w0))
+            for n in range(N):
+                o = n * stride + (oy * CW + ox) * C
+                out[o:o + C] = m[n].astype(dt)
+
+
+Emulator.resize_area_crop = _resize_area_crop

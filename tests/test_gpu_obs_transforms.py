@@ -1,0 +1,64 @@
+"""SURVEY §8(f) N1 on the GPU: the fused ResizeShortestEdge + CenterCropperPerSensor kernel at the RxR sensor size
+(480x640, ``rxr_vlnce_english_task.yaml:15-26``) against the CPU oracle (torch ``F.interpolate(mode="area")`` + crop):
+uint8 bit-exact, fp32 within 1e-6; achieved HBM bandwidth printed against the kernel's algorithmic bytes."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import obs_transforms as oracle_ot
+from vlnce_b200 import obs_transforms as ot
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def frames(n, h=480, w=640, seed=6):
+    g = torch.Generator().manual_seed(seed)
+    return {"rgb": torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8),
+            "depth": torch.rand(n, h, w, 1, generator=g)}
+
+
+@pytest.mark.parametrize("n,h,w,size,crops", [(3, 480, 640, 256, {"rgb": (224, 224), "depth": (256, 256)}),
+                                               (2, 97, 133, 64, {"rgb": (50, 40), "depth": (64, 64)}),
+                                               (2, 256, 256, 224, {"rgb": (224, 224), "depth": (200, 224)})])
+def test_fused_resize_crop_matches_oracle(n, h, w, size, crops):
+    f = frames(n, h, w)
+    want = oracle_ot.apply_obs_transforms_batch(dict(f), [oracle_ot.ResizeShortestEdge(size),
+                                                          oracle_ot.CenterCropperPerSensor(list(crops.items()))])
+    got = ot.apply_obs_transforms_batch({k: v.to(DEV) for k, v in f.items()},
+                                        [ot.ResizeShortestEdge(size), ot.CenterCropperPerSensor(list(crops.items()))])
+    torch.cuda.synchronize()
+    assert got["rgb"].dtype == torch.uint8 and torch.equal(got["rgb"].cpu(), want["rgb"])
+    torch.testing.assert_close(got["depth"].cpu(), want["depth"], rtol=0, atol=1e-6)
+    # un-fused use of the single classes + writing into a stack slot
+    r = ot.ResizeShortestEdge(size)({"rgb": f["rgb"].to(DEV)})["rgb"]
+    assert torch.equal(r.cpu(), oracle_ot.image_resize_shortest_edge(f["rgb"], size, True))
+    ch, cw = crops["rgb"]
+    dst = torch.zeros(n, 2, ch, cw, 3, dtype=torch.uint8, device=DEV)
+    ot.resize_area_crop(f["rgb"].to(DEV), size, (ch, cw), out=dst[:, 1])
+    assert torch.equal(dst[:, 1].cpu(), want["rgb"]) and int(dst[:, 0].sum()) == 0
+
+
+def test_resize_crop_bandwidth():
+    n = 64
+    f = {k: v.to(DEV) for k, v in frames(n).items()}
+    tr = [ot.ResizeShortestEdge(256), ot.CenterCropperPerSensor([("rgb", (224, 224)), ("depth", (256, 256))])]
+    for _ in range(3):
+        ot.apply_obs_transforms_batch(dict(f), tr)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        ot.apply_obs_transforms_batch(dict(f), tr)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 20
+    # algorithmic bytes: the source pixels under the crop window once + the output (rgb u8, depth f32)
+    src = lambda ch, cw, bpp: (ch * 480 / 256) * (cw * 640 / 341) * bpp  # noqa: E731
+    by = n * (src(224, 224, 3) + 224 * 224 * 3 + src(256, 256, 4) + 256 * 256 * 4)
+    res = {"ms_per_batch64": ms, "frames_per_s": n / (ms * 1e-3), "algorithmic_GBps": by / (ms * 1e-3) / 1e9}
+    print("resize+crop 64 x (480x640 rgb u8 + depth f32):", json.dumps(res))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/obs_transforms_bw.json", "w"))
+    assert ms < 5.0

@@ -868,3 +868,75 @@ extern "C" int vlnce_groupnorm_fused16(const void* x, const float* gamma, const 
   VLNCE_LAUNCH_CHECK("gn_apply_kernel");
   return VLNCE_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// SURVEY 8(f) N1 — observation transforms in front of the policy: ResizeShortestEdge (habitat_baselines v0.1.7
+// obs_transformers.py / utils/common.py image_resize_shortest_edge: F.interpolate(mode="area") = adaptive average
+// pooling, result cast back to the input dtype) fused with CenterCropperPerSensor
+// (habitat_extensions/obs_transformers.py:21-87, hb center_crop): only the cropped window of the resized image is
+// ever computed.  NHWC in, NHWC out; uint8 stays uint8 (truncating cast, bit-exact: the window sums are exact
+// integers), fp32 stays fp32.  One thread per output element, channel-fastest (coalesced stores; the loads of
+// neighbouring threads hit the same 128-B lines).  HBM-bound: reads each source pixel of the crop window once.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CC>
+__global__ void resize_area_crop_kernel(const T* __restrict__ x, T* __restrict__ y, long long y_frame_stride, int N,
+                                        int H, int W, int RH, int RW, int y0, int x0, int CH, int CW) {
+  // one thread per output PIXEL (all CC channels): the source window is (h1-h0) runs of (w1-w0)*CC contiguous elements
+  const long long total = (long long)N * CH * CW;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % CW);
+    const int oy = (int)((idx / CW) % CH);
+    const int n = (int)(idx / ((long long)CW * CH));
+    const int ry = oy + y0, rx = ox + x0;  // position in the (virtual) resized image
+    const int h0 = (int)(((long long)ry * H) / RH), h1 = (int)((((long long)ry + 1) * H + RH - 1) / RH);
+    const int w0 = (int)(((long long)rx * W) / RW), w1 = (int)((((long long)rx + 1) * W + RW - 1) / RW);
+    float acc[CC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) acc[c] = 0.f;
+    for (int ih = h0; ih < h1; ++ih) {
+      const T* row = x + (((size_t)n * H + ih) * W + w0) * CC;
+      for (int k = 0; k < (w1 - w0); ++k) {
+#pragma unroll
+        for (int c = 0; c < CC; ++c) acc[c] += (float)row[k * CC + c];
+      }
+    }
+    const float cnt = (float)((h1 - h0) * (w1 - w0));
+    T* o = y + (size_t)n * y_frame_stride + ((size_t)oy * CW + ox) * CC;
+#pragma unroll
+    for (int c = 0; c < CC; ++c) o[c] = (T)(acc[c] / cnt);
+  }
+}
+
+extern "C" int vlnce_resize_area_crop(const void* x, void* y, int dtype, long long y_frame_stride, int N, int H, int W,
+                                      int C, int RH, int RW, int y0, int x0, int CH, int CW, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && RH > 0 && RW > 0, "resize_area_crop: bad arguments");
+  VLNCE_CHECK_ARG(y0 >= 0 && x0 >= 0 && CH > 0 && CW > 0 && y0 + CH <= RH && x0 + CW <= RW,
+                  "resize_area_crop: crop window outside the resized image");
+  if (y_frame_stride == 0) y_frame_stride = (long long)CH * CW * C;
+  VLNCE_CHECK_ARG(C >= 1 && C <= 4, "resize_area_crop: 1..4 channels (C=%d)", C);
+  const long long total = (long long)N * CH * CW;
+#define VLNCE_RAC(T, CC)                                                                                      \
+  resize_area_crop_kernel<T, CC><<<grid_for(total, 128), 128, 0, stream>>>((const T*)x, (T*)y, y_frame_stride, N, H, W, \
+                                                                           RH, RW, y0, x0, CH, CW)
+#define VLNCE_RAC_C(T)                        \
+  switch (C) {                                \
+    case 1: VLNCE_RAC(T, 1); break;           \
+    case 2: VLNCE_RAC(T, 2); break;           \
+    case 3: VLNCE_RAC(T, 3); break;           \
+    default: VLNCE_RAC(T, 4); break;          \
+  }
+  if (dtype == VLNCE_U8) {
+    VLNCE_RAC_C(unsigned char)
+  } else if (dtype == VLNCE_F32) {
+    VLNCE_RAC_C(float)
+  } else {
+    set_error("resize_area_crop: dtype must be u8 or f32");
+    return VLNCE_ERR_INVALID_ARGUMENT;
+  }
+#undef VLNCE_RAC_C
+#undef VLNCE_RAC
+  VLNCE_LAUNCH_CHECK("resize_area_crop_kernel");
+  return VLNCE_OK;
+}
