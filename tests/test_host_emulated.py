@@ -166,3 +166,47 @@ def test_fused_wddppo_update_matches_oracle_loop(name):
         if p.requires_grad:
             # Adam's first steps move every weight by ~lr regardless of the gradient's size: compare the UPDATE
             torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=4e-5, msg=lambda m: f"{k}: {m}")
+
+
+# ---------------------------------------------------------------------------------------------
+# fused imitation-learning step (the benchmarked path): ILTrainerStep.update_agent on the emulator against the
+# restated ``_update_agent`` + torch Adam (common/base_il_trainer.py:134-180)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,accum", [("cma_train_features", 1), ("cma_rxr_train_features", 1),
+                                        ("seq2seq_train_features", 1), ("cma_train_features_nopm", 2)])
+def test_fused_il_step_matches_oracle_update(name, accum):
+    from oracle import vlnce as oracle_vlnce
+    from vlnce_b200.il_step import ILTrainerStep
+
+    case = cases.CASES[name]
+    impl = cases.oracle_impl(case)
+    opol = cases.build_policy(impl, case)
+    cases.set_mode(opol, case)
+    opt = torch.optim.Adam([p for p in opol.parameters() if p.requires_grad], lr=2.5e-4)
+    aux = oracle_vlnce.AuxLosses
+    aux.activate()
+    batch = cases.inputs(case)
+    want = []
+    for k in range(accum):
+        want.append(oracle_vlnce.update_agent(opol, opt, *batch, step_grad=(k == accum - 1),
+                                              loss_accumulation_scalar=accum, aux=aux))
+    aux.deactivate()
+
+    pol = cases.build_policy(vlnce_b200, case)
+    cases.set_mode(pol, case)
+    vlnce_b200.AuxLosses.activate()
+    step = ILTrainerStep(pol, lr=2.5e-4)
+    got = []
+    with lib.dry_run(executor=Emulator()):
+        for k in range(accum):
+            got.append(step.update_agent(*batch, step_grad=(k == accum - 1), loss_accumulation_scalar=accum))
+    vlnce_b200.AuxLosses.deactivate()
+    torch.testing.assert_close(torch.tensor(got), torch.tensor(want), rtol=2e-5, atol=1e-6)
+    ref = dict(opol.named_parameters())
+    moved = 0
+    for k, p in pol.named_parameters():
+        if p.requires_grad:
+            # first Adam step: |update| ~ lr wherever the gradient is not tiny; a wrong sign shows as 2*lr
+            torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=5e-5, msg=lambda m: f"{k}: {m}")
+            moved += 1
+    assert moved >= 10
