@@ -161,3 +161,67 @@ def test_waypoint_ppo_world2_equals_single_process():
     assert abs(res[0][3] - want_norm) < 1e-4 * want_norm
     mean_losses = (res[0][2] + res[1][2]) / 2          # per-rank means over equal shards
     assert np.allclose(mean_losses[1:5], want_losses.numpy()[1:5], rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# imitation-learning step (the benchmarked path): the same NUMERICAL data-parallel identity
+# ---------------------------------------------------------------------------------------------
+def _il_grad(world, rank):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    import vlnce_b200
+    from abi_emulator import Emulator
+    from oracle import cases
+    from vlnce_b200 import dist as vdist, il_step, lib
+
+    case = dict(cases.CASES["cma_train_features_nopm"], n=4)
+    pol = cases.build_policy(vlnce_b200, case).eval()
+    full = cases.inputs(case)
+    batch = vdist.shard_batch(full, rank, world) if world > 1 else full
+    step = il_step.ILTrainerStep(pol, lr=1e-3)
+    assert step.world == world
+    before = None
+    with lib.dry_run(executor=Emulator()) as rec:
+        step.compute_grads(*batch)
+        local = step.fp.grad.clone()
+        before = step.fp.flat.clone()
+        step.apply_grads(True)
+    assert rec.calls[-1] == "vlnce_adam_step"
+    return step.fp.grad.clone() / world, local, step.fp.flat.clone() - before, step._losses.clone()
+
+
+def _il_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    avg, local, delta, losses = _il_grad(world, rank)
+    out.put((rank, avg.numpy(), local.numpy(), delta.numpy(), losses.numpy()))
+    dist.destroy_process_group()
+
+
+def test_il_step_world2_equals_single_process():
+    """ILTrainerStep on two ranks (2 of 4 trajectories each): the all-reduced gradient with the 1/world factor folded
+    into Adam equals the single-process gradient of the whole batch (per-trajectory weighted means, equal shards,
+    ``base_il_trainer.py:159-165``), and both replicas apply the same parameter update."""
+    import numpy as np
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_il_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    want_grad, _, want_delta, want_losses = _il_grad(1, 0)
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][3], res[1][3])   # replicas in lock-step
+    assert not np.array_equal(res[0][2], res[1][2])                                       # ...from different shards
+    scale = float(want_grad.abs().max())
+    assert float(np.abs(res[0][1] - want_grad.numpy()).max()) < 2e-5 * scale
+    assert float(np.abs(res[0][3] - want_delta.numpy()).max()) < 2e-5        # same Adam update (lr 1e-3)
+    assert abs((res[0][4][1] + res[1][4][1]) / 2 - float(want_losses[1])) < 1e-5 * abs(float(want_losses[1]))
