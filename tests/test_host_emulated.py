@@ -210,3 +210,37 @@ def test_fused_il_step_matches_oracle_update(name, accum):
             torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=5e-5, msg=lambda m: f"{k}: {m}")
             moved += 1
     assert moved >= 10
+
+
+def test_pipelined_loop_plan_equals_plain_loop():
+    """Host logic of the pipelined training loop (ILTrainerStep.pipelined_step: visual features of batch i+1 into
+    the 'next' slot while batch i trains from the 'cur' slot, then rotate) on the emulator with cached features:
+    bit-identical losses and parameters to the plain sequential loop (the emulator is deterministic)."""
+    from vlnce_b200 import synth
+    from vlnce_b200.il_step import ILTrainerStep
+
+    case = dict(cases.CASES["cma_train_features"], t=2, n=3)
+    batches = [synth.make_train_batch(700 + i, 2, 3, length=16, features=True) for i in range(3)]
+    VIS = ("rgb_features", "depth_features")
+
+    def make():
+        pol = cases.build_policy(vlnce_b200, case).eval()
+        return pol, ILTrainerStep(pol, lr=1e-3)
+
+    aux = vlnce_b200.AuxLosses
+    aux.activate()
+    with lib.dry_run(executor=Emulator()):
+        _, st_a = make()
+        plain = [st_a.update_agent(*b) for b in batches]
+        _, st_b = make()
+        st_b._prepare()
+        st_b.prefetch_visual(batches[0][0])
+        st_b.rotate_visual(batches[0][1].shape[0])
+        piped = []
+        for i, b in enumerate(batches):
+            nxt = {k: batches[(i + 1) % len(batches)][0][k] for k in VIS}
+            obs_nv = {k: v for k, v in b[0].items() if k not in VIS}
+            piped.append(st_b.pipelined_step(obs_nv, b[1], b[2], b[3], b[4], nxt).tolist())
+    aux.deactivate()
+    torch.testing.assert_close(torch.tensor(piped), torch.tensor(plain), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(st_b.fp.flat, st_a.fp.flat, rtol=0, atol=1e-7)
