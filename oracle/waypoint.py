@@ -22,8 +22,6 @@ and frozen in ``tests/golden/wp_*.pt``.  Reference quirks that are kept on purpo
 from __future__ import annotations
 
 import math
-from collections import defaultdict
-
 import numpy as np
 import torch
 import torch.nn as nn

@@ -11,7 +11,6 @@ import math
 import os
 import warnings
 
-import numpy as np
 import pytest
 import torch
 

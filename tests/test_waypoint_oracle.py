@@ -7,7 +7,7 @@ import warnings
 import pytest
 import torch
 
-from oracle import hb017, reference_import, waypoint
+from oracle import reference_import, waypoint
 
 warnings.filterwarnings("ignore")
 GOLD = os.path.join(os.path.dirname(__file__), "golden")

@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 import torch
@@ -39,7 +39,6 @@ from .policy import CategoricalNet
 PREV_ACTION_DIM = 4
 PANO_ATTN_KEY_DIM = 128
 ANGLE_FEATURE_SIZE = 4
-F4 = 4
 
 
 def _host_floats(vals):
