@@ -1,7 +1,7 @@
 #!/bin/bash
 # Full GPU suite (default launch mode), then the conv/policy/train/waypoint suites and the bench with
 # programmatic dependent launch on, for an A/B.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export VLNCE_AUTOTUNE_CACHE=/tmp/vlnce_tune.json
 tools/gpu_checks.sh tests/test_gpu_conv.py tests/test_gpu_head_ops.py tests/test_gpu_policy.py tests/test_gpu_train.py tests/test_gpu_waypoint.py 2>&1 | grep -v "^PASSED"

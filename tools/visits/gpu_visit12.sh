@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU visit: NCCL gradient all-reduce test + the torchrun bench at N=2 (weak scaling check).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export VLNCE_AUTOTUNE_CACHE=/tmp/vlnce_tune.json
 nvidia-smi --query-gpu=name --format=csv,noheader | head -4

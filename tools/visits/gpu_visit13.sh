@@ -1,6 +1,6 @@
 #!/bin/bash
 # Experiment: leave a few SMs free of the persistent RGB conv CTAs so the depth trunk runs beside them.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export VLNCE_AUTOTUNE_CACHE=/tmp/vlnce_tune.json
 ( timeout 400 python tools/perf_probe.py --caps 0,140,132,124,116,104 ) > gpurun_out/phases_caps.log 2>&1; echo "probe exit $?"; grep -E "^cap|rgb_trunk" gpurun_out/phases_caps.log | cut -c1-400

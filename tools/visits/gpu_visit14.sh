@@ -1,6 +1,6 @@
 #!/bin/bash
 # Experiment: depth trunk as independent batch chunks on parallel streams.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export VLNCE_AUTOTUNE_CACHE=/tmp/vlnce_tune.json
 ( timeout 500 python tools/perf_probe.py --chunks 1,2,4,8 ) > gpurun_out/phases_chunks.log 2>&1; echo "probe exit $?"; grep -E "^chunks|rgb_trunk|Error|error" gpurun_out/phases_chunks.log | cut -c1-300

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Experiment: fp16 raw conv output under GroupNorm (depth trunk traffic).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export VLNCE_AUTOTUNE_CACHE=/tmp/vlnce_tune.json
 for r in 0 1; do

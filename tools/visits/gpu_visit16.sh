@@ -1,6 +1,6 @@
 #!/bin/bash
 # Experiment: constant max-shared carve-out for the chained kernels (no SM reconfiguration between kernels).
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export VLNCE_AUTOTUNE_CACHE=/tmp/vlnce_tune.json
 for r in 0 1; do

@@ -1,6 +1,6 @@
 #!/bin/bash
 # waypoint GPU tests (after the test fix) + ncu --set full captures of RGB-trunk conv tiles in situ.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export VLNCE_AUTOTUNE_CACHE=/tmp/vlnce_tune.json
 tools/gpu_checks.sh tests/test_gpu_waypoint.py 2>&1 | grep -v "^PASSED"

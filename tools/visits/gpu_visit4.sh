@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L="stem,l3.c1 1x1 1024,l2.c2 3x3 128,l1.c3,l3.c2 3x3 256,l1.c1 1x1 256"
 run() { echo "=== $1"; shift; ( env "$@" timeout 200 python tools/conv_layers.py --reps 10 --only "$L" 2>&1 | grep -v "^sum" | sed -E 's/bn(32|64|128|256):[^b]*//g' ) ; }

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_conv.py -m gpu -q -x --timeout 120 -p no:cacheprovider -k "tma or s2d" > gpurun_out/t_conv_new.log 2>&1
 echo "new conv tests exit $?"; tail -5 gpurun_out/t_conv_new.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Evidence refresh for the conv_tma v3 kernel mix: launch list of one eager step + two ncu --set full
 # captures of the dominant RGB-trunk tiles (3x3 and 1x1+residual).  Outputs under gpurun_out/.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export VLNCE_AUTOTUNE_CACHE=/tmp/vlnce_tune.json
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/gpu.txt 2>&1
