@@ -46,6 +46,16 @@ CASES = {
                         iseed=109, bn_train=False, rxr=768, actions=6),
     "cma_rxr_train_features": dict(policy="CMAPolicy", pm=True, kind="train", t=3, n=3, hw=256, length=40, wseed=20,
                                    iseed=110, bn_train=False, features=True, rxr=768, actions=6, coef=1.9),
+    # modality ablations (config/default.py:217-219; the paper's ablation studies)
+    "cma_train_features_abl_i": dict(policy="CMAPolicy", pm=True, kind="train", t=3, n=3, hw=256, length=24, wseed=31,
+                                     iseed=131, bn_train=False, features=True, ablate=("instruction",)),
+    "cma_train_features_abl_v": dict(policy="CMAPolicy", pm=False, kind="train", t=3, n=3, hw=256, length=24, wseed=32,
+                                     iseed=132, bn_train=False, features=True, ablate=("rgb", "depth")),
+    "seq2seq_train_features_abl": dict(policy="Seq2SeqPolicy", pm=False, kind="train", t=3, n=3, hw=256, length=24,
+                                       wseed=33, iseed=133, bn_train=False, features=True, prev_action=True,
+                                       ablate=("instruction", "rgb")),
+    "wp_eval_abl": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=34, iseed=134,
+                        ablate=("instruction", "depth")),
     # Waypoint path (BASELINE config C4 dims, 1-wpn-cc.yaml): act on a fresh/continuing env pair,
     # and one PPO mini-batch (evaluate_actions -> WDDPPO losses -> gradients)
     "wp_act": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=40, wseed=21, iseed=201),
@@ -81,11 +91,12 @@ def oracle_impl(case):
 
 
 def model_config(case) -> hb017.Config:
+    abl = {"ablate_" + k: True for k in case.get("ablate", ())}
     if case["policy"] == "WaypointPolicy":
         from . import waypoint
 
-        return waypoint.waypoint_model_config(WAYPOINT=dict(case.get("waypoint", {})))
-    over = dict(PROGRESS_MONITOR=dict(use=bool(case["pm"]), alpha=1.0))
+        return waypoint.waypoint_model_config(WAYPOINT=dict(case.get("waypoint", {})), **abl)
+    over = dict(PROGRESS_MONITOR=dict(use=bool(case["pm"]), alpha=1.0), **abl)
     if case.get("rxr"):  # rxr_cma_en.yaml:43-48
         over["INSTRUCTION_ENCODER"] = dict(sensor_uuid="rxr_instruction", embedding_size=int(case["rxr"]))
     if case["policy"] == "CMAPolicy":

@@ -154,10 +154,12 @@ def seq2seq_backward(eng, head_linear, g: Dict[str, torch.Tensor], d_raw: Option
                   width, masks_f, T, N, ptr(d_xin), width, leaves)
     # instruction final state -> its token's output gradient -> LSTM BPTT (own stream)
     with Branch("lstm_bwd") as br_lstm:
-        d_instr = b("d_instr", (R, L, Hs))
-        C.vlnce_scatter_last_token(ptr(d_xin), width, ptr(cx["lengths"]), ptr(d_instr), R, L, Hs, lib.stream())
-        instruction_backward(eng, g, d_instr)
-    # depth fc | rgb fc: ReLU'(y) then dW, db (inputs saved by the forward)
+        if not net.model_config.get("ablate_instruction", False):  # ``instruction_embedding * 0`` stops the gradient
+            d_instr = b("d_instr", (R, L, Hs))
+            C.vlnce_scatter_last_token(ptr(d_xin), width, ptr(cx["lengths"]), ptr(d_instr), R, L, Hs, lib.stream())
+            instruction_backward(eng, g, d_instr)
+    # depth fc | rgb fc: ReLU'(y) then dW, db (inputs saved by the forward).  An ablated slice was cleared in the
+    # forward, so ReLU' = 0 there and its fc gradients come out exactly 0, as in the reference.
     C.vlnce_relu_bwd(off(d_xin, Hs), width, off(xin, Hs), width, R, d_out + r_out, st)
     c, h, w = net.depth_encoder.visual_encoder.output_shape
     dep_flat = b("s2s_depth_flat", (R, c * h * w))
@@ -276,9 +278,11 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
         linear_dw(ptr(d_q_s), hk, ptr(xcat), eng.cat, ptr(g["net.state_q.weight"]), H, R, hk, H)
         _colsum(ptr(d_q_s), hk, ptr(g["net.state_q.bias"]), R, hk)
     linear_dx(ptr(d_q_s), hk, ptr(net.state_q.weight), ptr(dxcat), eng.cat, R, hk, H, beta=1.0)
+    cfg = net.model_config
     with Branch("lstm_bwd") as br_lstm:
         # 12. instruction encoder (BPTT) — independent of steps 8-11: own stream
-        instruction_backward(eng, g, d_instr)
+        if not cfg.get("ablate_instruction", False):  # ``instruction_embedding * 0``: nothing flows upstream
+            instruction_backward(eng, g, d_instr)
 
     # 8. first GRU (dh = dxcat[:, :H])
     d_state_in = b("d_state_in", (R, eng.state_in))
@@ -311,10 +315,12 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
                                   off(d_state_in, eng.rgb_out + eng.depth_out), eng.state_in,
                                   ptr(g["net.prev_action_embedding.weight"]), R, 32, pa_w.shape[0], st)
     # 11. spatial embeddings
-    C.vlnce_spatial_embed_grad(ptr(dE["rgb"]), P * eng.Crgb, eng.Crgb, c_rgb, None, 0, ptr(d_mean_sp), 64,
-                               ptr(g["net.rgb_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
-    C.vlnce_spatial_embed_grad(ptr(dE["depth"]), P * eng.Cdep, eng.Cdep, c_dep, ptr(d_flat_sp), 64 * P, None, 0,
-                               ptr(g["net.depth_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
+    if not cfg.get("ablate_rgb", False):
+        C.vlnce_spatial_embed_grad(ptr(dE["rgb"]), P * eng.Crgb, eng.Crgb, c_rgb, None, 0, ptr(d_mean_sp), 64,
+                                   ptr(g["net.rgb_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
+    if not cfg.get("ablate_depth", False):
+        C.vlnce_spatial_embed_grad(ptr(dE["depth"]), P * eng.Cdep, eng.Cdep, c_dep, ptr(d_flat_sp), 64 * P, None, 0,
+                                   ptr(g["net.depth_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
     br_lstm.join()
     leaves.join()
 

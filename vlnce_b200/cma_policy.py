@@ -87,9 +87,6 @@ class CMANet(Net):
         if model_config.PROGRESS_MONITOR.use:
             nn.init.kaiming_normal_(self.progress_monitor.weight, nonlinearity="tanh")
             nn.init.constant_(self.progress_monitor.bias, 0)
-        for flag in ("ablate_instruction", "ablate_depth", "ablate_rgb"):
-            if model_config.get(flag, False):
-                raise NotImplementedError(f"MODEL.{flag}=True is not built (ablation study switch)")
         self.precision = "bf16"  # conv-trunk arithmetic: "bf16" (tcgen05) | "fp32" (CUDA cores)
         self.train()
 

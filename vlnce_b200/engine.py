@@ -291,6 +291,13 @@ class CMAEngine(HeadEngine):
                                    P * self.Cdep, self.Cdep, c_dep, R, P, 64, st)
         C.vlnce_spatial_embed_fill(ptr(net.rgb_encoder.spatial_embeddings.weight), ptr(rgb_e), P * self.Crgb,
                                    self.Crgb, c_rgb, R, P, 64, st)
+        cfg = net.model_config
+        # modality ablations (cma_policy.py:237-242): ``embedding * 0`` — the buffers are cleared; the backward
+        # leaves the gradients of everything upstream of a cleared embedding at zero (backward.cma_backward)
+        if cfg.get("ablate_depth", False):
+            dep_e.zero_()
+        if cfg.get("ablate_rgb", False):
+            rgb_e.zero_()
         self.ctx["rgb_e"], self.ctx["dep_e"] = rgb_e, dep_e
 
         # ---- prev-action embedding into both concat slices (cma_policy.py:233-235, Q6)
@@ -321,6 +328,8 @@ class CMAEngine(HeadEngine):
 
         # ---- text attention (cma_policy.py:258-263)
         br_instr.join()
+        if net.model_config.get("ablate_instruction", False):
+            instr.zero_()
         if "scale" not in self.__dict__:
             self.scale = float(net._scale)  # one host sync, cached
         scale = self.scale

@@ -70,6 +70,13 @@ class Seq2SeqEngine(HeadEngine):
             pa = net.prev_action_embedding.weight
             C.vlnce_prev_action_embed(ptr(prev), ptr(masks_f), ptr(pa), off(xin, width - 32), width, None, 0, R, 32,
                                       pa.shape[0], st)
+        # modality ablations (seq2seq_policy.py:147-152): the encoder OUTPUTS are multiplied by 0
+        if cfg.get("ablate_instruction", False):
+            xin[:, :Hs].zero_()
+        if cfg.get("ablate_depth", False):
+            xin[:, Hs:Hs + d_out].zero_()
+        if cfg.get("ablate_rgb", False):
+            xin[:, Hs + d_out:Hs + d_out + r_out].zero_()
         x_out = self.buf("x_out", (R, H))
         h_out = self.buf("rnn_states_out", (N, 1, H))
         self._gru_forward("gru", net.state_encoder.rnn, ptr(xin), width, width, ptr(rnn_states), H, masks_f,
@@ -109,9 +116,6 @@ class Seq2SeqNet(Net):
         self.progress_monitor = nn.Linear(model_config.STATE_ENCODER.hidden_size, 1)
         nn.init.kaiming_normal_(self.progress_monitor.weight, nonlinearity="tanh")
         nn.init.constant_(self.progress_monitor.bias, 0)
-        for flag in ("ablate_instruction", "ablate_depth", "ablate_rgb"):
-            if model_config.get(flag, False):
-                raise NotImplementedError(f"MODEL.{flag}=True is not built (ablation study switch)")
         self.precision = "bf16"
         self.train()
 

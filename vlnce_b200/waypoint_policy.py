@@ -75,9 +75,6 @@ class WaypointPredictionNet(Net):
         nn.Module.__init__(self)
         cfg = self.model_config = model_config
         w = self.wypt_cfg = model_config.WAYPOINT
-        for flag in ("ablate_instruction", "ablate_depth", "ablate_rgb"):
-            if cfg.get(flag, False):
-                raise NotImplementedError(f"MODEL.{flag}=True is not built (ablation study switch)")
         H = self._hidden_size = cfg.STATE_ENCODER.hidden_size
         self._num_panos = cfg.num_panos
         rgb_out, dep_out = cfg.RGB_ENCODER.output_size, cfg.DEPTH_ENCODER.output_size
@@ -293,6 +290,11 @@ class WaypointEngine(HeadEngine):
         C.vlnce_spatial_embed_fill(ptr(net.rgb_encoder.spatial_embeddings.weight), ptr(rgb_e), S * self.Crgb,
                                    self.Crgb, self.c_rgb, F, S, 64, st)
         br_depth.join()
+        cfg = net.model_config  # modality ablations (waypoint_predictors.py:400-407): embeddings AND history * 0
+        if cfg.get("ablate_rgb", False):
+            rgb_e.zero_()
+        if cfg.get("ablate_depth", False):
+            dep_e.zero_()
         hist_rgb = off(rgb_e, B * P * S * self.Crgb)   # history frames: rows [B*P, B*P+B)
         hist_dep = off(dep_e, B * P * S * self.Cdep)
 
@@ -332,6 +334,8 @@ class WaypointEngine(HeadEngine):
 
         # ---- instruction attention (:419-424), quirk W1 -> xcat[:, 0:Di]
         br_instr.join()
+        if cfg.get("ablate_instruction", False):
+            instr.zero_()
         q1 = self.buf("wp_q1", (B, hk))
         lin = net.inst_attn_q[0]
         linear(off(xcat, self.col_hist), self.xcat, ptr(lin.weight), ptr(q1), hk, ptr(lin.bias), B, hk, H, act=1)
@@ -575,8 +579,10 @@ class WaypointEngine(HeadEngine):
             linear_dw(ptr(d_q1), hk, off(xcat, self.col_hist), self.xcat, ptr(g["net.inst_attn_q.0.weight"]), H, B, hk, H)
             _colsum(ptr(d_q1), hk, ptr(g["net.inst_attn_q.0.bias"]), B, hk)
         linear_dx(ptr(d_q1), hk, ptr(lin.weight), off(dxcat, self.col_hist), self.xcat, B, hk, H, beta=1.0)
+        cfg = net.model_config
         with Branch("lstm_bwd") as br_lstm:
-            instruction_backward(self, g, d_instr)
+            if not cfg.get("ablate_instruction", False):  # ``instruction_embedding *= 0``: nothing flows upstream
+                instruction_backward(self, g, d_instr)
         # 12. visual-history GRU
         d_state_in = b("wp_d_state_in", (B, self.state_in))
         _gru_backward(self, "wp_vgru", net.visual_rnn.rnn, "net.visual_rnn.rnn.", g, off(dxcat, self.col_hist), self.xcat,
@@ -608,12 +614,14 @@ class WaypointEngine(HeadEngine):
                   ldw=self.Cdep * S)
         # 14. spatial-embedding tables: attention source (all pano frames) + the history-frame branches
         g_rgb, g_dep = g["net.rgb_encoder.spatial_embeddings.weight"], g["net.depth_encoder.spatial_embeddings.weight"]
-        C.vlnce_spatial_embed_grad(ptr(dE["rgb"]), S * self.Crgb, self.Crgb, self.c_rgb, None, 0, None, 0, ptr(g_rgb), 0,
-                                   B * P, S, 64, st)
-        C.vlnce_spatial_embed_grad(None, 0, 0, 0, None, 0, ptr(d_mean_sp), 64, ptr(g_rgb), 1, B, S, 64, st)
-        C.vlnce_spatial_embed_grad(ptr(dE["dep"]), S * self.Cdep, self.Cdep, self.c_dep, None, 0, None, 0, ptr(g_dep), 0,
-                                   B * P, S, 64, st)
-        C.vlnce_spatial_embed_grad(None, 0, 0, 0, ptr(d_flat_sp), 64 * S, None, 0, ptr(g_dep), 1, B, S, 64, st)
+        if not cfg.get("ablate_rgb", False):
+            C.vlnce_spatial_embed_grad(ptr(dE["rgb"]), S * self.Crgb, self.Crgb, self.c_rgb, None, 0, None, 0, ptr(g_rgb),
+                                       0, B * P, S, 64, st)
+            C.vlnce_spatial_embed_grad(None, 0, 0, 0, None, 0, ptr(d_mean_sp), 64, ptr(g_rgb), 1, B, S, 64, st)
+        if not cfg.get("ablate_depth", False):
+            C.vlnce_spatial_embed_grad(ptr(dE["dep"]), S * self.Cdep, self.Cdep, self.c_dep, None, 0, None, 0, ptr(g_dep),
+                                       0, B * P, S, 64, st)
+            C.vlnce_spatial_embed_grad(None, 0, 0, 0, ptr(d_flat_sp), 64 * S, None, 0, ptr(g_dep), 1, B, S, 64, st)
         br_lstm.join()
         leaves.join()
 
