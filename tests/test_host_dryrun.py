@@ -108,3 +108,21 @@ def test_seq2seq_act_launch_sequence_and_keys():
         action, h_out = pol.act(obs, h, prev, masks, deterministic=True)
     assert action.shape == (2, 1) and h_out.shape == (2, 1, 512)
     assert sum(c.startswith("vlnce_conv") for c in rec.calls) == 107
+
+
+@pytest.mark.parametrize("name", ["wp_act", "wp_eval", "wp_act_dd"])
+def test_waypoint_launch_sequence(name):
+    """WaypointPolicy from raw pixels: one ResNet-18 + one DD-PPO ResNet-50 pass over the stacked
+    [12 pano | history] frames per call, every C-ABI call validated against the header."""
+    with lib.dry_run() as rec:
+        got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses)
+    n_conv = sum(c.startswith("vlnce_conv") for c in rec.calls)
+    passes = 2 if name.startswith("wp_act") else 1          # act + get_value | evaluate_actions
+    assert n_conv == passes * (20 + 54), n_conv
+    assert rec.calls.count("vlnce_wp_stack_frames") == 2 * passes
+    assert rec.calls.count("vlnce_wp_inst_attn_fwd") == passes and rec.calls.count("vlnce_layernorm_fwd") == passes
+    if name == "wp_eval":
+        assert rec.calls.count("vlnce_wp_eval_bwd") == 1 and rec.calls.count("vlnce_lstm_seq_bwd") == 1
+        assert any(k.startswith("grad/net.pano_attn") for k in got)
+    else:
+        assert rec.calls.count("vlnce_wp_act") == 1
