@@ -126,3 +126,20 @@ def test_waypoint_launch_sequence(name):
         assert any(k.startswith("grad/net.pano_attn") for k in got)
     else:
         assert rec.calls.count("vlnce_wp_act") == 1
+
+
+@pytest.mark.parametrize("name", ["cma_act", "cma_rxr_act", "seq2seq_train_features", "wp_act", "wp_act_dc", "wp_act_dd"])
+def test_checkpoint_surface_matches_oracle(name):
+    """Checkpoint compatibility: the CUDA policy exposes exactly the reference's ``state_dict`` keys,
+    shapes and ``requires_grad`` flags (the oracle is pinned to the reference's key list in
+    tests/test_oracle_vs_reference.py), and a reference-style checkpoint round-trips through ``load_state_dict``."""
+    case = cases.CASES[name]
+    ref = cases.build_policy(cases.oracle_impl(case), case)
+    pol = cases.build_policy(vlnce_b200, case)
+    rs, ps = ref.state_dict(), pol.state_dict()
+    assert list(ps) == list(rs)
+    assert all(ps[k].shape == rs[k].shape and ps[k].dtype == rs[k].dtype for k in rs)
+    rg = {k: p.requires_grad for k, p in ref.named_parameters()}
+    assert {k: p.requires_grad for k, p in pol.named_parameters()} == rg
+    pol.load_state_dict(rs, strict=True)
+    assert all(torch.equal(pol.state_dict()[k], rs[k]) for k in rs)

@@ -27,9 +27,9 @@ def test_oracle_equals_reference_live(name):
 
 def test_state_dict_keys_match_reference():
     ref = reference_import.load()
-    for name in ("cma_act", "seq2seq_act"):
+    for name in ("cma_act", "seq2seq_act", "cma_rxr_act", "wp_act", "wp_act_dc", "wp_act_dd"):
         case = cases.CASES[name]
         r = cases.build_policy(ref, case).state_dict()
-        o = cases.build_policy(vlnce, case).state_dict()
+        o = cases.build_policy(cases.oracle_impl(case), case).state_dict()
         assert list(r) == list(o)
         assert all(r[k].shape == o[k].shape for k in r)
