@@ -143,3 +143,26 @@ def test_checkpoint_surface_matches_oracle(name):
     assert {k: p.requires_grad for k, p in pol.named_parameters()} == rg
     pol.load_state_dict(rs, strict=True)
     assert all(torch.equal(pol.state_dict()[k], rs[k]) for k in rs)
+
+
+def test_ddppo_depth_checkpoint_mapping(tmp_path):
+    """``MODEL.DEPTH_ENCODER.ddppo_checkpoint`` (resnet_encoders.py:48-61): keys ``actor_critic.net.visual_encoder.*``
+    of a DD-PPO checkpoint are stripped to the encoder's own names and loaded strictly; everything else is ignored."""
+    from oracle import vlnce as oracle_vlnce
+    from oracle import hb017
+
+    case = cases.CASES["cma_act"]
+    donor = cases.build_policy(vlnce_b200, case)
+    enc_sd = donor.net.depth_encoder.visual_encoder.state_dict()
+    ckpt = {"state_dict": {"actor_critic.net.visual_encoder." + k: v + 1.0 for k, v in enc_sd.items()}}
+    ckpt["state_dict"]["actor_critic.net.state_encoder.rnn.weight_ih_l0"] = torch.zeros(3)   # not part of the encoder
+    path = str(tmp_path / "ddppo.pth")
+    torch.save(ckpt, path)
+    mc = cases.model_config(case)
+    mc.DEPTH_ENCODER.ddppo_checkpoint = path
+    cfg = hb017.Config(MODEL=mc, TORCH_GPU_ID=0, TASK_CONFIG=dict(TASK=dict(PANO_ROTATIONS=12)))
+    pol = vlnce_b200.CMAPolicy.from_config(cfg, cases.obs_space(case), hb017.Discrete(4))
+    got = pol.net.depth_encoder.visual_encoder.state_dict()
+    assert list(got) == list(enc_sd)
+    assert all(torch.equal(got[k], enc_sd[k] + 1.0) for k in enc_sd)
+    assert not any(p.requires_grad for p in pol.net.depth_encoder.visual_encoder.parameters())
