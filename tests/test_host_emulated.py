@@ -245,3 +245,20 @@ def test_pipelined_loop_plan_equals_plain_loop():
     aux.deactivate()
     torch.testing.assert_close(torch.tensor(piped), torch.tensor(plain), rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(st_b.fp.flat, st_a.fp.flat, rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("base,t,n,length", [("cma_train_features", 1, 1, 3), ("cma_train_features", 7, 1, 80),
+                                             ("seq2seq_train_features", 1, 2, 1), ("cma_rxr_train_features", 2, 1, 5)])
+def test_edge_shapes_match_oracle(base, t, n, length):
+    """Smallest / most lopsided batches (one row, one trajectory, one-token instructions): the launch plan against
+    the oracle run live on the same seeded inputs."""
+    name = f"_edge_{base}_{t}_{n}_{length}"
+    cases.CASES[name] = dict(cases.CASES[base], t=t, n=n, length=length)
+    try:
+        want = cases.run_case(cases.oracle_impl(cases.CASES[name]), name, aux=__import__("oracle.vlnce", fromlist=["x"]).AuxLosses)
+        with lib.dry_run(executor=Emulator()):
+            got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses)
+    finally:
+        del cases.CASES[name]
+    assert set(got) == set(want)
+    print(name, "worst", check(got, want, 3e-4))
