@@ -262,3 +262,21 @@ def test_edge_shapes_match_oracle(base, t, n, length):
         del cases.CASES[name]
     assert set(got) == set(want)
     print(name, "worst", check(got, want, 3e-4))
+
+
+@pytest.mark.parametrize("base,over", [("wp_eval", dict(t=1, n=1, length=3)), ("wp_act", dict(n=1, length=2)),
+                                       ("wp_eval_dd", dict(t=4, n=1, length=9))])
+def test_waypoint_edge_shapes_match_oracle(base, over):
+    from oracle import waypoint as oracle_wp
+
+    name = "_edge_" + base + "_".join(f"{k}{v}" for k, v in over.items())
+    cases.CASES[name] = dict(cases.CASES[base], **over)
+    try:
+        case = cases.CASES[name]
+        want = cases.run_case(oracle_wp, name)
+        with lib.dry_run(executor=Emulator()):
+            got = cases.run_case(_Impl(case), name, aux=vlnce_b200.AuxLosses)
+    finally:
+        del cases.CASES[name]
+    assert set(got) == set(want)
+    print(name, "worst", check(got, want, 3e-4))

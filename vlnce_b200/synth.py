@@ -225,7 +225,7 @@ def make_waypoint_eval_batch(seed: int, t: int, n: int, hidden: int = 256, layer
     obs = make_waypoint_rows(gen, r, length=length, instruction=instr, **kw)
     h0 = torch.randn(n, layers, hidden, generator=gen) * 0.5
     actions = make_waypoint_actions(gen, r, classes=classes)
-    actions["pano"][1] = 12  # make sure a STOP row is covered
+    actions["pano"][min(1, r - 1)] = 12  # make sure a STOP row is covered
     prev = {k: torch.zeros_like(v) for k, v in actions.items()}
     for k in actions:
         prev[k][n:] = actions[k][:-n]
