@@ -280,3 +280,56 @@ def test_waypoint_edge_shapes_match_oracle(base, over):
         del cases.CASES[name]
     assert set(got) == set(want)
     print(name, "worst", check(got, want, 3e-4))
+
+
+def test_recollect_style_loop_matches_oracle():
+    """BASELINE config C3 shape family at reduced size: the RecollectTrainer teacher-forcing loop
+    (``recollect_trainer.py:128-185``) — ragged trajectories -> collate_fn -> ``_update_agent`` with gradient
+    accumulation (``loss_accumulation_scalar = effective_batch_size // batch_size`` and the reference's
+    ``step_grad = bool(step_id % scalar)`` pattern).  Product side: device-style collate + inflection-weight kernel +
+    fused ILTrainerStep on the emulator; oracle side: the restated collate_fn / update_agent with torch Adam."""
+    from oracle import vlnce as oracle_vlnce
+    from vlnce_b200 import collate
+    from vlnce_b200.il_step import ILTrainerStep
+
+    case = dict(cases.CASES["cma_train_features"], pm=True)
+    g = torch.Generator().manual_seed(77)
+
+    def trajectory():
+        t = int(torch.randint(2, 7, (1,), generator=g))
+        obs = {"rgb_features": torch.rand(t, 2048, 4, 4, generator=g), "depth_features": torch.rand(t, 128, 4, 4, generator=g),
+               "instruction": torch.randint(1, 2504, (1, 12), generator=g).expand(t, 12).contiguous(),
+               "progress": torch.rand(t, 1, generator=g)}
+        actions = torch.randint(0, 4, (t,), generator=g)
+        prev = torch.cat([torch.zeros(1, dtype=torch.int64), actions[:-1]])
+        return obs, prev, actions
+    batches = [[trajectory() for _ in range(3)] for _ in range(4)]   # 4 micro-batches of 3 trajectories
+    scalar = 2                                                       # effective_batch_size 6 // batch_size 3
+
+    opol = cases.build_policy(oracle_vlnce, case).eval()
+    opt = torch.optim.Adam([p for p in opol.parameters() if p.requires_grad], lr=2.5e-4)
+    oracle_vlnce.AuxLosses.activate()
+    want = []
+    for step_id, trajs in enumerate(batches):
+        b = oracle_vlnce.collate_fn([(o, p, a, oracle_vlnce.inflection_weights(a, 3.2)) for o, p, a in trajs])
+        want.append(oracle_vlnce.update_agent(opol, opt, *b, step_grad=bool(step_id % scalar),
+                                              loss_accumulation_scalar=scalar, aux=oracle_vlnce.AuxLosses))
+    oracle_vlnce.AuxLosses.deactivate()
+
+    pol = cases.build_policy(vlnce_b200, case).eval()
+    vlnce_b200.AuxLosses.activate()
+    step = ILTrainerStep(pol, lr=2.5e-4)
+    got = []
+    with lib.dry_run(executor=Emulator()):
+        for step_id, trajs in enumerate(batches):
+            lengths = torch.tensor([a.shape[0] for _, _, a in trajs])
+            obs, prev, masks, actions, _ = collate.collate_fn([(o, p, a, torch.zeros(a.shape[0])) for o, p, a in trajs])
+            weights = collate.inflection_weights(actions, 3.2, lengths)   # one launch on the padded (T,N) matrix
+            got.append(step.update_agent(obs, prev, masks, actions, weights, step_grad=bool(step_id % scalar),
+                                         loss_accumulation_scalar=scalar))
+    vlnce_b200.AuxLosses.deactivate()
+    torch.testing.assert_close(torch.tensor(got), torch.tensor(want), rtol=3e-5, atol=1e-6)
+    ref = dict(opol.named_parameters())
+    for k, p in pol.named_parameters():
+        if p.requires_grad:
+            torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=1e-4, msg=lambda m: f"{k}: {m}")
