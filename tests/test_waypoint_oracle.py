@@ -171,3 +171,19 @@ if __name__ == "__main__":  # freeze the fixtures from the UNMODIFIED reference 
     torch.save({k: torch.tensor([float(v.double().sum()), float(v.double().abs().sum()), float(v.numel())])
                 for k, v in so.items()}, os.path.join(GOLD, "wp_storage.pt"))
     print("frozen", len(so), "storage tensors")
+
+
+def test_select_history_frames_equals_reference_loop():
+    """``ddppo_waypoint_trainer.py:190-199`` restated as the reference writes it (per-env loop) vs the batched gather."""
+    from vlnce_b200.ppo_step import select_history_frames
+
+    g = torch.Generator().manual_seed(2)
+    obs = {"rgb": torch.rand(5, 12, 4, 4, 3, generator=g), "depth": torch.rand(5, 12, 6, 6, 1, generator=g)}
+    pano = torch.tensor([[3], [12], [0], [11], [12]])
+    want = {"rgb": torch.zeros_like(obs["rgb"][:, 0]), "depth": torch.zeros_like(obs["depth"][:, 0])}
+    for i in range(5):
+        if int(pano[i]) != 12:                      # actions[i]["action"] != "STOP"
+            want["rgb"][i] = obs["rgb"][i, int(pano[i])]
+            want["depth"][i] = obs["depth"][i, int(pano[i])]
+    got = select_history_frames(obs, pano, 12)
+    assert torch.equal(got["rgb"], want["rgb"]) and torch.equal(got["depth"], want["depth"])

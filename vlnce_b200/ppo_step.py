@@ -205,3 +205,20 @@ class WDDPPOStep:
         n = self.ppo_epoch * self.num_mini_batch
         v = (acc / n).tolist()
         return v[1], v[2], v[3], v[5], v[6], v[7]
+
+
+def select_history_frames(step_observation: Dict[str, torch.Tensor], pano_stop: torch.Tensor, num_panos: int,
+                          keys=("rgb", "depth")) -> Dict[str, torch.Tensor]:
+    """The observation-history frames of the next step (``ddppo_waypoint_trainer.py:190-199``): for every env that
+    did not STOP, the pano frame it moved towards; zeros otherwise.  The reference loops over the envs with a
+    ``.item()`` each; this is one batched gather per sensor (data movement only, no host sync)."""
+    idx = pano_stop.reshape(-1).long()
+    go = idx != num_panos
+    sel = torch.where(go, idx, torch.zeros_like(idx))
+    out = {}
+    for k in keys:
+        frames = step_observation[k]                                   # (N, P, H, W, C)
+        n = frames.shape[0]
+        picked = frames[torch.arange(n, device=frames.device), sel]     # (N, H, W, C)
+        out[k] = torch.where(go.view(n, 1, 1, 1), picked, torch.zeros_like(picked))
+    return out
