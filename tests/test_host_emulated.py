@@ -333,3 +333,69 @@ def test_recollect_style_loop_matches_oracle():
     for k, p in pol.named_parameters():
         if p.requires_grad:
             torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=1e-4, msg=lambda m: f"{k}: {m}")
+
+
+def test_ddppo_collect_and_update_loop_matches_oracle():
+    """BASELINE config C4 shape family at reduced size: the DD-PPO waypoint loop of
+    ``ddppo_waypoint_trainer.py:140-300,470-560`` with a synthetic environment — ``act`` (deterministic, so both
+    sides take the same actions) -> history-frame gather -> ``rollouts.insert`` -> ``get_value`` -> GAE ->
+    ``WDDPPO.update``.  Product: WaypointPolicy / device storage / fused WDDPPOStep on the emulator; oracle: the
+    restated policy, storage and update loop."""
+    from oracle import waypoint as oracle_wp
+    from vlnce_b200 import synth
+    from vlnce_b200.ppo_step import ActionDictRolloutStorage, WDDPPOStep, select_history_frames
+
+    case = cases.CASES["wp_eval"]
+    T, N, L = 2, 2, 10
+    space = oracle_wp.storage_obs_space(length=L)
+    g = torch.Generator().manual_seed(31)
+    first = synth.make_waypoint_rows(g, N, length=L)
+    nxt = [synth.make_waypoint_rows(g, N, length=L) for _ in range(T)]
+    rewards = [torch.randn(N, 1, generator=g) for _ in range(T)]
+    dones = [torch.tensor([[0], [1]], dtype=torch.uint8), torch.tensor([[1], [1]], dtype=torch.uint8)]  # masks = not done
+    kw = dict(clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, offset_regularize_coef=0.1146,
+              pano_entropy_coef=1.0, offset_entropy_coef=1.0, distance_entropy_coef=1.0)
+
+    def run(pol, storage_cls, update):
+        st = storage_cls(T, N, space, 256, num_recurrent_layers=2)
+        for k in st.observations:
+            st.observations[k][0].copy_(first[k])
+        for t in range(T):
+            obs = {k: v[st.step] for k, v in st.observations.items()}
+            prev = {k: v[st.step].clone() for k, v in st.prev_actions.items()}
+            with torch.no_grad():
+                value, actions, elems, _, _, lp, h, _ = pol.act(obs, st.recurrent_hidden_states[st.step], prev,
+                                                                st.masks[st.step], deterministic=True)
+            hist = select_history_frames(obs, elems["pano"], 12)
+            batch = dict(nxt[t], rgb_history=hist["rgb"], depth_history=hist["depth"])
+            st.insert(batch, h, elems, lp, value, rewards[t], dones[t])
+        with torch.no_grad():
+            nv = pol.get_value({k: v[st.step] for k, v in st.observations.items()}, st.recurrent_hidden_states[st.step],
+                               {k: v[st.step].clone() for k, v in st.prev_actions.items()}, st.masks[st.step])
+        st.compute_returns(nv, True, 0.99, 0.95)
+        torch.manual_seed(5)
+        return st, update(pol, st)
+
+    opol = cases.build_policy(oracle_wp, case)
+    cases.set_mode(opol, case)
+    opt = torch.optim.Adam([p for p in opol.parameters() if p.requires_grad], lr=2e-4, eps=1e-5)
+    ost, want = run(opol, oracle_wp.ActionDictRolloutStorage,
+                    lambda p, s: oracle_wp.ppo_update(p, opt, s, ppo_epoch=1, num_mini_batch=2, max_grad_norm=0.2,
+                                                      use_clipped_value_loss=True, **kw))
+    pol = cases.build_policy(vlnce_b200, case)
+    cases.set_mode(pol, case)
+    substitute_trunks(pol, case)
+    with lib.dry_run(executor=Emulator()):
+        agent = WDDPPOStep(pol, ppo_epoch=1, num_mini_batch=2, lr=2e-4, eps=1e-5, max_grad_norm=0.2,
+                           use_clipped_value_loss=True, **kw)
+        st, got = run(pol, ActionDictRolloutStorage, lambda p, s: agent.update(s))
+    for name in ("returns", "value_preds", "action_log_probs", "rewards", "recurrent_hidden_states"):
+        torch.testing.assert_close(getattr(st, name), getattr(ost, name), rtol=1e-4, atol=1e-5, msg=lambda m: f"{name}: {m}")
+    for k in st.actions:
+        torch.testing.assert_close(st.actions[k], ost.actions[k], rtol=1e-4, atol=1e-5)
+    assert torch.equal(st.observations["rgb_history"], ost.observations["rgb_history"])
+    torch.testing.assert_close(torch.tensor(got), torch.tensor(want), rtol=3e-4, atol=3e-6)
+    ref = dict(opol.named_parameters())
+    for k, p in pol.named_parameters():
+        if p.requires_grad:
+            torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=5e-5, msg=lambda m: f"{k}: {m}")
