@@ -166,3 +166,43 @@ def test_ddppo_depth_checkpoint_mapping(tmp_path):
     assert list(got) == list(enc_sd)
     assert all(torch.equal(got[k], enc_sd[k] + 1.0) for k in enc_sd)
     assert not any(p.requires_grad for p in pol.net.depth_encoder.visual_encoder.parameters())
+
+
+def test_conv_autotune_picks_fastest_candidate(monkeypatch):
+    """``ConvTrunk._tune`` (GPU-only in production) with a fake event clock: every legal candidate is launched,
+    timed as the best of three bursts and the fastest one wins; the candidate set follows the layer's legality flags."""
+    from vlnce_b200 import trunk
+
+    clock = {"t": 0.0}
+    cost = {}
+
+    class FakeEvent:
+        def __init__(self, enable_timing=True):
+            self.t = None
+
+        def record(self):
+            self.t = clock["t"]
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    launched = []
+
+    def launch(code):
+        launched.append(code)
+        # persistent TMA kernel at width 128 with two pixel sub-tiles is the fastest; one burst of it is noisy
+        base = 1.0 if code == (trunk.TMAP | 128 | (4 << 16) | trunk.MT2) else 2.0 + (code % 7) * 0.1
+        n = cost[code] = cost.get(code, 0) + 1
+        clock["t"] += base * (5.0 if (code & trunk.TMAP and 3 <= n <= 8) else 1.0)
+
+    best = trunk.ConvTrunk._tune(launch, 256, halo_ok=True, tma_ok=True)
+    assert best == (trunk.TMAP | 128 | (4 << 16) | trunk.MT2)
+    kinds = {("tma" if c & trunk.TMAP else "halo" if c & trunk.HALO else "umma") for c in launched}
+    assert kinds == {"tma", "halo", "umma"}
+    only_umma = []
+    trunk.ConvTrunk._tune(only_umma.append, 96)            # K not a multiple of 64: 32-wide generic tiles only
+    assert {c & 0xffff for c in only_umma} == {32}
