@@ -719,3 +719,99 @@ def _resize_area_crop(self, x, y, dtype, y_frame_stride, N, H, W, C, RH, RW, y0,
 
 
 Emulator.resize_area_crop = _resize_area_crop
+
+
+# ======================================================================================
+# conv trunks, fp32 precision mode only (``net.precision = "fp32"``: vlnce_conv2d_ref + the normalisation /
+# pooling kernels).  Modelled with torch CPU ops on tensors that alias the caller's buffers, so the trunk launch
+# plans (block wiring, residual / downsample routing, folded BatchNorm, GroupNorm, stem scaling) can be executed on
+# the host as well.  The 16-bit tensor-core paths (operand packing, TMA tiles) are GPU-only.
+# ======================================================================================
+def _tt(ptr, shape, code=0):
+    import torch
+
+    npdt = {0: F32, 2: np.uint8}[code]
+    n = int(np.prod(shape))
+    return torch.from_numpy(_flat(ptr, n, npdt)).view(*shape)
+
+
+class TrunkOps:
+    def conv2d_ref(self, x, x_dtype, w, w_dtype, scale, shift, residual, res_dtype, y, y_dtype, N, H, W, C, K, R, S,
+                   stride, pad, relu, st):
+        import torch
+        import torch.nn.functional as Fn
+
+        assert w_dtype == 0 and y_dtype == 0, "fp32 mode only"
+        xi = _tt(x, (N, H, W, C), x_dtype).float().permute(0, 3, 1, 2)
+        wt = _tt(w, (K, R, S, C)).permute(0, 3, 1, 2)
+        out = Fn.conv2d(xi.contiguous(), wt.contiguous(), stride=stride, padding=pad)   # fp32 like the kernel
+        if scale:
+            out = out * _tt(scale, (K,)).view(1, K, 1, 1) + _tt(shift, (K,)).view(1, K, 1, 1)
+        P, Q = out.shape[2], out.shape[3]
+        if residual:
+            out = out + _tt(residual, (N, P, Q, K), res_dtype).float().permute(0, 3, 1, 2)
+        if relu:
+            out = out.clamp_min(0)
+        _tt(y, (N, P, Q, K)).copy_(out.permute(0, 2, 3, 1).float())
+
+    def avgpool2x2(self, x, y, N, H, W, C, st):
+        import torch.nn.functional as Fn
+
+        _tt(y, (N, H // 2, W // 2, C)).copy_(Fn.avg_pool2d(_tt(x, (N, H, W, C)).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1))
+
+    def maxpool3x3s2(self, x, y, dtype, N, H, W, C, st):
+        import torch.nn.functional as Fn
+
+        P, Q = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        out = Fn.max_pool2d(_tt(x, (N, H, W, C), dtype).permute(0, 3, 1, 2), 3, 2, 1)
+        _tt(y, (N, P, Q, C), dtype).copy_(out.permute(0, 2, 3, 1))
+
+    def adaptive_avgpool(self, x, dtype, y, ldy, N, H, W, C, O, st):
+        import torch.nn.functional as Fn
+
+        out = Fn.adaptive_avg_pool2d(_tt(x, (N, H, W, C), dtype).permute(0, 3, 1, 2).double(), (O, O))   # (N,C,O,O)
+        _ten3(y, N, O * O, C, O * O * ldy, ldy)[...] = out.flatten(2).permute(0, 2, 1).float().numpy()
+
+    def groupnorm_fused(self, x, gamma, beta, residual, y, y_dtype, ws, wsb, sc, sh, N, HW, C, groups, eps, relu, st):
+        import torch
+        import torch.nn.functional as Fn
+
+        assert y_dtype == 0
+        xi = _tt(x, (N, HW, C)).double().permute(0, 2, 1)     # (N,C,HW)
+        out = Fn.group_norm(xi, groups, _tt(gamma, (C,)).double(), _tt(beta, (C,)).double(), eps)
+        if residual:
+            out = out + _tt(residual, (N, HW, C)).double().permute(0, 2, 1)
+        if relu:
+            out = out.clamp_min(0)
+        _tt(y, (N, HW, C)).copy_(out.permute(0, 2, 1).float())
+
+    def batchnorm_train_stats(self, x, dtype, gamma, beta, rmean, rvar, momentum, scale, shift, ws, rows, C, eps, st):
+        import torch
+
+        xi = _tt(x, (rows, C), dtype).double()
+        mean, var = xi.mean(0), xi.var(0, unbiased=False)
+        g, b = _tt(gamma, (C,)).double(), _tt(beta, (C,)).double()
+        s = g / torch.sqrt(var + eps)
+        _tt(scale, (C,)).copy_(s.float())
+        _tt(shift, (C,)).copy_((b - mean * s).float())
+        rm, rv = _tt(rmean, (C,)), _tt(rvar, (C,))
+        rm.copy_(((1 - momentum) * rm.double() + momentum * mean).float())
+        rv.copy_(((1 - momentum) * rv.double() + momentum * xi.var(0, unbiased=True)).float())
+
+    def affine_apply(self, x, x_dtype, scale, shift, scale_stride_n, residual, y, y_dtype, N, HW, C, relu, st):
+        assert x_dtype == 0 and y_dtype == 0
+        xi = _tt(x, (N, HW, C)).double()
+        if scale_stride_n:
+            sc, sh = _tt(scale, (N, 1, C)).double(), _tt(shift, (N, 1, C)).double()
+        else:
+            sc, sh = _tt(scale, (1, 1, C)).double(), _tt(shift, (1, 1, C)).double()
+        out = xi * sc + sh
+        if residual:
+            out = out + _tt(residual, (N, HW, C)).double()
+        if relu:
+            out = out.clamp_min(0)
+        _tt(y, (N, HW, C)).copy_(out.float())
+
+
+for _name in [n for n in vars(TrunkOps) if not n.startswith("_")]:
+    setattr(Emulator, _name, getattr(TrunkOps, _name))

@@ -399,3 +399,24 @@ def test_ddppo_collect_and_update_loop_matches_oracle():
     for k, p in pol.named_parameters():
         if p.requires_grad:
             torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=5e-5, msg=lambda m: f"{k}: {m}")
+
+
+# ---------------------------------------------------------------------------------------------
+# raw-pixel paths in the fp32 precision mode: the conv-trunk launch plans (trunk.py) on the emulator as well
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cma_act", "cma_act_bntrain", "cma_act_rgb224", "seq2seq_act", "cma_train_pixels"])
+def test_pixel_paths_fp32_match_golden(name):
+    """Both conv trunks from raw pixels in ``precision="fp32"`` (vlnce_conv2d_ref + GroupNorm / BatchNorm / pooling
+    kernels, modelled with torch CPU ops): block wiring, residual and downsample routing, folded eval-mode and
+    train-mode BatchNorm, the 4x4 / global pools (Q2) against the reference goldens."""
+    with lib.dry_run(executor=Emulator()):
+        got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, precision="fp32")
+    print(name, "worst", check(got, gold(name), 3e-4))
+
+
+def test_waypoint_pixel_path_fp32_matches_golden():
+    """WaypointPolicy.act from raw pano pixels (ResNet-18 + DD-PPO ResNet-50 over the stacked frames), no trunk
+    substitution."""
+    with lib.dry_run(executor=Emulator()):
+        got = cases.run_case(vlnce_b200, "wp_act", aux=vlnce_b200.AuxLosses, precision="fp32")
+    print("wp_act pixels worst", check(got, gold("wp_act"), 3e-4))
