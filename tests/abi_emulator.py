@@ -815,3 +815,184 @@ class TrunkOps:
 
 for _name in [n for n in vars(TrunkOps) if not n.startswith("_")]:
     setattr(Emulator, _name, getattr(TrunkOps, _name))
+
+
+# ======================================================================================
+# 16-bit tensor-core paths (the default ``precision="bf16"``): functional models of the tcgen05 / TMA conv entry
+# points and the 16-bit variants of the normalisation / pooling kernels.  Operands are converted to fp32, the
+# convolution runs in fp32 (the kernels accumulate in fp32 in TMEM) and the result is rounded to the output dtype.
+# What this checks on the host is the operand PACKING and routing done by trunk.py: KRSC weights, the 2x2
+# space-to-depth stem (cell image + re-indexed 4x4 weights), the padded im2col depth stem, gemm_c calls, residual
+# and norm wiring, fp16-vs-bf16 trunk dtypes.
+# ======================================================================================
+def _tt16(ptr, shape, code):
+    """torch tensor aliasing caller memory for dtype codes F32=0, BF16=1, U8=2, F16=4."""
+    import torch
+
+    n = int(np.prod(shape))
+    if code in (0, 2):
+        return _tt(ptr, shape, code)
+    ct = ctypes.c_uint16
+    raw = np.ctypeslib.as_array(ctypes.cast(int(ptr), ctypes.POINTER(ct)), shape=(n,))
+    t = torch.from_numpy(raw.view(np.int16))
+    return t.view(torch.bfloat16 if code == 1 else torch.float16).view(*shape)
+
+
+def _epilogue(out, scale, shift, residual, res_code, relu, y, y_code, shape):
+    """out (N,K,P,Q) fp32 -> y (N,P,Q,K)"""
+    N, K, P, Q = out.shape
+    if scale:
+        out = out * _tt(scale, (K,)).view(1, K, 1, 1) + _tt(shift, (K,)).view(1, K, 1, 1)
+    if residual:
+        out = out + _tt16(residual, (N, P, Q, K), res_code).float().permute(0, 3, 1, 2)
+    if relu:
+        out = out.clamp_min(0)
+    yt = _tt16(y, (N, P, Q, K), y_code)
+    yt.copy_(out.permute(0, 2, 3, 1).to(yt.dtype))
+
+
+class TensorCoreOps:
+    def conv2d_bf16(self, x, w, ab, scale, shift, residual, y, y_dtype, N, H, W, C, K, R, S, stride, pad, relu, code, st):
+        import torch.nn.functional as Fn
+
+        xi = _tt16(x, (N, H, W, C), ab).float().permute(0, 3, 1, 2).contiguous()
+        wt = _tt16(w, (K, R, S, C), ab).float().permute(0, 3, 1, 2).contiguous()
+        _epilogue(Fn.conv2d(xi, wt, stride=stride, padding=pad), scale, shift, residual, ab, relu, y, y_dtype, None)
+
+    def conv_tma(self, x, w, ab, scale, shift, residual, y, y_dtype, N, H, W, C, K, R, relu, code, st):
+        self.conv2d_bf16(x, w, ab, scale, shift, residual, y, y_dtype, N, H, W, C, K, R, R, 1, R // 2, relu, code, st)
+
+    def conv3x3_halo(self, x, w, ab, scale, shift, residual, y, y_dtype, N, H, W, C, K, relu, code, st):
+        self.conv2d_bf16(x, w, ab, scale, shift, residual, y, y_dtype, N, H, W, C, K, 3, 3, 1, 1, relu, code, st)
+
+    def stem_s2d(self, x, x_code, cells, c_code, N, H, W, st):
+        import torch
+
+        P, Q = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        Ys, Xs = P + 3, Q + 3
+        img = _tt16(x, (N, H, W, 3), x_code).float()
+        pad = torch.zeros(N, 2 * Ys, 2 * Xs, 3)
+        # cell (Y,X) holds pixels (2Y+dy-3, 2X+dx-3): shift the image by +3 into a zero canvas
+        hh, ww = min(H, 2 * Ys - 3), min(W, 2 * Xs - 3)
+        pad[:, 3:3 + hh, 3:3 + ww] = img[:, :hh, :ww]
+        c = pad.view(N, Ys, 2, Xs, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(N, Ys, Xs, 12)
+        out = _tt16(cells, (N, Ys, Xs, 16), c_code)
+        out.zero_()
+        out[..., :12] = c.to(out.dtype)
+
+    def conv_stem_tma(self, cells, w, w_code, scale, shift, y, y_dtype, N, P, Q, K, relu, code, st):
+        import torch.nn.functional as Fn
+
+        ci = _tt16(cells, (N, P + 3, Q + 3, 16), w_code).float().permute(0, 3, 1, 2).contiguous()
+        wt = _tt16(w, (K, 4, 4, 16), w_code).float().permute(0, 3, 1, 2).contiguous()
+        _epilogue(Fn.conv2d(ci, wt), scale, shift, 0, 0, relu, y, y_dtype, None)
+
+    def conv2d_stem_rgb(self, x, x_code, w, w_code, scale, shift, y, y_dtype, N, H, W, K, relu, code, st):
+        import torch.nn.functional as Fn
+
+        xi = _tt16(x, (N, H, W, 3), x_code).float().permute(0, 3, 1, 2).contiguous()
+        wt = _tt16(w, (K, 192), w_code).float()[:, :147].reshape(K, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
+        _epilogue(Fn.conv2d(xi, wt, stride=2, padding=3), scale, shift, 0, 0, relu, y, y_dtype, None)
+
+    def im2col_depth_stem(self, x, a, a_code, N, H, W, st):
+        import torch.nn.functional as Fn
+
+        d = Fn.avg_pool2d(_tt(x, (N, H, W, 1)).permute(0, 3, 1, 2), 2)                # (N,1,H/2,W/2)
+        cols = Fn.unfold(d, kernel_size=7, padding=3, stride=2)                         # (N, 49, P*Q), K index r*7+s
+        out = _tt16(a, (N * cols.shape[2], 64), a_code)
+        out.zero_()
+        out[:, :49] = cols.permute(0, 2, 1).reshape(-1, 49).to(out.dtype)
+
+    def im2col_rgb_stem(self, x, x_code, a, a_code, N, H, W, st):
+        import torch.nn.functional as Fn
+
+        img = _tt16(x, (N, H, W, 3), x_code).float().permute(0, 3, 1, 2)
+        cols = Fn.unfold(img, kernel_size=7, padding=3, stride=2)                       # (N, 3*49, PQ): index c*49+r*7+s
+        PQ = cols.shape[2]
+        cols = cols.view(N, 3, 49, PQ).permute(0, 3, 2, 1).reshape(N * PQ, 147)        # -> (r*7+s)*3+c
+        out = _tt16(a, (N * PQ, 192), a_code)
+        out.zero_()
+        out[:, :147] = cols.to(out.dtype)
+
+
+def _wrap16(name, idx_codes):
+    """re-dispatch an fp32-only model above when any dtype argument is 16-bit"""
+    return None
+
+
+# 16-bit aware versions of the normalisation / pooling models (the fp32 ones above stay as the strict checks)
+def _groupnorm_fused(self, x, gamma, beta, residual, y, y_dtype, ws, wsb, sc, sh, N, HW, C, groups, eps, relu, st):
+    import torch.nn.functional as Fn
+
+    xi = _tt(x, (N, HW, C)).double().permute(0, 2, 1)
+    out = Fn.group_norm(xi, groups, _tt(gamma, (C,)).double(), _tt(beta, (C,)).double(), eps)
+    if residual:
+        out = out + _tt16(residual, (N, HW, C), y_dtype).double().permute(0, 2, 1)
+    if relu:
+        out = out.clamp_min(0)
+    yt = _tt16(y, (N, HW, C), y_dtype)
+    yt.copy_(out.permute(0, 2, 1).to(yt.dtype))
+
+
+def _groupnorm_fused16(self, x, gamma, beta, residual, y, ws, wsb, N, HW, C, groups, eps, relu, st):
+    import torch.nn.functional as Fn
+
+    xi = _tt16(x, (N, HW, C), 4).double().permute(0, 2, 1)
+    out = Fn.group_norm(xi, groups, _tt(gamma, (C,)).double(), _tt(beta, (C,)).double(), eps)
+    if residual:
+        out = out + _tt16(residual, (N, HW, C), 4).double().permute(0, 2, 1)
+    if relu:
+        out = out.clamp_min(0)
+    yt = _tt16(y, (N, HW, C), 4)
+    yt.copy_(out.permute(0, 2, 1).to(yt.dtype))
+
+
+def _maxpool3x3s2(self, x, y, dtype, N, H, W, C, st):
+    import torch.nn.functional as Fn
+
+    P, Q = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    out = Fn.max_pool2d(_tt16(x, (N, H, W, C), dtype).float().permute(0, 3, 1, 2), 3, 2, 1)
+    yt = _tt16(y, (N, P, Q, C), dtype)
+    yt.copy_(out.permute(0, 2, 3, 1).to(yt.dtype))
+
+
+def _adaptive_avgpool(self, x, dtype, y, ldy, N, H, W, C, O, st):
+    import torch.nn.functional as Fn
+
+    out = Fn.adaptive_avg_pool2d(_tt16(x, (N, H, W, C), dtype).double().permute(0, 3, 1, 2), (O, O))
+    _ten3(y, N, O * O, C, O * O * ldy, ldy)[...] = out.flatten(2).permute(0, 2, 1).float().numpy()
+
+
+def _affine_apply(self, x, x_dtype, scale, shift, scale_stride_n, residual, y, y_dtype, N, HW, C, relu, st):
+    xi = _tt16(x, (N, HW, C), x_dtype).double()
+    shp = (N, 1, C) if scale_stride_n else (1, 1, C)
+    out = xi * _tt(scale, shp).double() + _tt(shift, shp).double()
+    if residual:
+        out = out + _tt16(residual, (N, HW, C), y_dtype).double()
+    if relu:
+        out = out.clamp_min(0)
+    yt = _tt16(y, (N, HW, C), y_dtype)
+    yt.copy_(out.to(yt.dtype))
+
+
+def _batchnorm_train_stats(self, x, dtype, gamma, beta, rmean, rvar, momentum, scale, shift, ws, rows, C, eps, st):
+    import torch
+
+    xi = _tt16(x, (rows, C), dtype).double()
+    mean, var = xi.mean(0), xi.var(0, unbiased=False)
+    s = _tt(gamma, (C,)).double() / torch.sqrt(var + eps)
+    _tt(scale, (C,)).copy_(s.float())
+    _tt(shift, (C,)).copy_((_tt(beta, (C,)).double() - mean * s).float())
+    rm, rv = _tt(rmean, (C,)), _tt(rvar, (C,))
+    rm.copy_(((1 - momentum) * rm.double() + momentum * mean).float())
+    rv.copy_(((1 - momentum) * rv.double() + momentum * xi.var(0, unbiased=True)).float())
+
+
+for _name in [n for n in vars(TensorCoreOps) if not n.startswith("_")]:
+    setattr(Emulator, _name, getattr(TensorCoreOps, _name))
+Emulator.groupnorm_fused = _groupnorm_fused
+Emulator.groupnorm_fused16 = _groupnorm_fused16
+Emulator.maxpool3x3s2 = _maxpool3x3s2
+Emulator.adaptive_avgpool = _adaptive_avgpool
+Emulator.affine_apply = _affine_apply
+Emulator.batchnorm_train_stats = _batchnorm_train_stats

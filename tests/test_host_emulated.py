@@ -420,3 +420,22 @@ def test_waypoint_pixel_path_fp32_matches_golden():
     with lib.dry_run(executor=Emulator()):
         got = cases.run_case(vlnce_b200, "wp_act", aux=vlnce_b200.AuxLosses, precision="fp32")
     print("wp_act pixels worst", check(got, gold("wp_act"), 3e-4))
+
+
+@pytest.mark.parametrize("name,tol", [("cma_act", 1e-2), ("cma_act_rgb224", 1e-2), ("cma_act_bntrain", 2e-2),
+                                      ("seq2seq_act", 1e-2), ("wp_act", 2e-2)])
+def test_pixel_paths_16bit_packing_matches_golden(name, tol):
+    """The default 16-bit trunk paths on functional models of the tensor-core entry points: what is checked on the
+    host is trunk.py's operand packing and routing — KRSC weights, the 2x2 space-to-depth RGB stem (cell image +
+    re-indexed 4x4 weights), the padded im2col depth stem (gemm_c), fp16 vs bf16 trunk dtypes, folded / batch-stat
+    norms — at the 16-bit tolerance of BASELINE.json (outputs rounded to bf16 / fp16 after every layer as on the GPU)."""
+    want = gold(name)
+    with lib.dry_run(executor=Emulator()) as rec:
+        got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, precision="bf16")
+    assert "vlnce_stem_s2d" in rec.calls and "vlnce_conv_stem_tma" in rec.calls and "vlnce_im2col_depth_stem" in rec.calls
+    assert rec.calls.count("vlnce_conv_tma") > 20
+    logits = "pano_stop_logits" if name.startswith("wp_") else "logits"
+    e_p = float((got[logits].exp() - want[logits].exp()).abs().max() / want[logits].exp().abs().max())
+    e_h = float((got["rnn_states_out"] - want["rnn_states_out"]).norm() / want["rnn_states_out"].norm())
+    print(f"{name}[16-bit, host model] rel err probs {e_p:.3e} hidden {e_h:.3e}")
+    assert e_p < tol and e_h < tol
