@@ -217,6 +217,12 @@ int vlnce_lstm_seq_fwd(const float* gx, const float* whh_f, const float* whh_b, 
 int vlnce_gru_pointwise_fwd(const float* gi, const float* gh, const float* h, long long ldh,
                             float* hout, long long ldo, float* hout2, long long ldo2, float* save,
                             int rows, int H, cudaStream_t stream);
+/* LSTM cell pointwise part (rnn_state_encoder with STATE_ENCODER.rnn_type = "LSTM", cma_policy.py:129,175;
+ * seq2seq_policy.py:112; waypoint_predictors.py:72,160): gates i,f,g,o from gi + gh (rows,4H), c = mask-reset cell
+ * state; writes h', c' (and optional second copies into the rnn_states_out slots); save (rows,5H) for the backward. */
+int vlnce_lstm_pointwise_fwd(const float* gi, const float* gh, const float* c, long long ldc, float* hout,
+                             long long ldo, float* cout, long long ldco, float* hout2, float* cout2, long long ldo2,
+                             float* save, int rows, int H, cudaStream_t stream);
 /* out = h * mask[row]  (hidden reset at episode starts) */
 int vlnce_mask_rows(const float* h, long long ldh, const float* mask, float* out, long long ldo,
                     int rows, int H, cudaStream_t stream);
@@ -247,6 +253,10 @@ int vlnce_mask_rows_add(const float* src, long long lds, const float* mask, floa
                         int rows, int H, cudaStream_t stream);
 int vlnce_gru_pointwise_bwd(const float* dh, long long lddh, const float* save, const float* hm,
                             float* dgi, float* dgh, float* dhm, int rows, int H, cudaStream_t stream);
+/* LSTM cell backward: dgates (rows,4H) pre-activation gradients (shared by W_ih and W_hh); dc_in nullable (= 0),
+ * dc_out = d c_prev * mask[row] (mask nullable = 1) carried to the step before */
+int vlnce_lstm_pointwise_bwd(const float* dh, long long lddh, const float* dc_in, const float* save, const float* cm,
+                             const float* mask, float* dgates, float* dc_out, int rows, int H, cudaStream_t stream);
 int vlnce_attn_pool_bwd(const float* q, long long ldq, const float* E, long long lde_r, long long lde_p,
                         const float* probs, float scale, const float* dout, long long lddo, float* dq,
                         long long lddq, float* dE, long long ldde_r, long long ldde_p, int accumulate_dE,

@@ -54,6 +54,16 @@ CASES = {
     "seq2seq_train_features_abl": dict(policy="Seq2SeqPolicy", pm=False, kind="train", t=3, n=3, hw=256, length=24,
                                        wseed=33, iseed=133, bn_train=False, features=True, prev_action=True,
                                        ablate=("instruction", "rgb")),
+    # STATE_ENCODER.rnn_type = "LSTM" (config/default.py:259 allows GRU | LSTM; rnn_states carry (h, c) per encoder)
+    "cma_act_lstm": dict(policy="CMAPolicy", pm=True, kind="act", n=3, hw=256, length=24, wseed=35, iseed=135,
+                         bn_train=False, state_rnn="LSTM"),
+    "cma_train_features_lstm": dict(policy="CMAPolicy", pm=True, kind="train", t=4, n=3, hw=256, length=24, wseed=36,
+                                    iseed=136, bn_train=False, features=True, state_rnn="LSTM"),
+    "seq2seq_train_features_lstm": dict(policy="Seq2SeqPolicy", pm=True, kind="train", t=4, n=3, hw=256, length=24,
+                                        wseed=37, iseed=137, bn_train=False, features=True, prev_action=True,
+                                        state_rnn="LSTM"),
+    "wp_eval_lstm": dict(policy="WaypointPolicy", kind="wp_eval", t=3, n=2, length=24, wseed=38, iseed=138,
+                         state_rnn="LSTM"),
     "wp_eval_abl": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=34, iseed=134,
                         ablate=("instruction", "depth")),
     # Waypoint path (BASELINE config C4 dims, 1-wpn-cc.yaml): act on a fresh/continuing env pair,
@@ -92,6 +102,8 @@ def oracle_impl(case):
 
 def model_config(case) -> hb017.Config:
     abl = {"ablate_" + k: True for k in case.get("ablate", ())}
+    if case.get("state_rnn"):
+        abl["STATE_ENCODER"] = dict(rnn_type=case["state_rnn"])
     if case["policy"] == "WaypointPolicy":
         from . import waypoint
 
@@ -141,7 +153,9 @@ def set_mode(pol, case):
 
 
 def layers_of(case):
-    return 2 if case["policy"] == "CMAPolicy" else 1
+    """rnn_states slots: one per GRU state encoder, two (h, c) per LSTM one"""
+    encoders = 1 if case["policy"] == "Seq2SeqPolicy" else 2
+    return encoders * (2 if case.get("state_rnn") == "LSTM" else 1)
 
 
 def inputs(case):
@@ -153,7 +167,7 @@ def inputs(case):
             return synth.make_waypoint_act_batch(case["iseed"], case["n"], length=case["length"],
                                                  rgb_u8=case.get("rgb_u8", False), classes=classes)
         return synth.make_waypoint_eval_batch(case["iseed"], case["t"], case["n"], length=case["length"],
-                                              classes=classes)
+                                              classes=classes, layers=layers_of(case))
     if case["kind"] == "act":
         return synth.make_act_batch(case["iseed"], case["n"], hw=case["hw"],
                                     rgb_hw=case.get("rgb_hw"), length=case["length"],

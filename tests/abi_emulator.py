@@ -146,6 +146,19 @@ class Emulator:
         if save:
             _mat(save, rows, 4 * H, 4 * H)[...] = np.concatenate([r, z, n, ghn], 1)
 
+    def lstm_pointwise_fwd(self, gi, gh, c, ldc, hout, ldo, cout, ldco, hout2, cout2, ldo2, save, rows, H, st):
+        a = _mat(gi, rows, 4 * H, 4 * H).astype(np.float64) + _mat(gh, rows, 4 * H, 4 * H).astype(np.float64)
+        i, f, g, o = _sig(a[:, :H]), _sig(a[:, H:2 * H]), np.tanh(a[:, 2 * H:3 * H]), _sig(a[:, 3 * H:])
+        cn = f * _mat(c, rows, H, ldc).astype(np.float64) + i * g
+        tc = np.tanh(cn)
+        _mat(hout, rows, H, ldo)[...] = o * tc
+        _mat(cout, rows, H, ldco)[...] = cn
+        if hout2:
+            _mat(hout2, rows, H, ldo2)[...] = o * tc
+            _mat(cout2, rows, H, ldo2)[...] = cn
+        if save:
+            _mat(save, rows, 5 * H, 5 * H)[...] = np.concatenate([i, f, g, o, tc], 1)
+
     def mask_rows(self, h, ldh, mask, out, ldo, rows, H, st):
         _mat(out, rows, H, ldo)[...] = _mat(h, rows, H, ldh) * _flat(mask, rows)[:, None]
 
@@ -212,6 +225,19 @@ class Emulator:
         _mat(dgi, rows, 3 * H, 3 * H)[...] = np.concatenate([dpr, dpz, dpn], 1)
         _mat(dgh, rows, 3 * H, 3 * H)[...] = np.concatenate([dpr, dpz, dpn * r], 1)
         _mat(dhm, rows, H, H)[...] = g * z
+
+    def lstm_pointwise_bwd(self, dh, lddh, dc_in, save, cm, mask, dgates, dc_out, rows, H, st):
+        s = _mat(save, rows, 5 * H, 5 * H).astype(np.float64)
+        i, f, gg, o, tc = (s[:, k * H:(k + 1) * H] for k in range(5))
+        g = _mat(dh, rows, H, lddh).astype(np.float64)
+        dct = g * o * (1 - tc * tc)
+        if dc_in:
+            dct = dct + _mat(dc_in, rows, H, H).astype(np.float64)
+        cp = _mat(cm, rows, H, H).astype(np.float64)
+        _mat(dgates, rows, 4 * H, 4 * H)[...] = np.concatenate(
+            [dct * gg * i * (1 - i), dct * cp * f * (1 - f), dct * i * (1 - gg * gg), g * tc * o * (1 - o)], 1)
+        m = _flat(mask, rows)[:, None] if mask else 1.0
+        _mat(dc_out, rows, H, H)[...] = dct * f * m
 
     def attn_pool_bwd(self, q, ldq, E, lde_r, lde_p, probs, scale, dout, lddo, dq, lddq, dE, ldde_r, ldde_p, acc,
                       R, P, D, st):

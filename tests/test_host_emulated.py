@@ -41,7 +41,8 @@ def check(got, want, tol, skip=()):
 
 @pytest.mark.parametrize("name", ["cma_train_features", "cma_train_features_nopm", "seq2seq_train_features",
                                   "cma_rxr_train_features", "cma_train_features_abl_i", "cma_train_features_abl_v",
-                                  "seq2seq_train_features_abl"])
+                                  "seq2seq_train_features_abl", "cma_train_features_lstm",
+                                  "seq2seq_train_features_lstm"])
 def test_il_train_plan_matches_golden(name):
     with lib.dry_run(executor=Emulator()):
         got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses)
@@ -96,7 +97,7 @@ class _Impl:
 
 
 @pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_eval", "wp_act_hpn", "wp_eval_hpn", "wp_act_dc", "wp_act_dd",
-                                  "wp_eval_dd", "wp_eval_d_", "wp_eval_abl"])
+                                  "wp_eval_dd", "wp_eval_d_", "wp_eval_abl", "wp_eval_lstm"])
 def test_waypoint_plan_matches_golden(name):
     case = cases.CASES[name]
     with lib.dry_run(executor=Emulator()):
@@ -404,7 +405,8 @@ def test_ddppo_collect_and_update_loop_matches_oracle():
 # ---------------------------------------------------------------------------------------------
 # raw-pixel paths in the fp32 precision mode: the conv-trunk launch plans (trunk.py) on the emulator as well
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["cma_act", "cma_act_bntrain", "cma_act_rgb224", "seq2seq_act", "cma_train_pixels"])
+@pytest.mark.parametrize("name", ["cma_act", "cma_act_bntrain", "cma_act_rgb224", "seq2seq_act", "cma_train_pixels",
+                                  "cma_act_lstm"])
 def test_pixel_paths_fp32_match_golden(name):
     """Both conv trunks from raw pixels in ``precision="fp32"`` (vlnce_conv2d_ref + GroupNorm / BatchNorm / pooling
     kernels, modelled with torch CPU ops): block wiring, residual and downsample routing, folded eval-mode and

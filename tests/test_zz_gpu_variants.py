@@ -1,0 +1,88 @@
+"""Parity of the configuration variants outside the shipped recipes (``STATE_ENCODER.rnn_type = "LSTM"`` …) on the
+B200, against goldens frozen from the reference.  Collected last on purpose: these entry points were added after the
+round's final GPU visit, so under ``pytest -x`` a failure here cannot hide the results of the main parity files."""
+import os
+import warnings
+
+import pytest
+import torch
+
+import vlnce_b200
+from oracle import cases
+from vlnce_b200 import lib
+from vlnce_b200.lib import C, ptr
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+DEV = "cuda"
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gold(name):
+    return torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+
+
+def test_lstm_cell_kernels_match_torch_autograd():
+    """vlnce_lstm_pointwise_fwd / _bwd against torch.nn.LSTMCell arithmetic (fp32, gate order i,f,g,o) for two
+    chained steps with a row reset between them — values, saved residuals' effect and every gradient."""
+    g0 = torch.Generator().manual_seed(5)
+    N, H = 5, 96
+    gi = [torch.randn(N, 4 * H, generator=g0).to(DEV).requires_grad_() for _ in range(2)]
+    gh = [torch.randn(N, 4 * H, generator=g0).to(DEV).requires_grad_() for _ in range(2)]
+    c0 = torch.randn(N, H, generator=g0).to(DEV).requires_grad_()
+    mask = torch.tensor([1, 0, 1, 1, 0], dtype=torch.float32, device=DEV)
+    up = [torch.randn(N, H, generator=g0).to(DEV) for _ in range(2)]
+
+    def cell(a, c):
+        i, f, g, o = a.chunk(4, 1)
+        cn = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        return torch.sigmoid(o) * torch.tanh(cn), cn
+
+    h1, c1 = cell(gi[0] + gh[0], c0)
+    h2, c2 = cell(gi[1] + gh[1], c1 * mask[:, None])
+    ((h1 * up[0]).sum() + (h2 * up[1]).sum()).backward()
+
+    st = lib.stream()
+    hk = [torch.empty(N, H, device=DEV) for _ in range(2)]
+    ck = [torch.empty(N, H, device=DEV) for _ in range(2)]
+    fin = torch.empty(N, 2, H, device=DEV)
+    sv = [torch.empty(N, 5 * H, device=DEV) for _ in range(2)]
+    cm = torch.empty(N, H, device=DEV)
+    C.vlnce_lstm_pointwise_fwd(ptr(gi[0]), ptr(gh[0]), ptr(c0), H, ptr(hk[0]), H, ptr(ck[0]), H, None, None, 0,
+                               ptr(sv[0]), N, H, st)
+    C.vlnce_mask_rows(ptr(ck[0]), H, ptr(mask), ptr(cm), H, N, H, st)
+    C.vlnce_lstm_pointwise_fwd(ptr(gi[1]), ptr(gh[1]), ptr(cm), H, ptr(hk[1]), H, ptr(ck[1]), H, ptr(fin),
+                               fin.data_ptr() + 4 * H, 2 * H, ptr(sv[1]), N, H, st)
+    for got, want in ((hk[0], h1), (ck[0], c1), (hk[1], h2), (ck[1], c2), (fin[:, 0], h2), (fin[:, 1], c2)):
+        torch.testing.assert_close(got, want.detach(), rtol=1e-5, atol=1e-6)
+    dg = [torch.empty(N, 4 * H, device=DEV) for _ in range(2)]
+    dc = torch.empty(N, H, device=DEV)
+    C.vlnce_lstm_pointwise_bwd(ptr(up[1]), H, None, ptr(sv[1]), ptr(cm), ptr(mask), ptr(dg[1]), ptr(dc), N, H, st)
+    C.vlnce_lstm_pointwise_bwd(ptr(up[0]), H, ptr(dc), ptr(sv[0]), ptr(c0.detach()), None, ptr(dg[0]), ptr(dc), N, H, st)
+    for k in range(2):
+        torch.testing.assert_close(dg[k], gi[k].grad, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(dg[k], gh[k].grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dc, c0.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["cma_train_features_lstm", "seq2seq_train_features_lstm", "wp_eval_lstm"])
+def test_lstm_state_encoder_training_matches_golden(name):
+    """logits, losses and every trainable gradient with LSTM state encoders (rnn_states = (h, c) slots per encoder)"""
+    from test_gpu_train import check
+
+    got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, device=DEV, precision="fp32")
+    want = gold(name)
+    assert set(got) == {k for k in want if not k.startswith("_")}
+    check(got, want, 1e-3, name)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
+def test_lstm_state_encoder_act_matches_golden(precision, tol):
+    got = cases.run_case(vlnce_b200, "cma_act_lstm", aux=vlnce_b200.AuxLosses, device=DEV, precision=precision)
+    want = gold("cma_act_lstm")
+    assert got["rnn_states_out"].shape == want["rnn_states_out"].shape == (3, 4, 512)
+    p, q = got["logits"].exp(), want["logits"].exp()
+    assert float((p - q).abs().max() / q.abs().max()) < tol
+    assert float((got["rnn_states_out"] - want["rnn_states_out"]).norm() / want["rnn_states_out"].norm()) < tol
+    if precision == "fp32":
+        assert torch.equal(got["action"], want["action"])

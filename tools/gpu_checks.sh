@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/gpu.txt 2>&1
 FILES="$@"
-[ -z "$FILES" ] && FILES="tests/test_gpu_conv.py tests/test_gpu_head_ops.py tests/test_gpu_obs_transforms.py tests/test_gpu_policy.py tests/test_gpu_train.py tests/test_gpu_waypoint.py"
+[ -z "$FILES" ] && FILES="tests/test_gpu_conv.py tests/test_gpu_head_ops.py tests/test_gpu_obs_transforms.py tests/test_gpu_policy.py tests/test_gpu_train.py tests/test_gpu_waypoint.py tests/test_zz_gpu_variants.py"
 rc=0
 for f in $FILES; do
   name=$(basename $f .py)

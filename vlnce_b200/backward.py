@@ -47,6 +47,9 @@ class _Leaves:
 
 
 def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, masks_f, T, N, dx, lddx, leaves):
+    """BPTT of ``HeadEngine._gru_forward`` (GRU, or LSTM when the state encoder is one)."""
+    if isinstance(rnn, torch.nn.LSTM):
+        return _lstm_backward(eng, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, masks_f, T, N, dx, lddx, leaves)
     H = eng.H
     R = T * N
     st = lib.stream()
@@ -67,6 +70,32 @@ def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, m
         linear_dw(ptr(d_gi), 3 * H, x, ldx, ptr(g[pfx + "weight_ih_l0"]), in_size, R, 3 * H, in_size)
         _colsum(ptr(d_gi), 3 * H, ptr(g[pfx + "bias_ih_l0"]), R, 3 * H)
     linear_dx(ptr(d_gi), 3 * H, ptr(rnn.weight_ih_l0), dx, lddx, R, 3 * H, in_size)
+
+
+def _lstm_backward(eng, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, masks_f, T, N, dx, lddx, leaves):
+    """LSTM state encoder: gates = gi + gh, so one pre-activation gradient buffer feeds both weight matrices;
+    the cell-state gradient is carried (and mask-reset) between steps inside the pointwise kernel."""
+    H = eng.H
+    R = T * N
+    st = lib.stream()
+    d_g = eng.buf(tag + "_dgi", (R, 4 * H))
+    dhm = eng.buf(tag + "_dhm", (N, H))
+    dc = eng.buf(tag + "_dc", (N, H))
+    save = eng.buf(tag + "_save", (R, 5 * H))
+    hm_all, cm_all = eng.buf(tag + "_hm", (R, H)), eng.buf(tag + "_cm", (R, H))
+    for t in range(T - 1, -1, -1):
+        C.vlnce_lstm_pointwise_bwd(dh + F4 * t * N * lddh, lddh, ptr(dc) if t < T - 1 else None,
+                                   off(save, t * N * 5 * H), off(cm_all, t * N * H), off(masks_f, t * N),
+                                   off(d_g, t * N * 4 * H), ptr(dc), N, H, st)
+        if t > 0:
+            linear_dx(off(d_g, t * N * 4 * H), 4 * H, ptr(rnn.weight_hh_l0), ptr(dhm), H, N, 4 * H, H)
+            C.vlnce_mask_rows_add(ptr(dhm), H, off(masks_f, t * N), dh + F4 * (t - 1) * N * lddh, lddh, N, H, st)
+    with leaves():
+        linear_dw(ptr(d_g), 4 * H, ptr(hm_all), H, ptr(g[pfx + "weight_hh_l0"]), H, R, 4 * H, H)
+        _colsum(ptr(d_g), 4 * H, ptr(g[pfx + "bias_hh_l0"]), R, 4 * H)
+        linear_dw(ptr(d_g), 4 * H, x, ldx, ptr(g[pfx + "weight_ih_l0"]), in_size, R, 4 * H, in_size)
+        _colsum(ptr(d_g), 4 * H, ptr(g[pfx + "bias_ih_l0"]), R, 4 * H)
+    linear_dx(ptr(d_g), 4 * H, ptr(rnn.weight_ih_l0), dx, lddx, R, 4 * H, in_size)
 
 
 def instruction_backward(eng, g: Dict[str, torch.Tensor], d_instr: torch.Tensor):

@@ -20,15 +20,19 @@ from .policy import ILPolicy
 
 
 class _GRUStateEncoder(nn.Module):
-    """Parameter container of habitat_baselines v0.1.7 ``build_rnn_state_encoder`` for a GRU:
-    attribute ``rnn`` (orthogonal weights, zero biases), ``num_recurrent_layers``."""
+    """Parameter container of habitat_baselines v0.1.7 ``build_rnn_state_encoder`` (GRU, or LSTM with the
+    packed ``(h, c)`` hidden state): attribute ``rnn`` (orthogonal weights, zero biases), ``num_recurrent_layers``
+    (= layers for a GRU, 2 x layers for an LSTM)."""
 
     def __init__(self, input_size, hidden_size, rnn_type="GRU", num_layers=1):
         super().__init__()
-        if rnn_type.upper() != "GRU":
-            raise NotImplementedError("STATE_ENCODER.rnn_type=LSTM is not built (every recipe uses GRU)")
-        self.num_recurrent_layers = num_layers
-        self.rnn = nn.GRU(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
+        rnn_type = rnn_type.upper()
+        if rnn_type not in ("GRU", "LSTM"):
+            raise ValueError(f"STATE_ENCODER.rnn_type must be GRU or LSTM, got {rnn_type!r}")
+        if num_layers != 1:
+            raise NotImplementedError("state encoders are single-layer in every net of the reference")
+        self.num_recurrent_layers = num_layers * (2 if rnn_type == "LSTM" else 1)
+        self.rnn = getattr(nn, rnn_type)(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
         for name, p in self.rnn.named_parameters():
             if "weight" in name:
                 nn.init.orthogonal_(p)

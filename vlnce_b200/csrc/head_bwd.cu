@@ -82,6 +82,32 @@ __global__ void gru_pointwise_bwd_kernel(const float* __restrict__ dh, long long
 }
 
 // ------------------------------------------------------------------------------------
+// LSTM cell backward (pointwise part).  save = [i, f, g, o, tanh(c')] from the forward, cm = the mask-reset cell
+// state the step consumed.  dc (rows, H) carries the cell-state gradient between steps: read (unless null = 0),
+// then overwritten with d c_prev * mask[row] (null mask = 1) for the step before.  The gate pre-activations are
+// gi + gh, so one dgates (rows, 4H) buffer serves both weight matrices.
+// ------------------------------------------------------------------------------------
+__global__ void lstm_pointwise_bwd_kernel(const float* __restrict__ dh, long long lddh, const float* dc_in,
+                                          const float* __restrict__ save, const float* __restrict__ cm,
+                                          const float* __restrict__ mask, float* __restrict__ dgates,
+                                          float* dc_out, int rows, int H) {
+  const int total = rows * H;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int b = idx / H, k = idx % H;
+    const float* s = save + (size_t)b * 5 * H;
+    const float i = s[k], f = s[H + k], gg = s[2 * H + k], o = s[3 * H + k], tc = s[4 * H + k];
+    const float g = dh[b * lddh + k];
+    const float dct = (dc_in != nullptr ? dc_in[(size_t)b * H + k] : 0.f) + g * o * (1.f - tc * tc);
+    float* d = dgates + (size_t)b * 4 * H;
+    d[k] = dct * gg * i * (1.f - i);
+    d[H + k] = dct * cm[(size_t)b * H + k] * f * (1.f - f);
+    d[2 * H + k] = dct * i * (1.f - gg * gg);
+    d[3 * H + k] = g * tc * o * (1.f - o);
+    dc_out[(size_t)b * H + k] = dct * f * (mask != nullptr ? mask[b] : 1.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Attention-pool backward.  out = sum_p a_p E_p, a = softmax(scale * (E q - mask)).
 //   da_p = E_p . dout;  dl_p = a_p (da_p - sum_j a_j da_j) * scale
 //   dq = sum_p dl_p E_p;  dE_p (+)= a_p dout + dl_p q
@@ -458,6 +484,16 @@ extern "C" int vlnce_gru_pointwise_bwd(const float* dh, long long lddh, const fl
   gru_pointwise_bwd_kernel<<<grid_for((long long)rows * H, 256), 256, 0, stream>>>(dh, lddh, save, hm, dgi, dgh,
                                                                                   dhm, rows, H);
   VLNCE_LAUNCH_CHECK("gru_pointwise_bwd_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_lstm_pointwise_bwd(const float* dh, long long lddh, const float* dc_in, const float* save,
+                                        const float* cm, const float* mask, float* dgates, float* dc_out, int rows,
+                                        int H, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(dh && save && cm && dgates && dc_out && rows > 0 && H > 0, "lstm_pointwise_bwd: bad arguments");
+  lstm_pointwise_bwd_kernel<<<grid_for((long long)rows * H, 256), 256, 0, stream>>>(dh, lddh, dc_in, save, cm, mask,
+                                                                                   dgates, dc_out, rows, H);
+  VLNCE_LAUNCH_CHECK("lstm_pointwise_bwd_kernel");
   return VLNCE_OK;
 }
 

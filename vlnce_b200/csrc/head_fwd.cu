@@ -186,6 +186,40 @@ __global__ void gru_pointwise_fwd_kernel(const float* __restrict__ gi, const flo
   }
 }
 
+// ------------------------------------------------------------------------------------
+// LSTM cell pointwise (habitat_baselines v0.1.7 rnn_state_encoder with rnn_type="LSTM"; torch.nn.LSTM gate order
+// i, f, g, o):  c' = s(f) c + s(i) tanh(g),  h' = s(o) tanh(c').  gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh
+// (both (rows, 4H)); c is the already mask-reset cell state.
+// ------------------------------------------------------------------------------------
+__global__ void lstm_pointwise_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                          const float* __restrict__ c, long long ldc,
+                                          float* __restrict__ hout, long long ldo,
+                                          float* __restrict__ cout, long long ldco,
+                                          float* __restrict__ hout2, float* __restrict__ cout2, long long ldo2,
+                                          float* __restrict__ save,  // (rows, 5H): i, f, g, o, tanh(c') or null
+                                          int rows, int H) {
+  const int total = rows * H;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int b = idx / H, k = idx % H;
+    const float* gib = gi + (size_t)b * 4 * H;
+    const float* ghb = gh + (size_t)b * 4 * H;
+    const float ig = sigmoid_precise(gib[k] + ghb[k]);
+    const float fg = sigmoid_precise(gib[H + k] + ghb[H + k]);
+    const float gg = tanhf(gib[2 * H + k] + ghb[2 * H + k]);
+    const float og = sigmoid_precise(gib[3 * H + k] + ghb[3 * H + k]);
+    const float cn = fmaf(fg, c[b * ldc + k], ig * gg);
+    const float tc = tanhf(cn);
+    const float hn = og * tc;
+    hout[b * ldo + k] = hn;
+    cout[b * ldco + k] = cn;
+    if (hout2 != nullptr) { hout2[b * ldo2 + k] = hn; cout2[b * ldo2 + k] = cn; }
+    if (save != nullptr) {
+      float* s = save + (size_t)b * 5 * H;
+      s[k] = ig; s[H + k] = fg; s[2 * H + k] = gg; s[3 * H + k] = og; s[4 * H + k] = tc;
+    }
+  }
+}
+
 // out[b, :] = h[b, :] * mask[b]   (hidden-state reset where an episode starts)
 __global__ void mask_rows_kernel(const float* __restrict__ h, long long ldh, const float* __restrict__ mask,
                                  float* __restrict__ out, long long ldo, int rows, int H) {
@@ -393,6 +427,18 @@ extern "C" int vlnce_gru_pointwise_fwd(const float* gi, const float* gh, const f
   gru_pointwise_fwd_kernel<<<grid_for((long long)rows * H, 256), 256, 0, stream>>>(
       gi, gh, h, ldh, hout, ldo, hout2, ldo2, save, rows, H);
   VLNCE_LAUNCH_CHECK("gru_pointwise_fwd_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_lstm_pointwise_fwd(const float* gi, const float* gh, const float* c, long long ldc,
+                                        float* hout, long long ldo, float* cout, long long ldco,
+                                        float* hout2, float* cout2, long long ldo2, float* save, int rows, int H,
+                                        cudaStream_t stream) {
+  VLNCE_CHECK_ARG(gi && gh && c && hout && cout && rows > 0 && H > 0, "lstm_pointwise_fwd: bad arguments");
+  VLNCE_CHECK_ARG((hout2 == nullptr) == (cout2 == nullptr), "lstm_pointwise_fwd: hout2 and cout2 go together");
+  lstm_pointwise_fwd_kernel<<<grid_for((long long)rows * H, 256), 256, 0, stream>>>(
+      gi, gh, c, ldc, hout, ldo, cout, ldco, hout2, cout2, ldo2, save, rows, H);
+  VLNCE_LAUNCH_CHECK("lstm_pointwise_fwd_kernel");
   return VLNCE_OK;
 }
 

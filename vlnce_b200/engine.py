@@ -189,12 +189,22 @@ class HeadEngine:
                              ptr(hn), ptr(sg), ptr(sc), R, L, Hs, dirs, st)
         return instr, hn, lengths, L
 
-    # ------------------------------------------------------------------ GRU helper
+    # ------------------------------------------------------------------ state-encoder helper
+    @staticmethod
+    def slots(rnn) -> int:
+        """rnn_states slots one state encoder owns: (h) for a GRU, (h, c) for an LSTM
+        (habitat_baselines v0.1.7 ``RNNStateEncoder.num_recurrent_layers``)."""
+        return 2 if isinstance(rnn, torch.nn.LSTM) else 1
+
     def _gru_forward(self, tag, rnn, x, ldx, in_size, h0, ldh0, masks_f, out, ldo, h_final, ldhf, T, N,
                      save):
         """habitat_baselines v0.1.7 RNNStateEncoder forward (single step when T == 1, else a
         T-step sequence with hidden reset where masks == 0); writes all T*N outputs into
-        ``out`` and the final hidden state into ``h_final``."""
+        ``out`` and the final hidden state into ``h_final``.  ``h0`` / ``h_final`` point at the encoder's
+        first slot of the (N, slots, H) state rows; an LSTM's cell state is the slot after it."""
+        if isinstance(rnn, torch.nn.LSTM):
+            return self._lstm_forward(tag, rnn, x, ldx, in_size, h0, ldh0, masks_f, out, ldo, h_final, ldhf, T, N,
+                                      save)
         H = self.H
         R = T * N
         gi = self.buf(tag + "_gi", (R, 3 * H))
@@ -214,6 +224,33 @@ class HeadEngine:
             C.vlnce_gru_pointwise_fwd(off(gi, t * N * 3 * H), ptr(gh), hm, H, out + F4 * t * N * ldo, ldo,
                                       h_final if last else None, ldhf,
                                       off(sv, t * N * 4 * H) if save else None, N, H, st)
+
+    def _lstm_forward(self, tag, rnn, x, ldx, in_size, h0, ldh0, masks_f, out, ldo, h_final, ldhf, T, N, save):
+        """``STATE_ENCODER.rnn_type = "LSTM"``: the packed hidden state is ``cat([h, c], 0)``
+        (rnn_state_encoder ``_pack_hidden``), i.e. slots (h, c) of each row; both are reset where masks == 0."""
+        H = self.H
+        R = T * N
+        gi = self.buf(tag + "_gi", (R, 4 * H))
+        linear(x, ldx, ptr(rnn.weight_ih_l0), ptr(gi), 4 * H, ptr(rnn.bias_ih_l0), R, 4 * H, in_size)
+        hm_all, cm_all = self.buf(tag + "_hm", (R, H)), self.buf(tag + "_cm", (R, H))
+        c_all = self.buf(tag + "_c", (R, H))
+        gh = self.buf(tag + "_gh", (N, 4 * H))
+        sv = self.buf(tag + "_save", (R, 5 * H)) if save else None
+        st = lib.stream()
+        for t in range(T):
+            hm, cm = off(hm_all, t * N * H), off(cm_all, t * N * H)
+            if t == 0:
+                C.vlnce_mask_rows(h0, ldh0, off(masks_f, 0), hm, H, N, H, st)
+                C.vlnce_mask_rows(h0 + F4 * H, ldh0, off(masks_f, 0), cm, H, N, H, st)
+            else:
+                C.vlnce_mask_rows(out + F4 * (t - 1) * N * ldo, ldo, off(masks_f, t * N), hm, H, N, H, st)
+                C.vlnce_mask_rows(off(c_all, (t - 1) * N * H), H, off(masks_f, t * N), cm, H, N, H, st)
+            linear(hm, H, ptr(rnn.weight_hh_l0), ptr(gh), 4 * H, ptr(rnn.bias_hh_l0), N, 4 * H, H)
+            last = t == T - 1
+            C.vlnce_lstm_pointwise_fwd(off(gi, t * N * 4 * H), ptr(gh), cm, H, out + F4 * t * N * ldo, ldo,
+                                       off(c_all, t * N * H), H, h_final if last else None,
+                                       h_final + F4 * H if last else None, ldhf,
+                                       off(sv, t * N * 5 * H) if save else None, N, H, st)
 
     # ------------------------------------------------------------------ action head
     def action_logits(self, head_linear, x_out, R):
@@ -322,9 +359,10 @@ class CMAEngine(HeadEngine):
                ptr(lin.bias), R, self.depth_out, self.Cdep * P, act=1)
 
         # ---- first GRU -> xcat[:, 0:H]  (cma_policy.py:247-256)
-        h_out = self.buf("rnn_states_out", (N, 2, H))
+        s1, Lr = self.slots(net.state_encoder.rnn), net.num_recurrent_layers  # (N, Lr, H): encoder 1 | encoder 2
+        h_out = self.buf("rnn_states_out", (N, Lr, H))
         self._gru_forward("gru1", net.state_encoder.rnn, ptr(state_in), self.state_in, self.state_in,
-                          ptr(rnn_states), 2 * H, masks_f, ptr(xcat), self.cat, ptr(h_out), 2 * H, T, N, save)
+                          ptr(rnn_states), Lr * H, masks_f, ptr(xcat), self.cat, ptr(h_out), Lr * H, T, N, save)
 
         # ---- text attention (cma_policy.py:258-263)
         br_instr.join()
@@ -362,8 +400,8 @@ class CMAEngine(HeadEngine):
         lin = net.second_state_compress[0]
         linear(ptr(xcat), self.cat, ptr(lin.weight), ptr(x2), H, ptr(lin.bias), R, H, self.cat, act=1)
         x_out = self.buf("x_out", (R, H))
-        self._gru_forward("gru2", net.second_state_encoder.rnn, ptr(x2), H, H, off(rnn_states, H), 2 * H,
-                          masks_f, ptr(x_out), H, off(h_out, H), 2 * H, T, N, save)
+        self._gru_forward("gru2", net.second_state_encoder.rnn, ptr(x2), H, H, off(rnn_states, s1 * H), Lr * H,
+                          masks_f, ptr(x_out), H, off(h_out, s1 * H), Lr * H, T, N, save)
 
         # ---- progress monitor (cma_policy.py:296) — tanh(Linear(x)); the loss lives in the caller
         hat = None

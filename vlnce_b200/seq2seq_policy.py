@@ -78,9 +78,10 @@ class Seq2SeqEngine(HeadEngine):
         if cfg.get("ablate_rgb", False):
             xin[:, Hs + d_out:Hs + d_out + r_out].zero_()
         x_out = self.buf("x_out", (R, H))
-        h_out = self.buf("rnn_states_out", (N, 1, H))
-        self._gru_forward("gru", net.state_encoder.rnn, ptr(xin), width, width, ptr(rnn_states), H, masks_f,
-                          ptr(x_out), H, ptr(h_out), H, T, N, save)
+        Lr = net.num_recurrent_layers  # 1 (GRU) or 2 (LSTM: h, c)
+        h_out = self.buf("rnn_states_out", (N, Lr, H))
+        self._gru_forward("gru", net.state_encoder.rnn, ptr(xin), width, width, ptr(rnn_states), Lr * H, masks_f,
+                          ptr(x_out), H, ptr(h_out), Lr * H, T, N, save)
         hat = None
         if cfg.PROGRESS_MONITOR.use:
             hat = self.buf("progress_hat", (R, 1))

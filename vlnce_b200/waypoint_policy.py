@@ -328,9 +328,10 @@ class WaypointEngine(HeadEngine):
                ptr(lin.bias), B, self.dep_out, self.Cdep * S, act=1)
 
         # ---- visual-history GRU -> xcat[:, col_hist:col_hist+H] (:407-413)
-        h_out = self.buf("wp_rnn_states_out", (N, 2, H))
+        s1, Lr = self.slots(net.visual_rnn.rnn), net.num_recurrent_layers  # (N, Lr, H): visual_rnn | main encoder
+        h_out = self.buf("wp_rnn_states_out", (N, Lr, H))
         self._gru_forward("wp_vgru", net.visual_rnn.rnn, ptr(state_in), self.state_in, self.state_in, ptr(rnn_states),
-                          2 * H, masks_f, off(xcat, self.col_hist), self.xcat, ptr(h_out), 2 * H, T, N, save)
+                          Lr * H, masks_f, off(xcat, self.col_hist), self.xcat, ptr(h_out), Lr * H, T, N, save)
 
         # ---- instruction attention (:419-424), quirk W1 -> xcat[:, 0:Di]
         br_instr.join()
@@ -391,8 +392,8 @@ class WaypointEngine(HeadEngine):
         lin = net.main_state_compress[0]
         linear(ptr(xcat), self.xcat, ptr(lin.weight), ptr(x2), H, ptr(lin.bias), B, H, self.xcat, act=1)
         x_out = self.buf("wp_x_out", (B, H))
-        self._gru_forward("wp_mgru", net.main_state_encoder.rnn, ptr(x2), H, H, off(rnn_states, H), 2 * H, masks_f,
-                          ptr(x_out), H, off(h_out, H), 2 * H, T, N, save)
+        self._gru_forward("wp_mgru", net.main_state_encoder.rnn, ptr(x2), H, H, off(rnn_states, s1 * H), Lr * H,
+                          masks_f, ptr(x_out), H, off(h_out, s1 * H), Lr * H, T, N, save)
 
         # ---- heads (:546-615)
         xs = self.buf("wp_xs", (B, D))
