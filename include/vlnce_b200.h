@@ -213,6 +213,12 @@ int vlnce_lstm_seq_fwd(const float* gx, const float* whh_f, const float* whh_b, 
                        const float* bhh_b, const int* lengths, float* out, float* hn,
                        float* save_gates, float* save_c, int R, int L, int H, int dirs,
                        cudaStream_t stream);
+/* persistent (bi)GRU over packed rows (instruction_encoder.py:27,80-94 with INSTRUCTION_ENCODER.rnn_type = "GRU"):
+ * gx (dirs,R,L,3H) = input projection + b_ih; gate order r,z,n; out / hn as vlnce_lstm_seq_fwd;
+ * save (dirs,R,L,4H) = r, z, n, W_hn h + b_hn for the backward (optional). */
+int vlnce_gru_seq_fwd(const float* gx, const float* whh_f, const float* whh_b, const float* bhh_f,
+                      const float* bhh_b, const int* lengths, float* out, float* hn, float* save, int R, int L,
+                      int H, int dirs, cudaStream_t stream);
 /* GRU cell pointwise part (habitat_baselines v0.1.7 rnn_state_encoder / torch.nn.GRU) */
 int vlnce_gru_pointwise_fwd(const float* gi, const float* gh, const float* h, long long ldh,
                             float* hout, long long ldo, float* hout2, long long ldo2, float* save,
@@ -261,6 +267,11 @@ int vlnce_attn_pool_bwd(const float* q, long long ldq, const float* E, long long
                         const float* probs, float scale, const float* dout, long long lddo, float* dq,
                         long long lddq, float* dE, long long ldde_r, long long ldde_p, int accumulate_dE,
                         int R, int P, int D, cudaStream_t stream);
+/* BPTT of the packed (bi)GRU: dgx / dgh (dirs,R,L,3H) gradients w.r.t. the input- and hidden-side gate
+ * pre-activations, hprev (dirs,R,L,H) the hidden state fed to every step; zero beyond each row's length. */
+int vlnce_gru_seq_bwd(const float* dout, const float* save, const float* out, const float* whh_f,
+                      const float* whh_b, const int* lengths, float* dgx, float* dgh, float* hprev, int R, int L,
+                      int H, int dirs, cudaStream_t stream);
 /* BPTT of the packed (bi)LSTM: emits pre-activation gate gradients dgx (dirs,R,L,4H) and the
  * hidden state fed to every step hprev (dirs,R,L,H); the weight gradients are then GEMMs. */
 int vlnce_lstm_seq_bwd(const float* dout, const float* gates, const float* cs, const float* out,

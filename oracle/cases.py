@@ -64,6 +64,14 @@ CASES = {
                                         state_rnn="LSTM"),
     "wp_eval_lstm": dict(policy="WaypointPolicy", kind="wp_eval", t=3, n=2, length=24, wseed=38, iseed=138,
                          state_rnn="LSTM"),
+    # INSTRUCTION_ENCODER.rnn_type = "GRU" (instruction_encoder.py:27): bi-GRU per-token outputs (CMA, waypoint),
+    # uni-directional final state (Seq2Seq)
+    "cma_train_features_igru": dict(policy="CMAPolicy", pm=True, kind="train", t=3, n=3, hw=256, length=24, wseed=39,
+                                    iseed=139, bn_train=False, features=True, instr_rnn="GRU"),
+    "seq2seq_train_features_igru": dict(policy="Seq2SeqPolicy", pm=False, kind="train", t=3, n=3, hw=256, length=24,
+                                        wseed=40, iseed=140, bn_train=False, features=True, instr_rnn="GRU"),
+    "wp_eval_igru": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=41, iseed=141,
+                         instr_rnn="GRU", state_rnn="LSTM"),
     "wp_eval_abl": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=34, iseed=134,
                         ablate=("instruction", "depth")),
     # Waypoint path (BASELINE config C4 dims, 1-wpn-cc.yaml): act on a fresh/continuing env pair,
@@ -104,6 +112,8 @@ def model_config(case) -> hb017.Config:
     abl = {"ablate_" + k: True for k in case.get("ablate", ())}
     if case.get("state_rnn"):
         abl["STATE_ENCODER"] = dict(rnn_type=case["state_rnn"])
+    if case.get("instr_rnn"):
+        abl["INSTRUCTION_ENCODER"] = dict(rnn_type=case["instr_rnn"])
     if case["policy"] == "WaypointPolicy":
         from . import waypoint
 

@@ -132,6 +132,61 @@ class Emulator:
                 if hna is not None:
                     hna[d, r] = h
 
+    def gru_seq_fwd(self, gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save, R, L, H, dirs, st):
+        gxa = _flat(gx, dirs * R * L * 3 * H).reshape(dirs, R, L, 3 * H)
+        o = _flat(out, R * L * dirs * H).reshape(R, L, dirs * H)
+        o[...] = 0
+        lens = np.minimum(_flat(lengths, R, I32), L)
+        sva = _flat(save, dirs * R * L * 4 * H).reshape(dirs, R, L, 4 * H) if save else None
+        hna = _flat(hn, dirs * R * H).reshape(dirs, R, H) if hn else None
+        for d in range(dirs):
+            W = _flat(whh_b if d else whh_f, 3 * H * H).reshape(3 * H, H).astype(np.float64)
+            bh = _flat(bhh_b if d else bhh_f, 3 * H).astype(np.float64)
+            for r in range(R):
+                h = np.zeros(H)
+                for step in range(lens[r]):
+                    t = step if d == 0 else lens[r] - 1 - step
+                    x = gxa[d, r, t].astype(np.float64)
+                    gh = W @ h + bh
+                    rg, zg = _sig(x[:H] + gh[:H]), _sig(x[H:2 * H] + gh[H:2 * H])
+                    ng = np.tanh(x[2 * H:] + rg * gh[2 * H:])
+                    h = (1 - zg) * ng + zg * h
+                    o[r, t, d * H:(d + 1) * H] = h
+                    if sva is not None:
+                        sva[d, r, t] = np.concatenate([rg, zg, ng, gh[2 * H:]])
+                if hna is not None:
+                    hna[d, r] = h
+
+    def gru_seq_bwd(self, dout, save, out, whh_f, whh_b, lengths, dgx, dgh, hprev, R, L, H, dirs, st):
+        do = _flat(dout, R * L * dirs * H).reshape(R, L, dirs * H).astype(np.float64)
+        sv = _flat(save, dirs * R * L * 4 * H).reshape(dirs, R, L, 4 * H).astype(np.float64)
+        o = _flat(out, R * L * dirs * H).reshape(R, L, dirs * H).astype(np.float64)
+        dx_ = _flat(dgx, dirs * R * L * 3 * H).reshape(dirs, R, L, 3 * H)
+        dh_ = _flat(dgh, dirs * R * L * 3 * H).reshape(dirs, R, L, 3 * H)
+        hp_ = _flat(hprev, dirs * R * L * H).reshape(dirs, R, L, H)
+        dx_[...] = 0
+        dh_[...] = 0
+        hp_[...] = 0
+        lens = np.minimum(_flat(lengths, R, I32), L)
+        for d in range(dirs):
+            W = _flat(whh_b if d else whh_f, 3 * H * H).reshape(3 * H, H).astype(np.float64)
+            for r in range(R):
+                carry = np.zeros(H)
+                for step in range(lens[r] - 1, -1, -1):
+                    tt = step if d == 0 else lens[r] - 1 - step
+                    tp = tt - 1 if d == 0 else tt + 1
+                    rg, zg, ng, ghn = (sv[d, r, tt, i * H:(i + 1) * H] for i in range(4))
+                    hp = o[r, tp, d * H:(d + 1) * H] if step > 0 else np.zeros(H)
+                    hp_[d, r, tt] = hp
+                    g = do[r, tt, d * H:(d + 1) * H] + carry
+                    dpn = g * (1 - zg) * (1 - ng * ng)
+                    dpz = g * (hp - ng) * zg * (1 - zg)
+                    dpr = dpn * ghn * rg * (1 - rg)
+                    dx_[d, r, tt] = np.concatenate([dpr, dpz, dpn])
+                    gh = np.concatenate([dpr, dpz, dpn * rg])
+                    dh_[d, r, tt] = gh
+                    carry = g * zg + W.T @ gh
+
     def gru_pointwise_fwd(self, gi, gh, h, ldh, hout, ldo, hout2, ldo2, save, rows, H, st):
         gi_, gh_ = _mat(gi, rows, 3 * H, 3 * H).astype(np.float64), _mat(gh, rows, 3 * H, 3 * H).astype(np.float64)
         hp = _mat(h, rows, H, ldh).astype(np.float64)

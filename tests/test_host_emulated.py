@@ -42,7 +42,8 @@ def check(got, want, tol, skip=()):
 @pytest.mark.parametrize("name", ["cma_train_features", "cma_train_features_nopm", "seq2seq_train_features",
                                   "cma_rxr_train_features", "cma_train_features_abl_i", "cma_train_features_abl_v",
                                   "seq2seq_train_features_abl", "cma_train_features_lstm",
-                                  "seq2seq_train_features_lstm"])
+                                  "seq2seq_train_features_lstm", "cma_train_features_igru",
+                                  "seq2seq_train_features_igru"])
 def test_il_train_plan_matches_golden(name):
     with lib.dry_run(executor=Emulator()):
         got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses)
@@ -97,7 +98,7 @@ class _Impl:
 
 
 @pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_eval", "wp_act_hpn", "wp_eval_hpn", "wp_act_dc", "wp_act_dd",
-                                  "wp_eval_dd", "wp_eval_d_", "wp_eval_abl", "wp_eval_lstm"])
+                                  "wp_eval_dd", "wp_eval_d_", "wp_eval_abl", "wp_eval_lstm", "wp_eval_igru"])
 def test_waypoint_plan_matches_golden(name):
     case = cases.CASES[name]
     with lib.dry_run(executor=Emulator()):

@@ -86,3 +86,70 @@ def test_lstm_state_encoder_act_matches_golden(precision, tol):
     assert float((got["rnn_states_out"] - want["rnn_states_out"]).norm() / want["rnn_states_out"].norm()) < tol
     if precision == "fp32":
         assert torch.equal(got["action"], want["action"])
+
+
+@pytest.mark.parametrize("dirs", [1, 2])
+def test_gru_sequence_kernels_match_packed_torch(dirs):
+    """vlnce_gru_seq_fwd / _bwd against torch.nn.GRU on a packed ragged batch (CPU fp32): per-token outputs, final
+    states, and — through the GEMMs the plan runs on the emitted gate gradients — every weight / input gradient."""
+    import torch.nn as nn
+
+    from vlnce_b200.engine import linear, linear_dw, linear_dx
+
+    R, L, E, H = 5, 11, 50, 128
+    torch.manual_seed(0)
+    rnn = nn.GRU(E, H, bidirectional=dirs == 2)
+    for p in rnn.parameters():
+        p.data.mul_(2.0)
+    lens = torch.tensor([11, 1, 7, 4, 9])
+    x = torch.randn(R, L, E) * (torch.arange(L).view(1, L, 1) < lens.view(R, 1, 1))
+    xr = x.clone().requires_grad_()
+    o, hn = rnn(nn.utils.rnn.pack_padded_sequence(xr, lens, batch_first=True, enforce_sorted=False))
+    want = nn.utils.rnn.pad_packed_sequence(o, batch_first=True, total_length=L)[0]
+    up = torch.randn(R, L, dirs * H)
+    (want * up).sum().backward()
+
+    G = 3 * H
+    dev = {k: v.detach().to(DEV) for k, v in rnn.named_parameters()}
+    xd, lengths, st = x.to(DEV), lens.to(DEV).int(), lib.stream()
+    sfx = ["", "_reverse"][:dirs]
+    gx = torch.empty(dirs, R, L, G, device=DEV)
+    for d, s in enumerate(sfx):
+        linear(ptr(xd), E, ptr(dev["weight_ih_l0" + s]), gx[d].data_ptr(), G, ptr(dev["bias_ih_l0" + s]), R * L, G, E)
+    out = torch.full((R, L, dirs * H), float("nan"), device=DEV)
+    hn_got = torch.empty(dirs, R, H, device=DEV)
+    save = torch.empty(dirs, R, L, 4 * H, device=DEV)
+    rev = (lambda k: ptr(dev[k + "_reverse"])) if dirs == 2 else (lambda k: None)
+    C.vlnce_gru_seq_fwd(ptr(gx), ptr(dev["weight_hh_l0"]), rev("weight_hh_l0"), ptr(dev["bias_hh_l0"]), rev("bias_hh_l0"),
+                        ptr(lengths), ptr(out), ptr(hn_got), ptr(save), R, L, H, dirs, st)
+    torch.testing.assert_close(out.cpu(), want.detach(), rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(hn_got.cpu(), hn.detach(), rtol=1e-4, atol=2e-5)
+
+    dgx, dgh = torch.empty(dirs, R, L, G, device=DEV), torch.empty(dirs, R, L, G, device=DEV)
+    hprev = torch.empty(dirs, R, L, H, device=DEV)
+    C.vlnce_gru_seq_bwd(ptr(up.to(DEV)), ptr(save), ptr(out), ptr(dev["weight_hh_l0"]), rev("weight_hh_l0"), ptr(lengths),
+                        ptr(dgx), ptr(dgh), ptr(hprev), R, L, H, dirs, st)
+    dx = torch.zeros(R * L, E, device=DEV)
+    for d, s in enumerate(sfx):
+        gw_ih, gw_hh = torch.zeros(G, E, device=DEV), torch.zeros(G, H, device=DEV)
+        linear_dw(dgx[d].data_ptr(), G, ptr(xd), E, ptr(gw_ih), E, R * L, G, E)
+        linear_dw(dgh[d].data_ptr(), G, hprev[d].data_ptr(), H, ptr(gw_hh), H, R * L, G, H)
+        linear_dx(dgx[d].data_ptr(), G, ptr(dev["weight_ih_l0" + s]), ptr(dx), E, R * L, G, E, beta=0.0 if d == 0 else 1.0)
+        named = dict(rnn.named_parameters())
+        torch.testing.assert_close(gw_ih.cpu(), named["weight_ih_l0" + s].grad, rtol=1e-3, atol=1e-4)
+        torch.testing.assert_close(gw_hh.cpu(), named["weight_hh_l0" + s].grad, rtol=1e-3, atol=1e-4)
+        torch.testing.assert_close(dgx[d].sum((0, 1)).cpu(), named["bias_ih_l0" + s].grad, rtol=1e-3, atol=1e-4)
+        torch.testing.assert_close(dgh[d].sum((0, 1)).cpu(), named["bias_hh_l0" + s].grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(dx.view(R, L, E).cpu(), xr.grad, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["cma_train_features_igru", "seq2seq_train_features_igru", "wp_eval_igru"])
+def test_gru_instruction_encoder_training_matches_golden(name):
+    """INSTRUCTION_ENCODER.rnn_type = "GRU": logits, losses and every trainable gradient (wp_eval_igru also runs the
+    LSTM state encoders)."""
+    from test_gpu_train import check
+
+    got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, device=DEV, precision="fp32")
+    want = gold(name)
+    assert set(got) == {k for k in want if not k.startswith("_")}
+    check(got, want, 1e-3, name)

@@ -99,7 +99,7 @@ def _lstm_backward(eng, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, masks_f, T,
 
 
 def instruction_backward(eng, g: Dict[str, torch.Tensor], d_instr: torch.Tensor):
-    """BPTT of the packed (bi)LSTM instruction encoder (instruction_encoder.py:63-94) from the
+    """BPTT of the packed (bi)LSTM / (bi)GRU instruction encoder (instruction_encoder.py:63-94) from the
     gradient w.r.t. its per-token outputs ``d_instr`` (R, L, dirs*Hs): pre-activation gate gradients
     from the persistent kernel, then the weight / embedding gradients as GEMMs + a scatter."""
     net, cx, b = eng.net, eng.ctx, eng.buf
@@ -108,24 +108,34 @@ def instruction_backward(eng, g: Dict[str, torch.Tensor], d_instr: torch.Tensor)
     rnn = ie.encoder_rnn
     Hs, dirs, E = eng.Hs, eng.dirs, eng.E
     instr = b("instr_out", (R, L, dirs * Hs))
-    dgx = b("lstm_dgx", (dirs, R, L, 4 * Hs))
+    gates = 3 if isinstance(rnn, torch.nn.GRU) else 4
+    G = gates * Hs
+    dgx = b("lstm_dgx", (dirs, R, L, G))
     hprev = b("lstm_hprev", (dirs, R, L, Hs))
-    C.vlnce_lstm_seq_bwd(ptr(d_instr), ptr(b("lstm_gates", (dirs, R, L, 4 * Hs))), ptr(b("lstm_c", (dirs, R, L, Hs))),
-                         ptr(instr), ptr(rnn.weight_hh_l0), ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None,
-                         ptr(cx["lengths"]), ptr(dgx), ptr(hprev), R, L, Hs, dirs, lib.stream())
+    whh_b = ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None
+    if gates == 3:  # GRU: the hidden-side pre-activation gradient differs from the input-side one (candidate rows * r)
+        dgh = b("gru_seq_dgh", (dirs, R, L, G))
+        C.vlnce_gru_seq_bwd(ptr(d_instr), ptr(b("gru_seq_save", (dirs, R, L, 4 * Hs))), ptr(instr),
+                            ptr(rnn.weight_hh_l0), whh_b, ptr(cx["lengths"]), ptr(dgx), ptr(dgh), ptr(hprev), R, L,
+                            Hs, dirs, lib.stream())
+    else:
+        dgh = dgx
+        C.vlnce_lstm_seq_bwd(ptr(d_instr), ptr(b("lstm_gates", (dirs, R, L, 4 * Hs))), ptr(b("lstm_c", (dirs, R, L, Hs))),
+                             ptr(instr), ptr(rnn.weight_hh_l0), whh_b, ptr(cx["lengths"]), ptr(dgx), ptr(hprev), R, L,
+                             Hs, dirs, lib.stream())
     emb_in = b("instr_emb", (R * L, E)) if ie.config.sensor_uuid == "instruction" else cx["rxr"]
     emb_trainable = ie.config.sensor_uuid == "instruction" and ie.embedding_layer.weight.requires_grad
     d_emb = b("d_instr_emb", (R * L, E)) if emb_trainable else None
     for d, sfx in enumerate(["", "_reverse"][:dirs]):
-        dg = off(dgx, d * R * L * 4 * Hs)
+        dg, dh_ = off(dgx, d * R * L * G), off(dgh, d * R * L * G)
         pfx = "net.instruction_encoder.encoder_rnn."
-        linear_dw(dg, 4 * Hs, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, 4 * Hs, E)
-        linear_dw(dg, 4 * Hs, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, 4 * Hs, Hs)
-        _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, 4 * Hs)
-        _colsum(dg, 4 * Hs, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, 4 * Hs)
+        linear_dw(dg, G, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, G, E)
+        linear_dw(dh_, G, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, G, Hs)
+        _colsum(dg, G, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, G)
+        _colsum(dh_, G, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, G)
         if emb_trainable:
             w_ih = getattr(rnn, "weight_ih_l0" + sfx)
-            linear_dx(dg, 4 * Hs, ptr(w_ih), ptr(d_emb), E, R * L, 4 * Hs, E, beta=0.0 if d == 0 else 1.0)
+            linear_dx(dg, G, ptr(w_ih), ptr(d_emb), E, R * L, G, E, beta=0.0 if d == 0 else 1.0)
     if emb_trainable:
         el = ie.embedding_layer
         pad = -1 if el.padding_idx is None else el.padding_idx

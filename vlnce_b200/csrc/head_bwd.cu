@@ -237,6 +237,80 @@ lstm_seq_bwd_kernel(const float* __restrict__ dout,   // (R, L, dirs*H)
 }
 
 // ------------------------------------------------------------------------------------
+// GRU backward through time (packed instruction encoder with rnn_type = "GRU"), one CTA per (row, direction),
+// 3H threads.  Thread t owns hidden unit k = t % H and the gate-row third part = t / H with the transposed
+// weights W_hh[j, k], j in its third (half registers / half shared memory).  Emits d_gx (gradient w.r.t.
+// x W_ih^T + b_ih), d_gh (w.r.t. h W_hh^T + b_hh; differs in the candidate rows by the factor r) and hprev
+// (h fed to each step) — all zero beyond len; the weight gradients are GEMMs over them.
+// ------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(3 * H, 1)
+gru_seq_bwd_kernel(const float* __restrict__ dout,   // (R, L, dirs*H)
+                   const float* __restrict__ save,   // (dirs, R, L, 4H): r, z, n, gh_n
+                   const float* __restrict__ out,    // (R, L, dirs*H) forward outputs
+                   const float* __restrict__ whh_f, const float* __restrict__ whh_b,
+                   const int* __restrict__ lengths, float* __restrict__ dgx, float* __restrict__ dgh,  // (dirs,R,L,3H)
+                   float* __restrict__ hprev,                                                         // (dirs,R,L,H)
+                   int R, int L, int dirs) {
+  constexpr int G = 3 * H;
+  constexpr int JR = H / 2;
+  constexpr int JS = H - JR;
+  extern __shared__ __align__(16) float smem_g[];
+  float* w_s = smem_g;                      // [JS][G]: w_s[jj][t] = W[part*H + JR + jj, k]
+  float* dp_s = w_s + (size_t)JS * G;       // G: d_gh of this step
+  float* red_s = dp_s + G;                  // G partial sums
+  const int r = blockIdx.x, dir = blockIdx.y;
+  const int t = threadIdx.x, k = t % H, part = t / H;
+  const float* whh = dir == 0 ? whh_f : whh_b;
+  float w[JR];
+#pragma unroll
+  for (int jj = 0; jj < JR; ++jj) w[jj] = __ldg(whh + (size_t)(part * H + jj) * H + k);
+  for (int jj = 0; jj < JS; ++jj) w_s[(size_t)jj * G + t] = __ldg(whh + (size_t)(part * H + JR + jj) * H + k);
+  const int len = min(lengths[r], L);
+  const size_t row_base = ((size_t)dir * R + r) * L;
+  const int DH = dirs * H;
+  float dh_carry = 0.f, dh_direct = 0.f;  // meaningful for part == 0 threads (unit k)
+  __syncthreads();
+  for (int step = len - 1; step >= 0; --step) {
+    const int tt = dir == 0 ? step : len - 1 - step;
+    const int tp = dir == 0 ? tt - 1 : tt + 1;
+    if (part == 0) {
+      const float* sv = save + (row_base + tt) * 4 * H;
+      const float rg = sv[k], zg = sv[H + k], ng = sv[2 * H + k], ghn = sv[3 * H + k];
+      const float hp = step > 0 ? out[((size_t)r * L + tp) * DH + dir * H + k] : 0.f;
+      hprev[(row_base + tt) * H + k] = hp;
+      const float dh = dout[((size_t)r * L + tt) * DH + dir * H + k] + dh_carry;
+      const float dpn = dh * (1.f - zg) * (1.f - ng * ng);
+      const float dpz = dh * (hp - ng) * zg * (1.f - zg);
+      const float dpr = dpn * ghn * rg * (1.f - rg);
+      dh_direct = dh * zg;
+      float* ox = dgx + (row_base + tt) * G;
+      ox[k] = dpr; ox[H + k] = dpz; ox[2 * H + k] = dpn;
+      float* oh = dgh + (row_base + tt) * G;
+      oh[k] = dpr; oh[H + k] = dpz; oh[2 * H + k] = dpn * rg;
+      dp_s[k] = dpr; dp_s[H + k] = dpz; dp_s[2 * H + k] = dpn * rg;
+    }
+    __syncthreads();
+    float a0 = 0.f, a1 = 0.f;
+    const float* dp = dp_s + part * H;
+#pragma unroll
+    for (int jj = 0; jj < JR; jj += 2) {
+      a0 = fmaf(w[jj], dp[jj], a0);
+      a1 = fmaf(w[jj + 1], dp[jj + 1], a1);
+    }
+#pragma unroll 8
+    for (int jj = 0; jj < JS; jj += 2) {
+      a0 = fmaf(w_s[(size_t)jj * G + t], dp[JR + jj], a0);
+      a1 = fmaf(w_s[(size_t)(jj + 1) * G + t], dp[JR + jj + 1], a1);
+    }
+    red_s[t] = a0 + a1;
+    __syncthreads();
+    if (part == 0) dh_carry = dh_direct + (red_s[k] + red_s[H + k]) + red_s[2 * H + k];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Gradient of a final-state-only sequence encoder (instruction_encoder.py:87-90, h_n of the packed
 // sequence = the output at token lengths[r]-1): dout (R, L, H) = 0 except dout[r, lengths[r]-1, :] = dh[r].
 // ------------------------------------------------------------------------------------
@@ -532,6 +606,32 @@ extern "C" int vlnce_lstm_seq_bwd(const float* dout, const float* gates, const f
   lstm_seq_bwd_kernel<H_><<<grid, 4 * H_, smem, stream>>>(dout, gates, cs, out, whh_f, whh_b, lengths, dgx, hprev,
                                                         R, L, dirs);
   VLNCE_LAUNCH_CHECK("lstm_seq_bwd_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_gru_seq_bwd(const float* dout, const float* save, const float* out, const float* whh_f,
+                                 const float* whh_b, const int* lengths, float* dgx, float* dgh, float* hprev, int R,
+                                 int L, int H, int dirs, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(dout && save && out && whh_f && lengths && dgx && dgh && hprev && R > 0 && L > 0 &&
+                      (dirs == 1 || dirs == 2) && (dirs == 1 || whh_b),
+                  "gru_seq_bwd: bad arguments");
+  VLNCE_CHECK_ARG(H == 128, "gru_seq_bwd: hidden size %d not built (128 only)", H);
+  cudaError_t e = cudaMemsetAsync(dgx, 0, sizeof(float) * (size_t)dirs * R * L * 3 * H, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dgh, 0, sizeof(float) * (size_t)dirs * R * L * 3 * H, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(hprev, 0, sizeof(float) * (size_t)dirs * R * L * H, stream);
+  if (e != cudaSuccess) return cuda_status(e, "gru_seq_bwd memset");
+  constexpr int H_ = 128;
+  const size_t smem = sizeof(float) * ((size_t)(H_ / 2) * 3 * H_ + 6 * H_);
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(gru_seq_bwd_kernel<H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gru_seq_bwd)");
+    configured = true;
+  }
+  dim3 grid(R, dirs);
+  gru_seq_bwd_kernel<H_><<<grid, 3 * H_, smem, stream>>>(dout, save, out, whh_f, whh_b, lengths, dgx, dgh, hprev, R, L,
+                                                       dirs);
+  VLNCE_LAUNCH_CHECK("gru_seq_bwd_kernel");
   return VLNCE_OK;
 }
 

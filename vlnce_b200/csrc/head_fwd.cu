@@ -155,6 +155,88 @@ lstm_seq_fwd_kernel(const float* __restrict__ gx,   // (dirs, R, L, 4H) = x W_ih
 }
 
 // ------------------------------------------------------------------------------------
+// Persistent GRU recurrence (instruction_encoder.py:27,80-84 with INSTRUCTION_ENCODER.rnn_type = "GRU":
+// torch.nn.GRU on a packed sequence): one CTA per (row, direction), 3H threads; thread j owns row j of W_hh
+// (half in registers, half in shared memory) for all L steps.  gx = x W_ih^T + b_ih comes from one GEMM; b_hh
+// is added here because the candidate gate needs r * (W_hn h + b_hn).  Gate order r, z, n (PyTorch).
+// Steps t >= len are skipped (outputs stay zero); the reverse direction starts at each row's last token.
+// ------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(3 * H, 1)
+gru_seq_fwd_kernel(const float* __restrict__ gx,   // (dirs, R, L, 3H)
+                   const float* __restrict__ whh_f, const float* __restrict__ whh_b,  // (3H, H) per direction
+                   const float* __restrict__ bhh_f, const float* __restrict__ bhh_b,  // (3H) per direction
+                   const int* __restrict__ lengths, float* __restrict__ out,  // (R, L, dirs*H)
+                   float* __restrict__ hn,     // (dirs, R, H) or null
+                   float* __restrict__ save,   // (dirs, R, L, 4H): r, z, n, W_hn h + b_hn, or null
+                   int R, int L, int dirs) {
+  constexpr int G = 3 * H;
+  constexpr int KR = H / 2;
+  constexpr int KS4 = (H - KR) / 4;
+  extern __shared__ __align__(16) float gru_smem[];
+  float4* w_s = reinterpret_cast<float4*>(gru_smem);  // KS4 * G float4, [k/4][j]
+  float* h_s = gru_smem + (size_t)KS4 * G * 4;         // H
+  float* g_s = h_s + H;                                // G: W_hh h + b_hh of this step
+  const int r = blockIdx.x, dir = blockIdx.y;
+  const int j = threadIdx.x;
+  float w[KR];
+  {
+    const float4* wp = reinterpret_cast<const float4*>((dir == 0 ? whh_f : whh_b) + (size_t)j * H);
+#pragma unroll
+    for (int k = 0; k < KR / 4; ++k) {
+      const float4 t4 = __ldg(wp + k);
+      w[4 * k] = t4.x; w[4 * k + 1] = t4.y; w[4 * k + 2] = t4.z; w[4 * k + 3] = t4.w;
+    }
+#pragma unroll
+    for (int k = 0; k < KS4; ++k) w_s[k * G + j] = __ldg(wp + KR / 4 + k);
+  }
+  const int len = min(lengths[r], L);
+  const float bh = __ldg((dir == 0 ? bhh_f : bhh_b) + j);
+  if (j < H) h_s[j] = 0.f;
+  __syncthreads();
+  const size_t row_base = ((size_t)dir * R + r) * L;
+  for (int step = 0; step < len; ++step) {
+    const int t = dir == 0 ? step : len - 1 - step;
+    float a0 = bh, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KR; k += 4) {
+      const float4 h4 = *reinterpret_cast<const float4*>(&h_s[k]);
+      a0 = fmaf(w[k], h4.x, a0);
+      a1 = fmaf(w[k + 1], h4.y, a1);
+      a2 = fmaf(w[k + 2], h4.z, a2);
+      a3 = fmaf(w[k + 3], h4.w, a3);
+    }
+#pragma unroll
+    for (int k = 0; k < KS4; ++k) {
+      const float4 w4 = w_s[k * G + j];
+      const float4 h4 = *reinterpret_cast<const float4*>(&h_s[KR + 4 * k]);
+      a0 = fmaf(w4.x, h4.x, a0);
+      a1 = fmaf(w4.y, h4.y, a1);
+      a2 = fmaf(w4.z, h4.z, a2);
+      a3 = fmaf(w4.w, h4.w, a3);
+    }
+    g_s[j] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (j < H) {
+      const float* x = gx + (row_base + t) * G;
+      const float rg = sigmoid_precise(__ldg(x + j) + g_s[j]);
+      const float zg = sigmoid_precise(__ldg(x + H + j) + g_s[H + j]);
+      const float ghn = g_s[2 * H + j];
+      const float ng = tanhf(fmaf(rg, ghn, __ldg(x + 2 * H + j)));
+      const float h = fmaf(zg, h_s[j] - ng, ng);  // (1-z) n + z h
+      h_s[j] = h;
+      out[((size_t)r * L + t) * (dirs * H) + dir * H + j] = h;
+      if (save != nullptr) {
+        float* sv = save + (row_base + t) * 4 * H;
+        sv[j] = rg; sv[H + j] = zg; sv[2 * H + j] = ng; sv[3 * H + j] = ghn;
+      }
+    }
+    __syncthreads();
+  }
+  if (hn != nullptr && j < H) hn[((size_t)dir * R + r) * H + j] = h_s[j];
+}
+
+// ------------------------------------------------------------------------------------
 // GRU cell pointwise (habitat_baselines v0.1.7 rnn_state_encoder single step; torch.nn.GRU):
 //   r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r * gh_n), h' = (1-z) n + z h
 // gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (both (rows, 3H)) come from the GEMM; h is the
@@ -417,6 +499,30 @@ extern "C" int vlnce_lstm_seq_fwd(const float* gx, const float* whh_f, const flo
   lstm_seq_fwd_kernel<H_><<<grid, 4 * H_, smem, stream>>>(gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save_gates,
                                                         save_c, R, L, dirs);
   VLNCE_LAUNCH_CHECK("lstm_seq_fwd_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_gru_seq_fwd(const float* gx, const float* whh_f, const float* whh_b, const float* bhh_f,
+                                 const float* bhh_b, const int* lengths, float* out, float* hn, float* save, int R,
+                                 int L, int H, int dirs, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(gx && whh_f && bhh_f && lengths && out && R > 0 && L > 0 && (dirs == 1 || dirs == 2),
+                  "gru_seq_fwd: bad arguments");
+  VLNCE_CHECK_ARG(dirs == 1 || (whh_b && bhh_b), "gru_seq_fwd: reverse-direction weights missing");
+  VLNCE_CHECK_ARG(H == 128, "gru_seq_fwd: hidden size %d not built (128 only)", H);
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)R * L * dirs * H, stream);
+  if (e != cudaSuccess) return cuda_status(e, "gru_seq_fwd memset");
+  dim3 grid(R, dirs);
+  constexpr int H_ = 128;
+  const size_t smem = sizeof(float) * ((size_t)(H_ / 2) * 3 * H_ + H_ + 3 * H_);
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(gru_seq_fwd_kernel<H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gru_seq_fwd)");
+    configured = true;
+  }
+  gru_seq_fwd_kernel<H_><<<grid, 3 * H_, smem, stream>>>(gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save, R, L,
+                                                       dirs);
+  VLNCE_LAUNCH_CHECK("gru_seq_fwd_kernel");
   return VLNCE_OK;
 }
 

@@ -1,5 +1,5 @@
 """Instruction encoder parameter container (``instruction_encoder.py:11-94``); the forward
-(embedding gather, lengths, input projection, persistent (bi)LSTM) runs in the CUDA library
+(embedding gather, lengths, input projection, persistent (bi)LSTM or (bi)GRU) runs in the CUDA library
 and is sequenced by ``vlnce_b200.engine``."""
 from __future__ import annotations
 
@@ -14,10 +14,9 @@ class InstructionEncoder(nn.Module):
     def __init__(self, config):
         super().__init__()
         self.config = config
-        if config.rnn_type != "LSTM":
-            raise NotImplementedError("INSTRUCTION_ENCODER.rnn_type=GRU is not built (every recipe uses LSTM)")
-        self.encoder_rnn = nn.LSTM(input_size=config.embedding_size, hidden_size=config.hidden_size,
-                                   bidirectional=config.bidirectional)
+        rnn = nn.GRU if config.rnn_type == "GRU" else nn.LSTM  # instruction_encoder.py:27
+        self.encoder_rnn = rnn(input_size=config.embedding_size, hidden_size=config.hidden_size,
+                               bidirectional=config.bidirectional)
         if config.sensor_uuid == "instruction":
             if config.use_pretrained_embeddings:
                 with gzip.open(config.embedding_file, "rt") as f:

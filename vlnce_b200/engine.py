@@ -150,7 +150,7 @@ class HeadEngine:
         return rnn_states, masks_f, prev.contiguous(), R, N, R // N
 
     def _encode_instruction(self, observations, R, save):
-        """instruction_encoder.py:63-94: lengths, embedding, input projection, persistent LSTM.
+        """instruction_encoder.py:63-94: lengths, embedding, input projection, persistent LSTM / GRU.
         Returns (per-token outputs (R,L,dirs*Hs), final states (dirs,R,Hs), lengths, L)."""
         ie = self.net.instruction_encoder
         st = lib.stream()
@@ -174,19 +174,26 @@ class HeadEngine:
             C.vlnce_feature_lengths(ptr(emb), ptr(lengths), R, L, E, st)
             self.ctx["rxr"] = emb
         rnn = ie.encoder_rnn
-        gx = self.buf("lstm_gx", (dirs, R, L, 4 * Hs))
+        gates = 3 if isinstance(rnn, torch.nn.GRU) else 4  # r,z,n | i,f,g,o
+        gx = self.buf("lstm_gx", (dirs, R, L, gates * Hs))
         wih = [rnn.weight_ih_l0] + ([rnn.weight_ih_l0_reverse] if dirs == 2 else [])
         bih = [rnn.bias_ih_l0] + ([rnn.bias_ih_l0_reverse] if dirs == 2 else [])
         for d in range(dirs):
-            linear(ptr(emb), E, ptr(wih[d]), off(gx, d * R * L * 4 * Hs), 4 * Hs, ptr(bih[d]), R * L, 4 * Hs, E)
+            linear(ptr(emb), E, ptr(wih[d]), off(gx, d * R * L * gates * Hs), gates * Hs, ptr(bih[d]), R * L,
+                   gates * Hs, E)
         instr = self.buf("instr_out", (R, L, dirs * Hs))
         hn = self.buf("lstm_hn", (dirs, R, Hs))
+        whh_b = ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None
+        bhh_b = ptr(rnn.bias_hh_l0_reverse) if dirs == 2 else None
+        if gates == 3:  # INSTRUCTION_ENCODER.rnn_type = "GRU": final_state is h_n itself (instruction_encoder.py:86-87)
+            sv = self.buf("gru_seq_save", (dirs, R, L, 4 * Hs)) if save else None
+            C.vlnce_gru_seq_fwd(ptr(gx), ptr(rnn.weight_hh_l0), whh_b, ptr(rnn.bias_hh_l0), bhh_b, ptr(lengths),
+                                ptr(instr), ptr(hn), ptr(sv), R, L, Hs, dirs, st)
+            return instr, hn, lengths, L
         sg = self.buf("lstm_gates", (dirs, R, L, 4 * Hs)) if save else None
         sc = self.buf("lstm_c", (dirs, R, L, Hs)) if save else None
-        C.vlnce_lstm_seq_fwd(ptr(gx), ptr(rnn.weight_hh_l0),
-                             ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None, ptr(rnn.bias_hh_l0),
-                             ptr(rnn.bias_hh_l0_reverse) if dirs == 2 else None, ptr(lengths), ptr(instr),
-                             ptr(hn), ptr(sg), ptr(sc), R, L, Hs, dirs, st)
+        C.vlnce_lstm_seq_fwd(ptr(gx), ptr(rnn.weight_hh_l0), whh_b, ptr(rnn.bias_hh_l0), bhh_b, ptr(lengths),
+                             ptr(instr), ptr(hn), ptr(sg), ptr(sc), R, L, Hs, dirs, st)
         return instr, hn, lengths, L
 
     # ------------------------------------------------------------------ state-encoder helper
