@@ -124,6 +124,10 @@ int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w_dtype, con
  * permute + /255 + conv1; the /255 and optional mean/std live in the folded scale/shift). */
 int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int a_dtype, int N, int H, int W,
                           cudaStream_t stream);
+/* MODEL.normalize_rgb = True (resnet_encoders.py:171-192, config/default.py:216): y (pixels,3) f32 = x - (m0,m1,m2),
+ * m = 255 * ImageNet mean; 1/std is folded into the stem weights and 1/255 into the stem scale by the caller. */
+int vlnce_rgb_center(const void* x, int x_dtype, float* y, float m0, float m1, float m2, long long pixels,
+                     cudaStream_t stream);
 /* Depth stem operand: depth (N,H,W,1) f32 -> avg_pool2d(2) -> 7x7/2 pad-3 im2col rows
  * (N*P*Q, 64) bf16|f16, K index r*7+s, zero padded 49..63 (habitat_baselines v0.1.7
  * ResNetEncoder.forward: permute, avg_pool2d(2), backbone.conv1). */

@@ -72,6 +72,11 @@ CASES = {
                                         wseed=40, iseed=140, bn_train=False, features=True, instr_rnn="GRU"),
     "wp_eval_igru": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=41, iseed=141,
                          instr_rnn="GRU", state_rnn="LSTM"),
+    # MODEL.normalize_rgb = True (config/default.py:216; resnet_encoders.py:171-192): ImageNet mean / std on the RGB
+    "cma_act_nrgb": dict(policy="CMAPolicy", pm=False, kind="act", n=2, hw=256, rgb_hw=224, length=24, wseed=42,
+                         iseed=142, bn_train=False, normalize_rgb=True),
+    "wp_act_nrgb": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=24, wseed=43, iseed=143,
+                        normalize_rgb=True, rgb_u8=True),
     "wp_eval_abl": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=34, iseed=134,
                         ablate=("instruction", "depth")),
     # Waypoint path (BASELINE config C4 dims, 1-wpn-cc.yaml): act on a fresh/continuing env pair,
@@ -112,6 +117,8 @@ def model_config(case) -> hb017.Config:
     abl = {"ablate_" + k: True for k in case.get("ablate", ())}
     if case.get("state_rnn"):
         abl["STATE_ENCODER"] = dict(rnn_type=case["state_rnn"])
+    if case.get("normalize_rgb"):
+        abl["normalize_rgb"] = True
     if case.get("instr_rnn"):
         abl["INSTRUCTION_ENCODER"] = dict(rnn_type=case["instr_rnn"])
     if case["policy"] == "WaypointPolicy":

@@ -975,6 +975,11 @@ class TensorCoreOps:
         wt = _tt16(w, (K, 192), w_code).float()[:, :147].reshape(K, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
         _epilogue(Fn.conv2d(xi, wt, stride=2, padding=3), scale, shift, 0, 0, relu, y, y_dtype, None)
 
+    def rgb_center(self, x, x_code, y, m0, m1, m2, pixels, st):
+        import torch
+
+        _tt(y, (pixels, 3)).copy_(_tt16(x, (pixels, 3), x_code).float() - torch.tensor([m0, m1, m2]))
+
     def im2col_depth_stem(self, x, a, a_code, N, H, W, st):
         import torch.nn.functional as Fn
 

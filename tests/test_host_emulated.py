@@ -407,7 +407,7 @@ def test_ddppo_collect_and_update_loop_matches_oracle():
 # raw-pixel paths in the fp32 precision mode: the conv-trunk launch plans (trunk.py) on the emulator as well
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["cma_act", "cma_act_bntrain", "cma_act_rgb224", "seq2seq_act", "cma_train_pixels",
-                                  "cma_act_lstm"])
+                                  "cma_act_lstm", "cma_act_nrgb"])
 def test_pixel_paths_fp32_match_golden(name):
     """Both conv trunks from raw pixels in ``precision="fp32"`` (vlnce_conv2d_ref + GroupNorm / BatchNorm / pooling
     kernels, modelled with torch CPU ops): block wiring, residual and downsample routing, folded eval-mode and
@@ -417,16 +417,19 @@ def test_pixel_paths_fp32_match_golden(name):
     print(name, "worst", check(got, gold(name), 3e-4))
 
 
-def test_waypoint_pixel_path_fp32_matches_golden():
+@pytest.mark.parametrize("name", ["wp_act", "wp_act_nrgb"])
+def test_waypoint_pixel_path_fp32_matches_golden(name):
     """WaypointPolicy.act from raw pano pixels (ResNet-18 + DD-PPO ResNet-50 over the stacked frames), no trunk
-    substitution."""
-    with lib.dry_run(executor=Emulator()):
-        got = cases.run_case(vlnce_b200, "wp_act", aux=vlnce_b200.AuxLosses, precision="fp32")
-    print("wp_act pixels worst", check(got, gold("wp_act"), 3e-4))
+    substitution; ``wp_act_nrgb``: uint8 frames with MODEL.normalize_rgb."""
+    with lib.dry_run(executor=Emulator()) as rec:
+        got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, precision="fp32")
+    assert ("vlnce_rgb_center" in rec.calls) == name.endswith("nrgb")
+    print(name, "pixels worst", check(got, gold(name), 3e-4))
 
 
 @pytest.mark.parametrize("name,tol", [("cma_act", 1e-2), ("cma_act_rgb224", 1e-2), ("cma_act_bntrain", 2e-2),
-                                      ("seq2seq_act", 1e-2), ("wp_act", 2e-2)])
+                                      ("seq2seq_act", 1e-2), ("wp_act", 2e-2), ("cma_act_nrgb", 1e-2),
+                                      ("wp_act_nrgb", 2e-2)])
 def test_pixel_paths_16bit_packing_matches_golden(name, tol):
     """The default 16-bit trunk paths on functional models of the tensor-core entry points: what is checked on the
     host is trunk.py's operand packing and routing — KRSC weights, the 2x2 space-to-depth RGB stem (cell image +

@@ -153,3 +153,26 @@ def test_gru_instruction_encoder_training_matches_golden(name):
     want = gold(name)
     assert set(got) == {k for k in want if not k.startswith("_")}
     check(got, want, 1e-3, name)
+
+
+def test_rgb_center_kernel():
+    g0 = torch.Generator().manual_seed(2)
+    for dt in (torch.uint8, torch.float32):
+        x = torch.randint(0, 256, (3, 17, 19, 3), generator=g0).to(dt).to(DEV)
+        y = torch.empty(3, 17, 19, 3, device=DEV)
+        C.vlnce_rgb_center(ptr(x), lib.code(x), ptr(y), 123.675, 116.28, 103.53, 3 * 17 * 19, lib.stream())
+        want = x.float() - torch.tensor([123.675, 116.28, 103.53], device=DEV)
+        assert torch.equal(y, want)
+
+
+@pytest.mark.parametrize("name", ["cma_act_nrgb", "wp_act_nrgb"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_normalize_rgb_matches_golden(name, precision, tol):
+    """MODEL.normalize_rgb = True: ImageNet mean / std ahead of the RGB trunk (centring pre-pass + 1/std folded into
+    the stem weights), from raw pixels, against the reference goldens."""
+    got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, device=DEV, precision=precision)
+    want = gold(name)
+    logits = "pano_stop_logits" if name.startswith("wp_") else "logits"
+    p, q = got[logits].exp(), want[logits].exp()
+    assert float((p - q).abs().max() / q.abs().max()) < tol
+    assert float((got["rnn_states_out"] - want["rnn_states_out"]).norm() / want["rnn_states_out"].norm()) < tol

@@ -609,6 +609,36 @@ extern "C" int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w
   return VLNCE_ERR_INVALID_ARGUMENT;
 }
 
+// ------------------------------------------------------------------------------------
+// MODEL.normalize_rgb = True (resnet_encoders.py:171-192): (x/255 - mean_c) / std_c.  The per-channel 1/std is
+// folded into the stem weights' input channels and the 1/255 into the stem epilogue scale, so only the mean has
+// to be removed ahead of the zero-padded stem conv: y = x - 255 mean_c (fp32; the padding stays an exact 0 as in
+// the reference, where it is applied after the normalisation).
+// ------------------------------------------------------------------------------------
+template <typename TX>
+__global__ void rgb_center_kernel(const TX* __restrict__ x, float* __restrict__ y, float m0, float m1, float m2,
+                                  long long pixels) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels;
+       i += (long long)gridDim.x * blockDim.x) {
+    const TX* p = x + 3 * i;
+    float* o = y + 3 * i;
+    o[0] = (float)p[0] - m0;
+    o[1] = (float)p[1] - m1;
+    o[2] = (float)p[2] - m2;
+  }
+}
+
+extern "C" int vlnce_rgb_center(const void* x, int x_dtype, float* y, float m0, float m1, float m2, long long pixels,
+                                cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && y && pixels > 0, "rgb_center: bad arguments");
+  VLNCE_CHECK_ARG(x_dtype == VLNCE_U8 || x_dtype == VLNCE_F32, "rgb_center: rgb must be u8 or f32");
+  const unsigned grid = grid_for(pixels, 256);
+  if (x_dtype == VLNCE_U8) rgb_center_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)x, y, m0, m1, m2, pixels);
+  else rgb_center_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, y, m0, m1, m2, pixels);
+  VLNCE_LAUNCH_CHECK("rgb_center_kernel");
+  return VLNCE_OK;
+}
+
 extern "C" int vlnce_im2col_rgb_stem(const void* x, int x_dtype, void* a, int a_dtype, int N, int H, int W,
                                      cudaStream_t stream) {
   VLNCE_CHECK_ARG(x && a && N > 0 && H > 0 && W > 0, "im2col_rgb_stem: bad arguments");

@@ -184,13 +184,13 @@ class _RGBSequential(nn.Sequential):
 
     out_hw = 4
 
-    def trunk(self, precision) -> RGBTrunk:
+    def trunk(self, precision, normalize: bool = False) -> RGBTrunk:
         dev = self[0].weight.device
         cache = self.__dict__.setdefault("_trunks", {})
         half = torch.float16 if self[1].training else torch.bfloat16
-        key = (precision, dev, half)
+        key = (precision, dev, half, bool(normalize))
         if key not in cache:
-            cache[key] = RGBTrunk(self, dev, precision, half)
+            cache[key] = RGBTrunk(self, dev, precision, half, normalize=normalize)
         return cache[key]
 
     def forward(self, x):
@@ -224,9 +224,7 @@ class TorchVisionResNet(nn.Module):
 
         if trainable:
             raise NotImplementedError("RGB_ENCODER.trainable=True (trunk backward) is SURVEY 8f N4")
-        if normalize_visual_inputs:
-            raise NotImplementedError("MODEL.normalize_rgb=True is not built yet (default False)")
-        self.normalize_visual_inputs = normalize_visual_inputs
+        self.normalize_visual_inputs = normalize_visual_inputs  # MODEL.normalize_rgb (config/default.py:216)
         self.spatial_output = spatial_output
         # reference: pretrained=True (resnet_encoders.py:136); no network here -> seeded init,
         # real weights arrive through load_state_dict.
@@ -274,7 +272,7 @@ class TorchVisionResNet(nn.Module):
             lib.require_cuda(rgb, "rgb")
             if rgb.dtype not in (torch.uint8, torch.float32):
                 rgb = rgb.float()
-            self.cnn.trunk(precision).forward(rgb.contiguous(), out, ld, o)
+            self.cnn.trunk(precision, self.normalize_visual_inputs).forward(rgb.contiguous(), out, ld, o)
             nchw = None
         _run_hooks(self.cnn, observations, out, ld, c, o, o, nchw)
 

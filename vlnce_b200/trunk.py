@@ -96,8 +96,9 @@ class _Conv:
     """One packed convolution (+ its normalisation)."""
 
     def __init__(self, conv: nn.Conv2d, norm: nn.Module, precision: str, in_scale: float = 1.0,
-                 stem: Optional[str] = None, wdt=torch.bfloat16):
+                 stem: Optional[str] = None, wdt=torch.bfloat16, in_chan_scale=None):
         self.conv, self.norm, self.precision, self.in_scale, self.stem = conv, norm, precision, in_scale, stem
+        self.in_chan_scale = in_chan_scale  # per-input-channel factor folded into the packed weights (1/std)
         self.wdt = wdt if precision == "bf16" else torch.float32
         self.K, self.Cin, self.R, self.S = conv.weight.shape
         self.stride, self.pad = conv.stride[0], conv.padding[0]
@@ -115,6 +116,8 @@ class _Conv:
         if ver == self._ver:
             return
         w = self.conv.weight.detach()
+        if self.in_chan_scale is not None:
+            w = w * torch.tensor(self.in_chan_scale, device=w.device, dtype=w.dtype).view(1, -1, 1, 1)
         wdt = self.wdt
         krsc = w.permute(0, 2, 3, 1).contiguous()
         if self.precision == "bf16" and self.stem == "rgb":  # im2col operand: (r*7+s)*3+c, pad 147->192
@@ -284,14 +287,21 @@ class RGBTrunk(ConvTrunk):
 
     exclusive = RGB_EXCLUSIVE
 
-    def __init__(self, cnn: nn.Sequential, device, precision="bf16", half_dtype=torch.bfloat16):
+    # MODEL.normalize_rgb (resnet_encoders.py:181-190): ImageNet statistics
+    MEAN, STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+    def __init__(self, cnn: nn.Sequential, device, precision="bf16", half_dtype=torch.bfloat16, normalize=False):
         # eval-mode (folded) BatchNorm leaves the residual stream unbounded -> bf16 range;
         # train-mode BatchNorm renormalises every layer to O(1) -> fp16 precision.
         self.half_dtype = half_dtype
         super().__init__(device, precision)
         mods = list(cnn.children())
         _C = lambda c, g, p, **kw: _Conv(c, g, p, wdt=half_dtype, **kw)  # noqa: E731
-        self.stem = _C(mods[0], mods[1], precision, in_scale=1.0 / 255.0, stem="rgb")
+        # normalize: (x/255 - mean)/std = (x - 255 mean) * (1/255) * (1/std): the centring is a pre-pass over the
+        # pixels (the conv's zero padding is applied after the normalisation), 1/std goes into the weights
+        self.normalize = bool(normalize)
+        self.stem = _C(mods[0], mods[1], precision, in_scale=1.0 / 255.0, stem="rgb",
+                       in_chan_scale=[1.0 / v for v in self.STD] if normalize else None)
         self.blocks = []
         for layer in mods[4:8]:
             for blk in layer.children():
@@ -346,6 +356,10 @@ class RGBTrunk(ConvTrunk):
             cv.pack()
         n, h, w, _ = rgb.shape
         st = lib.stream()
+        if self.normalize:
+            centred = self.pool.get("rgb_centred", (n, h, w, 3), torch.float32)
+            C.vlnce_rgb_center(ptr(rgb), lib.code(rgb), ptr(centred), *(255.0 * m for m in self.MEAN), n * h * w, st)
+            rgb = centred
         cv = self.stem
         p, q = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
         x = None
