@@ -312,6 +312,17 @@ int vlnce_adam_step(float* p, const float* g, float* m, float* v, long long n, f
  * t >= lengths[n] (lengths may be NULL: no padding). */
 int vlnce_inflection_weights(const long long* actions, const int* lengths, float* weights, int T, int N, float coef,
                              cudaStream_t stream);
+/* Device-resident trajectory cache — batch assembly of dagger_trainer.py:39-114 (collate_fn) + :189-211
+ * + the float32 staging of :560-566 in one launch per observation key: arena holds the trajectories' rows back to
+ * back (dtype VLNCE_F32 | F16 (IL.DAGGER.lmdb_fp16) | BF16 | U8 | I64), trajectory n starts at element offsets[n] and
+ * has lengths[n] rows of D elements; out (T*N, D) f32 time-major, rows t >= lengths[n] = pad (1.0 for observations). */
+int vlnce_collate_rows(const void* arena, int dtype, const long long* offsets, const int* lengths, float* out, int T,
+                       int N, long long D, float pad, cudaStream_t stream);
+/* ... and the (T,N) matrices of the same batch: prev / oracle actions padded with 0, inflection weights
+ * ([1, coef][a_t != a_{t-1}], first step an inflection, 0 in the padding), not_done_masks (0 on the first row block). */
+int vlnce_collate_actions(const long long* prev_arena, const long long* act_arena, const long long* offsets,
+                          const int* lengths, long long* prev_out, long long* act_out, float* weights,
+                          unsigned char* masks, int T, int N, float coef, cudaStream_t stream);
 /* device-resident step counter for graph replays; y += alpha * x for gradient accumulation
  * (loss_accumulation_scalar, base_il_trainer.py:170-176) */
 int vlnce_counter_add(int* counter, int value, cudaStream_t stream);

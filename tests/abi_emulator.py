@@ -1082,3 +1082,51 @@ Emulator.maxpool3x3s2 = _maxpool3x3s2
 Emulator.adaptive_avgpool = _adaptive_avgpool
 Emulator.affine_apply = _affine_apply
 Emulator.batchnorm_train_stats = _batchnorm_train_stats
+
+
+# ======================================================================================
+# device-resident trajectory cache (vlnce_b200/feature_cache.py, csrc/cache_ops.cu)
+# ======================================================================================
+_CACHE_NP = {0: np.float32, 2: np.uint8, 3: np.int64, 4: np.float16}
+
+
+def _collate_rows(self, arena, dtype, offsets, lengths, out, T, N, D, pad, st):
+    offs, lens = _flat(offsets, N, I64), _flat(lengths, N, I32)
+    o = _flat(out, T * N * D).reshape(T, N, D)
+    o[...] = pad
+    for n in range(N):
+        ln = min(int(lens[n]), T)
+        if dtype == 1:  # bf16
+            import torch
+
+            src = _tt16(int(arena) + 2 * int(offs[n]), (ln, D), 1).float().numpy()
+        else:
+            nt = _CACHE_NP[dtype]
+            ct = np.ctypeslib.as_ctypes_type(np.uint16 if nt is np.float16 else nt)
+            raw = np.ctypeslib.as_array(ctypes.cast(int(arena) + int(offs[n]) * np.dtype(nt).itemsize, ctypes.POINTER(ct)),
+                                        shape=(ln * D,))
+            src = raw.view(nt).reshape(ln, D).astype(np.float32)
+        o[:ln, n] = src
+
+
+def _collate_actions(self, prev_arena, act_arena, offsets, lengths, prev_out, act_out, weights, masks, T, N, coef, st):
+    offs, lens = _flat(offsets, N, I64), _flat(lengths, N, I32)
+    po, ao = _flat(prev_out, T * N, I64).reshape(T, N), _flat(act_out, T * N, I64).reshape(T, N)
+    w = _flat(weights, T * N).reshape(T, N)
+    m = np.ctypeslib.as_array(ctypes.cast(int(masks), ctypes.POINTER(ctypes.c_uint8)), shape=(T * N,)).reshape(T, N)
+    po[...] = 0
+    ao[...] = 0
+    w[...] = 0
+    m[...] = 1
+    m[0] = 0
+    for n in range(N):
+        ln = int(lens[n])
+        a = _flat(int(act_arena) + 8 * int(offs[n]), ln, I64)
+        po[:ln, n] = _flat(int(prev_arena) + 8 * int(offs[n]), ln, I64)
+        ao[:ln, n] = a
+        infl = np.concatenate([[True], a[1:] != a[:-1]])
+        w[:ln, n] = np.where(infl, np.float32(coef), np.float32(1.0))
+
+
+Emulator.collate_rows = _collate_rows
+Emulator.collate_actions = _collate_actions

@@ -176,3 +176,25 @@ def test_normalize_rgb_matches_golden(name, precision, tol):
     p, q = got[logits].exp(), want[logits].exp()
     assert float((p - q).abs().max() / q.abs().max()) < tol
     assert float((got["rnn_states_out"] - want["rnn_states_out"]).norm() / want["rnn_states_out"].norm()) < tol
+
+
+@pytest.mark.parametrize("fp16", [False, True])
+@pytest.mark.parametrize("big", [False, True], ids=["small-rows", "2048x4x4-rows"])
+def test_device_feature_cache_equals_reference_pipeline(fp16, big):
+    """vlnce_collate_rows / vlnce_collate_actions: a batch assembled from the HBM-resident cache is bit-identical to
+    IWTrajectoryDataset items -> collate_fn -> float32 staging (dagger_trainer.py:39-114,189-211,560-566), for float32
+    and lmdb_fp16 records, vectorised (D % 4 == 0) and scalar row paths."""
+    from test_feature_cache import reference_pipeline, trajectories
+    from vlnce_b200 import feature_cache
+
+    trajs = trajectories(seed=21, n=6, big=big)
+    cache = feature_cache.TrajectoryCache(DEV, fp16=fp16)
+    for obs, prev, act in trajs:
+        cache.append({k: v.to(DEV) for k, v in obs.items()}, prev, act)
+    for idx in ([0, 1, 2, 3, 4, 5], [4, 2], [3]):
+        got = cache.batch(idx, inflection_weight_coef=3.2)
+        want = reference_pipeline(trajs, idx, 3.2, fp16)
+        for k in want[0]:
+            assert got[0][k].is_cuda and torch.equal(got[0][k].cpu(), want[0][k]), k
+        for a, b in zip(got[1:], want[1:]):
+            assert a.dtype == b.dtype and torch.equal(a.cpu(), b)
