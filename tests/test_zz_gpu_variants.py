@@ -1,6 +1,9 @@
-"""Parity of the configuration variants outside the shipped recipes (``STATE_ENCODER.rnn_type = "LSTM"`` …) on the
-B200, against goldens frozen from the reference.  Collected last on purpose: these entry points were added after the
-round's final GPU visit, so under ``pytest -x`` a failure here cannot hide the results of the main parity files."""
+"""Parity of the configuration variants outside the shipped recipes (``STATE_ENCODER.rnn_type = "LSTM"``,
+``INSTRUCTION_ENCODER.rnn_type = "GRU"``, ``MODEL.normalize_rgb``) and of the device-resident DAgger feature cache on
+the B200, against torch references and goldens frozen from the reference.  Collected last on purpose: the kernel-level
+tests here ran green on the B200 in round 1 (profiles/r01_logs/test_zz_gpu_variants_kernels.log), the end-to-end golden
+cases were added after the round's GPU budget was spent, so under ``pytest -x`` a failure in them cannot hide the
+results of the main parity files."""
 import os
 import warnings
 
