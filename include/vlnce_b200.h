@@ -417,6 +417,27 @@ int vlnce_gae_returns(const float* rewards, float* value_preds, const unsigned c
                       float* returns, float* advantages, int T, int N, float gamma, float tau, int use_gae,
                       cudaStream_t stream);
 
+/* ---- backward of the conv trunks (RGB_ENCODER.trainable / DEPTH_ENCODER.trainable, config/default.py:242,253;
+ * cma_policy.py:80,94) — fp32 correctness-first path mirroring vlnce_conv2d_ref.  All tensors fp32 NHWC / KRSC. ---- */
+/* dx (N,H,W,C) (+)= dgrad of dy (N,P,Q,K) through w (K,R,S,C) */
+int vlnce_conv2d_ref_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int C, int K, int R, int S,
+                           int stride, int pad, int accumulate, cudaStream_t stream);
+/* dw (K,R,S,C) (+)= alpha * wgrad of x (N,H,W,C; f32 or the u8 image of the RGB stem) and dy (N,P,Q,K) */
+int vlnce_conv2d_ref_wgrad(const void* x, int x_dtype, const float* dy, float* dw, int N, int H, int W, int C, int K,
+                           int R, int S, int stride, int pad, float alpha, int accumulate, cudaStream_t stream);
+/* GroupNorm backward on the raw conv output x (N,HW,C): dx, and per-image partial (N,2C) = [dgamma | dbeta] */
+int vlnce_groupnorm_bwd(const float* x, const float* dy, const float* gamma, float* dx, float* partial, int N, int HW,
+                        int C, int groups, float eps, cudaStream_t stream);
+/* BatchNorm2d backward on the raw conv output x (rows,C): batch statistics (training != 0) or the running ones */
+int vlnce_batchnorm_bwd(const float* x, const float* dy, const float* gamma, const float* running_mean,
+                        const float* running_var, float* dx, float* dgamma, float* dbeta, long long rows, int C,
+                        float eps, int training, cudaStream_t stream);
+/* max_pool2d(3, stride 2, pad 1) backward: dx zeroed, gradient routed to the first maximum of each window */
+int vlnce_maxpool3x3s2_bwd(const float* x, const float* dy, float* dx, int N, int H, int W, int C, cudaStream_t stream);
+/* adaptive_avg_pool2d backward from the positions layout dout (N, O*O, ld) (channels [0,C) of each row) */
+int vlnce_adaptive_avgpool_bwd(const float* dout, long long ld, float* dx, int N, int H, int W, int C, int O,
+                               cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1130,3 +1130,79 @@ def _collate_actions(self, prev_arena, act_arena, offsets, lengths, prev_out, ac
 
 Emulator.collate_rows = _collate_rows
 Emulator.collate_actions = _collate_actions
+
+
+# ======================================================================================
+# backward of the conv trunks (csrc/trunk_bwd.cu): torch-CPU functional models
+# ======================================================================================
+class TrunkBwdOps:
+    def conv2d_ref_dgrad(self, dy, w, dx, N, H, W, C, K, R, S, stride, pad, accumulate, st):
+        import torch
+
+        P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+        g = _tt(dy, (N, P, Q, K)).permute(0, 3, 1, 2).double()
+        wt = _tt(w, (K, R, S, C)).permute(0, 3, 1, 2).double()
+        out = torch.nn.grad.conv2d_input((N, C, H, W), wt, g, stride=stride, padding=pad).permute(0, 2, 3, 1).float()
+        t = _tt(dx, (N, H, W, C))
+        t.copy_(t + out if accumulate else out)
+
+    def conv2d_ref_wgrad(self, x, x_code, dy, dw, N, H, W, C, K, R, S, stride, pad, alpha, accumulate, st):
+        import torch
+
+        P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+        xi = _tt16(x, (N, H, W, C), x_code).double().permute(0, 3, 1, 2)
+        g = _tt(dy, (N, P, Q, K)).permute(0, 3, 1, 2).double()
+        out = torch.nn.grad.conv2d_weight(xi, (K, C, R, S), g, stride=stride, padding=pad).permute(0, 2, 3, 1)
+        out = (alpha * out).float()
+        t = _tt(dw, (K, R, S, C))
+        t.copy_(t + out if accumulate else out)
+
+    def groupnorm_bwd(self, x, dy, gamma, dx, partial, N, HW, C, groups, eps, st):
+        import torch
+
+        xi = _tt(x, (N, HW, C)).double().permute(0, 2, 1).contiguous().requires_grad_()
+        gm = _tt(gamma, (C,)).double()
+        g = _tt(dy, (N, HW, C)).double().permute(0, 2, 1)
+        xr = xi.reshape(N, groups, -1)
+        xhat = ((xr - xr.mean(2, keepdim=True)) / torch.sqrt(xr.var(2, unbiased=False, keepdim=True) + eps)).view(N, C, HW)
+        (xhat * gm.view(1, C, 1) * g).sum().backward()
+        _tt(dx, (N, HW, C)).copy_(xi.grad.permute(0, 2, 1).float())
+        part = _tt(partial, (N, 2 * C))
+        part[:, :C] = (g * xhat.detach()).sum(2).float()
+        part[:, C:] = g.sum(2).float()
+
+    def batchnorm_bwd(self, x, dy, gamma, rmean, rvar, dx, dgamma, dbeta, rows, C, eps, training, st):
+        import torch
+
+        xi = _tt(x, (rows, C)).double().clone().requires_grad_()
+        g = _tt(dy, (rows, C)).double()
+        if training:
+            mean, var = xi.mean(0), xi.var(0, unbiased=False)
+        else:
+            mean, var = _tt(rmean, (C,)).double(), _tt(rvar, (C,)).double()
+        xhat = (xi - mean) / torch.sqrt(var + eps)
+        (xhat * _tt(gamma, (C,)).double() * g).sum().backward()
+        _tt(dx, (rows, C)).copy_(xi.grad.float())
+        _tt(dgamma, (C,)).copy_((g * xhat.detach()).sum(0).float())
+        _tt(dbeta, (C,)).copy_(g.sum(0).float())
+
+    def maxpool3x3s2_bwd(self, x, dy, dx, N, H, W, C, st):
+        import torch.nn.functional as Fn
+
+        P, Q = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        xi = _tt(x, (N, H, W, C)).permute(0, 3, 1, 2).clone().requires_grad_()
+        Fn.max_pool2d(xi, 3, 2, 1).backward(_tt(dy, (N, P, Q, C)).permute(0, 3, 1, 2))
+        _tt(dx, (N, H, W, C)).copy_(xi.grad.permute(0, 2, 3, 1))
+
+    def adaptive_avgpool_bwd(self, dout, ld, dx, N, H, W, C, O, st):
+        import torch
+        import torch.nn.functional as Fn
+
+        xi = torch.zeros(N, C, H, W, dtype=torch.float64, requires_grad=True)
+        g = torch.from_numpy(_ten3(dout, N, O * O, C, O * O * ld, ld).copy()).double()     # (N, OO, C)
+        Fn.adaptive_avg_pool2d(xi, (O, O)).backward(g.permute(0, 2, 1).reshape(N, C, O, O))
+        _tt(dx, (N, H, W, C)).copy_(xi.grad.permute(0, 2, 3, 1).float())
+
+
+for _name in [n for n in vars(TrunkBwdOps) if not n.startswith("_")]:
+    setattr(Emulator, _name, getattr(TrunkBwdOps, _name))

@@ -201,3 +201,13 @@ def test_device_feature_cache_equals_reference_pipeline(fp16, big):
             assert got[0][k].is_cuda and torch.equal(got[0][k].cpu(), want[0][k]), k
         for a, b in zip(got[1:], want[1:]):
             assert a.dtype == b.dtype and torch.equal(a.cpu(), b)
+
+
+# ---- keep this test LAST in the file: its kernels have never run on a GPU (written after round 1's GPU budget was
+# spent), so a device fault here must not be able to disturb any other test.  Non-strict xfail: XPASS = verified.
+@pytest.mark.xfail(strict=False, reason="trunk-backward kernels (SURVEY 8f N4): first GPU run; host model verified on CPU")
+def test_zz_trunk_backward_entry_points_first_gpu_run():
+    from test_trunk_bwd_kernels import run
+
+    run(DEV, C)
+    torch.cuda.synchronize()
