@@ -77,6 +77,13 @@ CASES = {
                          iseed=142, bn_train=False, normalize_rgb=True),
     "wp_act_nrgb": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=24, wseed=43, iseed=143,
                         normalize_rgb=True, rgb_u8=True),
+    # trainable conv trunks (config/default.py:242,253; next-row N4): gradients through both ResNets, train-mode
+    # BatchNorm in the RGB trunk (``cnn.train(trainable)`` + ``policy.train()``), GroupNorm in the depth trunk
+    "cma_train_pixels_trunks": dict(policy="CMAPolicy", pm=True, kind="train", t=2, n=2, hw=256, rgb_hw=224, length=16,
+                                    wseed=44, iseed=144, bn_train=True, features=False, trainable=("rgb", "depth")),
+    "seq2seq_train_pixels_trunks": dict(policy="Seq2SeqPolicy", pm=False, kind="train", t=2, n=2, hw=256, length=16,
+                                        wseed=45, iseed=145, bn_train=False, features=False,
+                                        trainable=("rgb", "depth")),
     "wp_eval_abl": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=34, iseed=134,
                         ablate=("instruction", "depth")),
     # Waypoint path (BASELINE config C4 dims, 1-wpn-cc.yaml): act on a fresh/continuing env pair,
@@ -117,6 +124,8 @@ def model_config(case) -> hb017.Config:
     abl = {"ablate_" + k: True for k in case.get("ablate", ())}
     if case.get("state_rnn"):
         abl["STATE_ENCODER"] = dict(rnn_type=case["state_rnn"])
+    for m in case.get("trainable", ()):
+        abl.setdefault(m.upper() + "_ENCODER", {})["trainable"] = True
     if case.get("normalize_rgb"):
         abl["normalize_rgb"] = True
     if case.get("instr_rnn"):

@@ -1135,6 +1135,17 @@ Emulator.collate_actions = _collate_actions
 # ======================================================================================
 # backward of the conv trunks (csrc/trunk_bwd.cu): torch-CPU functional models
 # ======================================================================================
+def _with_grad(fn):
+    def wrapped(*a, **k):
+        import torch
+
+        with torch.enable_grad():
+            return fn(*a, **k)
+
+    wrapped.__name__ = fn.__name__
+    return wrapped
+
+
 class TrunkBwdOps:
     def conv2d_ref_dgrad(self, dy, w, dx, N, H, W, C, K, R, S, stride, pad, accumulate, st):
         import torch
@@ -1157,6 +1168,7 @@ class TrunkBwdOps:
         t = _tt(dw, (K, R, S, C))
         t.copy_(t + out if accumulate else out)
 
+    @_with_grad
     def groupnorm_bwd(self, x, dy, gamma, dx, partial, N, HW, C, groups, eps, st):
         import torch
 
@@ -1171,6 +1183,7 @@ class TrunkBwdOps:
         part[:, :C] = (g * xhat.detach()).sum(2).float()
         part[:, C:] = g.sum(2).float()
 
+    @_with_grad
     def batchnorm_bwd(self, x, dy, gamma, rmean, rvar, dx, dgamma, dbeta, rows, C, eps, training, st):
         import torch
 
@@ -1186,6 +1199,7 @@ class TrunkBwdOps:
         _tt(dgamma, (C,)).copy_((g * xhat.detach()).sum(0).float())
         _tt(dbeta, (C,)).copy_(g.sum(0).float())
 
+    @_with_grad
     def maxpool3x3s2_bwd(self, x, dy, dx, N, H, W, C, st):
         import torch.nn.functional as Fn
 
@@ -1194,6 +1208,7 @@ class TrunkBwdOps:
         Fn.max_pool2d(xi, 3, 2, 1).backward(_tt(dy, (N, P, Q, C)).permute(0, 3, 1, 2))
         _tt(dx, (N, H, W, C)).copy_(xi.grad.permute(0, 2, 3, 1))
 
+    @_with_grad
     def adaptive_avgpool_bwd(self, dout, ld, dx, N, H, W, C, O, st):
         import torch
         import torch.nn.functional as Fn

@@ -203,6 +203,18 @@ def test_device_feature_cache_equals_reference_pipeline(fp16, big):
             assert a.dtype == b.dtype and torch.equal(a.cpu(), b)
 
 
+@pytest.mark.xfail(strict=False, reason="trainable trunks (SURVEY 8f N4) run on kernels that have not seen a GPU yet; "
+                                        "launch plan verified on the host models (tests/test_trunk_backward.py)")
+@pytest.mark.parametrize("name", ["cma_train_pixels_trunks", "seq2seq_train_pixels_trunks"])
+def test_zy_trainable_trunks_match_golden_first_gpu_run(name):
+    from test_trunk_backward import check_groups, grouped_errors
+
+    got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, device=DEV, precision="fp32")
+    want = gold(name)
+    assert set(got) == {k for k in want if not k.startswith("_")}
+    check_groups(grouped_errors(got, want), name)
+
+
 # ---- keep this test LAST in the file: its kernels have never run on a GPU (written after round 1's GPU budget was
 # spent), so a device fault here must not be able to disturb any other test.  Non-strict xfail: XPASS = verified.
 @pytest.mark.xfail(strict=False, reason="trunk-backward kernels (SURVEY 8f N4): first GPU run; host model verified on CPU")

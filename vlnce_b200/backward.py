@@ -218,6 +218,20 @@ def seq2seq_backward(eng, head_linear, g: Dict[str, torch.Tensor], d_raw: Option
         pa_w = net.prev_action_embedding.weight
         C.vlnce_prev_action_embed_bwd(ptr(cx["prev"]), ptr(masks_f), off(d_xin, width - 32), width, None, 0,
                                       ptr(g["net.prev_action_embedding.weight"]), R, 32, pa_w.shape[0], st)
+    # trainable conv trunks (seq2seq_policy.py:78,92): fc input gradients -> the trunks' taped backward.  An ablated
+    # modality's slice has zero gradient after the ReLU mask above, as in the reference (``embedding * 0``).
+    pname = {id(p): k for k, p in trainable_named(net).items()}
+    if getattr(net.depth_encoder, "_taped", None) is not None:
+        P = h * w
+        d_flat = b("d_s2s_depth_flat", (R, c * P))
+        linear_dx(off(d_xin, Hs), width, ptr(net.depth_encoder.visual_fc[1].weight), ptr(d_flat), c * P, R, d_out, c * P)
+        d_tr = b("d_s2s_depth", (R, P, c))
+        C.vlnce_nchw_to_positions(ptr(d_flat), ptr(d_tr), c, R, c, P, st)
+        net.depth_encoder.backward_trunk(ptr(d_tr), c, g, pname)
+    if getattr(net.rgb_encoder, "_taped", None) is not None:
+        d_rgb = b("d_s2s_rgb", (R, 1, cr))
+        linear_dx(off(d_xin, Hs + d_out), width, ptr(net.rgb_encoder.fc[1].weight), ptr(d_rgb), cr, R, r_out, cr)
+        net.rgb_encoder.backward_trunk(ptr(d_rgb), cr, g, pname)
     br_lstm.join()
     leaves.join()
 
@@ -360,6 +374,29 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     if not cfg.get("ablate_depth", False):
         C.vlnce_spatial_embed_grad(ptr(dE["depth"]), P * eng.Cdep, eng.Cdep, c_dep, ptr(d_flat_sp), 64 * P, None, 0,
                                    ptr(g["net.depth_encoder.spatial_embeddings.weight"]), 0, R, P, 64, st)
+    # 13. trainable conv trunks (RGB_ENCODER.trainable / DEPTH_ENCODER.trainable, cma_policy.py:80,94): the trunk features
+    # feed the attention (dE) AND the rgb_linear / depth_linear inputs (steps 9), whose trunk-channel gradients were
+    # skipped above; both are gathered into a contiguous (R, P, c) buffer the trunk's taped backward starts from
+    pname = {id(p): k for k, p in trainable_named(net).items()}
+    if getattr(net.rgb_encoder, "_taped", None) is not None and not cfg.get("ablate_rgb", False):
+        d_mean = b("d_rgb_mean_tr", (R, c_rgb))
+        linear_dx(ptr(d_state_in), eng.state_in, ptr(net.rgb_linear[2].weight), ptr(d_mean), c_rgb, R, eng.rgb_out,
+                  c_rgb, ldw=eng.Crgb)
+        d_mean_p = b("d_rgb_mean_tr_p", (R, c_rgb))
+        d_mean_p.zero_()
+        C.vlnce_axpy(ptr(d_mean_p), ptr(d_mean), 1.0 / P, R * c_rgb, st)  # mean over the P positions
+        d_tr = b("d_rgb_trunk", (R, P, c_rgb))
+        C.vlnce_broadcast_rows(ptr(d_mean_p), c_rgb, ptr(d_tr), P * c_rgb, c_rgb, R, P, c_rgb, st)
+        C.vlnce_sum_positions(ptr(dE["rgb"]), eng.Crgb, eng.Crgb, ptr(d_tr), c_rgb, 1, R * P, 1, c_rgb, st)
+        net.rgb_encoder.backward_trunk(ptr(d_tr), c_rgb, g, pname)
+    if getattr(net.depth_encoder, "_taped", None) is not None and not cfg.get("ablate_depth", False):
+        d_flat = b("d_dep_flat_tr", (R, c_dep * P))  # NCHW-flat trunk channels of depth_linear's input
+        linear_dx(d_dep, eng.state_in, ptr(net.depth_linear[1].weight), ptr(d_flat), c_dep * P, R, eng.depth_out,
+                  c_dep * P, ldw=eng.Cdep * P)
+        d_tr = b("d_dep_trunk", (R, P, c_dep))
+        C.vlnce_nchw_to_positions(ptr(d_flat), ptr(d_tr), c_dep, R, c_dep, P, st)
+        C.vlnce_sum_positions(ptr(dE["depth"]), eng.Cdep, eng.Cdep, ptr(d_tr), c_dep, 1, R * P, 1, c_dep, st)
+        net.depth_encoder.backward_trunk(ptr(d_tr), c_dep, g, pname)
     br_lstm.join()
     leaves.join()
 

@@ -122,14 +122,13 @@ class VlnResnetDepthEncoder(nn.Module):
         super().__init__()
         if normalize_visual_inputs:
             raise NotImplementedError("RunningMeanAndVar input normalisation is not on the reference path")
-        if trainable:
-            raise NotImplementedError("DEPTH_ENCODER.trainable=True (trunk backward) is SURVEY 8f N4")
+        self.trainable = bool(trainable)
         shape = observation_space.spaces["depth"].shape
         depth_hw = shape[-3]
         self.visual_encoder = _DepthVisualEncoder(depth_hw, backbone, resnet_baseplanes,
                                                   resnet_baseplanes // 2)
         for p in self.visual_encoder.parameters():
-            p.requires_grad_(False)
+            p.requires_grad_(self.trainable)  # resnet_encoders.py:44-45
         if checkpoint != "NONE":  # resnet_encoders.py:48-61
             w = torch.load(checkpoint, map_location="cpu")
             sd = {}
@@ -153,11 +152,13 @@ class VlnResnetDepthEncoder(nn.Module):
     def is_blind(self):
         return False
 
-    def features_into(self, observations, out: torch.Tensor, ld: int, precision: str):
+    def features_into(self, observations, out: torch.Tensor, ld: int, precision: str, save: bool = False):
         """Writes the (R, P, C) channels-last trunk features into ``out[:, :, :C]`` (row stride
-        ``ld``), from the cached ``depth_features`` (resnet_encoders.py:92-93) or the trunk."""
+        ``ld``), from the cached ``depth_features`` (resnet_encoders.py:92-93) or the trunk.  A trainable trunk
+        (``DEPTH_ENCODER.trainable``) runs the fp32 path and, with ``save``, records the tape its backward walks."""
         c, h, w = self.visual_encoder.output_shape
         st = lib.stream()
+        self._taped = None
         if "depth_features" in observations:
             f = observations["depth_features"]
             lib.require_cuda(f, "depth_features")
@@ -167,9 +168,22 @@ class VlnResnetDepthEncoder(nn.Module):
         else:
             depth = observations["depth"]
             lib.require_cuda(depth, "depth")
-            self.visual_encoder.trunk(precision).forward(depth.contiguous().float(), out, ld, h)
+            tr = self.visual_encoder.trunk("fp32" if self.trainable else precision)
+            tr.tape = None
+            if self.trainable and save:
+                tr.begin_tape()
+                self._taped = tr
+            tr.forward(depth.contiguous().float(), out, ld, h)
             nchw = None
         _run_hooks(self.visual_encoder, observations, out, ld, c, h, w, nchw)
+
+    def backward_trunk(self, dout_ptr: int, ld: int, g, pname):
+        """Trunk parameter gradients of the last ``features_into(..., save=True)`` from the gradient w.r.t. the
+        (R, P, ld) positions it wrote (no-op when the trunk did not run: frozen, or cached features)."""
+        if getattr(self, "_taped", None) is not None:
+            self._taped.backward(dout_ptr, ld, g, pname)
+            self._taped.tape = None
+            self._taped = None
 
 
 # --------------------------------------------------------------------------------------
@@ -222,8 +236,7 @@ class TorchVisionResNet(nn.Module):
         super().__init__()
         import torchvision.models as tvm
 
-        if trainable:
-            raise NotImplementedError("RGB_ENCODER.trainable=True (trunk backward) is SURVEY 8f N4")
+        self.trainable = bool(trainable)
         self.normalize_visual_inputs = normalize_visual_inputs  # MODEL.normalize_rgb (config/default.py:216)
         self.spatial_output = spatial_output
         # reference: pretrained=True (resnet_encoders.py:136); no network here -> seeded init,
@@ -236,8 +249,8 @@ class TorchVisionResNet(nn.Module):
         self.resnet_layer_size = mods[-1].in_features
         self.cnn = _RGBSequential(*mods[:-1])
         for p in self.cnn.parameters():
-            p.requires_grad_(False)
-        self.cnn.train(False)
+            p.requires_grad_(self.trainable)  # resnet_encoders.py:141-143
+        self.cnn.train(self.trainable)
         if not spatial_output:
             self.output_shape = (output_size,)
             self.cnn.out_hw = 1
@@ -256,11 +269,13 @@ class TorchVisionResNet(nn.Module):
     def is_blind(self):
         return False
 
-    def features_into(self, observations, out: torch.Tensor, ld: int, precision: str):
-        """(R, P, 2048|512) channels-last trunk features into ``out[:, :, :C]``."""
+    def features_into(self, observations, out: torch.Tensor, ld: int, precision: str, save: bool = False):
+        """(R, P, 2048|512) channels-last trunk features into ``out[:, :, :C]``.  A trainable trunk
+        (``RGB_ENCODER.trainable``) runs the fp32 path and, with ``save``, records the tape its backward walks."""
         c = self.resnet_layer_size
         o = self.cnn.out_hw
         st = lib.stream()
+        self._taped = None
         if "rgb_features" in observations:  # resnet_encoders.py:194-195
             f = observations["rgb_features"]
             lib.require_cuda(f, "rgb_features")
@@ -272,9 +287,16 @@ class TorchVisionResNet(nn.Module):
             lib.require_cuda(rgb, "rgb")
             if rgb.dtype not in (torch.uint8, torch.float32):
                 rgb = rgb.float()
-            self.cnn.trunk(precision, self.normalize_visual_inputs).forward(rgb.contiguous(), out, ld, o)
+            tr = self.cnn.trunk("fp32" if self.trainable else precision, self.normalize_visual_inputs)
+            tr.tape = None
+            if self.trainable and save:
+                tr.begin_tape()
+                self._taped = tr
+            tr.forward(rgb.contiguous(), out, ld, o)
             nchw = None
         _run_hooks(self.cnn, observations, out, ld, c, o, o, nchw)
+
+    backward_trunk = VlnResnetDepthEncoder.backward_trunk
 
 
 class TorchVisionResNet50(TorchVisionResNet):

@@ -300,15 +300,15 @@ class CMAEngine(HeadEngine):
         """(rgb (R,16,2112), depth (R,16,192)) fp32 feature buffers of a named slot."""
         return (self.buf(f"rgb_emb_{slot}", (R, self.P, self.Crgb)), self.buf(f"depth_emb_{slot}", (R, self.P, self.Cdep)))
 
-    def encode_visual(self, observations, rgb_e, dep_e):
+    def encode_visual(self, observations, rgb_e, dep_e, save: bool = False):
         """Both frozen conv trunks (depth on a forked stream) -> channels [0, C_trunk) of the
         feature buffers.  Independent of every trainable parameter, so a training loop may run it
         for batch i+1 while the head of batch i trains (``ILTrainerStep.pipelined_step``)."""
         net = self.net
         self.ensure_pool(rgb_e.device)
         with Branch("depth") as br_depth:
-            net.depth_encoder.features_into(observations, dep_e, self.Cdep, self.precision)
-        net.rgb_encoder.features_into(observations, rgb_e, self.Crgb, self.precision)
+            net.depth_encoder.features_into(observations, dep_e, self.Cdep, self.precision, save=save)
+        net.rgb_encoder.features_into(observations, rgb_e, self.Crgb, self.precision, save=save)
         br_depth.join()
 
     def forward(self, observations, rnn_states, prev_actions, masks, save: bool, visual=None):
@@ -328,7 +328,7 @@ class CMAEngine(HeadEngine):
         if visual is None:
             rgb_e = self.buf("rgb_emb", (R, P, self.Crgb))
             dep_e = self.buf("depth_emb", (R, P, self.Cdep))
-            self.encode_visual(observations, rgb_e, dep_e)
+            self.encode_visual(observations, rgb_e, dep_e, save=save)
         else:  # trunk features were produced ahead of time (pipelined training loop)
             rgb_e, dep_e = visual
         C.vlnce_spatial_embed_fill(ptr(net.depth_encoder.spatial_embeddings.weight), ptr(dep_e),

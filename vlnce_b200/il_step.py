@@ -99,6 +99,10 @@ class ILTrainerStep:
         """Trunk features of the NEXT batch into the 'next' slot (call inside a forked stream or
         let ``pipelined_step`` do it)."""
         eng = self.policy.net.engine()
+        net = self.policy.net
+        if getattr(net.rgb_encoder, "trainable", False) or getattr(net.depth_encoder, "trainable", False):
+            raise lib.VlnceError("the pipelined loop runs the trunks ahead of the update: it needs frozen trunks "
+                                 "(RGB_ENCODER.trainable / DEPTH_ENCODER.trainable = False)")
         rgb = observations_next["rgb"] if "rgb" in observations_next else observations_next["rgb_features"]
         eng.ensure_pool(rgb.device)
         R = rgb.shape[0]

@@ -55,7 +55,7 @@ class Seq2SeqEngine(HeadEngine):
         # depth: Flatten((R,128,4,4)) -> Linear -> ReLU   (resnet_encoders.py:64-72)
         c, h, w = net.depth_encoder.visual_encoder.output_shape
         dep = self.buf("s2s_depth", (R, h * w, c))
-        net.depth_encoder.features_into(observations, dep, c, self.precision)
+        net.depth_encoder.features_into(observations, dep, c, self.precision, save=save)
         dep_flat = self.buf("s2s_depth_flat", (R, c * h * w))
         C.vlnce_positions_to_nchw(ptr(dep), h * w * c, c, ptr(dep_flat), c * h * w, R, h * w, c, st)
         fc = net.depth_encoder.visual_fc[1]
@@ -63,7 +63,7 @@ class Seq2SeqEngine(HeadEngine):
         # rgb: global-pooled (R,2048) -> Linear -> ReLU   (resnet_encoders.py:147-152)
         cr = net.rgb_encoder.resnet_layer_size
         rgb = self.buf("s2s_rgb", (R, 1, cr))
-        net.rgb_encoder.features_into(observations, rgb, cr, self.precision)
+        net.rgb_encoder.features_into(observations, rgb, cr, self.precision, save=save)
         fc = net.rgb_encoder.fc[1]
         linear(ptr(rgb), cr, ptr(fc.weight), off(xin, Hs + d_out), width, ptr(fc.bias), R, r_out, cr, act=1)
         if cfg.SEQ2SEQ.use_prev_action:  # seq2seq_policy.py:158-162

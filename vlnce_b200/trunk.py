@@ -143,6 +143,7 @@ class _Conv:
             sc = n.weight.detach().float() / torch.sqrt(n.running_var.detach().float() + n.eps)
             sh = n.bias.detach().float() - n.running_mean.detach().float() * sc
             self.scale = (sc * self.in_scale).contiguous()
+            self.bn_scale = sc.contiguous()  # without the input scaling (taped fp32 path of trainable trunks)
             self.shift = sh.contiguous()
             self.pre_scale = torch.full_like(sc, self.in_scale)
             self.pre_shift = torch.zeros_like(sc)
@@ -170,13 +171,98 @@ class ConvTrunk:
     # -------------------------------------------------------------- low-level steps
     _pfx = ""  # buffer-name prefix of the batch chunk being sequenced (chunks run concurrently: own buffers)
 
+    # ---- trainable trunks: while ``tape`` is a list the fp32 forward keeps every layer's input, raw
+    # conv output and output in its own buffer and appends one record per layer; ``backward`` walks it in reverse.
+    tape = None
+
+    def _name(self, tag: str) -> str:
+        return self._pfx + tag + (f"@{len(self.tape)}" if self.tape is not None else "")
+
     def _act(self, tag: str, shape):
-        return self.pool.get(self._pfx + tag, shape, self.adt)
+        return self.pool.get(self._name(tag), shape, self.adt)
 
     def _raw(self, tag, shape):
         """fp32 raw conv output feeding GroupNorm / train-mode BatchNorm statistics (one bf16
         rounding per layer instead of two)."""
-        return self.pool.get(self._pfx + tag, shape, torch.float32)
+        return self.pool.get(self._name(tag), shape, torch.float32)
+
+    def begin_tape(self):
+        assert self.precision == "fp32", "trainable trunks run the fp32 path"
+        self.tape = []
+
+    def backward(self, dout_ptr: int, ld: int, g: Dict[str, torch.Tensor], pname: Dict[int, str]):
+        """Backward of the last taped forward.  ``dout_ptr``: fp32 gradient w.r.t. the pooled positions
+        (N, O*O, ld) the forward wrote (channels [0, C) of each row); ``g``: parameter name -> zeroed gradient tensor;
+        ``pname``: id(parameter) -> its name in ``g``.  Layer by layer: ReLU mask -> residual branch -> norm backward on
+        the raw conv output -> wgrad (KRSC, permuted into the (K,C,R,S) parameter gradient) and dgrad."""
+        from .backward import _colsum
+
+        tape, st = self.tape, lib.stream()
+        assert tape, "backward needs a taped forward (begin_tape)"
+        f32 = torch.float32
+        grads: Dict[int, torch.Tensor] = {}
+        for i in range(len(tape) - 1, -1, -1):
+            rec = tape[i]
+            kind = rec["kind"]
+            if kind == "avgpool":
+                n, h, w, c = rec["shape_in"]
+                dx = self.pool.get(f"{self._pfx}d@{i}", rec["shape_in"], f32)
+                C.vlnce_adaptive_avgpool_bwd(dout_ptr, ld, ptr(dx), n, h, w, c, rec["O"], st)
+                grads[rec["x"].data_ptr()] = dx
+                continue
+            if kind == "maxpool":
+                n, h, w, c = rec["shape_in"]
+                dy = grads.pop(rec["y"].data_ptr())
+                dx = self.pool.get(f"{self._pfx}d@{i}", rec["shape_in"], f32)
+                C.vlnce_maxpool3x3s2_bwd(ptr(rec["x"]), ptr(dy), ptr(dx), n, h, w, c, st)
+                grads[rec["x"].data_ptr()] = dx
+                continue
+            cv, x, raw, y = rec["cv"], rec["x"], rec["raw"], rec["y"]
+            n, p, q, K = rec["shape"]
+            rows = n * p * q
+            dy = grads.pop(y.data_ptr())
+            if rec["relu"]:
+                C.vlnce_relu_bwd(ptr(dy), K, ptr(y), K, rows, K, st)
+            res = rec["residual"]
+            if res is not None:
+                k = res.data_ptr()
+                if k in grads:
+                    C.vlnce_axpy(ptr(grads[k]), ptr(dy), 1.0, dy.numel(), st)
+                else:
+                    grads[k] = dy  # dy is not written again by this layer; later consumers accumulate into it
+            d_raw = self.pool.get(f"{self._pfx}draw@{i}", rec["shape"], f32)
+            norm = cv.norm
+            if kind == "gn":
+                part = self.pool.get(self._pfx + "gn_part", (n, 2 * K), f32)
+                C.vlnce_groupnorm_bwd(ptr(raw), ptr(dy), ptr(norm.weight), ptr(d_raw), ptr(part), n, p * q, K,
+                                      norm.num_groups, float(norm.eps), st)
+                gb = self.pool.get(self._pfx + "gn_gb", (2 * K,), f32)
+                _colsum(ptr(part), 2 * K, ptr(gb), n, 2 * K)
+                g[pname[id(norm.weight)]].copy_(gb[:K])
+                g[pname[id(norm.bias)]].copy_(gb[K:])
+            else:
+                C.vlnce_batchnorm_bwd(ptr(raw), ptr(dy), ptr(norm.weight), ptr(norm.running_mean),
+                                      ptr(norm.running_var), ptr(d_raw), ptr(g[pname[id(norm.weight)]]),
+                                      ptr(g[pname[id(norm.bias)]]), rows, K, float(norm.eps), int(rec["training"]), st)
+            n, h, w, c = rec["shape_in"]
+            dw = self.pool.get(self._pfx + "dw_krsc", (K, cv.R, cv.S, c), f32)
+            C.vlnce_conv2d_ref_wgrad(ptr(x), lib.code(x), ptr(d_raw), ptr(dw), n, h, w, c, K, cv.R, cv.S, cv.stride, cv.pad,
+                                     float(cv.in_scale), 0, st)
+            gw = g[pname[id(cv.conv.weight)]]
+            gw.copy_(dw.permute(0, 3, 1, 2))
+            if cv.in_chan_scale is not None:  # normalize_rgb: the packed weights carry 1/std per input channel
+                gw.mul_(torch.tensor(cv.in_chan_scale, device=gw.device, dtype=gw.dtype).view(1, -1, 1, 1))
+            if rec.get("input"):
+                continue  # the image / depth map has no gradient
+            k = x.data_ptr()
+            if k in grads:
+                C.vlnce_conv2d_ref_dgrad(ptr(d_raw), ptr(cv.w), ptr(grads[k]), n, h, w, c, K, cv.R, cv.S, cv.stride,
+                                         cv.pad, 1, st)
+            else:
+                dx = self.pool.get(f"{self._pfx}d@{i}", rec["shape_in"], f32)
+                C.vlnce_conv2d_ref_dgrad(ptr(d_raw), ptr(cv.w), ptr(dx), n, h, w, c, K, cv.R, cv.S, cv.stride, cv.pad, 0, st)
+                grads[k] = dx
+        assert not grads, "activation gradients left unconsumed"
 
     def _conv(self, x, shape_in, cv: _Conv, y, *, scale, shift, residual=None, relu=False,
               gemm_c: Optional[int] = None, stem_rgb: bool = False, stem_s2d: bool = False):
@@ -327,6 +413,17 @@ class RGBTrunk(ConvTrunk):
         p, q = out_hw if out_hw is not None else self._out_hw(h, w, cv)
         y = self._act(tag, (n, p, q, cv.K))
         bn: nn.BatchNorm2d = cv.norm
+        if self.tape is not None and not bn.training:
+            # trainable trunk, eval-mode norms: same raw -> affine split as the train-mode path below so that the
+            # backward has the raw conv output; scale / shift are the folded running statistics
+            raw = self._raw("bn_raw", (n, p, q, cv.K))
+            pre = cv.in_scale != 1.0
+            self._conv(x, shape_in, cv, raw, scale=cv.pre_scale if pre else None, shift=cv.pre_shift if pre else None)
+            C.vlnce_affine_apply(ptr(raw), lib.code(raw), ptr(cv.bn_scale), ptr(cv.shift), 0, ptr(residual), ptr(y),
+                                 lib.code(y), n, p * q, cv.K, int(relu), lib.stream())
+            self.tape.append(dict(kind="bn", cv=cv, x=x, shape_in=tuple(shape_in), raw=raw, y=y, residual=residual,
+                                  relu=relu, shape=(n, p, q, cv.K), training=False, input=cv.stem is not None))
+            return y, (n, p, q, cv.K)
         if not bn.training:
             self._conv(x, shape_in, cv, y, scale=cv.scale, shift=cv.shift, residual=residual, relu=relu,
                        gemm_c=gemm_c, stem_rgb=stem_rgb, stem_s2d=stem_s2d)
@@ -348,6 +445,9 @@ class RGBTrunk(ConvTrunk):
         cv._ver = None  # running stats changed under the folded eval-mode scale/shift
         C.vlnce_affine_apply(ptr(raw), lib.code(raw), ptr(sc), ptr(sh), 0, ptr(residual), ptr(y), lib.code(y),
                              n, p * q, cv.K, int(relu), st)
+        if self.tape is not None:
+            self.tape.append(dict(kind="bn", cv=cv, x=x, shape_in=tuple(shape_in), raw=raw, y=y, residual=residual,
+                                  relu=relu, shape=(n, p, q, cv.K), training=True, input=cv.stem is not None))
         return y, (n, p, q, cv.K)
 
     def forward(self, rgb: torch.Tensor, out: torch.Tensor, ld_out: int, out_hw: int = 4):
@@ -391,6 +491,8 @@ class RGBTrunk(ConvTrunk):
         p, q = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
         y = self._act("pool_y", (n, p, q, c))
         C.vlnce_maxpool3x3s2(ptr(x), ptr(y), lib.code(x), n, h, w, c, st)
+        if self.tape is not None:
+            self.tape.append(dict(kind="maxpool", x=x, y=y, shape_in=(n, h, w, c)))
         x, shp = y, (n, p, q, c)
         slot = 0
         for b in self.blocks:
@@ -406,6 +508,8 @@ class RGBTrunk(ConvTrunk):
             slot ^= 1
         n, h, w, c = shp
         C.vlnce_adaptive_avgpool(ptr(x), lib.code(x), ptr(out), ld_out, n, h, w, c, out_hw, st)
+        if self.tape is not None:
+            self.tape.append(dict(kind="avgpool", x=x, shape_in=(n, h, w, c), O=out_hw))
         return shp
 
 
@@ -465,6 +569,9 @@ class DepthTrunk(ConvTrunk):
                                     ws.numel() * 4, n, p * q, cv.K, gn.num_groups, float(gn.eps), st)
             C.vlnce_affine_apply(ptr(raw), lib.code(raw), ptr(sc), ptr(sh), cv.K, ptr(residual), ptr(y),
                                  lib.code(y), n, p * q, cv.K, int(relu), st)
+        if self.tape is not None:
+            self.tape.append(dict(kind="gn", cv=cv, x=x, shape_in=tuple(shape_in), raw=raw, y=y, residual=residual,
+                                  relu=relu, shape=(n, p, q, cv.K), input=cv.stem is not None))
         return y, (n, p, q, cv.K)
 
     def forward(self, depth: torch.Tensor, out: torch.Tensor, ld_out: int, out_hw: int = 4):
@@ -513,6 +620,8 @@ class DepthTrunk(ConvTrunk):
         p, q = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
         y = self._act("pool_y", (n, p, q, c))
         C.vlnce_maxpool3x3s2(ptr(x), ptr(y), lib.code(x), n, h, w, c, st)
+        if self.tape is not None:
+            self.tape.append(dict(kind="maxpool", x=x, y=y, shape_in=(n, h, w, c)))
         x, shp = y, (n, p, q, c)
         slot = 0
         for b in self.blocks:
@@ -529,4 +638,6 @@ class DepthTrunk(ConvTrunk):
         x, shp = self._gn_conv(x, shp, self.compress, "cmp", relu=True)
         n, h, w, c = shp
         C.vlnce_adaptive_avgpool(ptr(x), lib.code(x), ptr(out), ld_out, n, h, w, c, out_hw, st)
+        if self.tape is not None:
+            self.tape.append(dict(kind="avgpool", x=x, shape_in=(n, h, w, c), O=out_hw))
         return shp
