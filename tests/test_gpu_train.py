@@ -85,7 +85,6 @@ def test_fused_step_matches_reference(name):
     assert abs(loss - want["loss"].item()) < 1e-4 * max(1, abs(want["loss"].item()))
     assert abs(action_loss - want["action_loss"].item()) < 1e-4
     assert abs(aux_loss - want["aux_loss"].item()) < 1e-4
-    got = {"grad/" + k[len("net."):] if False else "grad/" + k: None for k in ()}
     got = {}
     for k, gview in step.fp.grad_views.items():
         g = gview.detach().cpu()
