@@ -1,0 +1,15 @@
+#!/bin/bash
+# First GPU visit of round 2: everything written after round 1's GPU budget ran out.
+#   1. the late-collected variant tests with the non-strict xfails forced to run as normal tests (--runxfail):
+#      trunk-backward kernels + trainable-trunk goldens (N4), LSTM / GRU / normalize_rgb end-to-end goldens;
+#   2. the default bench line — its `roofline` object now comes from the per-launch model (bound "hbm");
+#   3. the usual suite.
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_zz_gpu_variants.py -m gpu -q -rA --runxfail --timeout 300 -p no:cacheprovider \
+  > gpurun_out/test_zz_gpu_variants.log 2>&1
+echo "variants exit $?"
+grep -E "^(PASSED|FAILED|ERROR)|passed|failed|trunk:|worst" gpurun_out/test_zz_gpu_variants.log | tail -40
+( time timeout 420 python bench.py ) > gpurun_out/bench.log 2> gpurun_out/bench.err
+echo "bench exit $?"; tail -1 gpurun_out/bench.log | python -c "import sys, json; d = json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], json.dumps(d['roofline'])[:900])"
+tools/gpu_checks.sh 2>&1 | grep -v "^PASSED"
