@@ -445,3 +445,53 @@ def test_pixel_paths_16bit_packing_matches_golden(name, tol):
     e_h = float((got["rnn_states_out"] - want["rnn_states_out"]).norm() / want["rnn_states_out"].norm())
     print(f"{name}[16-bit, host model] rel err probs {e_p:.3e} hidden {e_h:.3e}")
     assert e_p < tol and e_h < tol
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties of the path (run at BASELINE's full size on the GPU, tests/test_zz_gpu_variants.py)
+# ---------------------------------------------------------------------------------------------
+def path_properties(pol, n, hw, length, device, tol):
+    """Properties the reference's arithmetic guarantees for ``act`` in eval mode, checked on ``pol``:
+    rows are independent (a batch equals its halves), repeated calls agree, zero-padding the instruction further does
+    not change anything (packed LSTM + masked attention), and ``masks == 0`` rows ignore the carried hidden state and
+    the previous action (``rnn_state_encoder`` reset, ``((a + 1) * mask)`` index).  Returns the worst deviation."""
+    from vlnce_b200 import synth
+
+    obs, h, prev, masks = synth.make_act_batch(77, n, hw=hw, length=length)
+    masks[: n // 4] = 0
+    to = lambda t: t.to(device)  # noqa: E731
+    obs, h, prev, masks = {k: to(v) for k, v in obs.items()}, to(h), to(prev), to(masks)
+
+    def run(o, hh, pp, mm):
+        with torch.no_grad():
+            d = pol.build_distribution(o, hh, pp, mm)
+            _, h_out = pol.act(o, hh, pp, mm, deterministic=True)
+        return d.logits.exp().float().cpu(), h_out.float().cpu()
+
+    def dev(a, b):
+        return max(float((a[0] - b[0]).abs().max()), float((a[1] - b[1]).norm() / b[1].norm()))
+
+    full = run(obs, h, prev, masks)
+    worst = {"repeat": dev(run(obs, h, prev, masks), full)}
+    half = n // 2
+    parts = [run({k: v[s] for k, v in obs.items()}, h[s], prev[s], masks[s]) for s in (slice(0, half), slice(half, n))]
+    worst["halves"] = dev((torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])), full)
+    longer = dict(obs, instruction=torch.cat([obs["instruction"], torch.zeros_like(obs["instruction"][:, :9])], 1))
+    worst["padding"] = dev(run(longer, h, prev, masks), full)
+    h2, prev2 = h.clone(), prev.clone()
+    h2[: n // 4] = 3.0
+    prev2[: n // 4] = (prev2[: n // 4] + 1) % 4
+    worst["mask reset"] = dev(run(obs, h2, prev2, masks), full)
+    assert torch.isfinite(full[0]).all() and abs(float(full[0].sum(1).mean()) - 1.0) < 1e-3
+    for k, v in worst.items():
+        assert v <= tol, (k, v, worst)
+    return worst
+
+
+def test_path_properties_small():
+    case = dict(cases.CASES["cma_act"], n=4)
+    with lib.dry_run(executor=Emulator()):
+        pol = cases.build_policy(vlnce_b200, case)
+        pol.net.precision = "fp32"
+        pol.eval()
+        print("properties (host model, 4 rows):", path_properties(pol, 4, 256, 24, "cpu", 1e-5))

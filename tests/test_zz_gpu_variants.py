@@ -203,6 +203,20 @@ def test_device_feature_cache_equals_reference_pipeline(fp16, big):
             assert a.dtype == b.dtype and torch.equal(a.cpu(), b)
 
 
+@pytest.mark.parametrize("precision,tol", [("bf16", 1e-2), ("fp32", 1e-4)])
+def test_full_size_path_properties(precision, tol):
+    """BASELINE config C2's full size (64 rows, 256x256 RGB-D, 80 tokens): the size-independent properties of the path
+    — a batch equals its halves, repeated calls agree, extra zero padding of the instruction is invisible, masks == 0
+    rows ignore the carried state and previous action (tests/test_host_emulated.py::path_properties)."""
+    from test_host_emulated import path_properties
+
+    case = dict(cases.CASES["cma_act"], n=64)
+    pol = cases.build_policy(vlnce_b200, case).to(DEV)
+    pol.net.precision = precision
+    pol.eval()
+    print(f"properties at full size [{precision}]:", path_properties(pol, 64, 256, 80, DEV, tol))
+
+
 @pytest.mark.xfail(strict=False, reason="trainable trunks (SURVEY 8f N4) run on kernels that have not seen a GPU yet; "
                                         "launch plan verified on the host models (tests/test_trunk_backward.py)")
 @pytest.mark.parametrize("name", ["cma_train_pixels_trunks", "seq2seq_train_pixels_trunks"])
