@@ -165,3 +165,19 @@ def test_fused_il_step_trains_the_trunks():
     after = dict(pol.named_parameters())
     k = "net.rgb_encoder.cnn.0.weight"
     assert float((after[k].detach() - before[k]).abs().max()) > 1e-4   # ~lr per element on the first Adam step
+
+
+def test_trainable_trunk_repacks_weights_after_in_place_update():
+    """The fused Adam kernel writes the flat parameter buffer behind torch's version counters; a trainable trunk must
+    not keep serving the weights it packed before the update."""
+    case = cases.CASES["seq2seq_train_pixels_trunks"]
+    g0 = torch.Generator().manual_seed(8)
+    depth = torch.rand(2, 256, 256, 1, generator=g0)
+    denc = cases.build_policy(vlnce_b200, case).net.depth_encoder
+    with lib.dry_run(executor=Emulator()):
+        a, b = torch.zeros(2, 16, 128), torch.zeros(2, 16, 128)
+        denc.features_into({"depth": depth}, a, 128, "fp32")
+        w = denc.visual_encoder.compression[0].weight
+        w.data.view(-1).numpy()[::2] *= -1.0        # in place, no version bump (what a device kernel does)
+        denc.features_into({"depth": depth}, b, 128, "fp32")
+    assert rel(a, b) > 1e-2

@@ -170,6 +170,9 @@ class VlnResnetDepthEncoder(nn.Module):
             lib.require_cuda(depth, "depth")
             tr = self.visual_encoder.trunk("fp32" if self.trainable else precision)
             tr.tape = None
+            if self.trainable:  # the fused optimiser updates the flat parameter buffer in place, behind torch's version
+                for cv in tr._all():  # counters: repack the weights on every call
+                    cv._ver = None
             if self.trainable and save:
                 tr.begin_tape()
                 self._taped = tr
@@ -289,6 +292,9 @@ class TorchVisionResNet(nn.Module):
                 rgb = rgb.float()
             tr = self.cnn.trunk("fp32" if self.trainable else precision, self.normalize_visual_inputs)
             tr.tape = None
+            if self.trainable:  # see VlnResnetDepthEncoder.features_into
+                for cv in tr._all():
+                    cv._ver = None
             if self.trainable and save:
                 tr.begin_tape()
                 self._taped = tr
