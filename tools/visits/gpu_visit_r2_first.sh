@@ -3,7 +3,8 @@
 #   1. the late-collected variant tests with the non-strict xfails forced to run as normal tests (--runxfail):
 #      trunk-backward kernels + trainable-trunk goldens (N4), LSTM / GRU / normalize_rgb end-to-end goldens;
 #   2. the default bench line — its `roofline` object now comes from the per-launch model (bound "hbm");
-#   3. the usual suite.
+#   3. the library baseline (oracle torch modules = cuDNN / cuBLAS in CUDA eager mode: fp32 / tf32 / bf16 autocast);
+#   4. the usual suite.
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_zz_gpu_variants.py -m gpu -q -rA --runxfail --timeout 300 -p no:cacheprovider \
@@ -12,4 +13,5 @@ echo "variants exit $?"
 grep -E "^(PASSED|FAILED|ERROR)|passed|failed|trunk:|worst" gpurun_out/test_zz_gpu_variants.log | tail -40
 ( time timeout 420 python bench.py ) > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench exit $?"; tail -1 gpurun_out/bench.log | python -c "import sys, json; d = json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], json.dumps(d['roofline'])[:900])"
+( time timeout 600 python tests/library_baseline.py ) > gpurun_out/library_baseline.log 2>&1; echo "library baseline exit $?"; tail -2 gpurun_out/library_baseline.log
 tools/gpu_checks.sh 2>&1 | grep -v "^PASSED"
