@@ -13,5 +13,6 @@ echo "variants exit $?"
 grep -E "^(PASSED|FAILED|ERROR)|passed|failed|trunk:|worst" gpurun_out/test_zz_gpu_variants.log | tail -40
 ( time timeout 420 python bench.py ) > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench exit $?"; tail -1 gpurun_out/bench.log | python -c "import sys, json; d = json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], json.dumps(d['roofline'])[:900])"
+( time timeout 300 python tools/bench_act.py ) > gpurun_out/bench_act.log 2>&1; echo "bench_act exit $?"; tail -1 gpurun_out/bench_act.log
 ( time timeout 600 python tests/library_baseline.py ) > gpurun_out/library_baseline.log 2>&1; echo "library baseline exit $?"; tail -2 gpurun_out/library_baseline.log
 tools/gpu_checks.sh 2>&1 | grep -v "^PASSED"
