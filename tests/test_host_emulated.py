@@ -450,14 +450,14 @@ def test_pixel_paths_16bit_packing_matches_golden(name, tol):
 # ---------------------------------------------------------------------------------------------
 # size-independent properties of the path (run at BASELINE's full size on the GPU, tests/test_zz_gpu_variants.py)
 # ---------------------------------------------------------------------------------------------
-def path_properties(pol, n, hw, length, device, tol):
+def path_properties(pol, n, hw, length, device, tol, rgb_hw=None):
     """Properties the reference's arithmetic guarantees for ``act`` in eval mode, checked on ``pol``:
     rows are independent (a batch equals its halves), repeated calls agree, zero-padding the instruction further does
     not change anything (packed LSTM + masked attention), and ``masks == 0`` rows ignore the carried hidden state and
     the previous action (``rnn_state_encoder`` reset, ``((a + 1) * mask)`` index).  Returns the worst deviation."""
     from vlnce_b200 import synth
 
-    obs, h, prev, masks = synth.make_act_batch(77, n, hw=hw, length=length)
+    obs, h, prev, masks = synth.make_act_batch(77, n, hw=hw, rgb_hw=rgb_hw, length=length)
     masks[: n // 4] = 0
     to = lambda t: t.to(device)  # noqa: E731
     obs, h, prev, masks = {k: to(v) for k, v in obs.items()}, to(h), to(prev), to(masks)
@@ -494,4 +494,4 @@ def test_path_properties_small():
         pol = cases.build_policy(vlnce_b200, case)
         pol.net.precision = "fp32"
         pol.eval()
-        print("properties (host model, 4 rows):", path_properties(pol, 4, 256, 24, "cpu", 1e-5))
+        print("properties (host model, 4 rows):", path_properties(pol, 4, 256, 24, "cpu", 1e-5, rgb_hw=96))
