@@ -495,3 +495,19 @@ def test_path_properties_small():
         pol.net.precision = "fp32"
         pol.eval()
         print("properties (host model, 4 rows):", path_properties(pol, 4, 256, 24, "cpu", 1e-5, rgb_hw=96))
+
+
+@pytest.mark.parametrize("name", ["cma_train_pixels", "seq2seq_train_pixels"])
+def test_pixel_training_16bit_packing_matches_golden(name):
+    """The training step from raw pixels on the 16-bit trunk models: outputs / losses at the path's 16-bit tolerance,
+    head gradients by relative L2 (same yardstick as tests/test_gpu_train.py's bf16 cases)."""
+    from test_trunk_backward import grouped_errors
+
+    with lib.dry_run(executor=Emulator()):
+        got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, precision="bf16")
+    g = grouped_errors(got, gold(name))
+    assert g["outputs"][-1][0] < 1e-2
+    head = g["head"]
+    print(name, "[16-bit, host model] outputs %.2e, head gradients median %.2e worst %.2e (%s)"
+          % (g["outputs"][-1][0], head[len(head) // 2][0], head[-1][0], head[-1][1]))
+    assert head[len(head) // 2][0] < 5e-3 and head[-1][0] < 0.1
