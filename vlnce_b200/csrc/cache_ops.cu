@@ -37,6 +37,15 @@ __global__ void collate_rows_kernel(const TS* __restrict__ arena, const long lon
   const bool live = t < lengths[n];
   const TS* src = arena + offsets[n] + (long long)t * D;
   float* dst = out + row * D;
+  if constexpr (VEC == 4) {
+    // a trajectory that does not start on a 4-element boundary (never produced by TrajectoryCache: D % 4 == 0 there)
+    // takes the scalar route for its rows
+    if (live && (reinterpret_cast<uintptr_t>(src) % (4 * sizeof(TS))) != 0) {
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < D; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = to_f32(src[i]);
+      continue;
+    }
+  }
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < D;
        i += (long long)gridDim.x * blockDim.x * VEC) {
     if constexpr (VEC == 4) {
@@ -93,8 +102,8 @@ using namespace vlnce;
 extern "C" int vlnce_collate_rows(const void* arena, int dtype, const long long* offsets, const int* lengths, float* out,
                                   int T, int N, long long D, float pad, cudaStream_t stream) {
   VLNCE_CHECK_ARG(arena && offsets && lengths && out && T > 0 && N > 0 && D > 0, "collate_rows: bad arguments");
-  // vector path: row size a multiple of 4 elements and 16-byte aligned bases (trajectory offsets are then checked by
-  // the caller to be multiples of 4 elements)
+  // vector path: row size a multiple of 4 elements and 16-byte aligned bases; rows of a trajectory whose offset is not a
+  // multiple of 4 elements fall back to scalar accesses inside the kernel
   const bool vec = D % 4 == 0 && (reinterpret_cast<uintptr_t>(arena) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(out) % 16 == 0) && dtype != VLNCE_I64 && dtype != VLNCE_U8;
   const long long per_thread = vec ? 4 : 1;
