@@ -58,6 +58,10 @@ def main():
     ap.add_argument("--measured-conv-ms", type=float, default=None,
                     help="bench.py roofline.conv_ms_per_step of the same config (serial, CUDA-event timed)")
     ap.add_argument("--md", default=None)
+    ap.add_argument("--launch-csv", default=None,
+                    help="ncu launch list of one serial step (gpu__time_duration.sum); its conv launches are matched to "
+                         "the plan in order and a per-layer measured-vs-roofline table is appended (--gap-md)")
+    ap.add_argument("--gap-md", default=None)
     args = ap.parse_args()
     from vlnce_b200 import roofline
 
@@ -111,6 +115,60 @@ def main():
     if args.md:
         open(os.path.join(ROOT, args.md), "w").write(text)
     print(json.dumps(summ))
+    if args.launch_csv:
+        gap = gap_table(work, args.launch_csv, pt, ph)
+        print(gap)
+        if args.gap_md:
+            open(os.path.join(ROOT, args.gap_md), "w").write(gap)
+
+
+def gap_table(work, csv_path, pt, ph):
+    """Measured (ncu, cold-cache, serialised) duration of every conv launch against its roofline bound, grouped by
+    layer shape and ranked by the time lost."""
+    import csv
+    import io
+    import re
+
+    rows = list(csv.DictReader(io.StringIO("".join(l for l in open(csv_path) if l.startswith('"')))))
+    conv = [r for r in rows if any(k in r["Kernel Name"] for k in ("conv_umma_kernel", "conv_tma_kernel", "conv3x3_halo_kernel"))]
+    assert len(conv) == len(work), (len(conv), len(work))
+    groups, order = {}, []
+    for w, r in zip(work, conv):
+        m = re.search(r"(conv\w*_kernel<[^>]*>)", r["Kernel Name"])
+        kern = m.group(1).replace("_kernel", "") if m else r["Kernel Name"][:40]
+        key = (w["trunk"], w["name"], w["pixels"])
+        if key not in groups:
+            groups[key] = dict(w, count=0, us=0.0, kernels=set())
+            order.append(key)
+        g = groups[key]
+        g["count"] += 1
+        g["us"] += float(r["Metric Value"]) / 1e3
+        g["kernels"].add(kern)
+    out = ["# measured conv launches vs their roofline bound (round-1 launch list, one serial eager step under ncu)", "",
+           "Durations are ncu `gpu__time_duration.sum` of `profiles/r01d_launches_step.md`'s capture (cold caches, serialised "
+           "launches: read them as shares); `t_min` as in `r01e_layer_roofline.md`.  Sorted by the time lost per step.", "",
+           "| trunk | layer | launches | kernel picked | measured us (sum) | t_min us (sum) | % of roofline | lost us |",
+           "|---|---|---:|---|---:|---:|---:|---:|"]
+    tab = []
+    for key in order:
+        g = groups[key]
+        tmin = max(g["flops"] / (pt * 1e12), g["bytes"] / (ph * 1e9)) * 1e6 * g["count"]
+        tab.append((g["us"] - tmin, g, tmin))
+    tab.sort(key=lambda t: -t[0])
+    tot_m = tot_i = 0.0
+    for lost, g, tmin in tab:
+        tot_m += g["us"]
+        tot_i += tmin
+        out.append(f"| {g['trunk'][:-5]} | {g['name']} | {g['count']} | {', '.join(sorted(g['kernels']))} | {g['us']:.1f} | "
+                   f"{tmin:.1f} | {100 * tmin / g['us']:.0f} | {lost:.1f} |")
+    for tr in ("RGBTrunk", "DepthTrunk"):
+        m = sum(g["us"] for _, g, _ in tab if g["trunk"] == tr)
+        i = sum(t for _, g, t in tab if g["trunk"] == tr)
+        out.append("")
+        out.append(f"**{tr}** conv launches: measured {m:.0f} us, roofline {i:.0f} us ({100 * i / m:.0f} %).")
+    out.append("")
+    out.append(f"**All conv launches**: measured {tot_m:.0f} us, roofline {tot_i:.0f} us ({100 * tot_i / tot_m:.0f} %).")
+    return "\n".join(out) + "\n"
 
 
 if __name__ == "__main__":
