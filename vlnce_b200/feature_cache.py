@@ -143,6 +143,7 @@ class TrajectoryCache:
     def batch(self, indices: Sequence[int], inflection_weight_coef: float = 1.0, use_iw: bool = True):
         """-> (observations {k: (T*N, ...) f32}, prev_actions (T*N,1) i64, not_done_masks (T*N,1) u8,
         corrected_actions (T,N) i64, weights (T,N) f32), T = the longest selected trajectory."""
+        lib.require_cuda(self.prev.data, "TrajectoryCache storage")  # no CPU path: the batch is assembled by kernels
         N = len(indices)
         lens = [self.lengths[i] for i in indices]
         T = max(lens)
