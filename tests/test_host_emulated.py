@@ -494,7 +494,7 @@ def test_path_properties_small():
         pol = cases.build_policy(vlnce_b200, case)
         pol.net.precision = "fp32"
         pol.eval()
-        print("properties (host model, 4 rows):", path_properties(pol, 4, 256, 24, "cpu", 1e-5, rgb_hw=96))
+        print("properties (host model, 4 rows):", path_properties(pol, 4, 256, 24, "cpu", 1e-5, rgb_hw=64))
 
 
 @pytest.mark.parametrize("name", ["cma_train_pixels", "seq2seq_train_pixels"])
