@@ -16,3 +16,9 @@ echo "bench exit $?"; tail -1 gpurun_out/bench.log | python -c "import sys, json
 ( time timeout 300 python tools/bench_act.py ) > gpurun_out/bench_act.log 2>&1; echo "bench_act exit $?"; tail -1 gpurun_out/bench_act.log
 ( time timeout 600 python tests/library_baseline.py ) > gpurun_out/library_baseline.log 2>&1; echo "library baseline exit $?"; tail -2 gpurun_out/library_baseline.log
 tools/gpu_checks.sh 2>&1 | grep -v "^PASSED"
+# refresh the launch list of one serial step and the per-layer gap table derived from it
+timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+  --log-file gpurun_out/launches_step.csv python bench.py --ncu-step --no-cpu-baseline > gpurun_out/ncu_step.log 2>&1
+echo "ncu exit $?"
+python tools/roofline_model.py --launch-csv gpurun_out/launches_step.csv --gap-md gpurun_out/layer_gap.md > gpurun_out/roofline_model.log 2>&1
+tail -6 gpurun_out/layer_gap.md
