@@ -220,7 +220,8 @@ def seq2seq_backward(eng, head_linear, g: Dict[str, torch.Tensor], d_raw: Option
                                       ptr(g["net.prev_action_embedding.weight"]), R, 32, pa_w.shape[0], st)
     # trainable conv trunks (seq2seq_policy.py:78,92): fc input gradients -> the trunks' taped backward.  An ablated
     # modality's slice has zero gradient after the ReLU mask above, as in the reference (``embedding * 0``).
-    pname = {id(p): k for k, p in trainable_named(net).items()}
+    taped = [e for e in (net.rgb_encoder, net.depth_encoder) if getattr(e, "_taped", None) is not None]
+    pname = {id(p): k for k, p in trainable_named(net).items()} if taped else {}
     if getattr(net.depth_encoder, "_taped", None) is not None:
         P = h * w
         d_flat = b("d_s2s_depth_flat", (R, c * P))
@@ -377,7 +378,8 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     # 13. trainable conv trunks (RGB_ENCODER.trainable / DEPTH_ENCODER.trainable, cma_policy.py:80,94): the trunk features
     # feed the attention (dE) AND the rgb_linear / depth_linear inputs (steps 9), whose trunk-channel gradients were
     # skipped above; both are gathered into a contiguous (R, P, c) buffer the trunk's taped backward starts from
-    pname = {id(p): k for k, p in trainable_named(net).items()}
+    taped = [e for e in (net.rgb_encoder, net.depth_encoder) if getattr(e, "_taped", None) is not None]
+    pname = {id(p): k for k, p in trainable_named(net).items()} if taped else {}  # (walks the module tree: only when needed)
     if getattr(net.rgb_encoder, "_taped", None) is not None and not cfg.get("ablate_rgb", False):
         d_mean = b("d_rgb_mean_tr", (R, c_rgb))
         linear_dx(ptr(d_state_in), eng.state_in, ptr(net.rgb_linear[2].weight), ptr(d_mean), c_rgb, R, eng.rgb_out,
