@@ -109,7 +109,7 @@ def test_waypoint_plan_matches_golden(name):
     print(name, "worst", worst)
 
 
-def _fill_rollouts(st, T, N, length=12, classes=None):
+def _fill_rollouts(st, T, N, length=12, classes=None, layers=2):
     from vlnce_b200 import synth
 
     g = torch.Generator().manual_seed(9)
@@ -118,13 +118,13 @@ def _fill_rollouts(st, T, N, length=12, classes=None):
         st.observations[k][0].copy_(first[k])
     for t in range(T):
         a = synth.make_waypoint_actions(g, N, classes=classes)
-        st.insert(synth.make_waypoint_rows(g, N, length=length), torch.randn(N, 2, 256, generator=g) * 0.3, a,
+        st.insert(synth.make_waypoint_rows(g, N, length=length), torch.randn(N, layers, 256, generator=g) * 0.3, a,
                   -2 + 0.2 * torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g) * 0.3,
                   torch.randn(N, 1, generator=g), torch.ones(N, 1, dtype=torch.uint8))
     return torch.randn(N, 1, generator=g) * 0.3
 
 
-@pytest.mark.parametrize("name", ["wp_eval", "wp_eval_dd"])
+@pytest.mark.parametrize("name", ["wp_eval", "wp_eval_dd", "wp_eval_igru"])
 def test_fused_wddppo_update_matches_oracle_loop(name):
     """``WDDPPOStep.update`` (fused loss+gradient kernel, hand-written backward, clip, Adam; device-style rollout
     storage with the GAE kernel) against the restated ``WDDPPO.update`` loop (itself pinned to the reference's
@@ -134,6 +134,7 @@ def test_fused_wddppo_update_matches_oracle_loop(name):
 
     case = cases.CASES[name]
     T, N = 2, 2
+    Lr = cases.layers_of(case)  # 2 GRU slots, or 4 with LSTM state encoders (wp_eval_igru: GRU instruction encoder too)
     kw = dict(clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, offset_regularize_coef=0.1146,
               pano_entropy_coef=1.0, offset_entropy_coef=1.0, distance_entropy_coef=1.0)
     space = oracle_wp.storage_obs_space(length=12)
@@ -143,8 +144,8 @@ def test_fused_wddppo_update_matches_oracle_loop(name):
     # oracle
     opol = cases.build_policy(oracle_wp, case)
     cases.set_mode(opol, case)
-    ost = oracle_wp.ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2, **cont)
-    nv = _fill_rollouts(ost, T, N, classes=classes)
+    ost = oracle_wp.ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=Lr, **cont)
+    nv = _fill_rollouts(ost, T, N, classes=classes, layers=Lr)
     ost.compute_returns(nv, True, 0.99, 0.95)
     opt = torch.optim.Adam([p for p in opol.parameters() if p.requires_grad], lr=2e-4, eps=1e-5)
     torch.manual_seed(21)
@@ -154,8 +155,8 @@ def test_fused_wddppo_update_matches_oracle_loop(name):
     pol = cases.build_policy(vlnce_b200, case)
     cases.set_mode(pol, case)
     substitute_trunks(pol, case)
-    st = ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2, **cont)
-    nv2 = _fill_rollouts(st, T, N, classes=classes)
+    st = ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=Lr, **cont)
+    nv2 = _fill_rollouts(st, T, N, classes=classes, layers=Lr)
     with lib.dry_run(executor=Emulator()):
         st.compute_returns(nv2, True, 0.99, 0.95)
         torch.testing.assert_close(st.returns, ost.returns, rtol=1e-6, atol=1e-6)
