@@ -177,7 +177,8 @@ def test_fused_wddppo_update_matches_oracle_loop(name):
 # restated ``_update_agent`` + torch Adam (common/base_il_trainer.py:134-180)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,accum", [("cma_train_features", 1), ("cma_rxr_train_features", 1),
-                                        ("seq2seq_train_features", 1), ("cma_train_features_nopm", 2)])
+                                        ("seq2seq_train_features", 1), ("cma_train_features_nopm", 2),
+                                        ("cma_train_features_lstm", 1), ("seq2seq_train_features_igru", 1)])
 def test_fused_il_step_matches_oracle_update(name, accum):
     from oracle import vlnce as oracle_vlnce
     from vlnce_b200.il_step import ILTrainerStep
