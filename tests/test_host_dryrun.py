@@ -128,7 +128,8 @@ def test_waypoint_launch_sequence(name):
         assert rec.calls.count("vlnce_wp_act") == 1
 
 
-@pytest.mark.parametrize("name", ["cma_act", "cma_rxr_act", "seq2seq_train_features", "wp_act", "wp_act_dc", "wp_act_dd"])
+@pytest.mark.parametrize("name", ["cma_act", "cma_rxr_act", "seq2seq_train_features", "wp_act", "wp_act_dc", "wp_act_dd",
+                                  "cma_act_lstm", "wp_eval_igru", "cma_train_pixels_trunks"])
 def test_checkpoint_surface_matches_oracle(name):
     """Checkpoint compatibility: the CUDA policy exposes exactly the reference's ``state_dict`` keys,
     shapes and ``requires_grad`` flags (the oracle is pinned to the reference's key list in
