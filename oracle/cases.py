@@ -153,6 +153,25 @@ def obs_space(case):
                        "depth": hb017.Box(0.0, 1.0, (case["hw"], case["hw"], 1), "float32")})
 
 
+class _skip_random_init:
+    """Every parameter and buffer is overwritten by the seeded ``state_dict`` right after construction (strict load),
+    so the constructors' random initialisers (kaiming / orthogonal QR over ~30 M weights, about half of the build time
+    of the ~350 policies the test-suite constructs) are turned into no-ops while the policy is being built."""
+
+    NAMES = ("kaiming_normal_", "kaiming_uniform_", "orthogonal_", "normal_", "uniform_", "xavier_uniform_",
+             "xavier_normal_", "trunc_normal_")
+
+    def __enter__(self):
+        init = torch.nn.init
+        self.saved = {n: getattr(init, n) for n in self.NAMES}
+        for n in self.NAMES:
+            setattr(init, n, lambda tensor, *a, **k: tensor)
+
+    def __exit__(self, *exc):
+        for n, f in self.saved.items():
+            setattr(torch.nn.init, n, f)
+
+
 def build_policy(impl, case, num_actions=None):
     """impl: namespace with CMAPolicy / Seq2SeqPolicy (reference import, oracle.vlnce
     or the CUDA package)."""
@@ -160,8 +179,9 @@ def build_policy(impl, case, num_actions=None):
                        TASK_CONFIG=dict(TASK=dict(PANO_ROTATIONS=12)))
     cls = getattr(impl, case["policy"])
     num_actions = num_actions or case.get("actions", 4)
-    pol = cls.from_config(cfg, obs_space(case), hb017.Discrete(num_actions))
-    pol.load_state_dict(synth.seeded_state_dict(pol, case["wseed"]))
+    with _skip_random_init():
+        pol = cls.from_config(cfg, obs_space(case), hb017.Discrete(num_actions))
+    pol.load_state_dict(synth.seeded_state_dict(pol, case["wseed"]), strict=True)
     return pol
 
 
