@@ -83,6 +83,24 @@ def main():
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / args.steps
             out["modes"][mode] = {"ms_per_step": ms, "policy_steps_per_s": args.rows / (ms * 1e-3), "loss": float(loss)}
+            # act-only (no_grad), the same shapes: compare with tools/bench_act.py
+            h0 = torch.zeros(args.rows, pol.net.num_recurrent_layers, 512, device=dev)
+
+            def act(i):
+                obs, prev, masks = sets[i % 6][0], sets[i % 6][1], sets[i % 6][2]
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+                    return pol.act(obs, h0, prev, masks, deterministic=True)
+
+            for i in range(3):
+                act(i)
+            torch.cuda.synchronize()
+            a.record()
+            for i in range(args.steps):
+                act(i)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / args.steps
+            out["modes"][mode].update(act_ms_per_call=ms, act_policy_steps_per_s=args.rows / (ms * 1e-3))
         except Exception as e:  # keep the other modes
             out["modes"][mode] = {"error": f"{type(e).__name__}: {e}"[:300]}
         finally:
