@@ -83,6 +83,12 @@ def main():
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / args.steps
             out["modes"][mode] = {"ms_per_step": ms, "policy_steps_per_s": args.rows / (ms * 1e-3), "loss": float(loss)}
+        except Exception as e:  # keep the other modes
+            out["modes"][mode] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            continue
+        finally:
+            aux.deactivate()  # evaluation runs without the auxiliary-loss registry (base_il_trainer.py:278-280)
+        try:
             # act-only (no_grad), the same shapes: compare with tools/bench_act.py
             h0 = torch.zeros(args.rows, pol.net.num_recurrent_layers, 512, device=dev)
 
@@ -101,10 +107,8 @@ def main():
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / args.steps
             out["modes"][mode].update(act_ms_per_call=ms, act_policy_steps_per_s=args.rows / (ms * 1e-3))
-        except Exception as e:  # keep the other modes
-            out["modes"][mode] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        finally:
-            aux.deactivate()
+        except Exception as e:
+            out["modes"][mode]["act_error"] = f"{type(e).__name__}: {e}"[:300]
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "library_baseline.json"), "w"), indent=1)
