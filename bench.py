@@ -40,10 +40,16 @@ WORKLOAD = ("C2: CMAPolicy fwd+DAgger loss+bwd+Adam, T=1 N=64/GPU, rgb u8 256x25
             "L=80, progress monitor on, conv trunks frozen/eval-mode norms")
 
 
-def model_case():
-    from oracle import cases  # case table + seeded-weight builder only (no oracle compute here)
+WSEED = 13  # seeded "trained-like" weights (vlnce_b200.synth.seeded_state_dict); the parity case cma_train_pixels uses the same
 
-    return dict(cases.CASES["cma_train_pixels"], t=1, n=ROWS_PER_GPU)
+
+def oracle_case(rows=ROWS_PER_GPU):
+    """CHECKER side only (reference arm, cpu_baseline leg, parity block): the oracle's description of the same policy."""
+    from oracle import cases
+
+    case = dict(cases.CASES["cma_train_pixels"], t=1, n=rows)
+    assert case["wseed"] == WSEED
+    return case
 
 
 # ----------------------------------------------------------------------------------------
@@ -104,12 +110,14 @@ def run_reference(args, rank, world):
         return
     from oracle import cases, vlnce as oracle_vlnce
 
-    rows = 16  # bounded sample of the 64-row step
+    from vlnce_b200 import synth
+
+    rows = ROWS_PER_GPU  # the full 64-row step: same config as the GPU arm
     torch.set_num_threads(host_cores())
-    case = dict(model_case(), n=rows)
+    case = oracle_case(rows)
     pol = cases.build_policy(oracle_vlnce, case).eval()
     opt = torch.optim.Adam(pol.parameters(), lr=2.5e-4)
-    obs, prev, masks, actions, weights = cases.inputs(case)
+    obs, prev, masks, actions, weights = synth.make_train_batch(1000, 1, rows, hw=HW, length=LENGTH)
     oracle_vlnce.AuxLosses.activate()
 
     def step():
@@ -128,7 +136,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows_per_step": rows},
         "cpu_baseline": {"value": val, "unit": "policy steps/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{rows} of {ROWS_PER_GPU} rows per step, {args.steps} steps, torch {torch.__version__} CPU fp32"},
+                         "sample": f"{args.steps} full {rows}-row steps (+{args.warmup} warm-up), oracle/vlnce.py on torch {torch.__version__} CPU fp32"},
         "e2e": {"value": val, "unit": "policy steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -137,13 +145,13 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------------------
 def cpu_baseline_leg(seconds=15.0):
     from oracle import cases, vlnce as oracle_vlnce
+    from vlnce_b200 import synth
 
-    rows = 8
+    rows = ROWS_PER_GPU
     torch.set_num_threads(host_cores())
-    case = dict(model_case(), n=rows)
-    pol = cases.build_policy(oracle_vlnce, case).eval()
+    pol = cases.build_policy(oracle_vlnce, oracle_case(rows)).eval()
     opt = torch.optim.Adam(pol.parameters(), lr=2.5e-4)
-    obs, prev, masks, actions, weights = cases.inputs(case)
+    obs, prev, masks, actions, weights = synth.make_train_batch(1000, 1, rows, hw=HW, length=LENGTH)
     oracle_vlnce.AuxLosses.activate()
     oracle_vlnce.update_agent(pol, opt, obs, prev, masks, actions, weights)  # warm-up
     n, t0 = 0, time.perf_counter()
@@ -154,8 +162,69 @@ def cpu_baseline_leg(seconds=15.0):
         if dt > seconds or n >= 12:
             break
     oracle_vlnce.AuxLosses.deactivate()
-    return {"value": rows * n / dt, "unit": "policy steps/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} steps of {rows} rows (same workload, batch cut from {ROWS_PER_GPU}), oracle/vlnce.py on torch-CPU fp32"}
+    out = {"value": rows * n / dt, "unit": "policy steps/s", "cores": torch.get_num_threads(), "kind": "port",
+           "sample": f"{n} full {rows}-row steps after 1 warm-up (the benchmarked batch), oracle/vlnce.py on torch-CPU fp32; "
+                     "oracle/hb017.py (habitat_baselines v0.1.7 restatement) is parity-unpinned at the dependency boundary"}
+    try:  # run.py:66-67 forces one thread when CUDA is present
+        torch.set_num_threads(1)
+        t0 = time.perf_counter()
+        oracle_vlnce.AuxLosses.activate()
+        oracle_vlnce.update_agent(pol, opt, obs, prev, masks, actions, weights)
+        oracle_vlnce.AuxLosses.deactivate()
+        out["one_thread_value"] = rows / (time.perf_counter() - t0)
+    except Exception:
+        pass
+    return out
+
+
+def parity_block(gpu_snapshot, host_batch):
+    """ONE CPU-oracle step (checker) on the benchmark's own 64-row batch with the same seeded weights, compared with
+    what the CUDA path produced for that batch before its first optimiser step."""
+    import torch.nn.functional as F
+
+    from oracle import cases, vlnce as oracle_vlnce
+
+    torch.set_num_threads(host_cores())
+    rows = ROWS_PER_GPU
+    pol = cases.build_policy(oracle_vlnce, oracle_case(rows)).eval()
+    obs = {k: host_batch[k] for k in ("instruction", "rgb", "depth", "progress")}
+    prev, masks, actions, weights = (host_batch[k] for k in ("prev_actions", "masks", "actions", "weights"))
+    aux = oracle_vlnce.AuxLosses
+    aux.activate()
+    aux.clear()
+    h0 = torch.zeros(rows, pol.net.num_recurrent_layers, 512)
+    dist = pol.build_distribution(obs, h0, prev, masks)
+    logits = dist.logits.view(1, rows, -1)
+    ce = F.cross_entropy(logits.permute(0, 2, 1), actions, reduction="none")
+    action_loss = ((weights * ce).sum(0) / weights.sum(0)).mean()
+    aux_loss = aux.reduce((weights > 0).view(-1))
+    loss = action_loss + aux_loss
+    loss.backward()
+    aux.deactivate()
+    ref_p = dist.logits.detach().exp()
+    our_p = gpu_snapshot["logp"].exp()
+    top2 = ref_p.topk(2, dim=-1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    eq = (ref_p.argmax(-1) == our_p.argmax(-1))
+    num = den = 0.0
+    worst = ("", 0.0)
+    named = dict(pol.named_parameters())
+    for k, g in gpu_snapshot["grads"].items():
+        r = named[k].grad if named[k].grad is not None else torch.zeros_like(named[k])
+        num += float((g - r).double().pow(2).sum())
+        den += float(r.double().pow(2).sum())
+        rel = float((g - r).norm() / (r.norm() + 1e-12))
+        if rel > worst[1] and float(r.norm()) > 1e-6:
+            worst = (k, rel)
+    ref_l = [float(loss), float(action_loss), float(aux_loss)]
+    our_l = gpu_snapshot["losses"]
+    return {"rows": rows, "probs_max_abs": float((ref_p - our_p).abs().max()),
+            "probs_rel": float((ref_p - our_p).abs().max() / ref_p.max()),
+            "loss_rel": abs(our_l[0] - ref_l[0]) / abs(ref_l[0]), "losses_ours": our_l, "losses_oracle": ref_l,
+            "grad_rel_l2": (num / max(den, 1e-30)) ** 0.5, "grad_worst_tensor": worst[0], "grad_worst_rel_l2": worst[1],
+            "argmax_equal": int(eq.sum()), "argmax_rows": rows,
+            "argmax_mismatch_max_margin": float(margin[~eq].max()) if (~eq).any() else 0.0,
+            "oracle": "oracle/vlnce.py torch-CPU fp32, same seeded weights, batch = input set 0"}
 
 
 def main():
@@ -167,6 +236,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the CPU-oracle parity block (one 64-row oracle step)")
     ap.add_argument("--profile", action="store_true", help="also write gpurun_out/step_profile.json")
     ap.add_argument("--pdl", type=int, default=None, choices=[0, 1],
                     help="programmatic dependent launch of the chained kernels (default: VLNCE_PDL / library default)")
@@ -186,7 +256,6 @@ def main():
     import torch.distributed as dist
 
     import vlnce_b200
-    from oracle import cases
     from vlnce_b200 import lib, synth
     from vlnce_b200.il_step import ILTrainerStep
 
@@ -197,8 +266,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.pdl is not None:
         lib.C.vlnce_set_pdl(int(args.pdl))
-    case = model_case()
-    pol = cases.build_policy(vlnce_b200, case).to(dev).eval()
+    pol = synth.build_cma_policy(wseed=WSEED, hw=HW).to(dev).eval()
     pol.net.precision = args.precision
     vlnce_b200.AuxLosses.activate()
     step = ILTrainerStep(pol, lr=2.5e-4)
@@ -250,6 +318,18 @@ def main():
         step.prefetch_visual({k: first[k] for k in ("rgb", "depth")})
         step.rotate_visual(first["rgb"].shape[0])
 
+    # ---- parity snapshot: forward + loss + backward of input set 0 at the seeded weights, BEFORE the first optimiser
+    # step (this pass also autotunes every conv geometry); compared with one CPU-oracle step after the timed legs
+    snapshot = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        obs0, prev0, masks0, actions0, weights0 = split(dev_sets[0])
+        step.compute_grads(obs0, prev0, masks0, actions0, weights0)
+        eng = pol.net.engine()
+        torch.cuda.synchronize()
+        snapshot = {"logp": eng.buf("logits", (ROWS_PER_GPU, 4)).detach().cpu().clone(),
+                    "losses": step._losses.tolist(),
+                    "grads": {k: v.detach().cpu().clone() for k, v in step.fp.grad_views.items()}}
+
     # ---- warm-up (eager), count launches per step, then capture the step into a CUDA graph
     prime(dev_sets[0])
     for i in range(2):
@@ -276,7 +356,7 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         print(json.dumps({"ncu_step": True, "launches": launches_per_step}), flush=True)
-        os._exit(0)
+        return
     if not args.no_graph:
         try:
             # N = 1: the whole step is one graph.  N > 1: forward+loss+backward is captured, the NCCL
@@ -469,9 +549,14 @@ def main():
         except Exception as e:  # keep the tensor-peak figures above
             roof["layer_model_error"] = repr(e)
 
-    cpu = None
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_leg()
+    if snapshot is not None:
+        try:
+            parity = parity_block(snapshot, {k: v for k, v in host_sets[0].items()})
+        except Exception as e:  # the checker must never take the measurement down
+            parity = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         line = {
@@ -494,15 +579,19 @@ def main():
             line["roofline"] = roof
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if parity is not None:
+            line["parity"] = parity
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     sys.stderr.flush()
+    # Orderly teardown (graph before communicator, both before interpreter shutdown) so that the process exits
+    # normally and exit hooks run.
+    torch.cuda.synchronize()
+    graph = None  # noqa: F841  (drops the captured graph and its private pool)
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
-    # Hard exit: tearing down CUDA graphs / NCCL communicators at interpreter shutdown can block
-    # on each other; the measurement is complete and flushed, nothing is left to clean up.
-    os._exit(0)
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

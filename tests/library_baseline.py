@@ -4,9 +4,11 @@ baseline to beat"): the oracle's restatement of the reference model — plain to
 and cuBLAS GEMMs — run in CUDA eager mode on the bench workload (config C2: CMAPolicy forward + DAgger loss + backward
 + Adam, T=1, 64 rows, 256x256 RGB-D, L=80, frozen trunks with eval-mode norms), in three arithmetic modes:
 
-    fp32    TF32 off everywhere (the true-fp32 parity reference)
-    tf32    torch defaults + TF32 matmuls allowed (cuDNN conv / RNN TF32, as stock PyTorch would run the reference)
-    bf16    torch.autocast(bfloat16) around the forward
+    fp32     TF32 off everywhere (the true-fp32 parity reference)
+    tf32     torch defaults + TF32 matmuls allowed (cuDNN conv / RNN TF32, as stock PyTorch would run the reference)
+    bf16     torch.autocast(bfloat16) around the forward
+    bf16_cl  the same with the conv trunks' weights in channels_last (cuDNN's NHWC tensor-core kernels, no layout
+             transposes; the simulator's NHWC images permuted to NCHW are already channels_last-strided)
 
 This is TEST INFRASTRUCTURE (it executes oracle/, which only tests / smoke / the bench's CPU legs may do) and a side
 measurement for DESIGN.md — not a bench arm.  CUDA events, warm-up, 6 rotating input batches (> L2).
@@ -50,6 +52,9 @@ def main():
     ap.add_argument("--rows", type=int, default=64)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--modes", default="fp32,tf32,bf16,bf16_cl")
+    ap.add_argument("--no-act", action="store_true")
+    ap.add_argument("--out", default="library_baseline.json")
     args = ap.parse_args()
     from oracle import cases, vlnce as oracle_vlnce
     from vlnce_b200 import synth
@@ -64,21 +69,24 @@ def main():
     out = {"workload": f"C2: oracle CMAPolicy (torch modules: cuDNN / cuBLAS), CUDA eager, fwd+loss+bwd+Adam, T=1 N={args.rows}, "
                        "256x256 RGB-D, L=80, frozen trunks / eval-mode norms", "modes": {}}
     aux = oracle_vlnce.AuxLosses
-    for mode in ("fp32", "tf32", "bf16"):
+    for mode in args.modes.split(","):
         try:
             tf32 = mode != "fp32"
             torch.backends.cuda.matmul.allow_tf32 = tf32
             torch.backends.cudnn.allow_tf32 = tf32
             pol = cases.build_policy(oracle_vlnce, case).to(dev).eval()
+            if mode.endswith("_cl"):
+                pol.net.rgb_encoder.to(memory_format=torch.channels_last)
+                pol.net.depth_encoder.to(memory_format=torch.channels_last)
             opt = torch.optim.Adam([p for p in pol.parameters() if p.requires_grad], lr=2.5e-4)
             aux.activate()
             for i in range(args.warmup):
-                step_fn(pol, opt, aux, sets[i % 6], mode == "bf16")
+                step_fn(pol, opt, aux, sets[i % 6], mode.startswith("bf16"))
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for i in range(args.steps):
-                loss = step_fn(pol, opt, aux, sets[i % 6], mode == "bf16")
+                loss = step_fn(pol, opt, aux, sets[i % 6], mode.startswith("bf16"))
             b.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / args.steps
@@ -88,13 +96,31 @@ def main():
             continue
         finally:
             aux.deactivate()  # evaluation runs without the auxiliary-loss registry (base_il_trainer.py:278-280)
+        try:  # the two frozen trunks alone (what RGBTrunk / DepthTrunk replace)
+            for name, enc in (("rgb_trunk_ms", pol.net.rgb_encoder), ("depth_trunk_ms", pol.net.depth_encoder)):
+                def run(i):
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode.startswith("bf16")):
+                        return enc(sets[i % 6][0])
+                for i in range(3):
+                    run(i)
+                torch.cuda.synchronize()
+                a.record()
+                for i in range(args.steps):
+                    run(i)
+                b.record()
+                torch.cuda.synchronize()
+                out["modes"][mode][name] = a.elapsed_time(b) / args.steps
+        except Exception as e:
+            out["modes"][mode]["trunk_error"] = f"{type(e).__name__}: {e}"[:300]
+        if args.no_act:
+            continue
         try:
             # act-only (no_grad), the same shapes: compare with tools/bench_act.py
             h0 = torch.zeros(args.rows, pol.net.num_recurrent_layers, 512, device=dev)
 
             def act(i):
                 obs, prev, masks = sets[i % 6][0], sets[i % 6][1], sets[i % 6][2]
-                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode.startswith("bf16")):
                     return pol.act(obs, h0, prev, masks, deterministic=True)
 
             for i in range(3):
@@ -111,7 +137,7 @@ def main():
             out["modes"][mode]["act_error"] = f"{type(e).__name__}: {e}"[:300]
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "library_baseline.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", args.out), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -19,8 +19,21 @@ def test_metric_and_workload_follow_baseline():
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     assert bench.METRIC.startswith("policy steps/sec (batch 64") and "policy steps/sec" in base["metric"]
     assert bench.ROWS_PER_GPU == 64 and bench.HW == 256 and bench.LENGTH == 80     # configs[1] (C2)
-    case = bench.model_case()
+    case = bench.oracle_case()
     assert case["policy"] == "CMAPolicy" and case["n"] == 64 and case["t"] == 1 and case["pm"]
+    # the product arm builds its policy from the package alone (no checker import on that path) ...
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    main_src = src[src.index("def main():"):]
+    assert "from oracle" not in main_src and "os._exit" not in src
+    # ... and it is the same seeded policy the checker rebuilds on its side
+    import torch
+    import vlnce_b200
+    from oracle import cases
+    from vlnce_b200 import synth
+
+    a = synth.build_cma_policy(wseed=bench.WSEED, hw=bench.HW).state_dict()
+    b = cases.build_policy(vlnce_b200, case).state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
     assert "C2" in bench.WORKLOAD and "DAgger" in bench.WORKLOAD
 
 

@@ -34,7 +34,9 @@ def test_assemble_contract_keys(work):
     roof = roofline.assemble(3 * 3.0719, flops, work * 3, peaks, 79.9e6, 321, steps=3)
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel"):
         assert k in roof
-    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["peak"] == 6534.8
+    # the conv trunks are tensor-core class -> the headline pair is the tensor one, the byte model sits beside
+    assert roof["bound"] == "tensor" and roof["unit"] == "TFLOP/s" and roof["peak"] == 1369.7
+    assert roof["hbm"]["unit"] == "GB/s" and roof["hbm"]["peak"] == 6534.8
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
     assert abs(roof["tensor"]["achieved"] - 237.0) < 1.0                      # the figure measured in round 1
     lm = roof["layer_model"]

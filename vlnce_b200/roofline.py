@@ -82,10 +82,9 @@ def assemble(conv_ms_total: float, conv_flops_total: float, work: List[Dict[str,
              traffic, launches_timed: int, steps: int = 3) -> Dict[str, object]:
     """The ``roofline`` object of the bench line for the dominant kernel family (the tcgen05 conv tiles).
 
-    ``achieved`` / ``peak`` / ``frac`` are quoted against whichever resource bounds the launches in aggregate
-    (``layer_model.bound``): algorithmic bytes / time against the measured HBM copy bandwidth, or algorithmic flops /
-    time against the sustained bf16 tensor throughput; the other pair is kept under ``tensor`` / ``hbm`` and the
-    per-launch bound sum under ``layer_model`` (``frac_of_ideal`` = that sum / measured time)."""
+    ``achieved`` / ``peak`` / ``frac`` = algorithmic conv flops / summed conv launch time against the sustained bf16
+    tensor throughput (the conv trunks are tensor-core class).  The unfused per-launch byte model is kept
+    beside it under ``hbm`` and ``layer_model`` (``frac_of_ideal`` = sum of per-launch bounds / measured time)."""
     pt = float(peaks.get("bf16_tflops_sustained", 1400.0))
     ph = float(peaks.get("hbm_gbs", 6500.0))
     src = "MEASURED_PEAKS.json" if peaks else "fallback (1.4 PFLOP/s, 6.5 TB/s)"
@@ -100,8 +99,8 @@ def assemble(conv_ms_total: float, conv_flops_total: float, work: List[Dict[str,
         roof["layer_model"] = lm
         roof["tensor"] = {"achieved": tflops, "peak": pt, "unit": "TFLOP/s", "frac": tflops / pt}
         roof["hbm"] = {"achieved": lm["achieved_gbs"], "peak": ph, "unit": "GB/s", "frac": lm["achieved_gbs"] / ph}
-        if lm["bound"] == "hbm":
-            roof.update(bound="hbm", achieved=lm["achieved_gbs"], peak=ph, unit="GB/s", frac=lm["achieved_gbs"] / ph,
-                        peak_source=src + " hbm_gbs")
-            roof["algorithmic_bytes_per_launch"] = lm["algorithmic_gb_per_step"] * 1e9 / max(lm["launches"], 1)
+        # SURVEY 8d classes the conv trunks as tensor-core work: the headline pair stays the tensor one.  The unfused
+        # per-launch byte model (every conv reads its input and writes its output once) is a work list, not an
+        # algorithmic minimum — fusing 1x1 chains removes bytes — so it is reported beside, never instead.
+        roof["algorithmic_bytes_per_launch"] = lm["algorithmic_gb_per_step"] * 1e9 / max(lm["launches"], 1)
     return roof

@@ -237,3 +237,71 @@ def make_waypoint_eval_batch(seed: int, t: int, n: int, hidden: int = 256, layer
     lp_old = -2.0 + torch.randn(r, 1, generator=gen) * 0.3
     adv = torch.randn(r, 1, generator=gen)
     return obs, h0, actions, prev, v_old, ret, masks, lp_old, adv
+
+
+# ---------------------------------------------------------------------------------------------
+# Seeded policies of the benchmarked configuration, built from the package alone (the benchmark's
+# product arm must not depend on the checker package ``oracle/``).
+# ---------------------------------------------------------------------------------------------
+def cma_model_config(progress_monitor: bool = True, rxr_dim: int = 0, **over):
+    """``vlnce_baselines/config/default.py:214-285`` MODEL node with the ``cma.yaml:31-35`` /
+    ``cma_pm.yaml`` overrides (bi-directional instruction encoder, progress monitor) and, for
+    ``rxr_dim`` > 0, ``rxr_cma_en.yaml:43-48`` (``rxr_instruction`` sensor, 768-d features)."""
+    from .compat import Config
+
+    c = dict(
+        policy_name="CMAPolicy", normalize_rgb=False, ablate_depth=False, ablate_rgb=False, ablate_instruction=False,
+        INSTRUCTION_ENCODER=dict(sensor_uuid="instruction", vocab_size=2504, use_pretrained_embeddings=False,
+                                 embedding_file="", dataset_vocab="", fine_tune_embeddings=False, embedding_size=50,
+                                 hidden_size=128, rnn_type="LSTM", final_state_only=True, bidirectional=True),
+        RGB_ENCODER=dict(cnn_type="TorchVisionResNet50", output_size=256, trainable=False),
+        DEPTH_ENCODER=dict(cnn_type="VlnResnetDepthEncoder", output_size=128, backbone="resnet50",
+                           ddppo_checkpoint="NONE", trainable=False),
+        STATE_ENCODER=dict(hidden_size=512, rnn_type="GRU"),
+        PROGRESS_MONITOR=dict(use=bool(progress_monitor), alpha=1.0),
+        SEQ2SEQ=dict(use_prev_action=False),
+    )
+    if rxr_dim:
+        c["INSTRUCTION_ENCODER"].update(sensor_uuid="rxr_instruction", embedding_size=int(rxr_dim))
+    for k, v in over.items():
+        if isinstance(v, dict) and k in c:
+            c[k].update(v)
+        else:
+            c[k] = v
+    return Config(c)
+
+
+class _no_random_init:
+    """Every tensor is overwritten by ``seeded_state_dict`` right after construction: skip the constructors'
+    random initialisers (orthogonal QR / kaiming over ~30 M weights)."""
+
+    NAMES = ("kaiming_normal_", "kaiming_uniform_", "orthogonal_", "normal_", "uniform_", "xavier_uniform_",
+             "xavier_normal_", "trunc_normal_")
+
+    def __enter__(self):
+        self.saved = {n: getattr(torch.nn.init, n) for n in self.NAMES}
+        for n in self.NAMES:
+            setattr(torch.nn.init, n, lambda tensor, *a, **k: tensor)
+
+    def __exit__(self, *exc):
+        for n, f in self.saved.items():
+            setattr(torch.nn.init, n, f)
+
+
+def build_cma_policy(wseed: int = 13, hw: int = 256, rgb_hw: int | None = None, num_actions: int = 4,
+                     progress_monitor: bool = True, rxr_dim: int = 0, **over):
+    """``CMAPolicy.from_config`` on the benchmark's observation space with ``seeded_state_dict(wseed)`` weights.
+    Defaults = BASELINE config C2 (the same construction + seed as the parity case ``cma_train_pixels``, so the CPU
+    checker can rebuild the identical policy on its side)."""
+    from .cma_policy import CMAPolicy
+    from .compat import Box, Config, Dict as SpaceDict, Discrete
+
+    rgb_hw = rgb_hw or hw
+    space = SpaceDict({"rgb": Box(0, 255, (rgb_hw, rgb_hw, 3), "uint8"),
+                       "depth": Box(0.0, 1.0, (hw, hw, 1), "float32")})
+    cfg = Config(MODEL=cma_model_config(progress_monitor, rxr_dim, **over), TORCH_GPU_ID=0,
+                 TASK_CONFIG=dict(TASK=dict(PANO_ROTATIONS=12)))
+    with _no_random_init():
+        pol = CMAPolicy.from_config(cfg, space, Discrete(num_actions))
+    pol.load_state_dict(seeded_state_dict(pol, wseed), strict=True)
+    return pol
