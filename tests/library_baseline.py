@@ -75,6 +75,10 @@ def main():
             torch.backends.cuda.matmul.allow_tf32 = tf32
             torch.backends.cudnn.allow_tf32 = tf32
             pol = cases.build_policy(oracle_vlnce, case).to(dev).eval()
+            # cuDNN's RNN backward needs train mode; the frozen trunks keep eval-mode norms (the benchmarked config)
+            pol.train()
+            pol.net.rgb_encoder.cnn.eval()
+            pol.net.depth_encoder.visual_encoder.eval()
             if mode.endswith("_cl"):
                 pol.net.rgb_encoder.to(memory_format=torch.channels_last)
                 pol.net.depth_encoder.to(memory_format=torch.channels_last)
