@@ -135,6 +135,23 @@ int vlnce_im2col_depth_stem(const float* x, void* a, int a_dtype, int N, int H, 
                             cudaStream_t stream);
 /* avg_pool2d(2) on (N,H,W,C) f32 -> (N,H/2,W/2,C) f32 (fp32-exact mode of the depth stem) */
 int vlnce_avgpool2x2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);
+/* Image-stationary GroupNorm-ResNet trunk (the whole depth encoder of resnet_encoders.py:85-115 /
+ * habitat_baselines v0.1.7 ResNetEncoder in ONE launch, csrc/depth_fused.cu): every CTA owns whole images and
+ * walks the step table by itself - conv as TMA-fed tcgen05 tiles with the image's accumulators resident in
+ * TMEM, GroupNorm (+residual)(+ReLU) applied out of TMEM, 16-bit activations in the caller's scratch.
+ * table: n_steps rows of 20 int64 (host memory):
+ *   [0] kind (0 conv+GroupNorm, 1 maxpool 3x3/2)  [1] x (N,hin,win,cin) f16  [2] w (cout, k*k*cin) f16
+ *   [3] gamma f32  [4] beta f32  [5] residual (N,hout,wout,cout) f16 | 0  [6] y f16 | 0
+ *   [7] y_f32 (N*hout*wout, ld) | 0  [8] ld  [9] cin  [10] cout  [11] k (1|3)  [12] stride (1|2)  [13] hin
+ *   [14] win  [15] groups  [16] relu  [17] x was written before the launch  [18] eps (float bits)  [19] 0
+ * vlnce_depth_fused_plan encodes the table (tensor maps included) into plan_host (host memory,
+ * vlnce_depth_fused_plan_bytes(n_steps) bytes); the caller copies it to device memory (128-byte aligned) and
+ * passes that to vlnce_depth_fused_run.  The plan holds device addresses: rebuild it when a buffer moves.
+ * ctas: persistent grid (0 = one CTA per image up to the SM count); a CTA loops over images b, b+ctas, ... */
+long long vlnce_depth_fused_plan_bytes(int n_steps);
+int vlnce_depth_fused_plan(const long long* table, int n_steps, int n_images, void* plan_host, long long plan_bytes);
+int vlnce_depth_fused_run(const void* plan_dev, int n_images, int ctas, cudaStream_t stream);
+
 /* MaxPool2d(3, stride 2, pad 1) NHWC */
 int vlnce_maxpool3x3s2(const void* x, void* y, int dtype, int N, int H, int W, int C,
                        cudaStream_t stream);
