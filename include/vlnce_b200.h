@@ -151,6 +151,10 @@ int vlnce_avgpool2x2(const float* x, float* y, int N, int H, int W, int C, cudaS
 long long vlnce_depth_fused_plan_bytes(int n_steps);
 int vlnce_depth_fused_plan(const long long* table, int n_steps, int n_images, void* plan_host, long long plan_bytes);
 int vlnce_depth_fused_run(const void* plan_dev, int n_images, int ctas, cudaStream_t stream);
+/* Debug aid: device buffer of n_steps * 2 * 8 int64; CTA 0 of later vlnce_depth_fused_run launches stamps
+ * %globaltimer per (step, slab) of its first image: [0] MMA pass start, [1] last MMA committed, [2] epilogue sees the
+ * accumulators, [3] statistics done, [4] pass stored, [5] activation producer released.  NULL = off. */
+int vlnce_depth_fused_set_trace(void* buffer);
 
 /* MaxPool2d(3, stride 2, pad 1) NHWC */
 int vlnce_maxpool3x3s2(const void* x, void* y, int dtype, int N, int H, int W, int C,

@@ -1,0 +1,4 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+timeout 200 python tools/trace_depth.py 64 > gpurun_out/trace_depth.log 2>&1; echo "trace exit $?"; head -1 gpurun_out/trace_depth.log; tail -7 gpurun_out/trace_depth.log

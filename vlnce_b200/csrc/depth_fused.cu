@@ -19,7 +19,7 @@
 //
 // Activations live in a caller-owned scratch that stays L2-resident (an image's largest tensor is
 // 256 KB).  Roles: warp 0 / 1 = TMA producers of the tiled / slab rings, warp 2 = MMA issuer,
-// warp 3 = TMEM owner, warps 4-11 = epilogue (two warps per TMEM lane quarter).  The weight producer
+// (and TMEM owner), warps 3-10 = epilogue (two warps per TMEM lane quarter).  The weight producer
 // runs ahead across step boundaries; activation loads wait for the step that produced them.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -32,18 +32,19 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kT = 6;                  // tiled-operand ring slots (128 rows x 128 B)
-constexpr int kS = 2;                  // slab-operand ring slots (<= 256 rows x 128 B)
+constexpr int kT = 8;                  // tiled-operand ring slots: one 128-row x 128-byte tile, or two 64-byte-row tiles
+constexpr int kS = 4;                  // slab-operand ring slots (<= 128 rows x 128 B)
 constexpr int kTBytes = 16 * 1024;
-constexpr int kSBytes = 32 * 1024;
+constexpr int kSBytes = 16 * 1024;
 constexpr int kEpiWarps = 8;
 constexpr int kEpi = kEpiWarps * 32;   // 256 epilogue threads
-constexpr int kThreads = 4 * 32 + kEpi;
+constexpr int kThreads = 3 * 32 + kEpi;   // T producer, S producer, MMA issuer (+ TMEM owner), epilogue
 constexpr int kMaxGroups = 16;         // groups per pass (non-swapped: per slab; swapped: per layer)
 constexpr int kMaxCout = 1024;
-constexpr int kAccBytes = kMaxGroups * kEpi * 8;  // float2 acc[group][thread]  (aliased by chs[cout][2] float2)
-constexpr int kTabBytes = 256 * 8;                // float2 (scale, shift) per slab column
-constexpr int kSmemBytes = kT * kTBytes + kS * kSBytes + kAccBytes + kTabBytes + 1024 /*stats+barriers*/ + 1024 /*align*/;
+constexpr int kMaxSlab = 128;          // MMA N per pass
+constexpr int kStageBytes = 32 * 1024; // swapped epilogue: fp32 staging of one 128-filter tile x <= 64 pixels
+                                       // (aliases the per-channel statistics chs[cout][2] float2 of pass 1)
+constexpr int kSmemBytes = kT * kTBytes + kS * kSBytes + kStageBytes + 1024 /*stats+barriers*/ + 1024 /*align*/;
 
 struct FStep {
   int kind;        // 0 conv + GroupNorm (+residual)(+ReLU), 1 maxpool 3x3/2 pad 1
@@ -87,7 +88,8 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy global writes of this thread -> ordered before later async-proxy (TMA) reads of global memory
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
@@ -103,21 +105,37 @@ __device__ __forceinline__ void wait_steps(const uint32_t* counter, uint32_t wan
   const uint64_t t0 = global_timer_ns();
   for (uint32_t i = 1;; ++i) {
     if (ld_acquire_u32(counter) >= want) return;
-    if ((i & 255u) == 0) {
-      __nanosleep(64);
-      if (global_timer_ns() - t0 > 2000000000ull) break;
-    }
+    __nanosleep(100);
+    if ((i & 255u) == 0 && global_timer_ns() - t0 > 2000000000ull) break;
   }
   printf("vlnce: depth_fused step wait timed out (tag %d, block %d, want %u)\n", tag, blockIdx.x, want);
   __trap();
 }
 
-// tap -> (parity view, x offset, y offset) of the activation window
-__device__ __forceinline__ void tap_window(const FStep& s, int tap, int& mi, int& xo, int& yo) {
-  mi = 0; xo = 0; yo = 0;
-  if (s.taps == 1) return;
+// Debug trace (vlnce_depth_fused_set_trace): CTA 0 / its first image records %globaltimer per (step, slab):
+//   [0] MMA issuer starts the pass   [1] last MMA committed   [2] epilogue sees the accumulators
+//   [3] statistics done   [4] pass stored   [5] activation producer released by the previous step
+//   [6] / [7] ns the MMA issuer spent blocked on the slab / tile ring during the pass
+constexpr int kTraceSlots = 8;
+
+// Sum of v[k] over the 32 lanes for all 32 k at once: 31 shuffles, lane l returns the total of v[l].
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = up ? v[k] : v[k + off];
+      const float keep = up ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void window_of_tap(int tap, int stride, int& mi, int& xo, int& yo) {
   const int r = tap / 3, q = tap - r * 3;
-  if (s.stride == 1) { xo = q - 1; yo = r - 1; return; }
+  if (stride == 1) { mi = 0; xo = q - 1; yo = r - 1; return; }
   // stride 2: input row 2y + r - 1 = parity (r != 1), row index y + (r == 0 ? -1 : 0) of that view
   mi = (r != 1 ? 2 : 0) + (q != 1 ? 1 : 0);
   yo = r == 0 ? -1 : 0;
@@ -125,19 +143,19 @@ __device__ __forceinline__ void tap_window(const FStep& s, int tap, int& mi, int
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
+depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images, long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const uint32_t t_ring = smem_u32(smem);
   const uint32_t s_ring = t_ring + kT * kTBytes;
   uint8_t* scratch = smem + kT * kTBytes + kS * kSBytes;
-  float2* acc = reinterpret_cast<float2*>(scratch);                 // [group][thread] | chs[channel][half]
-  float2* tab = reinterpret_cast<float2*>(scratch + kAccBytes);     // (scale, shift) per slab column
-  uint8_t* tail = scratch + kAccBytes + kTabBytes;
-  float2* stat = reinterpret_cast<float2*>(tail);                   // (mean, rstd) per group   [16]
-  double* red = reinterpret_cast<double*>(tail + 128);              // cross-warp scratch        [16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 256);
+  float* stage = reinterpret_cast<float*>(scratch);                 // [pixel][128 filters] fp32 | chs[channel][half] float2
+  uint8_t* tail = scratch + kStageBytes;
+  float2* stat = reinterpret_cast<float2*>(tail);                   // (mean, rstd) per group          [16]
+  float* part = reinterpret_cast<float*>(tail + 128);               // [group][quarter][sum|sq] floats [16*8]
+  double* red = reinterpret_cast<double*>(tail + 640);              // cross-warp scratch              [16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 768);
   uint64_t* t_full = bars;
   uint64_t* t_empty = t_full + kT;
   uint64_t* s_full = t_empty + kT;
@@ -151,6 +169,7 @@ depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
   const FStep* steps = reinterpret_cast<const FStep*>(plan + hdr->steps_off);
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(plan + hdr->maps_off);
   const int n_steps = hdr->n_steps;
+  if (blockIdx.x != 0) trace = nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -161,7 +180,7 @@ depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
     *steps_done = 0;
     fence_barrier_init();
   }
-  if (warp == 3) {
+  if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -177,27 +196,55 @@ depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
       uint32_t tph = 0, gstep = 0;
       for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
         for (int si = 0; si < n_steps; ++si, ++gstep) {
-          const FStep& s = steps[si];
-          if (s.kind != 0) continue;
-          const bool is_x = !s.swapped;
-          if (is_x && !s.external_input) wait_steps(steps_done, gstep, 1);
-          const CUtensorMap* mw = maps + s.map_w;
-          const uint32_t bytes = 128u * (uint32_t)s.kc * 2u;
-          for (int slab = 0; slab < s.n_slabs; ++slab) {
-            for (int tap = 0; tap < s.taps; ++tap) {
-              int mi, xo, yo;
-              tap_window(s, tap, mi, xo, yo);
-              const CUtensorMap* mx = maps + s.map_x[mi];
-              for (int cc = 0; cc < s.cin_chunks; ++cc) {
-                for (int i = 0; i < s.n_tiles; ++i) {
-                  mbar_wait(&t_empty[ts], tph ^ 1, 40);
-                  mbar_arrive_expect_tx(&t_full[ts], bytes);
-                  const uint32_t dst = t_ring + ts * kTBytes;
-                  if (is_x) tma_load_4d(dst, mx, &t_full[ts], cc * s.kc, xo, i * s.rows_per_tile + yo, img);
-                  else tma_load_2d(dst, mw, &t_full[ts], tap * s.cin + cc * s.kc, i * 128);
-                  if (++ts == kT) { ts = 0; tph ^= 1; }
+          const FStep* sp = steps + si;
+          if (sp->kind != 0) continue;
+          const bool is_x = !sp->swapped;
+          const int kc = sp->kc, cin = sp->cin, n_tiles = sp->n_tiles, rpt = sp->rows_per_tile;
+          const int cin_chunks = sp->cin_chunks, n_slabs = sp->n_slabs, stride = sp->stride;
+          const int U = sp->taps * cin_chunks * n_tiles;
+          const bool taps9 = sp->taps == 9;
+          const int per = kc == 32 ? 2 : 1;          // 64-byte-row tiles travel in pairs
+          const CUtensorMap* mw = maps + sp->map_w;
+          const CUtensorMap* mxs[4] = {maps + sp->map_x[0], maps + sp->map_x[1], maps + sp->map_x[2], maps + sp->map_x[3]};
+          {  // descriptor prefetch for the next conv step (its first loads would otherwise pay the fetch latency)
+            for (int sj = si + 1; sj < n_steps; ++sj) {
+              const FStep* nx = steps + sj;
+              if (nx->kind != 0) continue;
+              tma_prefetch_desc(maps + nx->map_w);
+              tma_prefetch_desc(maps + nx->map_x[0]);
+              if (nx->map_x[1] != nx->map_x[0]) {
+                tma_prefetch_desc(maps + nx->map_x[1]);
+                tma_prefetch_desc(maps + nx->map_x[2]);
+                tma_prefetch_desc(maps + nx->map_x[3]);
+              }
+              break;
+            }
+          }
+          if (is_x && !sp->external_input) {
+            wait_steps(steps_done, gstep, 1);
+            if (trace && img == (int)blockIdx.x) trace[(si * 2) * kTraceSlots + 5] = (long long)global_timer_ns();
+          }
+          const uint32_t bytes = 128u * (uint32_t)kc * 2u;
+          for (int slab = 0; slab < n_slabs; ++slab) {
+            for (int u0 = 0; u0 < U; u0 += per) {
+              const int cnt = U - u0 >= per ? per : U - u0;
+              mbar_wait(&t_empty[ts], tph ^ 1, 40);
+              mbar_arrive_expect_tx(&t_full[ts], bytes * cnt);
+              for (int e = 0; e < cnt; ++e) {
+                const int u = u0 + e;
+                const int kk = u / n_tiles, i = u - kk * n_tiles;
+                const int tap = kk / cin_chunks, cc = kk - tap * cin_chunks;
+                const uint32_t dst = t_ring + ts * kTBytes + e * (kTBytes / 2);
+                if (is_x) {
+                  int mi = 0, xo = 0, yo = 0;
+                  if (taps9) window_of_tap(tap, stride, mi, xo, yo);
+                  const CUtensorMap* mx = mi == 0 ? mxs[0] : (mi == 1 ? mxs[1] : (mi == 2 ? mxs[2] : mxs[3]));
+                  tma_load_4d(dst, mx, &t_full[ts], cc * kc, xo, i * rpt + yo, img);
+                } else {
+                  tma_load_2d(dst, mw, &t_full[ts], tap * cin + cc * kc, i * 128);
                 }
               }
+              if (++ts == kT) { ts = 0; tph ^= 1; }
             }
           }
         }
@@ -211,25 +258,35 @@ depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
       uint32_t sph = 0, gstep = 0;
       for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
         for (int si = 0; si < n_steps; ++si, ++gstep) {
-          const FStep& s = steps[si];
-          if (s.kind != 0) continue;
-          const bool is_x = s.swapped != 0;
-          if (is_x && !s.external_input) wait_steps(steps_done, gstep, 2);
-          const CUtensorMap* mw = maps + s.map_w;
-          const uint32_t bytes = (uint32_t)s.slab_rows * (uint32_t)s.kc * 2u;
-          for (int slab = 0; slab < s.n_slabs; ++slab) {
-            for (int tap = 0; tap < s.taps; ++tap) {
-              int mi, xo, yo;
-              tap_window(s, tap, mi, xo, yo);
-              const CUtensorMap* mx = maps + s.map_x[mi];
-              for (int cc = 0; cc < s.cin_chunks; ++cc) {
-                mbar_wait(&s_empty[ss], sph ^ 1, 41);
-                mbar_arrive_expect_tx(&s_full[ss], bytes);
-                const uint32_t dst = s_ring + ss * kSBytes;
-                if (is_x) tma_load_4d(dst, mx, &s_full[ss], cc * s.kc, xo, yo, img);
-                else tma_load_2d(dst, mw, &s_full[ss], tap * s.cin + cc * s.kc, slab * s.slab_rows);
-                if (++ss == kS) { ss = 0; sph ^= 1; }
+          const FStep* sp = steps + si;
+          if (sp->kind != 0) continue;
+          const bool is_x = sp->swapped != 0;
+          const int kc = sp->kc, cin = sp->cin, slab_rows = sp->slab_rows;
+          const int cin_chunks = sp->cin_chunks, n_slabs = sp->n_slabs, stride = sp->stride;
+          const int KK = sp->taps * cin_chunks;
+          const bool taps9 = sp->taps == 9;
+          const CUtensorMap* mw = maps + sp->map_w;
+          const CUtensorMap* mxs[4] = {maps + sp->map_x[0], maps + sp->map_x[1], maps + sp->map_x[2], maps + sp->map_x[3]};
+          if (is_x && !sp->external_input) {
+            wait_steps(steps_done, gstep, 2);
+            if (trace && img == (int)blockIdx.x) trace[(si * 2) * kTraceSlots + 5] = (long long)global_timer_ns();
+          }
+          const uint32_t bytes = (uint32_t)slab_rows * (uint32_t)kc * 2u;
+          for (int slab = 0; slab < n_slabs; ++slab) {
+            for (int kk = 0; kk < KK; ++kk) {
+              const int tap = kk / cin_chunks, cc = kk - tap * cin_chunks;
+              mbar_wait(&s_empty[ss], sph ^ 1, 41);
+              mbar_arrive_expect_tx(&s_full[ss], bytes);
+              const uint32_t dst = s_ring + ss * kSBytes;
+              if (is_x) {
+                int mi = 0, xo = 0, yo = 0;
+                if (taps9) window_of_tap(tap, stride, mi, xo, yo);
+                const CUtensorMap* mx = mi == 0 ? mxs[0] : (mi == 1 ? mxs[1] : (mi == 2 ? mxs[2] : mxs[3]));
+                tma_load_4d(dst, mx, &s_full[ss], cc * kc, xo, yo, img);
+              } else {
+                tma_load_2d(dst, mw, &s_full[ss], tap * cin + cc * kc, slab * slab_rows);
               }
+              if (++ss == kS) { ss = 0; sph ^= 1; }
             }
           }
         }
@@ -243,59 +300,98 @@ depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
       uint32_t tph = 0, sph = 0, pass = 0;
       for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
         for (int si = 0; si < n_steps; ++si) {
-          const FStep& s = steps[si];
-          if (s.kind != 0) continue;
-          const uint32_t idesc = make_idesc_f16(128, (uint32_t)s.slab_rows, 0u);
-          const uint32_t row_bytes = (uint32_t)s.kc * 2u;
-          const int ksteps = s.kc / 16;
-          for (int slab = 0; slab < s.n_slabs; ++slab, ++pass) {
+          const FStep* sp = steps + si;
+          if (sp->kind != 0) continue;
+          const int slab_rows = sp->slab_rows, n_tiles = sp->n_tiles, n_slabs = sp->n_slabs;
+          const int KK = sp->taps * sp->cin_chunks, U = KK * n_tiles;
+          const uint32_t idesc = make_idesc_f16(128, (uint32_t)slab_rows, 0u);
+          const uint32_t row_bytes = (uint32_t)sp->kc * 2u;
+          const int ksteps = sp->kc / 16;
+          const int per = sp->kc == 32 ? 2 : 1;
+          const uint64_t desc_hi = make_smem_desc(0, row_bytes);
+          const bool tr = trace && img == (int)blockIdx.x;
+          for (int slab = 0; slab < n_slabs; ++slab, ++pass) {
+            if (tr) trace[(si * 2 + (slab & 1)) * kTraceSlots + 0] = (long long)global_timer_ns();
             mbar_wait(tmem_free, (pass & 1) ^ 1, 42);  // epilogue has drained the previous pass
             tc_fence_after_sync();
-            uint32_t first = 0;
-            for (int kk = 0; kk < s.taps * s.cin_chunks; ++kk) {
-              mbar_wait(&s_full[ss], sph, 43);
-              tc_fence_after_sync();
-              const uint64_t bdesc = make_smem_desc(s_ring + ss * kSBytes, row_bytes);
-              for (int i = 0; i < s.n_tiles; ++i) {
-                mbar_wait(&t_full[ts], tph, 44);
-                tc_fence_after_sync();
-                const uint64_t adesc = make_smem_desc(t_ring + ts * kTBytes, row_bytes);
-                const uint32_t d = tmem_base + (uint32_t)(i * s.slab_rows);
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (first | (uint32_t)k) != 0 ? 1u : 0u);
-                umma_commit(&t_empty[ts]);
-                if (++ts == kT) { ts = 0; tph ^= 1; }
+            int u = 0;
+            long long wait_s = 0, wait_t = 0;
+            long long* fine = (tr && si == n_steps - 1) ? trace + n_steps * 2 * kTraceSlots : nullptr;
+            for (int kk = 0; kk < KK; ++kk) {
+              if (fine && kk >= 20 && kk < 24) fine[(kk - 20) * 8 + 0] = clock64();
+              if (tr) {
+                const long long t0 = (long long)global_timer_ns();
+                mbar_wait(&s_full[ss], sph, 43);
+                wait_s += (long long)global_timer_ns() - t0;
+              } else {
+                mbar_wait(&s_full[ss], sph, 43);
               }
-              first = 1;
+              tc_fence_after_sync();
+              if (fine && kk >= 20 && kk < 24) fine[(kk - 20) * 8 + 1] = clock64();
+              const uint64_t bdesc = desc_hi | (uint64_t)(((s_ring + ss * kSBytes) & 0x3FFFFu) >> 4);
+              for (int i = 0; i < n_tiles; ++i, ++u) {
+                const int sub = per == 2 ? (u & 1) : 0;
+                if (sub == 0) {
+                  if (tr) {
+                    const long long t0 = (long long)global_timer_ns();
+                    mbar_wait(&t_full[ts], tph, 44);
+                    wait_t += (long long)global_timer_ns() - t0;
+                  } else {
+                    mbar_wait(&t_full[ts], tph, 44);
+                  }
+                  tc_fence_after_sync();
+                }
+                const uint64_t adesc = desc_hi | (uint64_t)(((t_ring + ts * kTBytes + sub * (kTBytes / 2)) & 0x3FFFFu) >> 4);
+                const uint32_t d = tmem_base + (uint32_t)(i * slab_rows);
+                if (fine && kk >= 20 && kk < 24) fine[(kk - 20) * 8 + 2] = clock64();
+                umma_bf16(d, adesc, bdesc, idesc, kk != 0 ? 1u : 0u);
+                if (fine && kk >= 20 && kk < 24) fine[(kk - 20) * 8 + 3] = clock64();
+                for (int k = 1; k < ksteps; ++k) umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                if (fine && kk >= 20 && kk < 24) fine[(kk - 20) * 8 + 4] = clock64();
+                if (sub == per - 1 || u == U - 1) {
+                  umma_commit(&t_empty[ts]);
+                  if (++ts == kT) { ts = 0; tph ^= 1; }
+                }
+                if (fine && kk >= 20 && kk < 24) fine[(kk - 20) * 8 + 5] = clock64();
+              }
               umma_commit(&s_empty[ss]);
+              if (fine && kk >= 20 && kk < 24) fine[(kk - 20) * 8 + 6] = clock64();
               if (++ss == kS) { ss = 0; sph ^= 1; }
             }
             umma_commit(acc_full);
+            if (tr) {
+              long long* row = trace + (si * 2 + (slab & 1)) * kTraceSlots;
+              row[1] = (long long)global_timer_ns();
+              row[6] = wait_s;
+              row[7] = wait_t;
+            }
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (warps 4-11)
-    const int ew = warp - 4;
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 3-10)
+    const int ew = warp - 3;
     const int q = warp & 3;          // TMEM lane quarter this warp may read
-    const int half = ew >> 2;        // two warps per quarter split the work items
+    const int half = ew >> 2;        // two warps per quarter split the 16-column chunks
     const int r = q * 32 + lane;     // accumulator row (pixel in tile | filter in tile)
-    const int tid = threadIdx.x - 128;
+    const int tid = threadIdx.x - 96;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t pass = 0, gstep = 0;
     for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
       for (int si = 0; si < n_steps; ++si, ++gstep) {
-        const FStep& s = steps[si];
+        const FStep* sp = steps + si;
+        const bool tr = trace && img == (int)blockIdx.x && tid == 0;
         // all epilogue threads have finished writing the previous step (residual / pool inputs
         // are read below by other threads than the ones that wrote them)
         named_barrier_sync(1, kEpi);
-        if (s.kind == 1) {
+        if (sp->kind == 1) {
           // ---- MaxPool2d(3, 2, 1) on the 16-bit NHWC image
-          const int C8 = s.cin / 8, P = s.hout, Q = s.wout;
-          const __half* in = s.pool_in + (size_t)img * s.hin * s.win * s.cin;
-          __half* out = s.out + (size_t)img * P * Q * s.cin;
+          const int cin = sp->cin, hin = sp->hin, win = sp->win;
+          const int C8 = cin / 8, P = sp->hout, Q = sp->wout;
+          const __half* in = sp->pool_in + (size_t)img * hin * win * cin;
+          __half* out = sp->out + (size_t)img * P * Q * cin;
           for (int idx = tid; idx < P * Q * C8; idx += kEpi) {
             const int c8 = idx % C8;
             const int m = idx / C8;
@@ -305,12 +401,12 @@ depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
               const int ih = po * 2 + dy - 1;
-              if ((unsigned)ih >= (unsigned)s.hin) continue;
+              if ((unsigned)ih >= (unsigned)hin) continue;
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
                 const int iw = qo * 2 + dx - 1;
-                if ((unsigned)iw >= (unsigned)s.win) continue;
-                const uint4 v = *reinterpret_cast<const uint4*>(in + ((size_t)ih * s.win + iw) * s.cin + c8 * 8);
+                if ((unsigned)iw >= (unsigned)win) continue;
+                const uint4 v = *reinterpret_cast<const uint4*>(in + ((size_t)ih * win + iw) * cin + c8 * 8);
                 const __half2* hv = reinterpret_cast<const __half2*>(&v);
                 if (!any) {
 #pragma unroll
@@ -322,146 +418,169 @@ depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
                 }
               }
             }
-            *reinterpret_cast<uint4*>(out + (size_t)m * s.cin + c8 * 8) = *reinterpret_cast<const uint4*>(best);
+            *reinterpret_cast<uint4*>(out + (size_t)m * cin + c8 * 8) = *reinterpret_cast<const uint4*>(best);
           }
         } else {
-          const int cpt = s.slab_rows / 16;           // 16-column chunks per tile
-          const int items = s.n_tiles * cpt;
-          for (int slab = 0; slab < s.n_slabs; ++slab, ++pass) {
-            if (!s.swapped) {
-              // ================= tiles = pixels, columns = filters of this slab
-              const int ngs = s.slab_rows / s.gs;
-              for (int g = 0; g < ngs; ++g) acc[g * kEpi + tid] = make_float2(0.f, 0.f);
-              mbar_wait(acc_full, pass & 1, 45);
-              tc_fence_after_sync();
-              // ---- pass 1: per-thread partial sums of every group
-              for (int j = half; j < items; j += 2) {
-                const int i = j / cpt, c0 = (j - i * cpt) * 16;
-                uint32_t v[16];
-                tmem_ld_32x16(lane_addr + (uint32_t)(i * s.slab_rows + c0), v);
-                tmem_ld_wait();
-                float sum = 0.f, sq = 0.f;
+          const int slab_rows = sp->slab_rows, n_tiles = sp->n_tiles, n_slabs = sp->n_slabs;
+          const int gs = sp->gs, cout = sp->cout, px = sp->px, relu = sp->relu, ld_f32 = sp->ld_f32;
+          const int gs_shift = 31 - __clz(gs);
+          const float eps = sp->eps;
+          const float* gamma = sp->gamma;
+          const float* beta = sp->beta;
+          const __half* res = sp->res;
+          __half* outp = sp->out;
+          float* out_f32 = sp->out_f32;
+          const int nchunks = slab_rows / 16;       // 16-column chunks of a tile
+          for (int slab = 0; slab < n_slabs; ++slab, ++pass) {
+            long long* trow = tr ? trace + (si * 2 + (slab & 1)) * kTraceSlots : nullptr;
+            mbar_wait(acc_full, pass & 1, 45);
+            tc_fence_after_sync();
+            if (trow) trow[2] = (long long)global_timer_ns();
+            if (!sp->swapped) {
+              // ================= tiles = pixels (this thread: row r of every tile), columns = filters of the slab
+              // ---- pass 1: per-column sums over the thread's pixels in registers (chunk outer, tile inner),
+              // then one 31-shuffle transpose-reduce per chunk and a group fold
+              for (int ch = half; ch < nchunks; ch += 2) {
+                float v[32];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const float f = __uint_as_float(v[e]);
-                  sum += f;
-                  sq = fmaf(f, f, sq);
-                  if (((e + 1) & (s.gs - 1)) == 0) {   // gs is a power of two <= 16
-                    float2* a = &acc[((c0 + e) / s.gs) * kEpi + tid];
-                    float2 t = *a;
-                    t.x += sum; t.y += sq;
-                    *a = t;
-                    sum = 0.f; sq = 0.f;
+                for (int e = 0; e < 32; ++e) v[e] = 0.f;
+                uint32_t vb[2][16];
+                const uint32_t col = lane_addr + (uint32_t)(ch * 16);
+                tmem_ld_32x16(col, vb[0]);
+                for (int i0 = 0; i0 < n_tiles; i0 += 2) {
+#pragma unroll
+                  for (int b = 0; b < 2; ++b) {
+                    const int i = i0 + b;
+                    if (i < n_tiles) {
+                      tmem_ld_wait();
+                      if (i + 1 < n_tiles) tmem_ld_32x16(col + (uint32_t)((i + 1) * slab_rows), vb[b ^ 1]);
+#pragma unroll
+                      for (int e = 0; e < 16; ++e) {
+                        const float f = __uint_as_float(vb[b][e]);
+                        v[e] += f;
+                        v[16 + e] = fmaf(f, f, v[16 + e]);
+                      }
+                    }
                   }
                 }
+                float tot = warp_transpose_reduce32(v, lane);   // lane l < 16: sum of column l; else sumsq of column l - 16
+                for (int off = 1; off < gs; off <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+                if ((lane & (gs - 1)) == 0)
+                  part[((ch * 16 + (lane & 15)) >> gs_shift) * 8 + q * 2 + (lane >> 4)] = tot;
               }
               named_barrier_sync(1, kEpi);
-              // ---- group statistics: fp64 combine of the 256 per-thread partials
-              for (int g = ew; g < ngs; g += kEpiWarps) {
+              const int ngs = slab_rows >> gs_shift;
+              if (tid < ngs) {   // fp64 combine of the four lane quarters
                 double ds = 0.0, dq = 0.0;
 #pragma unroll
-                for (int m = 0; m < kEpi / 32; ++m) {
-                  const float2 t = acc[g * kEpi + m * 32 + lane];
-                  ds += (double)t.x;
-                  dq += (double)t.y;
+                for (int k = 0; k < 4; ++k) {
+                  ds += (double)part[tid * 8 + k * 2];
+                  dq += (double)part[tid * 8 + k * 2 + 1];
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  ds += __shfl_xor_sync(0xffffffffu, ds, o);
-                  dq += __shfl_xor_sync(0xffffffffu, dq, o);
-                }
-                if (lane == 0) {
-                  const double cnt = (double)s.px * (double)s.gs;
-                  const double mean = ds / cnt;
-                  double var = dq / cnt - mean * mean;
-                  if (var < 0.0) var = 0.0;
-                  stat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)s.eps)));
-                }
+                const double cnt = (double)px * (double)gs;
+                const double mean = ds / cnt;
+                double var = dq / cnt - mean * mean;
+                if (var < 0.0) var = 0.0;
+                stat[tid] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
               }
               named_barrier_sync(1, kEpi);
-              for (int t = tid; t < s.slab_rows; t += kEpi) {
-                const int c = slab * s.slab_rows + t;
-                const float2 st = stat[t / s.gs];
-                const float sc = st.y * __ldg(s.gamma + c);
-                tab[t] = make_float2(sc, __ldg(s.beta + c) - st.x * sc);
-              }
-              named_barrier_sync(1, kEpi);
-              // ---- pass 2: normalise (+ residual)(+ ReLU), 16-bit store
-              for (int j = half; j < items; j += 2) {
-                const int i = j / cpt, c0 = (j - i * cpt) * 16;
-                const size_t o = ((size_t)img * s.px + (size_t)(i * 128 + r)) * s.cout + slab * s.slab_rows + c0;
-                uint4 rv[2];
-                if (s.res != nullptr) {
-                  rv[0] = *reinterpret_cast<const uint4*>(s.res + o);
-                  rv[1] = *reinterpret_cast<const uint4*>(s.res + o + 8);
-                }
-                uint32_t v[16];
-                tmem_ld_32x16(lane_addr + (uint32_t)(i * s.slab_rows + c0), v);
-                tmem_ld_wait();
-                float f[16];
+              if (trow) trow[3] = (long long)global_timer_ns();
+              // ---- pass 2: normalise (+ residual)(+ ReLU), 16-bit store; the chunk's scale / shift stay in registers,
+              // TMEM loads are double-buffered and the residual segment is requested one tile ahead
+              for (int ch = half; ch < nchunks; ch += 2) {
+                float sc[16], sh[16];
+                const int cbase = slab * slab_rows + ch * 16;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                  const float2 t = tab[c0 + e];
-                  f[e] = fmaf(__uint_as_float(v[e]), t.x, t.y);
+                  const float2 st = stat[(ch * 16 + e) >> gs_shift];
+                  sc[e] = st.y * __ldg(gamma + cbase + e);
+                  sh[e] = __ldg(beta + cbase + e) - st.x * sc[e];
                 }
-                if (s.res != nullptr) {
-                  const __half2* rh = reinterpret_cast<const __half2*>(rv);
+                uint32_t vb[2][16];
+                uint4 rb[2][2];
+                const uint32_t col = lane_addr + (uint32_t)(ch * 16);
+                const size_t o0 = ((size_t)img * px + (size_t)r) * cout + cbase;   // tile i: + i * 128 * cout
+                const size_t tile_stride = (size_t)128 * cout;
+                tmem_ld_32x16(col, vb[0]);
+                if (res != nullptr) {
+                  rb[0][0] = *reinterpret_cast<const uint4*>(res + o0);
+                  rb[0][1] = *reinterpret_cast<const uint4*>(res + o0 + 8);
+                }
+                for (int i0 = 0; i0 < n_tiles; i0 += 2) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float2 t = __half22float2(rh[e]);
-                    f[2 * e] += t.x;
-                    f[2 * e + 1] += t.y;
+                  for (int b = 0; b < 2; ++b) {
+                    const int i = i0 + b;
+                    if (i < n_tiles) {
+                      const size_t o = o0 + (size_t)i * tile_stride;
+                      tmem_ld_wait();
+                      if (i + 1 < n_tiles) {
+                        tmem_ld_32x16(col + (uint32_t)((i + 1) * slab_rows), vb[b ^ 1]);
+                        if (res != nullptr) {
+                          rb[b ^ 1][0] = *reinterpret_cast<const uint4*>(res + o + tile_stride);
+                          rb[b ^ 1][1] = *reinterpret_cast<const uint4*>(res + o + tile_stride + 8);
+                        }
+                      }
+                      float f[16];
+#pragma unroll
+                      for (int e = 0; e < 16; ++e) f[e] = fmaf(__uint_as_float(vb[b][e]), sc[e], sh[e]);
+                      if (res != nullptr) {
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rb[b][0]);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                          const float2 t = __half22float2(rh[e]);
+                          f[2 * e] += t.x;
+                          f[2 * e + 1] += t.y;
+                        }
+                      }
+                      if (relu) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
+                      }
+                      if (outp != nullptr) {
+                        __align__(16) __half2 hv[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) hv[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                        *reinterpret_cast<uint4*>(outp + o) = *reinterpret_cast<const uint4*>(&hv[0]);
+                        *reinterpret_cast<uint4*>(outp + o + 8) = *reinterpret_cast<const uint4*>(&hv[4]);
+                      }
+                      if (out_f32 != nullptr) {
+                        float* of = out_f32 + ((size_t)img * px + (size_t)(i * 128 + r)) * ld_f32 + cbase;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) of[e] = f[e];
+                      }
+                    }
                   }
                 }
-                if (s.relu) {
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
-                }
-                if (s.out != nullptr) {
-                  __align__(16) __half2 hv[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) hv[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-                  *reinterpret_cast<uint4*>(s.out + o) = *reinterpret_cast<const uint4*>(&hv[0]);
-                  *reinterpret_cast<uint4*>(s.out + o + 8) = *reinterpret_cast<const uint4*>(&hv[4]);
-                }
-                if (s.out_f32 != nullptr) {
-                  float* of = s.out_f32 + ((size_t)img * s.px + (size_t)(i * 128 + r)) * s.ld_f32 + slab * s.slab_rows + c0;
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) of[e] = f[e];
-                }
               }
+              tc_fence_before_sync();
+              mbar_arrive(tmem_free);     // this thread is done with the accumulator
             } else {
-              // ================= tiles = filters, columns = the image's pixels
-              float2* chs = acc;  // [channel][half] partial (sum, sumsq)
-              for (int t = tid; t < s.cout * 2; t += kEpi) chs[t] = make_float2(0.f, 0.f);
-              named_barrier_sync(1, kEpi);
-              mbar_wait(acc_full, pass & 1, 46);
-              tc_fence_after_sync();
-              for (int j = half; j < items; j += 2) {
-                const int i = j / cpt, c0 = (j - i * cpt) * 16;
-                uint32_t v[16];
-                tmem_ld_32x16(lane_addr + (uint32_t)(i * s.slab_rows + c0), v);
-                tmem_ld_wait();
+              // ================= tiles = filters (this thread: filter r of every tile), columns = the image's pixels
+              float2* chs = reinterpret_cast<float2*>(stage);  // [channel][half] partial (sum, sumsq)
+              // ---- pass 1: this thread's filter summed over its pixel chunks
+              for (int i = 0; i < n_tiles; ++i) {
                 float sum = 0.f, sq = 0.f;
+                for (int ch = half; ch < nchunks; ch += 2) {
+                  uint32_t v[16];
+                  tmem_ld_32x16(lane_addr + (uint32_t)(i * slab_rows + ch * 16), v);
+                  tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const float f = __uint_as_float(v[e]);
-                  sum += f;
-                  sq = fmaf(f, f, sq);
+                  for (int e = 0; e < 16; ++e) {
+                    const float f = __uint_as_float(v[e]);
+                    sum += f;
+                    sq = fmaf(f, f, sq);
+                  }
                 }
-                float2* a = &chs[(i * 128 + r) * 2 + half];
-                float2 t = *a;
-                t.x += sum; t.y += sq;
-                *a = t;
+                chs[(i * 128 + r) * 2 + half] = make_float2(sum, sq);
               }
               named_barrier_sync(1, kEpi);
               {
-                const int G = s.groups;
+                const int G = sp->groups;
                 const int tpg = kEpi / G;          // threads per group (host: 256 % G == 0, tpg <= 32 or G == 1)
                 const int g = tid / tpg, sub = tid - g * tpg;
                 double ds = 0.0, dq = 0.0;
-                for (int e = sub; e < 2 * s.gs; e += tpg) {
-                  const float2 t = chs[g * s.gs * 2 + e];
+                for (int e = sub; e < 2 * gs; e += tpg) {
+                  const float2 t = chs[g * gs * 2 + e];
                   ds += (double)t.x;
                   dq += (double)t.y;
                 }
@@ -477,47 +596,71 @@ depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
                   for (int w8 = 0; w8 < kEpiWarps; ++w8) { ds += red[w8 * 2]; dq += red[w8 * 2 + 1]; }
                 }
                 if (sub == 0) {
-                  const double cnt = (double)s.px * (double)s.gs;
+                  const double cnt = (double)px * (double)gs;
                   const double mean = ds / cnt;
                   double var = dq / cnt - mean * mean;
                   if (var < 0.0) var = 0.0;
-                  stat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)s.eps)));
+                  stat[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
                 }
               }
               named_barrier_sync(1, kEpi);
-              int cur_tile = -1;
-              float sc = 0.f, sh = 0.f;
-              for (int j = half; j < items; j += 2) {
-                const int i = j / cpt, c0 = (j - i * cpt) * 16;
+              if (trow) trow[3] = (long long)global_timer_ns();
+              // ---- pass 2, tile by tile: normalised fp32 tile -> smem [pixel][128 filters] (transpose), then a
+              // coalesced copy-out in 8-filter vectors that adds the residual, applies ReLU and rounds
+              const int vecs = px * 16;
+              for (int i = 0; i < n_tiles; ++i) {
                 const int c = i * 128 + r;
-                if (i != cur_tile) {
-                  cur_tile = i;
-                  const float2 st = stat[c / s.gs];
-                  sc = st.y * __ldg(s.gamma + c);
-                  sh = __ldg(s.beta + c) - st.x * sc;
-                }
-                const size_t o = ((size_t)img * s.px + c0) * s.cout + c;
-                float rf[16];
-                if (s.res != nullptr) {
+                const float2 st = stat[c >> gs_shift];
+                const float scv = st.y * __ldg(gamma + c);
+                const float shv = __ldg(beta + c) - st.x * scv;
+                for (int ch = half; ch < nchunks; ch += 2) {
+                  uint32_t v[16];
+                  tmem_ld_32x16(lane_addr + (uint32_t)(i * slab_rows + ch * 16), v);
+                  tmem_ld_wait();
 #pragma unroll
-                  for (int e = 0; e < 16; ++e) rf[e] = __half2float(s.res[o + (size_t)e * s.cout]);
+                  for (int e = 0; e < 16; ++e) stage[(ch * 16 + e) * 128 + r] = fmaf(__uint_as_float(v[e]), scv, shv);
                 }
-                uint32_t v[16];
-                tmem_ld_32x16(lane_addr + (uint32_t)(i * s.slab_rows + c0), v);
-                tmem_ld_wait();
+                if (i == n_tiles - 1) {   // last TMEM read of the pass: the MMA issuer may start the next one
+                  tc_fence_before_sync();
+                  mbar_arrive(tmem_free);
+                }
+                named_barrier_sync(1, kEpi);
+                for (int t = tid; t < vecs; t += kEpi) {
+                  const int p = t >> 4, c8 = (t & 15) * 8;
+                  const float4 a = *reinterpret_cast<const float4*>(stage + p * 128 + c8);
+                  const float4 b4 = *reinterpret_cast<const float4*>(stage + p * 128 + c8 + 4);
+                  float f[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+                  const size_t o = ((size_t)img * px + p) * cout + i * 128 + c8;
+                  if (res != nullptr) {
+                    const uint4 rv = *reinterpret_cast<const uint4*>(res + o);
+                    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  float f = fmaf(__uint_as_float(v[e]), sc, sh);
-                  if (s.res != nullptr) f += rf[e];
-                  if (s.relu) f = fmaxf(f, 0.f);
-                  if (s.out != nullptr) s.out[o + (size_t)e * s.cout] = __float2half_rn(f);
-                  if (s.out_f32 != nullptr) s.out_f32[((size_t)img * s.px + c0 + e) * s.ld_f32 + c] = f;
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 t2 = __half22float2(rh[e]);
+                      f[2 * e] += t2.x;
+                      f[2 * e + 1] += t2.y;
+                    }
+                  }
+                  if (relu) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                  }
+                  if (outp != nullptr) {
+                    __align__(16) __half2 hv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) hv[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                    *reinterpret_cast<uint4*>(outp + o) = *reinterpret_cast<const uint4*>(hv);
+                  }
+                  if (out_f32 != nullptr) {
+                    float* of = out_f32 + ((size_t)img * px + p) * ld_f32 + i * 128 + c8;
+                    *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                  }
                 }
+                named_barrier_sync(1, kEpi);   // the staging tile is free again
               }
             }
-            // this thread is done with the accumulator: hand TMEM back to the MMA issuer
-            tc_fence_before_sync();
-            mbar_arrive(tmem_free);
+            if (trow) trow[4] = (long long)global_timer_ns();
           }
         }
         // publish the step: generic-proxy global writes -> visible to the TMA (async proxy) loads of later steps
@@ -531,7 +674,7 @@ depth_fused_kernel(const uint8_t* __restrict__ plan, int n_images) {
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 3) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -564,6 +707,7 @@ int encode(EncodeTiledFn enc, CUtensorMap* m, const void* base, int rank, const 
 }
 
 constexpr int kStepFields = 20;
+long long* g_fused_trace = nullptr;
 
 }  // namespace
 }  // namespace vlnce
@@ -654,7 +798,7 @@ extern "C" int vlnce_depth_fused_plan(const long long* table, int n_steps, int n
       s.n_tiles = px / 128;
       s.rows_per_tile = 128 / wout;
       int slab = cout;
-      while (slab > 256 || s.n_tiles * slab > 512) slab /= 2;
+      while (slab > kMaxSlab || s.n_tiles * slab > 512) slab /= 2;
       VLNCE_CHECK_ARG(slab >= 16 && slab % 16 == 0 && cout % slab == 0 && slab % gs == 0 && slab / gs <= kMaxGroups && gs <= 16,
                       "depth_fused_plan: step %d cannot slab %d filters over %d pixel tiles (group size %d)", si, cout, s.n_tiles, gs);
       s.slab_rows = slab;
@@ -663,7 +807,7 @@ extern "C" int vlnce_depth_fused_plan(const long long* table, int n_steps, int n
       box_y = s.rows_per_tile;
     } else {
       // small image: tiles = 128 filters, slab = the image's pixels
-      VLNCE_CHECK_ARG(cout % 128 == 0 && px % 16 == 0 && (cout / 128) * px <= 512,
+      VLNCE_CHECK_ARG(cout % 128 == 0 && px % 16 == 0 && px * 128 * 4 <= kStageBytes && (cout / 128) * px <= 512,
                       "depth_fused_plan: step %d small image %dx%d with %d filters", si, hout, wout, cout);
       VLNCE_CHECK_ARG(groups <= kMaxGroups && kEpi % groups == 0 && (kEpi / groups <= 32 || groups == 1),
                       "depth_fused_plan: step %d group count %d", si, groups);
@@ -725,7 +869,15 @@ extern "C" int vlnce_depth_fused_run(const void* plan_dev, int n_images, int cta
   int grid = ctas > 0 ? ctas : num_sms;
   if (grid > n_images) grid = n_images;
   if (grid > num_sms) grid = num_sms;
-  depth_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(reinterpret_cast<const uint8_t*>(plan_dev), n_images);
+  depth_fused_kernel<<<grid, kThreads, kSmemBytes, stream>>>(reinterpret_cast<const uint8_t*>(plan_dev), n_images,
+                                                             g_fused_trace);
   VLNCE_LAUNCH_CHECK("depth_fused_kernel");
+  return VLNCE_OK;
+}
+
+// Debug: device buffer of n_steps * 2 * 8 int64 that CTA 0 fills with %globaltimer stamps per (step, slab) for its
+// first image (see kTraceSlots); NULL switches tracing off.
+extern "C" int vlnce_depth_fused_set_trace(void* buffer) {
+  g_fused_trace = reinterpret_cast<long long*>(buffer);
   return VLNCE_OK;
 }
