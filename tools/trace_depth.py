@@ -23,7 +23,7 @@ def main():
     plan = next(p for p in tr._plans.values() if p is not False)
     table = plan[2]
     n_steps = table.shape[0]
-    trace = torch.zeros(n_steps * 2 * 8 + 64, dtype=torch.int64, device="cuda")
+    trace = torch.zeros(n_steps * 2 * 8 + 128, dtype=torch.int64, device="cuda")
     C.vlnce_depth_fused_set_trace(ptr(trace))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -48,14 +48,8 @@ def main():
             print(f"{si:3d} {sl} k{row[0]} {row[9]:5d}->{row[10]:<5d} {row[11]} {row[12]} {row[13]:4d} | "
                   f"{us[0]:8.1f} {us[1]:8.1f} {us[2]:8.1f} {us[3]:8.1f} {us[4]:8.1f} {us[5]:8.1f} | "
                   f"{mma:6.1f} {us[2] - us[1]:5.1f} {us[3] - us[2]:6.1f} {us[4] - us[3]:6.1f}   step total {us[4] - prev_end:6.1f}"
-                  f"  mma-phase {us[1] - prev_end:6.1f} (blocked: slab ring {int(r[6]) / 1e3:5.1f}, tile ring {int(r[7]) / 1e3:5.1f})")
+                  f"  mma-phase {us[1] - prev_end:6.1f}")
             prev_end = us[4]
-    f = [int(v) for v in fine]
-    if f[0]:
-        print("MMA-issuer clock64 stamps, last step, k-chunks 20..23 (cycles since the first):")
-        print(" columns: loop top | slab ready | before 1st MMA | after 1st MMA | after MMAs | after tile commit | after slab commit")
-        for k in range(4):
-            print("  ", [f[k * 8 + c] - f[0] for c in range(7)])
 
 
 if __name__ == "__main__":

@@ -139,6 +139,30 @@ __device__ __forceinline__ Tile decode_tile(const TmaConvParams& p, int t, int b
   return ti;
 }
 
+// Look-ahead barrier tests of the MMA issuer: mbarrier.test_wait writes a predicate that is only READ after the
+// current stage's MMAs have been issued, so the ~150-cycle query overlaps their issue (an in-order thread stalls at
+// the first reader of the predicate, not at the test).  The predicates live in function-scope PTX registers
+// (declared once per kernel) because a predicate cannot leave an inline-asm block any other way.
+#define LOOKAHEAD_DECLARE() asm volatile(".reg .pred vlnce_pa, vlnce_pb;")
+__device__ __forceinline__ void lookahead_test_a(uint64_t* bar, uint32_t parity, bool enable) {
+  asm volatile("setp.ne.u32 vlnce_pa, 0, 0;" ::: "memory");   // "not seen" unless the test below runs and succeeds
+  if (enable) asm volatile("mbarrier.test_wait.parity.shared::cta.b64 vlnce_pa, [%0], %1;" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void lookahead_test_b(uint64_t* bar, uint32_t parity, bool enable) {
+  asm volatile("setp.ne.u32 vlnce_pb, 0, 0;" ::: "memory");
+  if (enable) asm volatile("mbarrier.test_wait.parity.shared::cta.b64 vlnce_pb, [%0], %1;" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool lookahead_read_a() {
+  uint32_t ok;
+  asm volatile("selp.u32 %0, 1, 0, vlnce_pa;" : "=r"(ok)::"memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool lookahead_read_b() {
+  uint32_t ok;
+  asm volatile("selp.u32 %0, 1, 0, vlnce_pb;" : "=r"(ok)::"memory");
+  return ok != 0;
+}
+
 template <int BLOCK_N, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -147,6 +171,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   static_assert(2 * MT * BLOCK_N <= 512, "two accumulator sets must fit the 512 TMEM columns");
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int NI = BLOCK_N / 64;  // 32-column epilogue iterations per warp (each warp owns half the columns)
+  LOOKAHEAD_DECLARE();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -263,6 +288,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       Trace tr(p.trace, 1);
+      // The ring barriers are tested ONE stage ahead (mbar_test, non-blocking) before the current stage's MMAs
+      // are issued, so the ~180-cycle round trip of the barrier query hides behind the MMA issue instead of
+      // sitting between every two k-chunks (ptx_sm100.cuh: mbar_test).
+      bool a_ok = false, b_ok = false;   // stage (as / bs) already seen full by a look-ahead test
       for (int it = 0; it < my_tiles; ++it) {
         const int buf = it & 1;
         const uint32_t u = (uint32_t)(it >> 1);
@@ -273,15 +302,31 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const bool wait_b = !p.b_stationary || it == 0;
         uint32_t first = 0;  // 0 until the first MMA of the tile has been issued (it overwrites the accumulator)
         for (int cc = 0; cc < p.c_chunks; ++cc) {
-          mbar_wait(&a_full[as], aph, 25);
+          if (!a_ok) mbar_wait(&a_full[as], aph, 25);
+          a_ok = false;
           tr.rec(11, it * p.c_chunks + cc);
           uint32_t a_row = smem_a0 + as * a_slot;
+          // next activation stage (may belong to the next tile: the ring runs across tile boundaries)
+          int as_n = as + 1;
+          uint32_t aph_n = aph;
+          if (as_n == p.a_stages) { as_n = 0; aph_n ^= 1; }
+          const bool more_a = cc + 1 < p.c_chunks || it + 1 < my_tiles;
           for (int r = 0; r < rs; ++r, a_row += row_step) {
             uint32_t a_tap = a_row;
             for (int sx = 0; sx < rs; ++sx, a_tap += 128) {
-              if (wait_b) mbar_wait(&b_full[bs], bph, 26);
+              if (wait_b && !b_ok) mbar_wait(&b_full[bs], bph, 26);
+              b_ok = false;
               tc_fence_after_sync();
               const uint64_t bdesc = b_hi | (uint64_t)(((smem_b0 + bs * B_BYTES) & 0x3FFFFu) >> 4);
+              // look one stage ahead before issuing this stage's MMAs
+              int bs_n = bs + 1;
+              uint32_t bph_n = bph;
+              if (bs_n == p.b_stages) { bs_n = 0; bph_n ^= 1; }
+              const bool last_tap = r == rs - 1 && sx == rs - 1;
+              const bool last_of_tile = last_tap && cc == p.c_chunks - 1;
+              const bool wait_b_next = last_of_tile ? (!p.b_stationary && it + 1 < my_tiles) : wait_b;
+              lookahead_test_b(&b_full[bs_n], bph_n, wait_b_next);
+              lookahead_test_a(&a_full[as_n], aph_n, last_tap && more_a);
 #pragma unroll
               for (int h = 0; h < MT; ++h) {
                 const uint64_t adesc = a_hi | (uint64_t)(((a_tap + h * p.a_bytes) & 0x3FFFFu) >> 4);
@@ -291,12 +336,14 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               }
               first = 1;
               if (!p.b_stationary) umma_commit(&b_empty[bs]);
-              if (r == rs - 1 && sx == rs - 1) umma_commit(&a_empty[as]);
+              if (last_tap) umma_commit(&a_empty[as]);
               tr.rec(13, it * p.c_chunks + cc);
-              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+              bs = bs_n; bph = bph_n;
+              b_ok = lookahead_read_b();
+              if (last_tap) a_ok = lookahead_read_a();
             }
           }
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          as = as_n; aph = aph_n;
         }
         umma_commit(&acc_full[buf]);
       }

@@ -42,6 +42,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking test of a phase (mbarrier.test_wait never suspends the thread): used to look ONE ring stage ahead
+// from the MMA-issuing thread.  A completed try_wait costs ~180 cycles of that thread's time and nothing issued
+// after it can overlap it (measured: tools/micro/mma_loop.cu); a test issued before the current stage's MMAs has
+// its latency hidden behind their issue, and the blocking wait is only taken when the test says "not yet".
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait (2 s of %globaltimer): a protocol bug becomes a trap with a message instead
 // of a hung GPU.
 __device__ __forceinline__ uint64_t global_timer_ns() {

@@ -89,8 +89,8 @@ def assemble(conv_ms_total: float, conv_flops_total: float, work: List[Dict[str,
     ph = float(peaks.get("hbm_gbs", 6500.0))
     src = "MEASURED_PEAKS.json" if peaks else "fallback (1.4 PFLOP/s, 6.5 TB/s)"
     tflops = conv_flops_total / (conv_ms_total * 1e-3) / 1e12
-    roof = {"kernel": f"conv_tma_kernel + conv_umma_kernel (tcgen05 implicit-GEMM conv tiles, all "
-                      f"{launches_timed // steps} conv launches/step)",
+    roof = {"kernel": f"tcgen05 conv tiles: conv_tma_kernel / conv_umma_kernel / conv3x3_halo_kernel (RGB trunk) + "
+                      f"depth_fused_kernel (whole depth trunk, one launch): {launches_timed // steps} launches/step",
             "bound": "tensor", "achieved": tflops, "peak": pt, "unit": "TFLOP/s", "frac": tflops / pt, "traffic": traffic,
             "peak_source": src + " bf16_tflops_sustained", "launches_timed": launches_timed,
             "conv_ms_per_step": conv_ms_total / steps, "algorithmic_gflop_per_step": conv_flops_total / steps / 1e9}
