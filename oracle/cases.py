@@ -86,6 +86,23 @@ CASES = {
                                         trainable=("rgb", "depth")),
     "wp_eval_abl": dict(policy="WaypointPolicy", kind="wp_eval", t=2, n=2, length=24, wseed=34, iseed=134,
                         ablate=("instruction", "depth")),
+    # trained-like action heads (SURVEY hard-part 2): the head's logit spread is far above every tolerance, so the
+    # argmax action is asserted bit-exact on EVERY row, 16-bit trunks included (``head_scale`` multiplies the seeded
+    # head weight; a trained CMA head separates its top-2 logits by O(1))
+    "cma_act_sharp": dict(policy="CMAPolicy", pm=True, kind="act", n=6, hw=256, length=80, wseed=61, iseed=161,
+                          bn_train=False, head_scale=24.0),
+    "seq2seq_act_sharp": dict(policy="Seq2SeqPolicy", pm=False, kind="act", n=4, hw=256, length=80, wseed=62,
+                              iseed=162, bn_train=False, head_scale=24.0),
+    # BASELINE config C5 at its real instruction shape: (R, 512, 768) multilingual-BERT features
+    # (habitat_extensions/sensors.py:176-196, rxr_cma_en.yaml:43-48), 6 actions, 224 / 256 frames
+    "cma_rxr_act_l512": dict(policy="CMAPolicy", pm=False, kind="act", n=2, hw=256, rgb_hw=224, length=512, wseed=63,
+                             iseed=163, bn_train=False, rxr=768, actions=6, head_scale=24.0),
+    "cma_rxr_train_features_l512": dict(policy="CMAPolicy", pm=True, kind="train", t=2, n=2, hw=256, length=512,
+                                        wseed=64, iseed=164, bn_train=False, features=True, rxr=768, actions=6,
+                                        coef=1.9),
+    # "+ waypoint head" of C5: WaypointPolicy fed the RxR features (the net still asserts an ``instruction`` key,
+    # waypoint_predictors.py:310-315; its encoder reads ``rxr_instruction``, instruction_encoder.py:74-78)
+    "wp_act_rxr": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=512, wseed=65, iseed=165, rxr=768),
     # Waypoint path (BASELINE config C4 dims, 1-wpn-cc.yaml): act on a fresh/continuing env pair,
     # and one PPO mini-batch (evaluate_actions -> WDDPPO losses -> gradients)
     "wp_act": dict(policy="WaypointPolicy", kind="wp_act", n=2, length=40, wseed=21, iseed=201),
@@ -133,6 +150,9 @@ def model_config(case) -> hb017.Config:
     if case["policy"] == "WaypointPolicy":
         from . import waypoint
 
+        if case.get("rxr"):
+            abl.setdefault("INSTRUCTION_ENCODER", {}).update(sensor_uuid="rxr_instruction",
+                                                             embedding_size=int(case["rxr"]))
         return waypoint.waypoint_model_config(WAYPOINT=dict(case.get("waypoint", {})), **abl)
     over = dict(PROGRESS_MONITOR=dict(use=bool(case["pm"]), alpha=1.0), **abl)
     if case.get("rxr"):  # rxr_cma_en.yaml:43-48
@@ -181,7 +201,10 @@ def build_policy(impl, case, num_actions=None):
     num_actions = num_actions or case.get("actions", 4)
     with _skip_random_init():
         pol = cls.from_config(cfg, obs_space(case), hb017.Discrete(num_actions))
-    pol.load_state_dict(synth.seeded_state_dict(pol, case["wseed"]), strict=True)
+    sd = synth.seeded_state_dict(pol, case["wseed"])
+    if case.get("head_scale"):
+        sd["action_distribution.linear.weight"] = sd["action_distribution.linear.weight"] * float(case["head_scale"])
+    pol.load_state_dict(sd, strict=True)
     return pol
 
 
@@ -210,8 +233,13 @@ def inputs(case):
         classes = dict(distance=0 if wp.get("continuous_distance", True) else 6,
                        offset=0 if wp.get("continuous_offset", True) else 7)
         if case["kind"] == "wp_act":
-            return synth.make_waypoint_act_batch(case["iseed"], case["n"], length=case["length"],
-                                                 rgb_u8=case.get("rgb_u8", False), classes=classes)
+            batch = synth.make_waypoint_act_batch(case["iseed"], case["n"], length=case["length"],
+                                                  rgb_u8=case.get("rgb_u8", False), classes=classes)
+            if case.get("rxr"):  # RxR features beside the (still required) token ids
+                gen = torch.Generator().manual_seed(case["iseed"] + 7)
+                batch[0]["rxr_instruction"] = synth.make_rxr_instruction(gen, case["n"], case["length"], case["rxr"],
+                                                                         min_len=case["length"] // 2)
+            return batch
         return synth.make_waypoint_eval_batch(case["iseed"], case["t"], case["n"], length=case["length"],
                                               classes=classes, layers=layers_of(case))
     if case["kind"] == "act":

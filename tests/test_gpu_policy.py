@@ -31,7 +31,7 @@ def cuda_policy(case, precision):
     return pol
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])   # north_star: 1e-3 fp32 / 1e-2 16-bit
 def test_trunks_match_oracle(precision, tol):
     case = cases.CASES["cma_act"]
     opol = cases.build_policy(oracle_vlnce, case).eval()
@@ -54,7 +54,11 @@ def test_trunks_match_oracle(precision, tol):
     assert e_rgb < tol and e_dep < tol
 
 
-@pytest.mark.parametrize("name", ["cma_act", "cma_act_rgb224", "cma_act_bntrain", "cma_rxr_act"])
+SHARP = ("cma_act_sharp", "seq2seq_act_sharp", "cma_rxr_act_l512")   # trained-like heads: every row is decided
+
+
+@pytest.mark.parametrize("name", ["cma_act", "cma_act_rgb224", "cma_act_bntrain", "cma_rxr_act", "cma_act_sharp",
+                                  "cma_rxr_act_l512"])
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
 def test_cma_act_matches_golden(name, precision, tol):
     case = cases.CASES[name]
@@ -78,14 +82,16 @@ def test_cma_act_matches_golden(name, precision, tol):
     # precision (a tie within the stated tolerance has no defined winner)
     top2 = gold["logits"].topk(2, dim=1).values
     decided = (top2[:, 0] - top2[:, 1]) > (0.0 if precision == "fp32" else 5 * tol)
+    if name in SHARP:  # trained-like head: the top-2 logit gap is >= 0.25 on every row, no row is exempt
+        assert bool(decided.all()) and float((top2[:, 0] - top2[:, 1]).min()) > 0.2
     assert torch.equal(action.cpu()[decided], gold["action"][decided]), "argmax actions must be bit-exact"
     assert h_out.shape == gold["rnn_states_out"].shape and action.dtype == torch.int64
 
 
+@pytest.mark.parametrize("name", ["seq2seq_act", "seq2seq_act_sharp"])
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
-def test_seq2seq_act_matches_golden(precision, tol):
-    """BASELINE config C1: Seq2SeqPolicy, batch 2, 256x256 RGB-D, 80-token instruction."""
-    name = "seq2seq_act"
+def test_seq2seq_act_matches_golden(name, precision, tol):
+    """BASELINE config C1: Seq2SeqPolicy, batch 2, 256x256 RGB-D, 80-token instruction (+ a trained-like head)."""
     gold = torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
     got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, device=DEV, precision=precision)
     e_p, e_h = rel(got["logits"].exp(), gold["logits"].exp()), rel(got["rnn_states_out"], gold["rnn_states_out"])

@@ -57,6 +57,7 @@ def check(got, want, rtol, name, grad_norm_tol=None):
 @pytest.mark.parametrize("name,precision,rtol", [
     ("cma_train_features", "fp32", 1e-3), ("cma_train_features_nopm", "fp32", 1e-3),
     ("cma_rxr_train_features", "fp32", 1e-3),  # BASELINE C5 family: RxR BERT-feature instructions, 6 actions
+    ("cma_rxr_train_features_l512", "fp32", 1e-3),   # C5 at its real instruction shape (R, 512, 768)
     ("cma_train_pixels", "fp32", 1e-3), ("cma_train_pixels", "bf16", 1e-2),
     ("seq2seq_train_features", "fp32", 1e-3), ("seq2seq_train_pixels", "fp32", 1e-3),
     ("seq2seq_train_pixels", "bf16", 1e-2)])
@@ -64,7 +65,7 @@ def test_reference_update_arithmetic_on_cuda_policy(name, precision, rtol):
     """base_il_trainer.py:134-172 verbatim (torch CE / AuxLosses.reduce / loss.backward()) on
     the CUDA policy: logits, losses and every trainable gradient vs the reference."""
     got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, device=DEV, precision=precision)
-    check(got, gold(name), rtol, name, grad_norm_tol=0.1 if precision == "bf16" else None)
+    check(got, gold(name), rtol, name, grad_norm_tol=0.05 if precision == "bf16" else None)
 
 
 @pytest.mark.parametrize("name", ["cma_train_features", "cma_train_features_nopm", "seq2seq_train_features",

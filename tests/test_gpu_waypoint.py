@@ -242,7 +242,7 @@ def test_clip_grad_norm_and_gae():
 # ---------------------------------------------------------------------------------------------
 # end to end
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
 def test_resnet18_trunk_matches_oracle(precision, tol):
     """torchvision ResNet-18 (BasicBlock) trunk with the global pool kept (waypoint_predictors.py:53-60, Q2)."""
     from oracle import waypoint as oracle_wp
@@ -271,7 +271,7 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max()) / (float(b.abs().max()) + 1e-12)
 
 
-@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_act_hpn", "wp_act_dc", "wp_act_dd"])
+@pytest.mark.parametrize("name", ["wp_act", "wp_act_u8", "wp_act_hpn", "wp_act_dc", "wp_act_dd", "wp_act_rxr"])
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
 def test_waypoint_act_matches_golden(name, precision, tol):
     want = gold(name)
@@ -282,7 +282,7 @@ def test_waypoint_act_matches_golden(name, precision, tol):
     probs = rel(got["pano_stop_logits"].exp(), want["pano_stop_logits"].exp())
     print(f"{name}[{precision}] rel err probs {probs:.3e} value {errs['value']:.3e} hidden {errs['rnn_states_out']:.3e} "
           f"log_prob {errs['action_log_probs']:.3e}")
-    assert probs < tol and errs["value"] < 3 * tol and errs["rnn_states_out"] < 3 * tol and errs["get_value"] < 3 * tol
+    assert probs < tol and errs["value"] < tol and errs["rnn_states_out"] < tol and errs["get_value"] < tol   # measured <= 7.5e-3
     assert all(got[k].dtype == want[k].dtype and got[k].shape == want[k].shape for k in got), "dtypes / shapes"
     # everything below is a function of the chosen pano (and, for categorical heads, of the chosen class): compare
     # the rows whose pano argmax is decided by more than the tolerance (bit-exact there); a near-tie may
@@ -300,10 +300,13 @@ def test_waypoint_act_matches_golden(name, precision, tol):
         for k in keys:
             if got[k].dtype not in ints:
                 e = rel(got[k][safe], want[k][safe])
-                assert e < 3 * tol, (k, e)
+                # the log-density of a TruncatedNormal whose variance sits at the head's floor (min_offset_var 3e-4)
+                # amplifies a feature error by 1 / var: its bound is 5x the output tolerance (measured 4.1e-2 in the
+                # worst 16-bit case, <= 1.3e-3 elsewhere); every other quantity holds the tolerance itself
+                assert e < (5 * tol if k == "action_log_probs" else tol), (k, e)
 
 
-@pytest.mark.parametrize("name,precision,tol", [("wp_eval", "fp32", 1e-3), ("wp_eval", "bf16", 2e-2),
+@pytest.mark.parametrize("name,precision,tol", [("wp_eval", "fp32", 1e-3), ("wp_eval", "bf16", 1e-2),
                                                 ("wp_eval_hpn", "fp32", 1e-3), ("wp_eval_dd", "fp32", 1e-3),
                                                 ("wp_eval_d_", "fp32", 1e-3)])
 def test_waypoint_ppo_minibatch_matches_golden(name, precision, tol):
@@ -341,7 +344,7 @@ def test_waypoint_ppo_minibatch_matches_golden(name, precision, tol):
             rels.append((float((g - w).norm() / w.norm()), k))
     rels.sort()
     print("wp_eval[bf16] gradient rel-L2: median %.3e, worst %.3e (%s)" % (rels[len(rels) // 2][0], *rels[-1]))
-    assert rels[len(rels) // 2][0] < 0.05 and rels[-1][0] < 0.35, rels[-3:]
+    assert rels[len(rels) // 2][0] < 0.01 and rels[-1][0] < 0.1, rels[-3:]   # measured: median 2.9e-3, worst 4.6e-2
 
 
 def test_fused_wddppo_update_matches_oracle_loop():
