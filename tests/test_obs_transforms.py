@@ -111,3 +111,25 @@ if __name__ == "__main__":
     out = oracle_ot.apply_obs_transforms_batch(frames(), pipeline(oracle_ot))
     torch.save({k: v.clone() for k, v in out.items()}, GOLD)
     print("frozen", GOLD)
+
+
+def test_observation_space_transforms_and_from_config():
+    """``transform_observation_space`` / ``from_config`` of the three transformers (``obs_transformers.py:43-65,83-87,
+    102-128,143-145``; hb v0.1.7 ``ResizeShortestEdge``): what ``get_active_obs_transforms`` +
+    ``apply_obs_transforms_obs_space`` need so that the policy sees the post-transform sensor shapes."""
+    from vlnce_b200 import obs_transforms as ot
+    from vlnce_b200.compat import Box, Config, Dict as SpaceDict
+
+    space = SpaceDict({"rgb": Box(0, 255, (480, 640, 3), "uint8"), "depth": Box(0.0, 1.0, (480, 640, 1), "float32"),
+                       "rgb_1": Box(0, 255, (224, 224, 3), "uint8"), "rgb_2": Box(0, 255, (224, 224, 3), "uint8")})
+    cfg = Config(RL=dict(POLICY=dict(OBS_TRANSFORMS=dict(
+        RESIZE_SHORTEST_EDGE=dict(SIZE=256),
+        CENTER_CROPPER_PER_SENSOR=dict(SENSOR_CROPS=[("rgb", (224, 224)), ("depth", (256, 256))]),
+        OBS_STACK=dict(SENSOR_REWRITES=[("rgb_pano", ["rgb_1", "rgb_2"])])))))
+    ts = [ot.ResizeShortestEdge.from_config(cfg), ot.CenterCropperPerSensor.from_config(cfg), ot.ObsStack.from_config(cfg)]
+    out = ot.apply_obs_transforms_obs_space(space, ts)
+    assert out.spaces["rgb"].shape == (224, 224, 3) and out.spaces["depth"].shape == (256, 256, 1)   # rxr_cma_en.yaml:28-30
+    assert out.spaces["rgb_pano"].shape == (2, 224, 224, 3) and "rgb_1" not in out.spaces
+    assert space.spaces["rgb"].shape == (480, 640, 3)            # the input space is not modified
+    mid = ts[0].transform_observation_space(space)
+    assert mid.spaces["rgb"].shape == (256, 341, 3)              # shortest edge 480 -> 256, 640 -> int(640 * 256 / 480)

@@ -82,6 +82,7 @@ class ILTrainerStep:
             self._loss_acc = torch.zeros(3, device=dev)
 
     # ---------------------------------------------------------------- the reference signature
+    @lib.guarded
     def update_agent(self, observations, prev_actions, not_done_masks, corrected_actions, weights,
                      step_grad: bool = True, loss_accumulation_scalar: int = 1, return_tensor: bool = False):
         self.compute_grads(observations, prev_actions, not_done_masks, corrected_actions, weights,
@@ -95,6 +96,7 @@ class ILTrainerStep:
     # The two phases are separately CUDA-graph capturable; the NCCL all-reduce sits between them.
     # ---- pipelined training loop: the frozen trunks of batch i+1 run concurrently with the head
     # forward/backward/Adam of batch i (they depend on no trainable parameter); bit-identical results
+    @lib.guarded
     def prefetch_visual(self, observations_next):
         """Trunk features of the NEXT batch into the 'next' slot (call inside a forked stream or
         let ``pipelined_step`` do it)."""
@@ -108,11 +110,13 @@ class ILTrainerStep:
         R = rgb.shape[0]
         eng.encode_visual(observations_next, *eng.visual_buffers(R, "next"))
 
+    @lib.guarded
     def rotate_visual(self, R):
         eng = self.policy.net.engine()
         for cur, nxt in zip(eng.visual_buffers(R, "cur"), eng.visual_buffers(R, "next")):
             cur.copy_(nxt)
 
+    @lib.guarded
     def pipelined_step(self, observations, prev_actions, not_done_masks, corrected_actions, weights,
                        observations_next, apply: bool = True):
         """One update on the CURRENT batch (its trunk features were prefetched by the previous
@@ -130,6 +134,7 @@ class ILTrainerStep:
         self.rotate_visual(R)
         return self._losses
 
+    @lib.guarded
     def compute_grads(self, observations, prev_actions, not_done_masks, corrected_actions, weights,
                       loss_accumulation_scalar: int = 1, visual_slot=None):
         pol = self.policy
@@ -169,6 +174,7 @@ class ILTrainerStep:
         fp.grad.zero_()
         eng.run_backward(head, fp.grad_views, d_raw, None, d_hat if use_pm else None)
 
+    @lib.guarded
     def apply_grads(self, step_grad: bool = True, allreduce: bool = True):
         fp = self.fp
         st = lib.stream()

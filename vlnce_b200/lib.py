@@ -110,6 +110,54 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class guard:
+    """Make ``device`` the current CUDA device for the duration of a public entry point.  Kernels are enqueued on
+    ``torch.cuda.current_stream()`` and scratch is allocated on the current device, while the reference's trainers
+    never call ``torch.cuda.set_device`` (they build ``torch.device("cuda", TORCH_GPU_ID / local_rank)``,
+    ``base_il_trainer.py:46``, ``ddppo_waypoint_trainer.py:328-341``): without this a policy on cuda:1 would launch on
+    device 0's stream with device-1 pointers.  No-op for CPU tensors (dry-run walks) and when the device is current."""
+
+    def __init__(self, device):
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        self.ctx = None
+        if dev.type == "cuda" and torch.cuda.is_available():
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            if idx != torch.cuda.current_device():
+                self.ctx = torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def guarded(fn):
+    """Decorator for methods of an ``nn.Module`` (or of an object with a ``.policy`` / ``.actor_critic`` module):
+    run with the module's device current (see ``guard``)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        mod = self
+        for attr in ("policy", "actor_critic"):
+            if not isinstance(mod, torch.nn.Module) or attr in getattr(mod, "__dict__", {}):
+                mod = getattr(self, attr, mod)
+                break
+        try:
+            dev = next(mod.parameters()).device
+        except (StopIteration, AttributeError):
+            return fn(self, *args, **kwargs)
+        with guard(dev):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 def require_cuda(t: torch.Tensor, what: str = "tensor"):
     if not t.is_cuda:
         raise VlnceError(f"{what} is on {t.device}: vlnce_b200 computes on CUDA only (no CPU fallback)")

@@ -9,12 +9,15 @@ and keeps uint8 frames uint8; cropping / stacking alone are views and copies (no
 """
 from __future__ import annotations
 
+import copy
+
 import numbers
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
 
 from . import lib
+from .compat import HAVE_HABITAT, Box, baseline_registry
 from .lib import C, ptr
 
 
@@ -59,6 +62,21 @@ class ResizeShortestEdge:
         assert channels_last, "the simulator's layout (NHWC) is the only one on this path"
         self._size, self.trans_keys = size, trans_keys
 
+    def transform_observation_space(self, observation_space):
+        """hb v0.1.7 ``ResizeShortestEdge.transform_observation_space``: image boxes shrink to the resized (h, w)."""
+        observation_space = copy.deepcopy(observation_space)
+        if self._size is not None:
+            for key, sp in observation_space.spaces.items():
+                if key in self.trans_keys and len(sp.shape) >= 3:
+                    h, w = sp.shape[-3], sp.shape[-2]
+                    if self._size != min(h, w):
+                        observation_space.spaces[key] = _box_with_hw(sp, _resized_hw(h, w, self._size))
+        return observation_space
+
+    @classmethod
+    def from_config(cls, config):
+        return cls(config.RL.POLICY.OBS_TRANSFORMS.RESIZE_SHORTEST_EDGE.SIZE)
+
     @torch.no_grad()
     def forward(self, observations: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         if self._size is not None:
@@ -76,6 +94,19 @@ class CenterCropperPerSensor:
         assert channels_last
         self.sensor_crops = {k: ((int(v), int(v)) if isinstance(v, numbers.Number) else tuple(v))
                              for k, v in dict(sensor_crops).items()}
+
+    def transform_observation_space(self, observation_space):
+        """``obs_transformers.py:43-65``."""
+        observation_space = copy.deepcopy(observation_space)
+        for key, sp in observation_space.spaces.items():
+            if key in self.sensor_crops and tuple(sp.shape[-3:-1]) != self.sensor_crops[key]:
+                observation_space.spaces[key] = _box_with_hw(sp, self.sensor_crops[key])
+        return observation_space
+
+    @classmethod
+    def from_config(cls, config):
+        """``obs_transformers.py:83-87``."""
+        return cls(config.RL.POLICY.OBS_TRANSFORMS.CENTER_CROPPER_PER_SENSOR.SENSOR_CROPS)
 
     @torch.no_grad()
     def forward(self, observations):
@@ -95,6 +126,26 @@ class ObsStack:
     def __init__(self, sensor_rewrites: List[Tuple[str, Sequence[str]]]):
         self.rewrite_dict = dict(sensor_rewrites)
 
+    def transform_observation_space(self, observation_space):
+        """``obs_transformers.py:102-128``: the stacked sensor is a Box of shape (K,) + sensor shape."""
+        import numpy as np
+
+        observation_space = copy.deepcopy(observation_space)
+        for target, sensors in self.rewrite_dict.items():
+            orig = observation_space.spaces[sensors[0]]
+            for k in sensors:
+                del observation_space.spaces[k]
+            low = orig.low if np.isscalar(orig.low) else np.min(orig.low)
+            high = orig.high if np.isscalar(orig.high) else np.max(orig.high)
+            observation_space.spaces[target] = Box(low=low, high=high, shape=(len(sensors),) + tuple(orig.shape),
+                                                   dtype=orig.dtype)
+        return observation_space
+
+    @classmethod
+    def from_config(cls, config):
+        """``obs_transformers.py:143-145``."""
+        return cls(config.RL.POLICY.OBS_TRANSFORMS.OBS_STACK.SENSOR_REWRITES)
+
     @torch.no_grad()
     def forward(self, observations):
         for new_key, old_keys in self.rewrite_dict.items():
@@ -105,6 +156,30 @@ class ObsStack:
         return observations
 
     __call__ = forward
+
+
+def _box_with_hw(box, hw):
+    """hb v0.1.7 ``overwrite_gym_box_shape``: the same Box with its (h, w) replaced (channels last)."""
+    import numpy as np
+
+    shape = tuple(box.shape[:-3]) + (int(hw[0]), int(hw[1])) + tuple(box.shape[-1:])
+    low = box.low if np.isscalar(box.low) else np.min(box.low)
+    high = box.high if np.isscalar(box.high) else np.max(box.high)
+    return Box(low=low, high=high, shape=shape, dtype=box.dtype)
+
+
+def apply_obs_transforms_obs_space(obs_space, obs_transforms):
+    """hb v0.1.7 ``apply_obs_transforms_obs_space``."""
+    for t in obs_transforms:
+        obs_space = t.transform_observation_space(obs_space)
+    return obs_space
+
+
+# with habitat_baselines installed the classes register under the reference's names, so
+# ``get_active_obs_transforms(config)`` (``ddppo_waypoint_trainer.py:92``, ``recollect_trainer.py:57``) builds these
+if HAVE_HABITAT:  # pragma: no cover - not installable in the build image
+    for _cls in (CenterCropperPerSensor, ObsStack):
+        baseline_registry.register_obs_transformer(_cls, name=_cls.__name__)
 
 
 def apply_obs_transforms_batch(batch: Dict[str, torch.Tensor], obs_transforms) -> Dict[str, torch.Tensor]:

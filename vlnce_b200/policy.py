@@ -34,6 +34,7 @@ class ILPolicy(Policy):
         raise NotImplementedError
 
     # ---- reference surface ---------------------------------------------------------------
+    @lib.guarded
     def act(self, observations, rnn_states, prev_actions, masks, deterministic=False):
         """``policy.py:26-44``: features -> Categorical -> mode() / sample()."""
         with torch.no_grad():
@@ -53,6 +54,7 @@ class ILPolicy(Policy):
     def evaluate_actions(self, *args, **kwargs):
         raise NotImplementedError
 
+    @lib.guarded
     def build_distribution(self, observations, rnn_states, prev_actions, masks):
         """``policy.py:52-58``; ``.logits`` are normalised log-probabilities and carry the
         hand-written backward when grad is enabled."""

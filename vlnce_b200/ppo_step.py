@@ -115,7 +115,47 @@ class ActionDictRolloutStorage:
                    tm(self.value_preds), tm(self.returns), tm(self.masks), tm(self.action_log_probs), tm(advantages))
 
 
-class WDDPPOStep:
+class FusedAdam(torch.optim.Optimizer):
+    """The optimiser object the reference trainer talks to (``agent.optimizer``: ``state_dict()`` into checkpoints,
+    ``LambdaLR(agent.optimizer)`` for the linear lr decay, ``ddppo_waypoint_trainer.py:425,485``).  The update itself
+    is the fused ``vlnce_adam_step`` launch of ``WDDPPOStep.apply_grads`` on the flat parameter buffer; this class
+    holds the hyper-parameters (``param_groups[0]["lr"]`` is read at every step, so schedulers work) and serialises
+    the flat moments."""
+
+    def __init__(self, params, lr, betas, eps, owner):
+        super().__init__(list(params), dict(lr=lr, betas=betas, eps=eps))
+        self._owner = owner
+
+    def step(self, closure=None):  # the fused path applies the update inside WDDPPOStep.apply_grads
+        raise RuntimeError("FusedAdam is stepped by WDDPPOStep.update / apply_grads")
+
+    def state_dict(self):
+        o = self._owner
+        o._prepare()
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        return {"state": {"step": int(o.step_id), "exp_avg": o.fp.exp_avg.detach().clone(),
+                          "exp_avg_sq": o.fp.exp_avg_sq.detach().clone(), "names": list(o.fp.named)},
+                "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        o = self._owner
+        o._prepare()
+        st = sd["state"]
+        if list(st.get("names", list(o.fp.named))) != list(o.fp.named):
+            raise ValueError("optimizer state belongs to a different parameter layout")
+        o.fp.exp_avg.copy_(st["exp_avg"])
+        o.fp.exp_avg_sq.copy_(st["exp_avg_sq"])
+        o.step_id = int(st["step"])
+        o._step_dev.fill_(o.step_id)
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            g.update({k: v for k, v in saved.items() if k != "params"})
+
+
+class WDDPPOStep(torch.nn.Module):
+    """``nn.Module`` like the reference's ``WDDPPO`` (habitat_baselines ``PPO``): ``state_dict()`` keys are prefixed
+    ``actor_critic.`` (``ddppo_waypoint_trainer.py:141-143,484``), ``.optimizer`` exists, and ``clip_param`` may be
+    reassigned between updates (``use_linear_clip_decay``)."""
+
     LOSS_KEYS = ("loss", "value_loss", "action_loss", "entropy_loss", "offset_loss", "pano_entropy", "offset_entropy",
                  "distance_entropy")
 
@@ -123,13 +163,15 @@ class WDDPPOStep:
                  entropy_coef=0.01, lr=2.0e-4, eps=1e-5, max_grad_norm=0.2, use_clipped_value_loss=True,
                  use_normalized_advantage=False, offset_regularize_coef=0.1146, pano_entropy_coef=1.0,
                  offset_entropy_coef=0.0, distance_entropy_coef=0.0, betas=(0.9, 0.999), process_group=None):
+        super().__init__()
         self.actor_critic = actor_critic
         self.clip_param, self.ppo_epoch, self.num_mini_batch = clip_param, ppo_epoch, num_mini_batch
-        self.lr, self.eps, self.betas, self.max_grad_norm = lr, eps, betas, max_grad_norm
+        self.eps, self.betas, self.max_grad_norm = eps, betas, max_grad_norm
         self.use_normalized_advantage = use_normalized_advantage
-        self.ppo_consts = _host_floats([clip_param, value_loss_coef, entropy_coef, offset_regularize_coef,
-                                        pano_entropy_coef, offset_entropy_coef, distance_entropy_coef,
-                                        float(bool(use_clipped_value_loss))])
+        self._loss_coefs = [value_loss_coef, entropy_coef, offset_regularize_coef, pano_entropy_coef,
+                            offset_entropy_coef, distance_entropy_coef, float(bool(use_clipped_value_loss))]
+        self.ppo_consts = _host_floats([clip_param] + self._loss_coefs)
+        self.optimizer = FusedAdam((p for p in actor_critic.parameters() if p.requires_grad), lr, betas, eps, self)
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -137,9 +179,24 @@ class WDDPPOStep:
         self.fp: Optional[FlatParams] = None
         self.step_id = 0
 
+    @property
+    def lr(self):
+        return float(self.optimizer.param_groups[0]["lr"])
+
+    @lr.setter
+    def lr(self, value):
+        self.optimizer.param_groups[0]["lr"] = float(value)
+
+    def forward(self, *x):
+        raise NotImplementedError
+
     def _prepare(self):
         if self.fp is None or not self.fp.aliased():
+            old = self.fp
             self.fp = FlatParams(trainable_named(self.actor_critic))
+            if old is not None and old.total == self.fp.total:  # parameters were re-pointed (load_state_dict / .to()): keep the moments
+                self.fp.exp_avg.copy_(old.exp_avg)
+                self.fp.exp_avg_sq.copy_(old.exp_avg_sq)
             dev = self.fp.flat.device
             self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
             self._step_dev.fill_(self.step_id)
@@ -153,11 +210,13 @@ class WDDPPOStep:
             return adv
         return (adv - adv.mean()) / (adv.std() + 1e-5)  # optional, off in every shipped recipe: (T,N) torch ops
 
+    @lib.guarded
     def update_minibatch(self, sample, apply: bool = True):
         """One mini-batch of ``WDDPPO.update`` (:56-140).  Returns the device tensor of ``LOSS_KEYS``."""
         obs, h0, actions, prev_actions, v_old, ret, masks, lp_old, adv = sample
         pol = self.actor_critic
         self._prepare()
+        self.ppo_consts[0] = float(self.clip_param)  # the trainer may decay it between updates (use_linear_clip_decay)
         eng = pol.net.engine()
         fp = self.fp
         st = lib.stream()
@@ -179,6 +238,7 @@ class WDDPPOStep:
             self.apply_grads()
         return self._losses
 
+    @lib.guarded
     def apply_grads(self):
         fp = self.fp
         st = lib.stream()
@@ -191,6 +251,7 @@ class WDDPPOStep:
         C.vlnce_adam_step(ptr(fp.flat), ptr(fp.grad), ptr(fp.exp_avg), ptr(fp.exp_avg_sq), fp.total, float(self.lr),
                           float(self.betas[0]), float(self.betas[1]), float(self.eps), 0, ptr(self._step_dev), 1.0, st)
 
+    @lib.guarded
     def update(self, rollouts):
         """``WDDPPO.update``: returns (value_loss, action_loss, entropy_loss, pano_entropy, offset_entropy,
         distance_entropy) averaged over epochs x mini-batches — ONE D2H read at the end instead of six

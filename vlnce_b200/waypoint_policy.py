@@ -694,7 +694,11 @@ class WaypointPolicy(Policy):
         self.wypt_cfg = model_config.WAYPOINT
         self._offset_limit = np.pi / self._config.num_panos
         self._sample_calls = 0
-        self.sample_seed = 0x5EED
+        # stream of the counter-based sampler: torch's seed (the trainer seeds per rank with
+        # SEED + world_rank * NUM_ENVIRONMENTS, ddppo_waypoint_trainer.py:330-336) mixed with the rank, so DD-PPO
+        # workers draw different exploration noise; ``_sample_calls`` advances per act() and can be restored on requeue
+        rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+        self.sample_seed = (int(torch.initial_seed()) * 0x9E3779B1 + rank * 0x85EBCA77 + 0x5EED) & 0x7FFFFFFF
 
     def forward(self, *x):
         raise NotImplementedError
@@ -707,6 +711,7 @@ class WaypointPolicy(Policy):
         return cls(observation_space=observation_space, action_space=action_space, model_config=config.MODEL)
 
     # ------------------------------------------------------------------ act (waypoint_policy.py:129-247)
+    @lib.guarded
     def act(self, observations, rnn_states, prev_actions, masks, deterministic=False):
         with torch.no_grad():
             eng = self.net.engine()
@@ -736,6 +741,7 @@ class WaypointPolicy(Policy):
             dist = CustomFixedCategorical(logits=out["logp"].clone())
             return (out["values"].clone(), actions, action_elements, modes, variances, col(2), out["h_out"].clone(), dist)
 
+    @lib.guarded
     def get_value(self, observations, rnn_states, prev_actions, masks):  # :249-263
         with torch.no_grad():
             out = self.net.engine().forward(observations, rnn_states, prev_actions, masks, save=False, critic=self.critic)
@@ -746,6 +752,7 @@ class WaypointPolicy(Policy):
     def _action_rows(actions, B):
         return tuple(actions[k].reshape(B).float().contiguous() for k in ("pano", "offset", "distance"))
 
+    @lib.guarded
     def evaluate_actions(self, observations, rnn_states, prev_actions, masks, action_components):
         named = trainable_named(self)
         need_grad = torch.is_grad_enabled() and len(named) > 0
