@@ -41,14 +41,47 @@ WORKLOAD = ("C2: CMAPolicy fwd+DAgger loss+bwd+Adam, T=1 N=64/GPU, rgb u8 256x25
 
 
 WSEED = 13  # seeded "trained-like" weights (vlnce_b200.synth.seeded_state_dict); the parity case cma_train_pixels uses the same
+RGB_HW, RXR_DIM, ACTIONS, COEF = 256, 0, 4, 3.2
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
+    "c2": dict(rows=64, hw=256, rgb_hw=256, length=80, rxr=0, actions=4, coef=3.2),
+    # BASELINE.json configs[4]: RxR-shaped multilingual-BERT features (512 tokens x 768), 6 actions, frames after the
+    # RxR observation transforms (rgb 224x224, depth 256x256: rxr_cma_en.yaml:28-30), 256 rows over 8 GPUs = 32 / GPU
+    "c5": dict(rows=32, hw=256, rgb_hw=224, length=512, rxr=768, actions=6, coef=1.9),
+}
 
 
-def oracle_case(rows=ROWS_PER_GPU):
+def select_workload(name):
+    global ROWS_PER_GPU, HW, RGB_HW, LENGTH, RXR_DIM, ACTIONS, COEF, METRIC, WORKLOAD
+    w = WORKLOADS[name]
+    ROWS_PER_GPU, HW, RGB_HW, LENGTH = w["rows"], w["hw"], w["rgb_hw"], w["length"]
+    RXR_DIM, ACTIONS, COEF = w["rxr"], w["actions"], w["coef"]
+    if name == "c5":
+        METRIC = "policy steps/sec (RxR: batch 32/GPU, 224x224 RGB + 256x256 depth, 512x768 BERT instruction features)"
+        WORKLOAD = ("C5: CMAPolicy fwd+DAgger loss+bwd+Adam, T=1 N=32/GPU, rgb u8 224x224x3, depth f32 256x256x1, "
+                    "rxr_instruction f32 512x768, 6 actions, progress monitor on, conv trunks frozen/eval-mode norms")
+
+
+def make_batch(seed, rows):
+    from vlnce_b200 import synth
+
+    return synth.make_train_batch(seed, 1, rows, hw=HW, rgb_hw=RGB_HW, length=LENGTH, num_actions=ACTIONS, coef=COEF,
+                                  rxr_dim=RXR_DIM)
+
+
+def instr_key():
+    return "rxr_instruction" if RXR_DIM else "instruction"
+
+
+def oracle_case(rows=None):
+    rows = ROWS_PER_GPU if rows is None else rows
     """CHECKER side only (reference arm, cpu_baseline leg, parity block): the oracle's description of the same policy."""
     from oracle import cases
 
     case = dict(cases.CASES["cma_train_pixels"], t=1, n=rows)
     assert case["wseed"] == WSEED
+    if RXR_DIM:
+        case.update(rgb_hw=RGB_HW, length=LENGTH, rxr=RXR_DIM, actions=ACTIONS, coef=COEF)
     return case
 
 
@@ -117,7 +150,7 @@ def run_reference(args, rank, world):
     case = oracle_case(rows)
     pol = cases.build_policy(oracle_vlnce, case).eval()
     opt = torch.optim.Adam(pol.parameters(), lr=2.5e-4)
-    obs, prev, masks, actions, weights = synth.make_train_batch(1000, 1, rows, hw=HW, length=LENGTH)
+    obs, prev, masks, actions, weights = make_batch(1000, rows)
     oracle_vlnce.AuxLosses.activate()
 
     def step():
@@ -151,7 +184,7 @@ def cpu_baseline_leg(seconds=15.0):
     torch.set_num_threads(host_cores())
     pol = cases.build_policy(oracle_vlnce, oracle_case(rows)).eval()
     opt = torch.optim.Adam(pol.parameters(), lr=2.5e-4)
-    obs, prev, masks, actions, weights = synth.make_train_batch(1000, 1, rows, hw=HW, length=LENGTH)
+    obs, prev, masks, actions, weights = make_batch(1000, rows)
     oracle_vlnce.AuxLosses.activate()
     oracle_vlnce.update_agent(pol, opt, obs, prev, masks, actions, weights)  # warm-up
     n, t0 = 0, time.perf_counter()
@@ -187,7 +220,7 @@ def parity_block(gpu_snapshot, host_batch):
     torch.set_num_threads(host_cores())
     rows = ROWS_PER_GPU
     pol = cases.build_policy(oracle_vlnce, oracle_case(rows)).eval()
-    obs = {k: host_batch[k] for k in ("instruction", "rgb", "depth", "progress")}
+    obs = {k: host_batch[k] for k in (instr_key(), "rgb", "depth", "progress")}
     prev, masks, actions, weights = (host_batch[k] for k in ("prev_actions", "masks", "actions", "weights"))
     aux = oracle_vlnce.AuxLosses
     aux.activate()
@@ -234,7 +267,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE metric config (default); "
+                    "c5 = RxR-shaped features (side measurement)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--eager-allreduce", action="store_true",
+                    help="world > 1: keep the NCCL all-reduce + Adam outside the CUDA graph (round-1 scheme)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the CPU-oracle parity block (one 64-row oracle step)")
     ap.add_argument("--profile", action="store_true", help="also write gpurun_out/step_profile.json")
@@ -245,6 +282,7 @@ def main():
                          "(for `ncu --profile-from-start off`); prints no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    select_workload(args.workload)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -266,7 +304,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.pdl is not None:
         lib.C.vlnce_set_pdl(int(args.pdl))
-    pol = synth.build_cma_policy(wseed=WSEED, hw=HW).to(dev).eval()
+    pol = synth.build_cma_policy(wseed=WSEED, hw=HW, rgb_hw=RGB_HW, num_actions=ACTIONS, rxr_dim=RXR_DIM).to(dev).eval()
     pol.net.precision = args.precision
     vlnce_b200.AuxLosses.activate()
     step = ILTrainerStep(pol, lr=2.5e-4)
@@ -276,7 +314,7 @@ def main():
     NSETS = 6
     host_sets, dev_sets = [], []
     for i in range(NSETS):
-        b = synth.make_train_batch(1000 + 17 * rank + i, 1, ROWS_PER_GPU, hw=HW, length=LENGTH)
+        b = make_batch(1000 + 17 * rank + i, ROWS_PER_GPU)
         obs, prev, masks, actions, weights = b
         flat = dict(obs, prev_actions=prev, masks=masks, actions=actions, weights=weights)
         host_sets.append({k: v.pin_memory() for k, v in flat.items()})
@@ -286,7 +324,7 @@ def main():
     static_next = {k: torch.empty_like(dev_sets[0][k]) for k in ("rgb", "depth")}
 
     def split(d):
-        obs = {k: d[k] for k in ("instruction", "rgb", "depth", "progress") if k in d}
+        obs = {k: d[k] for k in (instr_key(), "rgb", "depth", "progress") if k in d}
         return obs, d["prev_actions"], d["masks"], d["actions"], d["weights"]
 
     VIS = ("rgb", "depth")
@@ -326,7 +364,7 @@ def main():
         step.compute_grads(obs0, prev0, masks0, actions0, weights0)
         eng = pol.net.engine()
         torch.cuda.synchronize()
-        snapshot = {"logp": eng.buf("logits", (ROWS_PER_GPU, 4)).detach().cpu().clone(),
+        snapshot = {"logp": eng.buf("logits", (ROWS_PER_GPU, ACTIONS)).detach().cpu().clone(),
                     "losses": step._losses.tolist(),
                     "grads": {k: v.detach().cpu().clone() for k, v in step.fp.grad_views.items()}}
 
@@ -342,6 +380,7 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = int(lib.C.vlnce_launch_count() - c0)
     graph = None
+    graph_has_allreduce = False
     losses = step._losses
     if args.ncu_step:
         from vlnce_b200 import engine as engine_mod
@@ -359,28 +398,45 @@ def main():
         return
     if not args.no_graph:
         try:
-            # N = 1: the whole step is one graph.  N > 1: forward+loss+backward is captured, the NCCL
-            # all-reduce and the Adam launch stay eager between replays (no collectives inside graphs).
-            body = eager_step if world == 1 else grads_only
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                body(static)
-                side.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=side):
+            # The whole pipelined step is ONE graph, the NCCL gradient all-reduce included (world > 1): inside the graph
+            # the all-reduce + Adam of batch i sit on the head branch and overlap the frozen trunks of batch i+1 on the
+            # forked branch instead of trailing every replay.  If this NCCL build refuses capture, fall back to
+            # forward+loss+backward in the graph and all-reduce + Adam launched eagerly after each replay.
+            def capture(body):
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
                     body(static)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
+                    side.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        body(static)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                return g
+
+            graph_has_allreduce = True
+            if world > 1 and args.eager_allreduce:
+                raise RuntimeError("eager all-reduce requested")
+            graph = capture(eager_step)
         except Exception as e:  # graph capture is an optimisation, not a requirement
-            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
             graph = None
             torch.cuda.synchronize()
+            if world > 1:
+                try:
+                    graph_has_allreduce = False
+                    graph = capture(grads_only)
+                except Exception as e2:
+                    print(f"[bench] CUDA-graph capture failed ({type(e2).__name__}: {e2}); running eagerly", file=sys.stderr)
+                    graph = None
+                    torch.cuda.synchronize()
+            else:
+                print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
 
     def run_step():
         if graph is not None:
             graph.replay()
-            if world > 1:
+            if world > 1 and not graph_has_allreduce:
                 step.apply_grads(True)
         else:
             eager_step(static)
@@ -594,7 +650,8 @@ def main():
                        "parallelism": f"dp{world}", "precision": "rgb trunk bf16 / depth trunk fp16 tcgen05, head fp32"
                        if args.precision == "bf16" else "fp32 CUDA cores",
                        "l2": f"inputs rotated over {NSETS} distinct batches ({NSETS * h2d_bytes / 1e6:.0f} MB > L2)",
-                       "cuda_graph": graph is not None, "pdl": bool(lib.C.vlnce_get_pdl()),
+                       "cuda_graph": graph is not None, "allreduce_in_graph": bool(graph is not None and graph_has_allreduce and world > 1),
+                       "pdl": bool(lib.C.vlnce_get_pdl()),
                        "schedule": "pipelined loop: frozen trunks of batch i+1 overlap head fwd/bwd/Adam of batch i "
                                    "(every timed step = one trunk pass + one head update; fill done in warm-up)"},
             "e2e": {"value": e2e_value, "unit": "policy steps/s", "h2d_bytes_per_step": h2d_bytes,

@@ -178,6 +178,7 @@ class WDDPPOStep(torch.nn.Module):
             self.world = torch.distributed.get_world_size(process_group)
         self.fp: Optional[FlatParams] = None
         self.step_id = 0
+        self._graphs = None
 
     @property
     def lr(self):
@@ -251,6 +252,54 @@ class WDDPPOStep(torch.nn.Module):
         C.vlnce_adam_step(ptr(fp.flat), ptr(fp.grad), ptr(fp.exp_avg), ptr(fp.exp_avg_sq), fp.total, float(self.lr),
                           float(self.betas[0]), float(self.betas[1]), float(self.eps), 0, ptr(self._step_dev), 1.0, st)
 
+    # ---- CUDA-graph replay of a mini-batch (the eager step is ~490 launches at ~13 us of host time each) ----------
+    use_cuda_graph = True     # instance / class switch; VLNCE_PPO_GRAPH=0 in the environment turns it off
+
+    @staticmethod
+    def _tensors(sample):
+        out = []
+        for part in sample:
+            if isinstance(part, dict):
+                out.extend(part[k] for k in sorted(part))
+            else:
+                out.append(part)
+        return out
+
+    def _update_minibatch_graphed(self, sample):
+        """Replays a captured ``update_minibatch`` (forward, fused loss, backward, [NCCL all-reduce], clip, Adam) on
+        static copies of the sample; one graph per sample signature, built on first use after an eager pass without
+        the optimiser step (plans, tile selection and workspace allocation happen there)."""
+        tensors = self._tensors(sample)
+        key = tuple((tuple(t.shape), t.dtype) for t in tensors)
+        if self._graphs is None:
+            self._graphs = {}
+        entry = self._graphs.get(key)
+        hyper = (float(self.lr), float(self.clip_param))   # launch arguments baked into the captured kernels
+        if entry is None or entry[2] != hyper:
+            if entry is None:
+                static = tuple({k: v.clone() for k, v in part.items()} if isinstance(part, dict) else part.clone()
+                               for part in sample)
+                self.update_minibatch(static, apply=False)
+                torch.cuda.synchronize()
+            else:   # lr schedule / clip decay moved on: re-record with the same static buffers (no eager pass needed)
+                static = entry[0]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    self.update_minibatch(static, apply=True)
+            torch.cuda.current_stream().wait_stream(side)
+            self.step_id -= 1          # the captured call was recorded, not run
+            entry = (static, graph, hyper)
+            self._graphs[key] = entry
+        static, graph = entry[0], entry[1]
+        for dst, src in zip(self._tensors(static), tensors):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        self.step_id += 1
+        return self._losses
+
     @lib.guarded
     def update(self, rollouts):
         """``WDDPPO.update``: returns (value_loss, action_loss, entropy_loss, pano_entropy, offset_entropy,
@@ -259,9 +308,26 @@ class WDDPPOStep(torch.nn.Module):
         advantages = self.get_advantages(rollouts)
         self._prepare()
         acc = torch.zeros_like(self._losses)
+        import os
+
+        graphed = (self.use_cuda_graph and os.environ.get("VLNCE_PPO_GRAPH", "1") != "0" and self._losses.is_cuda
+                   and not torch.cuda.is_current_stream_capturing())
         for _ in range(self.ppo_epoch):
             for sample in rollouts.recurrent_generator(advantages, self.num_mini_batch):
-                self.update_minibatch(sample)
+                if graphed:
+                    try:
+                        self._update_minibatch_graphed(sample)
+                    except Exception as e:  # capture is an optimisation: fall back to eager launches for good
+                        import warnings
+
+                        warnings.warn(f"WDDPPOStep: CUDA-graph capture of the mini-batch failed ({type(e).__name__}: {e}); "
+                                      "running eagerly")
+                        torch.cuda.synchronize()
+                        graphed = self.use_cuda_graph = False
+                        self._graphs = None
+                        self.update_minibatch(sample)
+                else:
+                    self.update_minibatch(sample)
                 C.vlnce_axpy(ptr(acc), ptr(self._losses), 1.0, 8, lib.stream())
         n = self.ppo_epoch * self.num_mini_batch
         v = (acc / n).tolist()

@@ -82,13 +82,35 @@ DEPTH_FUSED_CTAS = int(_os.environ.get("VLNCE_DEPTH_FUSED_CTAS", "0"))  # persis
 # processes on the same box (profilers, the second bench leg) skip the timing sweep.
 _TUNE_CACHE_PATH = _os.environ.get("VLNCE_AUTOTUNE_CACHE", "")
 _TUNE_CACHE = {}
+# Committed tile-selection table for the B200 (kernel variant | tile width | ring depth per conv geometry, measured
+# by the sweep below on this pool's B200s: tools/make_tile_table.py): the autotuner only runs on a MISS, so first use
+# of the shipped geometries costs no timing launches and every process picks the same tiles.  VLNCE_TILE_TABLE=0
+# ignores it (re-measure everything).
+_TILE_TABLE_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "tile_table_b200.json")
+if _os.environ.get("VLNCE_TILE_TABLE", "1") != "0" and _os.path.exists(_TILE_TABLE_PATH):
+    try:
+        import json as _json
+
+        _TUNE_CACHE.update(_json.load(open(_TILE_TABLE_PATH)))
+    except Exception:
+        pass
 if _TUNE_CACHE_PATH and _os.path.exists(_TUNE_CACHE_PATH):
     try:
         import json as _json
 
-        _TUNE_CACHE = _json.load(open(_TUNE_CACHE_PATH))
+        _TUNE_CACHE.update(_json.load(open(_TUNE_CACHE_PATH)))
     except Exception:
-        _TUNE_CACHE = {}
+        pass
+
+
+def _batch_bucket(n: int) -> int:
+    """Tile selection is keyed by the batch size rounded down to a power of two and capped at 64: above that every
+    layer already fills the 148 SMs and the best tile no longer depends on the image count (a training loop with a
+    varying number of rows - RecollectTrainer's padded T x N - must not re-tune per batch)."""
+    b = 1
+    while b * 2 <= min(int(n), 64):
+        b *= 2
+    return b
 
 
 def _tune_cache_put(key: str, val: int):
@@ -320,7 +342,14 @@ class ConvTrunk:
                            or (geom[5] == 3 and geom[8] == 1 and geom[1] % 16 == 0 and geom[2] % 8 == 0)))
             halo_ok = (HALO_3X3 and not stem_rgb and gemm_c is None and cv.R == 3 and cv.S == 3 and cv.stride == 1
                        and cv.pad == 1 and c % 64 == 0 and cv.K % 64 == 0 and h % 16 == 0 and w % 8 == 0)
-            key = (geom, lib.code(y), residual is not None)
+            nb = _batch_bucket(n)
+            if stem_s2d or stem_rgb:
+                gkey = (geom[0], nb) + tuple(geom[2:])
+            elif gemm_c is not None:
+                gkey = ("gemm", nb, h, w) + tuple(geom[3:])
+            else:
+                gkey = (nb,) + tuple(geom[1:])
+            key = (gkey, lib.code(y), residual is not None)
             bn = cv.block_n.get(key)
             if bn is None:
                 skey = repr((key, lib.code(cv.w), scale is not None, relu, halo_ok, tma_ok, self.exclusive))
