@@ -19,7 +19,9 @@ def main():
     code = eval(sys.argv[2]) if len(sys.argv) > 2 else (128 | (4 << 16) | NOSTAT)
     dev = "cuda"
     n = 64
-    geo = {"l3c1": (16, 1024, 256, 1), "l2c2": (32, 128, 128, 3), "l1c1": (64, 256, 64, 1)}
+    geo = {"l3c1": (16, 1024, 256, 1), "l2c2": (32, 128, 128, 3), "l1c1": (64, 256, 64, 1), "l1c2": (64, 64, 64, 3),
+           "l1c3": (64, 64, 256, 1, True), "l2c3": (32, 128, 512, 1, True), "l3c3": (16, 256, 1024, 1, True),
+           "l3c2": (16, 256, 256, 3), "l4c3": (8, 512, 2048, 1, True)}
     trace = torch.zeros(4 * 768 * 2, dtype=torch.int64, device=dev)
     if layer == "stem":
         img = torch.randint(0, 256, (n, 256, 256, 3), device=dev, dtype=torch.uint8)
@@ -33,14 +35,15 @@ def main():
             C.vlnce_conv_stem_tma(ptr(cells), ptr(w), lib.BF16, ptr(scale), ptr(shift), ptr(y), lib.BF16, n, 128, 128,
                                   64, 1, code, lib.stream())
     else:
-        hw, cin, cout, r = geo[layer]
+        hw, cin, cout, r = geo[layer][:4]
+        res = torch.randn(n, hw, hw, cout, device=dev).bfloat16() if len(geo[layer]) > 4 else None
         x = torch.randn(n, hw, hw, cin, device=dev).bfloat16()
         w = (torch.randn(cout, r, r, cin, device=dev) * 0.05).bfloat16()
         scale, shift = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
         y = torch.empty(n, hw, hw, cout, device=dev, dtype=torch.bfloat16)
 
         def launch():
-            C.vlnce_conv_tma(ptr(x), ptr(w), lib.BF16, ptr(scale), ptr(shift), None, ptr(y), lib.BF16, n, hw, hw, cin,
+            C.vlnce_conv_tma(ptr(x), ptr(w), lib.BF16, ptr(scale), ptr(shift), ptr(res), ptr(y), lib.BF16, n, hw, hw, cin,
                              cout, r, 1, code, lib.stream())
     for _ in range(5):
         launch()
