@@ -93,7 +93,7 @@ int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scal
  *   vlnce_conv_stem_tma y (N,P,Q,K) = act(scale * (xs (*) w) + shift), w (K,256) = [k][r'][s'][16] with
  *                       w[k][r'][s'][(dy*2+dx)*3+c] = conv1.weight[k][c][2r'+dy][2s'+dx] (0 where the index
  *                       is 7 or the channel is padding).  K % 64 == 0; block_n as vlnce_conv_tma. */
-/* Debug aid of the persistent conv tiles: a device buffer of 4*768*2 int64 that CTA 0 of every later
+/* Debug aid of the persistent conv tiles: a device buffer of 5*768*2 int64 that CTA 0 of every later
  * vlnce_conv_tma / vlnce_conv_stem_tma launch fills with per-role (event, clock64) records; NULL = off. */
 /* cap on the persistent conv_tma grid (0 = one CTA per SM; default: environment VLNCE_TMA_CTA_CAP) */
 int vlnce_set_tma_cta_cap(int cap);
@@ -208,13 +208,23 @@ int vlnce_resize_area_crop(const void* x, void* y, int dtype, long long y_frame_
 /* ---- trainable head: dense algebra --------------------------------------------------- */
 /* C[m,n] = act(sum_k A[m*lda_m + k*lda_k] * B[k*ldb_k + n*ldb_n] + bias[n] + beta*C[m,n]),
  * fp32 on CUDA cores; act 0 none / 1 ReLU / 2 tanh.  One routine for every Linear / Conv1d(k=1) of
- * workspace (optional, caller-owned) enables a deterministic split-K for skinny problems.
  * the head forward and backward (cma_policy.py:101-184: rgb_linear, depth_linear, state_q,
  * text_k, text_q, rgb_kv, depth_kv, second_state_compress, progress_monitor; policy.py:19-21
- * CategoricalNet; GRU / LSTM input and hidden projections). */
+ * CategoricalNet; GRU / LSTM input and hidden projections).
+ * workspace (optional, caller-owned, one per stream) enables a deterministic split-K for skinny problems, reduced
+ * inside the same launch by the last CTA to reach a tile.  Its first 16 KB are arrival counters: they must be
+ * ZERO before the first call and are left zero by every call. */
 int vlnce_sgemm(const float* A, long long lda_m, long long lda_k, const float* B, long long ldb_k,
                 long long ldb_n, float* C, long long ldc, const float* bias, int M, int N, int K,
                 float beta, int act, float* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* `count` INDEPENDENT problems of the form above in one launch (no problem may read or accumulate into another's
+ * output).  descs: count x 16 64-bit words per problem, in this order:
+ *   { A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta (IEEE-754 double), act, 0, 0 }
+ * (pointers as 64-bit addresses).  B == 0 means B == 1 everywhere, i.e. C[m,0..N) = sum_k A[m,k]: with lda_m = 1,
+ * lda_k = ld, N = 1 that is the column sum of a row-major matrix — the bias gradients ride in the same launch as
+ * the weight gradients.  More than 24 problems are issued as consecutive launches of up to 24. */
+int vlnce_sgemm_grouped(const long long* descs, int count, float* workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
 /* out[n] (+)= sum_m A[m*lda + n]  — bias gradients */
 int vlnce_colsum(const float* A, long long lda, float* out, int M, int N, int accumulate,
                  float* workspace, size_t workspace_bytes, cudaStream_t stream);

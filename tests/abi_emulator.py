@@ -77,6 +77,24 @@ class Emulator:
             y = np.tanh(y)
         c[...] = y.astype(F32)
 
+    def sgemm_grouped(self, descs, count, ws, wsb, st):
+        import ctypes
+        import struct
+
+        raw = ctypes.string_at(descs, count * 128)
+        for i in range(count):
+            (A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta, act, _, _) = struct.unpack_from(
+                "<12qdq2q", raw, i * 128)
+            if B == 0:  # column sums of A over k
+                a = _mat(A, M, K, lda_m, lda_k).astype(np.float64)
+                c = _mat(C, M, N, ldc)
+                y = np.repeat(a.sum(1, keepdims=True), N, axis=1)
+                if beta != 0.0:
+                    y = y + beta * c.astype(np.float64)
+                c[...] = y.astype(F32)
+            else:
+                self.sgemm(A, lda_m, lda_k, B, ldb_k, ldb_n, C, ldc, bias, M, N, K, beta, act, ws, wsb, st)
+
     def colsum(self, A, lda, out, M, N, accumulate, ws, wsb, st):
         s = _mat(A, M, N, lda).astype(np.float64).sum(0)
         o = _flat(out, N)

@@ -41,6 +41,49 @@ def test_sgemm_variants(m, n, k):
     torch.testing.assert_close(cs, dy.sum(0), rtol=1e-4, atol=1e-4)
 
 
+def test_sgemm_grouped_matches_torch_and_is_deterministic():
+    """One grouped launch = the same results as the problems one by one: mixed shapes (split-K and not), a fused
+    accumulate (beta = 1), activations, and bias-gradient column sums riding along; bit-identical when repeated
+    (the in-launch split-K reduction sums the partials in a fixed order whatever CTA arrives last)."""
+    from vlnce_b200.engine import colsum, gemm_group
+
+    x1, w1, b1 = _r(64, 2112), _r(256, 2112, scale=0.1), _r(256)
+    x2, w2, b2 = _r(64, 3072, seed=1), _r(128, 3072, seed=1, scale=0.1), _r(128, seed=1)
+    dy, xs = _r(5120, 512, seed=2, scale=0.1), _r(5120, 50, seed=2)
+    d3 = _r(64, 7, seed=3)
+
+    def run():
+        o1 = torch.full((64, 256 + 128), float("nan"), device=DEV)
+        dw = torch.ones(512, 50, device=DEV)
+        db = torch.full((512,), float("nan"), device=DEV)
+        db3 = torch.ones(7, device=DEV)
+        with gemm_group():
+            linear(ptr(x1), 2112, ptr(w1), ptr(o1), 384, ptr(b1), 64, 256, 2112, act=1)
+            linear(ptr(x2), 3072, ptr(w2), ptr(o1) + 4 * 256, 384, ptr(b2), 64, 128, 3072, act=2)
+            linear_dw(ptr(dy), 512, ptr(xs), 50, ptr(dw), 50, 5120, 512, 50, beta=1.0)
+            colsum(ptr(dy), 512, ptr(db), 5120, 512)
+            colsum(ptr(d3), 7, ptr(db3), 64, 7, acc=1)
+        return o1, dw, db, db3
+
+    o1, dw, db, db3 = run()
+    torch.testing.assert_close(o1[:, :256], torch.relu(x1 @ w1.t() + b1), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(o1[:, 256:], torch.tanh(x2 @ w2.t() + b2), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dw, 1 + dy.t() @ xs, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(db, dy.sum(0), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(db3, 1 + d3.sum(0), rtol=1e-4, atol=1e-4)
+    for _ in range(3):
+        again = run()
+        assert all(torch.equal(a, b) for a, b in zip(again, (o1, dw, db, db3)))
+    # more problems than one launch holds (24): issued as consecutive launches
+    outs = [torch.empty(8, 8, device=DEV) for _ in range(30)]
+    a = _r(8, 40, seed=5)
+    with gemm_group():
+        for i, o in enumerate(outs):
+            linear(ptr(a), 40, ptr(w1) + 4 * 2112 * i, ptr(o), 8, None, 8, 8, 40, ldw=2112)
+    for i, o in enumerate(outs):
+        torch.testing.assert_close(o, a @ w1[i:i + 8, :40].t(), rtol=1e-4, atol=1e-4)
+
+
 @pytest.mark.parametrize("dirs", [1, 2])
 def test_lstm_matches_packed_torch(dirs):
     R, L, E, H = 5, 11, 50, 128

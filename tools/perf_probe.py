@@ -94,8 +94,13 @@ def main():
 
     res["head_update_ms"] = graph_time(head)
     res["full_step_ms"] = graph_time(lambda: step.update_agent(obs, prev, masks, actions, weights, return_tensor=True))
-    res["pipelined_step_ms"] = graph_time(
-        lambda: step.pipelined_step(obs_nv, prev, masks, actions, weights, {k: obs[k] for k in ("rgb", "depth")}))
+    vis_next = {k: obs[k] for k in ("rgb", "depth")}
+    res["pipelined_step_ms"] = graph_time(lambda: step.pipelined_step(obs_nv, prev, masks, actions, weights, vis_next))
+    for cap in [int(c) for c in args.caps.split(",")][1:]:   # persistent-grid cap of conv_tma: SMs left to the head
+        lib.C.vlnce_set_tma_cta_cap(cap)
+        res.setdefault("pipelined_by_cap", {})[cap] = graph_time(
+            lambda: step.pipelined_step(obs_nv, prev, masks, actions, weights, vis_next))
+    lib.C.vlnce_set_tma_cta_cap(int(args.caps.split(",")[0]))
     print(json.dumps(res))
     os.makedirs("gpurun_out", exist_ok=True)
     open("gpurun_out/phases.json", "w").write(json.dumps(res, indent=1))

@@ -11,7 +11,7 @@ from vlnce_b200.lib import C, ptr  # noqa: E402
 
 MT2, NOSTAT = 1 << 21, 1 << 22
 EV = {1: "A:want_a", 2: "A:a_free", 3: "A:a_issued", 4: "B:b_free", 5: "B:b_issued", 10: "M:acc_free", 11: "M:a_full",
-      12: "M:b_full", 13: "M:issued", 20: "E:want_acc", 21: "E:acc_full", 22: "E:staged", 23: "E:barrier", 24: "E:stored"}
+      12: "M:b_full", 13: "M:issued", 20: "E:want_acc", 21: "E:acc_full", 22: "E:staged", 23: "E:barrier", 24: "S:stored", 25: "E:stg_ready", 26: "E:tmem_ld"}
 
 
 def main():
@@ -22,7 +22,7 @@ def main():
     geo = {"l3c1": (16, 1024, 256, 1), "l2c2": (32, 128, 128, 3), "l1c1": (64, 256, 64, 1), "l1c2": (64, 64, 64, 3),
            "l1c3": (64, 64, 256, 1, True), "l2c3": (32, 128, 512, 1, True), "l3c3": (16, 256, 1024, 1, True),
            "l3c2": (16, 256, 256, 3), "l4c3": (8, 512, 2048, 1, True)}
-    trace = torch.zeros(4 * 768 * 2, dtype=torch.int64, device=dev)
+    trace = torch.zeros(5 * 768 * 2, dtype=torch.int64, device=dev)
     if layer == "stem":
         img = torch.randint(0, 256, (n, 256, 256, 3), device=dev, dtype=torch.uint8)
         cells = torch.empty(n, 131, 131, 16, device=dev, dtype=torch.bfloat16)
@@ -52,9 +52,9 @@ def main():
     launch()
     torch.cuda.synchronize()
     C.vlnce_debug_set_trace(None)
-    t = trace.cpu().view(4, 768, 2)
+    t = trace.cpu().view(5, 768, 2)
     recs = []
-    for role in range(4):
+    for role in range(5):
         for i in range(768):
             tag, clk = int(t[role, i, 0]), int(t[role, i, 1])
             if clk == 0:

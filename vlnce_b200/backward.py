@@ -11,7 +11,7 @@ from typing import Dict, Optional
 import torch
 
 from . import lib
-from .engine import F4, Branch, CMAEngine, linear, linear_dw, linear_dx, off
+from .engine import F4, Branch, CMAEngine, gemm_group, linear, linear_dw, linear_dx, off
 from .lib import C, ptr
 
 
@@ -24,26 +24,59 @@ def trainable_named(net, head_linear=None) -> Dict[str, torch.nn.Parameter]:
 
 
 def _colsum(a, lda, out, m, n, acc=0):
-    from .engine import gemm_workspace
+    from .engine import colsum
 
-    ws = gemm_workspace()
-    C.vlnce_colsum(a, lda, out, m, n, acc, ws.data_ptr(), ws.numel(), lib.stream())
+    colsum(a, lda, out, m, n, acc)
 
 
 class _Leaves:
-    """Weight/bias gradients are leaves of the backward graph: they run on a side stream while
-    the dX chain continues on the caller's stream; ``join()`` once at the end."""
+    """Weight/bias gradients are leaves of the backward graph.  ``defer=False``: each ``with leaves():`` block runs
+    on a side stream while the dX chain continues on the caller's stream; ``join()`` once at the end.
+    ``defer=True``: the blocks only QUEUE their GEMMs / column sums and ``join()`` issues all of them as one grouped
+    launch (``vlnce_sgemm_grouped``) — their operands (saved activations and finished dY buffers) are not written
+    again before the end of the backward, which the caller guarantees by opting in."""
 
-    def __init__(self):
+    def __init__(self, defer: bool = False):
+        from . import engine
+
         self.last = None
+        self.defer = defer and engine.GROUPING and engine.DEFER_LEAVES
+        self.pending = []
 
     def __call__(self):
+        if self.defer:
+            return _Queue(self.pending)
         self.last = Branch("dw")
         return self.last
 
     def join(self):
-        if self.last is not None:
+        if self.defer:
+            from . import engine
+
+            problems, self.pending = self.pending, []
+            engine._flush(problems)
+        elif self.last is not None:
             self.last.join()
+
+
+class _Queue:
+    """``with`` block whose GEMMs are appended to ``sink`` instead of being launched."""
+
+    def __init__(self, sink):
+        self.sink = sink
+
+    def __enter__(self):
+        from . import engine
+
+        self.outer = engine._PENDING  # (an open gemm_group keeps collecting after this block)
+        engine._PENDING = self.sink
+        return self
+
+    def __exit__(self, *exc):
+        from . import engine
+
+        engine._PENDING = self.outer
+        return False
 
 
 def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, masks_f, T, N, dx, lddx, leaves):
@@ -61,8 +94,8 @@ def _gru_backward(eng: CMAEngine, tag, rnn, pfx, g, dh, lddh, x, ldx, in_size, m
     for t in range(T - 1, -1, -1):
         C.vlnce_gru_pointwise_bwd(dh + F4 * t * N * lddh, lddh, off(save, t * N * 4 * H), off(hm_all, t * N * H),
                                   off(d_gi, t * N * 3 * H), off(d_gh, t * N * 3 * H), ptr(dhm), N, H, st)
-        linear_dx(off(d_gh, t * N * 3 * H), 3 * H, ptr(rnn.weight_hh_l0), ptr(dhm), H, N, 3 * H, H, beta=1.0)
-        if t > 0:
+        if t > 0:  # (the gradient w.r.t. the initial hidden state has no consumer: rnn_states are inputs)
+            linear_dx(off(d_gh, t * N * 3 * H), 3 * H, ptr(rnn.weight_hh_l0), ptr(dhm), H, N, 3 * H, H, beta=1.0)
             C.vlnce_mask_rows_add(ptr(dhm), H, off(masks_f, t * N), dh + F4 * (t - 1) * N * lddh, lddh, N, H, st)
     with leaves():
         linear_dw(ptr(d_gh), 3 * H, ptr(hm_all), H, ptr(g[pfx + "weight_hh_l0"]), H, R, 3 * H, H)
@@ -126,16 +159,18 @@ def instruction_backward(eng, g: Dict[str, torch.Tensor], d_instr: torch.Tensor)
     emb_in = b("instr_emb", (R * L, E)) if ie.config.sensor_uuid == "instruction" else cx["rxr"]
     emb_trainable = ie.config.sensor_uuid == "instruction" and ie.embedding_layer.weight.requires_grad
     d_emb = b("d_instr_emb", (R * L, E)) if emb_trainable else None
-    for d, sfx in enumerate(["", "_reverse"][:dirs]):
-        dg, dh_ = off(dgx, d * R * L * G), off(dgh, d * R * L * G)
-        pfx = "net.instruction_encoder.encoder_rnn."
-        linear_dw(dg, G, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, G, E)
-        linear_dw(dh_, G, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, G, Hs)
-        _colsum(dg, G, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, G)
-        _colsum(dh_, G, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, G)
+    pfx = "net.instruction_encoder.encoder_rnn."
+    with gemm_group():  # every problem of this block is independent of the others: one launch
+        for d, sfx in enumerate(["", "_reverse"][:dirs]):
+            dg, dh_ = off(dgx, d * R * L * G), off(dgh, d * R * L * G)
+            linear_dw(dg, G, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, G, E)
+            linear_dw(dh_, G, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, G, Hs)
+            _colsum(dg, G, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, G)
+            _colsum(dh_, G, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, G)
         if emb_trainable:
-            w_ih = getattr(rnn, "weight_ih_l0" + sfx)
-            linear_dx(dg, G, ptr(w_ih), ptr(d_emb), E, R * L, G, E, beta=0.0 if d == 0 else 1.0)
+            linear_dx(ptr(dgx), G, ptr(rnn.weight_ih_l0), ptr(d_emb), E, R * L, G, E)
+    if emb_trainable and dirs == 2:  # accumulates into the forward direction's d_emb: after the group
+        linear_dx(off(dgx, R * L * G), G, ptr(rnn.weight_ih_l0_reverse), ptr(d_emb), E, R * L, G, E, beta=1.0)
     if emb_trainable:
         el = ie.embedding_layer
         pad = -1 if el.padding_idx is None else el.padding_idx
@@ -186,7 +221,7 @@ def seq2seq_backward(eng, head_linear, g: Dict[str, torch.Tensor], d_raw: Option
     st = lib.stream()
     masks_f = b("masks_f", (R,))
     xin = b("s2s_in", (R, width))
-    leaves = _Leaves()
+    leaves = _Leaves(defer=True)  # operands of every leaf stay untouched until the end of this backward
     dx_out = head_and_progress_backward(eng, head_linear, g, d_raw, d_x, d_hat, leaves)
     d_xin = b("d_s2s_in", (R, width))
     _gru_backward(eng, "gru", net.state_encoder.rnn, "net.state_encoder.rnn.", g, ptr(dx_out), H, ptr(xin), width,
@@ -253,7 +288,9 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     x_out, x2, xcat, state_in = b("x_out", (R, H)), b("x2", (R, H)), b("xcat", (R, eng.cat)), b("state_in", (R, eng.state_in))
     masks_f = b("masks_f", (R,))
     dx_out = b("d_x_out", (R, H))
-    leaves = _Leaves()
+    # the weight / bias gradients are leaves whose operands stay untouched until the end of this backward (saved
+    # forward buffers and finished dY buffers, each with its own name): all of them go out as ONE grouped launch
+    leaves = _Leaves(defer=True)
 
     # 1. action head / feature gradient
     if head_linear is not None:
@@ -291,27 +328,31 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     text_q = b("text_q", (R, hk))
     d_text_q = b("d_text_q", (R, hk))
     dE = {}
-    first = True
-    for name, Cc, kv, v_out, col in (("rgb", eng.Crgb, net.rgb_kv, eng.rgb_out, H + eng.Dt),
-                                     ("depth", eng.Cdep, net.depth_kv, eng.depth_out, H + eng.Dt + eng.rgb_out)):
-        E_ = cx["rgb_e"] if name == "rgb" else cx["dep_e"]
-        pooled, qv, probs = b("pooled_" + name, (R, Cc)), b("q_" + name, (R, Cc)), b("p_" + name, (R, P))
+    vis = (("rgb", eng.Crgb, net.rgb_kv, eng.rgb_out, H + eng.Dt),
+           ("depth", eng.Cdep, net.depth_kv, eng.depth_out, H + eng.Dt + eng.rgb_out))
+    for name, Cc, kv, v_out, col in vis:
         gw, gb = g[f"net.{name}_kv.weight"], g[f"net.{name}_kv.bias"]
-        d_att = off(dxcat, col)
         with leaves():
-            linear_dw(d_att, eng.cat, ptr(pooled), Cc, off(gw, hk * Cc), Cc, R, v_out, Cc)  # dW_v
-            _colsum(d_att, eng.cat, off(gb, hk), R, v_out)
-        d_pooled = b("d_pooled_" + name, (R, Cc))
-        linear_dx(d_att, eng.cat, off(kv.weight, hk * Cc), ptr(d_pooled), Cc, R, v_out, Cc)
+            linear_dw(off(dxcat, col), eng.cat, ptr(b("pooled_" + name, (R, Cc))), Cc, off(gw, hk * Cc), Cc, R, v_out,
+                      Cc)  # dW_v
+            _colsum(off(dxcat, col), eng.cat, off(gb, hk), R, v_out)
+    with gemm_group():  # gradients w.r.t. the two pooled embeddings: independent, one launch
+        for name, Cc, kv, v_out, col in vis:
+            linear_dx(off(dxcat, col), eng.cat, off(kv.weight, hk * Cc), ptr(b("d_pooled_" + name, (R, Cc))), Cc, R,
+                      v_out, Cc)
+    for name, Cc, kv, v_out, col in vis:
+        E_ = cx["rgb_e"] if name == "rgb" else cx["dep_e"]
+        qv, probs = b("q_" + name, (R, Cc)), b("p_" + name, (R, P))
         dq = b("d_q_" + name, (R, Cc))
         dEn = b("d_emb_" + name, (R, P, Cc))
-        C.vlnce_attn_pool_bwd(ptr(qv), Cc, ptr(E_), P * Cc, Cc, ptr(probs), eng.scale, ptr(d_pooled), Cc, ptr(dq),
-                              Cc, ptr(dEn), P * Cc, Cc, 0, R, P, Cc, st)
+        C.vlnce_attn_pool_bwd(ptr(qv), Cc, ptr(E_), P * Cc, Cc, ptr(probs), eng.scale, ptr(b("d_pooled_" + name, (R, Cc))),
+                              Cc, ptr(dq), Cc, ptr(dEn), P * Cc, Cc, 0, R, P, Cc, st)
         dE[name] = dEn
         with leaves():
-            linear_dw(ptr(text_q), hk, ptr(dq), Cc, ptr(gw), Cc, R, hk, Cc)  # dW_k = text_q^T dq'
-        linear(ptr(dq), Cc, ptr(kv.weight), ptr(d_text_q), hk, None, R, hk, Cc, beta=0.0 if first else 1.0)
-        first = False
+            linear_dw(ptr(text_q), hk, ptr(dq), Cc, ptr(g[f"net.{name}_kv.weight"]), Cc, R, hk, Cc)  # dW_k = text_q^T dq'
+    for i, (name, Cc, kv, v_out, col) in enumerate(vis):  # both accumulate into d_text_q: in order
+        linear(ptr(b("d_q_" + name, (R, Cc))), Cc, ptr(kv.weight), ptr(d_text_q), hk, None, R, hk, Cc,
+               beta=0.0 if i == 0 else 1.0)
     # 6. text_q = Linear(text_embedding)
     with leaves():
         linear_dw(ptr(d_text_q), hk, off(xcat, H), eng.cat, ptr(g["net.text_q.weight"]), eng.Dt, R, hk, eng.Dt)
@@ -348,21 +389,24 @@ def cma_backward(eng: CMAEngine, head_linear, g: Dict[str, torch.Tensor], d_raw:
     C.vlnce_relu_bwd(ptr(d_state_in), eng.state_in, ptr(state_in), eng.state_in, R, eng.rgb_out + eng.depth_out, st)
     rgb_mean = b("rgb_mean", (R, eng.Crgb))
     lin = net.rgb_linear[2]
-    linear_dw(ptr(d_state_in), eng.state_in, ptr(rgb_mean), eng.Crgb, ptr(g["net.rgb_linear.2.weight"]), eng.Crgb, R,
-              eng.rgb_out, eng.Crgb)
-    _colsum(ptr(d_state_in), eng.state_in, ptr(g["net.rgb_linear.2.bias"]), R, eng.rgb_out)
+    with leaves():
+        linear_dw(ptr(d_state_in), eng.state_in, ptr(rgb_mean), eng.Crgb, ptr(g["net.rgb_linear.2.weight"]), eng.Crgb,
+                  R, eng.rgb_out, eng.Crgb)
+        _colsum(ptr(d_state_in), eng.state_in, ptr(g["net.rgb_linear.2.bias"]), R, eng.rgb_out)
     d_mean_sp = b("d_mean_sp", (R, 64))
-    linear_dx(ptr(d_state_in), eng.state_in, off(lin.weight, c_rgb), ptr(d_mean_sp), 64, R, eng.rgb_out, 64,
-              ldw=eng.Crgb)
-    dep_flat = b("depth_flat", (R, eng.Cdep * P))
-    lin = net.depth_linear[1]
-    d_dep = off(d_state_in, eng.rgb_out)
-    linear_dw(d_dep, eng.state_in, ptr(dep_flat), eng.Cdep * P, ptr(g["net.depth_linear.1.weight"]), eng.Cdep * P, R,
-              eng.depth_out, eng.Cdep * P)
-    _colsum(d_dep, eng.state_in, ptr(g["net.depth_linear.1.bias"]), R, eng.depth_out)
     d_flat_sp = b("d_flat_sp", (R, 64 * P))
-    linear_dx(d_dep, eng.state_in, off(lin.weight, c_dep * P), ptr(d_flat_sp), 64 * P, R, eng.depth_out, 64 * P,
-              ldw=eng.Cdep * P)
+    dep_flat = b("depth_flat", (R, eng.Cdep * P))
+    lin_d = net.depth_linear[1]
+    d_dep = off(d_state_in, eng.rgb_out)
+    with leaves():
+        linear_dw(d_dep, eng.state_in, ptr(dep_flat), eng.Cdep * P, ptr(g["net.depth_linear.1.weight"]), eng.Cdep * P,
+                  R, eng.depth_out, eng.Cdep * P)
+        _colsum(d_dep, eng.state_in, ptr(g["net.depth_linear.1.bias"]), R, eng.depth_out)
+    with gemm_group():  # the two spatial-embedding input gradients are independent: one launch
+        linear_dx(ptr(d_state_in), eng.state_in, off(lin.weight, c_rgb), ptr(d_mean_sp), 64, R, eng.rgb_out, 64,
+                  ldw=eng.Crgb)
+        linear_dx(d_dep, eng.state_in, off(lin_d.weight, c_dep * P), ptr(d_flat_sp), 64 * P, R, eng.depth_out, 64 * P,
+                  ldw=eng.Cdep * P)
     # 10. prev-action embedding (two concat slices share the rows)
     pa_w = net.prev_action_embedding.weight
     C.vlnce_prev_action_embed_bwd(ptr(cx["prev"]), ptr(masks_f), off(dxcat, eng.cat - 32), eng.cat,

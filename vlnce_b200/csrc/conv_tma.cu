@@ -22,16 +22,18 @@
 // Persistent CTAs (one per SM) walk a static round-robin tile schedule.  Three roles run
 // concurrently and never wait for each other's whole tile:
 //
-//   warp 5     TMA producer: activation ring (requested one channel chunk ahead, across tile
-//              boundaries), weight ring, residual tile prefetch into the staging buffer.
-//   warp 4     MMA issuer: accumulates tile i into TMEM buffer i&1 (2 x BLOCK_N columns allocated).
-//   warps 0-3  epilogue of tile i-1 WHILE tile i is being accumulated: tcgen05.ld, scale/shift,
-//              residual, ReLU, swizzled staging (double buffered when it fits), TMA store.
+//   warp 9     activation producer (one thread): TMA ring requested across tile boundaries.
+//   warp 10    weight producer (one thread): weight ring (or the stationary slice, once).
+//   warp 11    store issuer (one thread): TMA store of every staged sub-tile; the residual of a later sub-tile is
+//              prefetched into a staging buffer as soon as its last store has been read.
+//   warp 8     MMA issuer (one thread): accumulates tile i into TMEM buffer i&1.
+//   warps 0-7  epilogue of tile i-1 WHILE tile i is being accumulated: tcgen05.ld, scale/shift, residual, ReLU,
+//              swizzled staging, then ONE mbarrier arrive (no CTA-wide barrier, no store issue on this path).
 //
-// Barrier protocol (all mbarriers, phases tracked per role): a_full/a_empty, b_full/b_empty rings;
-// acc_full[2] (MMA -> epilogue, tcgen05.commit), acc_empty[2] (epilogue -> MMA, 128 arrivals after the
-// last tcgen05.ld of the tile); res_full[s] (residual landed in staging s); stg_free[s] (the TMA
-// store that last read staging s has finished reading it).
+// Barrier protocol (all mbarriers, phases tracked per role): a_full/a_empty, b_full/b_empty rings (empty:
+// tcgen05.commit); acc_full[2] (issuer -> epilogue), acc_empty[2] (epilogue -> issuer, 256 arrivals after
+// the last tcgen05.ld of the tile); staged[s] (256 arrivals: sub-tile written to staging s); res_full[s] (residual
+// landed in staging s); stg_free[s] (the TMA store that last read staging s has finished reading it).
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -45,7 +47,8 @@ using namespace ptx;
 constexpr int TH = 16, TW = 8;
 constexpr int kEpiWarps = 8;                       // two groups of four: each TMEM lane quarter is read by 2 warps
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = kEpiThreads + 3 * 32;     // + MMA issuer, activation producer, weight producer
+constexpr int kThreads = kEpiThreads + 4 * 32;     // + MMA issuer, activation producer, weight producer, store issuer
+constexpr int kMaxStg = 4;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kMaxA = 8, kMaxB = 18;
 
@@ -91,7 +94,7 @@ __device__ __forceinline__ uint64_t desc_sbo(uint32_t smem_addr, uint32_t sbo_by
 }
 
 // Debug trace (CTA 0 only): role 0 activation producer / 1 MMA issuer / 2 epilogue thread 0 / 3 weight
-// producer; up to kTraceCap
+// producer / 4 store issuer; up to kTraceCap
 // records per role of {event << 32 | index, clock64}.
 constexpr int kTraceCap = 768;
 struct Trace {
@@ -186,8 +189,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint64_t* acc_full = b_empty + kMaxB;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* res_full = acc_empty + 2;
-  uint64_t* stg_free = res_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
+  uint64_t* stg_free = res_full + kMaxStg;
+  uint64_t* staged = stg_free + kMaxStg;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + kMaxStg);
   const uint32_t stg_bytes = 128u * BLOCK_N * (p.y_fp32 ? 4u : 2u);
   const uint32_t stage_out = smem_b0 + p.b_stages * B_BYTES + 1024;
 
@@ -201,8 +205,11 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], kEpiThreads);
+    }
+    for (int s = 0; s < kMaxStg; ++s) {
       mbar_init(&res_full[s], 1);
       mbar_init(&stg_free[s], 1);
+      mbar_init(&staged[s], kEpiThreads);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmap_x);
@@ -221,6 +228,30 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   // wait for the producer of our operands before the first global access (TMA loads / stores below)
   pdl_trigger();
   pdl_wait();
+
+  // residual of sub-tile vt -> staging buffer sb (the buffer is free: nothing has used it yet / its last store has
+  // been read); TMA store of the staged sub-tile vt out of buffer sb.  Issued by the store thread of the CTA.
+  auto issue_res = [&](int vt, int sb) {
+    const Tile ti = decode_tile(p, blockIdx.x + (vt / MT) * gridDim.x, BLOCK_N, MT, vt % MT);
+    mbar_arrive_expect_tx(&res_full[sb], 128 * BLOCK_N * 2);
+    for (int b = 0; b < BLOCK_N / 64; ++b) {
+      const uint32_t dst = stage_out + sb * stg_bytes + (uint32_t)b * (128 * 128);
+      if (p.mode == 0) tma_load_2d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.m0);
+      else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.x0, ti.y0, ti.img);
+    }
+  };
+  auto store_subtile = [&](int vt, int sb) {
+    const Tile ti = decode_tile(p, blockIdx.x + (vt / MT) * gridDim.x, BLOCK_N, MT, vt % MT);
+    const uint32_t stg = stage_out + sb * stg_bytes;
+    const int boxes = p.y_fp32 ? BLOCK_N / 32 : BLOCK_N / 64;
+    const int cols = p.y_fp32 ? 32 : 64;
+    for (int b = 0; b < boxes; ++b) {
+      const uint32_t src = stg + (uint32_t)b * (128 * 128);
+      if (p.mode == 0) tma_store_2d(&tmap_y, src, ti.n0 + b * cols, ti.m0);
+      else tma_store_4d_(&tmap_y, src, ti.n0 + b * cols, ti.x0, ti.y0, ti.img);
+    }
+    tma_store_commit();
+  };
 
   if (warp == kEpiWarps + 1) {
     // ------------------------------------------------------------ activation producer (one thread)
@@ -251,34 +282,58 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     __syncwarp();
   } else if (warp == kEpiWarps + 2) {
-    // ------------------------------------------------------------ weight producer (one thread)
-    if (lane == 0) {
-      int bs = 0;
-      uint32_t bph = 0;
-      Trace tr(p.trace, 3);
-      const int tiles_b = p.b_stationary ? (my_tiles > 0 ? 1 : 0) : my_tiles;  // stationary: loaded once
-      for (int it = 0; it < tiles_b; ++it) {
-        int n_tile;
-        fast_divmod(blockIdx.x + it * gridDim.x, p.n_tiles, p.rcp_n_tiles, n_tile);
-        const int n0 = n_tile * BLOCK_N;
-        for (int cc = 0; cc < p.c_chunks; ++cc) {
-          int col = cc * 64;
-          for (int tap = 0; tap < p.taps; ++tap, col += p.w_cols) {
-            mbar_wait(&b_empty[bs], bph ^ 1, 22);
-            tr.rec(4, it * p.c_chunks + cc);
-            mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
-            tma_load_2d(smem_b0 + bs * B_BYTES, &tmap_w, &b_full[bs], col, n0);
-            tr.rec(5, it * p.c_chunks + cc);
-            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+    {
+      // ---------------------------------------------------------- weight producer (one thread)
+      if (lane == 0) {
+        int bs = 0;
+        uint32_t bph = 0;
+        Trace tr(p.trace, 3);
+        const int tiles_b = p.b_stationary ? (my_tiles > 0 ? 1 : 0) : my_tiles;  // stationary: loaded once
+        for (int it = 0; it < tiles_b; ++it) {
+          int n_tile;
+          fast_divmod(blockIdx.x + it * gridDim.x, p.n_tiles, p.rcp_n_tiles, n_tile);
+          const int n0 = n_tile * BLOCK_N;
+          for (int cc = 0; cc < p.c_chunks; ++cc) {
+            int col = cc * 64;
+            for (int tap = 0; tap < p.taps; ++tap, col += p.w_cols) {
+              mbar_wait(&b_empty[bs], bph ^ 1, 22);
+              tr.rec(4, it * p.c_chunks + cc);
+              mbar_arrive_expect_tx(&b_full[bs], B_BYTES);
+              tma_load_2d(smem_b0 + bs * B_BYTES, &tmap_w, &b_full[bs], col, n0);
+              tr.rec(5, it * p.c_chunks + cc);
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+            }
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp == kEpiWarps) {
-    // ------------------------------------------------------------ MMA issuer (one thread: no per-step
-    // warp reconvergence; this thread's instruction latency bounds the pipeline period)
-    if (lane == 0) {
+  } else if (warp == kEpiWarps || warp == kEpiWarps + 3) {
+    if (warp == kEpiWarps + 3) {
+      // ---------------------------------------------------------- store issuer (one thread): TMA store of each staged
+      // sub-tile; the staging buffer is handed on (or refilled with its next residual) once the store has read it
+      if (lane == 0) {
+        Trace tr(p.trace, 4);
+        const int S = p.stg_bufs;
+        const int total_vt = my_tiles * MT;
+        int sb = 0;
+        uint32_t ph = 0;
+        if (p.has_res)
+          for (int vt = 0; vt < S && vt < total_vt; ++vt) issue_res(vt, vt);
+        for (int vt = 0; vt < total_vt; ++vt) {
+          mbar_wait(&staged[sb], ph, 30);
+          store_subtile(vt, sb);
+          tma_store_wait_read_n<0>();   // the store has left its staging buffer: hand the buffer on at once
+          if (!p.has_res) mbar_arrive(&stg_free[sb]);
+          else if (vt + S < total_vt) issue_res(vt + S, sb);
+          tr.rec(24, vt);
+          if (++sb == S) { sb = 0; ph ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
+      // ---------------------------------------------------------- MMA issuer (one thread: no per-step warp
+      // reconvergence).  Two issuing threads (one per sub-tile) were measured and bought nothing: the tensor pipe,
+      // not the issue rate, paces these tiles (tools/micro/mma_issue.cu).
       const uint32_t idesc = make_idesc_f16(128, BLOCK_N, p.ab_half ? 0u : 1u);
       const uint32_t sbo = (uint32_t)p.halo_w * 128u;
       // descriptor constants: only the 14-bit start-address field changes between MMAs
@@ -354,23 +409,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     // warp w reads TMEM lanes 32*(w&3).. (its hardware-accessible quarter) and the column half w>>2.
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
-    const int total_vt = my_tiles * MT;
     Trace tr(threadIdx.x == 0 ? p.trace : nullptr, 2);
-    // thread 0 also owns the residual prefetch: a staging buffer is refilled with the residual of its
-    // next sub-tile as soon as the TMA store that last read it has drained (no producer round trip)
-    auto issue_res = [&](int vt) {
-      const int it2 = vt / MT, h2 = vt % MT;
-      const int sb = vt % p.stg_bufs;
-      const Tile ti = decode_tile(p, blockIdx.x + it2 * gridDim.x, BLOCK_N, MT, h2);
-      mbar_arrive_expect_tx(&res_full[sb], 128 * BLOCK_N * 2);
-      for (int b = 0; b < BLOCK_N / 64; ++b) {
-        const uint32_t dst = stage_out + sb * stg_bytes + (uint32_t)b * (128 * 128);
-        if (p.mode == 0) tma_load_2d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.m0);
-        else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.x0, ti.y0, ti.img);
-      }
-    };
-    if (threadIdx.x == 0 && p.has_res)
-      for (int vt = 0; vt < p.stg_bufs && vt < total_vt; ++vt) issue_res(vt);
+    int sb = 0;            // staging buffer of the next sub-tile
+    uint32_t sph = 0;      // parity of this buffer's use count
     for (int it = 0; it < my_tiles; ++it) {
       const int buf = it & 1;
       const uint32_t u = (uint32_t)(it >> 1);
@@ -385,11 +426,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll 1
       for (int h = 0; h < MT; ++h) {
         const int vt = it * MT + h;   // sub-tiles are the unit of staging / residual / store
-        const int sb = vt % p.stg_bufs;
-        const uint32_t v = (uint32_t)(vt / p.stg_bufs);
         const uint32_t stg = stage_out + sb * stg_bytes;
-        if (p.has_res) mbar_wait(&res_full[sb], v & 1, 28);   // residual landed (implies staging free)
-        else mbar_wait(&stg_free[sb], (v & 1) ^ 1, 29);       // previous store has left the staging buffer
+        if (p.has_res) mbar_wait(&res_full[sb], sph, 28);     // residual landed (implies staging free)
+        else mbar_wait(&stg_free[sb], sph ^ 1, 29);           // previous store has left the staging buffer
+        tr.rec(25, vt);
         const uint32_t t_row = tmem_base + (buf * MT + h) * BLOCK_N + ((uint32_t)(q * 32) << 16);
         uint32_t vv[2][32];
         tmem_ld_32x32(t_row + (half * NI) * 32, vv[0]);
@@ -406,6 +446,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             }
           }
           tmem_ld_wait();
+          tr.rec(26, vt * 8 + i);
           if (i + 1 < NI) tmem_ld_32x32(t_row + (cb + 1) * 32, vv[(i + 1) & 1]);
           float f[32];
 #pragma unroll
@@ -480,37 +521,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           mbar_arrive(&acc_empty[buf]);
         }
         tr.rec(22, vt);
+        // this thread's part of the sub-tile is in the staging buffer: make it visible to the async proxy and
+        // count in — the store issuer (warp 10) sends the TMA store once all 256 threads have arrived
         fence_proxy_async_smem();
-        named_barrier_sync(1, kEpiThreads);
-        tr.rec(23, vt);
-        if (threadIdx.x == 0) {
-          const Tile ti = decode_tile(p, blockIdx.x + it * gridDim.x, BLOCK_N, MT, h);
-          const int boxes = p.y_fp32 ? BLOCK_N / 32 : BLOCK_N / 64;
-          const int cols = p.y_fp32 ? 32 : 64;
-          for (int b = 0; b < boxes; ++b) {
-            const uint32_t src = stg + (uint32_t)b * (128 * 128);
-            if (p.mode == 0) tma_store_2d(&tmap_y, src, ti.n0 + b * cols, ti.m0);
-            else tma_store_4d_(&tmap_y, src, ti.n0 + b * cols, ti.x0, ti.y0, ti.img);
-          }
-          tma_store_commit();
-          // a staging buffer is reusable once the store that read it has drained: release it to the other
-          // epilogue threads (stg_free) or refill it with its next sub-tile's residual (res_full)
-          if (p.stg_bufs == 2) {
-            tma_store_wait_read_n<1>();
-            if (vt >= 1) {
-              if (!p.has_res) mbar_arrive(&stg_free[(vt - 1) & 1]);
-              else if (vt + 1 < total_vt) issue_res(vt + 1);
-            }
-          } else {
-            tma_store_wait_read_n<0>();
-            if (!p.has_res) mbar_arrive(&stg_free[0]);
-            else if (vt + 1 < total_vt) issue_res(vt + 1);
-          }
-          tr.rec(24, vt);
-        }
+        mbar_arrive(&staged[sb]);
+        if (++sb == p.stg_bufs) { sb = 0; sph ^= 1; }
       }
     }
-    if (threadIdx.x == 0) tma_store_wait_read_n<0>();
   }
 
   tc_fence_before_sync();
@@ -612,24 +629,32 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   const int a_slot = MT * p.a_bytes;
   auto bytes = [&](int as, int bs, int sbufs) { return as * a_slot + bs * B_BYTES + 1024 + sbufs * stg + 1024; };
   int as, bs, sbufs;
+  // A third staging buffer gives the residual prefetch (and the lagging buffer release of the store issuer) a whole
+  // sub-tile of slack; it is given up before the rings drop below three stages, except under a residual.
   // (1) stationary weights: this CTA's whole weight slice (all taps x chunks) stays in shared memory
   const int b_all = p.taps * p.c_chunks;
   p.b_stationary = 0;
   if (!no_stationary && p.n_tiles == 1 && b_all <= kMaxB) {
-    as = p.mode == 1 ? 3 : 4; sbufs = 2;
+    as = p.mode == 1 ? 3 : 4; sbufs = 3;
     while (bytes(as, b_all, sbufs) > kSmemBudget) {
-      if (as > 2) --as;
+      if (as > 3) --as;
+      else if (sbufs > 2 && !p.has_res) --sbufs;
+      else if (as > 2) --as;
       else if (sbufs > 1) --sbufs;
       else break;
     }
     if (bytes(as, b_all, sbufs) <= kSmemBudget) { p.b_stationary = 1; bs = b_all; }
   }
   if (!p.b_stationary) {
-    // (2) streaming: preference order double staging, deep rings; shrink until it fits
-    as = p.mode == 1 ? 3 : 4; bs = b_stages_req > 0 ? b_stages_req : 4; sbufs = 2;
+    // (2) streaming: deep rings, then staging; shrink until it fits
+    as = p.mode == 1 ? 3 : 4; bs = b_stages_req > 0 ? b_stages_req : 4; sbufs = 3;
     if (bs > kMaxB) bs = kMaxB;
     while (bytes(as, bs, sbufs) > kSmemBudget) {
-      if (bs > 3) --bs;
+      if (bs > 4) --bs;
+      else if (as > 3) --as;
+      else if (sbufs > 2 && !p.has_res) --sbufs;
+      else if (bs > 3) --bs;
+      else if (sbufs > 2) --sbufs;
       else if (as > 2) --as;
       else if (sbufs > 1) --sbufs;
       else if (bs > 2) --bs;
@@ -650,7 +675,7 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   }
   if (ov_as > 0 && ov_as <= kMaxA) as = ov_as;
   if (ov_bs > 0 && ov_bs <= kMaxB && !p.b_stationary) bs = ov_bs;
-  if (ov_stg > 0 && ov_stg <= 2) sbufs = ov_stg;
+  if (ov_stg > 0 && ov_stg <= kMaxStg) sbufs = ov_stg;
   while (bytes(as, bs, sbufs) > kSmemBudget) {  // overrides must still fit
     if (!p.b_stationary && bs > 2) --bs;
     else if (as > 2) --as;
@@ -792,7 +817,7 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
   return dispatch(bn, mt, tx, tw, ty, tr, p, b_stages, no_stationary, stream);
 }
 
-// Debug: device buffer of 4 * 768 * 2 int64 that CTA 0 of every later conv_tma launch fills with
+// Debug: device buffer of 5 * 768 * 2 int64 that CTA 0 of every later conv_tma launch fills with
 // (event, clock64) records per role (producer / MMA issuer / epilogue); NULL switches tracing off.
 extern "C" int vlnce_debug_set_trace(void* buffer) {
   g_trace = reinterpret_cast<long long*>(buffer);

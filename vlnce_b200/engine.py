@@ -36,29 +36,88 @@ def gemm_workspace(nbytes: int = 16 << 20):
         key = (-1, 0)
     ws = _WS.get(key)
     if ws is None:
-        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda" if key[0] >= 0 else "cpu")
+        # zeroed: the first 16 KB are the split-K arrival counters of sgemm_grouped_kernel (left zero by every launch)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device="cuda" if key[0] >= 0 else "cpu")
         _WS[key] = ws
     return ws
 
 
+# ---- grouped GEMM launches: inside ``with gemm_group():`` the head's GEMMs (and bias-gradient column sums) are
+# queued and issued as ONE ``vlnce_sgemm_grouped`` launch when the outermost group closes.  Only problems that do
+# not depend on each other may share a group (the launch plans below mark those regions by hand).
+_PENDING = None  # list of problem tuples while a group is open
+# VLNCE_GEMM_GROUPS=0: every GEMM is its own launch again (A/B switch for measurements and bisection)
+GROUPING = __import__("os").environ.get("VLNCE_GEMM_GROUPS", "1") != "0"
+# VLNCE_DEFER_LEAVES=0: weight / bias gradients run on a side stream next to the dX chain (one launch each) instead of
+# being collected into one grouped launch at the end of the backward
+DEFER_LEAVES = __import__("os").environ.get("VLNCE_DEFER_LEAVES", "1") != "0"
+
+
+def _flush(problems):
+    if not problems:
+        return
+    import ctypes
+    import struct
+
+    blob = b"".join(struct.pack("<12qdq2q", a or 0, lda_m, lda_k, b or 0, ldb_k, ldb_n, c, ldc, bias or 0, m, n, k,
+                                float(beta), int(act), 0, 0)
+                    for (a, lda_m, lda_k, b, ldb_k, ldb_n, c, ldc, bias, m, n, k, beta, act) in problems)
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    ws = gemm_workspace()
+    C.vlnce_sgemm_grouped(ctypes.addressof(buf), len(problems), ws.data_ptr(), ws.numel(), lib.stream())
+
+
+class gemm_group:
+    def __enter__(self):
+        global _PENDING
+        self.outer = GROUPING and _PENDING is None
+        if self.outer:
+            _PENDING = []
+        return self
+
+    def __exit__(self, et, ev, tb):
+        global _PENDING
+        if self.outer:
+            problems, _PENDING = _PENDING, None
+            if et is None:
+                _flush(problems)
+        return False
+
+
+def colsum(a, lda, out, m, n, acc=0):
+    """out[n] (+)= sum_m a[m*lda + n] (bias gradients): a column-sum problem of the open group, else one launch."""
+    if _PENDING is not None:
+        _PENDING.append((a, 1, lda, None, 0, 0, out, 1, None, n, 1, m, 1.0 if acc else 0.0, 0))
+        return
+    ws = gemm_workspace()
+    C.vlnce_colsum(a, lda, out, m, n, acc, ws.data_ptr(), ws.numel(), lib.stream())
+
+
 class Branch:
     """Fork/join of an independent branch of the step onto a side stream (captured as parallel
-    graph branches under CUDA-graph capture).  No-op without CUDA (CPU dry-run walks)."""
+    graph branches under CUDA-graph capture).  No-op without CUDA (CPU dry-run walks).
+    ``priority``: CUDA stream priority of the side stream (-1 = high); branches opened inside a
+    high-priority branch inherit it, so a whole sub-graph (the head update next to the conv trunks of
+    the following batch) can be preferred by the block scheduler."""
 
     _streams = {}
+    _inherit = 0  # priority of the innermost open branch that asked for one
 
-    def __init__(self, name: str, enabled=None):
+    def __init__(self, name: str, enabled=None, priority=None):
         self.enabled = (OVERLAP if enabled is None else enabled) and torch.cuda.is_available()
         self.name = name
         self.ctx = None
+        self.priority = Branch._inherit if priority is None else int(priority)
         if self.enabled:
-            key = (torch.cuda.current_device(), name)
+            key = (torch.cuda.current_device(), name, self.priority)
             if key not in Branch._streams:
-                Branch._streams[key] = torch.cuda.Stream()
+                Branch._streams[key] = torch.cuda.Stream(priority=self.priority)
             self.stream = Branch._streams[key]
             self.done = torch.cuda.Event()
 
     def __enter__(self):
+        self._saved_inherit = Branch._inherit
+        Branch._inherit = self.priority
         if self.enabled:
             self.stream.wait_stream(torch.cuda.current_stream())
             self.ctx = torch.cuda.stream(self.stream)
@@ -66,6 +125,7 @@ class Branch:
         return self
 
     def __exit__(self, *exc):
+        Branch._inherit = self._saved_inherit
         if self.enabled:
             self.done.record(self.stream)
             self.ctx.__exit__(*exc)
@@ -77,6 +137,9 @@ class Branch:
 
 
 def _gemm(a, lda_m, lda_k, b, ldb_k, ldb_n, c, ldc, bias, m, n, k, beta=0.0, act=0):
+    if _PENDING is not None:
+        _PENDING.append((a, lda_m, lda_k, b, ldb_k, ldb_n, c, ldc, bias, m, n, k, beta, act))
+        return
     ws = gemm_workspace()
     C.vlnce_sgemm(a, lda_m, lda_k, b, ldb_k, ldb_n, c, ldc, bias, m, n, k, float(beta), int(act),
                   ws.data_ptr(), ws.numel(), lib.stream())
@@ -178,9 +241,10 @@ class HeadEngine:
         gx = self.buf("lstm_gx", (dirs, R, L, gates * Hs))
         wih = [rnn.weight_ih_l0] + ([rnn.weight_ih_l0_reverse] if dirs == 2 else [])
         bih = [rnn.bias_ih_l0] + ([rnn.bias_ih_l0_reverse] if dirs == 2 else [])
-        for d in range(dirs):
-            linear(ptr(emb), E, ptr(wih[d]), off(gx, d * R * L * gates * Hs), gates * Hs, ptr(bih[d]), R * L,
-                   gates * Hs, E)
+        with gemm_group():  # both directions' input projections: one launch
+            for d in range(dirs):
+                linear(ptr(emb), E, ptr(wih[d]), off(gx, d * R * L * gates * Hs), gates * Hs, ptr(bih[d]), R * L,
+                       gates * Hs, E)
         instr = self.buf("instr_out", (R, L, dirs * Hs))
         hn = self.buf("lstm_hn", (dirs, R, Hs))
         whh_b = ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None
@@ -215,7 +279,6 @@ class HeadEngine:
         H = self.H
         R = T * N
         gi = self.buf(tag + "_gi", (R, 3 * H))
-        linear(x, ldx, ptr(rnn.weight_ih_l0), ptr(gi), 3 * H, ptr(rnn.bias_ih_l0), R, 3 * H, in_size)
         hm_all = self.buf(tag + "_hm", (R, H))
         gh = self.buf(tag + "_gh", (N, 3 * H))
         sv = self.buf(tag + "_save", (R, 4 * H)) if save else None
@@ -224,9 +287,12 @@ class HeadEngine:
             hm = off(hm_all, t * N * H)
             if t == 0:
                 C.vlnce_mask_rows(h0, ldh0, off(masks_f, 0), hm, H, N, H, st)
+                with gemm_group():  # input projection of every step + hidden projection of step 0: independent
+                    linear(x, ldx, ptr(rnn.weight_ih_l0), ptr(gi), 3 * H, ptr(rnn.bias_ih_l0), R, 3 * H, in_size)
+                    linear(hm, H, ptr(rnn.weight_hh_l0), ptr(gh), 3 * H, ptr(rnn.bias_hh_l0), N, 3 * H, H)
             else:
                 C.vlnce_mask_rows(out + F4 * (t - 1) * N * ldo, ldo, off(masks_f, t * N), hm, H, N, H, st)
-            linear(hm, H, ptr(rnn.weight_hh_l0), ptr(gh), 3 * H, ptr(rnn.bias_hh_l0), N, 3 * H, H)
+                linear(hm, H, ptr(rnn.weight_hh_l0), ptr(gh), 3 * H, ptr(rnn.bias_hh_l0), N, 3 * H, H)
             last = t == T - 1
             C.vlnce_gru_pointwise_fwd(off(gi, t * N * 3 * H), ptr(gh), hm, H, out + F4 * t * N * ldo, ldo,
                                       h_final if last else None, ldhf,
@@ -355,15 +421,16 @@ class CMAEngine(HeadEngine):
         # ---- rgb_linear / depth_linear (cma_policy.py:244-245)
         rgb_mean = self.buf("rgb_mean", (R, self.Crgb))
         C.vlnce_mean_positions(ptr(rgb_e), P * self.Crgb, self.Crgb, ptr(rgb_mean), self.Crgb, R, P, self.Crgb, st)
-        lin = net.rgb_linear[2]
-        linear(ptr(rgb_mean), self.Crgb, ptr(lin.weight), ptr(state_in), self.state_in, ptr(lin.bias), R,
-               self.rgb_out, self.Crgb, act=1)
         dep_flat = self.buf("depth_flat", (R, self.Cdep * P))
         C.vlnce_positions_to_nchw(ptr(dep_e), P * self.Cdep, self.Cdep, ptr(dep_flat), self.Cdep * P, R, P,
                                   self.Cdep, st)
-        lin = net.depth_linear[1]
-        linear(ptr(dep_flat), self.Cdep * P, ptr(lin.weight), off(state_in, self.rgb_out), self.state_in,
-               ptr(lin.bias), R, self.depth_out, self.Cdep * P, act=1)
+        with gemm_group():  # independent: one launch
+            lin = net.rgb_linear[2]
+            linear(ptr(rgb_mean), self.Crgb, ptr(lin.weight), ptr(state_in), self.state_in, ptr(lin.bias), R,
+                   self.rgb_out, self.Crgb, act=1)
+            lin = net.depth_linear[1]
+            linear(ptr(dep_flat), self.Cdep * P, ptr(lin.weight), off(state_in, self.rgb_out), self.state_in,
+                   ptr(lin.bias), R, self.depth_out, self.Cdep * P, act=1)
 
         # ---- first GRU -> xcat[:, 0:H]  (cma_policy.py:247-256)
         s1, Lr = self.slots(net.state_encoder.rnn), net.num_recurrent_layers  # (N, Lr, H): encoder 1 | encoder 2
@@ -390,17 +457,19 @@ class CMAEngine(HeadEngine):
         # ---- visual attentions (cma_policy.py:265-274)
         text_q = self.buf("text_q", (R, hk))
         linear(off(xcat, H), self.cat, ptr(net.text_q.weight), ptr(text_q), hk, ptr(net.text_q.bias), R, hk, self.Dt)
-        for name, E_, Cc, kv, v_out, col in (
-                ("rgb", rgb_e, self.Crgb, net.rgb_kv, self.rgb_out, H + self.Dt),
-                ("depth", dep_e, self.Cdep, net.depth_kv, self.depth_out, H + self.Dt + self.rgb_out)):
-            qv = self.buf("q_" + name, (R, Cc))
-            linear_dx(ptr(text_q), hk, ptr(kv.weight), ptr(qv), Cc, R, hk, Cc)  # W_k = rows [0, hk)
+        vis = (("rgb", rgb_e, self.Crgb, net.rgb_kv, self.rgb_out, H + self.Dt),
+               ("depth", dep_e, self.Cdep, net.depth_kv, self.depth_out, H + self.Dt + self.rgb_out))
+        with gemm_group():  # W_k^T text_q for both modalities (W_k = rows [0, hk))
+            for name, E_, Cc, kv, v_out, col in vis:
+                linear_dx(ptr(text_q), hk, ptr(kv.weight), ptr(self.buf("q_" + name, (R, Cc))), Cc, R, hk, Cc)
+        for name, E_, Cc, kv, v_out, col in vis:
             probs = self.buf("p_" + name, (R, P)) if save else None
-            pooled = self.buf("pooled_" + name, (R, Cc))
-            C.vlnce_attn_pool_fwd(ptr(qv), Cc, ptr(E_), P * Cc, Cc, None, scale, ptr(probs), ptr(pooled), Cc,
-                                  R, P, Cc, st)
-            linear(ptr(pooled), Cc, off(kv.weight, hk * Cc), off(xcat, col), self.cat, off(kv.bias, hk), R,
-                   v_out, Cc)  # W_v = rows [hk, hk+v_out)
+            C.vlnce_attn_pool_fwd(ptr(self.buf("q_" + name, (R, Cc))), Cc, ptr(E_), P * Cc, Cc, None, scale, ptr(probs),
+                                  ptr(self.buf("pooled_" + name, (R, Cc))), Cc, R, P, Cc, st)
+        with gemm_group():  # W_v pooled + b_v for both modalities (W_v = rows [hk, hk+v_out))
+            for name, E_, Cc, kv, v_out, col in vis:
+                linear(ptr(self.buf("pooled_" + name, (R, Cc))), Cc, off(kv.weight, hk * Cc), off(xcat, col), self.cat,
+                       off(kv.bias, hk), R, v_out, Cc)
 
         # ---- compress + second GRU (cma_policy.py:276-294)
         x2 = self.buf("x2", (R, H))

@@ -22,6 +22,11 @@ from .backward import trainable_named
 from .lib import C, ptr
 
 
+import os as _os
+
+HEAD_PRIORITY = _os.environ.get("VLNCE_HEAD_PRIORITY", "1") != "0"
+
+
 class FlatParams:
     """All trainable parameters as views of one flat fp32 buffer (+ flat grad / Adam moments),
     so the optimiser and the gradient all-reduce are single launches."""
@@ -124,12 +129,16 @@ class ILTrainerStep:
         from .engine import Branch
 
         R = prev_actions.shape[0]
-        with Branch("visual_next") as br:
+        with Branch("visual_next", priority=0) as br:
             self.prefetch_visual(observations_next)
-        self.compute_grads(observations, prev_actions, not_done_masks, corrected_actions, weights,
-                           visual_slot="cur")
-        if apply:
-            self.apply_grads(True)
+        # the head update is a long chain of short kernels next to the trunks' SM-filling ones: on a high-priority
+        # stream its CTAs are placed first whenever a conv CTA retires (VLNCE_HEAD_PRIORITY=0: same priority)
+        with Branch("head", enabled=None if HEAD_PRIORITY else False, priority=-1 if HEAD_PRIORITY else 0) as bh:
+            self.compute_grads(observations, prev_actions, not_done_masks, corrected_actions, weights,
+                               visual_slot="cur")
+            if apply:
+                self.apply_grads(True)
+        bh.join()
         br.join()
         self.rotate_visual(R)
         return self._losses
