@@ -84,31 +84,51 @@ def test_sgemm_grouped_matches_torch_and_is_deterministic():
         torch.testing.assert_close(o, a @ w1[i:i + 8, :40].t(), rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("dirs", [1, 2])
-def test_lstm_matches_packed_torch(dirs):
-    R, L, E, H = 5, 11, 50, 128
+@pytest.mark.parametrize("dirs,R", [(1, 5), (2, 5), (2, 21), (1, 64)])
+def test_lstm_matches_packed_torch(dirs, R):
+    """Persistent (bi)LSTM forward AND backward-through-time against torch.nn.LSTM on a packed ragged batch (CPU fp32
+    autograd).  R = 5: one row per CTA; R = 21 / 64: four rows per CTA (with a ragged tail group) — lengths differ inside
+    every group, including a length-1 row and full-length rows."""
+    L, E, H = 11, 50, 128
     torch.manual_seed(0)
     rnn = nn.LSTM(E, H, bidirectional=dirs == 2)
     x = _r(R, L, E).cpu()
-    lens = torch.tensor([11, 1, 7, 4, 9])
+    lens = torch.tensor(([11, 1, 7, 4, 9, 2, 11, 3] * 8)[:R])
     x = x * (torch.arange(L).view(1, L, 1) < lens.view(R, 1, 1))
     packed = nn.utils.rnn.pack_padded_sequence(x, lens, batch_first=True, enforce_sorted=False)
-    with torch.no_grad():  # CPU fp32 reference (cuDNN RNNs default to TF32)
-        o, (hn, _) = rnn(packed)
-    want = nn.utils.rnn.pad_packed_sequence(o, batch_first=True, total_length=L)[0].to(DEV)
-    hn, x, rnn = hn.to(DEV), x.to(DEV), rnn.to(DEV)
+    o, (hn, _) = rnn(packed)  # CPU fp32 reference (cuDNN RNNs default to TF32)
+    want = nn.utils.rnn.pad_packed_sequence(o, batch_first=True, total_length=L)[0]
+    d_out = torch.randn(R, L, dirs * H, generator=torch.Generator().manual_seed(3)) * (
+        torch.arange(L).view(1, L, 1) < lens.view(R, 1, 1))
+    (want * d_out).sum().backward()
+    grads = {k: p.grad.clone().to(DEV) for k, p in rnn.named_parameters()}
+    want, hn, x, rnn, d_out = want.detach().to(DEV), hn.detach().to(DEV), x.to(DEV), rnn.to(DEV), d_out.to(DEV)
     lengths = lens.to(DEV).int()
     gx = torch.empty(dirs, R, L, 4 * H, device=DEV)
-    ws = [(rnn.weight_ih_l0, rnn.bias_ih_l0)] + ([(rnn.weight_ih_l0_reverse, rnn.bias_ih_l0_reverse)] if dirs == 2 else [])
-    for d, (w, b) in enumerate(ws):
-        linear(ptr(x), E, ptr(w), gx[d].data_ptr(), 4 * H, ptr(b), R * L, 4 * H, E)
+    sfx = ["", "_reverse"][:dirs]
+    for d, sf in enumerate(sfx):
+        linear(ptr(x), E, ptr(getattr(rnn, "weight_ih_l0" + sf)), gx[d].data_ptr(), 4 * H,
+               ptr(getattr(rnn, "bias_ih_l0" + sf)), R * L, 4 * H, E)
     out = torch.full((R, L, dirs * H), float("nan"), device=DEV)
     hn_got = torch.empty(dirs, R, H, device=DEV)
-    C.vlnce_lstm_seq_fwd(ptr(gx), ptr(rnn.weight_hh_l0), ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None,
+    gates = torch.zeros(dirs, R, L, 4 * H, device=DEV)
+    cs = torch.zeros(dirs, R, L, H, device=DEV)
+    whh_b = ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None
+    C.vlnce_lstm_seq_fwd(ptr(gx), ptr(rnn.weight_hh_l0), whh_b,
                          ptr(rnn.bias_hh_l0), ptr(rnn.bias_hh_l0_reverse) if dirs == 2 else None, ptr(lengths),
-                         ptr(out), ptr(hn_got), None, None, R, L, H, dirs, lib.stream())
+                         ptr(out), ptr(hn_got), ptr(gates), ptr(cs), R, L, H, dirs, lib.stream())
     torch.testing.assert_close(out, want, rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(hn_got, hn, rtol=1e-4, atol=2e-5)
+    # backward: pre-activation gate gradients and the hidden states fed to each step -> every parameter gradient
+    dgx = torch.full((dirs, R, L, 4 * H), float("nan"), device=DEV)
+    hprev = torch.full((dirs, R, L, H), float("nan"), device=DEV)
+    C.vlnce_lstm_seq_bwd(ptr(d_out), ptr(gates), ptr(cs), ptr(out), ptr(rnn.weight_hh_l0), whh_b, ptr(lengths),
+                         ptr(dgx), ptr(hprev), R, L, H, dirs, lib.stream())
+    for d, sf in enumerate(sfx):
+        dg = dgx[d].reshape(R * L, 4 * H)
+        torch.testing.assert_close(dg.t() @ x.reshape(R * L, E), grads["weight_ih_l0" + sf], rtol=1e-3, atol=2e-4)
+        torch.testing.assert_close(dg.t() @ hprev[d].reshape(R * L, H), grads["weight_hh_l0" + sf], rtol=1e-3, atol=2e-4)
+        torch.testing.assert_close(dg.sum(0), grads["bias_ih_l0" + sf], rtol=1e-3, atol=2e-4)
 
 
 def test_gru_cell_matches_torch():

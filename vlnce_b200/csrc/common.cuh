@@ -10,6 +10,8 @@
 
 #include "../../include/vlnce_b200.h"
 
+#include <stdlib.h>
+
 namespace vlnce {
 
 // ---- error plumbing: integer status across the C ABI, message kept per thread ----
@@ -126,5 +128,18 @@ template <>
 __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <>
 __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+
+// Rows of the instruction batch that one CTA of the persistent LSTM kernels carries (forward and backward agree):
+// 4 once there are enough rows to keep the GPU's share of the recurrence busy, 1 for single rows / tiny batches.
+// VLNCE_LSTM_NR=1|4 overrides (A/B measurements).
+inline int lstm_rows_per_cta(int R) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("VLNCE_LSTM_NR");
+    forced = (e != nullptr && (e[0] == '1' || e[0] == '4') && e[1] == 0) ? e[0] - '0' : 0;
+  }
+  if (forced) return forced;
+  return R >= 16 ? 4 : 1;
+}
 
 }  // namespace vlnce

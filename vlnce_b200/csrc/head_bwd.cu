@@ -158,12 +158,15 @@ __global__ void attn_pool_bwd_kernel(const float* __restrict__ q, long long ldq,
 }
 
 // ------------------------------------------------------------------------------------
-// LSTM backward through time, one CTA per (row, direction), 4H threads.
+// LSTM backward through time, one CTA per (group of NR rows, direction), 4H threads.
 // Thread t owns hidden unit k = t % H and the gate-row quarter part = t / H; it keeps the
-// transposed weights W_hh[j, k], j in its quarter, half in registers / half in shared memory.
+// transposed weights W_hh[j, k], j in its quarter, half in registers / half in shared memory, and
+// applies them to the NR rows of its group in every step (as the forward kernel: the weights are
+// read once per step for NR rows, the recurrence occupies R/NR SMs).  The saved activations of the
+// NEXT step are fetched while the current step computes.
 // Emits d_gx (pre-activation gate grads, zero beyond len) and hprev (h fed to each step).
 // ------------------------------------------------------------------------------------
-template <int H>
+template <int H, int NR>
 __global__ void __launch_bounds__(4 * H, 1)
 lstm_seq_bwd_kernel(const float* __restrict__ dout,   // (R, L, dirs*H)
                     const float* __restrict__ gates,  // (dirs, R, L, 4H) activated i,f,g,o
@@ -177,60 +180,109 @@ lstm_seq_bwd_kernel(const float* __restrict__ dout,   // (R, L, dirs*H)
   constexpr int JS = H - JR;       // weights in shared memory
   extern __shared__ __align__(16) float smem_b[];
   float* w_s = smem_b;                         // [JS][4H]: w_s[jj][t] = W[part*H + JR + jj, k]
-  float* dp_s = w_s + (size_t)JS * 4 * H;      // 4H pre-activation grads of this step
-  float* red_s = dp_s + 4 * H;                 // 4H partial sums
-  const int r = blockIdx.x, dir = blockIdx.y;
+  float* dp_s = w_s + (size_t)JS * 4 * H;      // NR x 4H pre-activation grads of this step
+  float* red_s = dp_s + NR * 4 * H;            // NR x 4H partial sums
+  const int r0 = blockIdx.x * NR, dir = blockIdx.y;
   const int t = threadIdx.x, k = t % H, part = t / H;
   const float* whh = dir == 0 ? whh_f : whh_b;
   float w[JR];
 #pragma unroll
   for (int jj = 0; jj < JR; ++jj) w[jj] = __ldg(whh + (size_t)(part * H + jj) * H + k);
   for (int jj = 0; jj < JS; ++jj) w_s[(size_t)jj * 4 * H + t] = __ldg(whh + (size_t)(part * H + JR + jj) * H + k);
-  const int len = min(lengths[r], L);
-  const size_t row_base = ((size_t)dir * R + r) * L;
+  int len[NR];
+  int maxlen = 0;
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) {
+    len[rr] = (r0 + rr < R) ? min(lengths[r0 + rr], L) : 0;
+    maxlen = max(maxlen, len[rr]);
+  }
   const int DH = dirs * H;
-  float dh_carry = 0.f, dc_carry = 0.f;  // meaningful for part == 0 threads (unit k)
-  __syncthreads();
-  for (int step = len - 1; step >= 0; --step) {
-    const int tt = dir == 0 ? step : len - 1 - step;          // time index of this step
+  float dh_carry[NR], dc_carry[NR];  // meaningful for part == 0 threads (unit k)
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) { dh_carry[rr] = 0.f; dc_carry[rr] = 0.f; }
+  // saved values of (row rr, step) needed by unit k: the four gates, c, c_prev, h_prev, dout
+  struct Saved { float ig, fg, gg, og, c, cp, hp, d; };
+  auto fetch = [&](int rr, int step) -> Saved {
+    Saved v = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (part != 0 || step < 0 || step >= len[rr]) return v;
+    const size_t row_base = ((size_t)dir * R + r0 + rr) * L;
+    const int tt = dir == 0 ? step : len[rr] - 1 - step;      // time index of this step
     const int tp = dir == 0 ? tt - 1 : tt + 1;                // time index of the previous step
-    const bool has_prev = step > 0;
+    const float* g = gates + (row_base + tt) * 4 * H;
+    v.ig = __ldg(g + k); v.fg = __ldg(g + H + k); v.gg = __ldg(g + 2 * H + k); v.og = __ldg(g + 3 * H + k);
+    v.c = __ldg(cs + (row_base + tt) * H + k);
+    if (step > 0) {
+      v.cp = __ldg(cs + (row_base + tp) * H + k);
+      v.hp = __ldg(out + ((size_t)(r0 + rr) * L + tp) * DH + dir * H + k);
+    }
+    v.d = __ldg(dout + ((size_t)(r0 + rr) * L + tt) * DH + dir * H + k);
+    return v;
+  };
+  Saved nxt[NR];
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) nxt[rr] = fetch(rr, maxlen - 1);   // (zeros for rows shorter than the longest)
+  __syncthreads();
+  for (int step = maxlen - 1; step >= 0; --step) {
     if (part == 0) {
-      const float* g = gates + (row_base + tt) * 4 * H;
-      const float ig = g[k], fg = g[H + k], gg = g[2 * H + k], og = g[3 * H + k];
-      const float c = cs[(row_base + tt) * H + k];
-      const float cp = has_prev ? cs[(row_base + tp) * H + k] : 0.f;
-      const float hp = has_prev ? out[((size_t)r * L + tp) * DH + dir * H + k] : 0.f;
-      hprev[(row_base + tt) * H + k] = hp;
-      const float th = tanhf(c);
-      const float dh = dout[((size_t)r * L + tt) * DH + dir * H + k] + dh_carry;
-      const float dc = fmaf(dh * og, 1.f - th * th, dc_carry);
-      const float dpi = dc * gg * ig * (1.f - ig);
-      const float dpf = dc * cp * fg * (1.f - fg);
-      const float dpg = dc * ig * (1.f - gg * gg);
-      const float dpo = dh * th * og * (1.f - og);
-      dc_carry = dc * fg;
-      dp_s[k] = dpi; dp_s[H + k] = dpf; dp_s[2 * H + k] = dpg; dp_s[3 * H + k] = dpo;
-      float* o = dgx + (row_base + tt) * 4 * H;
-      o[k] = dpi; o[H + k] = dpf; o[2 * H + k] = dpg; o[3 * H + k] = dpo;
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const Saved v = nxt[rr];
+        nxt[rr] = fetch(rr, step - 1);   // in flight during this step
+        float* dp = dp_s + rr * 4 * H;
+        if (step < len[rr]) {
+          const size_t row_base = ((size_t)dir * R + r0 + rr) * L;
+          const int tt = dir == 0 ? step : len[rr] - 1 - step;
+          hprev[(row_base + tt) * H + k] = v.hp;
+          const float th = tanhf(v.c);
+          const float dh = v.d + dh_carry[rr];
+          const float dc = fmaf(dh * v.og, 1.f - th * th, dc_carry[rr]);
+          const float dpi = dc * v.gg * v.ig * (1.f - v.ig);
+          const float dpf = dc * v.cp * v.fg * (1.f - v.fg);
+          const float dpg = dc * v.ig * (1.f - v.gg * v.gg);
+          const float dpo = dh * th * v.og * (1.f - v.og);
+          dc_carry[rr] = dc * v.fg;
+          dp[k] = dpi; dp[H + k] = dpf; dp[2 * H + k] = dpg; dp[3 * H + k] = dpo;
+          float* o = dgx + (row_base + tt) * 4 * H;
+          o[k] = dpi; o[H + k] = dpf; o[2 * H + k] = dpg; o[3 * H + k] = dpo;
+        } else {
+          dp[k] = 0.f; dp[H + k] = 0.f; dp[2 * H + k] = 0.f; dp[3 * H + k] = 0.f;
+        }
+      }
     }
     __syncthreads();
     // dh_prev[k] = sum_j W[j, k] dp[j]; this thread covers j in [part*H, (part+1)*H)
-    float a0 = 0.f, a1 = 0.f;
-    const float* dp = dp_s + part * H;
+    float a0[NR], a1[NR];
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr) { a0[rr] = 0.f; a1[rr] = 0.f; }
 #pragma unroll
     for (int jj = 0; jj < JR; jj += 2) {
-      a0 = fmaf(w[jj], dp[jj], a0);
-      a1 = fmaf(w[jj + 1], dp[jj + 1], a1);
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const float* dp = dp_s + rr * 4 * H + part * H;
+        a0[rr] = fmaf(w[jj], dp[jj], a0[rr]);
+        a1[rr] = fmaf(w[jj + 1], dp[jj + 1], a1[rr]);
+      }
     }
 #pragma unroll 8
     for (int jj = 0; jj < JS; jj += 2) {
-      a0 = fmaf(w_s[(size_t)jj * 4 * H + t], dp[JR + jj], a0);
-      a1 = fmaf(w_s[(size_t)(jj + 1) * 4 * H + t], dp[JR + jj + 1], a1);
+      const float w0 = w_s[(size_t)jj * 4 * H + t], w1 = w_s[(size_t)(jj + 1) * 4 * H + t];
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const float* dp = dp_s + rr * 4 * H + part * H;
+        a0[rr] = fmaf(w0, dp[JR + jj], a0[rr]);
+        a1[rr] = fmaf(w1, dp[JR + jj + 1], a1[rr]);
+      }
     }
-    red_s[t] = a0 + a1;
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr) red_s[rr * 4 * H + t] = a0[rr] + a1[rr];
     __syncthreads();
-    if (part == 0) dh_carry = (red_s[k] + red_s[H + k]) + (red_s[2 * H + k] + red_s[3 * H + k]);
+    if (part == 0) {
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const float* rs = red_s + rr * 4 * H;
+        dh_carry[rr] = (rs[k] + rs[H + k]) + (rs[2 * H + k] + rs[3 * H + k]);
+      }
+    }
     // next iteration's first phase only touches dp_s after the barrier below
     __syncthreads();
   }
@@ -595,16 +647,23 @@ extern "C" int vlnce_lstm_seq_bwd(const float* dout, const float* gates, const f
   if (e == cudaSuccess) e = cudaMemsetAsync(hprev, 0, sizeof(float) * (size_t)dirs * R * L * H, stream);
   if (e != cudaSuccess) return cuda_status(e, "lstm_seq_bwd memset");
   constexpr int H_ = 128;
-  const size_t smem = sizeof(float) * ((size_t)(H_ / 2) * 4 * H_ + 8 * H_);
+  const int nr = lstm_rows_per_cta(R);   // rows per CTA (common.cuh; same choice as the forward kernel)
+  const size_t smem = sizeof(float) * ((size_t)(H_ / 2) * 4 * H_ + (size_t)nr * 8 * H_);
   static bool configured = false;
   if (!configured) {
-    e = cudaFuncSetAttribute(lstm_seq_bwd_kernel<H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int big = (int)(sizeof(float) * ((size_t)(H_ / 2) * 4 * H_ + 4 * 8 * H_));
+    e = cudaFuncSetAttribute(lstm_seq_bwd_kernel<H_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_seq_bwd_kernel<H_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lstm_seq_bwd)");
     configured = true;
   }
-  dim3 grid(R, dirs);
-  lstm_seq_bwd_kernel<H_><<<grid, 4 * H_, smem, stream>>>(dout, gates, cs, out, whh_f, whh_b, lengths, dgx, hprev,
-                                                        R, L, dirs);
+  dim3 grid((R + nr - 1) / nr, dirs);
+  if (nr == 4)
+    lstm_seq_bwd_kernel<H_, 4><<<grid, 4 * H_, smem, stream>>>(dout, gates, cs, out, whh_f, whh_b, lengths, dgx, hprev,
+                                                             R, L, dirs);
+  else
+    lstm_seq_bwd_kernel<H_, 1><<<grid, 4 * H_, smem, stream>>>(dout, gates, cs, out, whh_f, whh_b, lengths, dgx, hprev,
+                                                             R, L, dirs);
   VLNCE_LAUNCH_CHECK("lstm_seq_bwd_kernel");
   return VLNCE_OK;
 }

@@ -74,12 +74,15 @@ __global__ void feature_lengths_kernel(const float* __restrict__ x, int* __restr
 
 // ------------------------------------------------------------------------------------
 // Persistent LSTM recurrence (instruction_encoder.py:80-84, torch.nn.LSTM on a packed
-// sequence): one CTA per (row, direction), 4H threads; thread j keeps row j of W_hh in
-// registers for all L steps.  gx = x W_ih^T + b_ih + b_hh is precomputed by one GEMM.
-// Gate order i, f, g, o (PyTorch).  Steps t >= len are skipped (outputs stay zero); the
-// reverse direction starts at each row's own last token.
+// sequence): one CTA per (group of NR rows, direction), 4H threads; thread j keeps row j of
+// W_hh on chip for all L steps and applies it to the NR rows of its group in every step, so
+// the weights are read once per step for NR rows and the (latency-bound) recurrence occupies
+// R/NR SMs instead of R.  gx = x W_ih^T + b_ih is precomputed by one GEMM; the value of the
+// NEXT step is fetched while the current step computes.  Gate order i, f, g, o (PyTorch).
+// Steps t >= len are skipped (outputs stay zero); the reverse direction starts at each row's
+// own last token.  Per-row arithmetic (summation order) does not depend on NR.
 // ------------------------------------------------------------------------------------
-template <int H>
+template <int H, int NR>
 __global__ void __launch_bounds__(4 * H, 1)
 lstm_seq_fwd_kernel(const float* __restrict__ gx,   // (dirs, R, L, 4H) = x W_ih^T + b_ih
                     const float* __restrict__ whh_f, const float* __restrict__ whh_b,  // (4H, H) per direction
@@ -95,9 +98,9 @@ lstm_seq_fwd_kernel(const float* __restrict__ gx,   // (dirs, R, L, 4H) = x W_ih
   constexpr int KS4 = (H - KR) / 4;
   extern __shared__ __align__(16) float lstm_smem[];
   float4* w_s = reinterpret_cast<float4*>(lstm_smem);           // KS4 * 4H float4
-  float* h_s = lstm_smem + (size_t)KS4 * 4 * H * 4;              // H
-  float* g_s = h_s + H;                                          // 4H
-  const int r = blockIdx.x, dir = blockIdx.y;
+  float* h_s = lstm_smem + (size_t)KS4 * 4 * H * 4;              // NR x H
+  float* g_s = h_s + NR * H;                                     // NR x 4H
+  const int r0 = blockIdx.x * NR, dir = blockIdx.y;
   const int j = threadIdx.x;  // gate row
   float w[KR];
   {
@@ -110,48 +113,95 @@ lstm_seq_fwd_kernel(const float* __restrict__ gx,   // (dirs, R, L, 4H) = x W_ih
 #pragma unroll
     for (int k = 0; k < KS4; ++k) w_s[k * 4 * H + j] = __ldg(wp + KR / 4 + k);
   }
-  const int len = min(lengths[r], L);
+  int len[NR];
+  int maxlen = 0;
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) {
+    len[rr] = (r0 + rr < R) ? min(lengths[r0 + rr], L) : 0;
+    maxlen = max(maxlen, len[rr]);
+  }
   const float bh = __ldg((dir == 0 ? bhh_f : bhh_b) + j);
-  float c = 0.f;
-  if (j < H) h_s[j] = 0.f;
+  float c[NR];
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) {
+    c[rr] = 0.f;
+    if (j < H) h_s[rr * H + j] = 0.f;
+  }
+  // gx of (row rr, step): time index t = step (forward) | len-1-step (reverse)
+  auto gx_at = [&](int rr, int step) -> float {
+    if (step >= len[rr]) return 0.f;
+    const int t = dir == 0 ? step : len[rr] - 1 - step;
+    return __ldg(gx + (((size_t)dir * R + r0 + rr) * L + t) * 4 * H + j);
+  };
+  float gnext[NR];
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) gnext[rr] = gx_at(rr, 0);
   __syncthreads();
-  const size_t row_base = ((size_t)dir * R + r) * L;
-  for (int step = 0; step < len; ++step) {
-    const int t = dir == 0 ? step : len - 1 - step;
-    float a0 = __ldg(gx + (row_base + t) * 4 * H + j) + bh, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int step = 0; step < maxlen; ++step) {
+    float a0[NR], a1[NR], a2[NR], a3[NR];
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr) {
+      a0[rr] = gnext[rr] + bh; a1[rr] = 0.f; a2[rr] = 0.f; a3[rr] = 0.f;
+      gnext[rr] = gx_at(rr, step + 1);   // in flight during this step's dot products
+    }
 #pragma unroll
     for (int k = 0; k < KR; k += 4) {
-      const float4 h4 = *reinterpret_cast<const float4*>(&h_s[k]);
-      a0 = fmaf(w[k], h4.x, a0);
-      a1 = fmaf(w[k + 1], h4.y, a1);
-      a2 = fmaf(w[k + 2], h4.z, a2);
-      a3 = fmaf(w[k + 3], h4.w, a3);
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const float4 h4 = *reinterpret_cast<const float4*>(&h_s[rr * H + k]);
+        a0[rr] = fmaf(w[k], h4.x, a0[rr]);
+        a1[rr] = fmaf(w[k + 1], h4.y, a1[rr]);
+        a2[rr] = fmaf(w[k + 2], h4.z, a2[rr]);
+        a3[rr] = fmaf(w[k + 3], h4.w, a3[rr]);
+      }
     }
 #pragma unroll
     for (int k = 0; k < KS4; ++k) {
       const float4 w4 = w_s[k * 4 * H + j];
-      const float4 h4 = *reinterpret_cast<const float4*>(&h_s[KR + 4 * k]);
-      a0 = fmaf(w4.x, h4.x, a0);
-      a1 = fmaf(w4.y, h4.y, a1);
-      a2 = fmaf(w4.z, h4.z, a2);
-      a3 = fmaf(w4.w, h4.w, a3);
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        const float4 h4 = *reinterpret_cast<const float4*>(&h_s[rr * H + KR + 4 * k]);
+        a0[rr] = fmaf(w4.x, h4.x, a0[rr]);
+        a1[rr] = fmaf(w4.y, h4.y, a1[rr]);
+        a2[rr] = fmaf(w4.z, h4.z, a2[rr]);
+        a3[rr] = fmaf(w4.w, h4.w, a3[rr]);
+      }
     }
-    const float pre = (a0 + a1) + (a2 + a3);
-    const float act = (j >= 2 * H && j < 3 * H) ? tanhf(pre) : sigmoid_precise(pre);
-    g_s[j] = act;
-    if (save_gates != nullptr) save_gates[(row_base + t) * 4 * H + j] = act;
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr) {
+      if (step < len[rr]) {
+        const float pre = (a0[rr] + a1[rr]) + (a2[rr] + a3[rr]);
+        const float act = (j >= 2 * H && j < 3 * H) ? tanhf(pre) : sigmoid_precise(pre);
+        g_s[rr * 4 * H + j] = act;
+        if (save_gates != nullptr) {
+          const int t = dir == 0 ? step : len[rr] - 1 - step;
+          save_gates[(((size_t)dir * R + r0 + rr) * L + t) * 4 * H + j] = act;
+        }
+      }
+    }
     __syncthreads();
     if (j < H) {
-      const float ig = g_s[j], fg = g_s[H + j], gg = g_s[2 * H + j], og = g_s[3 * H + j];
-      c = fmaf(fg, c, ig * gg);
-      const float h = og * tanhf(c);
-      h_s[j] = h;
-      out[((size_t)r * L + t) * (dirs * H) + dir * H + j] = h;
-      if (save_c != nullptr) save_c[(row_base + t) * H + j] = c;
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) {
+        if (step < len[rr]) {
+          const float* g = g_s + rr * 4 * H;
+          const float ig = g[j], fg = g[H + j], gg = g[2 * H + j], og = g[3 * H + j];
+          c[rr] = fmaf(fg, c[rr], ig * gg);
+          const float h = og * tanhf(c[rr]);
+          h_s[rr * H + j] = h;
+          const int t = dir == 0 ? step : len[rr] - 1 - step;
+          out[((size_t)(r0 + rr) * L + t) * (dirs * H) + dir * H + j] = h;
+          if (save_c != nullptr) save_c[(((size_t)dir * R + r0 + rr) * L + t) * H + j] = c[rr];
+        }
+      }
     }
     __syncthreads();
   }
-  if (hn != nullptr && j < H) hn[((size_t)dir * R + r) * H + j] = h_s[j];
+  if (hn != nullptr && j < H) {
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr)
+      if (r0 + rr < R) hn[((size_t)dir * R + r0 + rr) * H + j] = h_s[rr * H + j];
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -487,17 +537,26 @@ extern "C" int vlnce_lstm_seq_fwd(const float* gx, const float* whh_f, const flo
   VLNCE_CHECK_ARG(H == 128, "lstm_seq_fwd: hidden size %d not built (128 only)", H);
   cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)R * L * dirs * H, stream);
   if (e != cudaSuccess) return cuda_status(e, "lstm_seq_fwd memset");
-  dim3 grid(R, dirs);
   constexpr int H_ = 128;
-  const size_t smem = sizeof(float) * ((size_t)(H_ / 2) * 4 * H_ + H_ + 4 * H_);
+  // NR rows per CTA: with a batch of rows the recurrence is latency-bound, so 4 rows share one SM (and one read of
+  // the weights per step); single rows / tiny batches keep one row per CTA
+  const int nr = lstm_rows_per_cta(R);
+  dim3 grid((R + nr - 1) / nr, dirs);
+  const size_t smem = sizeof(float) * ((size_t)(H_ / 2) * 4 * H_ + (size_t)nr * 5 * H_);
   static bool configured = false;
   if (!configured) {
-    e = cudaFuncSetAttribute(lstm_seq_fwd_kernel<H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int big = (int)(sizeof(float) * ((size_t)(H_ / 2) * 4 * H_ + 4 * 5 * H_));
+    e = cudaFuncSetAttribute(lstm_seq_fwd_kernel<H_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_seq_fwd_kernel<H_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lstm_seq_fwd)");
     configured = true;
   }
-  lstm_seq_fwd_kernel<H_><<<grid, 4 * H_, smem, stream>>>(gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save_gates,
-                                                        save_c, R, L, dirs);
+  if (nr == 4)
+    lstm_seq_fwd_kernel<H_, 4><<<grid, 4 * H_, smem, stream>>>(gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save_gates,
+                                                             save_c, R, L, dirs);
+  else
+    lstm_seq_fwd_kernel<H_, 1><<<grid, 4 * H_, smem, stream>>>(gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save_gates,
+                                                             save_c, R, L, dirs);
   VLNCE_LAUNCH_CHECK("lstm_seq_fwd_kernel");
   return VLNCE_OK;
 }
