@@ -98,6 +98,11 @@ int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scal
 /* cap on the persistent conv_tma grid (0 = one CTA per SM; default: environment VLNCE_TMA_CTA_CAP) */
 int vlnce_set_tma_cta_cap(int cap);
 int vlnce_debug_set_trace(void* buffer);
+/* rows of the instruction batch per CTA of the persistent LSTM kernels: 1 (default) | 4; 0 = back to the default /
+ * environment VLNCE_LSTM_NR (see csrc/common.cuh) */
+int vlnce_set_lstm_rows(int rows_per_cta);
+/* Debug aid: *slot = %globaltimer (ns) when `stream` reaches this point (graph-capturable timeline probe). */
+int vlnce_debug_stamp(long long* slot, cudaStream_t stream);
 int vlnce_stem_s2d(const void* x, int x_dtype, void* out, int out_dtype, int N, int H, int W,
                    cudaStream_t stream);
 int vlnce_conv_stem_tma(const void* xs, const void* w, int ab_dtype, const float* scale, const float* shift,

@@ -84,11 +84,19 @@ def test_sgemm_grouped_matches_torch_and_is_deterministic():
         torch.testing.assert_close(o, a @ w1[i:i + 8, :40].t(), rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("dirs,R", [(1, 5), (2, 5), (2, 21), (1, 64)])
-def test_lstm_matches_packed_torch(dirs, R):
+@pytest.mark.parametrize("dirs,R,nr", [(1, 5, 1), (2, 5, 1), (2, 21, 4), (1, 64, 4), (2, 21, 1)])
+def test_lstm_matches_packed_torch(dirs, R, nr):
     """Persistent (bi)LSTM forward AND backward-through-time against torch.nn.LSTM on a packed ragged batch (CPU fp32
-    autograd).  R = 5: one row per CTA; R = 21 / 64: four rows per CTA (with a ragged tail group) — lengths differ inside
-    every group, including a length-1 row and full-length rows."""
+    autograd), with one row per CTA (the default) and with four rows per CTA (``vlnce_set_lstm_rows(4)``; R = 21 has a
+    ragged tail group) — lengths differ inside every group, including a length-1 row and full-length rows."""
+    C.vlnce_set_lstm_rows(nr)
+    try:
+        _lstm_case(dirs, R)
+    finally:
+        C.vlnce_set_lstm_rows(0)
+
+
+def _lstm_case(dirs, R):
     L, E, H = 11, 50, 128
     torch.manual_seed(0)
     rnn = nn.LSTM(E, H, bidirectional=dirs == 2)
@@ -197,6 +205,13 @@ def test_small_layout_ops():
     C.vlnce_adaptive_avgpool(ptr(x), lib.F32, ptr(y), 40, 4, 9, 9, 40, 4, lib.stream())
     want = F.adaptive_avg_pool2d(x.permute(0, 3, 1, 2), (4, 4)).flatten(2).permute(0, 2, 1)
     torch.testing.assert_close(y, want, rtol=1e-5, atol=1e-6)
+    for dt, code in ((torch.bfloat16, lib.BF16), (torch.float16, lib.F16)):   # 8-channel vector path, strided output
+        xb = _r(3, 8, 8, 64, seed=9).to(dt)
+        yb = torch.full((3, 16, 72), float("nan"), device=DEV)
+        C.vlnce_adaptive_avgpool(ptr(xb), code, ptr(yb), 72, 3, 8, 8, 64, 4, lib.stream())
+        want = F.adaptive_avg_pool2d(xb.float().permute(0, 3, 1, 2), (4, 4)).flatten(2).permute(0, 2, 1)
+        torch.testing.assert_close(yb[:, :, :64], want, rtol=1e-5, atol=1e-6)
+        assert torch.isnan(yb[:, :, 64:]).all()
     ids = torch.tensor([[3, 0, 5, 0], [0, 0, 0, 0], [1, 2, 3, 4]], device=DEV)
     lens = torch.empty(3, dtype=torch.int32, device=DEV)
     C.vlnce_token_lengths(ptr(ids), ptr(lens), 3, 4, lib.stream())

@@ -74,9 +74,16 @@ def test_reference_update_arithmetic_on_cuda_policy(name, precision, rtol):
     check(got, gold(name), rtol, name, grad_norm_tol=0.05 if precision == "bf16" else None)
 
 
-@pytest.mark.parametrize("name", ["cma_train_features", "cma_train_features_nopm", "seq2seq_train_features",
-                                  "seq2seq_train_pixels"])
-def test_fused_step_matches_reference(name):
+@pytest.mark.parametrize("name,grouped", [("cma_train_features", False), ("cma_train_features_nopm", False),
+                                          ("seq2seq_train_features", False), ("seq2seq_train_pixels", False),
+                                          ("cma_train_features", True), ("cma_rxr_train_features", True),
+                                          ("seq2seq_train_features", True)])
+def test_fused_step_matches_reference(name, grouped, monkeypatch):
+    """``grouped``: the head's GEMMs issued as grouped launches (vlnce_sgemm_grouped) with the weight / bias gradients
+    deferred into one launch at the end of the backward (engine.GROUPING, off by default — see engine.py)."""
+    from vlnce_b200 import engine
+
+    monkeypatch.setattr(engine, "GROUPING", grouped)
     case = cases.CASES[name]
     want = gold(name)
     pol = cases.build_policy(vlnce_b200, case).to(DEV)

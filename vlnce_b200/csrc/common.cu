@@ -51,8 +51,25 @@ bool carveout_first_use(const void* kernel) {
   return seen.insert(kernel).second;
 }
 
+static std::atomic<int> g_lstm_rows{-1};
+int lstm_rows_per_cta(int R) {
+  int v = g_lstm_rows.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("VLNCE_LSTM_NR");
+    v = (e != nullptr && (e[0] == '1' || e[0] == '4') && e[1] == 0) ? e[0] - '0' : 0;
+    g_lstm_rows.store(v, std::memory_order_relaxed);
+  }
+  (void)R;
+  return v == 4 ? 4 : 1;
+}
+void set_lstm_rows(int nr) { g_lstm_rows.store(nr == 4 ? 4 : (nr == 1 ? 1 : 0), std::memory_order_relaxed); }
+
 }  // namespace vlnce
 
+extern "C" int vlnce_set_lstm_rows(int rows_per_cta) {
+  vlnce::set_lstm_rows(rows_per_cta);
+  return VLNCE_OK;
+}
 extern "C" const char* vlnce_version(void) { return "vlnce_b200 0.1 (sm_100a)"; }
 extern "C" const char* vlnce_last_error(void) { return vlnce::g_err; }
 extern "C" long long vlnce_launch_count(void) { return vlnce::g_launches.load(); }
@@ -62,3 +79,19 @@ extern "C" int vlnce_set_pdl(int on) {
   return VLNCE_OK;
 }
 extern "C" long long vlnce_get_pdl(void) { return vlnce::pdl_enabled() ? 1 : 0; }
+
+// Debug aid: one thread writes %globaltimer (ns) into *slot when the stream reaches this point — a timeline probe
+// that can be captured into a CUDA graph on any branch (tools/timeline_probe.py).
+namespace vlnce {
+__global__ void stamp_kernel(long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = (long long)t;
+}
+}  // namespace vlnce
+extern "C" int vlnce_debug_stamp(long long* slot, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(slot != nullptr, "debug_stamp: null slot");
+  vlnce::stamp_kernel<<<1, 1, 0, stream>>>(slot);
+  VLNCE_LAUNCH_CHECK("stamp_kernel");
+  return VLNCE_OK;
+}

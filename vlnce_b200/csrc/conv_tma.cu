@@ -49,6 +49,7 @@ constexpr int kEpiWarps = 8;                       // two groups of four: each T
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 4 * 32;     // + MMA issuer, activation producer, weight producer, store issuer
 constexpr int kMaxStg = 4;
+constexpr int kSchedRing = 16;                     // tile ids in flight between the claiming thread and the slowest role
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kMaxA = 8, kMaxB = 18;
 
@@ -64,6 +65,7 @@ struct TmaConvParams {
   int w_cols;      // K extent of one filter tap in the weight matrix (C; stem: 0, chunks are consecutive)
   int b_stationary;  // 1: b_stages == taps*c_chunks and the weight slice is loaded once per CTA
   long long* trace;  // debug: per-role (event, clock64) records of CTA 0 (vlnce_debug_set_trace), else NULL
+  int* sched;        // dynamic tile scheduler: {next tile, finished CTAs} of this launch (both zero before and after)
   int taps;        // 1 | 9
   int halo_w;      // 8 (rows mode: plain 8-row groups) | 10
   int a_bytes;     // ring slot size (1024-multiple), a_tx = bytes the TMA delivers
@@ -191,13 +193,23 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint64_t* res_full = acc_empty + 2;
   uint64_t* stg_free = res_full + kMaxStg;
   uint64_t* staged = stg_free + kMaxStg;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(staged + kMaxStg);
+  uint64_t* sched_full = staged + kMaxStg;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_full + kSchedRing);
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_slot + 1);   // kSchedRing tile ids (-1 = no more tiles)
+  volatile int* sched_done = sched_tile + kSchedRing;                          // tiles the store issuer has finished
   const uint32_t stg_bytes = 128u * BLOCK_N * (p.y_fp32 ? 4u : 2u);
   const uint32_t stage_out = smem_b0 + p.b_stages * B_BYTES + 1024;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = (p.m_tiles / MT) * p.n_tiles;  // host guarantees m_tiles % MT == 0
-  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // Dynamic tile schedule: the activation producer claims tile ids from a global counter and publishes them to the
+  // other roles through a small ring (sched_tile / sched_full); position `it` of a role's walk is ring slot it & 15,
+  // phase (it >> 4) & 1.  A CTA that starts late (its SM was busy with another kernel of the step) simply claims
+  // fewer tiles — with a static round-robin list the whole launch waited for it.
+  auto tile_of = [&](int it) -> int {
+    mbar_wait(&sched_full[it & (kSchedRing - 1)], (uint32_t)(it >> 4) & 1u, 40);
+    return sched_tile[it & (kSchedRing - 1)];
+  };
 
   if (threadIdx.x == (kEpiWarps + 1) * 32) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -211,6 +223,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       mbar_init(&stg_free[s], 1);
       mbar_init(&staged[s], kEpiThreads);
     }
+    for (int s = 0; s < kSchedRing; ++s) mbar_init(&sched_full[s], 1);
+    *sched_done = 0;
     fence_barrier_init();
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
@@ -231,8 +245,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   // residual of sub-tile vt -> staging buffer sb (the buffer is free: nothing has used it yet / its last store has
   // been read); TMA store of the staged sub-tile vt out of buffer sb.  Issued by the store thread of the CTA.
-  auto issue_res = [&](int vt, int sb) {
-    const Tile ti = decode_tile(p, blockIdx.x + (vt / MT) * gridDim.x, BLOCK_N, MT, vt % MT);
+  auto issue_res = [&](int t, int h, int sb) {
+    const Tile ti = decode_tile(p, t, BLOCK_N, MT, h);
     mbar_arrive_expect_tx(&res_full[sb], 128 * BLOCK_N * 2);
     for (int b = 0; b < BLOCK_N / 64; ++b) {
       const uint32_t dst = stage_out + sb * stg_bytes + (uint32_t)b * (128 * 128);
@@ -240,8 +254,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.x0, ti.y0, ti.img);
     }
   };
-  auto store_subtile = [&](int vt, int sb) {
-    const Tile ti = decode_tile(p, blockIdx.x + (vt / MT) * gridDim.x, BLOCK_N, MT, vt % MT);
+  auto store_subtile = [&](int t, int h, int sb) {
+    const Tile ti = decode_tile(p, t, BLOCK_N, MT, h);
     const uint32_t stg = stage_out + sb * stg_bytes;
     const int boxes = p.y_fp32 ? BLOCK_N / 32 : BLOCK_N / 64;
     const int cols = p.y_fp32 ? 32 : 64;
@@ -259,8 +273,17 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       int as = 0;
       uint32_t aph = 0;
       Trace tr(p.trace, 0);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int t = blockIdx.x + it * gridDim.x;
+      // every tile is claimed, the first one too: a CTA that starts late finds the counter past the end and leaves
+      // (measured against a static first tile: 0.02 ms slower alone, 0.03 ms faster next to the other kernels of a step)
+      int t = atomicAdd(p.sched, 1);
+      if (t >= total_tiles) t = -1;
+      for (int it = 0;; ++it) {
+        // ring slot reuse: never more than kSchedRing tiles ahead of the store issuer (does not wait in practice)
+        while (it - *sched_done >= kSchedRing) { }
+        sched_tile[it & (kSchedRing - 1)] = t;
+        mbar_arrive(&sched_full[it & (kSchedRing - 1)]);   // (release: the id is visible to whoever acquires the phase)
+        if (t < 0) break;
+        int t_next = atomicAdd(p.sched, 1);                // in flight while this tile's loads are issued
         Tile ti[MT];
 #pragma unroll
         for (int h = 0; h < MT; ++h) ti[h] = decode_tile(p, t, BLOCK_N, MT, h);
@@ -278,7 +301,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           tr.rec(3, it * p.c_chunks + cc);
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
+        t = t_next < total_tiles ? t_next : -1;
       }
+      // last CTA out re-arms the launch's scheduler slot (every CTA has made its final claim by then)
+      if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; }
     }
     __syncwarp();
   } else if (warp == kEpiWarps + 2) {
@@ -288,10 +314,12 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         int bs = 0;
         uint32_t bph = 0;
         Trace tr(p.trace, 3);
-        const int tiles_b = p.b_stationary ? (my_tiles > 0 ? 1 : 0) : my_tiles;  // stationary: loaded once
-        for (int it = 0; it < tiles_b; ++it) {
+        for (int it = 0;; ++it) {
+          if (p.b_stationary && it > 0) break;   // stationary: the slice of the (only) filter tile is loaded once
+          const int tb = tile_of(it);
+          if (tb < 0) break;
           int n_tile;
-          fast_divmod(blockIdx.x + it * gridDim.x, p.n_tiles, p.rcp_n_tiles, n_tile);
+          fast_divmod(tb, p.n_tiles, p.rcp_n_tiles, n_tile);
           const int n0 = n_tile * BLOCK_N;
           for (int cc = 0; cc < p.c_chunks; ++cc) {
             int col = cc * 64;
@@ -315,18 +343,32 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (lane == 0) {
         Trace tr(p.trace, 4);
         const int S = p.stg_bufs;
-        const int total_vt = my_tiles * MT;
         int sb = 0;
         uint32_t ph = 0;
+        // residual prefetch walks the tile ring ahead of the stores: (rp_it, rp_h) = next sub-tile whose residual is
+        // still to be requested, rp_t its tile id (-1 = past the last tile)
+        int rp_it = 0, rp_h = 0, rp_t = p.has_res ? tile_of(0) : -1;
+        auto res_next = [&](int buffer) {
+          if (rp_t < 0) return;
+          issue_res(rp_t, rp_h, buffer);
+          if (++rp_h == MT) { rp_h = 0; rp_t = tile_of(++rp_it); }
+        };
         if (p.has_res)
-          for (int vt = 0; vt < S && vt < total_vt; ++vt) issue_res(vt, vt);
-        for (int vt = 0; vt < total_vt; ++vt) {
+          for (int i = 0; i < S; ++i) res_next(i);
+        int t_cur = -1;
+        for (int vt = 0;; ++vt) {
+          const int h = vt % MT;
+          if (h == 0) {
+            t_cur = tile_of(vt / MT);
+            if (t_cur < 0) break;
+          }
           mbar_wait(&staged[sb], ph, 30);
-          store_subtile(vt, sb);
+          store_subtile(t_cur, h, sb);
           tma_store_wait_read_n<0>();   // the store has left its staging buffer: hand the buffer on at once
           if (!p.has_res) mbar_arrive(&stg_free[sb]);
-          else if (vt + S < total_vt) issue_res(vt + S, sb);
+          else res_next(sb);
           tr.rec(24, vt);
+          if (h == MT - 1) *sched_done = vt / MT + 1;
           if (++sb == S) { sb = 0; ph ^= 1; }
         }
       }
@@ -347,7 +389,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       // are issued, so the ~180-cycle round trip of the barrier query hides behind the MMA issue instead of
       // sitting between every two k-chunks (ptx_sm100.cuh: mbar_test).
       bool a_ok = false, b_ok = false;   // stage (as / bs) already seen full by a look-ahead test
-      for (int it = 0; it < my_tiles; ++it) {
+      for (int it = 0;; ++it) {
+        if (tile_of(it) < 0) break;
         const int buf = it & 1;
         const uint32_t u = (uint32_t)(it >> 1);
         mbar_wait(&acc_empty[buf], (u & 1) ^ 1, 24);  // epilogue has drained this accumulator set
@@ -365,7 +408,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           int as_n = as + 1;
           uint32_t aph_n = aph;
           if (as_n == p.a_stages) { as_n = 0; aph_n ^= 1; }
-          const bool more_a = cc + 1 < p.c_chunks || it + 1 < my_tiles;
+          const bool more_a = true;   // (a look-ahead test past the last tile just never succeeds)
           for (int r = 0; r < rs; ++r, a_row += row_step) {
             uint32_t a_tap = a_row;
             for (int sx = 0; sx < rs; ++sx, a_tap += 128) {
@@ -379,7 +422,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               if (bs_n == p.b_stages) { bs_n = 0; bph_n ^= 1; }
               const bool last_tap = r == rs - 1 && sx == rs - 1;
               const bool last_of_tile = last_tap && cc == p.c_chunks - 1;
-              const bool wait_b_next = last_of_tile ? (!p.b_stationary && it + 1 < my_tiles) : wait_b;
+              const bool wait_b_next = last_of_tile ? !p.b_stationary : wait_b;
               lookahead_test_b(&b_full[bs_n], bph_n, wait_b_next);
               lookahead_test_a(&a_full[as_n], aph_n, last_tap && more_a);
 #pragma unroll
@@ -412,11 +455,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     Trace tr(threadIdx.x == 0 ? p.trace : nullptr, 2);
     int sb = 0;            // staging buffer of the next sub-tile
     uint32_t sph = 0;      // parity of this buffer's use count
-    for (int it = 0; it < my_tiles; ++it) {
+    for (int it = 0;; ++it) {
+      const int t_epi = tile_of(it);
+      if (t_epi < 0) break;
       const int buf = it & 1;
       const uint32_t u = (uint32_t)(it >> 1);
       int n_tile;
-      fast_divmod(blockIdx.x + it * gridDim.x, p.n_tiles, p.rcp_n_tiles, n_tile);
+      fast_divmod(t_epi, p.n_tiles, p.rcp_n_tiles, n_tile);
       const int n0 = n_tile * BLOCK_N;
       // this warp's folded-norm constants for the tile, fetched while the accumulators are still filling
       tr.rec(20, it);
@@ -605,6 +650,12 @@ int map_nd(EncodeTiledFn enc, CUtensorMap* m, const void* base, CUtensorMapDataT
 }
 
 long long* g_trace = nullptr;
+// Scheduler slots of the dynamic tile schedule: {next tile, finished CTAs} per launch, handed out round-robin (a slot
+// is re-armed to zero by the last CTA of its launch; 1024 launches later it is long idle).
+constexpr int kSchedSlots = 1024;
+__device__ int g_sched_mem[2 * kSchedSlots];
+int* g_sched = nullptr;
+unsigned g_sched_seq = 0;
 // Upper bound on the persistent grid (0 = one CTA per SM): leaving a few SMs free lets the short kernels of
 // concurrent graph branches (depth trunk, head) run beside the RGB trunk instead of queueing behind it.
 int g_cta_cap = -1;
@@ -684,6 +735,13 @@ int launch(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, 
   }
   p.a_stages = as; p.b_stages = bs; p.stg_bufs = sbufs;
   p.trace = g_trace;
+  if (g_sched == nullptr) {
+    void* ptr = nullptr;
+    cudaError_t e = cudaGetSymbolAddress(&ptr, g_sched_mem);
+    if (e != cudaSuccess) return cuda_status(e, "cudaGetSymbolAddress(conv_tma scheduler)");
+    g_sched = reinterpret_cast<int*>(ptr);
+  }
+  p.sched = g_sched + 2 * (g_sched_seq++ % kSchedSlots);
   p.rcp_n_tiles = 1.0f / (float)p.n_tiles;
   p.rcp_tiles_x = 1.0f / (float)p.tiles_x;
   p.rcp_tiles_y = 1.0f / (float)p.tiles_y;

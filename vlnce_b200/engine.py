@@ -46,8 +46,12 @@ def gemm_workspace(nbytes: int = 16 << 20):
 # queued and issued as ONE ``vlnce_sgemm_grouped`` launch when the outermost group closes.  Only problems that do
 # not depend on each other may share a group (the launch plans below mark those regions by hand).
 _PENDING = None  # list of problem tuples while a group is open
-# VLNCE_GEMM_GROUPS=0: every GEMM is its own launch again (A/B switch for measurements and bisection)
-GROUPING = __import__("os").environ.get("VLNCE_GEMM_GROUPS", "1") != "0"
+# VLNCE_GEMM_GROUPS=1 turns the grouping on.  It is OFF by default because it was measured, not because it is
+# unfinished: alone the grouped head is 59 C-ABI calls instead of 148 and ~0.3 ms shorter when its kernels run one
+# after the other, but in the pipelined training step the conv trunks of the next batch are the critical path
+# (tools/timeline_probe.py) and the step came out 0.03-0.05 ms (1-2 %) slower in three A/B runs on the B200 — bigger
+# head launches displace more conv CTAs at once.  Both settings are covered by the GPU tests.
+GROUPING = __import__("os").environ.get("VLNCE_GEMM_GROUPS", "0") != "0"
 # VLNCE_DEFER_LEAVES=0: weight / bias gradients run on a side stream next to the dX chain (one launch each) instead of
 # being collected into one grouped launch at the end of the backward
 DEFER_LEAVES = __import__("os").environ.get("VLNCE_DEFER_LEAVES", "1") != "0"
