@@ -96,6 +96,12 @@ int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scal
 /* Debug aid of the persistent conv tiles: a device buffer of 5*768*2 int64 that CTA 0 of every later
  * vlnce_conv_tma / vlnce_conv_stem_tma launch fills with per-role (event, clock64) records; NULL = off. */
 /* cap on the persistent conv_tma grid (0 = one CTA per SM; default: environment VLNCE_TMA_CTA_CAP) */
+/* Stride-2 convolutions, R = 1 (pad 0: ResNet downsample branches) or R = 3 (pad 1: conv2 of a stage's first block) —
+ * torchvision Bottleneck behind resnet_encoders.py:194-199: x (N,H,W,C) -> y (N,H/2,W/2,K) with the folded-norm epilogue
+ * of vlnce_conv_tma.  The activation operand is a TMA box with element strides {1,2,2,1} (only the sampled pixels are
+ * loaded; a 3x3 is nine tap-shifted boxes per channel chunk).  H, W even, (W/2) % 8 == 0; block_n as vlnce_conv_tma. */
+int vlnce_conv_s2_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift, void* y,
+                      int y_dtype, int N, int H, int W, int C, int K, int R, int relu, int block_n, cudaStream_t stream);
 int vlnce_set_tma_cta_cap(int cap);
 int vlnce_debug_set_trace(void* buffer);
 /* rows of the instruction batch per CTA of the persistent LSTM kernels: 1 (default) | 4; 0 = back to the default /

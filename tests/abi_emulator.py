@@ -961,6 +961,9 @@ class TensorCoreOps:
     def conv_tma(self, x, w, ab, scale, shift, residual, y, y_dtype, N, H, W, C, K, R, relu, code, st):
         self.conv2d_bf16(x, w, ab, scale, shift, residual, y, y_dtype, N, H, W, C, K, R, R, 1, R // 2, relu, code, st)
 
+    def conv_s2_tma(self, x, w, ab, scale, shift, y, y_dtype, N, H, W, C, K, R, relu, code, st):
+        self.conv2d_bf16(x, w, ab, scale, shift, 0, y, y_dtype, N, H, W, C, K, R, R, 2, R // 2, relu, code, st)
+
     def conv3x3_halo(self, x, w, ab, scale, shift, residual, y, y_dtype, N, H, W, C, K, relu, code, st):
         self.conv2d_bf16(x, w, ab, scale, shift, residual, y, y_dtype, N, H, W, C, K, 3, 3, 1, 1, relu, code, st)
 

@@ -209,6 +209,42 @@ def test_conv_tma_persistent_matches_reference(case, half, flags):
         assert err <= tol * max(want.abs().max().item(), 1.0), f"{case} {y_dtype}: max err {err}"
 
 
+S2_CASES = [
+    # n, h, w, c, k, block_n, R   (stride-2 convs through the strided-box TMA mode: 1x1 downsample, 3x3 pad 1)
+    (2, 32, 32, 64, 128, 0, 1),        # out 16x16: one image per tile, bh = 16
+    (64, 64, 64, 256, 512, 128, 1),    # ResNet-50 layer2 downsample at the benchmark batch: 512 tiles x 4 filter tiles
+    (4, 16, 16, 128, 256, 256, 1),     # out 8x8: two images per tile
+    (16, 8, 16, 64, 64, 64, 1),        # out 4x8: four images per tile
+    (6, 32, 16, 1024, 2048, 128, 1),   # long K loop, wide N, non-square
+    (2, 32, 32, 64, 64, 0, 3),         # 3x3: nine tap-shifted boxes, zero-filled borders
+    (24, 64, 64, 128, 128, 128, 3),    # ResNet-50 layer2 conv2 (stride 2): persistent, 18 K chunks
+    (4, 16, 16, 512, 512, 256, 3),     # layer4 conv2: out 8x8, two images per tile, 72 K chunks
+    (8, 8, 16, 64, 128, 64, 3),        # out 4x8: four images per tile (taps cross image boundaries -> zeros)
+]
+
+
+@pytest.mark.parametrize("flags", [0, MT2, NOSTAT], ids=["auto", "mt2", "stream"])
+@pytest.mark.parametrize("half", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", S2_CASES, ids=[str(c) for c in S2_CASES])
+def test_conv_s2_tma_matches_reference(case, half, flags):
+    n, h, w, c, k, code, r = case
+    g = torch.Generator(device="cpu").manual_seed(sum(case[:5]))
+    x = torch.randn(n, h, w, c, generator=g).to(DEV).to(half)
+    wt = (torch.randn(k, r, r, c, generator=g) * (2.0 / (r * r * c)) ** 0.5).to(DEV).to(half)
+    scale = (torch.rand(k, generator=g) + 0.5).to(DEV)
+    shift = torch.randn(k, generator=g).to(DEV) * 0.1
+    want = _ref_conv(x, wt, scale, shift, None, 2, r // 2, False)
+    for y_dtype in (half, torch.float32):
+        y = torch.full((n, h // 2, w // 2, k), float("nan"), device=DEV, dtype=y_dtype)
+        C.vlnce_conv_s2_tma(ptr(x), ptr(wt), lib.code(x), ptr(scale), ptr(shift), ptr(y), lib.code(y), n, h, w, c, k, r, 0,
+                            code | flags, lib.stream())
+        torch.cuda.synchronize()
+        tol = {torch.bfloat16: 2e-2, torch.float16: 3e-3, torch.float32: 2e-3}[y_dtype]
+        err = (y.float() - want).abs().max().item()
+        assert torch.isfinite(y.float()).all(), f"non-finite output ({y_dtype})"
+        assert err <= tol * max(want.abs().max().item(), 1.0), f"{case} {y_dtype}: max err {err}"
+
+
 @pytest.mark.parametrize("flags", [0, MT2, NOSTAT | MT2], ids=["auto", "mt2", "mt2-stream"])
 @pytest.mark.parametrize("hw", [40, 224, 256])
 @pytest.mark.parametrize("img_dtype", [torch.uint8, torch.float32])

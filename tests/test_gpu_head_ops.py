@@ -84,7 +84,7 @@ def test_sgemm_grouped_matches_torch_and_is_deterministic():
         torch.testing.assert_close(o, a @ w1[i:i + 8, :40].t(), rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("dirs,R,nr", [(1, 5, 1), (2, 5, 1), (2, 21, 4), (1, 64, 4), (2, 21, 1)])
+@pytest.mark.parametrize("dirs,R,nr", [(1, 5, 1), (2, 5, 1), (2, 21, 4), (1, 64, 4), (2, 21, 1), (2, 21, 2)])
 def test_lstm_matches_packed_torch(dirs, R, nr):
     """Persistent (bi)LSTM forward AND backward-through-time against torch.nn.LSTM on a packed ragged batch (CPU fp32
     autograd), with one row per CTA (the default) and with four rows per CTA (``vlnce_set_lstm_rows(4)``; R = 21 has a

@@ -117,6 +117,26 @@ def main():
                     us = a.elapsed_time(b) * 1e3 / args.reps
                     row["bn"][f"P{bn}{tag}"] = {"us": round(us, 1), "tflops": round(flops / us / 1e6, 1),
                                                "min_traffic_gbs": round(bytes_min / us / 1e3, 0)}
+        if stride == 2 and cin % 64 == 0 and cout % 64 == 0 and (hw // 2) % 8 == 0 and args.bn < 0:
+            MT2, NOSTAT = 1 << 21, 1 << 22
+            for bn in [b for b in (64, 128, 256) if cout % b == 0]:
+                for tag, fl in (("", NOSTAT), ("s", 0), ("m", MT2 | NOSTAT)):
+                    if "m" in tag and bn == 256:
+                        continue
+                    def launch():
+                        C.vlnce_conv_s2_tma(ptr(x), ptr(w), lib.BF16, ptr(scale), ptr(shift), ptr(y), lib.BF16, n, hw, hw,
+                                            cin, cout, r, 1, bn | (4 << 16) | fl, lib.stream())
+                    for _ in range(3):
+                        launch()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(args.reps):
+                        launch()
+                    b.record()
+                    b.synchronize()
+                    us = a.elapsed_time(b) * 1e3 / args.reps
+                    row["bn"][f"S{bn}{tag}"] = {"us": round(us, 1), "tflops": round(flops / us / 1e6, 1),
+                                               "min_traffic_gbs": round(bytes_min / us / 1e3, 0)}
         best = min(row["bn"].items(), key=lambda kv: kv[1]["us"])
         row["best_bn"], row["best_us"] = best[0], best[1]["us"]
         total_best += best[1]["us"] * count

@@ -39,17 +39,40 @@ def launches(src, dst, note=""):
         a[1] += us
         tot += us
         n += 1
-    conv = sum(us for k, (_, us) in agg.items() if k.startswith("conv_"))
+    conv = sum(us for k, (_, us) in agg.items() if k.startswith("conv") or k.startswith("depth_fused"))
+    # DRAM traffic of the same launches (when the pass also collected dram__bytes_*): mean per conv-class launch ->
+    # profiles/conv_traffic.json, the source of bench.py's roofline.traffic
+    dram, ids = collections.defaultdict(float), {}
+    for r in rows:
+        if r["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            unit = r["Metric Unit"].lower()
+            scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+            dram[r["ID"]] += float(r["Metric Value"]) * scale
+            ids[r["ID"]] = short(r["Kernel Name"])
+    conv_ids = [i for i, k in ids.items() if k.startswith("conv") or k.startswith("depth_fused")]
+    if conv_ids:
+        import json
+        import os
+
+        mean = sum(dram[i] for i in conv_ids) / len(conv_ids)
+        json.dump({"kernel": "tcgen05 conv-class launches of one eager training step (conv_tma / conv_umma / "
+                             "conv3x3_halo / depth_fused), " + os.path.basename(dst),
+                   "launches": len(conv_ids), "dram_bytes_per_launch": mean,
+                   "dram_bytes_per_step": sum(dram[i] for i in conv_ids),
+                   "note": "mean of dram__bytes_read.sum + dram__bytes_write.sum over exactly the launches whose "
+                           "algorithmic bytes bench.py sums (same pass as the launch list; serial launches, caches warm "
+                           "from the producing layer)"},
+                  open(os.path.join(os.path.dirname(dst), "conv_traffic.json"), "w"), indent=1)
     with open(dst, "w") as f:
         f.write("# launch list of one training step (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n")
-        f.write("Command: `ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv "
+        f.write("Command: `ncu --profile-from-start off --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --clock-control none --csv "
                 "python bench.py --ncu-step --no-cpu-baseline` (one eager, serial-stream step between "
                 "cudaProfilerStart/Stop; B200, batch 64, bf16/fp16 trunks).  Cold-cache serialised launch times: "
                 "compare SHARES, not absolutes.\n" + note + "\n")
         f.write(f"One step = {n} launches, {tot:.0f} us summed device time.\n\n| kernel | launches | us | share |\n|---|---:|---:|---:|\n")
         for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {c} | {us:.1f} | {100 * us / tot:.1f}% |\n")
-        f.write(f"\ntcgen05 conv tiles (`conv_tma_kernel` + `conv_umma_kernel`, all shapes): {conv:.0f} us = "
+        f.write(f"\ntcgen05 conv tiles (`conv_tma_kernel` + `conv_umma_kernel` + `conv3x3_halo_kernel` + `depth_fused_kernel`): {conv:.0f} us = "
                 f"{100 * conv / tot:.1f}% of the step (bench.py's live CUDA-event measurement of the same launches: "
                 "`roofline.conv_ms_per_step`).\n")
 

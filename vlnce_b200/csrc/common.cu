@@ -56,13 +56,13 @@ int lstm_rows_per_cta(int R) {
   int v = g_lstm_rows.load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = getenv("VLNCE_LSTM_NR");
-    v = (e != nullptr && (e[0] == '1' || e[0] == '4') && e[1] == 0) ? e[0] - '0' : 0;
+    v = (e != nullptr && (e[0] == '1' || e[0] == '2' || e[0] == '4') && e[1] == 0) ? e[0] - '0' : 0;
     g_lstm_rows.store(v, std::memory_order_relaxed);
   }
   (void)R;
-  return v == 4 ? 4 : 1;
+  return (v == 4 || v == 2) ? v : 1;
 }
-void set_lstm_rows(int nr) { g_lstm_rows.store(nr == 4 ? 4 : (nr == 1 ? 1 : 0), std::memory_order_relaxed); }
+void set_lstm_rows(int nr) { g_lstm_rows.store((nr == 4 || nr == 2 || nr == 1) ? nr : 0, std::memory_order_relaxed); }
 
 }  // namespace vlnce
 

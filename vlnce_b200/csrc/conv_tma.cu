@@ -56,7 +56,12 @@ constexpr int kMaxA = 8, kMaxB = 18;
 struct TmaConvParams {
   const float* scale;
   const float* shift;
-  int mode;        // 0 rows (1x1), 1 halo (3x3), 2 stem (s2d 4x4, chunk = cell row)
+  int mode;        // 0 rows (1x1), 1 halo (3x3), 2 stem (s2d 4x4, chunk = cell row), 3 strided 1x1 (stride 2: the TMA box
+                   //   walks the input with element strides {1,2,2,1}, so only the sampled pixels are ever loaded)
+  int img_per_tile;  // mode 3: images per 128-pixel tile (small outputs: 8x8 -> 2 images)
+  int cpt;           // mode 3: 64-channel chunks per filter tap (K chunk q = tap * cpt + channel chunk); taps_s2 = 1 | 9
+  int taps_s2;
+  float rcp_cpt;
   int M;           // rows mode: N*H*W
   int N, H, W, C, K;
   int c_chunks, n_tiles, m_tiles, tiles_x, tiles_y;
@@ -139,7 +144,7 @@ __device__ __forceinline__ Tile decode_tile(const TmaConvParams& p, int t, int b
   ti.m0 = m * 128;
   m = fast_divmod(m, p.tiles_x, p.rcp_tiles_x, xi);
   ti.x0 = xi * p.tw;
-  ti.img = fast_divmod(m, p.tiles_y, p.rcp_tiles_y, yi);
+  ti.img = fast_divmod(m, p.tiles_y, p.rcp_tiles_y, yi) * p.img_per_tile;
   ti.y0 = yi * p.th;
   return ti;
 }
@@ -296,6 +301,14 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             const uint32_t dst = smem_a0 + as * a_slot + h * p.a_bytes;
             if (p.mode == 0) tma_load_2d(dst, &tmap_x, &a_full[as], cc * 64, ti[h].m0);
             else if (p.mode == 1) tma_load_4d(dst, &tmap_x, &a_full[as], cc * 64, ti[h].x0 - 1, ti[h].y0 - 1, ti[h].img);
+            else if (p.mode == 3) {
+              // K chunk cc = (tap, channel chunk); a 3x3 tap (r, s) samples the input at (2y + r - 1, 2x + s - 1):
+              // the same strided box, shifted — pixels left of / above the image arrive as zeros
+              int ch, dx = 0, dy = 0;
+              const int tap = fast_divmod(cc, p.cpt, p.rcp_cpt, ch);
+              if (p.taps_s2 == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
+              tma_load_4d(dst, &tmap_x, &a_full[as], ch * 64, 2 * ti[h].x0 + dx, 2 * ti[h].y0 + dy, ti[h].img);
+            }
             else tma_load_4d(dst, &tmap_x, &a_full[as], 0, ti[h].x0, ti[h].y0 + cc, ti[h].img);
           }
           tr.rec(3, it * p.c_chunks + cc);
@@ -638,8 +651,10 @@ EncodeTiledFn get_enc() {
 }
 
 int map_nd(EncodeTiledFn enc, CUtensorMap* m, const void* base, CUtensorMapDataType dt, int rank,
-           const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box, const char* what) {
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+           const cuuint64_t* gdim, const cuuint64_t* gstr, const cuuint32_t* box, const char* what,
+           const cuuint32_t* estr_in = nullptr) {
+  const cuuint32_t estr1[4] = {1, 1, 1, 1};
+  const cuuint32_t* estr = estr_in ? estr_in : estr1;
   CUresult r = enc(m, dt, rank, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -843,7 +858,7 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
       const cuuint32_t rb[2] = {64, 128};
       if ((rc = map_nd(enc, &tr, residual, dt16, 2, yd, rs, rb, "residual")) != VLNCE_OK) return rc;
     }
-    p.mode = 0; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024;
+    p.mode = 0; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1;
     p.m_tiles = cdiv(M, 128); p.tiles_x = 1; p.tiles_y = 1; p.tw = 128; p.th = 1;
   } else {
     const cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -862,7 +877,7 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
       const cuuint32_t rb[4] = {64, TW, TH, 1};
       if ((rc = map_nd(enc, &tr, residual, dt16, 4, yd, rs, rb, "residual")) != VLNCE_OK) return rc;
     }
-    p.mode = 1; p.taps = 9; p.halo_w = TW + 2; p.a_bytes = 23 * 1024; p.a_tx = (TW + 2) * (TH + 2) * 128;
+    p.mode = 1; p.taps = 9; p.halo_w = TW + 2; p.a_bytes = 23 * 1024; p.a_tx = (TW + 2) * (TH + 2) * 128; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1;
     p.tiles_x = W / TW; p.tiles_y = H / TH; p.m_tiles = N * p.tiles_x * p.tiles_y; p.tw = TW; p.th = TH;
   }
   p.scale = scale; p.shift = shift;
@@ -873,6 +888,79 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
   p.relu = relu; p.y_fp32 = f32; p.ab_half = (ab_dtype == VLNCE_F16); p.has_res = residual != nullptr;
   p.a_stages = p.b_stages = p.stg_bufs = 0; p.b_stationary = 0;
   return dispatch(bn, mt, tx, tw, ty, tr, p, b_stages, no_stationary, stream);
+}
+
+// Stride-2 convolutions, 1x1 pad 0 (the ResNet downsample branches) and 3x3 pad 1 (the first block of a stage):
+// x (N,H,W,C) -> y (N,H/2,W/2,K).  Every activation tile is ONE 4-D TMA box with element strides {1,2,2,1}: 128 sampled
+// pixels x 64 channels land as a plain K-major tile; the 1x1 never loads the three quarters of the input it does not
+// read, the 3x3 is nine such boxes per channel chunk, shifted by the tap (im2col by tensor map, borders zero-filled by
+// the TMA unit).  A tile is 8 x bh output pixels of 128/(8*bh) images (bh = min(16, H/2)).  Needs H, W even,
+// (W/2) % 8 == 0, (H/2) % bh == 0, N % images-per-tile == 0.
+extern "C" int vlnce_conv_s2_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
+                                 void* y, int y_dtype, int N, int H, int W, int C, int K, int R, int relu, int block_n,
+                                 cudaStream_t stream) {
+  VLNCE_CHECK_ARG(R == 1 || R == 3, "conv_s2_tma: 1x1 or 3x3");
+  VLNCE_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0, "conv_s2_tma: null tensor / empty shape");
+  VLNCE_CHECK_ARG(C % 64 == 0 && K % 64 == 0, "conv_s2_tma: C and K must be multiples of 64");
+  VLNCE_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "conv_s2_tma: even input size");
+  VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_s2_tma: scale/shift must come together");
+  VLNCE_CHECK_ARG(ab_dtype == VLNCE_BF16 || ab_dtype == VLNCE_F16, "conv_s2_tma: operand dtype");
+  VLNCE_CHECK_ARG(y_dtype == ab_dtype || y_dtype == VLNCE_F32, "conv_s2_tma: y dtype");
+  const int P = H / 2, Q = W / 2;
+  const int bh = P >= 16 ? 16 : P;
+  VLNCE_CHECK_ARG(Q % 8 == 0 && P % bh == 0 && 128 % (8 * bh) == 0, "conv_s2_tma: output %dx%d does not tile", P, Q);
+  const int ipt = 128 / (8 * bh);
+  VLNCE_CHECK_ARG(N % ipt == 0, "conv_s2_tma: %d images do not fill tiles of %d", N, ipt);
+  const int b_stages = (block_n >> 16) & 0xf;
+  const int mt = (block_n & VLNCE_TMA_MT2) ? 2 : 1;
+  const int no_stationary = (block_n & VLNCE_TMA_NO_STATIONARY) ? 1 : 0;
+  int bn = block_n & 0xffff;
+  if (bn == 0) bn = (K % 128 == 0) ? 128 : 64;
+  VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && K % bn == 0, "conv_s2_tma: block_n=%d vs K=%d", bn, K);
+  while (bn > 64 && 2 * 16 * 1024 * mt + 2 * bn * 128 + 2048 + 128 * bn * (y_dtype == VLNCE_F32 ? 4 : 2) > kSmemBudget) bn /= 2;
+  EncodeTiledFn enc = get_enc();
+  if (!enc) {
+    set_error("conv_s2_tma: cuTensorMapEncodeTiled unavailable");
+    return VLNCE_ERR_NO_DRIVER;
+  }
+  const CUtensorMapDataType dt16 = ab_dtype == VLNCE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const bool f32 = y_dtype == VLNCE_F32;
+  CUtensorMap tx, tw, ty;
+  int rc;
+  {  // weights [K, R*R*C]
+    const cuuint64_t gd[2] = {(cuuint64_t)R * R * C, (cuuint64_t)K};
+    const cuuint64_t gs[1] = {(cuuint64_t)R * R * C * 2};
+    const cuuint32_t bx[2] = {64, (cuuint32_t)bn};
+    if ((rc = map_nd(enc, &tw, w, dt16, 2, gd, gs, bx, "weights")) != VLNCE_OK) return rc;
+  }
+  {  // input, sampled with stride 2 in W and H: the box spans 16 x 2*bh pixels and keeps every second one
+    const cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t gs[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t bx[4] = {64, 16, (cuuint32_t)(2 * bh), (cuuint32_t)ipt};
+    const cuuint32_t es[4] = {1, 2, 2, 1};
+    if ((rc = map_nd(enc, &tx, x, dt16, 4, gd, gs, bx, "strided input", es)) != VLNCE_OK) return rc;
+  }
+  {
+    const int esz = f32 ? 4 : 2;
+    const cuuint64_t yd[4] = {(cuuint64_t)K, (cuuint64_t)Q, (cuuint64_t)P, (cuuint64_t)N};
+    const cuuint64_t ys[3] = {(cuuint64_t)K * esz, (cuuint64_t)Q * K * esz, (cuuint64_t)P * Q * K * esz};
+    const cuuint32_t yb[4] = {(cuuint32_t)(f32 ? 32 : 64), 8, (cuuint32_t)bh, (cuuint32_t)ipt};
+    if ((rc = map_nd(enc, &ty, y, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt16, 4, yd, ys, yb, "output")) != VLNCE_OK)
+      return rc;
+  }
+  TmaConvParams p;
+  p.mode = 3; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024; p.img_per_tile = ipt;
+  p.cpt = C / 64; p.rcp_cpt = 1.0f / (float)p.cpt; p.taps_s2 = R * R;
+  p.tw = 8; p.th = bh;
+  p.tiles_x = Q / 8; p.tiles_y = P / bh; p.m_tiles = (N / ipt) * p.tiles_x * p.tiles_y;
+  p.scale = scale; p.shift = shift;
+  p.M = N * P * Q; p.N = N; p.H = P; p.W = Q; p.C = C; p.K = K;
+  p.c_chunks = R * R * C / 64;   // K chunks in the weight matrix's column order: tap-major, channel chunk minor
+  p.w_cols = C;
+  p.n_tiles = K / bn;
+  p.relu = relu; p.y_fp32 = f32; p.ab_half = (ab_dtype == VLNCE_F16); p.has_res = 0;
+  p.a_stages = p.b_stages = p.stg_bufs = 0; p.b_stationary = 0;
+  return dispatch(bn, mt, tx, tw, ty, ty, p, b_stages, no_stationary, stream);
 }
 
 // Debug: device buffer of 5 * 768 * 2 int64 that CTA 0 of every later conv_tma launch fills with
@@ -952,7 +1040,7 @@ extern "C" int vlnce_conv_stem_tma(const void* xs, const void* w, int ab_dtype, 
       return rc;
   }
   TmaConvParams p;
-  p.mode = 2; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024;
+  p.mode = 2; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1;
   p.tw = 128; p.th = 1;
   p.tiles_x = cdiv(Q, 128); p.tiles_y = P; p.m_tiles = N * p.tiles_x * p.tiles_y;
   p.scale = scale; p.shift = shift;

@@ -653,6 +653,7 @@ extern "C" int vlnce_lstm_seq_bwd(const float* dout, const float* gates, const f
   if (!configured) {
     const int big = (int)(sizeof(float) * ((size_t)(H_ / 2) * 4 * H_ + 4 * 8 * H_));
     e = cudaFuncSetAttribute(lstm_seq_bwd_kernel<H_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_seq_bwd_kernel<H_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_seq_bwd_kernel<H_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lstm_seq_bwd)");
     configured = true;
@@ -660,6 +661,9 @@ extern "C" int vlnce_lstm_seq_bwd(const float* dout, const float* gates, const f
   dim3 grid((R + nr - 1) / nr, dirs);
   if (nr == 4)
     lstm_seq_bwd_kernel<H_, 4><<<grid, 4 * H_, smem, stream>>>(dout, gates, cs, out, whh_f, whh_b, lengths, dgx, hprev,
+                                                             R, L, dirs);
+  else if (nr == 2)
+    lstm_seq_bwd_kernel<H_, 2><<<grid, 4 * H_, smem, stream>>>(dout, gates, cs, out, whh_f, whh_b, lengths, dgx, hprev,
                                                              R, L, dirs);
   else
     lstm_seq_bwd_kernel<H_, 1><<<grid, 4 * H_, smem, stream>>>(dout, gates, cs, out, whh_f, whh_b, lengths, dgx, hprev,

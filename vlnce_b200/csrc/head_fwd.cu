@@ -547,12 +547,16 @@ extern "C" int vlnce_lstm_seq_fwd(const float* gx, const float* whh_f, const flo
   if (!configured) {
     const int big = (int)(sizeof(float) * ((size_t)(H_ / 2) * 4 * H_ + 4 * 5 * H_));
     e = cudaFuncSetAttribute(lstm_seq_fwd_kernel<H_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_seq_fwd_kernel<H_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_seq_fwd_kernel<H_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lstm_seq_fwd)");
     configured = true;
   }
   if (nr == 4)
     lstm_seq_fwd_kernel<H_, 4><<<grid, 4 * H_, smem, stream>>>(gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save_gates,
+                                                             save_c, R, L, dirs);
+  else if (nr == 2)
+    lstm_seq_fwd_kernel<H_, 2><<<grid, 4 * H_, smem, stream>>>(gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save_gates,
                                                              save_c, R, L, dirs);
   else
     lstm_seq_fwd_kernel<H_, 1><<<grid, 4 * H_, smem, stream>>>(gx, whh_f, whh_b, bhh_f, bhh_b, lengths, out, hn, save_gates,

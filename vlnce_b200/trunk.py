@@ -70,6 +70,7 @@ MT2 = 1 << 21     # conv_tma flag: two pixel sub-tiles share each weight stage
 NOSTAT = 1 << 22  # conv_tma flag: do not keep the weight slice stationary in shared memory
 HALO = 1 << 24  # tuning-code flag: TMA-halo 3x3 kernel instead of the generic tile
 TMAP = 1 << 25  # tuning-code flag: persistent TMA-fed kernel (1x1 rows / 3x3 halo, overlapped epilogue)
+S2TMA = 1 << 26  # tuning-code flag: stride-2 conv (1x1 / 3x3) through the strided-box TMA mode of the persistent kernel
 EXCL = 1 << 20  # launch flag understood by the conv entry points: one CTA per SM
 RGB_EXCLUSIVE = _os.environ.get("VLNCE_RGB_EXCLUSIVE", "0") != "0"
 # fp16 instead of fp32 raw conv output under GroupNorm (depth trunk): half the bytes of the statistics/apply passes
@@ -325,6 +326,9 @@ class ConvTrunk:
                 elif stem_rgb:
                     C.vlnce_conv2d_stem_rgb(ptr(x), lib.code(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift),
                                             ptr(y), lib.code(y), n, h, w, cv.K, int(relu), code, st)
+                elif code & S2TMA:
+                    C.vlnce_conv_s2_tma(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(y), lib.code(y),
+                                        n, h, w, c, cv.K, cv.R, int(relu), code & 0x6fffff, st)
                 elif code & TMAP:
                     C.vlnce_conv_tma(ptr(x), ptr(cv.w), lib.code(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y),
                                      lib.code(y), geom[0], geom[1], geom[2], geom[3], cv.K, geom[5], int(relu),
@@ -342,6 +346,12 @@ class ConvTrunk:
                            or (geom[5] == 3 and geom[8] == 1 and geom[1] % 16 == 0 and geom[2] % 8 == 0)))
             halo_ok = (HALO_3X3 and not stem_rgb and gemm_c is None and cv.R == 3 and cv.S == 3 and cv.stride == 1
                        and cv.pad == 1 and c % 64 == 0 and cv.K % 64 == 0 and h % 16 == 0 and w % 8 == 0)
+            s2_ok = False
+            if (PERSISTENT and not stem_rgb and not stem_s2d and gemm_c is None and residual is None
+                    and (cv.R, cv.S, cv.pad) in ((1, 1, 0), (3, 3, 1)) and cv.stride == 2 and c % 64 == 0 and cv.K % 64 == 0
+                    and h % 2 == 0 and w % 2 == 0 and (w // 2) % 8 == 0):
+                bh = min(16, h // 2)
+                s2_ok = (h // 2) % bh == 0 and 128 % (8 * bh) == 0 and n % (128 // (8 * bh)) == 0
             nb = _batch_bucket(n)
             if stem_s2d or stem_rgb:
                 gkey = (geom[0], nb) + tuple(geom[2:])
@@ -352,18 +362,19 @@ class ConvTrunk:
             key = (gkey, lib.code(y), residual is not None)
             bn = cv.block_n.get(key)
             if bn is None:
-                skey = repr((key, lib.code(cv.w), scale is not None, relu, halo_ok, tma_ok, self.exclusive))
+                skey = repr((key, lib.code(cv.w), scale is not None, relu, halo_ok, tma_ok, self.exclusive)
+                            + ((True,) if s2_ok else ()))   # (appended only when set: older table keys stay valid)
                 if skey in _TUNE_CACHE:
                     bn = int(_TUNE_CACHE[skey])
                 else:
                     tune = AUTOTUNE and x.is_cuda and not torch.cuda.is_current_stream_capturing()
                     if tune:
-                        bn = self._tune(launch, cv.K, halo_ok, tma_ok, stem_s2d)
+                        bn = self._tune(launch, cv.K, halo_ok, tma_ok, stem_s2d, s2_ok)
                         _tune_cache_put(skey, bn)
                     elif stem_s2d:
                         bn = 64 | MT2
                     else:
-                        bn = TMAP if tma_ok else (HALO if halo_ok else 0)
+                        bn = TMAP if tma_ok else (HALO if halo_ok else (S2TMA if s2_ok else 0))
                 cv.block_n[key] = bn
             launch(bn)
         else:
@@ -372,7 +383,7 @@ class ConvTrunk:
                                cv.stride, cv.pad, int(relu), st)
 
     @staticmethod
-    def _tune(launch, K, halo_ok=False, tma_ok=False, stem_s2d=False):
+    def _tune(launch, K, halo_ok=False, tma_ok=False, stem_s2d=False, s2_ok=False):
         """Pick kernel variant, output-tile width and ring depth empirically (once per layer
         shape): CUDA-event timing of the legal candidates on the real operands; the winner is
         cached on the layer."""
@@ -383,6 +394,9 @@ class ConvTrunk:
         if tma_ok:
             cands += [TMAP | bn | (4 << 16) | fl for bn in widths for fl in (0, NOSTAT)]
             cands += [TMAP | bn | (4 << 16) | MT2 | fl for bn in widths if bn <= 128 for fl in (0, NOSTAT)]
+        if s2_ok:
+            cands += [S2TMA | bn | (4 << 16) | fl for bn in widths for fl in (0, NOSTAT)]
+            cands += [S2TMA | bn | (4 << 16) | MT2 | fl for bn in widths if bn <= 128 for fl in (0, NOSTAT)]
         if stem_s2d:  # only the persistent TMA kernel runs this geometry
             cands = [bn | (4 << 16) | fl for bn in widths if bn <= 128 for fl in (0, MT2, NOSTAT, MT2 | NOSTAT)]
         best, best_t = 0, float("inf")
