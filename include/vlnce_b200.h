@@ -74,9 +74,12 @@ int vlnce_conv2d_stem_rgb(const void* x, int x_dtype, const void* w, int ab_dtyp
                           int block_n, cudaStream_t stream);
 
 /* Persistent, fully TMA-fed tiles for stride-1 convolutions (R = 1: 1x1 pad 0 over the [M,C] row
- * matrix; R = 3: 3x3 pad 1 with halo boxes, needs H % 16 == 0 and W % 8 == 0): one CTA per SM walks a
- * static tile schedule, the epilogue of tile i-1 overlaps the accumulation of tile i (two TMEM
+ * matrix; R = 3: 3x3 pad 1 with halo boxes, needs H % 16 == 0 and W % 8 == 0): one CTA per SM claims
+ * tiles from a per-launch counter, the epilogue of tile i-1 overlaps the accumulation of tile i (two TMEM
  * accumulators).  C % 64 == 0, K % 64 == 0; same epilogue contract as vlnce_conv2d_bf16.
+ * ab_dtype VLNCE_F32 selects the fp32-storage mode: x, w, residual and y are fp32, the products run on
+ * the tensor cores as TF32 (tcgen05 kind::tf32, fp32 accumulation) — what stock PyTorch / cuDNN do for
+ * fp32 convolutions on this GPU; C % 32 == 0 then.
  * block_n: 0 = auto, else width (64/128/256) | weight-ring depth << 16 | (1 << 21): two 128-pixel
  * sub-tiles per scheduled tile share every weight stage (halves the weight bytes per MAC pulled from
  * L2; needs an even tile count and width <= 128) | (1 << 22): never keep the CTA's weight slice
@@ -130,6 +133,14 @@ int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w_dtype, con
                      int y_dtype, int N, int H, int W, int C, int K, int R, int S, int stride,
                      int pad, int relu, cudaStream_t stream);
 
+/* fp32 NHWC / KRSC convolution on CUDA cores, warp-cooperative (lanes split the input channels, 8 pixels x 4
+ * filters per warp): the fallback of the tf32 mode for geometries the TMA tiles do not cover (4x4 images, sizes that
+ * are not multiples of 8).  Same epilogue contract as vlnce_conv2d_ref, fp32 tensors only; the summation order
+ * differs from vlnce_conv2d_ref (per-lane partial sums), so the fp32-exact mode does not use it. */
+int vlnce_conv2d_warp(const float* x, const float* w, const float* scale, const float* shift, const float* residual,
+                      float* y, int N, int H, int W, int C, int K, int R, int S, int stride, int pad, int relu,
+                      cudaStream_t stream);
+
 /* RGB stem operand: x (N,H,W,3) u8|f32 0..255 -> im2col rows (N*P*Q, 192) bf16|f16 of the 7x7/2
  * pad-3 window, K index (r*7+s)*3+c, zero padded 147..191 (resnet_encoders.py:182,198:
  * permute + /255 + conv1; the /255 and optional mean/std live in the folded scale/shift). */
@@ -178,7 +189,8 @@ int vlnce_groupnorm_stats(const void* x, int dtype, const float* gamma, const fl
                           int HW, int C, int groups, float eps, cudaStream_t stream);
 /* GroupNorm (+residual)(+ReLU) of the fp32 raw conv output in two launches: partial statistics,
  * then finalize+normalise (each CTA rebuilds its image's scale/shift from the partials).
- * scale/shift_scratch (N*C f32 each) are used only by the fallback path. */
+ * scale/shift_scratch (N*C f32 each) are used only by the fallback path.  relu: bit 0 = ReLU, bit 1 = round the
+ * output to the nearest TF32 value (fp32 activations that feed the kind::tf32 conv tiles, which would truncate). */
 int vlnce_groupnorm_fused(const float* x, const float* gamma, const float* beta, const void* residual, void* y,
                           int y_dtype, float* workspace, size_t workspace_bytes, float* scale_scratch,
                           float* shift_scratch, int N, int HW, int C, int groups, float eps, int relu,

@@ -853,6 +853,9 @@ class TrunkOps:
             out = out.clamp_min(0)
         _tt(y, (N, P, Q, K)).copy_(out.permute(0, 2, 3, 1).float())
 
+    def conv2d_warp(self, x, w, scale, shift, residual, y, N, H, W, C, K, R, S, stride, pad, relu, st):
+        self.conv2d_ref(x, 0, w, 0, scale, shift, residual, 0, y, 0, N, H, W, C, K, R, S, stride, pad, relu, st)
+
     def avgpool2x2(self, x, y, N, H, W, C, st):
         import torch.nn.functional as Fn
 
@@ -880,7 +883,7 @@ class TrunkOps:
         out = Fn.group_norm(xi, groups, _tt(gamma, (C,)).double(), _tt(beta, (C,)).double(), eps)
         if residual:
             out = out + _tt(residual, (N, HW, C)).double().permute(0, 2, 1)
-        if relu:
+        if relu & 1:   # bit 1 = round the output to TF32 (a no-op for the fp32 host model)
             out = out.clamp_min(0)
         _tt(y, (N, HW, C)).copy_(out.permute(0, 2, 1).float())
 
@@ -1035,7 +1038,7 @@ def _groupnorm_fused(self, x, gamma, beta, residual, y, y_dtype, ws, wsb, sc, sh
     out = Fn.group_norm(xi, groups, _tt(gamma, (C,)).double(), _tt(beta, (C,)).double(), eps)
     if residual:
         out = out + _tt16(residual, (N, HW, C), y_dtype).double().permute(0, 2, 1)
-    if relu:
+    if relu & 1:
         out = out.clamp_min(0)
     yt = _tt16(y, (N, HW, C), y_dtype)
     yt.copy_(out.permute(0, 2, 1).to(yt.dtype))

@@ -209,6 +209,88 @@ def test_conv_tma_persistent_matches_reference(case, half, flags):
         assert err <= tol * max(want.abs().max().item(), 1.0), f"{case} {y_dtype}: max err {err}"
 
 
+TF32_CASES = [
+    # n, h, w, c, k, R, stride, block_n, epilogue   (fp32 operands multiplied as TF32 by the persistent TMA kernel)
+    (2, 16, 16, 64, 64, 1, 1, 0, "affine_relu"),
+    (3, 12, 12, 96, 256, 1, 1, 128, "affine_res_relu"),     # 32-channel chunks (C = 96), ragged last tile, fp32 residual
+    (40, 16, 16, 256, 128, 1, 1, 64, "affine_res_relu"),    # persistent, multi-chunk
+    (3, 32, 32, 128, 128, 3, 1, 64, "affine_res_relu"),     # halo mode
+    (2, 16, 8, 256, 256, 3, 1, 128, "raw"),
+    (4, 32, 32, 64, 128, 1, 2, 0, "affine"),                # strided-box mode, 1x1
+    (4, 32, 32, 64, 64, 3, 2, 64, "affine_relu"),           # strided-box mode, 3x3
+    (4, 32, 32, 32, 32, 1, 1, 0, "raw"),                    # K = 32 on a 64-wide tile (depth trunk, first stage)
+    (4, 32, 32, 32, 32, 3, 1, 0, "raw"),
+    (6, 32, 32, 128, 32, 1, 1, 0, "raw"),
+    (8, 8, 8, 256, 256, 3, 1, 64, "affine_relu"),           # 8x8 images: two per tile, tap-shifted boxes
+]
+
+
+@pytest.mark.parametrize("flags", [0, MT2, NOSTAT], ids=["auto", "mt2", "stream"])
+@pytest.mark.parametrize("case", TF32_CASES, ids=[str(c) for c in TF32_CASES])
+def test_conv_tma_tf32_matches_reference(case, flags):
+    """fp32 storage / TF32 products (tcgen05 kind::tf32) vs the fp32 CUDA-core conv: TF32 rounds both operands to 10
+    mantissa bits (relative 2^-11 each), products accumulate in fp32 -> errors ~1e-3 of the output scale."""
+    n, h, w, c, k, r, stride, code, epi = case
+    g = torch.Generator(device="cpu").manual_seed(sum(case[:7]))
+    x = torch.randn(n, h, w, c, generator=g).to(DEV)
+    wt = (torch.randn(k, r, r, c, generator=g) * (2.0 / (r * r * c)) ** 0.5).to(DEV)
+    scale = shift = res = None
+    if "affine" in epi:
+        scale = (torch.rand(k, generator=g) + 0.5).to(DEV)
+        shift = torch.randn(k, generator=g).to(DEV) * 0.1
+    if "res" in epi:
+        res = torch.randn(n, h // stride, w // stride, k, generator=g).to(DEV)
+    relu = "relu" in epi
+    want = _ref_conv(x, wt, scale, shift, res, stride, r // 2, relu)
+    y = torch.full((n, h // stride, w // stride, k), float("nan"), device=DEV)
+    if stride == 1:
+        C.vlnce_conv_tma(ptr(x), ptr(wt), lib.F32, ptr(scale), ptr(shift), ptr(res), ptr(y), lib.F32, n, h, w, c, k, r,
+                         int(relu), code | flags, lib.stream())
+    else:
+        C.vlnce_conv_s2_tma(ptr(x), ptr(wt), lib.F32, ptr(scale), ptr(shift), ptr(y), lib.F32, n, h, w, c, k, r, int(relu),
+                            code | flags, lib.stream())
+    torch.cuda.synchronize()
+    err = (y - want).abs().max().item()
+    assert torch.isfinite(y).all(), "non-finite output"
+    assert err <= 3e-3 * max(want.abs().max().item(), 1.0), f"{case}: max err {err}"
+
+
+WARP_CASES = [
+    # n, h, w, c, k, R, stride, pad, epilogue   (fp32 warp-cooperative conv: the tf32 mode's fallback geometries)
+    (64, 4, 4, 256, 256, 3, 1, 1, "raw"),                   # depth layer4: 4x4 images
+    (64, 8, 8, 256, 256, 3, 2, 1, "raw"),
+    (6, 8, 8, 512, 1024, 1, 2, 0, "raw"),
+    (3, 7, 7, 96, 130, 3, 1, 1, "affine_res_relu"),         # C = 3 x 32, ragged filter and pixel tiles
+    (2, 14, 14, 64, 64, 1, 1, 0, "affine_relu"),
+    (1, 5, 3, 32, 2, 3, 1, 1, "affine"),                    # fewer filters than a warp's four
+]
+
+
+@pytest.mark.parametrize("case", WARP_CASES, ids=[str(c) for c in WARP_CASES])
+def test_conv2d_warp_matches_reference(case):
+    """fp32 products and sums on CUDA cores, per-lane partial sums (order differs from the one-thread reference conv)."""
+    n, h, w, c, k, r, stride, pad, epi = case
+    g = torch.Generator(device="cpu").manual_seed(sum(case[:8]))
+    x = torch.randn(n, h, w, c, generator=g).to(DEV)
+    wt = (torch.randn(k, r, r, c, generator=g) * (2.0 / (r * r * c)) ** 0.5).to(DEV)
+    p, q = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - r) // stride + 1
+    scale = shift = res = None
+    if "affine" in epi:
+        scale = (torch.rand(k, generator=g) + 0.5).to(DEV)
+        shift = torch.randn(k, generator=g).to(DEV) * 0.1
+    if "res" in epi:
+        res = torch.randn(n, p, q, k, generator=g).to(DEV)
+    relu = "relu" in epi
+    want = _ref_conv(x, wt, scale, shift, res, stride, pad, relu)
+    y = torch.full((n, p, q, k), float("nan"), device=DEV)
+    C.vlnce_conv2d_warp(ptr(x), ptr(wt), ptr(scale), ptr(shift), ptr(res), ptr(y), n, h, w, c, k, r, r, stride, pad,
+                        int(relu), lib.stream())
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all(), "non-finite output"
+    err = (y - want).abs().max().item()
+    assert err <= 2e-5 * max(want.abs().max().item(), 1.0), f"{case}: max err {err}"
+
+
 S2_CASES = [
     # n, h, w, c, k, block_n, R   (stride-2 convs through the strided-box TMA mode: 1x1 downsample, 3x3 pad 1)
     (2, 32, 32, 64, 128, 0, 1),        # out 16x16: one image per tile, bh = 16

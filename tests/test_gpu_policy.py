@@ -31,7 +31,11 @@ def cuda_policy(case, precision):
     return pol
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])   # north_star: 1e-3 fp32 / 1e-2 16-bit
+# north_star: 1e-3 fp32 / 1e-2 16-bit; "tf32" = fp32 storage with TF32 tensor-core products (what the stock reference's
+# cuDNN convolutions do on a GPU).  TF32 keeps 10 explicit mantissa bits, exactly fp16's, so the mode belongs to the
+# reduced-precision class and carries its 1e-2 bound (measured on the B200: RGB trunk 6.7e-4, depth trunk 5.0e-3 — the
+# same as the fp16 depth trunk —, probabilities 1.1e-6 .. 5.1e-3, hidden state 1.1e-3 .. 4.5e-3)
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2), ("tf32", 1e-2)])
 def test_trunks_match_oracle(precision, tol):
     case = cases.CASES["cma_act"]
     opol = cases.build_policy(oracle_vlnce, case).eval()
@@ -59,7 +63,7 @@ SHARP = ("cma_act_sharp", "seq2seq_act_sharp", "cma_rxr_act_l512")   # trained-l
 
 @pytest.mark.parametrize("name", ["cma_act", "cma_act_rgb224", "cma_act_bntrain", "cma_rxr_act", "cma_act_sharp",
                                   "cma_rxr_act_l512"])
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 1e-2), ("tf32", 1e-2)])
 def test_cma_act_matches_golden(name, precision, tol):
     case = cases.CASES[name]
     gold = torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)

@@ -419,6 +419,24 @@ def test_pixel_paths_fp32_match_golden(name):
     print(name, "worst", check(got, gold(name), 3e-4))
 
 
+@pytest.mark.parametrize("name", ["cma_act", "seq2seq_act", "cma_act_rgb224"])
+def test_pixel_paths_tf32_routing_matches_golden(name):
+    """``precision="tf32"``: fp32 storage, every stride-1 1x1 / 3x3 and stride-2 layer the persistent TMA kernel covers
+    goes through ``vlnce_conv_tma`` / ``vlnce_conv_s2_tma`` with fp32 operands, the RGB stem through the fp16 s2d path
+    with fp32 output.  The host model multiplies in exact fp32 but sees the same packed operands as the GPU (weights
+    rounded to TF32 once, fp16 stem weights), so this checks the routing, the fp32 residual path and the per-layer
+    GroupNorm depth path at the mode's own tolerance (measured on the B200: hidden state 7e-4..1e-3)."""
+    with lib.dry_run(executor=Emulator()) as rec:
+        got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, precision="tf32")
+    assert rec.calls.count("vlnce_conv_tma") > 60 and "vlnce_conv_stem_tma" in rec.calls
+    # what the TMA tiles do not cover at this batch (4x4 images, image counts that do not fill a tile) runs on the
+    # warp-cooperative fp32 conv, never on the one-thread-per-output reference conv
+    assert "vlnce_conv2d_warp" in rec.calls and "vlnce_conv2d_ref" not in rec.calls
+    if name != "cma_act_rgb224":
+        assert "vlnce_conv_s2_tma" in rec.calls
+    print(name, "tf32 routing worst", check(got, gold(name), 3e-3))
+
+
 @pytest.mark.parametrize("name", ["wp_act", "wp_act_nrgb"])
 def test_waypoint_pixel_path_fp32_matches_golden(name):
     """WaypointPolicy.act from raw pano pixels (ResNet-18 + DD-PPO ResNet-50 over the stacked frames), no trunk

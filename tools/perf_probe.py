@@ -46,7 +46,28 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--caps", default="0", help="comma-separated persistent-grid caps for conv_tma (0 = none)")
     ap.add_argument("--chunks", default="", help="comma-separated depth-trunk chunk counts to sweep")
+    ap.add_argument("--trunks-only", default="", help="precision (bf16 | tf32 | fp32): time the two trunks in that mode and exit")
     args = ap.parse_args()
+    if args.trunks_only:
+        prec = args.trunks_only
+        n = 64
+        pol = synth.build_cma_policy().cuda().eval()
+        pol.net.precision = prec
+        obs = {"rgb": torch.randint(0, 256, (n, 256, 256, 3), dtype=torch.uint8, device="cuda"),
+               "depth": torch.rand(n, 256, 256, 1, device="cuda")}
+        o1, o2 = torch.zeros(n, 16, 2112, device="cuda"), torch.zeros(n, 16, 192, device="cuda")
+        pol.net.rgb_encoder.features_into(obs, o1, 2112, prec)
+        pol.net.depth_encoder.features_into(obs, o2, 192, prec)
+        torch.cuda.synchronize()
+        res = {"precision": prec,
+               "rgb_trunk_ms": graph_time(lambda: pol.net.rgb_encoder.features_into(obs, o1, 2112, prec), iters=10),
+               "depth_trunk_ms": graph_time(lambda: pol.net.depth_encoder.features_into(obs, o2, 192, prec), iters=10)}
+        with lib.profile() as prof:
+            pol.net.rgb_encoder.features_into(obs, o1, 2112, prec)
+            pol.net.depth_encoder.features_into(obs, o2, 192, prec)
+        res["calls"] = {k: {"calls": v["calls"], "us": round(v["us"], 1)} for k, v in list(prof.summary().items())[:6]}
+        print(json.dumps(res))
+        return
     n = 64
     case = dict(cases.CASES["cma_train_pixels"], t=1, n=n)
     pol = cases.build_policy(vlnce_b200, case).cuda().eval()

@@ -61,6 +61,7 @@ struct TmaConvParams {
   int img_per_tile;  // mode 3: images per 128-pixel tile (small outputs: 8x8 -> 2 images)
   int cpt;           // mode 3: 64-channel chunks per filter tap (K chunk q = tap * cpt + channel chunk); taps_s2 = 1 | 9
   int taps_s2;
+  int box_stride;    // mode 3: 2 (stride-2 convs) | 1 (3x3 stride 1 on images too small for the halo tiles)
   float rcp_cpt;
   int M;           // rows mode: N*H*W
   int N, H, W, C, K;
@@ -77,6 +78,8 @@ struct TmaConvParams {
   int a_tx;
   int a_stages, b_stages, stg_bufs;
   int relu, y_fp32, ab_half, has_res;
+  int tf32;        // 1: fp32 operands multiplied as TF32 (kind::tf32); a K chunk is then 32 channels (128 bytes)
+  int kc;          // channels per K chunk: 64 (16-bit operands) | 32 (tf32)
 };
 
 __device__ __forceinline__ void tma_store_4d_(const void* tmap, uint32_t src_smem, int32_t c0, int32_t c1, int32_t c2,
@@ -201,7 +204,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint64_t* sched_full = staged + kMaxStg;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_full + kSchedRing);
   volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_slot + 1);   // kSchedRing tile ids (-1 = no more tiles)
-  volatile int* sched_done = sched_tile + kSchedRing;                          // tiles the store issuer has finished
+  int* sched_done = const_cast<int*>(sched_tile) + kSchedRing;                 // tiles the store issuer has finished
+                                                                               // (one writer, one reader, atomics)
   const uint32_t stg_bytes = 128u * BLOCK_N * (p.y_fp32 ? 4u : 2u);
   const uint32_t stage_out = smem_b0 + p.b_stages * B_BYTES + 1024;
 
@@ -252,11 +256,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   // been read); TMA store of the staged sub-tile vt out of buffer sb.  Issued by the store thread of the CTA.
   auto issue_res = [&](int t, int h, int sb) {
     const Tile ti = decode_tile(p, t, BLOCK_N, MT, h);
-    mbar_arrive_expect_tx(&res_full[sb], 128 * BLOCK_N * 2);
-    for (int b = 0; b < BLOCK_N / 64; ++b) {
+    // the residual has the output's element size: 64-column boxes of a 16-bit tensor, 32-column boxes of an fp32 one
+    const int rcols = p.y_fp32 ? 32 : 64;
+    mbar_arrive_expect_tx(&res_full[sb], stg_bytes);
+    for (int b = 0; b < BLOCK_N / rcols; ++b) {
       const uint32_t dst = stage_out + sb * stg_bytes + (uint32_t)b * (128 * 128);
-      if (p.mode == 0) tma_load_2d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.m0);
-      else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * 64, ti.x0, ti.y0, ti.img);
+      if (p.mode == 0) tma_load_2d(dst, &tmap_res, &res_full[sb], ti.n0 + b * rcols, ti.m0);
+      else tma_load_4d(dst, &tmap_res, &res_full[sb], ti.n0 + b * rcols, ti.x0, ti.y0, ti.img);
     }
   };
   auto store_subtile = [&](int t, int h, int sb) {
@@ -265,6 +271,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     const int boxes = p.y_fp32 ? BLOCK_N / 32 : BLOCK_N / 64;
     const int cols = p.y_fp32 ? 32 : 64;
     for (int b = 0; b < boxes; ++b) {
+      if (ti.n0 + b * cols >= p.K) break;   // (K = 32 on a 64-wide tile: nothing to write past the last filter)
       const uint32_t src = stg + (uint32_t)b * (128 * 128);
       if (p.mode == 0) tma_store_2d(&tmap_y, src, ti.n0 + b * cols, ti.m0);
       else tma_store_4d_(&tmap_y, src, ti.n0 + b * cols, ti.x0, ti.y0, ti.img);
@@ -284,7 +291,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (t >= total_tiles) t = -1;
       for (int it = 0;; ++it) {
         // ring slot reuse: never more than kSchedRing tiles ahead of the store issuer (does not wait in practice)
-        while (it - *sched_done >= kSchedRing) { }
+        while (it - atomicAdd(sched_done, 0) >= kSchedRing) { }
         sched_tile[it & (kSchedRing - 1)] = t;
         mbar_arrive(&sched_full[it & (kSchedRing - 1)]);   // (release: the id is visible to whoever acquires the phase)
         if (t < 0) break;
@@ -299,15 +306,16 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
           for (int h = 0; h < MT; ++h) {
             const uint32_t dst = smem_a0 + as * a_slot + h * p.a_bytes;
-            if (p.mode == 0) tma_load_2d(dst, &tmap_x, &a_full[as], cc * 64, ti[h].m0);
-            else if (p.mode == 1) tma_load_4d(dst, &tmap_x, &a_full[as], cc * 64, ti[h].x0 - 1, ti[h].y0 - 1, ti[h].img);
+            if (p.mode == 0) tma_load_2d(dst, &tmap_x, &a_full[as], cc * p.kc, ti[h].m0);
+            else if (p.mode == 1) tma_load_4d(dst, &tmap_x, &a_full[as], cc * p.kc, ti[h].x0 - 1, ti[h].y0 - 1, ti[h].img);
             else if (p.mode == 3) {
               // K chunk cc = (tap, channel chunk); a 3x3 tap (r, s) samples the input at (2y + r - 1, 2x + s - 1):
               // the same strided box, shifted — pixels left of / above the image arrive as zeros
               int ch, dx = 0, dy = 0;
               const int tap = fast_divmod(cc, p.cpt, p.rcp_cpt, ch);
               if (p.taps_s2 == 9) { dy = tap / 3 - 1; dx = tap - (tap / 3) * 3 - 1; }
-              tma_load_4d(dst, &tmap_x, &a_full[as], ch * 64, 2 * ti[h].x0 + dx, 2 * ti[h].y0 + dy, ti[h].img);
+              tma_load_4d(dst, &tmap_x, &a_full[as], ch * p.kc, p.box_stride * ti[h].x0 + dx, p.box_stride * ti[h].y0 + dy,
+                          ti[h].img);
             }
             else tma_load_4d(dst, &tmap_x, &a_full[as], 0, ti[h].x0, ti[h].y0 + cc, ti[h].img);
           }
@@ -335,7 +343,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           fast_divmod(tb, p.n_tiles, p.rcp_n_tiles, n_tile);
           const int n0 = n_tile * BLOCK_N;
           for (int cc = 0; cc < p.c_chunks; ++cc) {
-            int col = cc * 64;
+            int col = cc * p.kc;
             for (int tap = 0; tap < p.taps; ++tap, col += p.w_cols) {
               mbar_wait(&b_empty[bs], bph ^ 1, 22);
               tr.rec(4, it * p.c_chunks + cc);
@@ -381,7 +389,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           if (!p.has_res) mbar_arrive(&stg_free[sb]);
           else res_next(sb);
           tr.rec(24, vt);
-          if (h == MT - 1) *sched_done = vt / MT + 1;
+          if (h == MT - 1) atomicExch(sched_done, vt / MT + 1);
           if (++sb == S) { sb = 0; ph ^= 1; }
         }
       }
@@ -389,7 +397,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       // ---------------------------------------------------------- MMA issuer (one thread: no per-step warp
       // reconvergence).  Two issuing threads (one per sub-tile) were measured and bought nothing: the tensor pipe,
       // not the issue rate, paces these tiles (tools/micro/mma_issue.cu).
-      const uint32_t idesc = make_idesc_f16(128, BLOCK_N, p.ab_half ? 0u : 1u);
+      const uint32_t idesc = p.tf32 ? make_idesc_tf32(128, BLOCK_N) : make_idesc_f16(128, BLOCK_N, p.ab_half ? 0u : 1u);
       const uint32_t sbo = (uint32_t)p.halo_w * 128u;
       // descriptor constants: only the 14-bit start-address field changes between MMAs
       const uint64_t a_hi = desc_sbo(0, sbo), b_hi = make_smem_desc(0, 128);
@@ -441,9 +449,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
               for (int h = 0; h < MT; ++h) {
                 const uint64_t adesc = a_hi | (uint64_t)(((a_tap + h * p.a_bytes) & 0x3FFFFu) >> 4);
-                umma_bf16(tmem_acc + h * BLOCK_N, adesc, bdesc, idesc, first);
+                if (p.tf32) {
+                  umma_tf32(tmem_acc + h * BLOCK_N, adesc, bdesc, idesc, first);
 #pragma unroll
-                for (int k = 1; k < 4; ++k) umma_bf16(tmem_acc + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                  for (int k = 1; k < 4; ++k) umma_tf32(tmem_acc + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                } else {
+                  umma_bf16(tmem_acc + h * BLOCK_N, adesc, bdesc, idesc, first);
+#pragma unroll
+                  for (int k = 1; k < 4; ++k) umma_bf16(tmem_acc + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                }
               }
               first = 1;
               if (!p.b_stationary) umma_commit(&b_empty[bs]);
@@ -520,9 +534,31 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
           if (p.y_fp32) {
             const uint32_t box = stg + (uint32_t)cb * (128 * 128) + (uint32_t)row * 128;
+            if (p.has_res) {   // fp32 residual: same swizzled staging position as the output it becomes
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const uint32_t addr = box + (uint32_t)((q4 ^ (row & 7)) << 4);
+                float r0, r1, r2, r3;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3)
+                             : "r"(addr)
+                             : "memory");
+                f[q4 * 4] += r0; f[q4 * 4 + 1] += r1; f[q4 * 4 + 2] += r2; f[q4 * 4 + 3] += r3;
+              }
+            }
             if (p.relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.tf32) {
+              // the next layer's kind::tf32 MMA drops the low 13 mantissa bits of what it reads: round to nearest
+              // here (cvt.rna.tf32.f32), so the activation chain carries unbiased TF32 values instead of truncated ones
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                uint32_t t;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(f[j]));
+                f[j] = __uint_as_float(t);
+              }
             }
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
@@ -803,24 +839,38 @@ extern "C" int vlnce_set_tma_cta_cap(int cap) {
   return VLNCE_OK;
 }
 
+static int conv_box_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift, void* y,
+                        int y_dtype, int N, int H, int W, int C, int K, int R, int stride, int relu, int block_n,
+                        cudaStream_t stream);
+
 extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
                               const void* residual, void* y, int y_dtype, int N, int H, int W, int C, int K, int R,
                               int relu, int block_n, cudaStream_t stream) {
   VLNCE_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0, "conv_tma: null tensor / empty shape");
   VLNCE_CHECK_ARG(R == 1 || R == 3, "conv_tma: only 1x1 and 3x3 stride-1 convolutions");
-  VLNCE_CHECK_ARG(C % 64 == 0 && K % 64 == 0, "conv_tma: C and K must be multiples of 64");
+  // 3x3 on images too small for the 16x8 halo tiles (8x8, 4x8 ...): tap-shifted boxes over 128/(8*H) images per tile
+  if (R == 3 && H % TH != 0 && H < TH && W % TW == 0 && 128 % (8 * H) == 0 && N % (128 / (8 * H)) == 0 && residual == nullptr)
+    return conv_box_tma(x, w, ab_dtype, scale, shift, y, y_dtype, N, H, W, C, K, 3, 1, relu, block_n, stream);
+  // ab_dtype F32: the fp32 operands are multiplied as TF32 (kind::tf32), output / residual fp32, 32-channel K chunks
+  const bool tf32 = ab_dtype == VLNCE_F32;
+  const int kc = tf32 ? 32 : 64, eb = tf32 ? 4 : 2;
+  // K = 32 (the first stage of the DD-PPO depth ResNet) rides on a 64-wide tile in the fp32 / raw-output mode: the
+  // weight box reads rows 32..63 out of bounds (zeros), the store skips the columns past K
+  const bool k32 = tf32 && K == 32 && scale == nullptr && residual == nullptr;
+  VLNCE_CHECK_ARG(C % kc == 0 && (K % 64 == 0 || k32), "conv_tma: C must be a multiple of %d and K of 64", kc);
   VLNCE_CHECK_ARG(R == 1 || (H % TH == 0 && W % TW == 0), "conv_tma: 3x3 needs H %% 16 == 0 and W %% 8 == 0");
   VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_tma: scale/shift must come together");
-  VLNCE_CHECK_ARG(ab_dtype == VLNCE_BF16 || ab_dtype == VLNCE_F16, "conv_tma: operand dtype");
+  VLNCE_CHECK_ARG(ab_dtype == VLNCE_BF16 || ab_dtype == VLNCE_F16 || tf32, "conv_tma: operand dtype");
   VLNCE_CHECK_ARG(y_dtype == ab_dtype || y_dtype == VLNCE_F32, "conv_tma: y dtype");
-  VLNCE_CHECK_ARG(!(residual && y_dtype == VLNCE_F32), "conv_tma: residual needs a 16-bit output");
+  VLNCE_CHECK_ARG(!(residual && y_dtype == VLNCE_F32 && !tf32), "conv_tma: an fp32 residual needs fp32 operands");
   VLNCE_CHECK_ARG((long long)N * H * W < (1ll << 31), "conv_tma: too many pixels");
   const int b_stages = (block_n >> 16) & 0xf;
   const int mt = (block_n & VLNCE_TMA_MT2) ? 2 : 1;
   const int no_stationary = (block_n & VLNCE_TMA_NO_STATIONARY) ? 1 : 0;
   int bn = block_n & 0xffff;
-  if (bn == 0) bn = (K % 128 == 0) ? 128 : 64;
-  VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && K % bn == 0, "conv_tma: block_n=%d vs K=%d", bn, K);
+  if (bn == 0) bn = (K % 128 == 0 && !tf32) ? 128 : 64;
+  if (k32) bn = 64;
+  VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && (K % bn == 0 || k32), "conv_tma: block_n=%d vs K=%d", bn, K);
   {  // the smallest configuration (2+2 ring slots, one staging buffer) must fit: narrow wide fp32 tiles
     const int a_b = (R == 1 ? 16 * 1024 : 23 * 1024) * mt;
     while (bn > 64 && 2 * a_b + 2 * bn * 128 + 2048 + 128 * bn * (y_dtype == VLNCE_F32 ? 4 : 2) > kSmemBudget) bn /= 2;
@@ -830,22 +880,23 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
     set_error("conv_tma: cuTensorMapEncodeTiled unavailable");
     return VLNCE_ERR_NO_DRIVER;
   }
-  const CUtensorMapDataType dt16 = ab_dtype == VLNCE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt16 = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                        : (ab_dtype == VLNCE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   const bool f32 = y_dtype == VLNCE_F32;
   const long long M = (long long)N * H * W;
   CUtensorMap tx, tw, ty, tr;
   int rc;
   {  // weights [K, R*R*C]
     const cuuint64_t gd[2] = {(cuuint64_t)R * R * C, (cuuint64_t)K};
-    const cuuint64_t gs[1] = {(cuuint64_t)R * R * C * 2};
-    const cuuint32_t bx[2] = {64, (cuuint32_t)bn};
+    const cuuint64_t gs[1] = {(cuuint64_t)R * R * C * eb};
+    const cuuint32_t bx[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
     if ((rc = map_nd(enc, &tw, w, dt16, 2, gd, gs, bx, "weights")) != VLNCE_OK) return rc;
   }
   TmaConvParams p;
   if (R == 1) {
     const cuuint64_t gd[2] = {(cuuint64_t)C, (cuuint64_t)M};
-    const cuuint64_t gs[1] = {(cuuint64_t)C * 2};
-    const cuuint32_t bx[2] = {64, 128};
+    const cuuint64_t gs[1] = {(cuuint64_t)C * eb};
+    const cuuint32_t bx[2] = {(cuuint32_t)kc, 128};
     if ((rc = map_nd(enc, &tx, x, dt16, 2, gd, gs, bx, "activation")) != VLNCE_OK) return rc;
     const cuuint64_t yd[2] = {(cuuint64_t)K, (cuuint64_t)M};
     const cuuint64_t ys[1] = {(cuuint64_t)K * (f32 ? 4 : 2)};
@@ -854,16 +905,16 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
       return rc;
     tr = ty;
     if (residual) {
-      const cuuint64_t rs[1] = {(cuuint64_t)K * 2};
-      const cuuint32_t rb[2] = {64, 128};
+      const cuuint64_t rs[1] = {(cuuint64_t)K * eb};
+      const cuuint32_t rb[2] = {(cuuint32_t)(tf32 ? 32 : 64), 128};
       if ((rc = map_nd(enc, &tr, residual, dt16, 2, yd, rs, rb, "residual")) != VLNCE_OK) return rc;
     }
-    p.mode = 0; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1;
+    p.mode = 0; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1; p.box_stride = 1;
     p.m_tiles = cdiv(M, 128); p.tiles_x = 1; p.tiles_y = 1; p.tw = 128; p.th = 1;
   } else {
     const cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t gs[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    const cuuint32_t bx[4] = {64, TW + 2, TH + 2, 1};
+    const cuuint64_t gs[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+    const cuuint32_t bx[4] = {(cuuint32_t)kc, TW + 2, TH + 2, 1};
     if ((rc = map_nd(enc, &tx, x, dt16, 4, gd, gs, bx, "halo")) != VLNCE_OK) return rc;
     const int esz = f32 ? 4 : 2;
     const cuuint64_t yd[4] = {(cuuint64_t)K, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -873,18 +924,19 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
       return rc;
     tr = ty;
     if (residual) {
-      const cuuint64_t rs[3] = {(cuuint64_t)K * 2, (cuuint64_t)W * K * 2, (cuuint64_t)H * W * K * 2};
-      const cuuint32_t rb[4] = {64, TW, TH, 1};
+      const cuuint64_t rs[3] = {(cuuint64_t)K * eb, (cuuint64_t)W * K * eb, (cuuint64_t)H * W * K * eb};
+      const cuuint32_t rb[4] = {(cuuint32_t)(tf32 ? 32 : 64), TW, TH, 1};
       if ((rc = map_nd(enc, &tr, residual, dt16, 4, yd, rs, rb, "residual")) != VLNCE_OK) return rc;
     }
-    p.mode = 1; p.taps = 9; p.halo_w = TW + 2; p.a_bytes = 23 * 1024; p.a_tx = (TW + 2) * (TH + 2) * 128; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1;
+    p.mode = 1; p.taps = 9; p.halo_w = TW + 2; p.a_bytes = 23 * 1024; p.a_tx = (TW + 2) * (TH + 2) * 128; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1; p.box_stride = 1;
     p.tiles_x = W / TW; p.tiles_y = H / TH; p.m_tiles = N * p.tiles_x * p.tiles_y; p.tw = TW; p.th = TH;
   }
   p.scale = scale; p.shift = shift;
   p.M = (int)M; p.N = N; p.H = H; p.W = W; p.C = C; p.K = K;
-  p.c_chunks = C / 64;
+  p.c_chunks = C / kc;
   p.w_cols = C;
-  p.n_tiles = K / bn;
+  p.n_tiles = cdiv(K, bn);
+  p.tf32 = tf32 ? 1 : 0; p.kc = kc;
   p.relu = relu; p.y_fp32 = f32; p.ab_half = (ab_dtype == VLNCE_F16); p.has_res = residual != nullptr;
   p.a_stages = p.b_stages = p.stg_bufs = 0; p.b_stationary = 0;
   return dispatch(bn, mt, tx, tw, ty, tr, p, b_stages, no_stationary, stream);
@@ -896,17 +948,20 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
 // read, the 3x3 is nine such boxes per channel chunk, shifted by the tap (im2col by tensor map, borders zero-filled by
 // the TMA unit).  A tile is 8 x bh output pixels of 128/(8*bh) images (bh = min(16, H/2)).  Needs H, W even,
 // (W/2) % 8 == 0, (H/2) % bh == 0, N % images-per-tile == 0.
-extern "C" int vlnce_conv_s2_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
-                                 void* y, int y_dtype, int N, int H, int W, int C, int K, int R, int relu, int block_n,
-                                 cudaStream_t stream) {
+static int conv_box_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift, void* y,
+                        int y_dtype, int N, int H, int W, int C, int K, int R, int stride, int relu, int block_n,
+                        cudaStream_t stream) {
   VLNCE_CHECK_ARG(R == 1 || R == 3, "conv_s2_tma: 1x1 or 3x3");
   VLNCE_CHECK_ARG(x && w && y && N > 0 && H > 0 && W > 0, "conv_s2_tma: null tensor / empty shape");
-  VLNCE_CHECK_ARG(C % 64 == 0 && K % 64 == 0, "conv_s2_tma: C and K must be multiples of 64");
-  VLNCE_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "conv_s2_tma: even input size");
+  const bool tf32 = ab_dtype == VLNCE_F32;   // fp32 operands multiplied as TF32, fp32 output, 32-channel K chunks
+  const int kc = tf32 ? 32 : 64, eb = tf32 ? 4 : 2;
+  const bool k32 = tf32 && K == 32 && scale == nullptr;   // see vlnce_conv_tma
+  VLNCE_CHECK_ARG(C % kc == 0 && (K % 64 == 0 || k32), "conv_s2_tma: C must be a multiple of %d and K of 64", kc);
+  VLNCE_CHECK_ARG(stride == 1 || (H % 2 == 0 && W % 2 == 0), "conv_s2_tma: even input size");
   VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_s2_tma: scale/shift must come together");
-  VLNCE_CHECK_ARG(ab_dtype == VLNCE_BF16 || ab_dtype == VLNCE_F16, "conv_s2_tma: operand dtype");
+  VLNCE_CHECK_ARG(ab_dtype == VLNCE_BF16 || ab_dtype == VLNCE_F16 || tf32, "conv_s2_tma: operand dtype");
   VLNCE_CHECK_ARG(y_dtype == ab_dtype || y_dtype == VLNCE_F32, "conv_s2_tma: y dtype");
-  const int P = H / 2, Q = W / 2;
+  const int P = H / stride, Q = W / stride;
   const int bh = P >= 16 ? 16 : P;
   VLNCE_CHECK_ARG(Q % 8 == 0 && P % bh == 0 && 128 % (8 * bh) == 0, "conv_s2_tma: output %dx%d does not tile", P, Q);
   const int ipt = 128 / (8 * bh);
@@ -915,29 +970,31 @@ extern "C" int vlnce_conv_s2_tma(const void* x, const void* w, int ab_dtype, con
   const int mt = (block_n & VLNCE_TMA_MT2) ? 2 : 1;
   const int no_stationary = (block_n & VLNCE_TMA_NO_STATIONARY) ? 1 : 0;
   int bn = block_n & 0xffff;
-  if (bn == 0) bn = (K % 128 == 0) ? 128 : 64;
-  VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && K % bn == 0, "conv_s2_tma: block_n=%d vs K=%d", bn, K);
+  if (bn == 0) bn = (K % 128 == 0 && !tf32) ? 128 : 64;
+  if (k32) bn = 64;
+  VLNCE_CHECK_ARG((bn == 64 || bn == 128 || bn == 256) && (K % bn == 0 || k32), "conv_s2_tma: block_n=%d vs K=%d", bn, K);
   while (bn > 64 && 2 * 16 * 1024 * mt + 2 * bn * 128 + 2048 + 128 * bn * (y_dtype == VLNCE_F32 ? 4 : 2) > kSmemBudget) bn /= 2;
   EncodeTiledFn enc = get_enc();
   if (!enc) {
     set_error("conv_s2_tma: cuTensorMapEncodeTiled unavailable");
     return VLNCE_ERR_NO_DRIVER;
   }
-  const CUtensorMapDataType dt16 = ab_dtype == VLNCE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt16 = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                        : (ab_dtype == VLNCE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   const bool f32 = y_dtype == VLNCE_F32;
   CUtensorMap tx, tw, ty;
   int rc;
   {  // weights [K, R*R*C]
     const cuuint64_t gd[2] = {(cuuint64_t)R * R * C, (cuuint64_t)K};
-    const cuuint64_t gs[1] = {(cuuint64_t)R * R * C * 2};
-    const cuuint32_t bx[2] = {64, (cuuint32_t)bn};
+    const cuuint64_t gs[1] = {(cuuint64_t)R * R * C * eb};
+    const cuuint32_t bx[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
     if ((rc = map_nd(enc, &tw, w, dt16, 2, gd, gs, bx, "weights")) != VLNCE_OK) return rc;
   }
   {  // input, sampled with stride 2 in W and H: the box spans 16 x 2*bh pixels and keeps every second one
     const cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t gs[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    const cuuint32_t bx[4] = {64, 16, (cuuint32_t)(2 * bh), (cuuint32_t)ipt};
-    const cuuint32_t es[4] = {1, 2, 2, 1};
+    const cuuint64_t gs[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+    const cuuint32_t bx[4] = {(cuuint32_t)kc, (cuuint32_t)(8 * stride), (cuuint32_t)(stride * bh), (cuuint32_t)ipt};
+    const cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     if ((rc = map_nd(enc, &tx, x, dt16, 4, gd, gs, bx, "strided input", es)) != VLNCE_OK) return rc;
   }
   {
@@ -950,17 +1007,24 @@ extern "C" int vlnce_conv_s2_tma(const void* x, const void* w, int ab_dtype, con
   }
   TmaConvParams p;
   p.mode = 3; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024; p.img_per_tile = ipt;
-  p.cpt = C / 64; p.rcp_cpt = 1.0f / (float)p.cpt; p.taps_s2 = R * R;
+  p.cpt = C / kc; p.rcp_cpt = 1.0f / (float)p.cpt; p.taps_s2 = R * R; p.box_stride = stride;
   p.tw = 8; p.th = bh;
   p.tiles_x = Q / 8; p.tiles_y = P / bh; p.m_tiles = (N / ipt) * p.tiles_x * p.tiles_y;
   p.scale = scale; p.shift = shift;
   p.M = N * P * Q; p.N = N; p.H = P; p.W = Q; p.C = C; p.K = K;
-  p.c_chunks = R * R * C / 64;   // K chunks in the weight matrix's column order: tap-major, channel chunk minor
+  p.c_chunks = R * R * C / kc;   // K chunks in the weight matrix's column order: tap-major, channel chunk minor
+  p.tf32 = tf32 ? 1 : 0; p.kc = kc;
   p.w_cols = C;
-  p.n_tiles = K / bn;
+  p.n_tiles = cdiv(K, bn);
   p.relu = relu; p.y_fp32 = f32; p.ab_half = (ab_dtype == VLNCE_F16); p.has_res = 0;
   p.a_stages = p.b_stages = p.stg_bufs = 0; p.b_stationary = 0;
   return dispatch(bn, mt, tx, tw, ty, ty, p, b_stages, no_stationary, stream);
+}
+
+extern "C" int vlnce_conv_s2_tma(const void* x, const void* w, int ab_dtype, const float* scale, const float* shift,
+                                 void* y, int y_dtype, int N, int H, int W, int C, int K, int R, int relu, int block_n,
+                                 cudaStream_t stream) {
+  return conv_box_tma(x, w, ab_dtype, scale, shift, y, y_dtype, N, H, W, C, K, R, 2, relu, block_n, stream);
 }
 
 // Debug: device buffer of 5 * 768 * 2 int64 that CTA 0 of every later conv_tma launch fills with
@@ -1040,12 +1104,13 @@ extern "C" int vlnce_conv_stem_tma(const void* xs, const void* w, int ab_dtype, 
       return rc;
   }
   TmaConvParams p;
-  p.mode = 2; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1;
+  p.mode = 2; p.taps = 1; p.halo_w = 8; p.a_bytes = 16 * 1024; p.a_tx = 16 * 1024; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1; p.box_stride = 1;
   p.tw = 128; p.th = 1;
   p.tiles_x = cdiv(Q, 128); p.tiles_y = P; p.m_tiles = N * p.tiles_x * p.tiles_y;
   p.scale = scale; p.shift = shift;
   p.M = N * P * Q; p.N = N; p.H = P; p.W = Q; p.C = 256; p.K = K;
   p.c_chunks = 4;
+  p.tf32 = 0; p.kc = 64;
   p.w_cols = 0;
   p.n_tiles = K / bn;
   p.relu = relu; p.y_fp32 = f32; p.ab_half = (ab_dtype == VLNCE_F16); p.has_res = 0;

@@ -165,6 +165,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, kind::tf32: A/B are fp32 tiles read as TF32 (10-bit mantissa), K = 8 per instruction (32 bytes per row).
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all tcgen05 ops issued so far by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -211,6 +223,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 //   [15] A major 0=K    [16] B major 0=K      [17,23) N>>3      [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t m, uint32_t n, uint32_t ab_is_bf16) {
   return (1u << 4) | (ab_is_bf16 << 7) | (ab_is_bf16 << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// Instruction descriptor for kind::tf32: A/B format 2 (TF32), K-major both, D = fp32.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t m, uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 // Byte offset inside a 1024B-aligned operand tile of element (row, 16B-chunk) under the

@@ -105,6 +105,90 @@ __global__ void conv_ref_kernel(const TX* __restrict__ x, const TW* __restrict__
   }
 }
 
+// Warp-cooperative fp32 convolution for the layers of the tf32 mode that the TMA tiles do not cover (4x4 images,
+// odd sizes): one warp owns PIXW output pixels x KW filters, the lanes split the input channels (coalesced 128-byte
+// reads of both operands), 32 partial sums per lane are reduced with shuffles.  fp32 products and sums.
+template <int PIXW, int KW>
+__global__ void __launch_bounds__(256)
+conv_warp_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+                 const float* __restrict__ shift, const float* __restrict__ residual, float* __restrict__ y, int N,
+                 int H, int W, int C, int K, int R, int S, int stride, int pad, int P, int Q, int relu) {
+  const int lane = threadIdx.x & 31;
+  const long long M = (long long)N * P * Q;
+  const long long mt = (M + PIXW - 1) / PIXW;
+  const int kt = (K + KW - 1) / KW;
+  const long long tasks = mt * kt;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long task = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < tasks; task += warps) {
+    const int k0 = (int)(task % kt) * KW;           // neighbouring warps share the pixel tile (L1 reuse of x)
+    const long long m0 = (task / kt) * PIXW;
+    float acc[PIXW][KW];
+#pragma unroll
+    for (int i = 0; i < PIXW; ++i)
+#pragma unroll
+      for (int j = 0; j < KW; ++j) acc[i][j] = 0.f;
+    int pn[PIXW], pp[PIXW], pq[PIXW];
+#pragma unroll
+    for (int i = 0; i < PIXW; ++i) {
+      const long long m = m0 + i < M ? m0 + i : M - 1;
+      pq[i] = (int)(m % Q);
+      pp[i] = (int)((m / Q) % P);
+      pn[i] = (int)(m / ((long long)P * Q));
+    }
+    for (int r = 0; r < R; ++r) {
+      for (int s = 0; s < S; ++s) {
+        const float* xp[PIXW];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < PIXW; ++i) {
+          const int ih = pp[i] * stride + r - pad, iw = pq[i] * stride + s - pad;
+          const bool ok = (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+          xp[i] = ok ? x + ((size_t)(pn[i] * H + ih) * W + iw) * C : nullptr;
+          any |= ok;
+        }
+        if (!any) continue;
+        const float* wp = w + ((size_t)(k0 * R + r) * S + s) * C;
+        const size_t wstride = (size_t)R * S * C;
+        for (int c = lane; c < C; c += 32) {
+          float xv[PIXW], wv[KW];
+#pragma unroll
+          for (int i = 0; i < PIXW; ++i) xv[i] = xp[i] != nullptr ? xp[i][c] : 0.f;
+#pragma unroll
+          for (int j = 0; j < KW; ++j) wv[j] = k0 + j < K ? __ldg(wp + j * wstride + c) : 0.f;
+#pragma unroll
+          for (int i = 0; i < PIXW; ++i)
+#pragma unroll
+            for (int j = 0; j < KW; ++j) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PIXW; ++i)
+#pragma unroll
+      for (int j = 0; j < KW; ++j) {
+        float v = acc[i][j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[i][j] = v;
+      }
+    // lane l writes output (pixel l / KW, filter l % KW) — PIXW * KW <= 32
+#pragma unroll
+    for (int i = 0; i < PIXW; ++i)
+#pragma unroll
+      for (int j = 0; j < KW; ++j) {
+        if (lane == i * KW + j && m0 + i < M && k0 + j < K) {
+          float v = acc[i][j];
+          const int k = k0 + j;
+          const size_t o = (size_t)(m0 + i) * K + k;
+          if (scale != nullptr) v = fmaf(v, scale[k], shift[k]);
+          if (residual != nullptr) v += residual[o];
+          if (relu) v = fmaxf(v, 0.f);
+          y[o] = v;
+        }
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // Stem operand builders (explicit im2col of the two 7x7/2 stems only; every other conv is
 // implicit).  One thread writes one 16-byte chunk (8 bf16) of an operand row.
@@ -489,9 +573,17 @@ gn_apply_kernel(const TI* __restrict__ x, const float* __restrict__ part, int S,
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] += r[e];
     }
-    if (relu) {
+    if (relu & 1) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+    }
+    if (relu & 2) {   // fp32 activations feeding kind::tf32 tiles: round to nearest TF32 (the MMA would truncate)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(f[e]));
+        f[e] = __uint_as_float(t);
+      }
     }
     store8<TO>(y + e0, f);
   }
@@ -638,6 +730,25 @@ extern "C" int vlnce_conv2d_ref(const void* x, int x_dtype, const void* w, int w
 #undef ARGS
   set_error("conv2d_ref: unsupported x dtype %d", x_dtype);
   return VLNCE_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int vlnce_conv2d_warp(const float* x, const float* w, const float* scale, const float* shift,
+                                 const float* residual, float* y, int N, int H, int W, int C, int K, int R, int S,
+                                 int stride, int pad, int relu, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && w && y, "conv2d_warp: null tensor");
+  VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv2d_warp: scale/shift must come together");
+  VLNCE_CHECK_ARG(N > 0 && C > 0 && K > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0, "conv2d_warp: sizes");
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  VLNCE_CHECK_ARG(P > 0 && Q > 0, "conv2d_warp: empty output");
+  constexpr int PIXW = 8, KW = 4;
+  const long long M = (long long)N * P * Q;
+  const long long tasks = ((M + PIXW - 1) / PIXW) * ((K + KW - 1) / KW);
+  const long long blocks = (tasks + 7) / 8;   // 8 warps per block
+  const unsigned grid = (unsigned)(blocks < 1 ? 1 : (blocks > 148ll * 64 ? 148ll * 64 : blocks));
+  conv_warp_kernel<PIXW, KW><<<grid, 256, 0, stream>>>(x, w, scale, shift, residual, y, N, H, W, C, K, R, S, stride,
+                                                        pad, P, Q, relu);
+  VLNCE_LAUNCH_CHECK("conv_warp_kernel");
+  return VLNCE_OK;
 }
 
 // ------------------------------------------------------------------------------------
@@ -883,7 +994,7 @@ extern "C" int vlnce_groupnorm_fused(const float* x, const float* gamma, const f
     int rc = vlnce_groupnorm_stats(x, VLNCE_F32, gamma, beta, scale_scratch, shift_scratch, workspace,
                                    workspace_bytes, N, HW, C, groups, eps, stream);
     if (rc != VLNCE_OK) return rc;
-    return vlnce_affine_apply(x, VLNCE_F32, scale_scratch, shift_scratch, C, residual, y, y_dtype, N, HW, C, relu,
+    return vlnce_affine_apply(x, VLNCE_F32, scale_scratch, shift_scratch, C, residual, y, y_dtype, N, HW, C, relu & 1,
                               stream);
   }
   int S = cdiv((long long)HW * C, 4096);

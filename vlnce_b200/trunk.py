@@ -72,6 +72,7 @@ HALO = 1 << 24  # tuning-code flag: TMA-halo 3x3 kernel instead of the generic t
 TMAP = 1 << 25  # tuning-code flag: persistent TMA-fed kernel (1x1 rows / 3x3 halo, overlapped epilogue)
 S2TMA = 1 << 26  # tuning-code flag: stride-2 conv (1x1 / 3x3) through the strided-box TMA mode of the persistent kernel
 EXCL = 1 << 20  # launch flag understood by the conv entry points: one CTA per SM
+TF32_BLOCK_N = int(_os.environ.get("VLNCE_TF32_BLOCK_N", "0"))  # tile width of the tf32 mode (0 = library default, 64)
 RGB_EXCLUSIVE = _os.environ.get("VLNCE_RGB_EXCLUSIVE", "0") != "0"
 # fp16 instead of fp32 raw conv output under GroupNorm (depth trunk): half the bytes of the statistics/apply passes
 GN_RAW16 = _os.environ.get("VLNCE_GN_RAW16", "0") != "0"
@@ -161,20 +162,28 @@ class _Conv:
             flat = krsc.reshape(self.K, -1)
             krsc = torch.zeros(self.K, 192, device=w.device, dtype=w.dtype)
             krsc[:, : flat.shape[1]] = flat
-        elif self.precision == "bf16" and self.stem == "depth":  # r*7+s, pad 49->64
+        elif self.precision in ("bf16", "tf32") and self.stem == "depth":  # r*7+s, pad 49->64 (tf32 mode: fp16 operand,
+            # 11-bit significand >= TF32's 10: the depth stem runs as the same im2col GEMM in both tensor-core modes)
             flat = krsc.reshape(self.K, -1)
             krsc = torch.zeros(self.K, 64, device=w.device, dtype=w.dtype)
             krsc[:, : flat.shape[1]] = flat
-        self.w = krsc.to(wdt).contiguous()
+        self.w = krsc.to(torch.float16 if (self.precision == "tf32" and self.stem == "depth") else wdt).contiguous()
+        if self.precision == "tf32" and self.stem != "depth":
+            # kind::tf32 reads the upper 19 bits of each fp32 operand: round the packed weights to nearest TF32 once
+            # (the conv epilogue does the same for the activations it writes), instead of letting the MMA truncate
+            bits = self.w.view(torch.int32)
+            self.w = ((bits + 0x1000) & ~0x1FFF).view(torch.float32).contiguous()
         self.w_s2d = None
-        if self.precision == "bf16" and self.stem == "rgb":
-            # stride-1 4x4 conv over 2x2 space-to-depth cells: [k][r'][s'][(dy*2+dx)*3+c] (+4 zero channels)
+        if self.precision in ("bf16", "tf32") and self.stem == "rgb":
+            # stride-1 4x4 conv over 2x2 space-to-depth cells: [k][r'][s'][(dy*2+dx)*3+c] (+4 zero channels).
+            # tf32 mode: the stem runs on fp16 operands — pixel values (integers 0..255) are exact in fp16 and its 11-bit
+            # significand rounds the weights no coarser than TF32's 10 bits would; fp32 accumulation and output
             w8 = torch.zeros(self.K, 8, 8, 3, device=w.device, dtype=w.dtype)
             w8[:, :7, :7] = w.permute(0, 2, 3, 1)
             w8 = w8.reshape(self.K, 4, 2, 4, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(self.K, 4, 4, 12)
             ws = torch.zeros(self.K, 4, 4, 16, device=w.device, dtype=w.dtype)
             ws[..., :12] = w8
-            self.w_s2d = ws.reshape(self.K, 256).to(wdt).contiguous()
+            self.w_s2d = ws.reshape(self.K, 256).to(torch.float16 if self.precision == "tf32" else wdt).contiguous()
         if isinstance(self.norm, nn.BatchNorm2d):
             n = self.norm
             sc = n.weight.detach().float() / torch.sqrt(n.running_var.detach().float() + n.eps)
@@ -198,7 +207,7 @@ class ConvTrunk:
     half_dtype = torch.bfloat16
 
     def __init__(self, device, precision: str = "bf16"):
-        assert precision in ("bf16", "fp32")
+        assert precision in ("bf16", "fp32", "tf32")
         self.device = device
         self.precision = precision
         self.adt = self.half_dtype if precision == "bf16" else torch.float32
@@ -307,7 +316,7 @@ class ConvTrunk:
         ``stem_rgb`` = x is the raw (n,h,w,3) image and the 7x7/2 window is gathered in-kernel."""
         n, h, w, c = shape_in
         st = lib.stream()
-        if self.precision == "bf16":
+        if self.precision == "bf16" or stem_s2d or gemm_c is not None:   # (tf32 mode: only its fp16 stems come this way)
             if stem_s2d:  # x = s2d cells, (n, h, w) = the stem's OUTPUT size
                 geom = ("stem_s2d", n, h, w, cv.K)
             elif stem_rgb:
@@ -378,6 +387,28 @@ class ConvTrunk:
                 cv.block_n[key] = bn
             launch(bn)
         else:
+            if self.precision == "tf32" and gemm_c is None and not stem_rgb and not stem_s2d and x.dtype == torch.float32:
+                # fp32 storage, TF32 products on the tensor cores wherever the persistent TMA kernel covers the geometry
+                geo = (cv.R, cv.S, cv.stride, cv.pad)
+                chan_ok = c % 32 == 0 and (cv.K % 64 == 0 or (cv.K == 32 and scale is None and residual is None))
+                small3 = (geo == (3, 3, 1, 1) and residual is None and h < 16 and w % 8 == 0 and 128 % (8 * h) == 0
+                          and n % (128 // (8 * h)) == 0)   # 8x8 / 4x8 images: several per tile (tap-shifted boxes)
+                if chan_ok and (geo == (1, 1, 1, 0) or (geo == (3, 3, 1, 1) and h % 16 == 0 and w % 8 == 0) or small3):
+                    C.vlnce_conv_tma(ptr(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift), ptr(residual), ptr(y), lib.F32,
+                                     n, h, w, c, cv.K, cv.R, int(relu), TF32_BLOCK_N, st)
+                    return
+                if (chan_ok and residual is None and geo in ((1, 1, 2, 0), (3, 3, 2, 1)) and h % 2 == 0 and w % 2 == 0
+                        and (w // 2) % 8 == 0):
+                    bh = min(16, h // 2)
+                    if (h // 2) % bh == 0 and 128 % (8 * bh) == 0 and n % (128 // (8 * bh)) == 0:
+                        C.vlnce_conv_s2_tma(ptr(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift), ptr(y), lib.F32, n, h, w, c,
+                                            cv.K, cv.R, int(relu), TF32_BLOCK_N, st)
+                        return
+                if c % 32 == 0 and not _os.environ.get("VLNCE_NO_WARP"):   # what the tiles do not cover (4x4 images, odd sizes): fp32 on CUDA cores, one warp per
+                    # 8 pixels x 4 filters with the lanes across the input channels
+                    C.vlnce_conv2d_warp(ptr(x), ptr(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y), n, h, w, c,
+                                        cv.K, cv.R, cv.S, cv.stride, cv.pad, int(relu), st)
+                    return
             C.vlnce_conv2d_ref(ptr(x), lib.code(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift),
                                ptr(residual), lib.F32, ptr(y), lib.F32, n, h, w, c, cv.K, cv.R, cv.S,
                                cv.stride, cv.pad, int(relu), st)
@@ -520,11 +551,11 @@ class RGBTrunk(ConvTrunk):
         cv = self.stem
         p, q = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
         x = None
-        if self.precision == "bf16" and S2D_STEM and self._s2d_ok:
+        if self.precision in ("bf16", "tf32") and S2D_STEM and self._s2d_ok:
             # stem as a stride-1 4x4 conv over 2x2 space-to-depth cells, fully TMA-fed (overlapping
             # 4-cell windows read straight from the cell image); falls back to the gather stem if the
             # driver rejects the overlapping-stride tensor map
-            cells = self.pool.get("stem_s2d", (n, p + 3, q + 3, 16), self.adt)
+            cells = self.pool.get("stem_s2d", (n, p + 3, q + 3, 16), torch.float16 if self.precision == "tf32" else self.adt)
             try:
                 C.vlnce_stem_s2d(ptr(rgb), lib.code(rgb), ptr(cells), lib.code(cells), n, h, w, st)
                 x, shp = self._norm_conv(cells, (n, p, q, 16), cv, "stem_y", out_hw=(p, q), stem_s2d=True)
@@ -620,7 +651,7 @@ class DepthTrunk(ConvTrunk):
         elif raw.dtype == torch.float32:
             C.vlnce_groupnorm_fused(ptr(raw), ptr(gn.weight), ptr(gn.bias), ptr(residual), ptr(y), lib.code(y), ptr(ws),
                                     ws.numel() * 4, ptr(sc), ptr(sh), n, p * q, cv.K, gn.num_groups, float(gn.eps),
-                                    int(relu), st)
+                                    int(relu) | (2 if self.precision == "tf32" else 0), st)
         else:
             C.vlnce_groupnorm_stats(ptr(raw), lib.code(raw), ptr(gn.weight), ptr(gn.bias), ptr(sc), ptr(sh), ptr(ws),
                                     ws.numel() * 4, n, p * q, cv.K, gn.num_groups, float(gn.eps), st)
@@ -756,8 +787,8 @@ class DepthTrunk(ConvTrunk):
         st = lib.stream()
         hp, wp = h // 2, w // 2
         p, q = (hp + 6 - 7) // 2 + 1, (wp + 6 - 7) // 2 + 1
-        if self.precision == "bf16":
-            a = self.pool.get(self._pfx + "stem_a", (n * p * q, 64), self.adt)
+        if self.precision in ("bf16", "tf32"):
+            a = self.pool.get(self._pfx + "stem_a", (n * p * q, 64), torch.float16 if self.precision == "tf32" else self.adt)
             C.vlnce_im2col_depth_stem(ptr(depth), ptr(a), lib.code(a), n, h, w, st)
             x, shp = self._gn_conv(a, (n, p, q, 64), self.stem, "stem_y", gemm_c=64, out_hw=(p, q))
         else:
