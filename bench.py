@@ -42,20 +42,28 @@ WORKLOAD = ("C2: CMAPolicy fwd+DAgger loss+bwd+Adam, T=1 N=64/GPU, rgb u8 256x25
 
 WSEED = 13  # seeded "trained-like" weights (vlnce_b200.synth.seeded_state_dict); the parity case cma_train_pixels uses the same
 RGB_HW, RXR_DIM, ACTIONS, COEF = 256, 0, 4, 3.2
+T_STEPS = 1   # time steps per trajectory in a batch (rows = T_STEPS x trajectories, time-major as collate_fn stacks them)
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
     "c2": dict(rows=64, hw=256, rgb_hw=256, length=80, rxr=0, actions=4, coef=3.2),
     # BASELINE.json configs[4]: RxR-shaped multilingual-BERT features (512 tokens x 768), 6 actions, frames after the
     # RxR observation transforms (rgb 224x224, depth 256x256: rxr_cma_en.yaml:28-30), 256 rows over 8 GPUs = 32 / GPU
     "c5": dict(rows=32, hw=256, rgb_hw=224, length=512, rxr=768, actions=6, coef=1.9),
+    # SURVEY 8d's training variant of C2: the same 64 rows as 8 trajectories x 8 time steps (sequence GRUs with mask
+    # resets, per-trajectory loss normalisation) — side measurement
+    "c2t8": dict(rows=64, hw=256, rgb_hw=256, length=80, rxr=0, actions=4, coef=3.2, t=8),
 }
 
 
 def select_workload(name):
-    global ROWS_PER_GPU, HW, RGB_HW, LENGTH, RXR_DIM, ACTIONS, COEF, METRIC, WORKLOAD
+    global ROWS_PER_GPU, HW, RGB_HW, LENGTH, RXR_DIM, ACTIONS, COEF, METRIC, WORKLOAD, T_STEPS
     w = WORKLOADS[name]
+    T_STEPS = w.get("t", 1)
     ROWS_PER_GPU, HW, RGB_HW, LENGTH = w["rows"], w["hw"], w["rgb_hw"], w["length"]
     RXR_DIM, ACTIONS, COEF = w["rxr"], w["actions"], w["coef"]
+    if name == "c2t8":
+        METRIC = "policy steps/sec (batch 64 = 8 trajectories x 8 steps, 256x256 RGB-D, 80-tok instr)"
+        WORKLOAD = WORKLOAD.replace("T=1 N=64/GPU", "T=8 N=8/GPU")
     if name == "c5":
         METRIC = "policy steps/sec (RxR: batch 32/GPU, 224x224 RGB + 256x256 depth, 512x768 BERT instruction features)"
         WORKLOAD = ("C5: CMAPolicy fwd+DAgger loss+bwd+Adam, T=1 N=32/GPU, rgb u8 224x224x3, depth f32 256x256x1, "
@@ -65,7 +73,7 @@ def select_workload(name):
 def make_batch(seed, rows):
     from vlnce_b200 import synth
 
-    return synth.make_train_batch(seed, 1, rows, hw=HW, rgb_hw=RGB_HW, length=LENGTH, num_actions=ACTIONS, coef=COEF,
+    return synth.make_train_batch(seed, T_STEPS, rows // T_STEPS, hw=HW, rgb_hw=RGB_HW, length=LENGTH, num_actions=ACTIONS, coef=COEF,
                                   rxr_dim=RXR_DIM)
 
 
@@ -78,7 +86,7 @@ def oracle_case(rows=None):
     """CHECKER side only (reference arm, cpu_baseline leg, parity block): the oracle's description of the same policy."""
     from oracle import cases
 
-    case = dict(cases.CASES["cma_train_pixels"], t=1, n=rows)
+    case = dict(cases.CASES["cma_train_pixels"], t=T_STEPS, n=rows // T_STEPS)
     assert case["wseed"] == WSEED
     if RXR_DIM:
         case.update(rgb_hw=RGB_HW, length=LENGTH, rxr=RXR_DIM, actions=ACTIONS, coef=COEF)
@@ -225,9 +233,9 @@ def parity_block(gpu_snapshot, host_batch):
     aux = oracle_vlnce.AuxLosses
     aux.activate()
     aux.clear()
-    h0 = torch.zeros(rows, pol.net.num_recurrent_layers, 512)
+    h0 = torch.zeros(rows // T_STEPS, pol.net.num_recurrent_layers, 512)
     dist = pol.build_distribution(obs, h0, prev, masks)
-    logits = dist.logits.view(1, rows, -1)
+    logits = dist.logits.view(T_STEPS, rows // T_STEPS, -1)
     ce = F.cross_entropy(logits.permute(0, 2, 1), actions, reduction="none")
     action_loss = ((weights * ce).sum(0) / weights.sum(0)).mean()
     aux_loss = aux.reduce((weights > 0).view(-1))
@@ -266,7 +274,12 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="conv-trunk arithmetic: bf16/fp16 tcgen05 tiles (default) | tf32 = fp32 storage, kind::tf32 "
+                         "products (what stock torch does for fp32 convolutions on a GPU) | fp32 = CUDA-core exact mode")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the workload's rows (64) are split over the ranks (64 / world rows per GPU) "
+                         "instead of 64 rows per GPU; the line then says \"scaling\": \"strong\"")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = BASELINE metric config (default); "
                     "c5 = RxR-shaped features (side measurement)")
     ap.add_argument("--no-graph", action="store_true")
@@ -286,6 +299,10 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.strong and world > 1:
+        global ROWS_PER_GPU
+        assert ROWS_PER_GPU % world == 0, "--strong: the workload's rows must divide over the ranks"
+        ROWS_PER_GPU //= world
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -644,11 +661,12 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "policy steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32"}.get(args.precision, "f32"), "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": ROWS_PER_GPU * world, "rows_per_gpu": ROWS_PER_GPU,
-                       "parallelism": f"dp{world}", "precision": "rgb trunk bf16 / depth trunk fp16 tcgen05, head fp32"
-                       if args.precision == "bf16" else "fp32 CUDA cores",
+                       "parallelism": f"dp{world}", "precision": {"bf16": "rgb trunk bf16 / depth trunk fp16 tcgen05, head fp32",
+                                     "tf32": "trunks fp32 storage / TF32 tcgen05 products, head fp32"}.get(
+                                         args.precision, "fp32 CUDA cores"),
                        "l2": f"inputs rotated over {NSETS} distinct batches ({NSETS * h2d_bytes / 1e6:.0f} MB > L2)",
                        "cuda_graph": graph is not None, "allreduce_in_graph": bool(graph is not None and graph_has_allreduce and world > 1),
                        "pdl": bool(lib.C.vlnce_get_pdl()),

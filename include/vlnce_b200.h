@@ -281,6 +281,15 @@ int vlnce_gru_seq_fwd(const float* gx, const float* whh_f, const float* whh_b, c
 int vlnce_gru_pointwise_fwd(const float* gi, const float* gh, const float* h, long long ldh,
                             float* hout, long long ldo, float* hout2, long long ldo2, float* save,
                             int rows, int H, cudaStream_t stream);
+/* One whole GRU step of the state encoder in ONE launch (cma_policy.py:248-256 and :287-294, seq2seq_policy.py:112-137
+ * through habitat_baselines v0.1.7 RNNStateEncoder.single_forward): hm = h0 * mask[row]; gi = x W_ih^T + b_ih;
+ * gh = hm W_hh^T + b_hh; gates r, z, n; out = (1 - z) n + z hm (optionally also into out2, the rnn_states_out slot).
+ * hm (rows,H) and save (rows,4H) = r, z, n, gh_n are what vlnce_gru_pointwise_bwd and the weight-gradient GEMMs read
+ * (either may be NULL for inference).  Replaces vlnce_mask_rows + two vlnce_sgemm + vlnce_gru_pointwise_fwd.
+ * H % 4 == 0 and 12 * (in_size + H) floats of shared memory (<= 200 KB). */
+int vlnce_gru_step_fwd(const float* x, long long ldx, int in_size, const float* h0, long long ldh0, const float* mask,
+                       const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* hm, float* out,
+                       long long ldo, float* out2, long long ldo2, float* save, int rows, int H, cudaStream_t stream);
 /* LSTM cell pointwise part (rnn_state_encoder with STATE_ENCODER.rnn_type = "LSTM", cma_policy.py:129,175;
  * seq2seq_policy.py:112; waypoint_predictors.py:72,160): gates i,f,g,o from gi + gh (rows,4H), c = mask-reset cell
  * state; writes h', c' (and optional second copies into the rnn_states_out slots); save (rows,5H) for the backward. */

@@ -219,6 +219,25 @@ class Emulator:
         if save:
             _mat(save, rows, 4 * H, 4 * H)[...] = np.concatenate([r, z, n, ghn], 1)
 
+    def gru_step_fwd(self, x, ldx, in_size, h0, ldh0, mask, w_ih, w_hh, b_ih, b_hh, hm, out, ldo, out2, ldo2, save,
+                     rows, H, st):
+        hp = _mat(h0, rows, H, ldh0).astype(np.float64) * _flat(mask, rows).astype(np.float64)[:, None]
+        gi_ = _mat(x, rows, in_size, ldx).astype(np.float64) @ _mat(w_ih, 3 * H, in_size, in_size).astype(np.float64).T \
+            + _flat(b_ih, 3 * H).astype(np.float64)
+        gh_ = hp @ _mat(w_hh, 3 * H, H, H).astype(np.float64).T + _flat(b_hh, 3 * H).astype(np.float64)
+        r = _sig(gi_[:, :H] + gh_[:, :H])
+        z = _sig(gi_[:, H:2 * H] + gh_[:, H:2 * H])
+        ghn = gh_[:, 2 * H:]
+        n = np.tanh(gi_[:, 2 * H:] + r * ghn)
+        hn = (1 - z) * n + z * hp
+        _mat(out, rows, H, ldo)[...] = hn
+        if out2:
+            _mat(out2, rows, H, ldo2)[...] = hn
+        if hm:
+            _mat(hm, rows, H, H)[...] = hp
+        if save:
+            _mat(save, rows, 4 * H, 4 * H)[...] = np.concatenate([r, z, n, ghn], 1)
+
     def lstm_pointwise_fwd(self, gi, gh, c, ldc, hout, ldo, cout, ldco, hout2, cout2, ldo2, save, rows, H, st):
         a = _mat(gi, rows, 4 * H, 4 * H).astype(np.float64) + _mat(gh, rows, 4 * H, 4 * H).astype(np.float64)
         i, f, g, o = _sig(a[:, :H]), _sig(a[:, H:2 * H]), np.tanh(a[:, 2 * H:3 * H]), _sig(a[:, 3 * H:])

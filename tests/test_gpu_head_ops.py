@@ -155,6 +155,43 @@ def test_gru_cell_matches_torch():
     torch.testing.assert_close(out, want[0], rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("N,I,H", [(64, 416, 512), (7, 1184, 512), (1, 33, 64), (130, 50, 128)])
+def test_fused_gru_step_matches_torch_and_unfused(N, I, H):
+    """vlnce_gru_step_fwd (reset + both projections + gates + update in one launch) against torch.nn.GRU on the CPU and
+    against the unfused kernel sequence it replaces, including what the backward reads (masked hidden, saved gates)."""
+    torch.manual_seed(1)
+    rnn = nn.GRU(I, H)
+    x, h = _r(N, I), _r(N, 2 * H, seed=5)              # h0 rows strided like the (N, slots, H) state tensor
+    mask = (torch.arange(N) % 3 != 0).float().to(DEV)    # every third row restarts an episode
+    with torch.no_grad():
+        _, want = rnn(x.cpu().unsqueeze(0), (h[:, :H] * mask[:, None]).cpu().unsqueeze(0))
+    want, rnn = want[0].to(DEV), rnn.to(DEV)
+    out = torch.full((N, H + 5), float("nan"), device=DEV)
+    out2 = torch.full((N, 2 * H), float("nan"), device=DEV)
+    hm, save = torch.empty(N, H, device=DEV), torch.empty(N, 4 * H, device=DEV)
+    C.vlnce_gru_step_fwd(ptr(x), I, I, ptr(h), 2 * H, ptr(mask), ptr(rnn.weight_ih_l0), ptr(rnn.weight_hh_l0),
+                         ptr(rnn.bias_ih_l0), ptr(rnn.bias_hh_l0), ptr(hm), ptr(out), H + 5, ptr(out2), 2 * H, ptr(save),
+                         N, H, lib.stream())
+    torch.testing.assert_close(out[:, :H], want, rtol=1e-4, atol=2e-5)
+    assert torch.equal(out2[:, :H], out[:, :H]) and torch.isnan(out2[:, H:]).all() and torch.isnan(out[:, H:]).all()
+    assert torch.equal(hm, h[:, :H] * mask[:, None])
+    # the unfused sequence
+    hm_u = torch.empty(N, H, device=DEV)
+    C.vlnce_mask_rows(ptr(h), 2 * H, ptr(mask), ptr(hm_u), H, N, H, lib.stream())
+    gi, gh = torch.empty(N, 3 * H, device=DEV), torch.empty(N, 3 * H, device=DEV)
+    linear(ptr(x), I, ptr(rnn.weight_ih_l0), ptr(gi), 3 * H, ptr(rnn.bias_ih_l0), N, 3 * H, I)
+    linear(ptr(hm_u), H, ptr(rnn.weight_hh_l0), ptr(gh), 3 * H, ptr(rnn.bias_hh_l0), N, 3 * H, H)
+    out_u, save_u = torch.empty(N, H, device=DEV), torch.empty(N, 4 * H, device=DEV)
+    C.vlnce_gru_pointwise_fwd(ptr(gi), ptr(gh), ptr(hm_u), H, ptr(out_u), H, None, 0, ptr(save_u), N, H, lib.stream())
+    torch.testing.assert_close(out[:, :H], out_u, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(save, save_u, rtol=1e-4, atol=1e-5)
+    # inference form: no saved tensors
+    out3 = torch.empty(N, H, device=DEV)
+    C.vlnce_gru_step_fwd(ptr(x), I, I, ptr(h), 2 * H, ptr(mask), ptr(rnn.weight_ih_l0), ptr(rnn.weight_hh_l0),
+                         ptr(rnn.bias_ih_l0), ptr(rnn.bias_hh_l0), None, ptr(out3), H, None, 0, None, N, H, lib.stream())
+    assert torch.equal(out3, out[:, :H])
+
+
 @pytest.mark.parametrize("P,D,masked", [(80, 256, True), (16, 2112, False), (16, 192, False)])
 def test_attention_pool_matches_reference_attn(P, D, masked):
     """cma_policy.py:207-217 with keys/values from a Conv1d, against the re-associated kernel."""

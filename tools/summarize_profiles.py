@@ -92,5 +92,72 @@ def full(src, dst, note=""):
             f.write("\n")
 
 
+KERNEL_METRICS = ("gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
+                  "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,"
+                  "sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,"
+                  "lts__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__throughput.avg.pct_of_peak_sustained_elapsed")
+
+
+def kernels(src, dst, note=""):
+    """Per-kernel evidence table of one eager training step: duration, DRAM bytes -> achieved HBM GB/s and its share
+    of the measured copy bandwidth, tensor-pipe active %, SM / L2 / L1 throughput (time-weighted means over the
+    kernel's launches).  ``src`` = csv of `ncu --metrics <KERNEL_METRICS> --csv`."""
+    import json
+    import os
+
+    txt = open(src).read()
+    rows = list(csv.DictReader(io.StringIO(txt[txt.index('"ID"'):])))
+    per = collections.OrderedDict()
+    for r in rows:
+        d = per.setdefault(r["ID"], {"kernel": short(r["Kernel Name"]), "grid": r.get("Grid Size", ""), "block": r.get("Block Size", "")})
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"].lower()
+        if r["Metric Name"].startswith("dram__bytes"):
+            v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1e-3)   # -> us
+        d[r["Metric Name"]] = v
+    peak = 6534.8
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    agg = collections.OrderedDict()
+    for d in per.values():
+        a = agg.setdefault(d["kernel"], {"n": 0, "us": 0.0, "bytes": 0.0, "w": collections.defaultdict(float), "grids": set()})
+        us = d.get("gpu__time_duration.sum", 0.0)
+        a["n"] += 1
+        a["us"] += us
+        a["bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+        a["grids"].add(d["grid"].replace(" ", ""))
+        for m in ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                  "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+                  "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"):
+            a["w"][m] += d.get(m, 0.0) * us
+    tot = sum(a["us"] for a in agg.values())
+    with open(dst, "w") as f:
+        f.write("# every kernel of one training step under ncu: HBM GB/s, tensor-pipe active %, unit throughputs\n\n")
+        f.write("Command: `ncu --profile-from-start off --clock-control none --csv --metrics " + KERNEL_METRICS +
+                " python bench.py --ncu-step --no-cpu-baseline` (one eager, serial-stream step of C2: batch 64, bf16 / "
+                "fp16 trunks, between cudaProfilerStart/Stop; B200).  Launches are serialised and replayed per metric "
+                "pass, so durations are cold-ish and the table is for SHARES and per-kernel unit utilisation, not step "
+                "time.  HBM GB/s = (dram read + write bytes) / duration, summed over the kernel's launches; % of the "
+                f"measured copy bandwidth {peak:.0f} GB/s (MEASURED_PEAKS.json).  Percentages are time-weighted means.\n"
+                + note + "\n\n")
+        f.write(f"One step = {sum(a['n'] for a in agg.values())} launches, {tot:.0f} us summed.\n\n")
+        f.write("| kernel | launches | us | share | DRAM MB | HBM GB/s | % HBM peak | tensor pipe % | SM thr % | warps active % | L2 thr % | L1 thr % |\n")
+        f.write("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+            us = max(a["us"], 1e-9)
+            gbs = a["bytes"] / (us * 1e-6) / 1e9
+            w = a["w"]
+            f.write(f"| `{k}` | {a['n']} | {a['us']:.1f} | {100 * a['us'] / tot:.1f}% | {a['bytes'] / 1e6:.1f} | {gbs:.0f} | "
+                    f"{100 * gbs / peak:.1f} | {w['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'] / us:.1f} | "
+                    f"{w['sm__throughput.avg.pct_of_peak_sustained_elapsed'] / us:.1f} | "
+                    f"{w['sm__warps_active.avg.pct_of_peak_sustained_active'] / us:.1f} | "
+                    f"{w['lts__throughput.avg.pct_of_peak_sustained_elapsed'] / us:.1f} | "
+                    f"{w['l1tex__throughput.avg.pct_of_peak_sustained_elapsed'] / us:.1f} |\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "full": full, "kernels": kernels}[sys.argv[1]](*sys.argv[2:])

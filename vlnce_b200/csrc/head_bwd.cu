@@ -412,21 +412,26 @@ __global__ void prev_action_embed_bwd_kernel(const long long* __restrict__ prev,
 
 // d_table_flat[c*P + s] (+)= sum_r dE[r, s, c_off + c] + sum_r dflat[r, c*P + s] + sum_r dmean[r, c] / P
 // (the three paths the 64-channel spatial embedding takes: attention K/V source,
-//  depth_linear's NCHW flatten, rgb_linear's mean pool).  One CTA per (c, s) pair block.
+//  depth_linear's NCHW flatten, rgb_linear's mean pool).  One warp per (c, s) table entry.
 __global__ void spatial_embed_grad_kernel(const float* __restrict__ dE, long long lde_r, long long lde_p,
                                           int c_off, const float* __restrict__ dflat, long long ldf,
                                           const float* __restrict__ dmean, long long ldm,
                                           float* __restrict__ dtable, int accumulate, int R, int P, int Cs) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per table entry, the lanes split the rows (the three sources are strided in r: 64 dependent scattered
+  // loads per thread made this the slowest small kernel of the backward chain), shuffle reduction
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (idx >= Cs * P) return;
   const int c = idx / P, s = idx % P;
   float acc = 0.f;
-  for (int r = 0; r < R; ++r) {
+  for (int r = lane; r < R; r += 32) {
     if (dE != nullptr) acc += dE[r * lde_r + s * lde_p + c_off + c];
     if (dflat != nullptr) acc += dflat[r * ldf + idx];
     if (dmean != nullptr) acc += dmean[r * ldm + c] / (float)P;
   }
-  dtable[idx] = accumulate ? dtable[idx] + acc : acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) dtable[idx] = accumulate ? dtable[idx] + acc : acc;
 }
 
 // ------------------------------------------------------------------------------------
@@ -731,7 +736,7 @@ extern "C" int vlnce_spatial_embed_grad(const float* dE, long long lde_r, long l
                                         float* dtable, int accumulate, int R, int P, int Cs,
                                         cudaStream_t stream) {
   VLNCE_CHECK_ARG(dtable && R > 0 && P > 0 && Cs > 0, "spatial_embed_grad: bad arguments");
-  spatial_embed_grad_kernel<<<cdiv(Cs * P, 128), 128, 0, stream>>>(dE, lde_r, lde_p, c_off, dflat, ldf, dmean, ldm,
+  spatial_embed_grad_kernel<<<cdiv((long long)Cs * P * 32, 256), 256, 0, stream>>>(dE, lde_r, lde_p, c_off, dflat, ldf, dmean, ldm,
                                                                  dtable, accumulate, R, P, Cs);
   VLNCE_LAUNCH_CHECK("spatial_embed_grad_kernel");
   return VLNCE_OK;

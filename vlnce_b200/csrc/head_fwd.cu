@@ -319,6 +319,152 @@ __global__ void gru_pointwise_fwd_kernel(const float* __restrict__ gi, const flo
 }
 
 // ------------------------------------------------------------------------------------
+// One GRU step of the state encoder in ONE launch (cma_policy.py:248-256, 287-294; seq2seq_policy.py:112-137 via
+// habitat_baselines v0.1.7 RNNStateEncoder.single_forward): hidden reset (h * mask), input projection, hidden
+// projection, gates and the state update.  CTA j owns UN hidden units = 3*UN rows of W_ih and of W_hh, staged once in
+// shared memory; a warp takes 4 batch rows at a time, its lanes split the reduction dimension (coalesced reads of x and
+// h, conflict-free reads of the weight slice), 16 partial sums per row are shuffled down and lanes 0..15 finish the
+// cell.  Roles inside the CTA: all warps stage, then every warp is a compute warp over its row groups.
+// ------------------------------------------------------------------------------------
+constexpr int kGruUN = 4;        // hidden units per CTA
+constexpr int kGruRows = 4;      // batch rows per warp pass
+
+template <bool VEC>   // VEC: rows, leading dimensions and pointers are 16-byte aligned -> 128-bit loads, 4 k per lane
+__global__ void __launch_bounds__(512)
+gru_step_fused_kernel(const float* __restrict__ x, long long ldx, int Kx, const float* __restrict__ h0, long long ldh0,
+                      const float* __restrict__ mask, const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                      const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ hm,
+                      float* __restrict__ out, long long ldo, float* __restrict__ out2, long long ldo2,
+                      float* __restrict__ save, int rows, int H) {
+  extern __shared__ __align__(16) float smem_gru[];
+  constexpr int UN = kGruUN, G = 3 * kGruUN, RW = kGruRows;
+  float* s_wi = smem_gru;                   // [G][Kx]   slice row g*UN + u = W_ih[g*H + u0 + u]
+  float* s_wh = smem_gru + (size_t)G * Kx;  // [G][H]
+  const int u0 = blockIdx.x * UN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < 2 * G; j += nwarps) {   // one warp per weight row: coalesced, no index division per element
+    const int g = (j % G) / UN, u = (j % G) % UN;
+    if (j < G) {
+      const float* src = w_ih + (size_t)(g * H + u0 + u) * Kx;
+      for (int k = lane; k < Kx; k += 32) s_wi[j * Kx + k] = __ldg(src + k);
+    } else {
+      const float* src = w_hh + (size_t)(g * H + u0 + u) * H;
+      for (int k = lane; k < H; k += 32) s_wh[(j - G) * H + k] = __ldg(src + k);
+    }
+  }
+  __syncthreads();
+  const int groups = (rows + RW - 1) / RW;
+  for (int grp = warp; grp < groups; grp += nwarps) {
+    const int r0 = grp * RW;
+    // per row: [u] r-sum (gi+gh), [UN+u] z-sum, [2UN+u] gi_n, [3UN+u] gh_n
+    float acc[RW][4 * UN];
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+      for (int j = 0; j < 4 * UN; ++j) acc[r][j] = 0.f;
+    const float* xr[RW];
+    const float* hr[RW];
+    float mk[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      const int row = r0 + r < rows ? r0 + r : rows - 1;
+      xr[r] = x + (size_t)row * ldx;
+      hr[r] = h0 + (size_t)row * ldh0;
+      mk[r] = mask[row];
+    }
+    if constexpr (VEC) {
+#pragma unroll 1
+      for (int k = 4 * lane; k < Kx; k += 128) {
+        float4 xv[RW];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) xv[r] = *reinterpret_cast<const float4*>(xr[r] + k);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(s_wi + j * Kx + k);
+#pragma unroll
+          for (int r = 0; r < RW; ++r)
+            acc[r][j] = fmaf(xv[r].x, w.x, fmaf(xv[r].y, w.y, fmaf(xv[r].z, w.z, fmaf(xv[r].w, w.w, acc[r][j]))));
+        }
+      }
+#pragma unroll 1
+      for (int k = 4 * lane; k < H; k += 128) {
+        float4 hv[RW];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          hv[r] = *reinterpret_cast<const float4*>(hr[r] + k);
+          hv[r].x *= mk[r]; hv[r].y *= mk[r]; hv[r].z *= mk[r]; hv[r].w *= mk[r];
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(s_wh + j * H + k);
+          const int a = j < 2 * UN ? j : j + UN;   // r, z accumulate onto the input sums; the n gate keeps gh_n apart
+#pragma unroll
+          for (int r = 0; r < RW; ++r)
+            acc[r][a] = fmaf(hv[r].x, w.x, fmaf(hv[r].y, w.y, fmaf(hv[r].z, w.z, fmaf(hv[r].w, w.w, acc[r][a]))));
+        }
+      }
+    } else {
+      for (int k = lane; k < Kx; k += 32) {
+        float xv[RW], wv[G];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) xv[r] = xr[r][k];
+#pragma unroll
+        for (int j = 0; j < G; ++j) wv[j] = s_wi[j * Kx + k];
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+#pragma unroll
+          for (int j = 0; j < G; ++j) acc[r][j] = fmaf(xv[r], wv[j], acc[r][j]);   // r, z, gi_n
+      }
+      for (int k = lane; k < H; k += 32) {
+        float hv[RW], wv[G];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) hv[r] = hr[r][k] * mk[r];
+#pragma unroll
+        for (int j = 0; j < G; ++j) wv[j] = s_wh[j * H + k];
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+#pragma unroll
+          for (int j = 0; j < 2 * UN; ++j) acc[r][j] = fmaf(hv[r], wv[j], acc[r][j]);                       // r, z
+#pragma unroll
+          for (int u = 0; u < UN; ++u) acc[r][3 * UN + u] = fmaf(hv[r], wv[2 * UN + u], acc[r][3 * UN + u]);  // gh_n
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+      for (int j = 0; j < 4 * UN; ++j) {
+        float v = acc[r][j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[r][j] = v;
+      }
+    // lane = r * UN + u finishes row r0 + r, unit u0 + u (RW * UN = 16 lanes)
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (lane == r * UN + u && r0 + r < rows) {
+          const int row = r0 + r, k = u0 + u;
+          const float rg = sigmoid_precise(acc[r][u] + b_ih[k] + b_hh[k]);
+          const float zg = sigmoid_precise(acc[r][UN + u] + b_ih[H + k] + b_hh[H + k]);
+          const float ghn = acc[r][3 * UN + u] + b_hh[2 * H + k];
+          const float ng = tanhf(fmaf(rg, ghn, acc[r][2 * UN + u] + b_ih[2 * H + k]));
+          const float hp = h0[(size_t)row * ldh0 + k] * mk[r];
+          const float hn = fmaf(zg, hp - ng, ng);
+          out[(size_t)row * ldo + k] = hn;
+          if (out2 != nullptr) out2[(size_t)row * ldo2 + k] = hn;
+          if (hm != nullptr) hm[(size_t)row * H + k] = hp;
+          if (save != nullptr) {
+            float* sv = save + (size_t)row * 4 * H;
+            sv[k] = rg; sv[H + k] = zg; sv[2 * H + k] = ng; sv[3 * H + k] = ghn;
+          }
+        }
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // LSTM cell pointwise (habitat_baselines v0.1.7 rnn_state_encoder with rnn_type="LSTM"; torch.nn.LSTM gate order
 // i, f, g, o):  c' = s(f) c + s(i) tanh(g),  h' = s(o) tanh(c').  gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh
 // (both (rows, 4H)); c is the already mask-reset cell state.
@@ -596,6 +742,35 @@ extern "C" int vlnce_gru_pointwise_fwd(const float* gi, const float* gh, const f
   gru_pointwise_fwd_kernel<<<grid_for((long long)rows * H, 256), 256, 0, stream>>>(
       gi, gh, h, ldh, hout, ldo, hout2, ldo2, save, rows, H);
   VLNCE_LAUNCH_CHECK("gru_pointwise_fwd_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_gru_step_fwd(const float* x, long long ldx, int in_size, const float* h0, long long ldh0,
+                                  const float* mask, const float* w_ih, const float* w_hh, const float* b_ih,
+                                  const float* b_hh, float* hm, float* out, long long ldo, float* out2, long long ldo2,
+                                  float* save, int rows, int H, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(x && h0 && mask && w_ih && w_hh && b_ih && b_hh && out, "gru_step_fwd: null tensor");
+  VLNCE_CHECK_ARG(rows > 0 && H > 0 && in_size > 0 && H % kGruUN == 0, "gru_step_fwd: rows=%d H=%d in=%d", rows, H, in_size);
+  const size_t smem = sizeof(float) * 3 * kGruUN * ((size_t)in_size + H);
+  VLNCE_CHECK_ARG(smem <= 200 * 1024, "gru_step_fwd: weight slice of %zu bytes does not fit shared memory", smem);
+  const bool vec = in_size % 4 == 0 && ldx % 4 == 0 && ldh0 % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(h0) & 15) == 0;
+  static bool attr_set = false;   // (idempotent; a racing second call sets the same value)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gru_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gru_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(gru_step_fused)");
+    attr_set = true;
+  }
+  const int threads = rows > 32 ? 512 : 256;   // one warp per 4 batch rows, up to 16 warps
+  if (vec)
+    gru_step_fused_kernel<true><<<H / kGruUN, threads, smem, stream>>>(x, ldx, in_size, h0, ldh0, mask, w_ih, w_hh, b_ih,
+                                                                        b_hh, hm, out, ldo, out2, ldo2, save, rows, H);
+  else
+    gru_step_fused_kernel<false><<<H / kGruUN, threads, smem, stream>>>(x, ldx, in_size, h0, ldh0, mask, w_ih, w_hh, b_ih,
+                                                                         b_hh, hm, out, ldo, out2, ldo2, save, rows, H);
+  VLNCE_LAUNCH_CHECK("gru_step_fused_kernel");
   return VLNCE_OK;
 }
 

@@ -176,6 +176,8 @@ def set_overlap(on: bool):
     global OVERLAP
     OVERLAP = bool(on)
 F4 = 4  # sizeof(float)
+# single GRU steps of the state encoders as one fused launch (vlnce_gru_step_fwd); 0 = mask / two GEMMs / pointwise
+FUSED_GRU_STEP = _os.environ.get("VLNCE_FUSED_GRU", "1") != "0"
 
 
 def off(t: torch.Tensor, elems: int) -> int:
@@ -282,6 +284,14 @@ class HeadEngine:
                                       save)
         H = self.H
         R = T * N
+        if T == 1 and FUSED_GRU_STEP and H % 4 == 0 and 12 * (in_size + H) * F4 <= 200 * 1024:
+            # single step (act, T = 1 training): reset + both projections + gates + update in ONE launch
+            hm_all = self.buf(tag + "_hm", (R, H)) if save else None
+            sv = self.buf(tag + "_save", (R, 4 * H)) if save else None
+            C.vlnce_gru_step_fwd(x, ldx, in_size, h0, ldh0, ptr(masks_f), ptr(rnn.weight_ih_l0), ptr(rnn.weight_hh_l0),
+                                 ptr(rnn.bias_ih_l0), ptr(rnn.bias_hh_l0), ptr(hm_all), out, ldo, h_final, ldhf, ptr(sv),
+                                 N, H, lib.stream())
+            return
         gi = self.buf(tag + "_gi", (R, 3 * H))
         hm_all = self.buf(tag + "_hm", (R, H))
         gh = self.buf(tag + "_gh", (N, 3 * H))
