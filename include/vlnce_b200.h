@@ -50,6 +50,15 @@ long long vlnce_launch_count(void);
 int vlnce_set_pdl(int on);
 long long vlnce_get_pdl(void);
 
+/* Workspace sizes (host-only arithmetic; SURVEY 8b's vlnce_<op>_workspace_bytes).  Every entry point below that takes a
+ * caller-owned workspace also accepts a smaller one (it narrows its split-K / split-row plan) or NULL; these return the
+ * size with which the plan is never narrowed.  vlnce_sgemm / vlnce_sgemm_grouped / vlnce_colsum share one workspace whose
+ * first 16 KB are arrival counters (zero before first use, left zero by every call). */
+long long vlnce_sgemm_workspace_bytes(int M, int N, int K);
+long long vlnce_colsum_workspace_bytes(int M, int N);
+long long vlnce_groupnorm_workspace_bytes(int N, int HW, int C, int groups);
+long long vlnce_clip_grad_norm_workspace_bytes(long long n);
+
 /* ---- convolution trunks ------------------------------------------------------------ */
 /* Implicit-GEMM NHWC conv on tcgen05 tensor cores (16-bit operands, fp32 accumulate in TMEM):
  *   y = act(scale[k] * conv(x, w) + shift[k] (+ residual)).

@@ -40,6 +40,20 @@ def test_header_and_library_agree():
     assert b"sm_100a" in lib.C.vlnce_version()
 
 
+def test_workspace_queries_are_host_only_and_cover_the_plans():
+    """SURVEY 8b's ``vlnce_<op>_workspace_bytes``: pure host arithmetic (callable without a GPU), at least what the
+    package's own fixed-size scratch buffers provide for the benchmark shapes, zero for degenerate shapes."""
+    C = lib.C
+    assert C.vlnce_sgemm_workspace_bytes(0, 4, 4) == 0 and C.vlnce_colsum_workspace_bytes(10, 4) == 0
+    assert C.vlnce_sgemm_workspace_bytes(64, 1536, 512) == 16384 + 8 * 64 * 1536 * 4      # K / 64 = 8 partial tiles
+    assert C.vlnce_sgemm_workspace_bytes(512, 128, 5120) == 16384 + 32 * 512 * 128 * 4    # capped at 32 partials
+    assert C.vlnce_sgemm_workspace_bytes(512, 128, 5120) <= 16 << 20                      # engine.gemm_workspace
+    assert C.vlnce_colsum_workspace_bytes(5120, 512) == 16384 + 40 * 512 * 4
+    assert C.vlnce_groupnorm_workspace_bytes(64, 32 * 32, 128, 16) == 64 * 32 * 16 * 2 * 4
+    assert C.vlnce_groupnorm_workspace_bytes(64, 64 * 64, 32, 16) <= (1 << 20) * 4          # trunk.py's gn_ws
+    assert C.vlnce_clip_grad_norm_workspace_bytes(6_280_000) == 1026 * 4
+
+
 @pytest.mark.parametrize("name", ["cma_train_features", "cma_train_pixels"])
 def test_train_launch_sequence(name):
     """forward(save) -> reference loss arithmetic -> hand-written backward, launch-checked."""

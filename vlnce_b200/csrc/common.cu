@@ -95,3 +95,26 @@ extern "C" int vlnce_debug_stamp(long long* slot, cudaStream_t stream) {
   VLNCE_LAUNCH_CHECK("stamp_kernel");
   return VLNCE_OK;
 }
+
+// ---- workspace sizes (vlnce_<op>_workspace_bytes): host-only arithmetic, no CUDA call.  Every entry point
+// that takes a workspace also works with a smaller one (fewer split-K / split-row partials) or none; these return the
+// size with which the launch plan is never narrowed.
+extern "C" long long vlnce_sgemm_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const long long splits = K / 64 < 1 ? 1 : (K / 64 > 32 ? 32 : K / 64);   // gemm.cu: <= 32 partials of one (M,N) tile set
+  return 16384 /* arrival counters */ + splits * (long long)M * N * (long long)sizeof(float);
+}
+extern "C" long long vlnce_colsum_workspace_bytes(int M, int N) {
+  if (M < 256 || N <= 0) return 0;
+  const long long S = M / 128 > 64 ? 64 : M / 128;
+  return 16384 + S * N * (long long)sizeof(float);
+}
+extern "C" long long vlnce_groupnorm_workspace_bytes(int N, int HW, int C, int groups) {
+  if (N <= 0 || HW <= 0 || C <= 0 || groups <= 0) return 0;
+  const long long S = ((long long)HW * C + 4095) / 4096;   // trunk_ops.cu: 4096-element slices of an image
+  return (long long)N * S * groups * 2 * (long long)sizeof(float);
+}
+extern "C" long long vlnce_clip_grad_norm_workspace_bytes(long long n) {
+  (void)n;
+  return 1026 * (long long)sizeof(float);   // <= 1024 partial sums of squares, the norm, the clip factor
+}
