@@ -1089,6 +1089,111 @@ __global__ void resize_area_crop_kernel(const T* __restrict__ x, T* __restrict__
   }
 }
 
+// Row-staged variant (the default): one CTA per (image, group of RB output rows).  The source rows under those output
+// rows — only the column span the crop window maps back to — are copied to shared memory with 16-byte loads (the span
+// starts at an arbitrary byte, so the copy starts at the enclosing aligned address and the consumers skip `mis`
+// bytes), then one thread per output COLUMN computes its column window once and sums the RB windows out of shared
+// memory in the same order as the element-wise kernel above.  All index arithmetic is 32-bit (the host checks that
+// the products fit) and the per-column divisions are amortised over RB outputs: ncu showed the element-wise kernel
+// and the first row-staged version issue-bound (80 % issue-active at 8-13 % of DRAM throughput), seven emulated
+// 64-bit divisions per output pixel, not memory.
+constexpr int kRacRB = 4;
+
+template <typename T, int CC, int WMAX>   // WMAX: compile-time bound of the window width (0 = run-time loop)
+__global__ void __launch_bounds__(256)
+resize_area_crop_rows_kernel(const T* __restrict__ x, const T* __restrict__ x_end, T* __restrict__ y,
+                             long long y_frame_stride, int H, int W, int RH, int RW, int y0, int x0, int CH, int CW,
+                             int row_bytes /* smem bytes per staged row, multiple of 16 */, int groups /* per image */) {
+  extern __shared__ uint4 smem_rac[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>(smem_rac);
+  constexpr int RB = kRacRB;
+  __shared__ int s_geo[4];             // n, first output row, wa, wb
+  __shared__ int s_h[RB][2];           // source row range of each output row, relative to the first staged row
+  __shared__ int s_hA, s_rows;
+  __shared__ int s_mis[48];
+  if (threadIdx.x == 0) {
+    const unsigned g_ = blockIdx.x % (unsigned)groups, n_ = blockIdx.x / (unsigned)groups;
+    const unsigned oy0 = g_ * RB;
+    s_geo[0] = (int)n_; s_geo[1] = (int)oy0;
+    s_geo[2] = (int)(((unsigned)x0 * (unsigned)W) / (unsigned)RW);
+    s_geo[3] = (int)((((unsigned)x0 + (unsigned)CW) * (unsigned)W + (unsigned)RW - 1u) / (unsigned)RW);
+    int hA = 0, hB = 0;
+    for (int b = 0; b < RB; ++b) {
+      const unsigned ry = oy0 + b + (unsigned)y0;
+      const int h0 = (int)((ry * (unsigned)H) / (unsigned)RH);
+      const int h1 = (int)(((ry + 1u) * (unsigned)H + (unsigned)RH - 1u) / (unsigned)RH);
+      if (b == 0) hA = h0;
+      if ((int)oy0 + b < CH) hB = h1;
+      s_h[b][0] = h0 - hA; s_h[b][1] = h1 - hA;
+    }
+    s_hA = hA; s_rows = hB - hA;
+  }
+  __syncthreads();
+  const int n = s_geo[0], oy0 = s_geo[1], wa = s_geo[2], wb = s_geo[3], hA = s_hA, rows = s_rows;
+  const int span_bytes = (wb - wa) * CC * (int)sizeof(T);
+  const unsigned char* xb = reinterpret_cast<const unsigned char*>(x);
+  const unsigned char* xe = reinterpret_cast<const unsigned char*>(x_end);
+  for (int r = 0; r < rows; ++r) {
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(x + (((size_t)n * H + hA + r) * W + wa) * CC);
+    const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 15);
+    const unsigned char* base = src - mis;
+    if (threadIdx.x == 0) s_mis[r] = mis;
+    const int chunks = (span_bytes + mis + 15) >> 4;
+    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+      const unsigned char* p = base + i * 16;
+      uint4 v;
+      if (p >= xb && p + 16 <= xe) {
+        v = __ldg(reinterpret_cast<const uint4*>(p));
+      } else {   // the first / last bytes of the tensor: never read outside it
+        unsigned char b[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) b[e] = (p + e >= xb && p + e < xe) ? p[e] : (unsigned char)0;
+        v = *reinterpret_cast<uint4*>(b);
+      }
+      *reinterpret_cast<uint4*>(sm + r * row_bytes + i * 16) = v;
+    }
+  }
+  __syncthreads();
+  for (int ox = threadIdx.x; ox < CW; ox += blockDim.x) {
+    const unsigned rx = (unsigned)(ox + x0);
+    const int w0 = (int)((rx * (unsigned)W) / (unsigned)RW) - wa;
+    const int w1 = (int)(((rx + 1u) * (unsigned)W + (unsigned)RW - 1u) / (unsigned)RW) - wa;
+    const int wn = w1 - w0;
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+      const int oy = oy0 + b;
+      if (oy >= CH) break;
+      const int r0 = s_h[b][0], r1 = s_h[b][1];
+      float acc[CC];
+#pragma unroll
+      for (int c = 0; c < CC; ++c) acc[c] = 0.f;
+      for (int r = r0; r < r1; ++r) {   // (CTA-uniform bounds)
+        const T* row = reinterpret_cast<const T*>(sm + r * row_bytes + s_mis[r]) + w0 * CC;
+        if constexpr (WMAX > 0) {
+          // windows are 1..WMAX columns wide: a fully unrolled, predicated column loop instead of a per-thread trip
+          // count (the divergent loops' branch / reconvergence instructions were 3/4 of the instruction stream);
+          // adding the masked 0.f terms leaves the sum of the real terms, in the same order, unchanged
+#pragma unroll
+          for (int k = 0; k < WMAX; ++k) {
+            const bool on = k < wn;
+#pragma unroll
+            for (int c = 0; c < CC; ++c) acc[c] += on ? (float)row[k * CC + c] : 0.f;
+          }
+        } else {
+          for (int k = 0; k < wn; ++k) {
+#pragma unroll
+            for (int c = 0; c < CC; ++c) acc[c] += (float)row[k * CC + c];
+          }
+        }
+      }
+      const float cnt = (float)((r1 - r0) * wn);
+      T* o = y + (size_t)n * y_frame_stride + ((size_t)oy * CW + ox) * CC;
+#pragma unroll
+      for (int c = 0; c < CC; ++c) o[c] = (T)(acc[c] / cnt);
+    }
+  }
+}
+
 extern "C" int vlnce_resize_area_crop(const void* x, void* y, int dtype, long long y_frame_stride, int N, int H, int W,
                                       int C, int RH, int RW, int y0, int x0, int CH, int CW, cudaStream_t stream) {
   VLNCE_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && RH > 0 && RW > 0, "resize_area_crop: bad arguments");
@@ -1097,6 +1202,47 @@ extern "C" int vlnce_resize_area_crop(const void* x, void* y, int dtype, long lo
   if (y_frame_stride == 0) y_frame_stride = (long long)CH * CW * C;
   VLNCE_CHECK_ARG(C >= 1 && C <= 4, "resize_area_crop: 1..4 channels (C=%d)", C);
   const long long total = (long long)N * CH * CW;
+  // row-staged kernel when the source rows under one output row fit a modest shared-memory budget (always, for the
+  // sensor sizes of the reference: 480x640 -> 256 -> 224 / 256); VLNCE_RESIZE_ROWS=0 keeps the element-wise kernel
+  {
+    static const bool rows_on = [] { const char* e = getenv("VLNCE_RESIZE_ROWS"); return !(e && e[0] == '0'); }();
+    const int esz = dtype == VLNCE_U8 ? 1 : 4;
+    const int wa = (int)(((long long)x0 * W) / RW), wb = (int)((((long long)x0 + CW) * W + RW - 1) / RW);
+    const int row_bytes = (((wb - wa) * C * esz + 15 + 15) / 16) * 16;
+    const int max_rows = kRacRB * ((H + RH - 1) / RH) + 2;   // source rows under kRacRB consecutive output rows
+    const long long smem = (long long)row_bytes * max_rows + 64;   // + slack for the predicated-off reads of the last row
+    const int wmax = (W + RW - 1) / RW + 1;                         // widest window of any output column
+    const int groups = (CH + kRacRB - 1) / kRacRB;
+    if (rows_on && (dtype == VLNCE_U8 || dtype == VLNCE_F32) && max_rows <= 48 && smem <= 48 * 1024 &&
+        (long long)N * groups < (1ll << 31) && ((long long)RH + 1) * H + RH < (1ll << 32) &&
+        ((long long)RW + 1) * W + RW < (1ll << 32)) {
+#define VLNCE_RACR(T, CC)                                                                                              \
+  if (wmax <= 3)                                                                                                       \
+    resize_area_crop_rows_kernel<T, CC, 3><<<(unsigned)(N * groups), 256, (size_t)smem, stream>>>(                     \
+        (const T*)x, (const T*)x + (size_t)N * H * W * C, (T*)y, y_frame_stride, H, W, RH, RW, y0, x0, CH, CW,         \
+        row_bytes, groups);                                                                                            \
+  else                                                                                                                 \
+    resize_area_crop_rows_kernel<T, CC, 0><<<(unsigned)(N * groups), 256, (size_t)smem, stream>>>(                     \
+        (const T*)x, (const T*)x + (size_t)N * H * W * C, (T*)y, y_frame_stride, H, W, RH, RW, y0, x0, CH, CW,         \
+        row_bytes, groups)
+#define VLNCE_RACR_C(T)                       \
+  switch (C) {                                \
+    case 1: VLNCE_RACR(T, 1); break;          \
+    case 2: VLNCE_RACR(T, 2); break;          \
+    case 3: VLNCE_RACR(T, 3); break;          \
+    default: VLNCE_RACR(T, 4); break;         \
+  }
+      if (dtype == VLNCE_U8) {
+        VLNCE_RACR_C(unsigned char)
+      } else {
+        VLNCE_RACR_C(float)
+      }
+#undef VLNCE_RACR_C
+#undef VLNCE_RACR
+      VLNCE_LAUNCH_CHECK("resize_area_crop_rows_kernel");
+      return VLNCE_OK;
+    }
+  }
 #define VLNCE_RAC(T, CC)                                                                                      \
   resize_area_crop_kernel<T, CC><<<grid_for(total, 128), 128, 0, stream>>>((const T*)x, (T*)y, y_frame_stride, N, H, W, \
                                                                            RH, RW, y0, x0, CH, CW)
