@@ -323,7 +323,15 @@ static int launch_group(Group& g, float* workspace, size_t workspace_bytes, cuda
   const size_t ws_floats = can_split ? (workspace_bytes - kCounterBytes) / sizeof(float) : 0;
   size_t ws_used = 0;
   int ctr_used = 0, ctas = 0, red_ctas = 0;
-  const int budget = 296 / g.count > 8 ? 296 / g.count : 8;
+  // CTAs a launch may spread its split-K over: ~2 waves of the 148 SMs finishes a lone GEMM soonest; inside the pipelined
+  // step (every SM already busy with the trunks) a smaller budget trades latency for less partial-sum traffic
+  // (VLNCE_GEMM_BUDGET; measured in DESIGN 6)
+  static int total_budget = -1;
+  if (total_budget < 0) {
+    const char* e = getenv("VLNCE_GEMM_BUDGET");
+    total_budget = (e != nullptr && atoi(e) > 0) ? atoi(e) : 296;
+  }
+  const int budget = total_budget / g.count > 8 ? total_budget / g.count : 8;
   for (int i = 0; i < g.count; ++i) {
     Prob& P = g.p[i];
     P.tiles_n = cdiv(P.N, TN);

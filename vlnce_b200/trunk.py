@@ -72,7 +72,9 @@ HALO = 1 << 24  # tuning-code flag: TMA-halo 3x3 kernel instead of the generic t
 TMAP = 1 << 25  # tuning-code flag: persistent TMA-fed kernel (1x1 rows / 3x3 halo, overlapped epilogue)
 S2TMA = 1 << 26  # tuning-code flag: stride-2 conv (1x1 / 3x3) through the strided-box TMA mode of the persistent kernel
 EXCL = 1 << 20  # launch flag understood by the conv entry points: one CTA per SM
-TF32_BLOCK_N = int(_os.environ.get("VLNCE_TF32_BLOCK_N", "0"))  # tile width of the tf32 mode (0 = library default, 64)
+# tile width of the tf32 mode where the filter count allows it (else the library default 64); measured on the B200 at 64
+# rows (RGB trunk): 64 -> 5.41 ms, 128 -> 3.72 ms, 256 -> 4.12 ms, 64 / 128 with two pixel sub-tiles -> 4.04 / 3.88 ms
+TF32_BLOCK_N = int(_os.environ.get("VLNCE_TF32_BLOCK_N", "128"))
 RGB_EXCLUSIVE = _os.environ.get("VLNCE_RGB_EXCLUSIVE", "0") != "0"
 # fp16 instead of fp32 raw conv output under GroupNorm (depth trunk): half the bytes of the statistics/apply passes
 GN_RAW16 = _os.environ.get("VLNCE_GN_RAW16", "0") != "0"
@@ -393,16 +395,17 @@ class ConvTrunk:
                 chan_ok = c % 32 == 0 and (cv.K % 64 == 0 or (cv.K == 32 and scale is None and residual is None))
                 small3 = (geo == (3, 3, 1, 1) and residual is None and h < 16 and w % 8 == 0 and 128 % (8 * h) == 0
                           and n % (128 // (8 * h)) == 0)   # 8x8 / 4x8 images: several per tile (tap-shifted boxes)
+                bn32 = TF32_BLOCK_N if (TF32_BLOCK_N and cv.K % (TF32_BLOCK_N & 0xffff) == 0) else 0
                 if chan_ok and (geo == (1, 1, 1, 0) or (geo == (3, 3, 1, 1) and h % 16 == 0 and w % 8 == 0) or small3):
                     C.vlnce_conv_tma(ptr(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift), ptr(residual), ptr(y), lib.F32,
-                                     n, h, w, c, cv.K, cv.R, int(relu), TF32_BLOCK_N, st)
+                                     n, h, w, c, cv.K, cv.R, int(relu), bn32, st)
                     return
                 if (chan_ok and residual is None and geo in ((1, 1, 2, 0), (3, 3, 2, 1)) and h % 2 == 0 and w % 2 == 0
                         and (w // 2) % 8 == 0):
                     bh = min(16, h // 2)
                     if (h // 2) % bh == 0 and 128 % (8 * bh) == 0 and n % (128 // (8 * bh)) == 0:
                         C.vlnce_conv_s2_tma(ptr(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift), ptr(y), lib.F32, n, h, w, c,
-                                            cv.K, cv.R, int(relu), TF32_BLOCK_N, st)
+                                            cv.K, cv.R, int(relu), bn32, st)
                         return
                 if c % 32 == 0 and not _os.environ.get("VLNCE_NO_WARP"):   # what the tiles do not cover (4x4 images, odd sizes): fp32 on CUDA cores, one warp per
                     # 8 pixels x 4 filters with the lanes across the input channels
