@@ -88,7 +88,9 @@ int vlnce_conv2d_stem_rgb(const void* x, int x_dtype, const void* w, int ab_dtyp
  * accumulators).  C % 64 == 0, K % 64 == 0; same epilogue contract as vlnce_conv2d_bf16.
  * ab_dtype VLNCE_F32 selects the fp32-storage mode: x, w, residual and y are fp32, the products run on
  * the tensor cores as TF32 (tcgen05 kind::tf32, fp32 accumulation) — what stock PyTorch / cuDNN do for
- * fp32 convolutions on this GPU; C % 32 == 0 then.
+ * fp32 convolutions on this GPU; C % 32 == 0 then.  The fp32 outputs are rounded to the nearest TF32 value (they feed
+ * the next layer's TF32 products) unless bit 1 of `relu` is set (relu = 2 | 3: plain fp32 result — the R = 1 mode used
+ * as a GEMM  y[M,K] = x[M,C] w[K,C]^T * scale + shift  by the head's large projections, N*H*W = M).
  * block_n: 0 = auto, else width (64/128/256) | weight-ring depth << 16 | (1 << 21): two 128-pixel
  * sub-tiles per scheduled tile share every weight stage (halves the weight bytes per MAC pulled from
  * L2; needs an even tile count and width <= 128) | (1 << 22): never keep the CTA's weight slice
@@ -318,6 +320,13 @@ int vlnce_spatial_embed_fill(const float* table, float* E, long long lde_r, long
                              int c_off, int R, int P, int Cs, cudaStream_t stream);
 int vlnce_positions_to_nchw(const float* E, long long lde_r, long long lde_p, float* out,
                             long long ldo, int R, int P, int C, cudaStream_t stream);
+/* dst[c*ldd + r] = src[r*lds + c] (fp32, 32x32 smem tiles), optionally rounded to the nearest TF32 value; and the
+ * element-wise rounding alone (dst may equal src).  Operand preparation of the TF32 tensor-core GEMMs of the head
+ * (instruction-feature input projection and its weight gradient, instruction_encoder.py:27,80-94): kind::tf32 would
+ * truncate un-rounded operands, a systematic 2^-10 bias on every product. */
+int vlnce_transpose_f32(const float* src, long long lds, float* dst, long long ldd, int rows, int cols, int round_tf32,
+                        cudaStream_t stream);
+int vlnce_round_tf32(const float* src, float* dst, long long n, cudaStream_t stream);
 int vlnce_log_softmax_rows(float* x, int rows, int A, cudaStream_t stream);
 int vlnce_argmax_rows(const float* x, long long* out, int rows, int A, cudaStream_t stream);
 

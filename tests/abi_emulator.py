@@ -251,6 +251,12 @@ class Emulator:
         if save:
             _mat(save, rows, 5 * H, 5 * H)[...] = np.concatenate([i, f, g, o, tc], 1)
 
+    def transpose_f32(self, src, lds, dst, ldd, rows, cols, round_tf32, st):
+        _mat(dst, cols, rows, ldd)[...] = _mat(src, rows, cols, lds).T      # (host model: no TF32 rounding)
+
+    def round_tf32(self, src, dst, n, st):
+        _flat(dst, n)[...] = _flat(src, n)
+
     def mask_rows(self, h, ldh, mask, out, ldo, rows, H, st):
         _mat(out, rows, H, ldo)[...] = _mat(h, rows, H, ldh) * _flat(mask, rows)[:, None]
 
@@ -966,7 +972,7 @@ def _epilogue(out, scale, shift, residual, res_code, relu, y, y_code, shape):
         out = out * _tt(scale, (K,)).view(1, K, 1, 1) + _tt(shift, (K,)).view(1, K, 1, 1)
     if residual:
         out = out + _tt16(residual, (N, P, Q, K), res_code).float().permute(0, 3, 1, 2)
-    if relu:
+    if relu & 1:   # (bit 1 = keep the plain fp32 result: GEMM use of the TF32 tiles)
         out = out.clamp_min(0)
     yt = _tt16(y, (N, P, Q, K), y_code)
     yt.copy_(out.permute(0, 2, 3, 1).to(yt.dtype))

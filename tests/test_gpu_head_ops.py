@@ -155,6 +155,40 @@ def test_gru_cell_matches_torch():
     torch.testing.assert_close(out, want[0], rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("m,n,k", [(4096, 512, 768), (1000, 192, 96), (1024, 768, 2048)])
+def test_tensor_core_head_gemm_matches_fp64(m, n, k):
+    """engine.linear_tc: the persistent TMA tile's 1x1 mode as a TF32 GEMM (operands rounded to nearest TF32 by
+    vlnce_round_tf32 / vlnce_transpose_f32, fp32 accumulation, plain fp32 result).  Error model: two 2^-11 operand
+    roundings per product, random signs -> ~1e-3 of the result's scale at k ~ 1000."""
+    from vlnce_b200.engine import linear_tc
+    x, w, b = _r(m, k), _r(n, k, scale=k ** -0.5), _r(n)
+    xr, wr = torch.empty_like(x), torch.empty_like(w)
+    C.vlnce_round_tf32(ptr(x), ptr(xr), x.numel(), lib.stream())
+    C.vlnce_round_tf32(ptr(w), ptr(wr), w.numel(), lib.stream())
+    assert ((xr.view(torch.int32) & 0x1FFF) == 0).all() and (xr - x).abs().max() <= x.abs().max() * 2.0 ** -11
+    out = torch.full((m, n), float("nan"), device=DEV)
+    linear_tc(ptr(xr), ptr(wr), ptr(out), ptr(b), m, n, k, x.device)
+    want = (x.double() @ w.double().t() + b.double()).float()
+    err = (out - want).abs().max().item() / want.abs().max().item()
+    print(f"tf32 gemm {m}x{n}x{k}: max err / max |y| = {err:.2e}")
+    assert torch.isfinite(out).all() and err < 3e-3
+    exact = (xr.double() @ wr.double().t() + b.double()).float()        # same rounded operands: only fp32 accumulation left
+    assert (out - exact).abs().max().item() <= 2e-5 * want.abs().max().item()
+    # the weight-gradient form: transposed (token-minor) operands, no bias
+    dy = _r(m, n, seed=7)
+    dyt, xt = torch.empty(n, m, device=DEV), torch.empty(k, m, device=DEV)
+    C.vlnce_transpose_f32(ptr(dy), n, ptr(dyt), m, m, n, 1, lib.stream())
+    C.vlnce_transpose_f32(ptr(xr), k, ptr(xt), m, m, k, 0, lib.stream())
+    assert torch.equal(xt, xr.t().contiguous())
+    if m % 32 == 0 and k % 64 == 0:
+        dw = torch.full((n, k), float("nan"), device=DEV)
+        linear_tc(ptr(dyt), ptr(xt), ptr(dw), None, n, k, m, x.device)
+        want_dw = (dy.double().t() @ x.double()).float()
+        err = (dw - want_dw).abs().max().item() / want_dw.abs().max().item()
+        print(f"tf32 weight-gradient gemm: max err / max |dW| = {err:.2e}")
+        assert err < 3e-3
+
+
 @pytest.mark.parametrize("N,I,H", [(64, 416, 512), (7, 1184, 512), (1, 33, 64), (130, 50, 128)])
 def test_fused_gru_step_matches_torch_and_unfused(N, I, H):
     """vlnce_gru_step_fwd (reset + both projections + gates + update in one launch) against torch.nn.GRU on the CPU and

@@ -64,6 +64,9 @@ def check(got, want, rtol, name, grad_norm_tol=None):
     ("cma_train_features", "fp32", 1e-3), ("cma_train_features_nopm", "fp32", 1e-3),
     ("cma_rxr_train_features", "fp32", 1e-3),  # BASELINE C5 family: RxR BERT-feature instructions, 6 actions
     ("cma_rxr_train_features_l512", "fp32", 1e-3),   # C5 at its real instruction shape (R, 512, 768)
+    # the same in the default precision mode: 4 x 512 = 2048 token rows put the instruction-feature input projection
+    # and its weight gradient on the TF32 tensor-core tiles (engine.HEAD_TC_MIN_ROWS)
+    ("cma_rxr_train_features_l512", "bf16", 1e-2),
     ("cma_train_pixels", "fp32", 1e-3), ("cma_train_pixels", "bf16", 1e-2),
     ("seq2seq_train_features", "fp32", 1e-3), ("seq2seq_train_pixels", "fp32", 1e-3),
     ("seq2seq_train_pixels", "bf16", 1e-2)])

@@ -51,6 +51,36 @@ def test_il_train_plan_matches_golden(name):
     print(name, "worst", worst)
 
 
+def test_rxr_instruction_projection_takes_the_tensor_core_route(monkeypatch):
+    """Reduced-precision modes put the RxR instruction-feature input projection and its weight gradient on the TF32
+    tensor-core tiles once the batch has enough token rows (engine.HEAD_TC_MIN_ROWS): rounded operands, one
+    ``vlnce_conv_tma`` (1x1 mode = GEMM, plain fp32 result) per direction forward, transposed token-minor operands and
+    ONE stacked launch for both directions' weight gradients.  The host model multiplies in exact fp32, so this checks
+    the routing, the transposes and the gradient placement; precision="fp32" must stay on the CUDA-core GEMM."""
+    from vlnce_b200 import engine
+
+    monkeypatch.setattr(engine, "HEAD_TC_MIN_ROWS", 64)
+    name = "cma_rxr_train_features"        # 9 rows x 40 tokens = 360 token rows... not a multiple of 32: forward only
+    with lib.dry_run(executor=Emulator()) as rec:
+        got = cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, precision="bf16")
+    assert rec.calls.count("vlnce_conv_tma") == 2 and rec.calls.count("vlnce_round_tf32") == 3
+    assert "vlnce_transpose_f32" not in rec.calls
+    print(name, "tensor-core projection worst", check(got, gold(name), 2e-4))
+    with lib.dry_run(executor=Emulator()) as rec:
+        cases.run_case(vlnce_b200, name, aux=vlnce_b200.AuxLosses, precision="fp32")
+    assert "vlnce_conv_tma" not in rec.calls
+    # a batch whose token-row count is a multiple of 32 (8 rows x 40 tokens) also takes the weight-gradient route:
+    # same gradients as the CUDA-core plan of the same batch
+    monkeypatch.setitem(cases.CASES, "_rxr_tc", dict(cases.CASES[name], t=2, n=4))
+    with lib.dry_run(executor=Emulator()) as rec:
+        tc = cases.run_case(vlnce_b200, "_rxr_tc", aux=vlnce_b200.AuxLosses, precision="bf16")
+    assert rec.calls.count("vlnce_conv_tma") == 3 and rec.calls.count("vlnce_transpose_f32") == 3
+    monkeypatch.setattr(engine, "HEAD_TC_MIN_ROWS", 0)
+    with lib.dry_run(executor=Emulator()):
+        simt = cases.run_case(vlnce_b200, "_rxr_tc", aux=vlnce_b200.AuxLosses, precision="bf16")
+    print("tensor-core weight-gradient route vs CUDA-core plan worst", check(tc, simt, 2e-5))
+
+
 # ---------------------------------------------------------------------------------------------
 # waypoint path: the conv trunks are not emulated — their features come from the oracle's trunks
 # ---------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ from typing import Dict, Optional
 import torch
 
 from . import lib
-from .engine import F4, Branch, CMAEngine, gemm_group, linear, linear_dw, linear_dx, off
+from .engine import linear_tc, F4, Branch, CMAEngine, gemm_group, linear, linear_dw, linear_dx, off
 from .lib import C, ptr
 
 
@@ -160,10 +160,26 @@ def instruction_backward(eng, g: Dict[str, torch.Tensor], d_instr: torch.Tensor)
     emb_trainable = ie.config.sensor_uuid == "instruction" and ie.embedding_layer.weight.requires_grad
     d_emb = b("d_instr_emb", (R * L, E)) if emb_trainable else None
     pfx = "net.instruction_encoder.encoder_rnn."
+    M = R * L
+    tc = bool(cx.get("instr_tc")) and M % 32 == 0 and E % 64 == 0
+    if tc:
+        # weight gradient of the input projection on the tensor cores: dW[d] = dgx[d]^T @ features is the TMA tile's GEMM
+        # with the token axis as the reduction dimension — both operands transposed to token-minor (and rounded to TF32)
+        # first; the directions are stacked into ONE (dirs*G, M) x (E, M)^T launch
+        emb_t = b("instr_emb_t_tf32", (E, M))
+        C.vlnce_transpose_f32(ptr(b("instr_emb_tf32", (M, E))), E, ptr(emb_t), M, M, E, 0, lib.stream())
+        dgx_t = b("lstm_dgx_t_tf32", (dirs * G, M))
+        for d in range(dirs):
+            C.vlnce_transpose_f32(off(dgx, d * M * G), G, off(dgx_t, d * G * M), M, M, G, 1, lib.stream())
+        dw_all = b("instr_dwih", (dirs * G, E))
+        linear_tc(ptr(dgx_t), ptr(emb_t), ptr(dw_all), None, dirs * G, E, M, dgx.device)
+        for d, sfx in enumerate(["", "_reverse"][:dirs]):
+            g[pfx + "weight_ih_l0" + sfx].copy_(dw_all[d * G:(d + 1) * G])
     with gemm_group():  # every problem of this block is independent of the others: one launch
         for d, sfx in enumerate(["", "_reverse"][:dirs]):
             dg, dh_ = off(dgx, d * R * L * G), off(dgh, d * R * L * G)
-            linear_dw(dg, G, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, G, E)
+            if not tc:
+                linear_dw(dg, G, ptr(emb_in), E, ptr(g[pfx + "weight_ih_l0" + sfx]), E, R * L, G, E)
             linear_dw(dh_, G, off(hprev, d * R * L * Hs), Hs, ptr(g[pfx + "weight_hh_l0" + sfx]), Hs, R * L, G, Hs)
             _colsum(dg, G, ptr(g[pfx + "bias_ih_l0" + sfx]), R * L, G)
             _colsum(dh_, G, ptr(g[pfx + "bias_hh_l0" + sfx]), R * L, G)

@@ -546,11 +546,11 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                 f[q4 * 4] += r0; f[q4 * 4 + 1] += r1; f[q4 * 4 + 2] += r2; f[q4 * 4 + 3] += r3;
               }
             }
-            if (p.relu) {
+            if (p.relu & 1) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-            if (p.tf32) {
+            if (p.tf32 && !(p.relu & 2)) {   // (relu bit 1: GEMM use — the fp32 result is final, keep every bit)
               // the next layer's kind::tf32 MMA drops the low 13 mantissa bits of what it reads: round to nearest
               // here (cvt.rna.tf32.f32), so the activation chain carries unbiased TF32 values instead of truncated ones
 #pragma unroll
@@ -595,7 +595,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float a = f[q4 * 8 + e * 2], b = f[q4 * 8 + e * 2 + 1];
-                if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                if (p.relu & 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                 if (p.ab_half) {
                   __half2 h2 = __floats2half2_rn(a, b);
                   o[e] = *reinterpret_cast<uint32_t*>(&h2);

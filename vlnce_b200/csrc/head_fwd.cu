@@ -745,6 +745,54 @@ extern "C" int vlnce_gru_pointwise_fwd(const float* gi, const float* gh, const f
   return VLNCE_OK;
 }
 
+namespace vlnce {
+namespace {
+__device__ __forceinline__ float round_tf32_dev(float v) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+  return __uint_as_float(t);
+}
+__global__ void transpose_f32_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
+                                     int rows, int cols, int round_tf32) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * lds + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) {
+      const float v = tile[threadIdx.x][i];
+      dst[(size_t)c * ldd + r] = round_tf32 ? round_tf32_dev(v) : v;
+    }
+  }
+}
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = round_tf32_dev(src[i]);
+}
+}  // namespace
+}  // namespace vlnce
+
+extern "C" int vlnce_transpose_f32(const float* src, long long lds, float* dst, long long ldd, int rows, int cols,
+                                   int round_tf32, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(src && dst && rows > 0 && cols > 0 && lds >= cols && ldd >= rows, "transpose_f32: bad arguments");
+  VLNCE_CHECK_ARG((rows + 31) / 32 <= 65535, "transpose_f32: too many rows");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_f32_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, lds, dst, ldd, rows, cols, round_tf32);
+  VLNCE_LAUNCH_CHECK("transpose_f32_kernel");
+  return VLNCE_OK;
+}
+
+extern "C" int vlnce_round_tf32(const float* src, float* dst, long long n, cudaStream_t stream) {
+  VLNCE_CHECK_ARG(src && dst && n > 0, "round_tf32: bad arguments");
+  round_tf32_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, dst, n);
+  VLNCE_LAUNCH_CHECK("round_tf32_kernel");
+  return VLNCE_OK;
+}
+
 extern "C" int vlnce_gru_step_fwd(const float* x, long long ldx, int in_size, const float* h0, long long ldh0,
                                   const float* mask, const float* w_ih, const float* w_hh, const float* b_ih,
                                   const float* b_hh, float* hm, float* out, long long ldo, float* out2, long long ldo2,

@@ -168,6 +168,46 @@ def linear_dw(dy, lddy, x, ldx, dw, lddw, rows, n_out, n_in, beta=0.0):
 
 import os as _os
 
+# Large head GEMMs on the tensor cores (TF32 products, fp32 accumulation; the persistent TMA tile's 1x1 mode as a GEMM):
+# the instruction-feature input projection and its weight gradient at RxR size (512 tokens x 768 features: 2 x 12.9
+# GFLOP each way per 32 rows — the fp32 CUDA-core GEMM made the C5 step head-bound).  Used by the reduced-precision modes
+# (precision "bf16" / "tf32", 1e-2 class) for problems with at least this many rows; precision "fp32" keeps CUDA cores.
+HEAD_TC_MIN_ROWS = int(_os.environ.get("VLNCE_HEAD_TC_MIN_ROWS", "2048"))
+_ONES: Dict[tuple, torch.Tensor] = {}
+
+
+def _ones(n: int, device) -> torch.Tensor:
+    key = (n, str(device))
+    t = _ONES.get(key)
+    if t is None:
+        t = _ONES[key] = torch.ones(n, dtype=torch.float32, device=device)
+    return t
+
+
+def tc_gemm_ok(precision: str, rows: int, n_out: int, n_in: int) -> bool:
+    return (precision != "fp32" and HEAD_TC_MIN_ROWS > 0 and rows >= HEAD_TC_MIN_ROWS and n_in % 32 == 0
+            and n_out % 64 == 0)
+
+
+def linear_tc(x_r, w_r, out, bias, rows: int, n_out: int, n_in: int, device):
+    """out[rows, n_out] = x_r[rows, n_in] @ w_r[n_out, n_in]^T + bias on tcgen05 (kind::tf32); all matrices contiguous,
+    operands already rounded to TF32 (``vlnce_round_tf32`` / ``vlnce_transpose_f32``).  bias None = 0."""
+    shift = bias if bias is not None else _zeros(n_out, device).data_ptr()
+    C.vlnce_conv_tma(x_r, w_r, lib.F32, _ones(n_out, device).data_ptr(), shift, None, out, lib.F32, 1, 1, rows, n_in,
+                     n_out, 1, 2, 128 if n_out % 128 == 0 else 64, lib.stream())
+
+
+_ZEROS: Dict[tuple, torch.Tensor] = {}
+
+
+def _zeros(n: int, device) -> torch.Tensor:
+    key = (n, str(device))
+    t = _ZEROS.get(key)
+    if t is None:
+        t = _ZEROS[key] = torch.zeros(n, dtype=torch.float32, device=device)
+    return t
+
+
 OVERLAP = _os.environ.get("VLNCE_OVERLAP", "1") != "0"  # multi-stream branches on/off
 
 
@@ -247,10 +287,21 @@ class HeadEngine:
         gx = self.buf("lstm_gx", (dirs, R, L, gates * Hs))
         wih = [rnn.weight_ih_l0] + ([rnn.weight_ih_l0_reverse] if dirs == 2 else [])
         bih = [rnn.bias_ih_l0] + ([rnn.bias_ih_l0_reverse] if dirs == 2 else [])
-        with gemm_group():  # both directions' input projections: one launch
+        G = gates * Hs
+        self.ctx["instr_tc"] = tc_gemm_ok(self.precision, R * L, G, E)
+        if self.ctx["instr_tc"]:
+            # tensor-core input projection: operands rounded to TF32 once (the rounded features are kept for the
+            # weight gradient), one persistent TMA-tile launch per direction
+            emb_r = self.buf("instr_emb_tf32", (R * L, E))
+            C.vlnce_round_tf32(ptr(emb), ptr(emb_r), R * L * E, st)
+            w_r = self.buf("instr_wih_tf32", (dirs, G, E))
             for d in range(dirs):
-                linear(ptr(emb), E, ptr(wih[d]), off(gx, d * R * L * gates * Hs), gates * Hs, ptr(bih[d]), R * L,
-                       gates * Hs, E)
+                C.vlnce_round_tf32(ptr(wih[d]), off(w_r, d * G * E), G * E, st)
+                linear_tc(ptr(emb_r), off(w_r, d * G * E), off(gx, d * R * L * G), ptr(bih[d]), R * L, G, E, emb.device)
+        else:
+            with gemm_group():  # both directions' input projections: one launch
+                for d in range(dirs):
+                    linear(ptr(emb), E, ptr(wih[d]), off(gx, d * R * L * G), G, ptr(bih[d]), R * L, G, E)
         instr = self.buf("instr_out", (R, L, dirs * Hs))
         hn = self.buf("lstm_hn", (dirs, R, Hs))
         whh_b = ptr(rnn.weight_hh_l0_reverse) if dirs == 2 else None
