@@ -83,7 +83,8 @@ int vlnce_conv2d_stem_rgb(const void* x, int x_dtype, const void* w, int ab_dtyp
                           int block_n, cudaStream_t stream);
 
 /* Persistent, fully TMA-fed tiles for stride-1 convolutions (R = 1: 1x1 pad 0 over the [M,C] row
- * matrix; R = 3: 3x3 pad 1 with halo boxes, needs H % 16 == 0 and W % 8 == 0): one CTA per SM claims
+ * matrix; R = 3: 3x3 pad 1 with halo boxes over 16x8-pixel tiles, H >= 8 and W >= 8 — sizes that are not multiples of
+ * the tile get ragged border tiles, the TMA unit zero-fills / clips what lies outside the image): one CTA per SM claims
  * tiles from a per-launch counter, the epilogue of tile i-1 overlaps the accumulation of tile i (two TMEM
  * accumulators).  C % 64 == 0, K % 64 == 0; same epilogue contract as vlnce_conv2d_bf16.
  * ab_dtype VLNCE_F32 selects the fp32-storage mode: x, w, residual and y are fp32, the products run on

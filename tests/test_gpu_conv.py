@@ -171,6 +171,11 @@ TMA_CASES = [
     (3, 32, 32, 128, 128, 3, 128, "affine_res_relu"),
     (24, 32, 16, 64, 128, 3, 64, "affine_res_relu"),       # 192 patches x 2 n-tiles, persistent halo
     (2, 16, 8, 256, 256, 3, 256, "raw"),
+    # ragged border tiles (maps of 224-pixel frames): the TMA unit zero-fills the load boxes and clips the store boxes
+    (3, 56, 56, 64, 64, 3, 64, "affine_relu"),             # 4 x 7 tiles per image, the last tile row half outside
+    (4, 28, 28, 128, 128, 3, 128, "affine_res_relu"),      # ragged in both directions, residual boxes clipped too
+    (5, 14, 14, 256, 256, 3, 128, "raw"),                  # one tile row of 16 with 14 valid rows; odd tile count (no pairs)
+    (2, 20, 12, 64, 128, 3, 0, "affine"),
 ]
 
 
@@ -222,6 +227,8 @@ TF32_CASES = [
     (4, 32, 32, 32, 32, 3, 1, 0, "raw"),
     (6, 32, 32, 128, 32, 1, 1, 0, "raw"),
     (8, 8, 8, 256, 256, 3, 1, 64, "affine_relu"),           # 8x8 images: two per tile, tap-shifted boxes
+    (3, 28, 28, 128, 128, 3, 1, 128, "affine_res_relu"),    # ragged border tiles, fp32 residual boxes
+    (2, 14, 14, 64, 64, 3, 1, 0, "raw"),
 ]
 
 

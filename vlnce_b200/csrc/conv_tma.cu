@@ -858,7 +858,10 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
   // weight box reads rows 32..63 out of bounds (zeros), the store skips the columns past K
   const bool k32 = tf32 && K == 32 && scale == nullptr && residual == nullptr;
   VLNCE_CHECK_ARG(C % kc == 0 && (K % 64 == 0 || k32), "conv_tma: C must be a multiple of %d and K of 64", kc);
-  VLNCE_CHECK_ARG(R == 1 || (H % TH == 0 && W % TW == 0), "conv_tma: 3x3 needs H %% 16 == 0 and W %% 8 == 0");
+  // 3x3: 16x8-pixel tiles; an image whose height / width is not a multiple of the tile is covered by ragged border
+  // tiles — the TMA unit zero-fills the part of a load box that lies outside the tensor (exactly the conv's zero padding)
+  // and clips the store box, so nothing else in the kernel knows (224-pixel frames: 56 / 28 / 14-pixel feature maps)
+  VLNCE_CHECK_ARG(R == 1 || (H >= 8 && W >= TW), "conv_tma: 3x3 needs H >= 8 and W >= 8 (smaller images: the box mode)");
   VLNCE_CHECK_ARG((scale == nullptr) == (shift == nullptr), "conv_tma: scale/shift must come together");
   VLNCE_CHECK_ARG(ab_dtype == VLNCE_BF16 || ab_dtype == VLNCE_F16 || tf32, "conv_tma: operand dtype");
   VLNCE_CHECK_ARG(y_dtype == ab_dtype || y_dtype == VLNCE_F32, "conv_tma: y dtype");
@@ -929,7 +932,7 @@ extern "C" int vlnce_conv_tma(const void* x, const void* w, int ab_dtype, const 
       if ((rc = map_nd(enc, &tr, residual, dt16, 4, yd, rs, rb, "residual")) != VLNCE_OK) return rc;
     }
     p.mode = 1; p.taps = 9; p.halo_w = TW + 2; p.a_bytes = 23 * 1024; p.a_tx = (TW + 2) * (TH + 2) * 128; p.img_per_tile = 1; p.cpt = 1; p.rcp_cpt = 1.f; p.taps_s2 = 1; p.box_stride = 1;
-    p.tiles_x = W / TW; p.tiles_y = H / TH; p.m_tiles = N * p.tiles_x * p.tiles_y; p.tw = TW; p.th = TH;
+    p.tiles_x = cdiv(W, TW); p.tiles_y = cdiv(H, TH); p.m_tiles = N * p.tiles_x * p.tiles_y; p.tw = TW; p.th = TH;
   }
   p.scale = scale; p.shift = shift;
   p.M = (int)M; p.N = N; p.H = H; p.W = W; p.C = C; p.K = K;

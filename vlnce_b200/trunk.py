@@ -76,6 +76,7 @@ EXCL = 1 << 20  # launch flag understood by the conv entry points: one CTA per S
 # rows (RGB trunk): 64 -> 5.41 ms, 128 -> 3.72 ms, 256 -> 4.12 ms, 64 / 128 with two pixel sub-tiles -> 4.04 / 3.88 ms
 TF32_BLOCK_N = int(_os.environ.get("VLNCE_TF32_BLOCK_N", "128"))
 RGB_EXCLUSIVE = _os.environ.get("VLNCE_RGB_EXCLUSIVE", "0") != "0"
+RAGGED_TMA = _os.environ.get("VLNCE_RAGGED_TMA", "1") != "0"  # persistent TMA 3x3 tiles on maps that are not multiples of 16x8
 # fp16 instead of fp32 raw conv output under GroupNorm (depth trunk): half the bytes of the statistics/apply passes
 GN_RAW16 = _os.environ.get("VLNCE_GN_RAW16", "0") != "0"
 DEPTH_CHUNKS = int(_os.environ.get("VLNCE_DEPTH_CHUNKS", "1"))  # independent batch chunks of the depth trunk
@@ -354,7 +355,10 @@ class ConvTrunk:
             c_in = geom[3] if not (stem_rgb or stem_s2d) else 0
             tma_ok = (PERSISTENT and not stem_rgb and not stem_s2d and c_in % 64 == 0 and cv.K % 64 == 0 and geom[7:] in ((1, 0), (1, 1))
                       and ((geom[5] == 1 and geom[8] == 0)
-                           or (geom[5] == 3 and geom[8] == 1 and geom[1] % 16 == 0 and geom[2] % 8 == 0)))
+                           # 3x3: 16x8-pixel halo tiles; sizes that are not multiples of the tile (224-pixel frames: 56 / 28 /
+                           # 14-pixel maps) get ragged border tiles, zero-filled / clipped by the TMA unit
+                           or (geom[5] == 3 and geom[8] == 1 and (RAGGED_TMA or (geom[1] % 16 == 0 and geom[2] % 8 == 0))
+                               and geom[1] >= 14 and geom[2] >= 8)))
             halo_ok = (HALO_3X3 and not stem_rgb and gemm_c is None and cv.R == 3 and cv.S == 3 and cv.stride == 1
                        and cv.pad == 1 and c % 64 == 0 and cv.K % 64 == 0 and h % 16 == 0 and w % 8 == 0)
             s2_ok = False
@@ -396,7 +400,8 @@ class ConvTrunk:
                 small3 = (geo == (3, 3, 1, 1) and residual is None and h < 16 and w % 8 == 0 and 128 % (8 * h) == 0
                           and n % (128 // (8 * h)) == 0)   # 8x8 / 4x8 images: several per tile (tap-shifted boxes)
                 bn32 = TF32_BLOCK_N if (TF32_BLOCK_N and cv.K % (TF32_BLOCK_N & 0xffff) == 0) else 0
-                if chan_ok and (geo == (1, 1, 1, 0) or (geo == (3, 3, 1, 1) and h % 16 == 0 and w % 8 == 0) or small3):
+                if chan_ok and (geo == (1, 1, 1, 0) or small3 or (geo == (3, 3, 1, 1) and h >= 14 and w >= 8 and
+                                                                  (RAGGED_TMA or (h % 16 == 0 and w % 8 == 0)))):
                     C.vlnce_conv_tma(ptr(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift), ptr(residual), ptr(y), lib.F32,
                                      n, h, w, c, cv.K, cv.R, int(relu), bn32, st)
                     return
