@@ -387,3 +387,52 @@ def test_fused_wddppo_update_matches_oracle_loop():
     bad = [k for k, p in pol.named_parameters()
            if p.requires_grad and float((p.detach().cpu() - ref[k].detach()).abs().max()) > 1e-4]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_visual_cache_update_matches_recompute(precision):
+    """Frozen-trunk feature cache (``ActionDictRolloutStorage.enable_visual_cache``): the PPO update fed the features that
+    ``act`` / ``get_value`` exported for every stored step must equal the update that re-runs both ResNets on the stored
+    frames (what the reference does) — same losses, same parameters after the step."""
+    from oracle import waypoint as oracle_wp
+    from test_host_emulated import _fill_rollouts
+    from vlnce_b200.ppo_step import ActionDictRolloutStorage, WDDPPOStep
+    from vlnce_b200.waypoint_policy import VISUAL_CACHE_KEYS
+
+    case = cases.CASES["wp_eval"]
+    T, N = 2, 2
+    space = oracle_wp.storage_obs_space(length=12)
+    results = []
+    for cache in (False, True):
+        pol = cases.build_policy(vlnce_b200, case).to(DEV)
+        pol.net.precision = precision
+        cases.set_mode(pol, case)
+        st = ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2)
+        nv = _fill_rollouts(st, T, N)
+        st.to(DEV)
+        st.compute_returns(nv.to(DEV), True, 0.99, 0.95)
+        if cache:
+            st.enable_visual_cache(pol)
+            for s_ in range(T):   # what a collection loop does between act() and insert()
+                obs = {k: v[s_] for k, v in st.observations.items() if k not in VISUAL_CACHE_KEYS}
+                pol.get_value(obs, st.recurrent_hidden_states[s_], {k: v[s_] for k, v in st.prev_actions.items()},
+                              st.masks[s_])
+                st.step = s_
+                st.store_visual_features(pol.visual_features())
+            st.step = T
+            sample = next(iter(st.recurrent_generator(st.advantages[:T], 2, perm=torch.arange(N))))
+            assert VISUAL_CACHE_KEYS[0] in sample[0] and "rgb" not in sample[0] and "depth_history" not in sample[0]
+        agent = WDDPPOStep(pol, ppo_epoch=1, num_mini_batch=2, lr=2e-4, eps=1e-5, max_grad_norm=0.2)
+        torch.manual_seed(21)
+        c0 = lib.C.vlnce_launch_count()
+        losses = agent.update(st)
+        torch.cuda.synchronize()
+        results.append((losses, {k: p.detach().cpu().clone() for k, p in pol.named_parameters() if p.requires_grad},
+                        int(lib.C.vlnce_launch_count() - c0)))
+    (l0, p0, n0), (l1, p1, n1) = results
+    print(f"update[{precision}] recompute {l0} ({n0} launches) cached {l1} ({n1} launches)")
+    tol = 1e-6 if precision == "fp32" else 1e-4   # 16-bit trunks: tile choice may differ between batch sizes
+    torch.testing.assert_close(torch.tensor(l1), torch.tensor(l0), rtol=10 * tol, atol=tol)
+    worst = max(float((p1[k] - p0[k]).abs().max()) for k in p0)
+    assert worst <= 10 * tol, worst
+    assert n1 < n0

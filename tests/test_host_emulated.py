@@ -200,6 +200,38 @@ def test_fused_wddppo_update_matches_oracle_loop(name):
         if p.requires_grad:
             # Adam's first steps move every weight by ~lr regardless of the gradient's size: compare the UPDATE
             torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=4e-5, msg=lambda m: f"{k}: {m}")
+    if name != "wp_eval":
+        return
+    # the same update fed the frozen trunks' cached features instead of the stored frames (enable_visual_cache): what a
+    # collection loop stores between act() and insert() is reproduced here with get_value on every stored step
+    from vlnce_b200.waypoint_policy import VISUAL_CACHE_KEYS
+
+    pol2 = cases.build_policy(vlnce_b200, case)
+    cases.set_mode(pol2, case)
+    substitute_trunks(pol2, case)
+    st2 = ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=Lr, **cont)
+    nv3 = _fill_rollouts(st2, T, N, classes=classes, layers=Lr)
+    with lib.dry_run(executor=Emulator()) as rec:
+        st2.compute_returns(nv3, True, 0.99, 0.95)
+        st2.enable_visual_cache(pol2)
+        for s_ in range(T):
+            obs = {k: v[s_] for k, v in st2.observations.items() if k not in VISUAL_CACHE_KEYS}
+            pol2.get_value(obs, st2.recurrent_hidden_states[s_], {k: v[s_] for k, v in st2.prev_actions.items()},
+                           st2.masks[s_])
+            st2.step = s_
+            st2.store_visual_features(pol2.visual_features())
+        st2.step = T
+        pol2.net.rgb_encoder.features_into = pol2.net.depth_encoder.features_into = None   # the update must not need them
+        n_before = len(rec.calls)
+        agent2 = WDDPPOStep(pol2, ppo_epoch=1, num_mini_batch=2, lr=2e-4, eps=1e-5, max_grad_norm=0.2,
+                            use_clipped_value_loss=True, **kw)
+        torch.manual_seed(21)
+        got2 = agent2.update(st2)
+        assert "vlnce_wp_stack_frames" not in rec.calls[n_before:]
+    torch.testing.assert_close(torch.tensor(got2), torch.tensor(want), rtol=2e-4, atol=2e-6)
+    for k, p in pol2.named_parameters():
+        if p.requires_grad:
+            torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=4e-5, msg=lambda m: f"cached {k}: {m}")
 
 
 # ---------------------------------------------------------------------------------------------

@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--no-visual-cache", action="store_true",
+                    help="re-run both ResNets on the stored frames in the PPO update, as the reference does (default: the "
+                         "frozen trunks' features of every collected step are kept in the rollout storage)")
     args = ap.parse_args()
     import torch.distributed as dist
 
@@ -39,6 +42,7 @@ def main():
     from oracle import cases, waypoint as oracle_wp   # case table / observation-space description only (side tool)
     from vlnce_b200 import lib, synth
     from vlnce_b200.ppo_step import ActionDictRolloutStorage, WDDPPOStep, select_history_frames
+    from vlnce_b200.waypoint_policy import VISUAL_CACHE_KEYS
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -57,6 +61,8 @@ def main():
     space = oracle_wp.storage_obs_space(length=L)
     storage = ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2)
     storage.to(dev)
+    if not args.no_visual_cache:
+        storage.enable_visual_cache(pol)
     gen = torch.Generator().manual_seed(100 + rank)
     # a pool of pre-rendered observations (the simulator stub): new frames every step without host RNG in the loop
     pool = [{k: v.to(dev) for k, v in synth.make_waypoint_rows(gen, N, length=L).items()} for _ in range(6)]
@@ -67,14 +73,16 @@ def main():
     def collect():
         """One rollout: T act() steps + insert (``_collect_rollout_step``), then the bootstrap value + GAE."""
         pol.eval()
-        for k in storage.observations:
+        for k in pool[0]:
             storage.observations[k][0].copy_(pool[0][k])
         for t in range(T):
-            obs = {k: v[storage.step] for k, v in storage.observations.items()}
+            obs = {k: v[storage.step] for k, v in storage.observations.items() if k not in VISUAL_CACHE_KEYS}
             with torch.no_grad():
                 (value, actions, elems, _modes, _vars, logp, h, _dist) = pol.act(
                     obs, storage.recurrent_hidden_states[storage.step],
                     {k: v[storage.step] for k, v in storage.prev_actions.items()}, storage.masks[storage.step])
+            if storage.visual_cache:
+                storage.store_visual_features(pol.visual_features())
             nxt = dict(pool[(t + 1) % len(pool)])
             hist = select_history_frames(obs, elems["pano"], 12)      # frames the agent moved towards (:190-199)
             nxt["rgb_history"], nxt["depth_history"] = hist["rgb"].float(), hist["depth"]
@@ -82,7 +90,7 @@ def main():
             masks = (torch.rand(N, 1, device=dev) > 0.05).to(torch.uint8)
             storage.insert(nxt, h, elems, logp, value, rewards, masks)
         with torch.no_grad():
-            obs = {k: v[storage.step] for k, v in storage.observations.items()}
+            obs = {k: v[storage.step] for k, v in storage.observations.items() if k not in VISUAL_CACHE_KEYS}
             next_value = pol.get_value(obs, storage.recurrent_hidden_states[storage.step],
                                        {k: v[storage.step] for k, v in storage.prev_actions.items()},
                                        storage.masks[storage.step])
@@ -128,7 +136,7 @@ def main():
         line = {"metric": "env steps/sec (C4: DD-PPO waypoint trainer loop, 4 envs x 16 steps per rank, synthetic envs)",
                 "value": steps / (total.item() * 1e-3), "unit": "env steps/s", "n_gpus": world,
                 "collect_ms": ms_c / args.iters, "update_ms": ms_u / args.iters, "launches_collect": lc, "launches_update": lu,
-                "precision": args.precision, "losses_last_update": [float(x) for x in losses],
+                "precision": args.precision, "visual_cache": bool(storage.visual_cache), "losses_last_update": [float(x) for x in losses],
                 "config": {"envs_per_rank": N, "rollout_steps": T, "ppo_epoch": 2, "num_mini_batch": 4,
                            "frames_per_env_step": 13, "rgb": "12x224x224x3 f32", "depth": "12x256x256x1 f32", "L": L}}
         print(json.dumps(line), flush=True)

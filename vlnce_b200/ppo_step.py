@@ -49,6 +49,29 @@ class ActionDictRolloutStorage:
             self.prev_actions["offset"] = self.prev_actions["offset"].long()
         self.masks = torch.zeros(T + 1, N, 1, dtype=torch.uint8)
         self.num_steps, self.step = T, 0
+        self.visual_cache = False
+
+    RAW_FRAME_KEYS = ("rgb", "depth", "rgb_history", "depth_history")
+
+    def enable_visual_cache(self, policy):
+        """B200-first extension (not in the reference, whose update re-runs both ResNets on the stored frames,
+        ``ddppo_alg.py:56-75`` -> ``waypoint_policy.py:265-333``): keep the FROZEN trunks' features of every stored step
+        (``WaypointPolicy.visual_features()`` after ``act``) beside the observations; ``recurrent_generator`` then hands
+        the update those features instead of the raw frames and ``evaluate_actions`` skips the trunks.  Identical
+        results as long as the trunks are frozen and in eval mode — every waypoint recipe (``config/default.py:242,253``)."""
+        from .waypoint_policy import VISUAL_CACHE_KEYS
+
+        eng = policy.net.engine()
+        T1, N = self.masks.shape[0], self.masks.shape[1]
+        dev = self.masks.device
+        self.observations[VISUAL_CACHE_KEYS[0]] = torch.zeros(T1, N, eng.P + 1, eng.c_rgb, device=dev)
+        self.observations[VISUAL_CACHE_KEYS[1]] = torch.zeros(T1, N, eng.P + 1, eng.S, eng.c_dep, device=dev)
+        self.visual_cache = True
+
+    def store_visual_features(self, features: Dict[str, torch.Tensor]):
+        """features of the observations in the CURRENT slot (call between ``act`` and ``insert``)."""
+        for k, v in features.items():
+            self.observations[k][self.step].copy_(v)
 
     def to(self, device):
         for d in (self.observations, self.actions, self.prev_actions):
@@ -108,7 +131,8 @@ class ActionDictRolloutStorage:
                 y = x[:T].index_select(1, ind)
                 return y.reshape(T * y.shape[1], *y.shape[2:])
 
-            yield ({k: tm(v) for k, v in self.observations.items()},
+            skip = self.RAW_FRAME_KEYS if self.visual_cache else ()
+            yield ({k: tm(v) for k, v in self.observations.items() if k not in skip},
                    self.recurrent_hidden_states[0].index_select(0, ind),
                    {k: tm(v) for k, v in self.actions.items()},
                    {k: tm(v) for k, v in self.prev_actions.items()},

@@ -41,6 +41,10 @@ PANO_ATTN_KEY_DIM = 128
 ANGLE_FEATURE_SIZE = 4
 
 
+# observation keys of the frozen-trunk feature cache (WaypointEngine.export_visual_features / forward)
+VISUAL_CACHE_KEYS = ("pano_rgb_features", "pano_depth_features")
+
+
 def _host_floats(vals):
     """Small constant block handed to a kernel wrapper by HOST pointer (kept alive by the caller)."""
     return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
@@ -242,10 +246,31 @@ class WaypointEngine(HeadEngine):
             out.append(("wp_olog", "offset_linear", n.offset_linear, self.no))
         return out
 
+    def export_visual_features(self) -> Dict[str, torch.Tensor]:
+        """The frozen trunks' outputs of the LAST forward, per row: ``pano_rgb_features`` (B, P+1, c_rgb) — the RGB
+        trunk's pooled vector of the 12 pano frames and of the (mask-reset) history frame — and ``pano_depth_features``
+        (B, P+1, 16, c_dep).  Rows that carry these keys skip both ResNets in ``forward`` (strided copies, no arithmetic).
+        Call right after ``act`` / ``get_value``: the buffers are reused by the next forward."""
+        B, P, S = self._visual_rows, self.P, self.S
+        F = B * (P + 1)
+        rgb_e, dep_e = self.buf("wp_rgb_e", (F, S, self.Crgb)), self.buf("wp_dep_e", (F, S, self.Cdep))
+        fr = torch.empty(B, P + 1, self.c_rgb, device=rgb_e.device)
+        fd = torch.empty(B, P + 1, S, self.c_dep, device=rgb_e.device)
+        fr[:, :P].copy_(rgb_e[:B * P, 0, :self.c_rgb].reshape(B, P, self.c_rgb))
+        fr[:, P].copy_(rgb_e[B * P:, 0, :self.c_rgb])
+        fd[:, :P].copy_(dep_e[:B * P, :, :self.c_dep].reshape(B, P, S, self.c_dep))
+        fd[:, P].copy_(dep_e[B * P:, :, :self.c_dep])
+        return {VISUAL_CACHE_KEYS[0]: fr, VISUAL_CACHE_KEYS[1]: fd}
+
     # ------------------------------------------------------------------ forward
     def forward(self, observations, rnn_states, prev_actions: Dict[str, torch.Tensor], masks, save: bool, critic=None):
         net = self.net
-        for k in ("rgb", "depth", "rgb_history", "depth_history", "angle_features"):
+        # frozen-trunk feature cache (both conv trunks are frozen in every waypoint recipe, config/default.py:242,253):
+        # rows that carry the features a previous forward exported (export_visual_features, kept in the rollout storage
+        # by the trainer loop) skip frame stacking and both ResNets — the PPO update then re-reads 213 KB per env step
+        # instead of pushing 13 frames through two ResNet-50s again
+        cached = VISUAL_CACHE_KEYS[0] in observations and VISUAL_CACHE_KEYS[1] in observations
+        for k in (VISUAL_CACHE_KEYS if cached else ("rgb", "depth", "rgb_history", "depth_history")) + ("angle_features",):
             assert k in observations, k
             lib.require_cuda(observations[k], k)
         lib.require_cuda(rnn_states, "rnn_states")
@@ -254,8 +279,13 @@ class WaypointEngine(HeadEngine):
         st = lib.stream()
         H, P, S, hk = self.H, self.P, self.S, self.H // 2
         N = rnn_states.shape[0]
-        B = observations["rgb"].shape[0]
-        assert observations["rgb"].shape[1] == P and observations["depth"].shape[1] == P
+        B = observations["angle_features"].shape[0]
+        if cached:
+            assert tuple(observations[VISUAL_CACHE_KEYS[0]].shape) == (B, P + 1, self.c_rgb)
+            assert tuple(observations[VISUAL_CACHE_KEYS[1]].shape) == (B, P + 1, S, self.c_dep)
+        else:
+            assert observations["rgb"].shape[0] == B
+            assert observations["rgb"].shape[1] == P and observations["depth"].shape[1] == P
         assert B % N == 0, "rows must be T*N (time-major)"
         T = B // N
         F = B * (P + 1)
@@ -267,29 +297,43 @@ class WaypointEngine(HeadEngine):
             instr, _, lengths, L = self._encode_instruction(observations, B, save)
 
         # ---- 12 pano frames + masked history frame -> one trunk batch per modality (:327-366)
-        rgb, rgb_h = observations["rgb"], observations["rgb_history"]
-        if rgb.dtype != rgb_h.dtype or rgb.dtype not in (torch.uint8, torch.float32):
-            rgb, rgb_h = rgb.float(), rgb_h.float()
-        rgb, rgb_h = rgb.contiguous(), rgb_h.contiguous()
-        dep = observations["depth"].contiguous().float()
-        dep_h = observations["depth_history"].contiguous().float()
-        fr_rgb = self.buf("wp_frames_rgb", (F,) + tuple(rgb.shape[2:]), rgb.dtype)
-        fr_dep = self.buf("wp_frames_dep", (F,) + tuple(dep.shape[2:]), torch.float32)
-        C.vlnce_wp_stack_frames(ptr(rgb), ptr(rgb_h), ptr(masks_f), ptr(fr_rgb), B, P,
-                                rgb[0, 0].numel() * rgb.element_size(), st)
-        C.vlnce_wp_stack_frames(ptr(dep), ptr(dep_h), ptr(masks_f), ptr(fr_dep), B, P, dep[0, 0].numel() * 4, st)
         rgb_e = self.buf("wp_rgb_e", (F, S, self.Crgb))
         dep_e = self.buf("wp_dep_e", (F, S, self.Cdep))
-        with Branch("depth") as br_depth:
-            net.depth_encoder.features_into({"depth": fr_dep}, dep_e, self.Cdep, self.precision)
+        self._visual_rows = B
+        if cached:
+            # frame order of the trunk batch: [B*P pano frames (row-major) | B history frames]; strided copies only
+            fr = observations[VISUAL_CACHE_KEYS[0]].float()
+            fd = observations[VISUAL_CACHE_KEYS[1]].float()
+            rgb_e[:B * P, 0, :self.c_rgb].copy_(fr[:, :P].reshape(B * P, self.c_rgb))
+            rgb_e[B * P:, 0, :self.c_rgb].copy_(fr[:, P])
+            dep_e[:B * P, :, :self.c_dep].copy_(fd[:, :P].reshape(B * P, S, self.c_dep))
+            dep_e[B * P:, :, :self.c_dep].copy_(fd[:, P])
             C.vlnce_spatial_embed_fill(ptr(net.depth_encoder.spatial_embeddings.weight), ptr(dep_e), S * self.Cdep,
-                                       self.Cdep, self.c_dep, F, S, 64, lib.stream())
-        # W3: the trunk's global pool lands in position 0 of every frame, then is shown at all 16 positions
-        net.rgb_encoder.features_into({"rgb": fr_rgb}, rgb_e, S * self.Crgb, self.precision)
+                                       self.Cdep, self.c_dep, F, S, 64, st)
+            br_depth = None
+        else:
+            rgb, rgb_h = observations["rgb"], observations["rgb_history"]
+            if rgb.dtype != rgb_h.dtype or rgb.dtype not in (torch.uint8, torch.float32):
+                rgb, rgb_h = rgb.float(), rgb_h.float()
+            rgb, rgb_h = rgb.contiguous(), rgb_h.contiguous()
+            dep = observations["depth"].contiguous().float()
+            dep_h = observations["depth_history"].contiguous().float()
+            fr_rgb = self.buf("wp_frames_rgb", (F,) + tuple(rgb.shape[2:]), rgb.dtype)
+            fr_dep = self.buf("wp_frames_dep", (F,) + tuple(dep.shape[2:]), torch.float32)
+            C.vlnce_wp_stack_frames(ptr(rgb), ptr(rgb_h), ptr(masks_f), ptr(fr_rgb), B, P,
+                                    rgb[0, 0].numel() * rgb.element_size(), st)
+            C.vlnce_wp_stack_frames(ptr(dep), ptr(dep_h), ptr(masks_f), ptr(fr_dep), B, P, dep[0, 0].numel() * 4, st)
+            with Branch("depth") as br_depth:
+                net.depth_encoder.features_into({"depth": fr_dep}, dep_e, self.Cdep, self.precision)
+                C.vlnce_spatial_embed_fill(ptr(net.depth_encoder.spatial_embeddings.weight), ptr(dep_e), S * self.Cdep,
+                                           self.Cdep, self.c_dep, F, S, 64, lib.stream())
+            # W3: the trunk's global pool lands in position 0 of every frame, then is shown at all 16 positions
+            net.rgb_encoder.features_into({"rgb": fr_rgb}, rgb_e, S * self.Crgb, self.precision)
         C.vlnce_broadcast_positions(ptr(rgb_e), S * self.Crgb, self.Crgb, F, S, self.c_rgb, st)
         C.vlnce_spatial_embed_fill(ptr(net.rgb_encoder.spatial_embeddings.weight), ptr(rgb_e), S * self.Crgb,
                                    self.Crgb, self.c_rgb, F, S, 64, st)
-        br_depth.join()
+        if br_depth is not None:
+            br_depth.join()
         cfg = net.model_config  # modality ablations (waypoint_predictors.py:400-407): embeddings AND history * 0
         if cfg.get("ablate_rgb", False):
             rgb_e.zero_()
@@ -740,6 +784,12 @@ class WaypointPolicy(Policy):
             modes = {"offset": cls(col(5), eng.no), "distance": cls(col(6), eng.nd)}
             dist = CustomFixedCategorical(logits=out["logp"].clone())
             return (out["values"].clone(), actions, action_elements, modes, variances, col(2), out["h_out"].clone(), dist)
+
+    def visual_features(self) -> Dict[str, torch.Tensor]:
+        """Frozen-trunk features of the rows of the last ``act`` / ``get_value`` call (see
+        ``WaypointEngine.export_visual_features``); a trainer loop stores them beside the observations so that
+        ``evaluate_actions`` in the PPO update does not run the ResNets a second time."""
+        return self.net.engine().export_visual_features()
 
     @lib.guarded
     def get_value(self, observations, rnn_states, prev_actions, masks):  # :249-263
