@@ -401,6 +401,34 @@ def test_recollect_style_loop_matches_oracle():
             torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=1e-4, msg=lambda m: f"{k}: {m}")
 
 
+def test_padded_rows_bypass_the_trunks_without_changing_the_update():
+    """``ILTrainerStep.skip_padded_rows``: rows of a ragged teacher-forcing batch whose loss weight is 0 (padding after
+    the end of a trajectory) skip the frozen eval-mode conv trunks — same losses, same gradients as computing them."""
+    from vlnce_b200.il_step import ILTrainerStep
+
+    case = cases.CASES["cma_train_pixels"]                  # t = 3, n = 2, raw 256x256 frames
+    obs, prev, masks, actions, weights = cases.inputs(case)
+    weights = weights.clone()
+    weights[2, 1] = 0.0                                      # trajectory 1 ended after two steps
+    weights[1:, 0] = 0.0                                     # trajectory 0 after one
+    res = []
+    for skip in (False, True):
+        pol = cases.build_policy(vlnce_b200, case).eval()
+        pol.net.precision = "fp32"
+        vlnce_b200.AuxLosses.activate()
+        step = ILTrainerStep(pol, lr=2.5e-4)
+        step.skip_padded_rows = skip
+        with lib.dry_run(executor=Emulator()) as rec:
+            step.compute_grads(obs, prev, masks, actions, weights)
+        vlnce_b200.AuxLosses.deactivate()
+        res.append((step._losses.clone(), step.fp.grad.clone(), rec.calls.count("vlnce_conv2d_ref")))
+    (l0, g0, n0), (l1, g1, n1) = res
+    assert n0 == n1                                          # same layers ... on half the images
+    torch.testing.assert_close(l1, l0, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(g1, g0, rtol=1e-5, atol=1e-8)
+    assert float(g0.abs().max()) > 0
+
+
 def test_ddppo_collect_and_update_loop_matches_oracle():
     """BASELINE config C4 shape family at reduced size: the DD-PPO waypoint loop of
     ``ddppo_waypoint_trainer.py:140-300,470-560`` with a synthetic environment — ``act`` (deterministic, so both

@@ -71,7 +71,7 @@ def run_effective_batch(step, transforms, trajs, micro, coef=3.2):
     return losses, (valid, padded)
 
 
-def parity(dev):
+def parity(dev, skip=True):
     """The same loop at 4 trajectories x T in [3, 6], micro-batch 2, fp32 trunks, against the CPU oracle."""
     import vlnce_b200
     from oracle import cases, obs_transforms as oracle_ot, vlnce as oracle_vlnce
@@ -84,6 +84,7 @@ def parity(dev):
     pol.net.precision = "fp32"
     vlnce_b200.AuxLosses.activate()
     step = ILTrainerStep(pol, lr=2.5e-4)
+    step.skip_padded_rows = skip
     tf = [ot.ResizeShortestEdge(256), ot.CenterCropperPerSensor([("rgb", (224, 224)), ("depth", (256, 256))])]
     got, _ = run_effective_batch(step, tf, trajs, 2)
     got = torch.stack(got).cpu()
@@ -122,6 +123,9 @@ def main():
     ap.add_argument("--tmax", type=int, default=90)
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--parity", action="store_true")
+    ap.add_argument("--no-skip-padded", action="store_true",
+                    help="push the padded rows of every micro-batch through the conv trunks too, as the reference does "
+                         "(default: rows with loss weight 0 bypass the frozen eval-mode trunks, ILTrainerStep.skip_padded_rows)")
     args = ap.parse_args()
     import vlnce_b200
     from vlnce_b200 import lib, obs_transforms as ot, synth
@@ -129,10 +133,11 @@ def main():
 
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    par = parity(dev) if args.parity else None
+    par = parity(dev, skip=not args.no_skip_padded) if args.parity else None
     pol = synth.build_cma_policy(wseed=13, hw=256, rgb_hw=224).to(dev).eval()
     vlnce_b200.AuxLosses.activate()
     step = ILTrainerStep(pol, lr=2.5e-4)
+    step.skip_padded_rows = not args.no_skip_padded
     tf = [ot.ResizeShortestEdge(256), ot.CenterCropperPerSensor([("rgb", (224, 224)), ("depth", (256, 256))])]
     trajs = make_trajectories(args.trajectories, args.tmin, args.tmax, dev, seed=9)
     hbm_gb = sum(v.numel() * v.element_size() for o, _, _ in trajs for v in o.values()) / 1e9
@@ -158,7 +163,8 @@ def main():
             "config": {"trajectories": args.trajectories, "T": [args.tmin, args.tmax], "micro_batch": args.micro_batch,
                        "loss_accumulation_scalar": (args.trajectories + args.micro_batch - 1) // args.micro_batch,
                        "raw_frames": "480x640 rgb u8 + depth f32", "transforms": "ResizeShortestEdge(256) + CenterCrop rgb 224 / depth 256",
-                       "precision": "rgb trunk bf16 / depth trunk fp16 tcgen05, head fp32"}}
+                       "precision": "rgb trunk bf16 / depth trunk fp16 tcgen05, head fp32",
+                       "padded_rows_skip_the_trunks": bool(step.skip_padded_rows)}}
     if par is not None:
         line["parity"] = par
     print(json.dumps(line), flush=True)

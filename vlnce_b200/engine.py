@@ -437,10 +437,45 @@ class CMAEngine(HeadEngine):
         for batch i+1 while the head of batch i trains (``ILTrainerStep.pipelined_step``)."""
         net = self.net
         self.ensure_pool(rgb_e.device)
+        idx = getattr(self, "valid_rows", None)
+        if idx is not None and self._can_skip_rows(observations):
+            # teacher-forcing batches are padded to the longest trajectory (dagger_trainer.py:39-114): rows with weight
+            # 0 reach no loss term and no valid row's recurrent state (they follow their trajectory's last real step),
+            # so the frozen eval-mode trunks only see the real rows; the padded rows' features stay zero
+            sub = dict(observations, rgb=observations["rgb"].index_select(0, idx),
+                       depth=observations["depth"].index_select(0, idx))
+            n = idx.numel()
+            rc, dc = self.buf("rgb_emb_valid", (n, self.P, self.Crgb)), self.buf("depth_emb_valid", (n, self.P, self.Cdep))
+            with Branch("depth") as br_depth:
+                net.depth_encoder.features_into(sub, dc, self.Cdep, self.precision, save=False)
+            net.rgb_encoder.features_into(sub, rc, self.Crgb, self.precision, save=False)
+            br_depth.join()
+            rgb_e.zero_()
+            dep_e.zero_()
+            rgb_e.index_copy_(0, idx, rc)
+            dep_e.index_copy_(0, idx, dc)
+            return
         with Branch("depth") as br_depth:
             net.depth_encoder.features_into(observations, dep_e, self.Cdep, self.precision, save=save)
         net.rgb_encoder.features_into(observations, rgb_e, self.Crgb, self.precision, save=save)
         br_depth.join()
+
+    def _can_skip_rows(self, observations) -> bool:
+        """padded rows may bypass the trunks only if no image's features depend on another image (eval-mode BatchNorm;
+        GroupNorm is per image), the trunks are frozen, raw frames are the input and nobody hooks the trunk outputs."""
+        net = self.net
+        rgb_enc, dep_enc = net.rgb_encoder, net.depth_encoder
+        if "rgb" not in observations or "depth" not in observations:
+            return False
+        if getattr(rgb_enc, "trainable", False) or getattr(dep_enc, "trainable", False):
+            return False
+        cnn = getattr(rgb_enc, "cnn", None)
+        if cnn is None or getattr(cnn, "training", True):
+            return False
+        for m in (cnn, getattr(dep_enc, "visual_encoder", None)):
+            if m is not None and len(getattr(m, "_forward_hooks", {})) > 0:
+                return False
+        return True
 
     def forward(self, observations, rnn_states, prev_actions, masks, save: bool, visual=None):
         net = self.net

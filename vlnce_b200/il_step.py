@@ -74,6 +74,9 @@ class ILTrainerStep:
         self._step_dev = None
         self._accum = None
         self._pending = 0
+        # opt-in: rows whose loss weight is 0 (the padding of a ragged teacher-forcing batch) bypass the frozen
+        # eval-mode conv trunks (engine.encode_visual); costs one host read of the valid-row count per update
+        self.skip_padded_rows = False
 
     def _prepare(self):
         if self.fp is None or not self.fp.aliased():
@@ -159,7 +162,15 @@ class ILTrainerStep:
         AuxLosses.clear()
         R = T * N
         visual = eng.visual_buffers(R, visual_slot) if visual_slot is not None else None
-        x, _, hat = eng.forward(observations, h0, prev_actions, not_done_masks, save=True, visual=visual)
+        eng.valid_rows = None
+        if self.skip_padded_rows and visual is None and not (weights.is_cuda and torch.cuda.is_current_stream_capturing()):
+            idx = (weights.reshape(-1) > 0).nonzero().reshape(-1)       # (T, N) time-major == the row order
+            if 0 < idx.numel() < R:
+                eng.valid_rows = idx
+        try:
+            x, _, hat = eng.forward(observations, h0, prev_actions, not_done_masks, save=True, visual=visual)
+        finally:
+            eng.valid_rows = None
         head = pol.action_distribution.linear
         A = head.weight.shape[0]
         logp = eng.action_logits(head, x, R)
