@@ -436,3 +436,45 @@ def test_visual_cache_update_matches_recompute(precision):
     worst = max(float((p1[k] - p0[k]).abs().max()) for k in p0)
     assert worst <= 10 * tol, worst
     assert n1 < n0
+
+
+def test_graphed_act_matches_eager_act():
+    """``WaypointPolicy.graph_act``: the forward of ``act`` replayed from a CUDA graph (static input copies) returns what
+    the eager launches return — first call (eager pass + capture), a replay with different inputs, a replay after an
+    eager call in between."""
+    from vlnce_b200 import synth
+
+    case = dict(cases.CASES["wp_act"], n=3)
+    pol = cases.build_policy(vlnce_b200, case).to(DEV)
+    pol.net.precision = "bf16"
+    cases.set_mode(pol, case)
+    g = torch.Generator().manual_seed(4)
+    batches = [{k: v.to(DEV) for k, v in synth.make_waypoint_rows(g, 3, length=case["length"]).items()} for _ in range(3)]
+    h = (torch.randn(3, 2, 256, generator=g) * 0.3).to(DEV)
+    prev = {k: v.to(DEV) for k, v in synth.make_waypoint_actions(g, 3).items()}
+    masks = torch.tensor([[1], [0], [1]], dtype=torch.uint8, device=DEV)
+
+    def run(obs):
+        v, _env, elems, modes, var, lp, h_out, dist = pol.act(obs, h, prev, masks, deterministic=True)
+        feats = pol.visual_features()
+        return [v, elems["pano"], elems["offset"], elems["distance"], lp, h_out, dist.logits, feats["pano_rgb_features"],
+                feats["pano_depth_features"]]
+
+    pol.graph_act = False
+    want = [run(b) for b in batches]
+    pol.graph_act = True
+    c0 = lib.C.vlnce_launch_count()
+    got0 = run(batches[0])          # eager pass + capture
+    c1 = lib.C.vlnce_launch_count()
+    got1 = run(batches[1])          # replay
+    c2 = lib.C.vlnce_launch_count()
+    pol.graph_act = False
+    run(batches[2])
+    pol.get_value({k: v[:2] for k, v in batches[0].items()}, h[:2], {k: v[:2] for k, v in prev.items()}, masks[:2])
+    pol.graph_act = True
+    got2 = run(batches[2])          # replay after eager calls (one with another row count) reused the same workspaces
+    torch.cuda.synchronize()
+    assert c2 - c1 <= 3 < c1 - c0   # a replay launches only the sampling kernel through the C ABI
+    for got, ref in ((got0, want[0]), (got1, want[1]), (got2, want[2])):
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--no-graph-act", action="store_true", help="launch the forward of every act() eagerly")
     ap.add_argument("--no-visual-cache", action="store_true",
                     help="re-run both ResNets on the stored frames in the PPO update, as the reference does (default: the "
                          "frozen trunks' features of every collected step are kept in the rollout storage)")
@@ -57,6 +58,7 @@ def main():
     pol = cases.build_policy(vlnce_b200, case).to(dev)
     pol.net.precision = args.precision
     cases.set_mode(pol, case)
+    pol.graph_act = not args.no_graph_act
     agent = WDDPPOStep(pol)
     space = oracle_wp.storage_obs_space(length=L)
     storage = ActionDictRolloutStorage(T, N, space, 256, num_recurrent_layers=2)
@@ -136,7 +138,7 @@ def main():
         line = {"metric": "env steps/sec (C4: DD-PPO waypoint trainer loop, 4 envs x 16 steps per rank, synthetic envs)",
                 "value": steps / (total.item() * 1e-3), "unit": "env steps/s", "n_gpus": world,
                 "collect_ms": ms_c / args.iters, "update_ms": ms_u / args.iters, "launches_collect": lc, "launches_update": lu,
-                "precision": args.precision, "visual_cache": bool(storage.visual_cache), "losses_last_update": [float(x) for x in losses],
+                "precision": args.precision, "visual_cache": bool(storage.visual_cache), "graph_act": bool(pol.graph_act), "losses_last_update": [float(x) for x in losses],
                 "config": {"envs_per_rank": N, "rollout_steps": T, "ppo_epoch": 2, "num_mini_batch": 4,
                            "frames_per_env_step": 13, "rgb": "12x224x224x3 f32", "depth": "12x256x256x1 f32", "L": L}}
         print(json.dumps(line), flush=True)

@@ -755,11 +755,50 @@ class WaypointPolicy(Policy):
         return cls(observation_space=observation_space, action_space=action_space, model_config=config.MODEL)
 
     # ------------------------------------------------------------------ act (waypoint_policy.py:129-247)
+    # opt-in: replay the forward of ``act`` (stacking, both trunks, head: ~100 launches) from a CUDA graph keyed by the
+    # input signature — the rollout collection calls ``act`` once per environment step with fixed shapes, and at 4 envs
+    # per rank the eager launches cost as much host time as the kernels take.  The sampling kernel and the D2H read of
+    # the env actions stay outside the graph (their RNG counter is a launch argument).
+    graph_act = False
+
+    def _forward_for_act(self, eng, observations, rnn_states, prev_actions, masks):
+        if not (self.graph_act and rnn_states.is_cuda) or torch.cuda.is_current_stream_capturing():
+            return eng.forward(observations, rnn_states, prev_actions, masks, save=False, critic=self.critic)
+        parts = (observations, rnn_states, prev_actions, masks)
+        flat = []
+        for part in parts:
+            flat.extend(part[k] for k in sorted(part)) if isinstance(part, dict) else flat.append(part)
+        key = tuple((tuple(t.shape), t.dtype) for t in flat) + (id(eng),)
+        graphs = self.__dict__.setdefault("_act_graphs", {})
+        entry = graphs.get(key)
+        if entry is None:
+            static = tuple({k: v.clone() for k, v in part.items()} if isinstance(part, dict) else part.clone()
+                           for part in parts)
+            eng.forward(*static, save=False, critic=self.critic)      # eager pass: plans, tile selection, workspaces
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    out = eng.forward(*static, save=False, critic=self.critic)
+            torch.cuda.current_stream().wait_stream(side)
+            sflat = []
+            for part in static:
+                sflat.extend(part[k] for k in sorted(part)) if isinstance(part, dict) else sflat.append(part)
+            entry = graphs[key] = (sflat, graph, out)
+        sflat, graph, out = entry
+        for dst, src in zip(sflat, flat):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        eng._visual_rows = out["B"]     # (python-side state of forward() that a replay does not re-run)
+        return out
+
     @lib.guarded
     def act(self, observations, rnn_states, prev_actions, masks, deterministic=False):
         with torch.no_grad():
             eng = self.net.engine()
-            out = eng.forward(observations, rnn_states, prev_actions, masks, save=False, critic=self.critic)
+            out = self._forward_for_act(eng, observations, rnn_states, prev_actions, masks)
             B, P = out["B"], eng.P
             dev = rnn_states.device
             pano_stop = torch.empty(B, 1, dtype=torch.int64, device=dev)
