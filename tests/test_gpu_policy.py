@@ -9,6 +9,7 @@ import torch
 
 import vlnce_b200
 from oracle import cases, vlnce as oracle_vlnce
+from vlnce_b200 import lib
 
 pytestmark = pytest.mark.gpu
 warnings.filterwarnings("ignore")
@@ -110,3 +111,35 @@ def test_no_cpu_fallback():
     obs, h, prev, masks = cases.inputs(case)
     with pytest.raises(vlnce_b200.lib.VlnceError, match="CUDA only"):
         pol.act(obs, h, prev, masks, deterministic=True)
+
+
+@pytest.mark.parametrize("name", ["cma_act", "seq2seq_act"])
+def test_graphed_act_matches_eager_act(name):
+    """``ILPolicy.graph_act``: the forward of ``act`` replayed from a CUDA graph returns exactly what the eager launches
+    return (first call = eager pass + capture, then replays with other inputs of the same signature, then a second
+    signature)."""
+    from vlnce_b200 import synth
+
+    case = dict(cases.CASES[name], n=4)
+    pol = cuda_policy(case, "bf16")
+    layers = cases.layers_of(case)
+    sets = []
+    for i in range(3):
+        obs, h, prev, masks = synth.make_act_batch(700 + i, 4, hw=256, length=80, layers=layers)
+        sets.append(({k: v.to(DEV) for k, v in obs.items()}, h.to(DEV), prev.to(DEV), masks.to(DEV)))
+    with torch.no_grad():
+        want = [pol.act(*s, deterministic=True) for s in sets]
+        small = tuple({k: v[:2] for k, v in p.items()} if isinstance(p, dict) else p[:2] for p in sets[0])
+        want_small = pol.act(*small, deterministic=True)
+        pol.graph_act = True
+        c0 = lib.C.vlnce_launch_count()
+        got = [pol.act(*s, deterministic=True) for s in sets]
+        c1 = lib.C.vlnce_launch_count()
+        got_small = pol.act(*small, deterministic=True)          # another signature: its own graph
+        again = pol.act(*sets[1], deterministic=True)
+        c2 = lib.C.vlnce_launch_count()
+    torch.cuda.synchronize()
+    for (a, h1), (b, h2) in zip(got + [got_small, again], want + [want_small, want[1]]):
+        assert torch.equal(a, b) and torch.equal(h1, h2)
+    assert len(pol._act_graphs) == 2
+    print(f"{name}: launches through the C ABI: capture + 2 replays {c1 - c0}, new signature + 1 replay {c2 - c1}")

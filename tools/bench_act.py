@@ -60,6 +60,23 @@ def main():
         ms = a.elapsed_time(b) / args.iters
         out[label] = {"ms_per_call": ms, "policy_steps_per_s": n / (ms * 1e-3),
                       "launches_per_call": (lib.C.vlnce_launch_count() - c0) // args.iters}
+        # the same calls with the forward replayed from a CUDA graph (ILPolicy.graph_act)
+        pol.graph_act = True
+        ref = act(0)
+        for i in range(3):
+            act(i)
+        torch.cuda.synchronize()
+        a.record()
+        for i in range(args.iters):
+            act(i)
+        b.record()
+        torch.cuda.synchronize()
+        msg = a.elapsed_time(b) / args.iters
+        pol.graph_act = False
+        eager = act(0)
+        torch.cuda.synchronize()
+        out[label].update({"graph_ms_per_call": msg, "graph_policy_steps_per_s": n / (msg * 1e-3),
+                           "graph_equals_eager": bool(torch.equal(ref[0], eager[0]) and torch.equal(ref[1], eager[1]))})
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "bench_act.json"), "w"), indent=1)

@@ -33,13 +33,50 @@ class ILPolicy(Policy):
     def forward(self, *x):
         raise NotImplementedError
 
+    # opt-in: replay the forward of ``act`` (both trunks + head, ~150 launches) from a CUDA graph keyed by the input
+    # signature (an evaluation / rollout loop calls ``act`` with fixed shapes; at most ``GRAPH_ACT_MAX`` signatures are
+    # kept, e.g. for the shrinking batch of an evaluation run).  Sampling stays outside the graph.
+    graph_act = False
+    GRAPH_ACT_MAX = 8
+
+    def _logits_and_states(self, observations, rnn_states, prev_actions, masks):
+        from .aux_losses import AuxLosses
+
+        head = self.action_distribution.linear
+        if (not self.graph_act or not rnn_states.is_cuda or torch.cuda.is_current_stream_capturing()
+                or AuxLosses.is_active()):
+            return self.net.logits_and_states(head, observations, rnn_states, prev_actions, masks)
+        flat = [observations[k] for k in sorted(observations)] + [rnn_states, prev_actions, masks]
+        key = tuple((tuple(t.shape), t.dtype) for t in flat) + tuple(sorted(observations))
+        graphs = self.__dict__.setdefault("_act_graphs", {})
+        entry = graphs.get(key)
+        if entry is None:
+            if len(graphs) >= self.GRAPH_ACT_MAX:
+                graphs.pop(next(iter(graphs)))
+            s_obs = {k: v.clone() for k, v in observations.items()}
+            s_rest = [rnn_states.clone(), prev_actions.clone(), masks.clone()]
+            self.net.logits_and_states(head, s_obs, *s_rest)     # eager pass: plans, tile selection, workspaces
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    out = self.net.logits_and_states(head, s_obs, *s_rest)
+            torch.cuda.current_stream().wait_stream(side)
+            entry = graphs[key] = ([s_obs[k] for k in sorted(s_obs)] + s_rest, graph, out)
+        static, graph, out = entry
+        for dst, src in zip(static, flat):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return out[0].clone(), out[1].clone()
+
     # ---- reference surface ---------------------------------------------------------------
     @lib.guarded
     def act(self, observations, rnn_states, prev_actions, masks, deterministic=False):
         """``policy.py:26-44``: features -> Categorical -> mode() / sample()."""
         with torch.no_grad():
-            logits, rnn_states_out = self.net.logits_and_states(
-                self.action_distribution.linear, observations, rnn_states, prev_actions, masks)
+            logits, rnn_states_out = self._logits_and_states(observations, rnn_states, prev_actions, masks)
             R, A = logits.shape
             if deterministic:  # CustomFixedCategorical.mode(): probs.argmax(-1, keepdim=True)
                 action = torch.empty(R, 1, dtype=torch.int64, device=logits.device)
