@@ -143,3 +143,14 @@ def test_graphed_act_matches_eager_act(name):
         assert torch.equal(a, b) and torch.equal(h1, h2)
     assert len(pol._act_graphs) == 2
     print(f"{name}: launches through the C ABI: capture + 2 replays {c1 - c0}, new signature + 1 replay {c2 - c1}")
+    # new weights (load_state_dict bumps the parameter versions: the trunks repack into new buffers): the cached graphs
+    # must not be replayed against the old operands
+    sd = {k: (v * 1.05 if v.is_floating_point() and v.dim() >= 2 else v) for k, v in pol.state_dict().items()}
+    pol.load_state_dict(sd)
+    with torch.no_grad():
+        fresh = pol.act(*sets[0], deterministic=True)             # graph_act is still on
+        assert len(pol._act_graphs) == 1
+        pol.graph_act = False
+        eager = pol.act(*sets[0], deterministic=True)
+    assert torch.equal(fresh[0], eager[0]) and torch.equal(fresh[1], eager[1])
+    assert not torch.equal(fresh[1], want[0][1])

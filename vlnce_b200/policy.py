@@ -23,6 +23,37 @@ class CategoricalNet(nn.Module):
         nn.init.constant_(self.linear.bias, 0)
 
 
+def act_graph_fingerprint(policy) -> tuple:
+    """Everything a captured ``act`` forward bakes in besides the input signature: the precision mode, the BatchNorm mode
+    of the trunks (it selects the trunk variant), the versions of the conv weights the packed trunk operands were built
+    from (``load_state_dict`` bumps them -> the trunks repack into new buffers) and the addresses of the parameters
+    the head kernels read in place (``.to()`` / ``.float()`` re-create them).  A changed fingerprint drops the graphs."""
+    net = policy.net
+    fp = [getattr(net, "precision", None)]
+    for enc, mod in (("rgb_encoder", "cnn"), ("depth_encoder", "visual_encoder")):
+        m = getattr(getattr(net, enc, None), mod, None)
+        if m is None:
+            continue
+        fp.append(bool(m.training))
+        for tr in list(getattr(m, "_trunks", {}).values()):
+            fp.append(tuple(cv.conv.weight._version for cv in tr._all()))
+    first = next(iter(policy.parameters()), None)
+    last = None
+    for last in policy.parameters():
+        pass
+    fp.append((first.data_ptr() if first is not None else 0, last.data_ptr() if last is not None else 0))
+    return tuple(fp)
+
+
+def act_graph_cache(policy) -> dict:
+    """The policy's {input signature: (static inputs, graph, outputs)} cache, emptied when the fingerprint moved."""
+    fp = act_graph_fingerprint(policy)
+    if policy.__dict__.get("_act_graph_fp") != fp:
+        policy.__dict__["_act_graphs"] = {}
+        policy.__dict__["_act_graph_fp"] = fp
+    return policy.__dict__["_act_graphs"]
+
+
 class ILPolicy(Policy):
     def __init__(self, net, dim_actions):
         nn.Module.__init__(self)
@@ -48,7 +79,7 @@ class ILPolicy(Policy):
             return self.net.logits_and_states(head, observations, rnn_states, prev_actions, masks)
         flat = [observations[k] for k in sorted(observations)] + [rnn_states, prev_actions, masks]
         key = tuple((tuple(t.shape), t.dtype) for t in flat) + tuple(sorted(observations))
-        graphs = self.__dict__.setdefault("_act_graphs", {})
+        graphs = act_graph_cache(self)
         entry = graphs.get(key)
         if entry is None:
             if len(graphs) >= self.GRAPH_ACT_MAX:
@@ -65,6 +96,7 @@ class ILPolicy(Policy):
                     out = self.net.logits_and_states(head, s_obs, *s_rest)
             torch.cuda.current_stream().wait_stream(side)
             entry = graphs[key] = ([s_obs[k] for k in sorted(s_obs)] + s_rest, graph, out)
+            self.__dict__["_act_graph_fp"] = act_graph_fingerprint(self)   # (the eager pass may have built the trunks)
         static, graph, out = entry
         for dst, src in zip(static, flat):
             dst.copy_(src, non_blocking=True)

@@ -769,9 +769,13 @@ class WaypointPolicy(Policy):
         for part in parts:
             flat.extend(part[k] for k in sorted(part)) if isinstance(part, dict) else flat.append(part)
         key = tuple((tuple(t.shape), t.dtype) for t in flat) + (id(eng),)
-        graphs = self.__dict__.setdefault("_act_graphs", {})
+        from .policy import act_graph_cache, act_graph_fingerprint
+
+        graphs = act_graph_cache(self)
         entry = graphs.get(key)
         if entry is None:
+            if len(graphs) >= 8:
+                graphs.pop(next(iter(graphs)))
             static = tuple({k: v.clone() for k, v in part.items()} if isinstance(part, dict) else part.clone()
                            for part in parts)
             eng.forward(*static, save=False, critic=self.critic)      # eager pass: plans, tile selection, workspaces
@@ -787,6 +791,7 @@ class WaypointPolicy(Policy):
             for part in static:
                 sflat.extend(part[k] for k in sorted(part)) if isinstance(part, dict) else sflat.append(part)
             entry = graphs[key] = (sflat, graph, out)
+            self.__dict__["_act_graph_fp"] = act_graph_fingerprint(self)   # (the eager pass may have built the trunks)
         sflat, graph, out = entry
         for dst, src in zip(sflat, flat):
             dst.copy_(src, non_blocking=True)
