@@ -495,7 +495,8 @@ def main():
     # Every step's inputs travel pinned-host -> device INSIDE the timed region (one H2D per step)
     # and the step's losses travel back (D2H + host read).  Like a DataLoader prefetcher, the copy
     # of batch i+1 runs on a copy stream while batch i computes.
-    host_loss = torch.empty(3).pin_memory()
+    host_loss = [torch.empty(3).pin_memory() for _ in range(2)]
+    ev_loss = [torch.cuda.Event(), torch.cuda.Event()]
     stage_buf = {k: torch.empty_like(v) for k, v in {**static, **static_next}.items()}
     copy_stream = torch.cuda.Stream()
     ev_ready, ev_free = torch.cuda.Event(), torch.cuda.Event()
@@ -520,9 +521,16 @@ def main():
             if i + 1 < nsteps:
                 prefetch(i + 1)
             run_step()
-            host_loss.copy_(losses, non_blocking=True)   # D2H of the step result
-            main.synchronize()
-            last = host_loss.tolist()
+            # D2H of THIS step's losses into a pinned slot; the host reads the PREVIOUS step's slot (its copy finished
+            # while this step was being enqueued), so every step's result is read inside the timed region without
+            # draining the queue after each step — what a trainer that logs its loss one step late does
+            host_loss[i & 1].copy_(losses, non_blocking=True)
+            ev_loss[i & 1].record(main)
+            if i > 0:
+                ev_loss[(i - 1) & 1].synchronize()
+                last = host_loss[(i - 1) & 1].tolist()
+        ev_loss[(nsteps - 1) & 1].synchronize()
+        last = host_loss[(nsteps - 1) & 1].tolist()
         return last
 
     e2e_loop(args.warmup)
@@ -673,7 +681,9 @@ def main():
                        "schedule": "pipelined loop: frozen trunks of batch i+1 overlap head fwd/bwd/Adam of batch i "
                                    "(every timed step = one trunk pass + one head update; fill done in warm-up)"},
             "e2e": {"value": e2e_value, "unit": "policy steps/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps, "last_losses": last},
+                    "d2h_bytes_per_step": 12, "ms_per_step": e2e_ms / args.steps, "last_losses": last,
+                    "d2h_read": "every step's 3 losses are copied to pinned memory and read by the host inside the timed "
+                                "region; the read of step i happens while step i+1 runs (one step of lag)"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": summarize_clocks(samples),
         }

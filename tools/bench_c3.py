@@ -63,6 +63,10 @@ def run_effective_batch(step, transforms, trajs, micro, coef=3.2):
         weights = collate.inflection_weights(actions, coef, lengths)
         obs = apply_obs_transforms_batch(obs, transforms)
         last = i + micro >= len(trajs)
+        if step.skip_padded_rows:   # real rows from the lengths the collate step knows (no device read)
+            tmax, n = int(lengths.max()), len(part)
+            real = torch.arange(tmax).view(tmax, 1) < lengths.view(1, n)
+            step.valid_rows_hint = real.reshape(-1).nonzero().reshape(-1).pin_memory()
         out = step.update_agent(obs, prev, masks, actions, weights, step_grad=last, loss_accumulation_scalar=scalar,
                                 return_tensor=True)
         losses.append(out.clone())

@@ -77,6 +77,9 @@ class ILTrainerStep:
         # opt-in: rows whose loss weight is 0 (the padding of a ragged teacher-forcing batch) bypass the frozen
         # eval-mode conv trunks (engine.encode_visual); costs one host read of the valid-row count per update
         self.skip_padded_rows = False
+        # optional: the indices of the real rows of the NEXT update (int64, time-major row = t * N + n), e.g. built on
+        # the host from the trajectory lengths the collate step already knows — saves the host read above
+        self.valid_rows_hint = None
 
     def _prepare(self):
         if self.fp is None or not self.fp.aliased():
@@ -164,9 +167,12 @@ class ILTrainerStep:
         visual = eng.visual_buffers(R, visual_slot) if visual_slot is not None else None
         eng.valid_rows = None
         if self.skip_padded_rows and visual is None and not (weights.is_cuda and torch.cuda.is_current_stream_capturing()):
-            idx = (weights.reshape(-1) > 0).nonzero().reshape(-1)       # (T, N) time-major == the row order
+            idx = self.valid_rows_hint
+            self.valid_rows_hint = None
+            if idx is None:
+                idx = (weights.reshape(-1) > 0).nonzero().reshape(-1)   # (T, N) time-major == the row order
             if 0 < idx.numel() < R:
-                eng.valid_rows = idx
+                eng.valid_rows = idx.to(weights.device, non_blocking=True)
         try:
             x, _, hat = eng.forward(observations, h0, prev_actions, not_done_masks, save=True, visual=visual)
         finally:

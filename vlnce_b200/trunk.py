@@ -412,8 +412,8 @@ class ConvTrunk:
                         C.vlnce_conv_s2_tma(ptr(x), ptr(cv.w), lib.F32, ptr(scale), ptr(shift), ptr(y), lib.F32, n, h, w, c,
                                             cv.K, cv.R, int(relu), bn32, st)
                         return
-                if c % 32 == 0 and not _os.environ.get("VLNCE_NO_WARP"):   # what the tiles do not cover (4x4 images, odd sizes): fp32 on CUDA cores, one warp per
-                    # 8 pixels x 4 filters with the lanes across the input channels
+                if c % 32 == 0:   # what the tiles do not cover (4x4 images, odd sizes): fp32 on CUDA cores, one warp
+                    # per 8 pixels x 4 filters with the lanes across the input channels
                     C.vlnce_conv2d_warp(ptr(x), ptr(cv.w), ptr(scale), ptr(shift), ptr(residual), ptr(y), n, h, w, c,
                                         cv.K, cv.R, cv.S, cv.stride, cv.pad, int(relu), st)
                     return
