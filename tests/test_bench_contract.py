@@ -46,3 +46,21 @@ def test_clock_parser_and_host_cores():
     assert c["sm_max_mhz"] == 1965.0 and c["sm_mhz"] == 1957.5 and c["reasons"] == ["sw_power_cap"]
     assert bench.summarize_clocks([]) == {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
     assert 1 <= bench.host_cores() <= (os.cpu_count() or 1)
+
+
+def test_side_workloads_keep_the_row_count_and_the_layout():
+    """``--workload c2t8`` (8 trajectories x 8 steps) and ``c5`` (RxR): rows per GPU, the time-major (T, N) layout of the
+    generated batch and the checker's case description stay consistent."""
+    bench = load_bench()
+    bench.select_workload("c2t8")
+    assert bench.ROWS_PER_GPU == 64 and bench.T_STEPS == 8 and "T=8 N=8/GPU" in bench.WORKLOAD
+    case = bench.oracle_case()
+    assert case["t"] == 8 and case["n"] == 8
+    bench.HW = 32                                      # tiny frames: only the layout is checked here
+    obs, prev, masks, actions, weights = bench.make_batch(3, 64)
+    assert actions.shape == (8, 8) and weights.shape == (8, 8) and prev.shape == (64, 1) and obs["rgb"].shape[0] == 64
+    assert int(masks.view(8, 8)[0].sum()) == 0 and int(masks.view(8, 8)[1:].min()) == 1     # hidden reset at t = 0 only
+    bench.select_workload("c5")
+    assert bench.ROWS_PER_GPU == 32 and bench.T_STEPS == 1 and bench.RXR_DIM == 768 and bench.instr_key() == "rxr_instruction"
+    bench.select_workload("c2")
+    assert bench.T_STEPS == 1 and bench.ROWS_PER_GPU == 64
