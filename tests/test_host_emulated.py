@@ -401,6 +401,27 @@ def test_recollect_style_loop_matches_oracle():
             torch.testing.assert_close(p.detach(), ref[k].detach(), rtol=0, atol=1e-4, msg=lambda m: f"{k}: {m}")
 
 
+def test_update_agent_from_host_equals_update_agent():
+    """``ILTrainerStep.update_agent_from_host`` stages the batch into persistent buffers on the policy's device and runs
+    the same fused step (here both live on the host model's memory)."""
+    from vlnce_b200.il_step import ILTrainerStep
+
+    case = cases.CASES["cma_train_features"]
+    batch = cases.inputs(case)
+    res = []
+    for from_host in (False, True):
+        pol = cases.build_policy(vlnce_b200, case).eval()
+        vlnce_b200.AuxLosses.activate()
+        step = ILTrainerStep(pol, lr=2.5e-4)
+        with lib.dry_run(executor=Emulator()):
+            fn = step.update_agent_from_host if from_host else step.update_agent
+            out = [fn(*batch) for _ in range(2)]           # second call re-uses the staging buffers
+        vlnce_b200.AuxLosses.deactivate()
+        res.append((out, step.fp.flat.clone()))
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
+    assert len(step._host_stage) == len(batch[0]) + 4
+
+
 def test_padded_rows_bypass_the_trunks_without_changing_the_update():
     """``ILTrainerStep.skip_padded_rows``: rows of a ragged teacher-forcing batch whose loss weight is 0 (padding after
     the end of a trajectory) skip the frozen eval-mode conv trunks — same losses, same gradients as computing them."""

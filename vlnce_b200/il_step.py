@@ -104,6 +104,26 @@ class ILTrainerStep:
         loss, action_loss, aux_loss = self._losses.tolist()  # one D2H read (the reference does three .item())
         return loss, action_loss, aux_loss
 
+    @lib.guarded
+    def update_agent_from_host(self, observations, prev_actions, not_done_masks, corrected_actions, weights, **kw):
+        """``update_agent`` for a batch that still lives in host memory (what a DataLoader hands the reference's
+        ``_update_agent`` before its ``.to(device)`` calls, ``dagger_trainer.py:560-583``): every tensor travels to the
+        policy's device with ONE non-blocking copy into a persistent staging buffer (pinned sources overlap with the
+        kernels already queued), then the fused step runs on the staged batch.  Same return value as ``update_agent``."""
+        dev = next(self.policy.parameters()).device
+        stage = self.__dict__.setdefault("_host_stage", {})
+
+        def put(name, t):
+            buf = stage.get(name)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype or buf.device != dev:
+                buf = stage[name] = torch.empty(t.shape, dtype=t.dtype, device=dev)
+            buf.copy_(t, non_blocking=True)
+            return buf
+
+        obs = {k: put("obs/" + k, v) for k, v in observations.items()}
+        return self.update_agent(obs, put("prev_actions", prev_actions), put("not_done_masks", not_done_masks),
+                                 put("corrected_actions", corrected_actions), put("weights", weights), **kw)
+
     # The two phases are separately CUDA-graph capturable; the NCCL all-reduce sits between them.
     # ---- pipelined training loop: the frozen trunks of batch i+1 run concurrently with the head
     # forward/backward/Adam of batch i (they depend on no trainable parameter); bit-identical results
