@@ -199,3 +199,28 @@ def test_pipelined_loop_equals_plain_loop():
     tol = 1e-5 + 1e-4 * st_a.fp.flat.abs()
     assert (diff > tol).float().mean().item() < 1e-4, (diff > tol).sum().item()
     assert diff.max().item() <= 2.0 * lr * steps + 1e-6, diff.max().item()
+
+
+def test_update_agent_from_host_equals_device_batch():
+    """``ILTrainerStep.update_agent_from_host``: a pinned host batch staged with non-blocking copies gives the losses (of two consecutive updates) of the same batch already resident on the device."""
+    from vlnce_b200.il_step import ILTrainerStep
+
+    case = cases.CASES["cma_train_features"]
+    batch = cases.inputs(case)
+    res = []
+    for from_host in (False, True):
+        pol = cases.build_policy(vlnce_b200, case).to(DEV).eval()
+        vlnce_b200.AuxLosses.activate()
+        step = ILTrainerStep(pol, lr=2.5e-4)
+        if from_host:
+            pinned = tuple({k: v.pin_memory() for k, v in p.items()} if isinstance(p, dict) else p.pin_memory() for p in batch)
+            out = [step.update_agent_from_host(*pinned) for _ in range(2)]
+        else:
+            dev = tuple({k: v.to(DEV) for k, v in p.items()} if isinstance(p, dict) else p.to(DEV) for p in batch)
+            out = [step.update_agent(*dev) for _ in range(2)]
+        vlnce_b200.AuxLosses.deactivate()
+        torch.cuda.synchronize()
+        res.append(out)
+    # (parameters are not compared bit for bit: the embedding gradient accumulates with float atomics, and Adam turns a
+    # last-bit difference of a near-zero gradient into a +-lr step; the second step's losses see the first step's update)
+    torch.testing.assert_close(torch.tensor(res[1]), torch.tensor(res[0]), rtol=1e-5, atol=1e-6)
